@@ -1,0 +1,24 @@
+"""CPU oracle for the VHAP photometric inner loop  --  TEST INFRASTRUCTURE ONLY.
+
+This package is a float64-capable PyTorch / numpy restatement of the reference's hot path
+(SURVEY.md section 8a).  It exists so that tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline leg have something to check the CUDA engine against.  Nothing under
+`vhap_b200/` imports it and the product path never routes through it.
+
+Pinning status
+  * FLAME / LBS / landmarks / camera (oracle/lbs.py, oracle/camera.py): PINNED.  Checked against
+    outputs of the reference's own `vhap/model/lbs.py` and `vhap/util/mesh.py`, imported unmodified
+    in the authoring container; vectors in tests/golden/lbs_golden.npz, generator
+    tests/golden/make_golden.py.
+  * rasterise / interpolate / texture / antialias (oracle/raster.py, oracle/render.py):
+    PARITY UNPINNED.  The arithmetic lives in the third-party dependency `nvdiffrast`
+    (ShenhanQian/nvdiffrast@backface-culling, pinned by branch name only at
+    /root/reference/pyproject.toml:30) whose source is absent from /root/reference and which
+    cannot be installed here (no network, no GPU).  The reference has no tests or golden vectors
+    for this path.  These modules restate nvdiffrast's *published* algorithm
+    (Laine et al. 2020, "Modular Primitives for High-Performance Differentiable Rendering") at the
+    reference's call sites (vhap/util/render_nvdiffrast.py:254,384,389,399,465); the exact
+    fixed-point snapping / fill rule / depth tie-break are this repo's own specification
+    (DESIGN.md "Rasteriser specification") and triangle-id bit-exactness is claimed against
+    this oracle only.
+"""
