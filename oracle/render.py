@@ -258,16 +258,17 @@ def disturb(rgba, rgba_bg, cid, num_clusters, w_fg, w_bg, u_rand):
 
 def render_rgba(rast, rast_db, verts, verts_clip, faces, verts_uv, faces_uv, tex, lights, background,
                 adj_opp, fid2cid_padded=None, align_texture_except_fid=None, align_boundary_except_vid=None,
-                disturbance=None):
+                disturbance=None, v_normal=None):
     """NVDiffRenderer.render_rgba (render_nvdiffrast.py:354-484), lighting_type='SH', lighting_space='world'.
     tex [3,T,T] (single shared texture; the reference expands it to B copies, tracker.py:234), verts_uv already has
     v flipped by the caller (tracker.py:315-316).  background: [B,H,W,3] image tensor (image orientation) or list.
     disturbance: None or dict(w_fg, w_bg, u_rand).  Returns dict of [B,H,W,C] tensors, flipped to image orientation."""
     B, H, W, _ = rast.shape
-    dt = verts.dtype
+    dt = rast.dtype
     ids = rast[..., 3].long()
     fg = ids > 0
-    v_normal = compute_v_normals(verts, faces)
+    if v_normal is None:                                     # (override only used by unit tests of the pixel math)
+        v_normal = compute_v_normals(verts, faces)
     normal, _ = interpolate(v_normal, rast, faces)
     normal = safe_normalize(normal)
     texc, texd = interpolate(verts_uv[None], rast, faces_uv, rast_db)
