@@ -97,6 +97,8 @@ typedef struct vhap_stage_cfg {
   float   bg_color[3];
   float   disturb_rate_fg, disturb_rate_bg;   /* <0 = None (render_nvdiffrast.py:428-435) */
   uint64_t rng_seed; uint64_t rng_step;        /* Philox counter base for the in-kernel disturbance */
+  float   shared_scale;         /* 1/world_size: batch-independent terms (shape/light/offset/texture regularisers) are scaled by this
+                                   on every rank so that the data-parallel sum-allreduce reproduces them exactly once */
 } vhap_stage_cfg;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------- */
@@ -110,10 +112,10 @@ int  vhap_abi_version(void);
  * and vertices whose clip position is detached inside antialias (align_boundary_except_vid, :349-352,:463-464);
  * per-vertex weights of reg_offset / reg_offset_lap (tracker.py:564-587, :607-614) and rigid-region ids (:589-594);
  * uv mask of reg_tex_res_clusters (tracker.py:536-539).  HOST pointers, copied. */
-int vhap_set_stage_masks(vhap_ctx* ctx, const uint8_t* face_tex_detach_host, const uint8_t* vert_aa_detach_host,
-                         const float* w_offset_host, const float* w_offset_lap_host,
-                         const int32_t* rigid_region_of_vertex_host, int32_t n_rigid_regions,
-                         const uint8_t* uvmask_res_host);
+int vhap_set_stage_masks(vhap_ctx* ctx, const uint8_t* face_tex_detach_host /*[F]*/, const uint8_t* vert_aa_detach_host /*[V]*/,
+                         const float* w_offset_host /*[V]*/, const float* w_offset_lap_host /*[V]*/,
+                         const int32_t* rigid_indptr_host /*[n_rigid+1]*/, const int32_t* rigid_vids_host, int32_t n_rigid_regions,
+                         const uint8_t* uvmask_res_host /*[T,T] 0/1*/);
 
 /* ---- FLAME (replaces FlameHead.forward, vhap/model/flame.py:571-646 + vhap/model/lbs.py) ------------------ */
 int vhap_flame_forward(vhap_ctx* ctx, const vhap_params* p, const vhap_frame_batch* fb,
@@ -146,11 +148,14 @@ int vhap_energy_forward_backward(vhap_ctx* ctx, const vhap_params* p, const vhap
 int vhap_energy_forward(vhap_ctx* ctx, const vhap_params* p, const vhap_frame_batch* fb, const vhap_stage_cfg* cfg,
                         float* reduce_slab /* device float[8] */, void* stream);
 int vhap_energy_backward(vhap_ctx* ctx, const vhap_params* p, const vhap_frame_batch* fb, const vhap_stage_cfg* cfg,
-                         const float* reduce_slab, int32_t global_B, const vhap_grads* g, float* losses_out, void* stream);
+                         const float* reduce_slab /* cross-rank reduced */, const float* local_slab /* this rank's own */,
+                         int32_t global_B, const vhap_grads* g, float* losses_out, void* stream);
 
 /* debug / logging planes of the last forward (render_out dict, render_nvdiffrast.py:476-483), image orientation.
  * which: 0 rgba (after AA), 1 rgba before AA, 2 albedo, 3 normal, 4 diffuse, 5 cid.  out [B,H,W,4] float. */
 int vhap_get_plane(vhap_ctx* ctx, int32_t which, float* out, void* stream);
+int vhap_set_want_planes(vhap_ctx* ctx, int32_t on);   /* make the next forward keep the logging planes */
+int vhap_overflow_flag(vhap_ctx* ctx, int32_t* out_host);   /* 1 if a raster tile list overflowed its capacity (synchronises) */
 /* test hook: inject the disturbance randomness (w bits: bit0 = w_fg, bit1 = w_bg; u in [0,1)); NULL = Philox. */
 int vhap_set_injected_random(vhap_ctx* ctx, const uint8_t* w_bits /*[B,H,W]*/, const float* u /*[B,H,W]*/);
 

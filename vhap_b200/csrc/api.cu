@@ -1,0 +1,415 @@
+// C-ABI entry points of libvhap_b200.so (include/vhap_b200.h) and context management.
+#include <stdlib.h>
+#include <vector>
+#include "engine.h"
+#include "accum.h"
+
+void launch_forward_slab(vhap_ctx* c, const PassArgs& P, const float* lights, float* slab, cudaStream_t s);
+void launch_finalize(vhap_ctx* c, const PassArgs& P, const vhap_stage_cfg* cfg, const float* slab_global, const float* slab_local, int global_B,
+                     const float* lights, float* g_lights, cudaStream_t s);
+void launch_flip_plane(const float* in, float* out, int B, int H, int W, cudaStream_t s);
+void launch_cid_plane(vhap_ctx* c, float* out, cudaStream_t s);
+
+static char g_err[512] = "";
+
+void vh_set_error(vhap_ctx* ctx, const char* what, const char* msg) {
+  char* dst = ctx ? ctx->err : g_err;
+  snprintf(dst, 512, "%s: %s", what, msg);
+}
+
+#define CK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { vh_set_error(ctx, #expr, cudaGetErrorString(_e)); return -2; } } while (0)
+
+template <typename T>
+static int upload(vhap_ctx* ctx, T** dst, const T* src, size_t n) {
+  CK(cudaMalloc((void**)dst, n * sizeof(T)));
+  if (src) CK(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  else CK(cudaMemset(*dst, 0, n * sizeof(T)));
+  return 0;
+}
+#define UP(dst, src, n) do { if (upload(ctx, &(dst), (src), (n))) return -2; } while (0)
+
+extern "C" int vhap_abi_version(void) { return 1; }
+
+extern "C" const char* vhap_last_error(const vhap_ctx* ctx) { return ctx ? ctx->err : g_err; }
+
+extern "C" int vhap_ctx_create(vhap_ctx** out, const vhap_mesh_desc* m, int32_t tex_size, int32_t device) {
+  vhap_ctx* ctx = (vhap_ctx*)calloc(1, sizeof(vhap_ctx));
+  if (!ctx) return -1;
+  *out = ctx;
+  ctx->device = device;
+  CK(cudaSetDevice(device));
+  int V = m->V, F = m->F, K = m->K;
+  ctx->V = V; ctx->F = F; ctx->VT = m->VT; ctx->K = K; ctx->n_shape = m->n_shape; ctx->n_expr = K - m->n_shape; ctx->n_lmk = m->n_lmk;
+  ctx->n_clusters = m->n_clusters; ctx->T = tex_size;
+  if (K > 512) { vh_set_error(ctx, "vhap_ctx_create", "K > 512 unsupported"); return -3; }
+  if (tex_size & (tex_size - 1)) { vh_set_error(ctx, "vhap_ctx_create", "texture size must be a power of two"); return -3; }
+  size_t M = (size_t)3 * V;
+  UP(ctx->v_template, m->v_template_host, M);
+  UP(ctx->S_bwd, m->shapedirs_host, M * K);                    // [3V][K] as given
+  {
+    std::vector<float> st(M * K);
+    for (size_t r = 0; r < M; ++r) for (int k = 0; k < K; ++k) st[(size_t)k * M + r] = m->shapedirs_host[r * K + k];
+    UP(ctx->S_fwd, st.data(), M * K);                          // [K][3V]
+    // JS[k][j*3+c] = sum_v Jreg[j][v] S[v][c][k] ; Jt = Jreg template
+    std::vector<float> js((size_t)K * 15, 0.f), jt(15, 0.f);
+    for (int j = 0; j < 5; ++j)
+      for (int v = 0; v < V; ++v) {
+        float w = m->J_regressor_host[(size_t)j * V + v];
+        if (w == 0.f) continue;
+        for (int c = 0; c < 3; ++c) {
+          jt[j * 3 + c] += w * m->v_template_host[(size_t)v * 3 + c];
+          const float* row = m->shapedirs_host + ((size_t)v * 3 + c) * K;
+          for (int k = 0; k < K; ++k) js[(size_t)k * 15 + j * 3 + c] += w * row[k];
+        }
+      }
+    UP(ctx->JS, js.data(), (size_t)K * 15);
+    UP(ctx->Jt, jt.data(), (size_t)15);
+  }
+  UP(ctx->posedirs, m->posedirs_host, (size_t)36 * M);
+  UP(ctx->Jreg, m->J_regressor_host, (size_t)5 * V);
+  UP(ctx->lbs_w, m->lbs_weights_host, (size_t)V * 5);
+  {
+    std::vector<i4> f4v(F), fu(F);
+    std::vector<int> adj((size_t)F * 4);
+    for (int i = 0; i < F; ++i) {
+      f4v[i] = {m->faces_host[i * 3], m->faces_host[i * 3 + 1], m->faces_host[i * 3 + 2], 0};
+      fu[i] = {m->faces_uv_host[i * 3], m->faces_uv_host[i * 3 + 1], m->faces_uv_host[i * 3 + 2], 0};
+      for (int k = 0; k < 3; ++k) adj[(size_t)i * 4 + k] = m->adj_opp_host[i * 3 + k];
+      adj[(size_t)i * 4 + 3] = 0;
+    }
+    UP(ctx->faces, f4v.data(), (size_t)F);
+    UP(ctx->faces_uv, fu.data(), (size_t)F);
+    UP(ctx->adj_opp, adj.data(), (size_t)F * 4);
+  }
+  UP(ctx->verts_uv, m->verts_uv_host, (size_t)m->VT * 2);
+  UP(ctx->lmk_faces, m->lmk_faces_host, (size_t)m->n_lmk);
+  UP(ctx->lmk_bary, m->lmk_bary_host, (size_t)m->n_lmk * 3);
+  UP(ctx->fid2cid, m->fid2cid_host, (size_t)F + 1);
+  UP(ctx->vf_indptr, m->vf_indptr_host, (size_t)V + 1);
+  UP(ctx->vf_faces, m->vf_faces_host, (size_t)3 * F);
+  ctx->lap_nnz = m->lap_indptr_host[V];
+  UP(ctx->lap_indptr, m->lap_indptr_host, (size_t)V + 1);
+  UP(ctx->lap_idx, m->lap_indices_host, (size_t)ctx->lap_nnz);
+  UP(ctx->lap_val, m->lap_values_host, (size_t)ctx->lap_nnz);
+  UP(ctx->lap_y, (const float*)nullptr, M);
+  UP(ctx->face_flags, (const uint8_t*)nullptr, (size_t)F);
+  UP(ctx->vert_flags, (const uint8_t*)nullptr, (size_t)V);
+  // texture pyramid
+  int T = tex_size, l = 0; size_t off = 0;
+  for (int s = T; s >= 1; s >>= 1, ++l) { ctx->mip_off[l] = (int)off; off += (size_t)s * s; }
+  ctx->max_level = l - 1; ctx->mip_total = off;
+  UP(ctx->mips[0], (const f4*)nullptr, off);
+  UP(ctx->mips[1], (const f4*)nullptr, off);
+  UP(ctx->g_tex, (const float*)nullptr, off * 4);
+  ctx->tv_nblocks = (int)(((size_t)T * T + 255) / 256);
+  UP(ctx->tv_partials, (const float*)nullptr, (size_t)ctx->tv_nblocks * 2);
+  UP(ctx->scal, (const float*)nullptr, (size_t)16);
+  UP(ctx->acc, (const float*)nullptr, (size_t)ACC_COUNT);
+  UP(ctx->maxslot, (const unsigned long long*)nullptr, (size_t)1);
+  UP(ctx->overflow_flag, (const int*)nullptr, (size_t)1);
+  UP(ctx->pool_base, (const int*)nullptr, (size_t)16);
+  UP(ctx->pool_count, (const int*)nullptr, (size_t)16);
+  return 0;
+}
+
+#define FREE(p) do { if (p) { cudaFree(p); p = nullptr; } } while (0)
+
+static void free_batch(vhap_ctx* c) {
+  FREE(c->v_shaped); FREE(c->v_posed); FREE(c->g_vshaped); FREE(c->verts); FREE(c->clip); FREE(c->vnorm); FREE(c->vnraw); FREE(c->snap);
+  FREE(c->g_clip); FREE(c->g_vnorm); FREE(c->g_verts); FREE(c->posebuf); FREE(c->poses); FREE(c->gA); FREE(c->gpf); FREE(c->gJ); FREE(c->gbetas);
+  FREE(c->betas); FREE(c->cam); FREE(c->tri_id); FREE(c->pre); FREE(c->signs); FREE(c->pool_list); FREE(c->final_rgba); FREE(c->plane_albedo);
+  FREE(c->plane_normal); FREE(c->plane_diffuse); FREE(c->tile_count); FREE(c->tile_off); FREE(c->tile_cursor); FREE(c->tile_list);
+  FREE(c->pool_blk_count); FREE(c->pool_blk_off); FREE(c->partials);
+}
+
+extern "C" int vhap_ctx_reserve(vhap_ctx* ctx, int32_t B, int32_t H, int32_t W) {
+  if (B <= ctx->maxB && H <= ctx->maxH && W <= ctx->maxW && (size_t)B * H * W <= (size_t)ctx->maxB * ctx->maxH * ctx->maxW) return 0;
+  CK(cudaSetDevice(ctx->device));
+  free_batch(ctx);
+  size_t V = ctx->V, M = 3 * V, n = (size_t)B * H * W;
+  UP(ctx->v_shaped, (const float*)nullptr, B * M); UP(ctx->v_posed, (const float*)nullptr, B * M); UP(ctx->g_vshaped, (const float*)nullptr, B * M);
+  UP(ctx->verts, (const f4*)nullptr, B * V); UP(ctx->clip, (const f4*)nullptr, B * V); UP(ctx->vnorm, (const f4*)nullptr, B * V);
+  UP(ctx->vnraw, (const f4*)nullptr, B * V); UP(ctx->snap, (const i4*)nullptr, B * V);
+  UP(ctx->g_clip, (const float*)nullptr, B * V * 4); UP(ctx->g_vnorm, (const float*)nullptr, B * V * 4); UP(ctx->g_verts, (const float*)nullptr, B * V * 4);
+  UP(ctx->posebuf, (const PoseFwd*)nullptr, (size_t)B); UP(ctx->poses, (const float*)nullptr, (size_t)B * 15);
+  UP(ctx->gA, (const float*)nullptr, (size_t)B * 60); UP(ctx->gpf, (const float*)nullptr, (size_t)B * 36); UP(ctx->gJ, (const float*)nullptr, (size_t)B * 15);
+  UP(ctx->gbetas, (const float*)nullptr, (size_t)B * ctx->K); UP(ctx->betas, (const float*)nullptr, (size_t)B * ctx->K);
+  UP(ctx->cam, (const CamParams*)nullptr, (size_t)B);
+  UP(ctx->tri_id, (const int*)nullptr, n); UP(ctx->pre, (const f4*)nullptr, n); UP(ctx->signs, (const uint8_t*)nullptr, n);
+  UP(ctx->pool_list, (const int*)nullptr, n);
+  UP(ctx->final_rgba, (const float*)nullptr, n * 4); UP(ctx->plane_albedo, (const f4*)nullptr, n); UP(ctx->plane_normal, (const f4*)nullptr, n);
+  UP(ctx->plane_diffuse, (const f4*)nullptr, n);
+  int tiles = B * ((H + VH_TILE - 1) / VH_TILE) * ((W + VH_TILE - 1) / VH_TILE);
+  UP(ctx->tile_count, (const int*)nullptr, (size_t)tiles); UP(ctx->tile_off, (const int*)nullptr, (size_t)tiles); UP(ctx->tile_cursor, (const int*)nullptr, (size_t)tiles);
+  ctx->tile_cap = (int)std::min<size_t>((size_t)B * ctx->F * 16, (size_t)1 << 30);
+  UP(ctx->tile_list, (const int*)nullptr, (size_t)ctx->tile_cap);
+  int nblk = (int)((n + 255) / 256);
+  ctx->pool_nblk = nblk;
+  UP(ctx->pool_blk_count, (const int*)nullptr, (size_t)16 * nblk); UP(ctx->pool_blk_off, (const int*)nullptr, (size_t)16 * nblk);
+  ctx->n_partials_rows = nblk;
+  UP(ctx->partials, (const float*)nullptr, (size_t)nblk * VH_NPART);
+  ctx->maxB = B; ctx->maxH = H; ctx->maxW = W;
+  return 0;
+}
+
+extern "C" void vhap_ctx_destroy(vhap_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  free_batch(c);
+  FREE(c->v_template); FREE(c->S_fwd); FREE(c->S_bwd); FREE(c->posedirs); FREE(c->Jreg); FREE(c->lbs_w); FREE(c->JS); FREE(c->Jt);
+  FREE(c->faces); FREE(c->faces_uv); FREE(c->verts_uv); FREE(c->lmk_faces); FREE(c->lmk_bary); FREE(c->adj_opp); FREE(c->fid2cid);
+  FREE(c->vf_indptr); FREE(c->vf_faces); FREE(c->lap_indptr); FREE(c->lap_idx); FREE(c->lap_val); FREE(c->lap_y);
+  FREE(c->face_flags); FREE(c->vert_flags); FREE(c->w_off); FREE(c->w_off_lap); FREE(c->rigid_indptr); FREE(c->rigid_vids); FREE(c->uvmask_res);
+  FREE(c->mips[0]); FREE(c->mips[1]); FREE(c->tex_painted); FREE(c->g_tex); FREE(c->tv_partials); FREE(c->scal); FREE(c->acc); FREE(c->maxslot);
+  FREE(c->overflow_flag); FREE(c->pool_base); FREE(c->pool_count);
+  free(c);
+}
+
+extern "C" int vhap_set_stage_masks(vhap_ctx* ctx, const uint8_t* face_tex_detach, const uint8_t* vert_aa_detach, const float* w_off,
+                                    const float* w_off_lap, const int32_t* rigid_indptr, const int32_t* rigid_vids, int32_t n_rigid,
+                                    const uint8_t* uvmask_res) {
+  CK(cudaSetDevice(ctx->device));
+  if (face_tex_detach) CK(cudaMemcpy(ctx->face_flags, face_tex_detach, ctx->F, cudaMemcpyHostToDevice)); else CK(cudaMemset(ctx->face_flags, 0, ctx->F));
+  if (vert_aa_detach) CK(cudaMemcpy(ctx->vert_flags, vert_aa_detach, ctx->V, cudaMemcpyHostToDevice)); else CK(cudaMemset(ctx->vert_flags, 0, ctx->V));
+  FREE(ctx->w_off); FREE(ctx->w_off_lap); FREE(ctx->rigid_indptr); FREE(ctx->rigid_vids);
+  if (w_off) UP(ctx->w_off, w_off, (size_t)ctx->V);
+  if (w_off_lap) UP(ctx->w_off_lap, w_off_lap, (size_t)ctx->V);
+  ctx->n_rigid = 0;
+  if (rigid_indptr && n_rigid > 0) {
+    UP(ctx->rigid_indptr, rigid_indptr, (size_t)n_rigid + 1);
+    UP(ctx->rigid_vids, rigid_vids, (size_t)rigid_indptr[n_rigid]);
+    ctx->n_rigid = n_rigid;
+  }
+  if (uvmask_res) { FREE(ctx->uvmask_res); UP(ctx->uvmask_res, uvmask_res, (size_t)ctx->T * ctx->T); }
+  return 0;
+}
+
+extern "C" int vhap_set_injected_random(vhap_ctx* ctx, const uint8_t* w_bits, const float* u) { ctx->inj_w = w_bits; ctx->inj_u = u; return 0; }
+extern "C" int vhap_set_want_planes(vhap_ctx* ctx, int32_t on) { ctx->want_planes = on; return 0; }
+extern "C" float* vhap_tex_grad_ptr(vhap_ctx* ctx) { return ctx->g_tex; }
+
+static int check_batch(vhap_ctx* ctx, const vhap_frame_batch* fb) {
+  if (fb->B > ctx->maxB || (size_t)fb->B * fb->H * fb->W > (size_t)ctx->maxB * ctx->maxH * ctx->maxW || fb->H > ctx->maxH || fb->W > ctx->maxW) {
+    vh_set_error(ctx, "batch", "exceeds vhap_ctx_reserve() shape");
+    return -4;
+  }
+  ctx->curB = fb->B; ctx->curH = fb->H; ctx->curW = fb->W;
+  return 0;
+}
+#define LAST() do { cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) { vh_set_error(ctx, "kernel launch", cudaGetErrorString(_e)); return -5; } } while (0)
+
+__global__ void k_copy_verts(const f4* __restrict__ v4, float* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  f4 v = v4[i]; out[i * 3] = v.x; out[i * 3 + 1] = v.y; out[i * 3 + 2] = v.z;
+}
+__global__ void k_load_gverts(const float* __restrict__ g3, float* __restrict__ g4, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  g4[i * 4] = g3[i * 3]; g4[i * 4 + 1] = g3[i * 3 + 1]; g4[i * 4 + 2] = g3[i * 3 + 2]; g4[i * 4 + 3] = 0.f;
+}
+__global__ void k_project_only(const float* __restrict__ verts, const CamParams* __restrict__ cam, int V, int H, int W, float* __restrict__ clip) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (v >= V) return;
+  const float* p = verts + ((size_t)b * V + v) * 3;
+  CamParams c = cam[b];
+  float x = p[0], y = p[1], z = p[2];
+  float cx_ = c.RT[0] * x + c.RT[1] * y + c.RT[2] * z + c.RT[3];
+  float cy_ = c.RT[4] * x + c.RT[5] * y + c.RT[6] * z + c.RT[7];
+  float cz_ = c.RT[8] * x + c.RT[9] * y + c.RT[10] * z + c.RT[11];
+  float p00 = c.fx * 2.f / W, p11 = c.fy * 2.f / H, p02 = (W - 2.f * c.cx) / W, p12 = (H - 2.f * c.cy) / H;
+  float p22 = -(10.f + 0.1f) / (10.f - 0.1f), p23 = -2.f * 10.f * 0.1f / (10.f - 0.1f);
+  float* o = clip + ((size_t)b * V + v) * 4;
+  o[0] = p00 * cx_ + p02 * cz_; o[1] = p11 * cy_ + p12 * cz_; o[2] = p22 * cz_ + p23; o[3] = -cz_;
+}
+
+static void zero_backward_scratch(vhap_ctx* c, int B, cudaStream_t s) {
+  size_t V = c->V;
+  cudaMemsetAsync(c->g_verts, 0, B * V * 4 * sizeof(float), s);
+  cudaMemsetAsync(c->g_clip, 0, B * V * 4 * sizeof(float), s);
+  cudaMemsetAsync(c->g_vnorm, 0, B * V * 4 * sizeof(float), s);
+  cudaMemsetAsync(c->gA, 0, (size_t)B * 60 * sizeof(float), s);
+  cudaMemsetAsync(c->gpf, 0, (size_t)B * 36 * sizeof(float), s);
+  cudaMemsetAsync(c->gbetas, 0, (size_t)B * c->K * sizeof(float), s);
+}
+
+extern "C" int vhap_flame_forward(vhap_ctx* ctx, const vhap_params* p, const vhap_frame_batch* fb, float* verts, float* verts_cano, float* lmks, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (check_batch(ctx, fb)) return -4;
+  launch_cam_setup(ctx, p, fb, s);
+  launch_flame_forward(ctx, p, fb, s);
+  size_t n = (size_t)fb->B * ctx->V;
+  if (verts) k_copy_verts<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ctx->verts, verts, n);
+  if (verts_cano) cudaMemcpyAsync(verts_cano, ctx->v_shaped, n * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s);
+  if (lmks) launch_landmarks(ctx, fb, 0.f, 0, lmks, nullptr, 0, 0, fb->B, s);
+  LAST();
+  return 0;
+}
+
+extern "C" int vhap_flame_backward(vhap_ctx* ctx, const vhap_params* p, const vhap_frame_batch* fb, const float* g_verts, const float* g_lmks,
+                                   const vhap_grads* g, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (check_batch(ctx, fb)) return -4;
+  zero_backward_scratch(ctx, fb->B, s);
+  size_t n = (size_t)fb->B * ctx->V;
+  if (g_verts) k_load_gverts<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(g_verts, ctx->g_verts, n);
+  if (g_lmks) launch_landmarks(ctx, fb, 0.f, 0, nullptr, (float*)g_lmks, 0, 0, fb->B, s);
+  launch_flame_backward(ctx, p, fb, g, 0, s);
+  LAST();
+  return 0;
+}
+
+extern "C" int vhap_project(vhap_ctx* ctx, const vhap_params* p, const vhap_frame_batch* fb, const float* verts, float* verts_clip, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (check_batch(ctx, fb)) return -4;
+  launch_cam_setup(ctx, p, fb, s);
+  dim3 g((ctx->V + 127) / 128, fb->B);
+  k_project_only<<<g, 128, 0, s>>>(verts, ctx->cam, ctx->V, fb->H, fb->W, verts_clip);
+  LAST();
+  return 0;
+}
+
+extern "C" int vhap_rasterize(vhap_ctx* ctx, const float* verts_clip, int32_t B, int32_t H, int32_t W, int32_t* tri_id, float* rast, float* rast_db,
+                              int32_t cull_backface, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  vhap_frame_batch fb; memset(&fb, 0, sizeof(fb)); fb.B = B; fb.H = H; fb.W = W;
+  if (check_batch(ctx, &fb)) return -4;
+  int* ids = tri_id ? tri_id : ctx->tri_id;
+  launch_raster(ctx, (const f4*)verts_clip, ctx->snap, B, H, W, ids, cull_backface, 1, s);
+  if (rast || rast_db) launch_rast_out(ctx, (const f4*)verts_clip, B, H, W, ids, rast, rast_db, s);
+  LAST();
+  return 0;
+}
+
+extern "C" int vhap_set_tex_painted(vhap_ctx* ctx, const float* tex_painted, void* stream) {
+  size_t n = (size_t)3 * ctx->T * ctx->T;
+  if (!ctx->tex_painted) CK(cudaMalloc((void**)&ctx->tex_painted, n * sizeof(float)));
+  CK(cudaMemcpyAsync(ctx->tex_painted, tex_painted, n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
+extern "C" int vhap_tex_rebuild(vhap_ctx* ctx, const float* tex_extra, void* stream) {
+  launch_tex_rebuild(ctx, tex_extra, (cudaStream_t)stream);
+  LAST();
+  return 0;
+}
+
+__global__ void k_assemble_losses(const float* __restrict__ acc, vhap_stage_cfg cfg, float max_hw, float* __restrict__ g_focal, int add_focal,
+                                  float* __restrict__ out) {
+  if (threadIdx.x != 0) return;
+  if (add_focal && g_focal) g_focal[0] += (acc[ACC_GFX] + acc[ACC_GFY]) * max_hw;       // fx = fy = focal * max(h,w) (tracker.py:153)
+  if (!out) return;
+  for (int i = 0; i < VHAP_N_LOSS; ++i) out[i] = 0.f;
+  out[VHAP_L_LMK] = acc[ACC_LMK]; out[VHAP_L_PHOTO] = acc[ACC_PHOTO]; out[VHAP_L_REG_SHAPE] = acc[ACC_REG_SHAPE];
+  out[VHAP_L_REG_EXPR] = acc[ACC_REG_EXPR]; out[VHAP_L_REG_JOINT] = acc[ACC_REG_JOINT]; out[VHAP_L_SMOOTH_POSE] = acc[ACC_SMOOTH_POSE];
+  out[VHAP_L_SMOOTH_JOINT] = acc[ACC_SMOOTH_JOINT]; out[VHAP_L_SMOOTH_EXPR] = acc[ACC_SMOOTH_EXPR]; out[VHAP_L_REG_TEX_TV] = acc[ACC_REG_TEX_TV];
+  out[VHAP_L_REG_TEX_RES] = acc[ACC_REG_TEX_RES]; out[VHAP_L_REG_DIFFUSE] = acc[ACC_REG_DIFFUSE]; out[VHAP_L_REG_LIGHT] = acc[ACC_REG_LIGHT];
+  out[VHAP_L_REG_OFFSET] = acc[ACC_REG_OFFSET]; out[VHAP_L_REG_OFFSET_LAP] = acc[ACC_REG_OFFSET_LAP]; out[VHAP_L_REG_OFFSET_RIGID] = acc[ACC_REG_OFFSET_RIGID];
+  out[VHAP_L_NFG] = acc[ACC_NFG]; out[VHAP_L_ABSERR] = acc[ACC_ABSERR];
+  float t = 0.f;
+  for (int i = VHAP_L_LMK; i <= VHAP_L_REG_OFFSET_RIGID; ++i) t += out[i];
+  out[VHAP_L_TOTAL] = t;
+}
+
+// forward half: FLAME, landmarks, rasterise, shade, disturb + AA + L1 partial sums; fills reduce_slab (see render.cu)
+extern "C" int vhap_energy_forward(vhap_ctx* ctx, const vhap_params* p, const vhap_frame_batch* fb, const vhap_stage_cfg* cfg, float* reduce_slab,
+                                   void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (check_batch(ctx, fb)) return -4;
+  cudaMemsetAsync(ctx->acc, 0, ACC_COUNT * sizeof(float), s);
+  zero_backward_scratch(ctx, fb->B, s);
+  launch_cam_setup(ctx, p, fb, s);
+  launch_flame_forward(ctx, p, fb, s);
+  if (cfg->photometric && cfg->w_photo >= 0.f) {
+    launch_vnormals(ctx, fb->B, s);
+    launch_raster(ctx, ctx->clip, ctx->snap, fb->B, fb->H, fb->W, ctx->tri_id, 0, 0, s);
+    PassArgs P;
+    fill_render_args(ctx, P, fb, cfg, p->lights);
+    launch_render_forward(ctx, P, s);
+    launch_forward_slab(ctx, P, p->lights, reduce_slab, s);
+  } else {
+    cudaMemsetAsync(reduce_slab, 0, 8 * sizeof(float), s);
+  }
+  LAST();
+  return 0;
+}
+
+extern "C" int vhap_energy_backward(vhap_ctx* ctx, const vhap_params* p, const vhap_frame_batch* fb, const vhap_stage_cfg* cfg, const float* reduce_slab,
+                                    const float* local_slab, int32_t global_B, const vhap_grads* g, float* losses_out, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (check_batch(ctx, fb)) return -4;
+  bool photo = cfg->photometric && cfg->w_photo >= 0.f;
+  vhap_grads none; memset(&none, 0, sizeof(none));
+  const vhap_grads* gg = g ? g : &none;
+  int opt_cam = (gg->focal_length != nullptr) && (fb->K == nullptr);
+  // landmark energy (tracker.py:712-719): mean over global_B * n landmarks
+  if (cfg->w_landmark >= 0.f) {
+    int nl = cfg->jawline_off ? 51 : 68;
+    launch_landmarks(ctx, fb, cfg->w_landmark / ((float)global_B * nl), cfg->jawline_off, nullptr, nullptr, 1, opt_cam, global_B, s);
+  }
+  if (photo) {
+    PassArgs P;
+    fill_render_args(ctx, P, fb, cfg, p->lights);
+    launch_finalize(ctx, P, cfg, reduce_slab, local_slab, global_B, p->lights, gg->lights, s);
+    if (g) {
+      P.g_tex = gg->tex_grad_pyramid;
+      launch_render_backward(ctx, P, cfg, p->lights, gg->lights, nullptr, s);
+      launch_vnormals_bwd(ctx, fb->B, s);
+    }
+  }
+  if (g) launch_flame_backward(ctx, p, fb, gg, opt_cam, s);
+  if (cfg->training) launch_regs(ctx, p, fb, cfg, g, global_B, s);
+  float max_hw = (float)(fb->H > fb->W ? fb->H : fb->W);
+  k_assemble_losses<<<1, 32, 0, s>>>(ctx->acc, *cfg, max_hw, gg->focal_length, opt_cam, losses_out);
+  LAST();
+  return 0;
+}
+
+extern "C" int vhap_energy_forward_backward(vhap_ctx* ctx, const vhap_params* p, const vhap_frame_batch* fb, const vhap_stage_cfg* cfg,
+                                            const vhap_grads* g, float* losses_out, void* stream) {
+  float* slab = ctx->scal + 8;     // scal[8..15] doubles as the single-GPU reduce slab
+  int r = vhap_energy_forward(ctx, p, fb, cfg, slab, stream);
+  if (r) return r;
+  return vhap_energy_backward(ctx, p, fb, cfg, slab, slab, fb->B, g, losses_out, stream);
+}
+
+extern "C" int vhap_get_plane(vhap_ctx* ctx, int32_t which, float* out, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  int B = ctx->curB, H = ctx->curH, W = ctx->curW;
+  const float* src = nullptr;
+  switch (which) {
+    case 0: src = ctx->final_rgba; break;
+    case 1: src = (const float*)ctx->pre; break;
+    case 2: src = (const float*)ctx->plane_albedo; break;
+    case 3: src = (const float*)ctx->plane_normal; break;
+    case 4: src = (const float*)ctx->plane_diffuse; break;
+    case 5: launch_cid_plane(ctx, out, s); LAST(); return 0;
+    default: vh_set_error(ctx, "vhap_get_plane", "unknown plane"); return -3;
+  }
+  launch_flip_plane(src, out, B, H, W, s);
+  LAST();
+  return 0;
+}
+
+extern "C" int vhap_tex_reg_fold_adam(vhap_ctx* ctx, float* tex_extra, float* g_out, float* adam_m, float* adam_v, float lr, int32_t step,
+                                      const vhap_stage_cfg* cfg, float photo_scale, float* losses_out, void* stream) {
+  (void)photo_scale;
+  launch_tex_fold(ctx, tex_extra, g_out, adam_m, adam_v, lr, step, cfg, losses_out, (cudaStream_t)stream);
+  if (losses_out) {
+    // add the two texture terms to the loss vector produced by vhap_energy_backward
+    k_assemble_losses<<<1, 32, 0, (cudaStream_t)stream>>>(ctx->acc, *cfg, 0.f, nullptr, 0, losses_out);
+  }
+  LAST();
+  return 0;
+}
+
+extern "C" int vhap_adam(vhap_ctx* ctx, float* param, const float* grad, float* m, float* v, int64_t n, float lr, int32_t step, void* stream) {
+  launch_adam(param, grad, m, v, n, lr, step, (cudaStream_t)stream);
+  LAST();
+  return 0;
+}
+
+extern "C" int vhap_overflow_flag(vhap_ctx* ctx, int32_t* out_host) {
+  CK(cudaMemcpy(out_host, ctx->overflow_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}

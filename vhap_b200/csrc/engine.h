@@ -1,0 +1,78 @@
+// Internal declarations shared by the translation units of libvhap_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/vhap_b200.h"
+#include "common.cuh"
+#include "flame_math.cuh"
+#include "render_bodies.cuh"
+
+#define VH_TILE 16                 // raster tile edge in pixels
+#define VH_NPART 40                // floats per block-partial row (>= 27 + a few)
+#define VH_MAXB_CHUNK 16           // frames processed per pass of the blend-shape kernels
+
+struct CamParams { float RT[12]; float fx, fy, cx, cy; };
+
+struct vhap_ctx {
+  char err[512];
+  int device;
+  int V, F, VT, K, n_shape, n_expr, n_lmk, n_clusters, T, max_level;
+  int mip_off[VH_MAX_MIPS]; size_t mip_total;
+  // ---- static model
+  float *v_template, *S_fwd, *S_bwd, *posedirs, *Jreg, *lbs_w, *JS, *Jt;
+  i4 *faces, *faces_uv; float* verts_uv; int* lmk_faces; float* lmk_bary; int* adj_opp; uint8_t* fid2cid;
+  int *vf_indptr, *vf_faces; int *lap_indptr, *lap_idx; float* lap_val; int lap_nnz;
+  // ---- stage masks
+  uint8_t *face_flags, *vert_flags; float *w_off, *w_off_lap; int *rigid_indptr, *rigid_vids; int n_rigid; uint8_t* uvmask_res;
+  // ---- texture
+  f4* mips[2]; int cur_mip; float* tex_painted; float* g_tex; float* tv_partials; int tv_nblocks;
+  // ---- per-batch scratch
+  int maxB, maxH, maxW, curB, curH, curW;
+  float *v_shaped, *v_posed, *g_vshaped;          // [B][3V]
+  f4 *verts, *clip, *vnorm, *vnraw; i4* snap;     // [B][V]
+  float *g_clip, *g_vnorm, *g_verts;              // [B][V][4]
+  PoseFwd* posebuf; float* poses;                 // [B], [B][15]
+  float *gA, *gpf, *gJ, *gbetas, *betas;          // [B][60], [B][36], [B][15], [B][K], [B][K]
+  CamParams* cam;                                 // [B]
+  float* lap_y;                                   // [V][3]
+  // pixels
+  int* tri_id; f4* pre; uint8_t* signs; int* pool_list; float* final_rgba; f4 *plane_albedo, *plane_normal, *plane_diffuse;
+  int want_planes;
+  // raster binning
+  int *tile_count, *tile_off, *tile_cursor, *tile_list; int tile_cap; int* overflow_flag;
+  // pools
+  int *pool_blk_count, *pool_blk_off, *pool_base, *pool_count; int pool_nblk;
+  // reductions
+  float* partials; int n_partials_rows;           // [rows][VH_NPART]
+  unsigned long long* maxslot;                    // packed (orderable float bits << 32 | idx)
+  float* scal;                                    // [16] device scalars for pass C
+  float* acc;                                     // [64] misc accumulators (loss sums, focal grad...)
+  const uint8_t* inj_w; const float* inj_u;
+};
+
+void vh_set_error(vhap_ctx* ctx, const char* what, const char* msg);
+
+// flame.cu
+void launch_cam_setup(vhap_ctx* c, const vhap_params* p, const vhap_frame_batch* fb, cudaStream_t s);
+void launch_flame_forward(vhap_ctx* c, const vhap_params* p, const vhap_frame_batch* fb, cudaStream_t s);
+void launch_landmarks(vhap_ctx* c, const vhap_frame_batch* fb, float w_scale, int jawline_off, float* lmks_out, float* g_lmk_in,
+                      int compute_loss, int opt_cam, int global_B, cudaStream_t s);
+void launch_flame_backward(vhap_ctx* c, const vhap_params* p, const vhap_frame_batch* fb, const vhap_grads* g, int opt_cam, cudaStream_t s);
+void launch_vnormals(vhap_ctx* c, int B, cudaStream_t s);
+void launch_vnormals_bwd(vhap_ctx* c, int B, cudaStream_t s);
+void launch_regs(vhap_ctx* c, const vhap_params* p, const vhap_frame_batch* fb, const vhap_stage_cfg* cfg, const vhap_grads* g, int global_B, cudaStream_t s);
+// raster.cu
+void launch_raster(vhap_ctx* c, const f4* clip, i4* snap, int B, int H, int W, int* tri_id, int cull_backface, int need_snap, cudaStream_t s);
+void launch_rast_out(vhap_ctx* c, const f4* clip, int B, int H, int W, const int* tri_id, float* rast, float* rast_db, cudaStream_t s);
+// render.cu
+void fill_render_args(vhap_ctx* c, PassArgs& P, const vhap_frame_batch* fb, const vhap_stage_cfg* cfg, const float* lights);
+void launch_render_forward(vhap_ctx* c, PassArgs& P, cudaStream_t s);
+void launch_render_finalize(vhap_ctx* c, PassArgs& P, const vhap_stage_cfg* cfg, const float* reduce_slab, int global_B, const float* lights, cudaStream_t s);
+void launch_render_backward(vhap_ctx* c, PassArgs& P, const vhap_stage_cfg* cfg, const float* lights, float* g_lights, const float* ext_grad, cudaStream_t s);
+// texture.cu
+void launch_tex_rebuild(vhap_ctx* c, const float* tex_extra, cudaStream_t s);
+void launch_tex_fold(vhap_ctx* c, float* tex_extra, float* g_out, float* m, float* v, float lr, int step, const vhap_stage_cfg* cfg,
+                     float* losses_out, cudaStream_t s);
+void launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, int step, cudaStream_t s);

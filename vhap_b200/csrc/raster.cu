@@ -1,0 +1,240 @@
+// Tile-binned triangle rasteriser (replaces dr.rasterize, vhap/util/render_nvdiffrast.py:254).
+// Specification: oracle/raster.py rasterize_ids (exact integer coverage, fp32 depth plane, lower-id tie break); the
+// triangle ids produced here are bit-identical to it.  Pipeline per call:
+//   k_snap (only for caller-provided clip positions; the fused path snaps inside k_skin_fwd)
+//   k_bin<COUNT> -> k_scan -> k_bin<FILL> : per-frame 16x16-pixel tile lists of triangle ids
+//   k_fine : one CTA (4 warps) per tile; lanes set up triangles into shared memory, each warp owns an 8x8 sub-tile and
+//            uses __ballot_sync to skip triangles whose bounding box misses it; every lane tests 2 pixels with int32 edge
+//            functions relative to the tile origin (saturated so the sign is exact) and keeps the nearest hit in registers.
+#include "engine.h"
+
+#define SNAP_GUARD 131072.f
+#define FINE_CHUNK 128
+
+__global__ void k_snap(const f4* __restrict__ clip, i4* __restrict__ snap, int n, int H, int W) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  f4 cl = clip[i];
+  bool valid = isfinite(cl.x) && isfinite(cl.y) && isfinite(cl.z) && isfinite(cl.w) && cl.w > 0.f;
+  i4 sn = {0, 0, 0, 0};
+  if (valid) {
+    float sx = __fmul_rn(__fdiv_rn(cl.x, cl.w), (float)(W * 8));
+    float sy = __fmul_rn(__fdiv_rn(cl.y, cl.w), (float)(H * 8));
+    sx = fminf(fmaxf(sx, -SNAP_GUARD), SNAP_GUARD); sy = fminf(fmaxf(sy, -SNAP_GUARD), SNAP_GUARD);
+    sn.x = __float2int_rn(sx); sn.y = __float2int_rn(sy);
+    sn.z = __float_as_int(__fdiv_rn(cl.z, cl.w)); sn.w = 1;
+  }
+  snap[i] = sn;
+}
+
+__device__ __forceinline__ int floordiv16(int a) { return a >> 4; }       // arithmetic shift = floor for negatives
+__device__ __forceinline__ int ceildiv16(int a) { return -((-a) >> 4); }
+
+// pixel bounding box of the samples a triangle can cover; false = culled
+__device__ __forceinline__ bool tri_bbox(const i4& s0, const i4& s1, const i4& s2, int H, int W, int cull_backface,
+                                         int& px0, int& px1, int& py0, int& py1, long long& area2) {
+  if (!(s0.w && s1.w && s2.w)) return false;
+  long long d1x = s1.x - s0.x, d1y = s1.y - s0.y, d2x = s2.x - s0.x, d2y = s2.y - s0.y;
+  area2 = d1x * d2y - d2x * d1y;
+  if (area2 == 0) return false;
+  if (cull_backface && area2 < 0) return false;
+  int mnx = min(s0.x, min(s1.x, s2.x)), mxx = max(s0.x, max(s1.x, s2.x));
+  int mny = min(s0.y, min(s1.y, s2.y)), mxy = max(s0.y, max(s1.y, s2.y));
+  px0 = max(ceildiv16(mnx + W * 8 - 8), 0); px1 = min(floordiv16(mxx + W * 8 - 8), W - 1);
+  py0 = max(ceildiv16(mny + H * 8 - 8), 0); py1 = min(floordiv16(mxy + H * 8 - 8), H - 1);
+  return px0 <= px1 && py0 <= py1;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_bin(const i4* __restrict__ snap, const i4* __restrict__ faces, int V, int F, int B, int H, int W,
+                                             int tiles_x, int tiles_y, int cull_backface, int* __restrict__ tile_count,
+                                             const int* __restrict__ tile_off, int* __restrict__ tile_cursor, int* __restrict__ tile_list,
+                                             int tile_cap, int* __restrict__ overflow) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (t >= F) return;
+  i4 f = faces[t];
+  const i4* sb = snap + (size_t)b * V;
+  i4 s0 = sb[f.x], s1 = sb[f.y], s2 = sb[f.z];
+  int px0, px1, py0, py1; long long area2;
+  if (!tri_bbox(s0, s1, s2, H, W, cull_backface, px0, px1, py0, py1, area2)) return;
+  int tx0 = px0 / VH_TILE, tx1 = px1 / VH_TILE, ty0 = py0 / VH_TILE, ty1 = py1 / VH_TILE;
+  for (int ty = ty0; ty <= ty1; ++ty)
+    for (int tx = tx0; tx <= tx1; ++tx) {
+      int tile = (b * tiles_y + ty) * tiles_x + tx;
+      if (!FILL) atomicAdd(tile_count + tile, 1);
+      else {
+        int pos = tile_off[tile] + atomicAdd(tile_cursor + tile, 1);
+        if (pos < tile_cap) tile_list[pos] = t; else *overflow = 1;
+      }
+    }
+}
+
+// exclusive scan of n ints by one block (n up to a few hundred thousand)
+__global__ void __launch_bounds__(1024) k_scan(const int* __restrict__ in, int* __restrict__ out, int n) {
+  __shared__ int sh[1024];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024 * 4) {
+    int i0 = base + threadIdx.x * 4;
+    int v[4], s = 0;
+    for (int k = 0; k < 4; ++k) { v[k] = (i0 + k < n) ? in[i0 + k] : 0; s += v[k]; }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      int t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    int excl = sh[threadIdx.x] - s + carry;
+    for (int k = 0; k < 4; ++k) { if (i0 + k < n) out[i0 + k] = excl; excl += v[k]; }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += sh[1023];
+    __syncthreads();
+  }
+}
+
+struct FineTri {        // shared-memory record, struct of arrays
+  int e[3][FINE_CHUNK], ea[3][FINE_CHUNK], eb[3][FINE_CHUNK];
+  float zx[FINE_CHUNK], zy[FINE_CHUNK], zc[FINE_CHUNK];
+  int id[FINE_CHUNK];
+  unsigned bbox[FINE_CHUNK];    // tile-relative pixel bbox packed x0 | x1<<8 | y0<<16 | y1<<24 ; 0xffffffff = skip
+};
+
+__device__ __forceinline__ int sat30(long long v) {
+  const long long L = 1ll << 30;
+  return (int)(v > L ? L : (v < -L ? -L : v));
+}
+
+__global__ void __launch_bounds__(128) k_fine(const i4* __restrict__ snap, const i4* __restrict__ faces, const int* __restrict__ tile_count,
+                                              const int* __restrict__ tile_off, const int* __restrict__ tile_list, int tile_cap,
+                                              int V, int H, int W, int tiles_x, int tiles_y, int cull_backface, int* __restrict__ tri_id) {
+  __shared__ FineTri T;
+  int tile = blockIdx.x;
+  int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+  int n = tile_count[tile], off = tile_off[tile];
+  if (off + n > tile_cap) n = max(tile_cap - off, 0);
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int sx0 = (warp & 1) * 8, sy0 = (warp >> 1) * 8;              // sub-tile origin inside the tile
+  int lx = sx0 + (lane & 7), ly0 = sy0 + (lane >> 3), ly1 = ly0 + 4;
+  int X0 = tx * VH_TILE, Y0 = ty * VH_TILE;
+  int gx = X0 + lx, gy0 = Y0 + ly0, gy1 = Y0 + ly1;
+  float Cxf = (float)((2 * gx + 1 - W) * 8), Cy0f = (float)((2 * gy0 + 1 - H) * 8), Cy1f = (float)((2 * gy1 + 1 - H) * 8);
+  float bz0 = INFINITY, bz1 = INFINITY; int bi0 = 0, bi1 = 0;
+  const i4* sb = snap + (size_t)b * V;
+  long long Cx0 = (long long)(2 * X0 + 1 - W) * 8, Cy0 = (long long)(2 * Y0 + 1 - H) * 8;   // sample of the tile's first pixel
+  for (int base = 0; base < n; base += FINE_CHUNK) {
+    int j = threadIdx.x, cnt = min(FINE_CHUNK, n - base);
+    __syncthreads();
+    if (j < cnt) {
+      int t = tile_list[off + base + j];
+      i4 f = faces[t];
+      i4 s0 = sb[f.x], s1 = sb[f.y], s2 = sb[f.z];
+      int px0, px1, py0, py1; long long area2;
+      unsigned bb = 0xffffffffu;
+      if (tri_bbox(s0, s1, s2, H, W, cull_backface, px0, px1, py0, py1, area2)) {
+        int rx0 = max(px0 - X0, 0), rx1 = min(px1 - X0, VH_TILE - 1), ry0 = max(py0 - Y0, 0), ry1 = min(py1 - Y0, VH_TILE - 1);
+        if (rx0 <= rx1 && ry0 <= ry1) {
+          bb = (unsigned)rx0 | ((unsigned)rx1 << 8) | ((unsigned)ry0 << 16) | ((unsigned)ry1 << 24);
+          int sgn = area2 > 0 ? 1 : -1;
+          const i4 sv[3] = {s0, s1, s2};
+          for (int k = 0; k < 3; ++k) {                       // edge k: v_{k+1} -> v_{k+2}
+            const i4& A = sv[(k + 1) % 3]; const i4& Bv = sv[(k + 2) % 3];
+            long long dx = (long long)sgn * (Bv.x - A.x), dy = (long long)sgn * (Bv.y - A.y);
+            long long E = dx * (Cy0 - A.y) - dy * (Cx0 - A.x);
+            bool tl = (dy < 0) || (dy == 0 && dx < 0);
+            if (!tl) E -= 1;                                   // E > 0  <=>  E - 1 >= 0
+            T.e[k][j] = sat30(E);
+            T.ea[k][j] = (int)(-16 * dy);                      // step per pixel in x
+            T.eb[k][j] = (int)(16 * dx);                       // step per pixel in y
+          }
+          // fp32 depth plane, every operation individually rounded (no FMA), see oracle/raster.py
+          float z0 = __int_as_float(s0.z), z1 = __int_as_float(s1.z), z2 = __int_as_float(s2.z);
+          float f1x = (float)(s1.x - s0.x), f1y = (float)(s1.y - s0.y), f2x = (float)(s2.x - s0.x), f2y = (float)(s2.y - s0.y);
+          float dz1 = __fsub_rn(z1, z0), dz2 = __fsub_rn(z2, z0);
+          float af = __ll2float_rn(area2);
+          float zx = __fdiv_rn(__fsub_rn(__fmul_rn(dz1, f2y), __fmul_rn(dz2, f1y)), af);
+          float zy = __fdiv_rn(__fsub_rn(__fmul_rn(dz2, f1x), __fmul_rn(dz1, f2x)), af);
+          float zc = __fsub_rn(__fsub_rn(z0, __fmul_rn(zx, (float)s0.x)), __fmul_rn(zy, (float)s0.y));
+          T.zx[j] = zx; T.zy[j] = zy; T.zc[j] = zc; T.id[j] = t + 1;
+        }
+      }
+      T.bbox[j] = bb;
+    }
+    __syncthreads();
+    for (int g = 0; g < cnt; g += 32) {
+      int q = g + lane;
+      bool hit = false;
+      if (q < cnt) {
+        unsigned bb = T.bbox[q];
+        if (bb != 0xffffffffu) {
+          int rx0 = bb & 255, rx1 = (bb >> 8) & 255, ry0 = (bb >> 16) & 255, ry1 = bb >> 24;
+          hit = rx0 <= sx0 + 7 && rx1 >= sx0 && ry0 <= sy0 + 7 && ry1 >= sy0;
+        }
+      }
+      unsigned mask = __ballot_sync(0xffffffffu, hit);
+      while (mask) {
+        int k = g + __ffs(mask) - 1;
+        mask &= mask - 1;
+        int e0 = T.e[0][k] + T.ea[0][k] * lx, e1 = T.e[1][k] + T.ea[1][k] * lx, e2 = T.e[2][k] + T.ea[2][k] * lx;
+        int b0 = T.eb[0][k], b1 = T.eb[1][k], b2 = T.eb[2][k];
+        float zx = T.zx[k], zy = T.zy[k], zc = T.zc[k];
+        int id = T.id[k];
+        float zxx = __fmul_rn(zx, Cxf);
+        if ((e0 + b0 * ly0 | e1 + b1 * ly0 | e2 + b2 * ly0) >= 0) {
+          float z = __fadd_rn(__fadd_rn(zxx, __fmul_rn(zy, Cy0f)), zc);
+          if (z >= -1.f && z <= 1.f && (z < bz0 || (z == bz0 && id < bi0))) { bz0 = z; bi0 = id; }
+        }
+        if ((e0 + b0 * ly1 | e1 + b1 * ly1 | e2 + b2 * ly1) >= 0) {
+          float z = __fadd_rn(__fadd_rn(zxx, __fmul_rn(zy, Cy1f)), zc);
+          if (z >= -1.f && z <= 1.f && (z < bz1 || (z == bz1 && id < bi1))) { bz1 = z; bi1 = id; }
+        }
+      }
+    }
+  }
+  if (gx < W) {
+    if (gy0 < H) tri_id[((size_t)b * H + gy0) * W + gx] = bi0;
+    if (gy1 < H) tri_id[((size_t)b * H + gy1) * W + gx] = bi1;
+  }
+}
+
+void launch_raster(vhap_ctx* c, const f4* clip, i4* snap, int B, int H, int W, int* tri_id, int cull_backface, int need_snap, cudaStream_t s) {
+  int V = c->V, F = c->F;
+  if (need_snap) k_snap<<<(B * V + 255) / 256, 256, 0, s>>>(clip, snap, B * V, H, W);
+  int tiles_x = (W + VH_TILE - 1) / VH_TILE, tiles_y = (H + VH_TILE - 1) / VH_TILE, ntiles = B * tiles_x * tiles_y;
+  cudaMemsetAsync(c->tile_count, 0, sizeof(int) * ntiles, s);
+  cudaMemsetAsync(c->tile_cursor, 0, sizeof(int) * ntiles, s);
+  dim3 g((F + 255) / 256, B);
+  k_bin<false><<<g, 256, 0, s>>>(snap, c->faces, V, F, B, H, W, tiles_x, tiles_y, cull_backface, c->tile_count, nullptr, nullptr, nullptr, 0, c->overflow_flag);
+  k_scan<<<1, 1024, 0, s>>>(c->tile_count, c->tile_off, ntiles);
+  k_bin<true><<<g, 256, 0, s>>>(snap, c->faces, V, F, B, H, W, tiles_x, tiles_y, cull_backface, c->tile_count, c->tile_off, c->tile_cursor, c->tile_list,
+                                c->tile_cap, c->overflow_flag);
+  k_fine<<<ntiles, 128, 0, s>>>(snap, c->faces, c->tile_count, c->tile_off, c->tile_list, c->tile_cap, V, H, W, tiles_x, tiles_y, cull_backface, tri_id);
+}
+
+// dr.rasterize's float outputs for the modular API: rast = (u, v, z/w, id), rast_db = (du/dx, du/dy, dv/dx, dv/dy)
+__global__ void k_rast_out(RenderArgs A, float* __restrict__ rast, float* __restrict__ rast_db) {
+  size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t n = (size_t)A.B * A.H * A.W;
+  if (pix >= n) return;
+  int x = pix % A.W, y = (pix / A.W) % A.H, b = pix / ((size_t)A.W * A.H);
+  int id = A.tri_id[pix];
+  float4 r = {0, 0, 0, 0}, d = {0, 0, 0, 0};
+  if (id > 0) {
+    TriSetup s;
+    tri_setup(A, b, x, y, id - 1, s);
+    r = make_float4(s.b0, s.b1, s.zw, (float)id);
+    d = make_float4(s.dudx, s.dudy, s.dvdx, s.dvdy);
+  }
+  if (rast) ((float4*)rast)[pix] = r;
+  if (rast_db) ((float4*)rast_db)[pix] = d;
+}
+
+void launch_rast_out(vhap_ctx* c, const f4* clip, int B, int H, int W, const int* tri_id, float* rast, float* rast_db, cudaStream_t s) {
+  RenderArgs A;
+  memset(&A, 0, sizeof(A));
+  A.B = B; A.H = H; A.W = W; A.V = c->V; A.F = c->F; A.faces = c->faces; A.clip = clip; A.tri_id = tri_id;
+  size_t n = (size_t)B * H * W;
+  k_rast_out<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(A, rast, rast_db);
+}

@@ -1,0 +1,319 @@
+// Fused render passes (kernels around render_bodies.cuh):
+//   k_passA      shade every foreground pixel, write its composite colour, per-block reg_diffuse partials + max
+//   k_pool_*     stable compaction of pixel indices per colour cluster (pools of render_nvdiffrast.py:445-459)
+//   k_passB      disturbance + antialias + L1 partial sums + sign bytes
+//   k_finalize   global scalars (photo scale = w/(3 n_fg), reg_diffuse scale / arg-max), loss values
+//   k_passC      analytic backward to clip positions, vertex normals, texels, lights
+// Replaces NVDiffRenderer.render_rgba (vhap/util/render_nvdiffrast.py:354-484), compute_photometric_energy
+// (vhap/model/tracker.py:391-478), reg_diffuse (tracker.py:547-550) and their autograd.
+#include "engine.h"
+#include "accum.h"
+
+#define PB 256     // pixels (threads) per block in the per-pixel passes
+
+__device__ __forceinline__ float warp_sum_r(float v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// reduce `n` per-thread values across the block and write them to row[blockIdx.x]; sh must hold 8*n floats (256 threads)
+template <int N>
+__device__ void block_reduce_store(float* vals, float* sh, float* row) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < N; ++i) { float v = warp_sum_r(vals[i]); if (lane == 0) sh[w * N + i] = v; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < PB / 32; ++k) s += sh[k * N + i];
+    row[i] = s;
+  }
+}
+
+__device__ __forceinline__ unsigned long long pack_max(float v, int idx) {
+  unsigned u = __float_as_uint(v);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);          // order-preserving map float -> uint
+  return ((unsigned long long)u << 32) | (unsigned)idx;
+}
+__host__ __device__ __forceinline__ float unpack_max_val(unsigned long long p) {
+  unsigned u = (unsigned)(p >> 32);
+  u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(u);
+#else
+  float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+
+__global__ void __launch_bounds__(PB) k_passA(PassArgs P, float* __restrict__ partials, unsigned long long* __restrict__ maxslot) {
+  __shared__ float sh[8 * 2];
+  __shared__ unsigned long long shm[8];
+  const RenderArgs& A = P.R;
+  size_t pix = (size_t)blockIdx.x * PB + threadIdx.x, n = (size_t)A.B * A.H * A.W;
+  float acc[2] = {0.f, 0.f}; float mx = -INFINITY; int mxi = 0;
+  if (pix < n) {
+    int x = pix % A.W, y = (pix / A.W) % A.H, b = pix / ((size_t)A.W * A.H);
+    passA_body(P, b, y, x, acc, mx, mxi);
+  }
+  block_reduce_store<2>(acc, sh, partials + (size_t)blockIdx.x * VH_NPART);
+  unsigned long long pm = mx > -INFINITY ? pack_max(mx, mxi) : 0ull;
+  for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, pm, o); pm = t > pm ? t : pm; }
+  if ((threadIdx.x & 31) == 0) shm[threadIdx.x >> 5] = pm;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < PB / 32; ++k) pm = shm[k] > pm ? shm[k] : pm;
+    if (pm) atomicMax(maxslot, pm);
+  }
+}
+
+// ---- cluster pools: count per block, scan, stable scatter
+__global__ void __launch_bounds__(PB) k_pool_count(const int* __restrict__ tri_id, const uint8_t* __restrict__ fid2cid, size_t n, int* __restrict__ blk_count) {
+  __shared__ int cnt[16];
+  if (threadIdx.x < 16) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  size_t pix = (size_t)blockIdx.x * PB + threadIdx.x;
+  int cid = pix < n ? fid2cid[tri_id[pix]] : -1;
+  for (int c = 0; c < 16; ++c) {
+    unsigned m = __ballot_sync(0xffffffffu, cid == c);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&cnt[c], __popc(m));
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) blk_count[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = cnt[threadIdx.x];    // [16][nblk]
+}
+
+// scans the [16][nblk] counts as ONE sequence -> pixel lists are laid out cluster after cluster; also emits base/count
+__global__ void __launch_bounds__(1024) k_pool_scan(const int* __restrict__ in, int* __restrict__ out, int nblk, int* __restrict__ base, int* __restrict__ count) {
+  __shared__ int sh[1024];
+  __shared__ int carry;
+  int n = 16 * nblk;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < n; b0 += 1024 * 4) {
+    int i0 = b0 + threadIdx.x * 4;
+    int v[4], s = 0;
+    for (int k = 0; k < 4; ++k) { v[k] = (i0 + k < n) ? in[i0 + k] : 0; s += v[k]; }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      int t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    int excl = sh[threadIdx.x] - s + carry;
+    for (int k = 0; k < 4; ++k) { if (i0 + k < n) out[i0 + k] = excl; excl += v[k]; }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += sh[1023];
+    __syncthreads();
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    int c = threadIdx.x;
+    int b = out[(size_t)c * nblk];
+    int e = c < 15 ? out[(size_t)(c + 1) * nblk] : carry;
+    base[c] = b; count[c] = e - b;
+  }
+}
+
+__global__ void __launch_bounds__(PB) k_pool_scatter(const int* __restrict__ tri_id, const uint8_t* __restrict__ fid2cid, size_t n,
+                                                     const int* __restrict__ blk_off, int* __restrict__ pool_list) {
+  __shared__ int wcnt[16][PB / 32];
+  size_t pix = (size_t)blockIdx.x * PB + threadIdx.x;
+  int cid = pix < n ? fid2cid[tri_id[pix]] : -1;
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int rank = 0;
+  for (int c = 0; c < 16; ++c) {
+    unsigned m = __ballot_sync(0xffffffffu, cid == c);
+    if (cid == c) rank = __popc(m & ((1u << lane) - 1));
+    if (lane == 0) wcnt[c][w] = __popc(m);
+  }
+  __syncthreads();
+  if (cid >= 0) {
+    int before = 0;
+    for (int k = 0; k < w; ++k) before += wcnt[cid][k];
+    pool_list[blk_off[(size_t)cid * gridDim.x + blockIdx.x] + before + rank] = (int)pix;
+  }
+}
+
+__global__ void __launch_bounds__(PB) k_passB(PassArgs P, float* __restrict__ partials) {
+  __shared__ float sh[8 * 2];
+  const RenderArgs& A = P.R;
+  size_t pix = (size_t)blockIdx.x * PB + threadIdx.x, n = (size_t)A.B * A.H * A.W;
+  float acc[2] = {0.f, 0.f};
+  if (pix < n) {
+    int x = pix % A.W, y = (pix / A.W) % A.H, b = pix / ((size_t)A.W * A.H);
+    passB_body(P, b, y, x, acc);
+  }
+  block_reduce_store<2>(acc, sh, partials + (size_t)blockIdx.x * VH_NPART + 2);
+}
+
+// sums the per-block partial rows (columns 0..3) into acc[ACC_VARSUM, ACC_NFGPIX, ACC_ABSERR, ACC_NFG]
+__global__ void __launch_bounds__(1024) k_reduce_partials(const float* __restrict__ partials, int rows, int ncol, float* __restrict__ out, const int* __restrict__ slot) {
+  __shared__ float sh[32];
+  for (int c = 0; c < ncol; ++c) {
+    float s = 0.f;
+    for (int r = threadIdx.x; r < rows; r += blockDim.x) s += partials[(size_t)r * VH_NPART + c];
+    s = warp_sum_r(s);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) { float t = sh[threadIdx.x]; t = warp_sum_r(t); if (threadIdx.x == 0) out[slot[c]] += t; }
+  }
+}
+
+__global__ void __launch_bounds__(PB) k_passC(PassArgs P, const float* __restrict__ ext_grad, float* __restrict__ partials) {
+  __shared__ float sh[8 * 27];
+  const RenderArgs& A = P.R;
+  size_t pix = (size_t)blockIdx.x * PB + threadIdx.x, n = (size_t)A.B * A.H * A.W;
+  float gl[27];
+#pragma unroll
+  for (int i = 0; i < 27; ++i) gl[i] = 0.f;
+  if (pix < n) {
+    int x = pix % A.W, y = (pix / A.W) % A.H, b = pix / ((size_t)A.W * A.H);
+    passC_body(P, b, y, x, ext_grad, gl);
+  }
+  block_reduce_store<27>(gl, sh, partials + (size_t)blockIdx.x * VH_NPART + 4);
+}
+
+// reduce_slab layout (floats): [0] sum |err|  [1] n(alpha_aa>0)  [2] sum var_c(diffuse) incl. background  [3] max diffuse
+//                              [4] this rank's arg-max index (int bits; -1 = background)  [5] local max (to find the owner)
+__global__ void k_forward_slab(const float* __restrict__ acc, const unsigned long long* __restrict__ maxslot, const float* __restrict__ lights,
+                               float n_pix_total, float* __restrict__ slab) {
+  float nfgpix = acc[ACC_NFGPIX], n_bg = n_pix_total - nfgpix;
+  float dbg[3], mbg = 0.f;
+  for (int c = 0; c < 3; ++c) { dbg[c] = VH_SH_C0 * lights[c] - VH_SH_C4 * lights[24 + c]; mbg += dbg[c] * (1.f / 3.f); }
+  float vbg = 0.f, mxbg = fmaxf(dbg[0], fmaxf(dbg[1], dbg[2]));
+  for (int c = 0; c < 3; ++c) vbg += 0.5f * (dbg[c] - mbg) * (dbg[c] - mbg);
+  unsigned long long pm = *maxslot;
+  float mxfg = pm ? unpack_max_val(pm) : -INFINITY;
+  int idx = pm ? (int)(unsigned)(pm & 0xffffffffu) : -1;
+  bool bg_is_max = n_bg > 0.f && mxbg > mxfg;
+  slab[0] = acc[ACC_ABSERR]; slab[1] = acc[ACC_NFG]; slab[2] = acc[ACC_VARSUM] + n_bg * vbg;
+  slab[3] = bg_is_max ? mxbg : mxfg;
+  ((int*)slab)[4] = bg_is_max ? -1 : idx;
+  slab[5] = slab[3];
+  slab[6] = n_bg; slab[7] = 0.f;
+}
+
+// consumes the (possibly cross-rank reduced) slab: scal[] for pass C, loss values, background share of the light gradient
+__global__ void k_finalize(const float* __restrict__ slab, const float* __restrict__ local_slab, vhap_stage_cfg cfg, const float* __restrict__ lights,
+                           float n_pix_global, float* __restrict__ scal, float* __restrict__ acc, float* __restrict__ g_lights) {
+  float abs_sum = slab[0], nfg = slab[1], varsum = slab[2], mx = slab[3];
+  float photo_scale = (cfg.w_photo >= 0.f && nfg > 0.f) ? cfg.w_photo / (3.f * nfg) : 0.f;
+  scal[0] = photo_scale;
+  acc[ACC_PHOTO] = (cfg.w_photo >= 0.f && nfg > 0.f) ? cfg.w_photo * abs_sum / (3.f * nfg) : 0.f;
+  bool regd = cfg.training && cfg.opt_lights && cfg.w_reg_diffuse >= 0.f;
+  float g_var = regd ? cfg.w_reg_diffuse / n_pix_global : 0.f;
+  float g_max = (regd && mx > 1.f) ? cfg.w_reg_diffuse : 0.f;
+  bool owner = local_slab[5] == mx;                          // the rank holding the global max keeps its gradient
+  int am = ((const int*)local_slab)[4];
+  scal[1] = g_var;
+  scal[2] = (owner && am >= 0) ? g_max : 0.f;
+  ((int*)scal)[3] = am;
+  acc[ACC_REG_DIFFUSE] = regd ? cfg.w_reg_diffuse * (fmaxf(mx - 1.f, 0.f) + varsum / n_pix_global) : 0.f;
+  if (regd && g_lights) {                                    // background pixels: normal = 0 -> basis {C0, 0,..., -C4}
+    float n_bg = local_slab[6];
+    float dbg[3], mbg = 0.f;
+    for (int c = 0; c < 3; ++c) { dbg[c] = VH_SH_C0 * lights[c] - VH_SH_C4 * lights[24 + c]; mbg += dbg[c] * (1.f / 3.f); }
+    int chm = dbg[0] >= dbg[1] ? (dbg[0] >= dbg[2] ? 0 : 2) : (dbg[1] >= dbg[2] ? 1 : 2);
+    for (int c = 0; c < 3; ++c) {
+      float gd = n_bg * (dbg[c] - mbg) * g_var + ((owner && am < 0 && c == chm) ? g_max : 0.f);
+      atomicAdd(g_lights + c, VH_SH_C0 * gd);
+      atomicAdd(g_lights + 24 + c, -VH_SH_C4 * gd);
+    }
+  }
+}
+
+__global__ void k_lights_reduce(const float* __restrict__ partials, int rows, float* __restrict__ g_lights) {
+  int i = threadIdx.x;      // 27 active threads per block, blocks stride over rows
+  if (i >= 27) return;
+  float s = 0.f;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) s += partials[(size_t)r * VH_NPART + 4 + i];
+  atomicAdd(g_lights + i, s);
+}
+
+// flips a raster-orientation float4 plane into image orientation
+__global__ void k_flip_plane(const float4* __restrict__ in, float4* __restrict__ out, int B, int H, int W) {
+  size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n = (size_t)B * H * W;
+  if (pix >= n) return;
+  int x = pix % W, y = (pix / W) % H, b = pix / ((size_t)W * H);
+  out[((size_t)b * H + (H - 1 - y)) * W + x] = in[pix];
+}
+void launch_flip_plane(const float* in, float* out, int B, int H, int W, cudaStream_t s) {
+  size_t n = (size_t)B * H * W;
+  k_flip_plane<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const float4*)in, (float4*)out, B, H, W);
+}
+__global__ void k_cid_plane(const int* __restrict__ tri_id, const uint8_t* __restrict__ fid2cid, float4* __restrict__ out, int B, int H, int W) {
+  size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n = (size_t)B * H * W;
+  if (pix >= n) return;
+  int x = pix % W, y = (pix / W) % H, b = pix / ((size_t)W * H);
+  int id = tri_id[pix];
+  out[((size_t)b * H + (H - 1 - y)) * W + x] = make_float4((float)fid2cid[id], (float)id, 0.f, 0.f);
+}
+void launch_cid_plane(vhap_ctx* c, float* out, cudaStream_t s) {
+  size_t n = (size_t)c->curB * c->curH * c->curW;
+  k_cid_plane<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(c->tri_id, c->fid2cid, (float4*)out, c->curB, c->curH, c->curW);
+}
+
+void fill_render_args(vhap_ctx* c, PassArgs& P, const vhap_frame_batch* fb, const vhap_stage_cfg* cfg, const float* lights) {
+  memset(&P, 0, sizeof(P));
+  RenderArgs& A = P.R;
+  A.B = fb->B; A.H = fb->H; A.W = fb->W; A.V = c->V; A.F = c->F; A.T = c->T; A.max_level = c->max_level;
+  A.faces = c->faces; A.faces_uv = c->faces_uv; A.verts_uv = c->verts_uv; A.clip = c->clip; A.vnorm = c->vnorm; A.lights = lights;
+  A.mips = c->mips[c->cur_mip];
+  for (int i = 0; i < VH_MAX_MIPS; ++i) A.mip_off[i] = c->mip_off[i];
+  A.tri_id = c->tri_id; A.face_flags = cfg->training ? c->face_flags : nullptr; A.vert_flags = cfg->training ? c->vert_flags : nullptr;
+  A.fid2cid = c->fid2cid; A.adj_opp = c->adj_opp;
+  P.target = (const uint16_t*)fb->target; P.pre = c->pre; P.signs = c->signs;
+  P.final_rgba = c->want_planes ? c->final_rgba : nullptr;
+  P.plane_albedo = c->want_planes ? c->plane_albedo : nullptr; P.plane_normal = c->want_planes ? c->plane_normal : nullptr;
+  P.plane_diffuse = c->want_planes ? c->plane_diffuse : nullptr;
+  P.pool_list = c->pool_list; P.pool_base = c->pool_base; P.pool_count = c->pool_count;
+  P.disturb = cfg->training ? 1 : 0;                        // enable_disturbance = stage != None (tracker.py:427)
+  P.rate_fg = cfg->disturb_rate_fg; P.rate_bg = cfg->disturb_rate_bg;
+  P.inj_w = c->inj_w; P.inj_u = c->inj_u; P.seed = cfg->rng_seed; P.step = cfg->rng_step;
+  P.bg_mode = cfg->bg_mode; P.bg_color[0] = cfg->bg_color[0]; P.bg_color[1] = cfg->bg_color[1]; P.bg_color[2] = cfg->bg_color[2];
+  P.scal = c->scal; P.g_clip = c->g_clip; P.g_vnorm = c->g_vnorm; P.g_tex = nullptr;
+}
+
+void launch_render_forward(vhap_ctx* c, PassArgs& P, cudaStream_t s) {
+  const RenderArgs& A = P.R;
+  size_t n = (size_t)A.B * A.H * A.W;
+  int nblk = (int)((n + PB - 1) / PB);
+  cudaMemsetAsync(c->maxslot, 0, sizeof(unsigned long long), s);
+  k_passA<<<nblk, PB, 0, s>>>(P, c->partials, c->maxslot);
+  if (P.disturb) {
+    k_pool_count<<<nblk, PB, 0, s>>>(A.tri_id, A.fid2cid, n, c->pool_blk_count);
+    k_pool_scan<<<1, 1024, 0, s>>>(c->pool_blk_count, c->pool_blk_off, nblk, c->pool_base, c->pool_count);
+    k_pool_scatter<<<nblk, PB, 0, s>>>(A.tri_id, A.fid2cid, n, c->pool_blk_off, c->pool_list);
+  }
+  k_passB<<<nblk, PB, 0, s>>>(P, c->partials);
+  static const int h_slot[4] = {ACC_VARSUM, ACC_NFGPIX, ACC_ABSERR, ACC_NFG};
+  static int* d_slot = nullptr;
+  if (!d_slot) { cudaMalloc(&d_slot, sizeof(h_slot)); cudaMemcpy(d_slot, h_slot, sizeof(h_slot), cudaMemcpyHostToDevice); }
+  k_reduce_partials<<<1, 1024, 0, s>>>(c->partials, nblk, 4, c->acc, d_slot);
+}
+
+void launch_forward_slab(vhap_ctx* c, const PassArgs& P, const float* lights, float* slab, cudaStream_t s) {
+  const RenderArgs& A = P.R;
+  k_forward_slab<<<1, 1, 0, s>>>(c->acc, c->maxslot, lights, (float)((size_t)A.B * A.H * A.W), slab);
+}
+
+void launch_render_finalize(vhap_ctx* c, PassArgs& P, const vhap_stage_cfg* cfg, const float* reduce_slab, int global_B, const float* lights, cudaStream_t s) {
+  (void)c; (void)P; (void)cfg; (void)reduce_slab; (void)global_B; (void)lights; (void)s;
+}
+
+void launch_finalize(vhap_ctx* c, const PassArgs& P, const vhap_stage_cfg* cfg, const float* slab_global, const float* slab_local, int global_B,
+                     const float* lights, float* g_lights, cudaStream_t s) {
+  const RenderArgs& A = P.R;
+  k_finalize<<<1, 1, 0, s>>>(slab_global, slab_local, *cfg, lights, (float)((size_t)global_B * A.H * A.W), c->scal, c->acc, g_lights);
+}
+
+void launch_render_backward(vhap_ctx* c, PassArgs& P, const vhap_stage_cfg* cfg, const float* lights, float* g_lights, const float* ext_grad, cudaStream_t s) {
+  (void)cfg; (void)lights;
+  const RenderArgs& A = P.R;
+  size_t n = (size_t)A.B * A.H * A.W;
+  int nblk = (int)((n + PB - 1) / PB);
+  k_passC<<<nblk, PB, 0, s>>>(P, ext_grad, c->partials);
+  if (g_lights) k_lights_reduce<<<64, 32, 0, s>>>(c->partials, nblk, g_lights);
+}

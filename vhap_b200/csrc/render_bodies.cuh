@@ -6,6 +6,9 @@
 // compute_photometric_energy (vhap/model/tracker.py:391-478); oracle: oracle/render.py, oracle/energy.py.
 #pragma once
 #include "pixel_math.cuh"
+#if defined(__CUDACC__)
+#include <cuda_fp16.h>
+#endif
 
 struct PassArgs {
   RenderArgs R;

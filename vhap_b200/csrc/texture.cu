@@ -1,0 +1,179 @@
+// Texture path: albedo = tex_painted + tex_extra (get_albedo, vhap/model/tracker.py:247-258) -> float4 mip pyramid
+// (the pyramid nvdiffrast builds inside dr.texture, vhap/util/render_nvdiffrast.py:399 -- here ONE copy shared by all
+// frames instead of B expanded copies, tracker.py:234); fold of the texel-gradient pyramid to level 0, total-variation
+// and residual-cluster regularisers (tracker.py:526-539), Adam (torch.optim.Adam, tracker.py:210) and rebuild of level 0,
+// fused into one streaming pass over the 3*T*T texels.
+#include "engine.h"
+#include "accum.h"
+
+__global__ void k_tex_level0(const float* __restrict__ painted, const float* __restrict__ extra, int T, f4* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n = (size_t)T * T;
+  if (i >= n) return;
+  f4 v;
+  v.x = (painted ? painted[i] : 0.f) + extra[i];
+  v.y = (painted ? painted[n + i] : 0.f) + extra[n + i];
+  v.z = (painted ? painted[2 * n + i] : 0.f) + extra[2 * n + i];
+  v.w = 0.f;
+  out[i] = v;
+}
+
+// 2x2 box filter, one level
+__global__ void k_mip_down(const f4* __restrict__ src, f4* __restrict__ dst, int sd) {   // sd = destination size
+  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= sd || y >= sd) return;
+  int ss = sd * 2;
+  f4 a = src[(size_t)(2 * y) * ss + 2 * x], b = src[(size_t)(2 * y + 1) * ss + 2 * x];
+  f4 c = src[(size_t)(2 * y) * ss + 2 * x + 1], d = src[(size_t)(2 * y + 1) * ss + 2 * x + 1];
+  f4 o = {0.25f * (a.x + b.x + c.x + d.x), 0.25f * (a.y + b.y + c.y + d.y), 0.25f * (a.z + b.z + c.z + d.z), 0.f};
+  dst[(size_t)y * sd + x] = o;
+}
+
+static void build_mips(vhap_ctx* c, f4* pyr, cudaStream_t s) {
+  for (int l = 1; l <= c->max_level; ++l) {
+    int sd = c->T >> l;
+    dim3 blk(16, 16), grd((sd + 15) / 16, (sd + 15) / 16);
+    k_mip_down<<<grd, blk, 0, s>>>(pyr + c->mip_off[l - 1], pyr + c->mip_off[l], sd);
+  }
+}
+
+void launch_tex_rebuild(vhap_ctx* c, const float* tex_extra, cudaStream_t s) {
+  size_t n = (size_t)c->T * c->T;
+  f4* pyr = c->mips[c->cur_mip];
+  k_tex_level0<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(c->tex_painted, tex_extra, c->T, pyr);
+  build_mips(c, pyr, s);
+}
+
+struct TexFoldArgs {
+  int T, max_level; int mip_off[VH_MAX_MIPS];
+  const f4* tex_old; f4* tex_new; float* g_pyr;
+  float* extra; float* g_out; float* m; float* v;
+  const uint8_t* mask;
+  float w_tv, w_res;            // already divided by their mean() denominators and scaled by shared_scale
+  float lr, bc1, bc2_sqrt;      // Adam: step size lr/bc1, sqrt(bias correction 2)
+  int do_adam;
+};
+
+__device__ __forceinline__ float chan(const f4& t, int c) { return c == 0 ? t.x : (c == 1 ? t.y : t.z); }
+
+// One thread per level-0 texel (all 3 channels).
+__global__ void __launch_bounds__(256) k_tex_fold(TexFoldArgs a, float* __restrict__ partials) {
+  __shared__ float sh[8 * 2];
+  int T = a.T;
+  size_t n = (size_t)T * T, i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float acc[2] = {0.f, 0.f};
+  if (i < n) {
+    int x = i % T, y = i / T;
+    // photometric gradient: fold every pyramid level back to level 0 (box-filter adjoint: 1/4 per level)
+    float g[3] = {0.f, 0.f, 0.f};
+    if (a.g_pyr) {
+      float sc = 1.f;
+      for (int l = 0; l <= a.max_level; ++l) {
+        int s = T >> l;
+        const float* p = a.g_pyr + ((size_t)a.mip_off[l] + (size_t)(y >> l) * s + (x >> l)) * 4;
+        g[0] += p[0] * sc; g[1] += p[1] * sc; g[2] += p[2] * sc;
+        sc *= 0.25f;
+      }
+      float* p0 = a.g_pyr + i * 4; p0[0] = 0.f; p0[1] = 0.f; p0[2] = 0.f;      // level 0 is re-zeroed here, coarser levels by a memset
+    }
+    f4 t = a.tex_old[i];
+    float ex[3] = {a.extra[i], a.extra[n + i], a.extra[2 * n + i]};
+    if (a.w_tv > 0.f) {                                                          // tracker.py:526-534
+      f4 tr = x + 1 < T ? a.tex_old[i + 1] : t, tl = x > 0 ? a.tex_old[i - 1] : t;
+      f4 td = y + 1 < T ? a.tex_old[i + T] : t, tu = y > 0 ? a.tex_old[i - T] : t;
+      for (int c = 0; c < 3; ++c) {
+        float v = chan(t, c), dr = v - chan(tr, c), dd = v - chan(td, c), dl = chan(tl, c) - v, du = chan(tu, c) - v;
+        acc[0] += a.w_tv * (dr * dr + dd * dd);                                  // each difference counted once (right, down)
+        g[c] += 2.f * a.w_tv * (dr + dd - dl - du);
+      }
+    }
+    if (a.w_res > 0.f && a.mask && a.mask[i]) {                                  // tracker.py:536-539
+      for (int c = 0; c < 3; ++c) { acc[1] += a.w_res * ex[c] * ex[c]; g[c] += 2.f * a.w_res * ex[c]; }
+    }
+    if (a.g_out) { a.g_out[i] = g[0]; a.g_out[n + i] = g[1]; a.g_out[2 * n + i] = g[2]; }
+    if (a.do_adam) {
+      f4 o = t;
+      for (int c = 0; c < 3; ++c) {
+        size_t k = c * n + i;
+        float m = 0.9f * a.m[k] + 0.1f * g[c];
+        float v = 0.999f * a.v[k] + 0.001f * g[c] * g[c];
+        a.m[k] = m; a.v[k] = v;
+        float upd = (a.lr / a.bc1) * m / (sqrtf(v) / a.bc2_sqrt + 1e-8f);
+        float ne = ex[c] - upd;
+        a.extra[k] = ne;
+        float base = chan(t, c) - ex[c];                                          // painted part
+        if (c == 0) o.x = base + ne; else if (c == 1) o.y = base + ne; else o.z = base + ne;
+      }
+      a.tex_new[i] = o;
+    }
+  }
+  // block partial sums of the two loss terms
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int q = 0; q < 2; ++q) {
+    float v = acc[q];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sh[w * 2 + q] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    float s = 0.f;
+    for (int k = 0; k < 8; ++k) s += sh[k * 2 + threadIdx.x];
+    partials[(size_t)blockIdx.x * 2 + threadIdx.x] = s;
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_tex_loss_reduce(const float* __restrict__ partials, int rows, float* __restrict__ acc) {
+  __shared__ float sh[32];
+  for (int q = 0; q < 2; ++q) {
+    float s = 0.f;
+    for (int r = threadIdx.x; r < rows; r += blockDim.x) s += partials[(size_t)r * 2 + q];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float t = sh[threadIdx.x];
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (threadIdx.x == 0) acc[q == 0 ? ACC_REG_TEX_TV : ACC_REG_TEX_RES] += t;
+    }
+  }
+}
+
+void launch_tex_fold(vhap_ctx* c, float* tex_extra, float* g_out, float* m, float* v, float lr, int step, const vhap_stage_cfg* cfg,
+                     float* losses_out, cudaStream_t s) {
+  (void)losses_out;
+  TexFoldArgs a;
+  memset(&a, 0, sizeof(a));
+  int T = c->T;
+  a.T = T; a.max_level = c->max_level;
+  for (int i = 0; i < VH_MAX_MIPS; ++i) a.mip_off[i] = c->mip_off[i];
+  a.tex_old = c->mips[c->cur_mip]; a.tex_new = c->mips[c->cur_mip ^ 1]; a.g_pyr = c->g_tex;
+  a.extra = tex_extra; a.g_out = g_out; a.m = m; a.v = v; a.mask = c->uvmask_res;
+  float sh = cfg->shared_scale;
+  // tv.mean(): (T-1)*T elements per channel, 3 channels (tracker.py:529-533); w already includes scale_factor^2 / ds^2
+  a.w_tv = (cfg->training && cfg->opt_texture && cfg->w_reg_tex_tv >= 0.f) ? sh * cfg->w_reg_tex_tv / (3.f * (float)(T - 1) * (float)T) : 0.f;
+  a.w_res = (cfg->training && cfg->opt_texture && cfg->w_reg_tex_res >= 0.f) ? sh * cfg->w_reg_tex_res / (3.f * (float)T * (float)T) : 0.f;
+  a.do_adam = (m != nullptr && v != nullptr) ? 1 : 0;
+  a.lr = lr; a.bc1 = 1.f - powf(0.9f, (float)step); a.bc2_sqrt = sqrtf(1.f - powf(0.999f, (float)step));
+  size_t n = (size_t)T * T;
+  int nblk = (int)((n + 255) / 256);
+  k_tex_fold<<<nblk, 256, 0, s>>>(a, c->tv_partials);
+  k_tex_loss_reduce<<<1, 1024, 0, s>>>(c->tv_partials, nblk, c->acc);
+  if (c->g_tex && c->max_level >= 1)                                      // coarser gradient levels
+    cudaMemsetAsync(c->g_tex + (size_t)c->mip_off[1] * 4, 0, (c->mip_total - c->mip_off[1]) * 4 * sizeof(float), s);
+  if (a.do_adam) { c->cur_mip ^= 1; build_mips(c, c->mips[c->cur_mip], s); }
+}
+
+__global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+                       float step_size, float bc2_sqrt) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float gi = g[i];
+  float mi = 0.9f * m[i] + 0.1f * gi, vi = 0.999f * v[i] + 0.001f * gi * gi;
+  m[i] = mi; v[i] = vi;
+  p[i] -= step_size * mi / (sqrtf(vi) / bc2_sqrt + 1e-8f);
+}
+
+void launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, int step, cudaStream_t s) {
+  float bc1 = 1.f - powf(0.9f, (float)step), bc2s = sqrtf(1.f - powf(0.999f, (float)step));
+  k_adam<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, g, m, v, n, lr / bc1, bc2s);
+}

@@ -1,0 +1,348 @@
+"""Host side of the B200 photometric engine: parameter store, stage configuration, input staging and the per-iteration
+`step()` that replaces FlameTracker.optimize_iter (vhap/model/tracker.py:1418-1435: compute_energy, backward, Adam).
+
+PyTorch is used for device memory, streams and torch.distributed only; all arithmetic of the hot path happens in
+libvhap_b200.so (hand-written sm_100a CUDA, include/vhap_b200.h) through raw pointers.  There is no fallback path."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import EngineConfig, StageConfig, STAGES, opt_dict_for
+from .flame_model import FlameModelData
+
+PER_FRAME = (("expr", None), ("rotation", 3), ("neck_pose", 3), ("jaw_pose", 3), ("eyes_pose", 6), ("translation", 3))
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class Batch:
+    """One staged batch of frames (the reference's `sample` dict, video_dataset.py:209-241)."""
+
+    def __init__(self, B, H, W, timesteps, target, lmk2d, RT=None, K=None):
+        self.B, self.H, self.W = B, H, W
+        self.timesteps, self.target, self.lmk2d, self.RT, self.K = timesteps, target, lmk2d, RT, K
+        self.c = _lib.FrameBatch(B, H, W, _ptr(timesteps), _ptr(target), _ptr(lmk2d), _ptr(RT), _ptr(K))
+
+
+class Engine:
+    def __init__(self, model: FlameModelData, cfg: EngineConfig, n_timesteps: int, device: str = "cuda:0",
+                 tex_painted: Optional[np.ndarray] = None, world_size: int = 1):
+        if not torch.cuda.is_available():
+            raise RuntimeError("vhap_b200.Engine needs a CUDA device (B200, sm_100a); there is no CPU path")
+        self.L = _lib.lib()
+        self.model, self.cfg, self.n_t = model, cfg, n_timesteps
+        self.dev = torch.device(device)
+        self.world_size = world_size
+        torch.cuda.set_device(self.dev)
+        self.T = cfg.tex_resolution
+        V, F, K = model.v_template.shape[0], model.faces.shape[0], model.shapedirs.shape[2]
+        self.V, self.F, self.K = V, F, K
+        self.n_shape, self.n_expr = model.n_shape, model.n_expr
+        # ---- static tables -> ctx
+        vuv = model.verts_uv.astype(np.float32).copy()
+        vuv[:, 1] = 1.0 - vuv[:, 1]                                         # tracker.py:315-316
+        fid2cid = np.concatenate([[0], model.fid2cid(cfg.tex_clusters)]).astype(np.uint8)   # render_nvdiffrast.py:77-79
+        vf_indptr, vf_faces = model.vertex_face_csr()
+        lap_ip, lap_idx, lap_val = model.laplacian_csr()
+        keep = dict(
+            v_template=np.ascontiguousarray(model.v_template, np.float32), shapedirs=np.ascontiguousarray(model.shapedirs, np.float32),
+            posedirs=np.ascontiguousarray(model.posedirs, np.float32), Jreg=np.ascontiguousarray(model.J_regressor, np.float32),
+            lbs=np.ascontiguousarray(model.lbs_weights, np.float32), faces=np.ascontiguousarray(model.faces, np.int32),
+            faces_uv=np.ascontiguousarray(model.faces_uv, np.int32), vuv=vuv, lmk_f=np.ascontiguousarray(model.lmk_faces_idx, np.int32),
+            lmk_b=np.ascontiguousarray(model.lmk_bary, np.float32), adj=np.ascontiguousarray(model.face_adjacency_opposite(), np.int32),
+            fid2cid=fid2cid, vf_ip=vf_indptr, vf_f=vf_faces, lap_ip=lap_ip, lap_idx=lap_idx, lap_val=lap_val)
+        hp = lambda a: a.ctypes.data_as(C.c_void_p)
+        md = _lib.MeshDesc(V, F, vuv.shape[0], K, model.n_shape, model.lmk_faces_idx.shape[0], int(fid2cid.max()) + 1,
+                           hp(keep["v_template"]), hp(keep["shapedirs"]), hp(keep["posedirs"]), hp(keep["Jreg"]), hp(keep["lbs"]),
+                           hp(keep["faces"]), hp(keep["faces_uv"]), hp(keep["vuv"]), hp(keep["lmk_f"]), hp(keep["lmk_b"]), hp(keep["adj"]),
+                           hp(keep["fid2cid"]), hp(keep["vf_ip"]), hp(keep["vf_f"]), hp(keep["lap_ip"]), hp(keep["lap_idx"]), hp(keep["lap_val"]))
+        self.ctx = C.c_void_p()
+        self._ck(self.L.vhap_ctx_create(C.byref(self.ctx), C.byref(md), self.T, self.dev.index or 0), None)
+        self.fid2cid = fid2cid
+        # ---- parameter slab (shared parameters first = the data-parallel allreduce slab)
+        self.layout: Dict[str, tuple] = {}
+        off = 0
+        for name, n in (("shape", model.n_shape), ("static_offset", 3 * V), ("lights", 27), ("focal_length", 1)):
+            self.layout[name] = (off, n)
+            off += n
+        self.n_shared = off
+        for name, d in PER_FRAME:
+            d = model.n_expr if d is None else d
+            self.layout[name] = (off, n_timesteps * d)
+            off += n_timesteps * d
+        self.n_small = off
+        z = lambda n: torch.zeros(n, dtype=torch.float32, device=self.dev)
+        self.slab, self.grad, self.m, self.v = z(off), z(off), z(off), z(off)
+        nt = 3 * self.T * self.T
+        self.tex_extra, self.tex_m, self.tex_v, self.tex_grad_dense = z(nt), z(nt), z(nt), None
+        self.p = {k: self.slab[o:o + n] for k, (o, n) in self.layout.items()}
+        self.g = {k: self.grad[o:o + n] for k, (o, n) in self.layout.items()}
+        self.p["lights"][0:3] = float(np.sqrt(4 * np.pi))                  # tracker.py:1301-1304
+        self.p["focal_length"][0] = 1.5                                     # tracker.py:1333
+        self.losses = z(_lib.N_LOSS)
+        self.slab_local, self.slab_global = z(8), z(8)
+        self.tex_painted = None
+        if tex_painted is not None:
+            self.tex_painted = torch.as_tensor(np.ascontiguousarray(tex_painted, np.float32), device=self.dev).reshape(-1)
+            self._ck(self.L.vhap_set_tex_painted(self.ctx, self.tex_painted.data_ptr(), self._stream()))
+        self.stage: Optional[StageConfig] = None
+        self.step_count = 0
+        self.global_step = 0
+        self.lr_scale = 1.0
+        self._inj = None
+        self.rebuild_texture()
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def _ck(self, r, _):
+        if r != 0:
+            raise RuntimeError("libvhap_b200: " + self.L.vhap_last_error(self.ctx).decode())
+
+    def close(self):
+        if self.ctx:
+            torch.cuda.synchronize(self.dev)
+            self.L.vhap_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def load_params(self, params: Dict[str, np.ndarray]):
+        for k, v in params.items():
+            t = torch.as_tensor(np.ascontiguousarray(v, np.float32)).reshape(-1).to(self.dev)
+            if k == "tex_extra":
+                self.tex_extra.copy_(t)
+            else:
+                self.p[k].copy_(t)
+        self.rebuild_texture()
+
+    def get_params(self) -> Dict[str, np.ndarray]:
+        out = {k: v.detach().cpu().numpy().copy() for k, v in self.p.items()}
+        out["tex_extra"] = self.tex_extra.cpu().numpy().reshape(3, self.T, self.T)
+        return out
+
+    def rebuild_texture(self):
+        self._ck(self.L.vhap_tex_rebuild(self.ctx, self.tex_extra.data_ptr(), self._stream()), None)
+
+    def reserve(self, B, H, W):
+        self._ck(self.L.vhap_ctx_reserve(self.ctx, B, H, W), None)
+
+    def _c_params(self) -> _lib.Params:
+        p = self.p
+        return _lib.Params(_ptr(p["shape"]), _ptr(p["expr"]), _ptr(p["rotation"]), _ptr(p["neck_pose"]), _ptr(p["jaw_pose"]), _ptr(p["eyes_pose"]),
+                           _ptr(p["translation"]), _ptr(p["static_offset"]), _ptr(p["lights"]),
+                           None if self.cfg.calibrated else _ptr(p["focal_length"]), _ptr(self.tex_extra), self.n_t)
+
+    def _c_grads(self, opt: dict) -> _lib.Grads:
+        g = self.g
+        on = lambda flag, t: _ptr(t) if flag else None
+        tex_ptr = self.L.vhap_tex_grad_ptr(self.ctx) if opt["texture"] else None
+        return _lib.Grads(on(opt["shape"], g["shape"]), on(opt["expr"], g["expr"]), on(opt["pose"], g["rotation"]), on(opt["joints"], g["neck_pose"]),
+                          on(opt["joints"], g["jaw_pose"]), on(opt["joints"], g["eyes_pose"]), on(opt["pose"], g["translation"]),
+                          on(opt["static_offset"], g["static_offset"]), on(opt["lights"], g["lights"]),
+                          on(opt["cam"] and not self.cfg.calibrated, g["focal_length"]), tex_ptr)
+
+    # ------------------------------------------------------------------ stages
+    def set_stage(self, stage, lr_scale: float = 1.0):
+        """begin of FlameTracker.optimize_stage (tracker.py:1391-1416): new Adam state, stage masks."""
+        if isinstance(stage, str):
+            stage = STAGES[stage]
+        self.stage = stage
+        self.lr_scale = lr_scale
+        self.step_count = 0
+        self.m.zero_(); self.v.zero_(); self.tex_m.zero_(); self.tex_v.zero_()
+        m, w = self.model, self.cfg.w
+        face_flags = np.zeros(self.F, np.uint8)
+        vert_flags = np.zeros(self.V, np.uint8)
+        if stage is not None:
+            face_flags[m.get_fid_by_region(list(stage.align_texture_except))] = 1
+            vert_flags[m.get_vid_by_region(list(stage.align_boundary_except))] = 1
+        w_off = np.ones(self.V, np.float32)
+        w_off[m.get_vid_by_region(list(w.reg_offset_relax_for))] *= w.reg_offset_relax_coef
+        w_lap = np.ones(self.V, np.float32)
+        w_lap[m.get_vid_by_region(list(w.reg_offset_lap_relax_for))] *= w.reg_offset_lap_relax_coef
+        ip, vids = [0], []
+        for r in w.reg_offset_rigid_for:
+            ids = m.get_vid_by_region([r])
+            vids.append(ids.astype(np.int32))
+            ip.append(ip[-1] + len(ids))
+        ip = np.asarray(ip, np.int32)
+        vids = np.concatenate(vids).astype(np.int32) if vids else np.zeros(0, np.int32)
+        mask = m.uvmask_res
+        if mask is None:
+            mask = np.zeros((self.T, self.T), bool)
+        if mask.shape[0] != self.T:
+            mask = mask[:: mask.shape[0] // self.T, :: mask.shape[1] // self.T]
+        mask = np.ascontiguousarray(mask.astype(np.uint8))
+        hp = lambda a: a.ctypes.data_as(C.c_void_p)
+        self._ck(self.L.vhap_set_stage_masks(self.ctx, hp(face_flags), hp(vert_flags), hp(w_off), hp(w_lap), hp(ip), hp(vids), len(ip) - 1, hp(mask)), None)
+
+    def _c_stage(self, training: bool) -> _lib.StageCfg:
+        w, st = self.cfg.w, self.stage
+        nz = lambda x: -1.0 if x is None else float(x)
+        s = _lib.StageCfg()
+        s.w_landmark, s.w_photo = nz(w.landmark), nz(w.photo)
+        s.w_reg_shape, s.w_reg_expr, s.w_reg_neck, s.w_reg_jaw, s.w_reg_eyes = w.reg_shape, w.reg_expr, w.reg_neck, w.reg_jaw, w.reg_eyes
+        w_tv = w.reg_tex_tv
+        if w_tv is not None:
+            w_tv = w_tv * self.cfg.scale_factor ** 2
+            if self.cfg.n_downsample_rgb is not None:
+                w_tv /= self.cfg.n_downsample_rgb ** 2
+        s.w_reg_tex_tv, s.w_reg_tex_res, s.w_reg_diffuse, s.w_reg_light = nz(w_tv), nz(w.reg_tex_res_clusters), nz(w.reg_diffuse), nz(w.reg_light)
+        s.w_reg_offset, s.w_reg_offset_lap, s.w_reg_offset_rigid = nz(w.reg_offset), nz(w.reg_offset_lap), nz(w.reg_offset_rigid)
+        s.w_smooth_trans, s.w_smooth_rot, s.w_smooth_neck, s.w_smooth_jaw = w.smooth_trans, w.smooth_rot, w.smooth_neck, w.smooth_jaw
+        s.w_smooth_eyes, s.w_smooth_expr = w.smooth_eyes, w.smooth_expr
+        train = training and st is not None
+        s.photometric = 1 if (st is None or st.photometric) else 0
+        s.jawline_off = 1 if (train and (not w.always_enable_jawline_landmarks) and st.disable_jawline_landmarks) else 0
+        s.tracking = 1 if (train and "tracking" in st.name) else 0
+        s.training = 1 if train else 0
+        opt = opt_dict_for(st) if train else {k: False for k in ("cam", "pose", "shape", "joints", "expr", "texture", "lights", "static_offset")}
+        s.opt_pose, s.opt_joints, s.opt_expr, s.opt_shape = int(opt["pose"]), int(opt["joints"]), int(opt["expr"]), int(opt["shape"])
+        s.opt_texture, s.opt_lights, s.opt_static_offset, s.opt_cam = int(opt["texture"]), int(opt["lights"]), int(opt["static_offset"]), int(opt["cam"])
+        bg = self.cfg.render.background_train if train else self.cfg.render.background_eval
+        if bg == "target":
+            s.bg_mode = 0
+        elif bg in ("white", "black"):
+            s.bg_mode = 1
+            s.bg_color[0] = s.bg_color[1] = s.bg_color[2] = 1.0 if bg == "white" else 0.0
+        else:
+            raise NotImplementedError(f"Unknown background mode: {bg}")                # tracker.py:302
+        if self.cfg.render.lighting_type != "SH":
+            raise NotImplementedError(f"Unknown lighting type: {self.cfg.render.lighting_type}")   # render_nvdiffrast.py:346
+        if self.cfg.render.lighting_space != "world":
+            raise NotImplementedError(f"Unknown lighting space: {self.cfg.render.lighting_space}")  # render_nvdiffrast.py:379
+        s.disturb_rate_fg = nz(self.cfg.render.disturb_rate_fg)
+        s.disturb_rate_bg = nz(self.cfg.render.disturb_rate_bg)
+        s.rng_seed, s.rng_step = 0x5EED5EED, self.global_step
+        s.shared_scale = 1.0 / self.world_size
+        return s
+
+    # ------------------------------------------------------------------ input staging
+    def stage_sample(self, rgb, lmk2d, timesteps, RT=None, K=None, non_blocking=True) -> Batch:
+        """rgb: [B,3,H,W] float (host or device, like sample['rgb']) or an already packed [B,H,W,4] fp16 tensor
+        (host pinned memory for the end-to-end path).  Returns device-resident Batch."""
+        if rgb.dtype == torch.float16 and rgb.dim() == 4 and rgb.shape[-1] == 4:
+            tgt = rgb.to(self.dev, non_blocking=non_blocking)
+            B, H, W = tgt.shape[:3]
+        else:
+            B, _, H, W = rgb.shape
+            r = rgb.to(self.dev, non_blocking=non_blocking)
+            tgt = torch.cat([r.permute(0, 2, 3, 1), torch.zeros(B, H, W, 1, device=self.dev, dtype=r.dtype)], -1).to(torch.float16).contiguous()
+        lm = torch.as_tensor(lmk2d, dtype=torch.float32).to(self.dev, non_blocking=non_blocking).contiguous()
+        ts = torch.as_tensor(np.asarray(timesteps), dtype=torch.int32).to(self.dev, non_blocking=non_blocking)
+        RTd = None if RT is None else torch.as_tensor(RT, dtype=torch.float32).to(self.dev).contiguous()
+        Kd = None if K is None else torch.as_tensor(K, dtype=torch.float32).to(self.dev).contiguous()
+        self.reserve(B, H, W)
+        return Batch(B, H, W, ts, tgt, lm, RTd, Kd)
+
+    def inject_random(self, w_fg, w_bg, u):
+        """test hook: fix the disturbance randomness (render_nvdiffrast.py:429-435,455)."""
+        if w_fg is None:
+            self._inj = None
+            self.L.vhap_set_injected_random(self.ctx, None, None)
+            return
+        wb = (w_fg.to(torch.uint8) | (w_bg.to(torch.uint8) << 1)).to(self.dev).contiguous()
+        uu = u.to(torch.float32).to(self.dev).contiguous()
+        self._inj = (wb, uu)
+        self.L.vhap_set_injected_random(self.ctx, wb.data_ptr(), uu.data_ptr())
+
+    # ------------------------------------------------------------------ energy / step
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def energy(self, batch: Batch, backward: bool = True, training: bool = True, global_B: Optional[int] = None, reduce_fn=None) -> torch.Tensor:
+        """compute_energy (+ backward).  Returns the loss vector (device tensor, see _lib.LOSS_NAMES).  With `reduce_fn`
+        (data parallel) the forward slab is reduced across ranks between the forward and backward halves."""
+        cs = self._c_stage(training)
+        cp = self._c_params()
+        train = training and self.stage is not None
+        opt = opt_dict_for(self.stage) if train else None
+        cg = self._c_grads(opt) if (backward and train) else None
+        s = self._stream()
+        gB = batch.B if global_B is None else global_B
+        self._ck(self.L.vhap_energy_forward(self.ctx, C.byref(cp), C.byref(batch.c), C.byref(cs), self.slab_local.data_ptr(), s), None)
+        if reduce_fn is not None:
+            reduce_fn(self.slab_local, self.slab_global)
+        else:
+            self.slab_global.copy_(self.slab_local)
+        self._ck(self.L.vhap_energy_backward(self.ctx, C.byref(cp), C.byref(batch.c), C.byref(cs), self.slab_global.data_ptr(),
+                                             self.slab_local.data_ptr(), gB, C.byref(cg) if cg is not None else None,
+                                             self.losses.data_ptr(), s), None)
+        self._last = (cs, opt)
+        return self.losses
+
+    def texture_grad_dense(self, training=True) -> torch.Tensor:
+        """Folds the texel-gradient pyramid (+ TV / residual regularisers) into a dense [3,T,T] gradient (no Adam)."""
+        if self.tex_grad_dense is None:
+            self.tex_grad_dense = torch.zeros(3 * self.T * self.T, dtype=torch.float32, device=self.dev)
+        cs = self._c_stage(training)
+        self._ck(self.L.vhap_tex_reg_fold_adam(self.ctx, self.tex_extra.data_ptr(), self.tex_grad_dense.data_ptr(), None, None, 0.0, 1,
+                                               C.byref(cs), 1.0, self.losses.data_ptr(), self._stream()), None)
+        return self.tex_grad_dense.view(3, self.T, self.T)
+
+    def _lr(self, name):
+        lr = self.cfg.lr                                                    # tracker.py:159-211
+        table = {"translation": lr.translation, "expr": lr.expr, "lights": lr.light, "focal_length": lr.camera, "static_offset": lr.static_offset}
+        return table.get(name, lr.base) * self.lr_scale
+
+    def adam_step(self, allreduce_fn=None):
+        """torch.optim.Adam.step() over the parameter groups of the current stage (dense rows, tracker.py:1284-1293,210)."""
+        opt = opt_dict_for(self.stage)
+        self.step_count += 1
+        s = self._stream()
+        groups = []
+        if opt["shape"]: groups.append("shape")
+        if opt["static_offset"]: groups.append("static_offset")
+        if opt["lights"]: groups.append("lights")
+        if opt["cam"] and not self.cfg.calibrated: groups.append("focal_length")
+        if opt["expr"]: groups.append("expr")
+        if opt["pose"]: groups += ["rotation", "translation"]
+        if opt["joints"]: groups += ["neck_pose", "jaw_pose", "eyes_pose"]
+        cs = self._c_stage(True)
+        if opt["texture"]:
+            if allreduce_fn is None:
+                self._ck(self.L.vhap_tex_reg_fold_adam(self.ctx, self.tex_extra.data_ptr(), None, self.tex_m.data_ptr(), self.tex_v.data_ptr(),
+                                                       self._lr("tex"), self.step_count, C.byref(cs), 1.0, self.losses.data_ptr(), s), None)
+            else:
+                g = self.texture_grad_dense()
+                allreduce_fn(g)
+                self._ck(self.L.vhap_adam(self.ctx, self.tex_extra.data_ptr(), g.data_ptr(), self.tex_m.data_ptr(), self.tex_v.data_ptr(),
+                                          g.numel(), self._lr("tex"), self.step_count, s), None)
+                self.rebuild_texture()
+        if allreduce_fn is not None:
+            allreduce_fn(self.grad)
+        for name in groups:
+            o, n = self.layout[name]
+            self._ck(self.L.vhap_adam(self.ctx, self.slab[o:o + n].data_ptr(), self.grad[o:o + n].data_ptr(), self.m[o:o + n].data_ptr(),
+                                      self.v[o:o + n].data_ptr(), n, self._lr(name), self.step_count, s), None)
+
+    def step(self, batch: Batch) -> torch.Tensor:
+        """One optimisation iteration (tracker.py:1418-1435): zero_grad, energy + backward, Adam."""
+        self.zero_grad()
+        losses = self.energy(batch, backward=True, training=True)
+        self.adam_step()
+        self.global_step += 1
+        return losses
+
+    # ------------------------------------------------------------------ logging planes (render_out dict)
+    def render_planes(self, batch: Batch, training=False) -> Dict[str, torch.Tensor]:
+        self.L.vhap_set_want_planes(self.ctx, 1)
+        self.energy(batch, backward=False, training=training)
+        self.L.vhap_set_want_planes(self.ctx, 0)
+        out = {}
+        for which, name in ((0, "rgba"), (1, "rgba_pre"), (2, "albedo"), (3, "normal"), (4, "diffuse"), (5, "cid")):
+            t = torch.empty(batch.B, batch.H, batch.W, 4, dtype=torch.float32, device=self.dev)
+            self._ck(self.L.vhap_get_plane(self.ctx, which, t.data_ptr(), self._stream()), None)
+            out[name] = t
+        return out
+
+    def loss_dict(self) -> Dict[str, float]:
+        v = self.losses.cpu().numpy()
+        return {n: float(v[i]) for i, n in enumerate(_lib.LOSS_NAMES)}
