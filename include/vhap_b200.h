@@ -129,6 +129,15 @@ int vhap_flame_backward(vhap_ctx* ctx, const vhap_params* p, const vhap_frame_ba
 int vhap_project(vhap_ctx* ctx, const vhap_params* p, const vhap_frame_batch* fb, const float* verts /*[B,V,3]*/,
                  float* verts_clip /*[B,V,4]*/, void* stream);
 
+/* adjoint of vhap_project: g_verts [B,V,3] += J^T g_clip, g_focal[0] += d/d focal_length (NULL to skip) */
+int vhap_project_backward(vhap_ctx* ctx, const vhap_params* p, const vhap_frame_batch* fb, const float* verts, const float* g_clip /*[B,V,4]*/,
+                          float* g_verts, float* g_focal, void* stream);
+
+/* ---- vertex normals (replaces NVDiffRenderer.compute_v_normals, render_nvdiffrast.py:297-316) ---------------- */
+int vhap_vertex_normals(vhap_ctx* ctx, const float* verts /*[B,V,3]*/, int32_t B, float* vnorm /*[B,V,3]*/, void* stream);
+int vhap_vertex_normals_backward(vhap_ctx* ctx, const float* verts, const float* g_vnorm /*[B,V,3]*/, int32_t B, float* g_verts /*[B,V,3], +=*/,
+                                 void* stream);
+
 /* ---- rasterise (replaces dr.rasterize at render_nvdiffrast.py:254) ---------------------------------------- */
 /* tri_id [B,H,W] int32 (triangle+1, 0 empty, row 0 = bottom); rast/rast_db [B,H,W,4] float (NULL to skip). */
 int vhap_rasterize(vhap_ctx* ctx, const float* verts_clip /*[B,V,4]*/, int32_t B, int32_t H, int32_t W,
@@ -150,6 +159,13 @@ int vhap_energy_forward(vhap_ctx* ctx, const vhap_params* p, const vhap_frame_ba
 int vhap_energy_backward(vhap_ctx* ctx, const vhap_params* p, const vhap_frame_batch* fb, const vhap_stage_cfg* cfg,
                          const float* reduce_slab /* cross-rank reduced */, const float* local_slab /* this rank's own */,
                          int32_t global_B, const vhap_grads* g, float* losses_out, void* stream);
+
+/* modular form: rasterise + render_rgba + photometric energy (+reg_diffuse) from caller-provided clip positions and vertex
+ * normals, and the analytic backward to them (NVDiffRenderer.rasterize/render_rgba, render_nvdiffrast.py:216-245,354-484;
+ * compute_photometric_energy, tracker.py:391-478).  Gradient outputs are overwritten; any may be NULL. */
+int vhap_render_photometric(vhap_ctx* ctx, const vhap_params* p, const vhap_frame_batch* fb, const vhap_stage_cfg* cfg,
+                            const float* verts_clip /*[B,V,4]*/, const float* vnorm /*[B,V,3]*/, float* losses_out,
+                            float* g_clip /*[B,V,4]*/, float* g_vnorm /*[B,V,3]*/, float* g_lights /*[27]*/, float* g_tex_pyramid, void* stream);
 
 /* debug / logging planes of the last forward (render_out dict, render_nvdiffrast.py:476-483), image orientation.
  * which: 0 rgba (after AA), 1 rgba before AA, 2 albedo, 3 normal, 4 diffuse, 5 cid.  out [B,H,W,4] float. */

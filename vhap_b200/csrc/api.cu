@@ -409,6 +409,116 @@ extern "C" int vhap_adam(vhap_ctx* ctx, float* param, const float* grad, float* 
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------- modular entry points
+__global__ void k_3to4(const float* __restrict__ a, float* __restrict__ b, size_t n, float w) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  b[i * 4] = a[i * 3]; b[i * 4 + 1] = a[i * 3 + 1]; b[i * 4 + 2] = a[i * 3 + 2]; b[i * 4 + 3] = w;
+}
+__global__ void k_4to3_add(const float* __restrict__ a, float* __restrict__ b, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  b[i * 3] += a[i * 4]; b[i * 3 + 1] += a[i * 4 + 1]; b[i * 3 + 2] += a[i * 4 + 2];
+}
+__global__ void k_4to3(const float* __restrict__ a, float* __restrict__ b, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  b[i * 3] = a[i * 4]; b[i * 3 + 1] = a[i * 4 + 1]; b[i * 3 + 2] = a[i * 4 + 2];
+}
+#define GRID1(n) (unsigned)(((n) + 255) / 256), 256
+
+// compute_v_normals (render_nvdiffrast.py:297-316)
+extern "C" int vhap_vertex_normals(vhap_ctx* ctx, const float* verts, int32_t B, float* vnorm, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  vhap_frame_batch fb; memset(&fb, 0, sizeof(fb)); fb.B = B; fb.H = ctx->maxH; fb.W = ctx->maxW;
+  if (check_batch(ctx, &fb)) return -4;
+  size_t n = (size_t)B * ctx->V;
+  k_3to4<<<GRID1(n), 0, s>>>(verts, (float*)ctx->verts, n, 1.f);
+  launch_vnormals(ctx, B, s);
+  k_4to3<<<GRID1(n), 0, s>>>((const float*)ctx->vnorm, vnorm, n);
+  LAST();
+  return 0;
+}
+// adjoint: g_verts += d(vnorm)/d(verts)^T g_vnorm
+extern "C" int vhap_vertex_normals_backward(vhap_ctx* ctx, const float* verts, const float* g_vnorm, int32_t B, float* g_verts, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  size_t n = (size_t)B * ctx->V;
+  k_3to4<<<GRID1(n), 0, s>>>(verts, (float*)ctx->verts, n, 1.f);
+  launch_vnormals(ctx, B, s);
+  k_3to4<<<GRID1(n), 0, s>>>(g_vnorm, ctx->g_vnorm, n, 0.f);
+  cudaMemsetAsync(ctx->g_verts, 0, n * 4 * sizeof(float), s);
+  launch_vnormals_bwd(ctx, B, s);
+  k_4to3_add<<<GRID1(n), 0, s>>>(ctx->g_verts, g_verts, n);
+  LAST();
+  return 0;
+}
+
+__global__ void k_project_bwd(const float* __restrict__ verts, const float* __restrict__ g_clip, const CamParams* __restrict__ cam, int V, int H, int W,
+                              float* __restrict__ g_verts, float* __restrict__ g_fxfy /* [2] accumulators */) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (v >= V) return;
+  const float* p = verts + ((size_t)b * V + v) * 3;
+  const float* g = g_clip + ((size_t)b * V + v) * 4;
+  CamParams c = cam[b];
+  float p00 = c.fx * 2.f / W, p11 = c.fy * 2.f / H, p02 = (W - 2.f * c.cx) / W, p12 = (H - 2.f * c.cy) / H, p22 = -(10.f + 0.1f) / (10.f - 0.1f);
+  float cx_ = c.RT[0] * p[0] + c.RT[1] * p[1] + c.RT[2] * p[2] + c.RT[3];
+  float cy_ = c.RT[4] * p[0] + c.RT[5] * p[1] + c.RT[6] * p[2] + c.RT[7];
+  float g_cx = p00 * g[0], g_cy = p11 * g[1], g_cz = p02 * g[0] + p12 * g[1] + p22 * g[2] - g[3];
+  float* o = g_verts + ((size_t)b * V + v) * 3;
+  o[0] += c.RT[0] * g_cx + c.RT[4] * g_cy + c.RT[8] * g_cz;
+  o[1] += c.RT[1] * g_cx + c.RT[5] * g_cy + c.RT[9] * g_cz;
+  o[2] += c.RT[2] * g_cx + c.RT[6] * g_cy + c.RT[10] * g_cz;
+  if (g_fxfy) { atomicAdd(g_fxfy, g[0] * cx_ * (2.f / W)); atomicAdd(g_fxfy + 1, g[1] * cy_ * (2.f / H)); }
+}
+// adjoint of vhap_project: g_verts += ..., g_focal += ... (uncalibrated camera, tracker.py:141-157)
+extern "C" int vhap_project_backward(vhap_ctx* ctx, const vhap_params* p, const vhap_frame_batch* fb, const float* verts, const float* g_clip,
+                                     float* g_verts, float* g_focal, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (check_batch(ctx, fb)) return -4;
+  launch_cam_setup(ctx, p, fb, s);
+  cudaMemsetAsync(ctx->acc, 0, ACC_COUNT * sizeof(float), s);
+  dim3 g((ctx->V + 127) / 128, fb->B);
+  k_project_bwd<<<g, 128, 0, s>>>(verts, g_clip, ctx->cam, ctx->V, fb->H, fb->W, g_verts, g_focal ? ctx->acc + ACC_GFX : nullptr);
+  if (g_focal) {
+    vhap_stage_cfg dummy; memset(&dummy, 0, sizeof(dummy));
+    k_assemble_losses<<<1, 32, 0, s>>>(ctx->acc, dummy, (float)(fb->H > fb->W ? fb->H : fb->W), g_focal, 1, nullptr);
+  }
+  LAST();
+  return 0;
+}
+
+// rasterise + render_rgba + photometric energy (+ reg_diffuse) from caller-provided clip positions and vertex normals, with the
+// analytic backward to them: the modular form of NVDiffRenderer.rasterize/render_rgba (render_nvdiffrast.py:216-245,354-484)
+// + compute_photometric_energy (tracker.py:391-478).  g_* outputs are overwritten (not accumulated); any may be NULL.
+extern "C" int vhap_render_photometric(vhap_ctx* ctx, const vhap_params* p, const vhap_frame_batch* fb, const vhap_stage_cfg* cfg,
+                                       const float* verts_clip, const float* vnorm, float* losses_out, float* g_clip, float* g_vnorm,
+                                       float* g_lights, float* g_tex_pyramid, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (check_batch(ctx, fb)) return -4;
+  size_t n = (size_t)fb->B * ctx->V;
+  cudaMemsetAsync(ctx->acc, 0, ACC_COUNT * sizeof(float), s);
+  zero_backward_scratch(ctx, fb->B, s);
+  cudaMemcpyAsync(ctx->clip, verts_clip, n * 4 * sizeof(float), cudaMemcpyDeviceToDevice, s);
+  k_3to4<<<GRID1(n), 0, s>>>(vnorm, (float*)ctx->vnorm, n, 0.f);
+  launch_raster(ctx, ctx->clip, ctx->snap, fb->B, fb->H, fb->W, ctx->tri_id, 0, 1, s);
+  PassArgs P;
+  fill_render_args(ctx, P, fb, cfg, p->lights);
+  launch_render_forward(ctx, P, s);
+  float* slab = ctx->scal + 8;
+  launch_forward_slab(ctx, P, p->lights, slab, s);
+  if (g_lights) cudaMemsetAsync(g_lights, 0, 27 * sizeof(float), s);
+  launch_finalize(ctx, P, cfg, slab, slab, fb->B, p->lights, g_lights, s);
+  if (g_clip || g_vnorm || g_lights || g_tex_pyramid) {
+    P.g_tex = g_tex_pyramid;
+    launch_render_backward(ctx, P, cfg, p->lights, g_lights, nullptr, s);
+    if (g_clip) cudaMemcpyAsync(g_clip, ctx->g_clip, n * 4 * sizeof(float), cudaMemcpyDeviceToDevice, s);
+    if (g_vnorm) k_4to3<<<GRID1(n), 0, s>>>(ctx->g_vnorm, g_vnorm, n);
+  }
+  k_assemble_losses<<<1, 32, 0, s>>>(ctx->acc, *cfg, 0.f, nullptr, 0, losses_out);
+  LAST();
+  return 0;
+}
+
 extern "C" int vhap_overflow_flag(vhap_ctx* ctx, int32_t* out_host) {
   CK(cudaMemcpy(out_host, ctx->overflow_flag, sizeof(int), cudaMemcpyDeviceToHost));
   return 0;

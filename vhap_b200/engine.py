@@ -103,7 +103,7 @@ class Engine:
     def _stream(self):
         return torch.cuda.current_stream(self.dev).cuda_stream
 
-    def _ck(self, r, _):
+    def _ck(self, r, _=None):
         if r != 0:
             raise RuntimeError("libvhap_b200: " + self.L.vhap_last_error(self.ctx).decode())
 

@@ -71,7 +71,12 @@ def landmarks_px(lmks_ndc_flipped: np.ndarray, H: int, W: int, seed: int = 0, no
     rng = np.random.default_rng(seed + 5)
     x = (lmks_ndc_flipped[:, :68, 0] * 0.5 + 0.5) * W
     y = (lmks_ndc_flipped[:, :68, 1] * 0.5 + 0.5) * H
-    x = x + rng.normal(0, noise_px, x.shape)
-    y = y + rng.normal(0, noise_px, y.shape)
+    # keep every residual at least 0.2 noise_px away from 0: the L1 landmark energy has a kink there and fp32 / fp64
+    # would legitimately disagree on the sign of the gradient
+    nx, ny = rng.normal(0, noise_px, x.shape), rng.normal(0, noise_px, y.shape)
+    nx = np.where(np.abs(nx) < 0.2 * noise_px, np.where(nx < 0, -0.2, 0.2) * noise_px, nx)
+    ny = np.where(np.abs(ny) < 0.2 * noise_px, np.where(ny < 0, -0.2, 0.2) * noise_px, ny)
+    x = x + nx
+    y = y + ny
     conf = rng.uniform(0.6, 1.0, x.shape)
     return np.stack([x, y, conf], -1).astype(np.float32)
