@@ -170,6 +170,8 @@ int vhap_render_photometric(vhap_ctx* ctx, const vhap_params* p, const vhap_fram
 /* debug / logging planes of the last forward (render_out dict, render_nvdiffrast.py:476-483), image orientation.
  * which: 0 rgba (after AA), 1 rgba before AA, 2 albedo, 3 normal, 4 diffuse, 5 cid.  out [B,H,W,4] float. */
 int vhap_get_plane(vhap_ctx* ctx, int32_t which, float* out, void* stream);
+/* the engine's own geometry of the last forward: which = 0 world vertices, 1 clip positions, 2 vertex normals; out [B,V,4] */
+int vhap_get_geometry(vhap_ctx* ctx, int32_t which, float* out, void* stream);
 int vhap_set_want_planes(vhap_ctx* ctx, int32_t on);   /* make the next forward keep the logging planes */
 int vhap_overflow_flag(vhap_ctx* ctx, int32_t* out_host);   /* 1 if a raster tile list overflowed its capacity (synchronises) */
 /* test hook: inject the disturbance randomness (w bits: bit0 = w_fg, bit1 = w_bg; u in [0,1)); NULL = Philox. */

@@ -156,3 +156,55 @@ def test_project_forward_backward(setup):
     e._ck(e.L.vhap_project_backward(e.ctx, C.byref(cp), C.byref(batch.c), dv.data_ptr(), dg.data_ptr(), gv.data_ptr(), gf.data_ptr(), e._stream()))
     assert rel(gv.cpu().numpy(), v.grad.numpy()) < 1e-5
     assert abs(gf.item() - f.grad.item()) < 1e-4 * abs(f.grad.item())
+
+
+def test_fused_path_equals_modular_chain(setup):
+    """The fused compute_energy backward must equal the chain of separately oracle-verified modular pieces evaluated on
+    the engine's OWN fp32 geometry: render_photometric -> project_backward + vertex_normals_backward -> flame_backward."""
+    import copy
+    from vhap_b200.config import STAGES
+    e, sc, _, _, _ = setup
+    B, H, W, V = sc["B"], sc["H"], sc["W"], e.V
+    cfg_save = e.cfg
+    e.cfg = copy.deepcopy(cfg_save)
+    w = e.cfg.w
+    w.landmark = None; w.reg_tex_tv = None; w.reg_tex_res_clusters = None
+    w.reg_shape = w.reg_expr = w.reg_neck = w.reg_jaw = w.reg_eyes = 0.0
+    w.reg_offset = w.reg_offset_lap = w.reg_offset_rigid = None
+    w.smooth_trans = w.smooth_rot = w.smooth_neck = w.smooth_jaw = w.smooth_eyes = w.smooth_expr = 0.0
+    e.load_params(sc["params"])
+    e.set_stage(STAGES["rgb_global_tracking"])
+    e.inject_random(sc["w_fg"], sc["w_bg"], sc["u_rand"])
+    batch = e.stage_sample(sc["rgb16"].to(torch.float32), sc["lmk2d"], sc["ts"])
+    e.zero_grad()
+    e.energy(batch, backward=True, training=True)
+    fused = {k: v.clone() for k, v in e.g.items()}
+    geo = []
+    for which in range(3):
+        t = torch.empty(B, V, 4, device=e.dev)
+        e._ck(e.L.vhap_get_geometry(e.ctx, which, t.data_ptr(), e._stream()))
+        geo.append(t)
+    verts3 = geo[0][..., :3].contiguous(); clip = geo[1].contiguous(); vn3 = geo[2][..., :3].contiguous()
+    e.texture_grad_dense()         # drain the texel-gradient pyramid
+    cs, cp = e._c_stage(True), e._c_params()
+    g_clip = torch.zeros(B, V, 4, device=e.dev); g_vn = torch.zeros(B, V, 3, device=e.dev); g_l = torch.zeros(27, device=e.dev)
+    e._ck(e.L.vhap_render_photometric(e.ctx, C.byref(cp), C.byref(batch.c), C.byref(cs), clip.data_ptr(), vn3.data_ptr(), e.losses.data_ptr(),
+                                      g_clip.data_ptr(), g_vn.data_ptr(), g_l.data_ptr(), None, e._stream()))
+    g_verts = torch.zeros(B, V, 3, device=e.dev); g_f = torch.zeros(1, device=e.dev)
+    e._ck(e.L.vhap_project_backward(e.ctx, C.byref(cp), C.byref(batch.c), verts3.data_ptr(), g_clip.data_ptr(), g_verts.data_ptr(), g_f.data_ptr(), e._stream()))
+    e._ck(e.L.vhap_vertex_normals_backward(e.ctx, verts3.data_ptr(), g_vn.data_ptr(), B, g_verts.data_ptr(), e._stream()))
+    e.zero_grad()
+    opt = {k: True for k in ("cam", "pose", "shape", "joints", "expr", "texture", "lights", "static_offset")}
+    opt["texture"] = False
+    cg = e._c_grads(opt)
+    # flame_forward must be re-run: render_photometric reused the ctx geometry buffers
+    e._ck(e.L.vhap_flame_forward(e.ctx, C.byref(cp), C.byref(batch.c), None, None, None, e._stream()))
+    e._ck(e.L.vhap_flame_backward(e.ctx, C.byref(cp), C.byref(batch.c), g_verts.data_ptr(), None, C.byref(cg), e._stream()))
+    torch.cuda.synchronize()
+    errs = {k: rel(fused[k].cpu().numpy(), e.g[k].cpu().numpy()) for k in ("shape", "expr", "rotation", "translation", "neck_pose", "jaw_pose",
+                                                                            "eyes_pose", "static_offset")}
+    errs["lights"] = rel(fused["lights"].cpu().numpy(), g_l.cpu().numpy())
+    errs["focal_length"] = abs(fused["focal_length"].item() - g_f.item()) / abs(g_f.item())
+    print("fused vs modular chain", {k: float("%.3g" % v) for k, v in errs.items()})
+    e.cfg = cfg_save
+    assert all(v < 1e-4 for v in errs.values()), errs

@@ -519,6 +519,13 @@ extern "C" int vhap_render_photometric(vhap_ctx* ctx, const vhap_params* p, cons
   return 0;
 }
 
+// copies the engine's own geometry of the last forward: which = 0 world vertices [B,V,4], 1 clip positions [B,V,4], 2 vertex normals [B,V,4]
+extern "C" int vhap_get_geometry(vhap_ctx* ctx, int32_t which, float* out, void* stream) {
+  const void* src = which == 0 ? (const void*)ctx->verts : (which == 1 ? (const void*)ctx->clip : (const void*)ctx->vnorm);
+  CK(cudaMemcpyAsync(out, src, (size_t)ctx->curB * ctx->V * 4 * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
 extern "C" int vhap_overflow_flag(vhap_ctx* ctx, int32_t* out_host) {
   CK(cudaMemcpy(out_host, ctx->overflow_flag, sizeof(int), cudaMemcpyDeviceToHost));
   return 0;
