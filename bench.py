@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- photometric tracking throughput of the B200 engine (BASELINE.json metric: frames x iterations / second).
+
+A "step" is one optimisation iteration of FlameTracker.optimize_iter (vhap/model/tracker.py:1418-1435) in stage
+`rgb_global_tracking` (every parameter group optimised, base.py:291-295): FLAME forward -> landmark energy -> rasterise ->
+shade -> disturbance + antialias + L1 -> analytic backward -> regularisers -> Adam (2048^2 texture included), on one batch
+of synthetic frames.  Workload at N GPUs: configs[1] "monocular 512x512 batch_size=16 photometric tracking" PER GPU (weak
+scaling: global batch 16 N, frames sharded one shard per rank, one NCCL allreduce of the shared-parameter gradients per
+Adam step).  `--size 1024` selects the 1024^2 variant.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+`--impl reference` times the CPU restatement of the reference's path (oracle/, kind "port": the reference's own GPU path
+needs nvdiffrast, absent here) on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "photometric frames*iters/sec"
+UNIT = "frame*iter/s"
+
+
+def peaks():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        d = json.loads(f.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """samples nvidia-smi during the timed region (B200_PROFILING.md clocks line)"""
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def build_workload(size, B, n_batches, rank, seed=0):
+    """Synthetic tracking inputs: real FLAME topology, seeded smooth bases, per-frame parameters, procedural
+    2048^2 texture; targets = the engine's own render of a perturbed parameter set (+ noise), stored fp16 RGBA."""
+    from vhap_b200 import synth
+    from vhap_b200.config import EngineConfig
+    from vhap_b200.flame_model import FlameModelData
+    from vhap_b200.engine import Engine
+    m = FlameModelData.synthetic()
+    cfg = EngineConfig()
+    n_t = B * n_batches
+    dev = f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}"
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    eng = Engine(m, cfg, n_t, device=dev, tex_painted=synth.procedural_texture(cfg.tex_resolution, seed), world_size=world)
+    # "ground truth" parameters -> target images and landmarks, rendered by the engine in evaluation mode
+    gt = synth.init_params(m, n_t, cfg.tex_resolution, seed=seed + 100 + rank)
+    eng.load_params(gt)
+    eng.set_stage(None)
+    H = W = size
+    batches = []
+    rng = np.random.default_rng(seed + rank)
+    for i in range(n_batches):
+        ts = np.arange(i * B, (i + 1) * B)
+        blank = torch.zeros(B, H, W, 4, dtype=torch.float16)
+        bt = eng.stage_sample(blank, np.zeros((B, 68, 3), np.float32), ts)
+        # render with a white background, then use it (plus noise) as the target
+        eng.cfg.render.background_eval = "white"
+        planes = eng.render_planes(bt, training=False)
+        eng.cfg.render.background_eval = "target"
+        rgb = planes["rgba"][..., :3].clamp(0, 1)
+        rgb = (rgb + 0.02 * torch.randn_like(rgb)).clamp(0, 1)
+        tgt = torch.cat([rgb, torch.ones_like(rgb[..., :1])], -1).to(torch.float16).cpu()
+        lm = torch.empty(B, 70, 3, device=eng.dev)
+        cp = eng._c_params()
+        eng._ck(eng.L.vhap_flame_forward(eng.ctx, C.byref(cp), C.byref(bt.c), None, None, lm.data_ptr(), eng._stream()))
+        # project landmarks like world_to_ndc(flip_y=True) with the default camera
+        f = 1.5 * max(H, W)
+        l = lm.cpu().numpy()
+        z = -(l[..., 2] - 1.0)
+        ndc = np.stack([(2 * f / W) * l[..., 0] / z, -(2 * f / H) * l[..., 1] / z], -1)
+        lmk2d = synth.landmarks_px(ndc, H, W, seed + i)
+        batches.append((tgt.pin_memory(), torch.tensor(lmk2d).pin_memory(), torch.tensor(ts, dtype=torch.int32).pin_memory()))
+        fg = float((planes["cid"][..., 1] > 0).float().mean())
+    # start the optimisation from a perturbed parameter set
+    start = synth.init_params(m, n_t, cfg.tex_resolution, seed=seed + 100 + rank)
+    prng = np.random.default_rng(seed + 7 + rank)
+    for k in ("shape", "expr", "rotation", "neck_pose", "jaw_pose", "eyes_pose", "translation"):
+        start[k] = (start[k] + prng.normal(0, 0.02, start[k].shape) * (0.2 if k == "translation" else 1.0)).astype(np.float32)
+    start["tex_extra"] = np.zeros_like(start["tex_extra"])
+    start["static_offset"] = np.zeros_like(start["static_offset"])
+    eng.load_params(start)
+    eng.set_stage("rgb_global_tracking", lr_scale=0.1)              # tracker.py:1385
+    return eng, batches, fg
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    B, size = args.batch, args.size
+    n_batches = 4
+    eng, batches, fg = build_workload(size, B, n_batches, rank)
+    dev = eng.dev
+    gB = B * world
+    resident = [eng.stage_sample(t, l, ts.numpy()) for (t, l, ts) in batches]
+
+    def reduce_slab(local_slab, out):
+        out.copy_(local_slab)
+        if world > 1:
+            s = out[:3].clone(); dist.all_reduce(s); out[:3] = s
+            mx = out[3:4].clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX); out[3:4] = mx
+
+    def allreduce(t):
+        if world > 1:
+            dist.all_reduce(t)
+
+    def one_step(batch):
+        eng.zero_grad()
+        eng.energy(batch, backward=True, training=True, global_B=gB, reduce_fn=reduce_slab if world > 1 else None)
+        eng.adam_step(allreduce_fn=allreduce if world > 1 else None)
+        eng.global_step += 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing
+    for i in range(args.warmup):
+        one_step(resident[i % n_batches])
+    barrier()
+    eng.L.vhap_profile_enable(eng.ctx, 1)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        one_step(resident[i % n_batches])
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    nk = eng.L.vhap_profile_kernel_count()
+    avg = (C.c_float * nk)(); cnt = (C.c_uint64 * nk)()
+    eng.L.vhap_profile_read(eng.ctx, avg, cnt)
+    eng.L.vhap_profile_enable(eng.ctx, 0)
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    losses = eng.loss_dict()
+
+    # ---------------- end to end: pinned host -> device copy of every step's inputs + device -> host read of the loss
+    host_loss = torch.empty(24, dtype=torch.float32).pin_memory()
+    for i in range(min(args.warmup, 3)):
+        t_, l_, ts_ = batches[i % n_batches]
+        one_step(eng.stage_sample(t_, l_, ts_.numpy()))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        t_, l_, ts_ = batches[i % n_batches]
+        bt = eng.stage_sample(t_, l_, ts_.numpy())          # H2D from pinned memory on the compute stream
+        one_step(bt)
+        host_loss.copy_(eng.losses, non_blocking=True)      # D2H of the step's loss vector
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    t = torch.tensor([ms_e2e], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t.item())
+    h2d = batches[0][0].numel() * 2 + batches[0][1].numel() * 4 + batches[0][2].numel() * 4
+    d2h = 24 * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    names = [eng.L.vhap_profile_kernel_name(k).decode() for k in range(nk)]
+    per_step = {names[k]: float(avg[k]) * cnt[k] / args.steps for k in range(nk) if cnt[k]}
+    launches = int(sum(cnt[k] for k in range(nk)))
+    P = B * size * size
+    peak, peak_src = peaks()
+    # algorithmic bytes per launch (SURVEY.md 8d / DESIGN.md "Roofline"): fused backward = 20 B/px read + 30 rho B/px texel RMW
+    algo = {
+        "passC_backward": P * (20 + 30 * fg),
+        "passB_disturb_aa_loss": P * 20,
+        "passA_shade": P * (4 + (16 + 15) * fg),
+        "fine_raster": P * 4,
+        "tex_fold_reg_adam": 3 * 2048 * 2048 * 4 * 7 + 2048 * 2048 * 16,
+    }
+    dom = max(per_step, key=per_step.get)
+    dom_avg = float(avg[names.index(dom)])
+    kern = {k: {"ms_per_step": round(v, 4), "share": round(v / (ms / args.steps), 3)} for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])[:12]}
+    roof_k = dom if dom in algo else "passC_backward"
+    k_avg = float(avg[names.index(roof_k)])
+    ach = algo[roof_k] / (k_avg * 1e-3) / 1e9 if k_avg > 0 else 0.0
+    out = {
+        "metric": METRIC, "value": round(gB * args.steps / (ms * 1e-3), 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic (real FLAME topology, seeded bases, procedural 2048^2 texture, engine-rendered targets + noise, fp16 RGBA)",
+        "config": {"workload": f"monocular {size}x{size} batch_size={B} per GPU photometric tracking (BASELINE configs[{1 if size == 512 else 3}]), "
+                               f"stage rgb_global_tracking, Adam on all groups incl. 2048^2 texture",
+                   "global_batch": gB, "image": [size, size], "tex": 2048, "foreground_fraction": round(fg, 3),
+                   "parallelism": f"dp{world} frame-sharded, 1 allreduce(shared grads)+1 allreduce(texture grad) per step" if world > 1 else "single GPU",
+                   "l2": "inputs larger than L2: 4 rotating batches; per-step working set ~0.7 GB (texture, Adam state, targets)"},
+        "e2e": {"value": round(gB * args.steps / (ms_e2e * 1e-3), 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": round(ms_e2e / args.steps, 4)},
+        "gpu_launches": launches,
+        "clocks": clk,
+        "roofline": {"bound": "hbm", "kernel": roof_k, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
+                     "traffic": None, "peak_source": peak_src, "avg_launch_ms": round(k_avg, 4),
+                     "algorithmic_bytes_per_launch": int(algo[roof_k]), "dominant_kernel": dom, "dominant_avg_ms": round(dom_avg, 4)},
+        "kernels": kern,
+        "losses": {k: round(v, 5) for k, v in losses.items() if k in ("total", "photo", "lmk")},
+    }
+    if not args.no_cpu and world == 1:
+        out["cpu_baseline"] = cpu_baseline(size, sample_frames=1)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(size, sample_frames=1, steps=1):
+    """The oracle (CPU port of the reference's path) timed on this box's host cores, bounded sample: `sample_frames` frame(s)
+    at size^2 with a 512^2 texture stand-in? no -- the full 2048^2 texture, one full iteration (energy + backward + Adam)."""
+    from oracle import energy as E, lbs as L, camera as Cm
+    from vhap_b200 import synth
+    from vhap_b200.config import EngineConfig, STAGES
+    from vhap_b200.flame_model import FlameModelData
+    torch.set_num_threads(os.cpu_count())
+    m = FlameModelData.synthetic()
+    cfg = EngineConfig()
+    T = cfg.tex_resolution
+    dt = torch.float32
+    model = L.model_tensors(m, dt)
+    B, H, W = sample_frames, size, size
+    p = synth.init_params(m, B, T, seed=100)
+    P = {k: torch.tensor(v, dtype=dt, requires_grad=True) for k, v in p.items()}
+    rgb = torch.tensor(synth.procedural_image(B, H, W)).to(torch.float16).to(dt)
+    ts = np.arange(B)
+    lmk2d = torch.zeros(B, 68, 3)
+    lmk2d[..., :2] = size / 2
+    lmk2d[..., 2] = 1
+    g = torch.Generator().manual_seed(0)
+    dist_ = dict(w_fg=torch.rand(B, H, W, generator=g) < 0.5, w_bg=torch.rand(B, H, W, generator=g) < 0.5, u_rand=torch.rand(B, H, W, generator=g))
+    tp = torch.tensor(synth.procedural_texture(T), dtype=dt)
+    sample = dict(rgb=rgb, lmk2d=lmk2d, timestep_index=ts)
+    lap = E.laplacian_dense(m, dt)
+    opt = torch.optim.Adam([v for v in P.values()], lr=5e-3)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        opt.zero_grad()
+        Et, _ = E.compute_energy(P, sample, STAGES["rgb_global_tracking"], cfg, m, model, lap=lap, disturbance=dist_, tex_painted=tp)
+        Et.backward()
+        opt.step()
+    dtm = time.perf_counter() - t0
+    # configs[0]: landmark-only FLAME fit stage on CPU, 1 frame 256x256 (plumbing baseline the north star asks for)
+    p1 = synth.init_params(m, 1, 8, seed=3)
+    P1 = {k: torch.tensor(v, dtype=dt, requires_grad=True) for k, v in p1.items() if k != "tex_extra"}
+    P1["tex_extra"] = torch.zeros(3, 8, 8)
+    s1 = dict(rgb=torch.zeros(1, 3, 256, 256), lmk2d=torch.cat([torch.full((1, 68, 2), 128.0), torch.ones(1, 68, 1)], -1), timestep_index=np.array([0]))
+    o1 = torch.optim.Adam([v for k, v in P1.items() if k != "tex_extra"], lr=5e-3)
+    n1 = 50
+    t1 = time.perf_counter()
+    for _ in range(n1):
+        o1.zero_grad()
+        E1, _ = E.compute_energy(P1, s1, STAGES["lmk_init_all"], cfg, m, model)
+        E1.backward()
+        o1.step()
+    d1 = time.perf_counter() - t1
+    return {"value": round(B * steps / dtm, 4), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{B} frame x {steps} iteration at {size}x{size}, 2048^2 texture, full energy+backward+Adam (oracle/, torch CPU fp32, "
+                      f"{os.cpu_count()} threads; python-loop rasteriser); {dtm:.1f} s",
+            "landmark_stage_iters_per_s": round(n1 / d1, 2),
+            "landmark_stage_sample": f"configs[0]: 1 frame 256x256 lmk_init_all, {n1} iterations, {os.cpu_count()} threads"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    vals = []
+    base = None
+    for _ in range(max(1, min(args.steps, 3))):
+        base = cpu_baseline(args.size, sample_frames=1)
+        vals.append(base["value"])
+    v = float(np.mean(vals))
+    base["value"] = v
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": len(vals),
+           "warmup": 0, "ms_per_step": round(1e3 / v, 2) if v else None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic", "config": {"workload": f"monocular {args.size}x{args.size} photometric tracking, bounded sample: 1 frame per step"},
+           "cpu_baseline": base, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

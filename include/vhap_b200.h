@@ -186,6 +186,13 @@ int vhap_tex_rebuild(vhap_ctx* ctx, const float* tex_extra /*[3,T,T]*/, void* st
 int vhap_tex_reg_fold_adam(vhap_ctx* ctx, float* tex_extra, float* g_out, float* adam_m, float* adam_v,
                            float lr, int32_t step, const vhap_stage_cfg* cfg, float photo_scale, float* losses_out, void* stream);
 
+/* ---- per-kernel accounting: every kernel launch is counted; with profiling enabled CUDA events bracket each launch on the
+ *      launching stream (used by bench.py to measure the dominant kernel live inside its timed region) --------------- */
+int vhap_profile_enable(vhap_ctx* ctx, int32_t on);            /* also resets counters */
+int vhap_profile_kernel_count(void);
+const char* vhap_profile_kernel_name(int32_t kid);
+int vhap_profile_read(vhap_ctx* ctx, float* avg_ms_host, uint64_t* launches_host);   /* arrays of vhap_profile_kernel_count(); synchronises */
+
 /* ---- fused Adam on small parameter slabs (torch.optim.Adam, tracker.py:159-211) ------------------------------ */
 int vhap_adam(vhap_ctx* ctx, float* param, const float* grad, float* m, float* v, int64_t n, float lr, int32_t step, void* stream);
 

@@ -83,6 +83,10 @@ def lib() -> C.CDLL:
         "vhap_vertex_normals_backward": (i32, [vp, vp, vp, i32, vp, vp]),
         "vhap_render_photometric": (i32, [vp, P(Params), P(FrameBatch), P(StageCfg), vp, vp, vp, vp, vp, vp, vp, vp]),
         "vhap_set_want_planes": (i32, [vp, i32]),
+        "vhap_profile_enable": (i32, [vp, i32]),
+        "vhap_profile_kernel_count": (i32, []),
+        "vhap_profile_kernel_name": (C.c_char_p, [i32]),
+        "vhap_profile_read": (i32, [vp, vp, vp]),
         "vhap_get_geometry": (i32, [vp, i32, vp, vp]),
         "vhap_overflow_flag": (i32, [vp, P(i32)]),
         "vhap_set_injected_random": (i32, [vp, vp, vp]),
@@ -102,6 +106,7 @@ def lib() -> C.CDLL:
 
 EXPORTED = ["vhap_abi_version", "vhap_last_error", "vhap_ctx_create", "vhap_ctx_reserve", "vhap_ctx_destroy", "vhap_set_stage_masks",
             "vhap_flame_forward", "vhap_flame_backward", "vhap_project", "vhap_rasterize", "vhap_energy_forward_backward",
-            "vhap_energy_forward", "vhap_energy_backward", "vhap_get_plane", "vhap_get_geometry", "vhap_set_want_planes", "vhap_overflow_flag",
+            "vhap_energy_forward", "vhap_energy_backward", "vhap_get_plane", "vhap_get_geometry", "vhap_profile_enable", "vhap_profile_kernel_count", "vhap_profile_kernel_name",
+            "vhap_profile_read", "vhap_set_want_planes", "vhap_overflow_flag",
             "vhap_set_injected_random", "vhap_project_backward", "vhap_vertex_normals",
             "vhap_vertex_normals_backward", "vhap_render_photometric", "vhap_tex_grad_ptr", "vhap_set_tex_painted", "vhap_tex_rebuild", "vhap_tex_reg_fold_adam", "vhap_adam"]

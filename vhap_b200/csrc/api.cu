@@ -7,7 +7,7 @@
 void launch_forward_slab(vhap_ctx* c, const PassArgs& P, const float* lights, float* slab, cudaStream_t s);
 void launch_finalize(vhap_ctx* c, const PassArgs& P, const vhap_stage_cfg* cfg, const float* slab_global, const float* slab_local, int global_B,
                      const float* lights, float* g_lights, cudaStream_t s);
-void launch_flip_plane(const float* in, float* out, int B, int H, int W, cudaStream_t s);
+void launch_flip_plane(vhap_ctx* c, const float* in, float* out, int B, int H, int W, cudaStream_t s);
 void launch_cid_plane(vhap_ctx* c, float* out, cudaStream_t s);
 
 static char g_err[512] = "";
@@ -30,6 +30,36 @@ static int upload(vhap_ctx* ctx, T** dst, const T* src, size_t n) {
 
 extern "C" int vhap_abi_version(void) { return 1; }
 
+static const char* const KID_NAMES[KID_COUNT] = {
+    "cam_setup", "pose_fwd", "blend_fwd", "skin_fwd", "landmarks", "vnormals", "vnormals_bwd", "skin_bwd", "pose_bwd", "joff_bwd", "blend_bwd",
+    "betas_scatter", "regs", "snap", "bin", "scan", "fine_raster", "rast_out", "passA_shade", "pool_count", "pool_scan", "pool_scatter",
+    "passB_disturb_aa_loss", "reduce_partials", "forward_slab", "finalize", "passC_backward", "lights_reduce", "tex_level0", "mip_down",
+    "tex_fold_reg_adam", "tex_loss_reduce", "adam", "assemble_losses", "misc"};
+
+// per-kernel device time, measured with CUDA events on the launching stream (see LAUNCH in engine.h)
+extern "C" int vhap_profile_enable(vhap_ctx* ctx, int32_t on) {
+  VhProf* p = ctx->prof;
+  if (on && !p->ev[0][0][0])
+    for (int k = 0; k < KID_COUNT; ++k) for (int i = 0; i < VH_PROF_SLOTS; ++i) { CK(cudaEventCreate(&p->ev[k][i][0])); CK(cudaEventCreate(&p->ev[k][i][1])); }
+  p->on = on;
+  for (int k = 0; k < KID_COUNT; ++k) { p->n[k] = 0; p->launches[k] = 0; }
+  return 0;
+}
+extern "C" int vhap_profile_kernel_count(void) { return KID_COUNT; }
+extern "C" const char* vhap_profile_kernel_name(int32_t kid) { return (kid >= 0 && kid < KID_COUNT) ? KID_NAMES[kid] : ""; }
+// synchronises; avg_ms[k] = mean device time of the recorded launches of kernel k, launches[k] = launches since enable/reset
+extern "C" int vhap_profile_read(vhap_ctx* ctx, float* avg_ms_host, uint64_t* launches_host) {
+  VhProf* p = ctx->prof;
+  CK(cudaDeviceSynchronize());
+  for (int k = 0; k < KID_COUNT; ++k) {
+    double s = 0;
+    for (int i = 0; i < p->n[k]; ++i) { float ms = 0; cudaEventElapsedTime(&ms, p->ev[k][i][0], p->ev[k][i][1]); s += ms; }
+    avg_ms_host[k] = p->n[k] ? (float)(s / p->n[k]) : 0.f;
+    launches_host[k] = p->launches[k];
+  }
+  return 0;
+}
+
 extern "C" const char* vhap_last_error(const vhap_ctx* ctx) { return ctx ? ctx->err : g_err; }
 
 extern "C" int vhap_ctx_create(vhap_ctx** out, const vhap_mesh_desc* m, int32_t tex_size, int32_t device) {
@@ -37,6 +67,7 @@ extern "C" int vhap_ctx_create(vhap_ctx** out, const vhap_mesh_desc* m, int32_t 
   if (!ctx) return -1;
   *out = ctx;
   ctx->device = device;
+  ctx->prof = (VhProf*)calloc(1, sizeof(VhProf));
   CK(cudaSetDevice(device));
   int V = m->V, F = m->F, K = m->K;
   ctx->V = V; ctx->F = F; ctx->VT = m->VT; ctx->K = K; ctx->n_shape = m->n_shape; ctx->n_expr = K - m->n_shape; ctx->n_lmk = m->n_lmk;
@@ -239,7 +270,7 @@ extern "C" int vhap_flame_forward(vhap_ctx* ctx, const vhap_params* p, const vha
   launch_cam_setup(ctx, p, fb, s);
   launch_flame_forward(ctx, p, fb, s);
   size_t n = (size_t)fb->B * ctx->V;
-  if (verts) k_copy_verts<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ctx->verts, verts, n);
+  if (verts) LAUNCH(ctx, KID_MISC, s, k_copy_verts<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ctx->verts, verts, n));
   if (verts_cano) cudaMemcpyAsync(verts_cano, ctx->v_shaped, n * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s);
   if (lmks) launch_landmarks(ctx, fb, 0.f, 0, lmks, nullptr, 0, 0, fb->B, s);
   LAST();
@@ -252,7 +283,7 @@ extern "C" int vhap_flame_backward(vhap_ctx* ctx, const vhap_params* p, const vh
   if (check_batch(ctx, fb)) return -4;
   zero_backward_scratch(ctx, fb->B, s);
   size_t n = (size_t)fb->B * ctx->V;
-  if (g_verts) k_load_gverts<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(g_verts, ctx->g_verts, n);
+  if (g_verts) LAUNCH(ctx, KID_MISC, s, k_load_gverts<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(g_verts, ctx->g_verts, n));
   if (g_lmks) launch_landmarks(ctx, fb, 0.f, 0, nullptr, (float*)g_lmks, 0, 0, fb->B, s);
   launch_flame_backward(ctx, p, fb, g, 0, s);
   LAST();
@@ -264,7 +295,7 @@ extern "C" int vhap_project(vhap_ctx* ctx, const vhap_params* p, const vhap_fram
   if (check_batch(ctx, fb)) return -4;
   launch_cam_setup(ctx, p, fb, s);
   dim3 g((ctx->V + 127) / 128, fb->B);
-  k_project_only<<<g, 128, 0, s>>>(verts, ctx->cam, ctx->V, fb->H, fb->W, verts_clip);
+  LAUNCH(ctx, KID_MISC, s, k_project_only<<<g, 128, 0, s>>>(verts, ctx->cam, ctx->V, fb->H, fb->W, verts_clip));
   LAST();
   return 0;
 }
@@ -360,7 +391,7 @@ extern "C" int vhap_energy_backward(vhap_ctx* ctx, const vhap_params* p, const v
   if (g) launch_flame_backward(ctx, p, fb, gg, opt_cam, s);
   if (cfg->training) launch_regs(ctx, p, fb, cfg, g, global_B, s);
   float max_hw = (float)(fb->H > fb->W ? fb->H : fb->W);
-  k_assemble_losses<<<1, 32, 0, s>>>(ctx->acc, *cfg, max_hw, gg->focal_length, opt_cam, losses_out);
+  LAUNCH(ctx, KID_ASSEMBLE, s, k_assemble_losses<<<1, 32, 0, s>>>(ctx->acc, *cfg, max_hw, gg->focal_length, opt_cam, losses_out));
   LAST();
   return 0;
 }
@@ -386,7 +417,7 @@ extern "C" int vhap_get_plane(vhap_ctx* ctx, int32_t which, float* out, void* st
     case 5: launch_cid_plane(ctx, out, s); LAST(); return 0;
     default: vh_set_error(ctx, "vhap_get_plane", "unknown plane"); return -3;
   }
-  launch_flip_plane(src, out, B, H, W, s);
+  launch_flip_plane(ctx, src, out, B, H, W, s);
   LAST();
   return 0;
 }
@@ -397,14 +428,14 @@ extern "C" int vhap_tex_reg_fold_adam(vhap_ctx* ctx, float* tex_extra, float* g_
   launch_tex_fold(ctx, tex_extra, g_out, adam_m, adam_v, lr, step, cfg, losses_out, (cudaStream_t)stream);
   if (losses_out) {
     // add the two texture terms to the loss vector produced by vhap_energy_backward
-    k_assemble_losses<<<1, 32, 0, (cudaStream_t)stream>>>(ctx->acc, *cfg, 0.f, nullptr, 0, losses_out);
+    LAUNCH(ctx, KID_ASSEMBLE, (cudaStream_t)stream, k_assemble_losses<<<1, 32, 0, (cudaStream_t)stream>>>(ctx->acc, *cfg, 0.f, nullptr, 0, losses_out));
   }
   LAST();
   return 0;
 }
 
 extern "C" int vhap_adam(vhap_ctx* ctx, float* param, const float* grad, float* m, float* v, int64_t n, float lr, int32_t step, void* stream) {
-  launch_adam(param, grad, m, v, n, lr, step, (cudaStream_t)stream);
+  launch_adam(ctx, param, grad, m, v, n, lr, step, (cudaStream_t)stream);
   LAST();
   return 0;
 }
@@ -433,9 +464,9 @@ extern "C" int vhap_vertex_normals(vhap_ctx* ctx, const float* verts, int32_t B,
   vhap_frame_batch fb; memset(&fb, 0, sizeof(fb)); fb.B = B; fb.H = ctx->maxH; fb.W = ctx->maxW;
   if (check_batch(ctx, &fb)) return -4;
   size_t n = (size_t)B * ctx->V;
-  k_3to4<<<GRID1(n), 0, s>>>(verts, (float*)ctx->verts, n, 1.f);
+  LAUNCH(ctx, KID_MISC, s, k_3to4<<<GRID1(n), 0, s>>>(verts, (float*)ctx->verts, n, 1.f));
   launch_vnormals(ctx, B, s);
-  k_4to3<<<GRID1(n), 0, s>>>((const float*)ctx->vnorm, vnorm, n);
+  LAUNCH(ctx, KID_MISC, s, k_4to3<<<GRID1(n), 0, s>>>((const float*)ctx->vnorm, vnorm, n));
   LAST();
   return 0;
 }
@@ -443,12 +474,12 @@ extern "C" int vhap_vertex_normals(vhap_ctx* ctx, const float* verts, int32_t B,
 extern "C" int vhap_vertex_normals_backward(vhap_ctx* ctx, const float* verts, const float* g_vnorm, int32_t B, float* g_verts, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   size_t n = (size_t)B * ctx->V;
-  k_3to4<<<GRID1(n), 0, s>>>(verts, (float*)ctx->verts, n, 1.f);
+  LAUNCH(ctx, KID_MISC, s, k_3to4<<<GRID1(n), 0, s>>>(verts, (float*)ctx->verts, n, 1.f));
   launch_vnormals(ctx, B, s);
-  k_3to4<<<GRID1(n), 0, s>>>(g_vnorm, ctx->g_vnorm, n, 0.f);
+  LAUNCH(ctx, KID_MISC, s, k_3to4<<<GRID1(n), 0, s>>>(g_vnorm, ctx->g_vnorm, n, 0.f));
   cudaMemsetAsync(ctx->g_verts, 0, n * 4 * sizeof(float), s);
   launch_vnormals_bwd(ctx, B, s);
-  k_4to3_add<<<GRID1(n), 0, s>>>(ctx->g_verts, g_verts, n);
+  LAUNCH(ctx, KID_MISC, s, k_4to3_add<<<GRID1(n), 0, s>>>(ctx->g_verts, g_verts, n));
   LAST();
   return 0;
 }
@@ -478,10 +509,10 @@ extern "C" int vhap_project_backward(vhap_ctx* ctx, const vhap_params* p, const 
   launch_cam_setup(ctx, p, fb, s);
   cudaMemsetAsync(ctx->acc, 0, ACC_COUNT * sizeof(float), s);
   dim3 g((ctx->V + 127) / 128, fb->B);
-  k_project_bwd<<<g, 128, 0, s>>>(verts, g_clip, ctx->cam, ctx->V, fb->H, fb->W, g_verts, g_focal ? ctx->acc + ACC_GFX : nullptr);
+  LAUNCH(ctx, KID_MISC, s, k_project_bwd<<<g, 128, 0, s>>>(verts, g_clip, ctx->cam, ctx->V, fb->H, fb->W, g_verts, g_focal ? ctx->acc + ACC_GFX : nullptr));
   if (g_focal) {
     vhap_stage_cfg dummy; memset(&dummy, 0, sizeof(dummy));
-    k_assemble_losses<<<1, 32, 0, s>>>(ctx->acc, dummy, (float)(fb->H > fb->W ? fb->H : fb->W), g_focal, 1, nullptr);
+    LAUNCH(ctx, KID_ASSEMBLE, s, k_assemble_losses<<<1, 32, 0, s>>>(ctx->acc, dummy, (float)(fb->H > fb->W ? fb->H : fb->W), g_focal, 1, nullptr));
   }
   LAST();
   return 0;
@@ -499,7 +530,7 @@ extern "C" int vhap_render_photometric(vhap_ctx* ctx, const vhap_params* p, cons
   cudaMemsetAsync(ctx->acc, 0, ACC_COUNT * sizeof(float), s);
   zero_backward_scratch(ctx, fb->B, s);
   cudaMemcpyAsync(ctx->clip, verts_clip, n * 4 * sizeof(float), cudaMemcpyDeviceToDevice, s);
-  k_3to4<<<GRID1(n), 0, s>>>(vnorm, (float*)ctx->vnorm, n, 0.f);
+  LAUNCH(ctx, KID_MISC, s, k_3to4<<<GRID1(n), 0, s>>>(vnorm, (float*)ctx->vnorm, n, 0.f));
   launch_raster(ctx, ctx->clip, ctx->snap, fb->B, fb->H, fb->W, ctx->tri_id, 0, 1, s);
   PassArgs P;
   fill_render_args(ctx, P, fb, cfg, p->lights);
@@ -512,9 +543,9 @@ extern "C" int vhap_render_photometric(vhap_ctx* ctx, const vhap_params* p, cons
     P.g_tex = g_tex_pyramid;
     launch_render_backward(ctx, P, cfg, p->lights, g_lights, nullptr, s);
     if (g_clip) cudaMemcpyAsync(g_clip, ctx->g_clip, n * 4 * sizeof(float), cudaMemcpyDeviceToDevice, s);
-    if (g_vnorm) k_4to3<<<GRID1(n), 0, s>>>(ctx->g_vnorm, g_vnorm, n);
+    if (g_vnorm) LAUNCH(ctx, KID_MISC, s, k_4to3<<<GRID1(n), 0, s>>>(ctx->g_vnorm, g_vnorm, n));
   }
-  k_assemble_losses<<<1, 32, 0, s>>>(ctx->acc, *cfg, 0.f, nullptr, 0, losses_out);
+  LAUNCH(ctx, KID_ASSEMBLE, s, k_assemble_losses<<<1, 32, 0, s>>>(ctx->acc, *cfg, 0.f, nullptr, 0, losses_out));
   LAST();
   return 0;
 }

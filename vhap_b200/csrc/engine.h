@@ -50,9 +50,36 @@ struct vhap_ctx {
   float* scal;                                    // [16] device scalars for pass C
   float* acc;                                     // [64] misc accumulators (loss sums, focal grad...)
   const uint8_t* inj_w; const float* inj_u;
+  struct VhProf* prof;
 };
 
 void vh_set_error(vhap_ctx* ctx, const char* what, const char* msg);
+
+// ---- per-kernel launch accounting: every kernel launch goes through LAUNCH(); when profiling is enabled
+// (vhap_profile_enable) CUDA events are recorded around each launch on the launching stream so that bench.py can
+// report per-kernel device time measured live inside its timed region.
+enum { KID_CAM = 0, KID_POSE_FWD, KID_BLEND_FWD, KID_SKIN_FWD, KID_LMK, KID_VNORM, KID_VNORM_BWD, KID_SKIN_BWD, KID_POSE_BWD, KID_JOFF_BWD,
+       KID_BLEND_BWD, KID_BETAS_SCATTER, KID_REGS, KID_SNAP, KID_BIN, KID_SCAN, KID_FINE, KID_RAST_OUT, KID_PASSA, KID_POOL_COUNT,
+       KID_POOL_SCAN, KID_POOL_SCATTER, KID_PASSB, KID_REDUCE, KID_SLAB, KID_FINALIZE, KID_PASSC, KID_LIGHTS_REDUCE, KID_TEX_L0, KID_MIP,
+       KID_TEX_FOLD, KID_TEX_LOSS, KID_ADAM, KID_ASSEMBLE, KID_MISC, KID_COUNT };
+#define VH_PROF_SLOTS 128
+struct VhProf {
+  int on;
+  unsigned long long launches[KID_COUNT];
+  int n[KID_COUNT];
+  cudaEvent_t ev[KID_COUNT][VH_PROF_SLOTS][2];
+};
+static inline VhProf* vh_prof(vhap_ctx* c) { return c->prof; }
+static inline void vh_prof_begin(vhap_ctx* c, int kid, cudaStream_t s) {
+  VhProf* p = vh_prof(c);
+  p->launches[kid]++;
+  if (p->on && p->n[kid] < VH_PROF_SLOTS) cudaEventRecord(p->ev[kid][p->n[kid]][0], s);
+}
+static inline void vh_prof_end(vhap_ctx* c, int kid, cudaStream_t s) {
+  VhProf* p = vh_prof(c);
+  if (p->on && p->n[kid] < VH_PROF_SLOTS) { cudaEventRecord(p->ev[kid][p->n[kid]][1], s); p->n[kid]++; }
+}
+#define LAUNCH(c, kid, s, ...) do { vh_prof_begin((c), (kid), (s)); __VA_ARGS__; vh_prof_end((c), (kid), (s)); } while (0)
 
 // flame.cu
 void launch_cam_setup(vhap_ctx* c, const vhap_params* p, const vhap_frame_batch* fb, cudaStream_t s);
@@ -75,4 +102,4 @@ void launch_render_backward(vhap_ctx* c, PassArgs& P, const vhap_stage_cfg* cfg,
 void launch_tex_rebuild(vhap_ctx* c, const float* tex_extra, cudaStream_t s);
 void launch_tex_fold(vhap_ctx* c, float* tex_extra, float* g_out, float* m, float* v, float lr, int step, const vhap_stage_cfg* cfg,
                      float* losses_out, cudaStream_t s);
-void launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, int step, cudaStream_t s);
+void launch_adam(vhap_ctx* c, float* p, const float* g, float* m, float* v, int64_t n, float lr, int step, cudaStream_t s);

@@ -40,7 +40,7 @@ __global__ void k_cam_setup(CamParams* cam, const float* RT, const float* K, con
 }
 
 void launch_cam_setup(vhap_ctx* c, const vhap_params* p, const vhap_frame_batch* fb, cudaStream_t s) {
-  k_cam_setup<<<(fb->B + 63) / 64, 64, 0, s>>>(c->cam, fb->RT, fb->K, p->focal_length, fb->B, fb->H, fb->W);
+  LAUNCH(c, KID_CAM, s, k_cam_setup<<<(fb->B + 63) / 64, 64, 0, s>>>(c->cam, fb->RT, fb->K, p->focal_length, fb->B, fb->H, fb->W));
 }
 
 #define VH_NEAR 0.1f
@@ -188,14 +188,14 @@ __global__ void __launch_bounds__(128) k_skin_fwd(const float* __restrict__ v_sh
 
 void launch_flame_forward(vhap_ctx* c, const vhap_params* p, const vhap_frame_batch* fb, cudaStream_t s) {
   int B = fb->B, V = c->V, M = 3 * V;
-  k_pose_fwd<<<B, 256, 0, s>>>(p->shape, p->expr, p->rotation, p->neck_pose, p->jaw_pose, p->eyes_pose, p->static_offset, fb->timesteps,
-                               c->JS, c->Jt, c->Jreg, V, c->K, c->n_shape, c->betas, c->posebuf, c->poses);
+  LAUNCH(c, KID_POSE_FWD, s, k_pose_fwd<<<B, 256, 0, s>>>(p->shape, p->expr, p->rotation, p->neck_pose, p->jaw_pose, p->eyes_pose, p->static_offset, fb->timesteps,
+                               c->JS, c->Jt, c->Jreg, V, c->K, c->n_shape, c->betas, c->posebuf, c->poses));
   dim3 g1((M + 127) / 128, (B + VH_MAXB_CHUNK - 1) / VH_MAXB_CHUNK);
-  k_blend_fwd<VH_MAXB_CHUNK><<<g1, 128, VH_MAXB_CHUNK * c->K * sizeof(float), s>>>(c->S_fwd, c->v_template, p->static_offset, c->betas, M, c->K,
-                                                                                  c->n_shape, B, c->v_shaped);
+  LAUNCH(c, KID_BLEND_FWD, s, k_blend_fwd<VH_MAXB_CHUNK><<<g1, 128, VH_MAXB_CHUNK * c->K * sizeof(float), s>>>(c->S_fwd, c->v_template, p->static_offset, c->betas, M, c->K,
+                                                                                  c->n_shape, B, c->v_shaped));
   dim3 g2((V + 127) / 128, (B + 7) / 8);
-  k_skin_fwd<8><<<g2, 128, 0, s>>>(c->v_shaped, c->posedirs, c->lbs_w, c->posebuf, p->translation, fb->timesteps, c->cam, V, B, fb->H, fb->W,
-                                   c->v_posed, c->verts, c->clip, c->snap);
+  LAUNCH(c, KID_SKIN_FWD, s, k_skin_fwd<8><<<g2, 128, 0, s>>>(c->v_shaped, c->posedirs, c->lbs_w, c->posebuf, p->translation, fb->timesteps, c->cam, V, B, fb->H, fb->W,
+                                   c->v_posed, c->verts, c->clip, c->snap));
 }
 
 // ------------------------------------------------------------------------------------------------ landmarks
@@ -262,8 +262,8 @@ __global__ void __launch_bounds__(96) k_landmarks(const f4* __restrict__ verts, 
 void launch_landmarks(vhap_ctx* c, const vhap_frame_batch* fb, float w_scale, int jawline_off, float* lmks_out, float* g_lmk_in,
                       int compute_loss, int opt_cam, int global_B, cudaStream_t s) {
   (void)global_B;
-  k_landmarks<<<fb->B, 96, 0, s>>>(c->verts, c->faces, c->lmk_faces, c->lmk_bary, fb->lmk2d, c->cam, c->V, c->n_lmk, fb->H, fb->W, w_scale, jawline_off,
-                                   compute_loss, opt_cam, lmks_out, g_lmk_in, c->g_verts, c->acc);
+  LAUNCH(c, KID_LMK, s, k_landmarks<<<fb->B, 96, 0, s>>>(c->verts, c->faces, c->lmk_faces, c->lmk_bary, fb->lmk2d, c->cam, c->V, c->n_lmk, fb->H, fb->W, w_scale, jawline_off,
+                                   compute_loss, opt_cam, lmks_out, g_lmk_in, c->g_verts, c->acc));
 }
 
 // ------------------------------------------------------------------------------------------------ vertex normals
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(128) k_vnormals(const f4* __restrict__ verts, 
 }
 void launch_vnormals(vhap_ctx* c, int B, cudaStream_t s) {
   dim3 g((c->V + 127) / 128, B);
-  k_vnormals<<<g, 128, 0, s>>>(c->verts, c->faces, c->vf_indptr, c->vf_faces, c->V, c->vnraw, c->vnorm);
+  LAUNCH(c, KID_VNORM, s, k_vnormals<<<g, 128, 0, s>>>(c->verts, c->faces, c->vf_indptr, c->vf_faces, c->V, c->vnraw, c->vnorm));
 }
 
 __global__ void __launch_bounds__(128) k_vnormals_bwd(const f4* __restrict__ verts, const i4* __restrict__ faces, const f4* __restrict__ vnraw,
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(128) k_vnormals_bwd(const f4* __restrict__ ver
 }
 void launch_vnormals_bwd(vhap_ctx* c, int B, cudaStream_t s) {
   dim3 g((c->F + 127) / 128, B);
-  k_vnormals_bwd<<<g, 128, 0, s>>>(c->verts, c->faces, c->vnraw, c->g_vnorm, c->V, c->F, c->g_verts);
+  LAUNCH(c, KID_VNORM_BWD, s, k_vnormals_bwd<<<g, 128, 0, s>>>(c->verts, c->faces, c->vnraw, c->g_vnorm, c->V, c->F, c->g_verts));
 }
 
 // ------------------------------------------------------------------------------------------------ skinning backward
@@ -488,15 +488,15 @@ void launch_flame_backward(vhap_ctx* c, const vhap_params* p, const vhap_frame_b
   int B = fb->B, V = c->V, M = 3 * V;
   bool need_betas = g->shape || g->expr;
   dim3 g1((V + 127) / 128, (B + 7) / 8);
-  k_skin_bwd<8><<<g1, 128, 0, s>>>(c->v_posed, c->verts, c->posedirs, c->lbs_w, c->posebuf, c->cam, fb->timesteps, c->g_verts, c->g_clip, V, B, fb->H, fb->W,
-                                   opt_cam, c->g_vshaped, g->static_offset, g->translation, c->gA, c->gpf, c->acc);
-  k_pose_bwd<<<B, 128, 0, s>>>(c->poses, c->posebuf, c->gA, c->gpf, fb->timesteps, c->JS, c->K, g->rotation, g->neck_pose, g->jaw_pose, g->eyes_pose,
-                               c->gJ, need_betas ? c->gbetas : nullptr);
-  if (g->static_offset) k_joff_bwd<<<(V + 127) / 128, 128, 0, s>>>(c->Jreg, c->gJ, V, B, g->static_offset);
+  LAUNCH(c, KID_SKIN_BWD, s, k_skin_bwd<8><<<g1, 128, 0, s>>>(c->v_posed, c->verts, c->posedirs, c->lbs_w, c->posebuf, c->cam, fb->timesteps, c->g_verts, c->g_clip, V, B, fb->H, fb->W,
+                                   opt_cam, c->g_vshaped, g->static_offset, g->translation, c->gA, c->gpf, c->acc));
+  LAUNCH(c, KID_POSE_BWD, s, k_pose_bwd<<<B, 128, 0, s>>>(c->poses, c->posebuf, c->gA, c->gpf, fb->timesteps, c->JS, c->K, g->rotation, g->neck_pose, g->jaw_pose, g->eyes_pose,
+                               c->gJ, need_betas ? c->gbetas : nullptr));
+  if (g->static_offset) LAUNCH(c, KID_JOFF_BWD, s, k_joff_bwd<<<(V + 127) / 128, 128, 0, s>>>(c->Jreg, c->gJ, V, B, g->static_offset));
   if (need_betas) {
     dim3 g2((M + BB_ROWS - 1) / BB_ROWS, (B + VH_MAXB_CHUNK - 1) / VH_MAXB_CHUNK);
-    k_blend_bwd<VH_MAXB_CHUNK><<<g2, 512, 0, s>>>(c->S_bwd, c->g_vshaped, M, c->K, B, c->gbetas);
-    k_betas_scatter<<<B, 256, 0, s>>>(c->gbetas, fb->timesteps, c->K, c->n_shape, g->shape, g->expr);
+    LAUNCH(c, KID_BLEND_BWD, s, k_blend_bwd<VH_MAXB_CHUNK><<<g2, 512, 0, s>>>(c->S_bwd, c->g_vshaped, M, c->K, B, c->gbetas));
+    LAUNCH(c, KID_BETAS_SCATTER, s, k_betas_scatter<<<B, 256, 0, s>>>(c->gbetas, fb->timesteps, c->K, c->n_shape, g->shape, g->expr));
   }
   (void)p;
 }
@@ -690,5 +690,5 @@ void launch_regs(vhap_ctx* c, const vhap_params* p, const vhap_frame_batch* fb, 
   a.ts = fb->timesteps; a.B = fb->B; a.V = c->V; a.n_shape = c->n_shape; a.n_expr = c->n_expr; a.global_B = global_B;
   a.w_off = c->w_off; a.w_off_lap = c->w_off_lap; a.lap_indptr = c->lap_indptr; a.lap_idx = c->lap_idx; a.lap_val = c->lap_val; a.lap_y = c->lap_y;
   a.rigid_indptr = c->rigid_indptr; a.rigid_vids = c->rigid_vids; a.n_rigid = c->n_rigid; a.acc = c->acc;
-  k_regs<<<1, 1024, 0, s>>>(a);
+  LAUNCH(c, KID_REGS, s, k_regs<<<1, 1024, 0, s>>>(a));
 }

@@ -201,16 +201,16 @@ __global__ void __launch_bounds__(128) k_fine(const i4* __restrict__ snap, const
 
 void launch_raster(vhap_ctx* c, const f4* clip, i4* snap, int B, int H, int W, int* tri_id, int cull_backface, int need_snap, cudaStream_t s) {
   int V = c->V, F = c->F;
-  if (need_snap) k_snap<<<(B * V + 255) / 256, 256, 0, s>>>(clip, snap, B * V, H, W);
+  if (need_snap) LAUNCH(c, KID_SNAP, s, k_snap<<<(B * V + 255) / 256, 256, 0, s>>>(clip, snap, B * V, H, W));
   int tiles_x = (W + VH_TILE - 1) / VH_TILE, tiles_y = (H + VH_TILE - 1) / VH_TILE, ntiles = B * tiles_x * tiles_y;
   cudaMemsetAsync(c->tile_count, 0, sizeof(int) * ntiles, s);
   cudaMemsetAsync(c->tile_cursor, 0, sizeof(int) * ntiles, s);
   dim3 g((F + 255) / 256, B);
-  k_bin<false><<<g, 256, 0, s>>>(snap, c->faces, V, F, B, H, W, tiles_x, tiles_y, cull_backface, c->tile_count, nullptr, nullptr, nullptr, 0, c->overflow_flag);
-  k_scan<<<1, 1024, 0, s>>>(c->tile_count, c->tile_off, ntiles);
-  k_bin<true><<<g, 256, 0, s>>>(snap, c->faces, V, F, B, H, W, tiles_x, tiles_y, cull_backface, c->tile_count, c->tile_off, c->tile_cursor, c->tile_list,
-                                c->tile_cap, c->overflow_flag);
-  k_fine<<<ntiles, 128, 0, s>>>(snap, c->faces, c->tile_count, c->tile_off, c->tile_list, c->tile_cap, V, H, W, tiles_x, tiles_y, cull_backface, tri_id);
+  LAUNCH(c, KID_BIN, s, k_bin<false><<<g, 256, 0, s>>>(snap, c->faces, V, F, B, H, W, tiles_x, tiles_y, cull_backface, c->tile_count, nullptr, nullptr, nullptr, 0, c->overflow_flag));
+  LAUNCH(c, KID_SCAN, s, k_scan<<<1, 1024, 0, s>>>(c->tile_count, c->tile_off, ntiles));
+  LAUNCH(c, KID_BIN, s, k_bin<true><<<g, 256, 0, s>>>(snap, c->faces, V, F, B, H, W, tiles_x, tiles_y, cull_backface, c->tile_count, c->tile_off, c->tile_cursor, c->tile_list,
+                                c->tile_cap, c->overflow_flag));
+  LAUNCH(c, KID_FINE, s, k_fine<<<ntiles, 128, 0, s>>>(snap, c->faces, c->tile_count, c->tile_off, c->tile_list, c->tile_cap, V, H, W, tiles_x, tiles_y, cull_backface, tri_id));
 }
 
 // dr.rasterize's float outputs for the modular API: rast = (u, v, z/w, id), rast_db = (du/dx, du/dy, dv/dx, dv/dy)
@@ -236,5 +236,5 @@ void launch_rast_out(vhap_ctx* c, const f4* clip, int B, int H, int W, const int
   memset(&A, 0, sizeof(A));
   A.B = B; A.H = H; A.W = W; A.V = c->V; A.F = c->F; A.faces = c->faces; A.clip = clip; A.tri_id = tri_id;
   size_t n = (size_t)B * H * W;
-  k_rast_out<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(A, rast, rast_db);
+  LAUNCH(c, KID_RAST_OUT, s, k_rast_out<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(A, rast, rast_db));
 }

@@ -239,9 +239,9 @@ __global__ void k_flip_plane(const float4* __restrict__ in, float4* __restrict__
   int x = pix % W, y = (pix / W) % H, b = pix / ((size_t)W * H);
   out[((size_t)b * H + (H - 1 - y)) * W + x] = in[pix];
 }
-void launch_flip_plane(const float* in, float* out, int B, int H, int W, cudaStream_t s) {
+void launch_flip_plane(vhap_ctx* c, const float* in, float* out, int B, int H, int W, cudaStream_t s) {
   size_t n = (size_t)B * H * W;
-  k_flip_plane<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const float4*)in, (float4*)out, B, H, W);
+  LAUNCH(c, KID_MISC, s, k_flip_plane<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const float4*)in, (float4*)out, B, H, W));
 }
 __global__ void k_cid_plane(const int* __restrict__ tri_id, const uint8_t* __restrict__ fid2cid, float4* __restrict__ out, int B, int H, int W) {
   size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n = (size_t)B * H * W;
@@ -252,7 +252,7 @@ __global__ void k_cid_plane(const int* __restrict__ tri_id, const uint8_t* __res
 }
 void launch_cid_plane(vhap_ctx* c, float* out, cudaStream_t s) {
   size_t n = (size_t)c->curB * c->curH * c->curW;
-  k_cid_plane<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(c->tri_id, c->fid2cid, (float4*)out, c->curB, c->curH, c->curW);
+  LAUNCH(c, KID_MISC, s, k_cid_plane<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(c->tri_id, c->fid2cid, (float4*)out, c->curB, c->curH, c->curW));
 }
 
 void fill_render_args(vhap_ctx* c, PassArgs& P, const vhap_frame_batch* fb, const vhap_stage_cfg* cfg, const float* lights) {
@@ -281,22 +281,22 @@ void launch_render_forward(vhap_ctx* c, PassArgs& P, cudaStream_t s) {
   size_t n = (size_t)A.B * A.H * A.W;
   int nblk = (int)((n + PB - 1) / PB);
   cudaMemsetAsync(c->maxslot, 0, sizeof(unsigned long long), s);
-  k_passA<<<nblk, PB, 0, s>>>(P, c->partials, c->maxslot);
+  LAUNCH(c, KID_PASSA, s, k_passA<<<nblk, PB, 0, s>>>(P, c->partials, c->maxslot));
   if (P.disturb) {
-    k_pool_count<<<nblk, PB, 0, s>>>(A.tri_id, A.fid2cid, n, c->pool_blk_count);
-    k_pool_scan<<<1, 1024, 0, s>>>(c->pool_blk_count, c->pool_blk_off, nblk, c->pool_base, c->pool_count);
-    k_pool_scatter<<<nblk, PB, 0, s>>>(A.tri_id, A.fid2cid, n, c->pool_blk_off, c->pool_list);
+    LAUNCH(c, KID_POOL_COUNT, s, k_pool_count<<<nblk, PB, 0, s>>>(A.tri_id, A.fid2cid, n, c->pool_blk_count));
+    LAUNCH(c, KID_POOL_SCAN, s, k_pool_scan<<<1, 1024, 0, s>>>(c->pool_blk_count, c->pool_blk_off, nblk, c->pool_base, c->pool_count));
+    LAUNCH(c, KID_POOL_SCATTER, s, k_pool_scatter<<<nblk, PB, 0, s>>>(A.tri_id, A.fid2cid, n, c->pool_blk_off, c->pool_list));
   }
-  k_passB<<<nblk, PB, 0, s>>>(P, c->partials);
+  LAUNCH(c, KID_PASSB, s, k_passB<<<nblk, PB, 0, s>>>(P, c->partials));
   static const int h_slot[4] = {ACC_VARSUM, ACC_NFGPIX, ACC_ABSERR, ACC_NFG};
   static int* d_slot = nullptr;
   if (!d_slot) { cudaMalloc(&d_slot, sizeof(h_slot)); cudaMemcpy(d_slot, h_slot, sizeof(h_slot), cudaMemcpyHostToDevice); }
-  k_reduce_partials<<<1, 1024, 0, s>>>(c->partials, nblk, 4, c->acc, d_slot);
+  LAUNCH(c, KID_REDUCE, s, k_reduce_partials<<<1, 1024, 0, s>>>(c->partials, nblk, 4, c->acc, d_slot));
 }
 
 void launch_forward_slab(vhap_ctx* c, const PassArgs& P, const float* lights, float* slab, cudaStream_t s) {
   const RenderArgs& A = P.R;
-  k_forward_slab<<<1, 1, 0, s>>>(c->acc, c->maxslot, lights, (float)((size_t)A.B * A.H * A.W), slab);
+  LAUNCH(c, KID_SLAB, s, k_forward_slab<<<1, 1, 0, s>>>(c->acc, c->maxslot, lights, (float)((size_t)A.B * A.H * A.W), slab));
 }
 
 void launch_render_finalize(vhap_ctx* c, PassArgs& P, const vhap_stage_cfg* cfg, const float* reduce_slab, int global_B, const float* lights, cudaStream_t s) {
@@ -306,7 +306,7 @@ void launch_render_finalize(vhap_ctx* c, PassArgs& P, const vhap_stage_cfg* cfg,
 void launch_finalize(vhap_ctx* c, const PassArgs& P, const vhap_stage_cfg* cfg, const float* slab_global, const float* slab_local, int global_B,
                      const float* lights, float* g_lights, cudaStream_t s) {
   const RenderArgs& A = P.R;
-  k_finalize<<<1, 1, 0, s>>>(slab_global, slab_local, *cfg, lights, (float)((size_t)global_B * A.H * A.W), c->scal, c->acc, g_lights);
+  LAUNCH(c, KID_FINALIZE, s, k_finalize<<<1, 1, 0, s>>>(slab_global, slab_local, *cfg, lights, (float)((size_t)global_B * A.H * A.W), c->scal, c->acc, g_lights));
 }
 
 void launch_render_backward(vhap_ctx* c, PassArgs& P, const vhap_stage_cfg* cfg, const float* lights, float* g_lights, const float* ext_grad, cudaStream_t s) {
@@ -314,6 +314,6 @@ void launch_render_backward(vhap_ctx* c, PassArgs& P, const vhap_stage_cfg* cfg,
   const RenderArgs& A = P.R;
   size_t n = (size_t)A.B * A.H * A.W;
   int nblk = (int)((n + PB - 1) / PB);
-  k_passC<<<nblk, PB, 0, s>>>(P, ext_grad, c->partials);
-  if (g_lights) k_lights_reduce<<<64, 32, 0, s>>>(c->partials, nblk, g_lights);
+  LAUNCH(c, KID_PASSC, s, k_passC<<<nblk, PB, 0, s>>>(P, ext_grad, c->partials));
+  if (g_lights) LAUNCH(c, KID_LIGHTS_REDUCE, s, k_lights_reduce<<<64, 32, 0, s>>>(c->partials, nblk, g_lights));
 }

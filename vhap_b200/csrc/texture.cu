@@ -32,14 +32,14 @@ static void build_mips(vhap_ctx* c, f4* pyr, cudaStream_t s) {
   for (int l = 1; l <= c->max_level; ++l) {
     int sd = c->T >> l;
     dim3 blk(16, 16), grd((sd + 15) / 16, (sd + 15) / 16);
-    k_mip_down<<<grd, blk, 0, s>>>(pyr + c->mip_off[l - 1], pyr + c->mip_off[l], sd);
+    LAUNCH(c, KID_MIP, s, k_mip_down<<<grd, blk, 0, s>>>(pyr + c->mip_off[l - 1], pyr + c->mip_off[l], sd));
   }
 }
 
 void launch_tex_rebuild(vhap_ctx* c, const float* tex_extra, cudaStream_t s) {
   size_t n = (size_t)c->T * c->T;
   f4* pyr = c->mips[c->cur_mip];
-  k_tex_level0<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(c->tex_painted, tex_extra, c->T, pyr);
+  LAUNCH(c, KID_TEX_L0, s, k_tex_level0<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(c->tex_painted, tex_extra, c->T, pyr));
   build_mips(c, pyr, s);
 }
 
@@ -156,8 +156,8 @@ void launch_tex_fold(vhap_ctx* c, float* tex_extra, float* g_out, float* m, floa
   a.lr = lr; a.bc1 = 1.f - powf(0.9f, (float)step); a.bc2_sqrt = sqrtf(1.f - powf(0.999f, (float)step));
   size_t n = (size_t)T * T;
   int nblk = (int)((n + 255) / 256);
-  k_tex_fold<<<nblk, 256, 0, s>>>(a, c->tv_partials);
-  k_tex_loss_reduce<<<1, 1024, 0, s>>>(c->tv_partials, nblk, c->acc);
+  LAUNCH(c, KID_TEX_FOLD, s, k_tex_fold<<<nblk, 256, 0, s>>>(a, c->tv_partials));
+  LAUNCH(c, KID_TEX_LOSS, s, k_tex_loss_reduce<<<1, 1024, 0, s>>>(c->tv_partials, nblk, c->acc));
   if (c->g_tex && c->max_level >= 1)                                      // coarser gradient levels
     cudaMemsetAsync(c->g_tex + (size_t)c->mip_off[1] * 4, 0, (c->mip_total - c->mip_off[1]) * 4 * sizeof(float), s);
   if (a.do_adam) { c->cur_mip ^= 1; build_mips(c, c->mips[c->cur_mip], s); }
@@ -173,7 +173,7 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
   p[i] -= step_size * mi / (sqrtf(vi) / bc2_sqrt + 1e-8f);
 }
 
-void launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, int step, cudaStream_t s) {
+void launch_adam(vhap_ctx* c, float* p, const float* g, float* m, float* v, int64_t n, float lr, int step, cudaStream_t s) {
   float bc1 = 1.f - powf(0.9f, (float)step), bc2s = sqrtf(1.f - powf(0.999f, (float)step));
-  k_adam<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, g, m, v, n, lr / bc1, bc2s);
+  LAUNCH(c, KID_ADAM, s, k_adam<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, g, m, v, n, lr / bc1, bc2s));
 }
