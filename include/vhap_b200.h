@@ -194,6 +194,9 @@ const char* vhap_profile_kernel_name(int32_t kid);
 int vhap_profile_read(vhap_ctx* ctx, float* avg_ms_host, uint64_t* launches_host);   /* arrays of vhap_profile_kernel_count(); synchronises */
 
 /* ---- fused Adam on small parameter slabs (torch.optim.Adam, tracker.py:159-211) ------------------------------ */
+/* all parameter groups of one slab in a single launch: segment k = [off[k], off[k]+len[k]) with learning rate lr[k] (HOST arrays, <= 24) */
+int vhap_adam_multi(vhap_ctx* ctx, float* param, const float* grad, float* m, float* v, int32_t n_seg, const int64_t* off_host,
+                    const int64_t* len_host, const float* lr_host, int32_t step, void* stream);
 int vhap_adam(vhap_ctx* ctx, float* param, const float* grad, float* m, float* v, int64_t n, float lr, int32_t step, void* stream);
 
 #ifdef __cplusplus

@@ -557,6 +557,16 @@ extern "C" int vhap_get_geometry(vhap_ctx* ctx, int32_t which, float* out, void*
   return 0;
 }
 
+void launch_adam_multi(vhap_ctx* c, float* p, const float* g, float* m, float* v, int n_seg, const int64_t* off, const int64_t* len, const float* lr,
+                       int step, cudaStream_t s);
+// one launch for all parameter groups of a slab: segment k covers [off[k], off[k]+len[k]) with learning rate lr[k] (HOST arrays)
+extern "C" int vhap_adam_multi(vhap_ctx* ctx, float* param, const float* grad, float* m, float* v, int32_t n_seg, const int64_t* off_host,
+                               const int64_t* len_host, const float* lr_host, int32_t step, void* stream) {
+  launch_adam_multi(ctx, param, grad, m, v, n_seg, off_host, len_host, lr_host, step, (cudaStream_t)stream);
+  LAST();
+  return 0;
+}
+
 extern "C" int vhap_overflow_flag(vhap_ctx* ctx, int32_t* out_host) {
   CK(cudaMemcpy(out_host, ctx->overflow_flag, sizeof(int), cudaMemcpyDeviceToHost));
   return 0;

@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(256) k_pose_fwd(
 // v_shaped[b][m] = template[m] + offset[m] + sum_k S[k][m] beta[b][k]   (lbs.py:218-239, flame.py:602-608)
 // S_fwd layout [K][3V]: a thread owns row m, every load is coalesced across the warp, betas are broadcast from smem.
 // The shape part (n_shape columns) is identical for all frames and accumulated once.
+#define BLEND_KS 8
 template <int NB>
 __global__ void __launch_bounds__(128) k_blend_fwd(const float* __restrict__ S, const float* __restrict__ tmpl, const float* __restrict__ offset,
                                                    const float* __restrict__ betas, int M, int K, int n_shape, int B, float* __restrict__ out) {
@@ -104,21 +105,24 @@ __global__ void __launch_bounds__(128) k_blend_fwd(const float* __restrict__ S, 
   __syncthreads();
   int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
-  float common = tmpl[m] + (offset ? offset[m] : 0.f);
+  // K is split over gridDim.z slices (more loads in flight per SM); slice 0 also adds template + offset
+  int kper = (K + gridDim.z - 1) / gridDim.z, k0 = blockIdx.z * kper, k1 = min(k0 + kper, K);
+  float common = blockIdx.z == 0 ? tmpl[m] + (offset ? offset[m] : 0.f) : 0.f;
   const float* s = S + m;
-#pragma unroll 4
-  for (int k = 0; k < n_shape; ++k) common += s[(size_t)k * M] * shb[k];
+  int ks = min(k1, n_shape);
+#pragma unroll 8
+  for (int k = k0; k < ks; ++k) common += s[(size_t)k * M] * shb[k];
   float acc[NB];
 #pragma unroll
   for (int i = 0; i < NB; ++i) acc[i] = 0.f;
-#pragma unroll 2
-  for (int k = n_shape; k < K; ++k) {
+#pragma unroll 4
+  for (int k = max(k0, n_shape); k < k1; ++k) {
     float sv = s[(size_t)k * M];
 #pragma unroll
     for (int i = 0; i < NB; ++i) acc[i] += sv * shb[i * K + k];
   }
 #pragma unroll
-  for (int i = 0; i < NB; ++i) if (i < nb) out[(size_t)(b0 + i) * M + m] = common + acc[i];
+  for (int i = 0; i < NB; ++i) if (i < nb) atomicAdd(out + (size_t)(b0 + i) * M + m, common + acc[i]);
 }
 
 // ------------------------------------------------------------------------------------------------ skin + project + snap
@@ -190,7 +194,8 @@ void launch_flame_forward(vhap_ctx* c, const vhap_params* p, const vhap_frame_ba
   int B = fb->B, V = c->V, M = 3 * V;
   LAUNCH(c, KID_POSE_FWD, s, k_pose_fwd<<<B, 256, 0, s>>>(p->shape, p->expr, p->rotation, p->neck_pose, p->jaw_pose, p->eyes_pose, p->static_offset, fb->timesteps,
                                c->JS, c->Jt, c->Jreg, V, c->K, c->n_shape, c->betas, c->posebuf, c->poses));
-  dim3 g1((M + 127) / 128, (B + VH_MAXB_CHUNK - 1) / VH_MAXB_CHUNK);
+  dim3 g1((M + 127) / 128, (B + VH_MAXB_CHUNK - 1) / VH_MAXB_CHUNK, BLEND_KS);
+  cudaMemsetAsync(c->v_shaped, 0, (size_t)B * M * sizeof(float), s);
   LAUNCH(c, KID_BLEND_FWD, s, k_blend_fwd<VH_MAXB_CHUNK><<<g1, 128, VH_MAXB_CHUNK * c->K * sizeof(float), s>>>(c->S_fwd, c->v_template, p->static_offset, c->betas, M, c->K,
                                                                                   c->n_shape, B, c->v_shaped));
   dim3 g2((V + 127) / 128, (B + 7) / 8);
@@ -332,16 +337,14 @@ __global__ void __launch_bounds__(128) k_skin_bwd(const float* __restrict__ v_po
                                                   float* __restrict__ g_vshaped, float* __restrict__ g_offset, float* __restrict__ g_transl,
                                                   float* __restrict__ gA, float* __restrict__ gpf, float* __restrict__ acc) {
   __shared__ float shA[NB][60];
-  __shared__ float sg[128][3], svp[128][3], sgvp[128][3], sw[128][5];
   __shared__ float shr[33];
   int b0 = blockIdx.y * NB, nb = min(NB, B - b0);
   for (int i = threadIdx.x; i < nb * 60; i += blockDim.x) shA[i / 60][i % 60] = ((const float*)posebuf[b0 + i / 60].A)[i % 60];
-  int v = blockIdx.x * blockDim.x + threadIdx.x, tid = threadIdx.x;
+  int v = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
   bool on = v < V;
-  int M = 3 * V, v0 = blockIdx.x * blockDim.x;
+  int M = 3 * V;
   float w[5] = {0, 0, 0, 0, 0};
   if (on) for (int j = 0; j < 5; ++j) w[j] = lbs_w[(size_t)v * 5 + j];
-  for (int j = 0; j < 5; ++j) sw[tid][j] = w[j];
   float goff[3] = {0, 0, 0};
   float gfx = 0.f, gfy = 0.f;
   __syncthreads();
@@ -375,32 +378,29 @@ __global__ void __launch_bounds__(128) k_skin_bwd(const float* __restrict__ v_po
       float* o = g_vshaped + (size_t)b * M + 3 * v; o[0] = gvp[0]; o[1] = gvp[1]; o[2] = gvp[2];
       goff[0] += gvp[0]; goff[1] += gvp[1]; goff[2] += gvp[2];
     }
-    __syncthreads();
-    for (int c = 0; c < 3; ++c) { sg[tid][c] = g[c]; svp[tid][c] = vp[c]; sgvp[tid][c] = gvp[c]; }
-    __syncthreads();
-    int nvb = min(128, V - v0);
-    if (tid < 60) {                                   // g_A[j][r][cidx]  (lbs.py:185: T = W A)
-      int j = tid / 12, e = tid % 12, r = e / 4, ci = e % 4;
-      float s = 0.f;
-      for (int q = 0; q < nvb; ++q) s += sw[q][j] * sg[q][r] * (ci < 3 ? svp[q][ci] : 1.f);
-      atomicAdd(gA + (size_t)b * 60 + tid, s);
-    } else if (tid < 96) {                            // g_pose_feature[p]  (lbs.py:166)
-      int p = tid - 60;
-      const float* pd = posedirs + (size_t)p * M + 3 * v0;
-      float s = 0.f;
-      for (int q = 0; q < nvb; ++q) s += pd[3 * q] * sgvp[q][0] + pd[3 * q + 1] * sgvp[q][1] + pd[3 * q + 2] * sgvp[q][2];
-      atomicAdd(gpf + (size_t)b * 36 + p, s);
-    } else if (tid < 99 && g_transl) {                // translation (flame.py:624)
-      int c = tid - 96;
-      float s = 0.f;
-      for (int q = 0; q < nvb; ++q) s += sg[q][c];
-      atomicAdd(g_transl + (size_t)ts[b] * 3 + c, s);
+    // warp-level reductions, one atomic per warp and value.  g_A[j][r][ci] (lbs.py:185: T = W A)
+    for (int j = 0; j < 5; ++j)
+      for (int r = 0; r < 3; ++r)
+        for (int ci = 0; ci < 4; ++ci) {
+          float val = warp_sum(w[j] * g[r] * (ci < 3 ? vp[ci] : 1.f));
+          if (lane == 0 && val != 0.f) atomicAdd(gA + (size_t)b * 60 + j * 12 + r * 4 + ci, val);
+        }
+    for (int p = 0; p < 36; ++p) {                      // g_pose_feature[p] (lbs.py:166); loads coalesced over vertices
+      float val = 0.f;
+      if (on) { const float* pd = posedirs + (size_t)p * M + 3 * v; val = pd[0] * gvp[0] + pd[1] * gvp[1] + pd[2] * gvp[2]; }
+      val = warp_sum(val);
+      if (lane == 0 && val != 0.f) atomicAdd(gpf + (size_t)b * 36 + p, val);
     }
+    if (g_transl)
+      for (int cc = 0; cc < 3; ++cc) {                  // translation (flame.py:624)
+        float val = warp_sum(g[cc]);
+        if (lane == 0 && val != 0.f) atomicAdd(g_transl + (size_t)ts[b] * 3 + cc, val);
+      }
   }
   if (g_offset && on) { atomicAdd(g_offset + 3 * v, goff[0]); atomicAdd(g_offset + 3 * v + 1, goff[1]); atomicAdd(g_offset + 3 * v + 2, goff[2]); }
   if (opt_cam) {
     float s1 = block_sum(gfx, shr), s2 = block_sum(gfy, shr);
-    if (tid == 0) { atomicAdd(acc + ACC_GFX, s1); atomicAdd(acc + ACC_GFY, s2); }
+    if (threadIdx.x == 0) { atomicAdd(acc + ACC_GFX, s1); atomicAdd(acc + ACC_GFY, s2); }
   }
 }
 
@@ -552,8 +552,9 @@ __global__ void __launch_bounds__(1024) k_regs(RegArgs a) {
   const vhap_stage_cfg& c = a.cfg;
   int B = a.B, GB = a.global_B;
   const int* ts = a.ts;
+  const int sec = blockIdx.x;      // 0: per-frame + shape + lights, 1: offset L1, 2: offset Laplacian, 3: offset rigidity
   // ---- expression / shape (tracker.py:508-520)
-  if (c.opt_expr) {
+  if (sec == 0 && c.opt_expr) {
     float l = 0.f;
     reg_sq_rows(a.p.expr, a.g.expr, ts, B, a.n_expr, c.w_reg_expr / ((float)GB * a.n_expr), &l);
     l = block_sum(l, sh); if (threadIdx.x == 0) a.acc[ACC_REG_EXPR] += l;
@@ -562,7 +563,7 @@ __global__ void __launch_bounds__(1024) k_regs(RegArgs a) {
       l = block_sum(l, sh); if (threadIdx.x == 0) a.acc[ACC_SMOOTH_EXPR] += l;
     }
   }
-  if (c.opt_shape) {
+  if (sec == 0 && c.opt_shape) {
     float l = 0.f;
     for (int k = threadIdx.x; k < a.n_shape; k += blockDim.x) {
       float v = a.p.shape[k], w = c.shared_scale * c.w_reg_shape / a.n_shape;
@@ -572,14 +573,14 @@ __global__ void __launch_bounds__(1024) k_regs(RegArgs a) {
     l = block_sum(l, sh); if (threadIdx.x == 0) a.acc[ACC_REG_SHAPE] += l;
   }
   // ---- pose smoothness (tracker.py:616-627)
-  if (c.opt_pose && c.tracking) {
+  if (sec == 0 && c.opt_pose && c.tracking) {
     float l = 0.f;
     reg_smooth_rows(a.p.translation, a.g.translation, ts, B, 3, a.p.n_timesteps, c.w_smooth_trans / (3.f * GB), &l);
     reg_smooth_rows(a.p.rotation, a.g.rotation, ts, B, 3, a.p.n_timesteps, c.w_smooth_rot / (3.f * GB), &l);
     l = block_sum(l, sh); if (threadIdx.x == 0) a.acc[ACC_SMOOTH_POSE] += l;
   }
   // ---- joints (tracker.py:496-505, 629-680)
-  if (c.opt_joints) {
+  if (sec == 0 && c.opt_joints) {
     float l = 0.f;
     reg_joint_rot(a.p.neck_pose, a.g.neck_pose, ts, B, GB, 3, 0, c.w_reg_neck, &l);
     reg_joint_rot(a.p.jaw_pose, a.g.jaw_pose, ts, B, GB, 3, 0, c.w_reg_jaw, &l);
@@ -609,7 +610,7 @@ __global__ void __launch_bounds__(1024) k_regs(RegArgs a) {
     }
   }
   // ---- lights (tracker.py:542-545)
-  if (c.opt_lights && c.w_reg_light >= 0.f) {
+  if (sec == 0 && c.opt_lights && c.w_reg_light >= 0.f) {
     float l = 0.f;
     for (int i = threadIdx.x; i < 27; i += blockDim.x) {
       float u = i < 3 ? 3.5449077018110318f : 0.f;          // sqrt(4 pi)
@@ -623,7 +624,7 @@ __global__ void __launch_bounds__(1024) k_regs(RegArgs a) {
   if (c.opt_static_offset && a.p.static_offset) {
     const float* off = a.p.static_offset;
     int V = a.V;
-    if (c.w_reg_offset >= 0.f) {
+    if (sec == 1 && c.w_reg_offset >= 0.f) {
       float l = 0.f, w = c.shared_scale * c.w_reg_offset / (3.f * V);
       for (int i = threadIdx.x; i < 3 * V; i += blockDim.x) {
         float wv = a.w_off ? a.w_off[i / 3] : 1.f, o = off[i];
@@ -632,7 +633,7 @@ __global__ void __launch_bounds__(1024) k_regs(RegArgs a) {
       }
       l = block_sum(l, sh); if (threadIdx.x == 0) a.acc[ACC_REG_OFFSET] += l;
     }
-    if (c.w_reg_offset_lap >= 0.f) {
+    if (sec == 2 && c.w_reg_offset_lap >= 0.f) {
       // L(base + off) - L(base) == L off  (uniform Laplacian is linear; tracker.py:682-690, flame.py:196-201)
       float l = 0.f, w = c.shared_scale * c.w_reg_offset_lap / V;
       for (int i = threadIdx.x; i < V; i += blockDim.x) {
@@ -655,7 +656,7 @@ __global__ void __launch_bounds__(1024) k_regs(RegArgs a) {
           }
       l = block_sum(l, sh); if (threadIdx.x == 0) a.acc[ACC_REG_OFFSET_LAP] += l;
     }
-    if (c.w_reg_offset_rigid >= 0.f && a.n_rigid > 0) {
+    if (sec == 3 && c.w_reg_offset_rigid >= 0.f && a.n_rigid > 0) {
       float ltot = 0.f;
       for (int r = 0; r < a.n_rigid; ++r) {
         int s0 = a.rigid_indptr[r], n = a.rigid_indptr[r + 1] - s0;
@@ -690,5 +691,5 @@ void launch_regs(vhap_ctx* c, const vhap_params* p, const vhap_frame_batch* fb, 
   a.ts = fb->timesteps; a.B = fb->B; a.V = c->V; a.n_shape = c->n_shape; a.n_expr = c->n_expr; a.global_B = global_B;
   a.w_off = c->w_off; a.w_off_lap = c->w_off_lap; a.lap_indptr = c->lap_indptr; a.lap_idx = c->lap_idx; a.lap_val = c->lap_val; a.lap_y = c->lap_y;
   a.rigid_indptr = c->rigid_indptr; a.rigid_vids = c->rigid_vids; a.n_rigid = c->n_rigid; a.acc = c->acc;
-  LAUNCH(c, KID_REGS, s, k_regs<<<1, 1024, 0, s>>>(a));
+  LAUNCH(c, KID_REGS, s, k_regs<<<4, 1024, 0, s>>>(a));
 }

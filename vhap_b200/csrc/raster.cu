@@ -69,30 +69,24 @@ __global__ void __launch_bounds__(256) k_bin(const i4* __restrict__ snap, const 
     }
 }
 
-// exclusive scan of n ints by one block (n up to a few hundred thousand)
+// exclusive scan of n ints by one block: each thread sums a contiguous chunk, the 1024 chunk sums are scanned in shared
+// memory, then every thread rewrites its chunk
 __global__ void __launch_bounds__(1024) k_scan(const int* __restrict__ in, int* __restrict__ out, int n) {
   __shared__ int sh[1024];
-  __shared__ int carry;
-  if (threadIdx.x == 0) carry = 0;
+  int chunk = (n + 1023) / 1024;
+  int i0 = threadIdx.x * chunk, i1 = min(i0 + chunk, n);
+  int s = 0;
+  for (int i = i0; i < i1; ++i) s += in[i];
+  sh[threadIdx.x] = s;
   __syncthreads();
-  for (int base = 0; base < n; base += 1024 * 4) {
-    int i0 = base + threadIdx.x * 4;
-    int v[4], s = 0;
-    for (int k = 0; k < 4; ++k) { v[k] = (i0 + k < n) ? in[i0 + k] : 0; s += v[k]; }
-    sh[threadIdx.x] = s;
+  for (int o = 1; o < 1024; o <<= 1) {
+    int t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
     __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-      int t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
-      __syncthreads();
-      sh[threadIdx.x] += t;
-      __syncthreads();
-    }
-    int excl = sh[threadIdx.x] - s + carry;
-    for (int k = 0; k < 4; ++k) { if (i0 + k < n) out[i0 + k] = excl; excl += v[k]; }
-    __syncthreads();
-    if (threadIdx.x == 1023) carry += sh[1023];
+    sh[threadIdx.x] += t;
     __syncthreads();
   }
+  int run = sh[threadIdx.x] - s;
+  for (int i = i0; i < i1; ++i) { int v = in[i]; out[i] = run; run += v; }
 }
 
 struct FineTri {        // shared-memory record, struct of arrays

@@ -1,22 +1,25 @@
-// Fused render passes (kernels around render_bodies.cuh):
-//   k_passA      shade every foreground pixel, write its composite colour, per-block reg_diffuse partials + max
-//   k_pool_*     stable compaction of pixel indices per colour cluster (pools of render_nvdiffrast.py:445-459)
-//   k_passB      disturbance + antialias + L1 partial sums + sign bytes
-//   k_finalize   global scalars (photo scale = w/(3 n_fg), reg_diffuse scale / arg-max), loss values
-//   k_passC      analytic backward to clip positions, vertex normals, texels, lights
+// Fused render passes (kernels around render_bodies.cuh).  Order per forward:
+//   k_pool_count / k_pool_scan / k_pool_scatter   stable compaction of pixel indices per colour cluster (the pools of
+//                     render_nvdiffrast.py:445-459); clusters >= 1 together form the compacted FOREGROUND pixel list
+//   k_passA      shade every foreground pixel (walks the compacted list), write its composite colour, reg_diffuse partials
+//   k_passB      disturbance + antialias + L1 partial sums + sign bytes, all pixels
+//   k_forward_slab / k_finalize   global scalars (photo scale = w/(3 n_fg), reg_diffuse scale / arg-max), loss values
+//   k_passC      analytic backward over the compacted foreground list -> clip positions, vertex normals, texels, lights
+// All per-pixel kernels are persistent grid-stride kernels sized to the machine (148 SMs x 8 CTAs of 256 threads).
 // Replaces NVDiffRenderer.render_rgba (vhap/util/render_nvdiffrast.py:354-484), compute_photometric_energy
 // (vhap/model/tracker.py:391-478), reg_diffuse (tracker.py:547-550) and their autograd.
 #include "engine.h"
 #include "accum.h"
 
-#define PB 256     // pixels (threads) per block in the per-pixel passes
+#define PB 256                 // threads per block in the per-pixel passes
+#define NPERSIST (148 * 8)     // persistent grid: one wave of 8 resident CTAs per SM
 
 __device__ __forceinline__ float warp_sum_r(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
 
-// reduce `n` per-thread values across the block and write them to row[blockIdx.x]; sh must hold 8*n floats (256 threads)
+// reduce N per-thread values across the block and write them to row[0..N); sh must hold 8*N floats (256 threads)
 template <int N>
 __device__ void block_reduce_store(float* vals, float* sh, float* row) {
   int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -35,24 +38,90 @@ __device__ __forceinline__ unsigned long long pack_max(float v, int idx) {
   u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);          // order-preserving map float -> uint
   return ((unsigned long long)u << 32) | (unsigned)idx;
 }
-__host__ __device__ __forceinline__ float unpack_max_val(unsigned long long p) {
+__device__ __forceinline__ float unpack_max_val(unsigned long long p) {
   unsigned u = (unsigned)(p >> 32);
   u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
-#if defined(__CUDA_ARCH__)
   return __uint_as_float(u);
-#else
-  float f; memcpy(&f, &u, 4); return f;
-#endif
 }
 
+// ---------------------------------------------------------------------------------------------- cluster pools
+__global__ void __launch_bounds__(PB) k_pool_count(const int* __restrict__ tri_id, const uint8_t* __restrict__ fid2cid, size_t n, int* __restrict__ blk_count) {
+  __shared__ int cnt[16];
+  if (threadIdx.x < 16) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  size_t pix = (size_t)blockIdx.x * PB + threadIdx.x;
+  int cid = pix < n ? fid2cid[tri_id[pix]] : -1;
+  unsigned any = __ballot_sync(0xffffffffu, cid > 0);
+  unsigned m0 = __ballot_sync(0xffffffffu, cid == 0);
+  if ((threadIdx.x & 31) == 0 && m0) atomicAdd(&cnt[0], __popc(m0));
+  if (any)                                                       // warps that are all background skip the per-cluster ballots
+    for (int c = 1; c < 16; ++c) {
+      unsigned m = __ballot_sync(0xffffffffu, cid == c);
+      if ((threadIdx.x & 31) == 0 && m) atomicAdd(&cnt[c], __popc(m));
+    }
+  __syncthreads();
+  if (threadIdx.x < 16) blk_count[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = cnt[threadIdx.x];    // [16][nblk]
+}
+
+// exclusive scan of the [16][nblk] counts as ONE sequence (pixel lists are laid out cluster after cluster) by a single
+// block: every thread sums a contiguous chunk, the 1024 chunk sums are scanned in shared memory, chunks are rewritten.
+__global__ void __launch_bounds__(1024) k_pool_scan(const int* __restrict__ in, int* __restrict__ out, int nblk, int* __restrict__ base, int* __restrict__ count) {
+  __shared__ int sh[1024];
+  int n = 16 * nblk, chunk = (n + 1023) / 1024;
+  int i0 = threadIdx.x * chunk, i1 = min(i0 + chunk, n);
+  int s = 0;
+  for (int i = i0; i < i1; ++i) s += in[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    int t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+    __syncthreads();
+    sh[threadIdx.x] += t;
+    __syncthreads();
+  }
+  int run = sh[threadIdx.x] - s;
+  for (int i = i0; i < i1; ++i) { int v = in[i]; out[i] = run; run += v; }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    int c = threadIdx.x;
+    int b = out[(size_t)c * nblk];
+    int e = c < 15 ? out[(size_t)(c + 1) * nblk] : sh[1023];
+    base[c] = b; count[c] = e - b;
+  }
+}
+
+__global__ void __launch_bounds__(PB) k_pool_scatter(const int* __restrict__ tri_id, const uint8_t* __restrict__ fid2cid, size_t n,
+                                                     const int* __restrict__ blk_off, int* __restrict__ pool_list) {
+  __shared__ int wcnt[16][PB / 32];
+  size_t pix = (size_t)blockIdx.x * PB + threadIdx.x;
+  int cid = pix < n ? fid2cid[tri_id[pix]] : -1;
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int rank = 0;
+  unsigned any = __ballot_sync(0xffffffffu, cid > 0);
+  for (int c = 0; c < 16; ++c) {
+    unsigned m = (c == 0 || any) ? __ballot_sync(0xffffffffu, cid == c) : 0u;
+    if (cid == c) rank = __popc(m & ((1u << lane) - 1));
+    if (lane == 0) wcnt[c][w] = __popc(m);
+  }
+  __syncthreads();
+  if (cid >= 0) {
+    int before = 0;
+    for (int k = 0; k < w; ++k) before += wcnt[cid][k];
+    pool_list[blk_off[(size_t)cid * gridDim.x + blockIdx.x] + before + rank] = (int)pix;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- passes
 __global__ void __launch_bounds__(PB) k_passA(PassArgs P, float* __restrict__ partials, unsigned long long* __restrict__ maxslot) {
   __shared__ float sh[8 * 2];
   __shared__ unsigned long long shm[8];
   const RenderArgs& A = P.R;
-  size_t pix = (size_t)blockIdx.x * PB + threadIdx.x, n = (size_t)A.B * A.H * A.W;
+  int n_fg = A.B * A.H * A.W - P.pool_count[0];
+  const int* list = P.pool_list + P.pool_base[1];
   float acc[2] = {0.f, 0.f}; float mx = -INFINITY; int mxi = 0;
-  if (pix < n) {
-    int x = pix % A.W, y = (pix / A.W) % A.H, b = pix / ((size_t)A.W * A.H);
+  for (int i = blockIdx.x * PB + threadIdx.x; i < n_fg; i += gridDim.x * PB) {
+    int pix = list[i];
+    int x = pix % A.W, y = (pix / A.W) % A.H, b = pix / (A.W * A.H);
     passA_body(P, b, y, x, acc, mx, mxi);
   }
   block_reduce_store<2>(acc, sh, partials + (size_t)blockIdx.x * VH_NPART);
@@ -66,117 +135,52 @@ __global__ void __launch_bounds__(PB) k_passA(PassArgs P, float* __restrict__ pa
   }
 }
 
-// ---- cluster pools: count per block, scan, stable scatter
-__global__ void __launch_bounds__(PB) k_pool_count(const int* __restrict__ tri_id, const uint8_t* __restrict__ fid2cid, size_t n, int* __restrict__ blk_count) {
-  __shared__ int cnt[16];
-  if (threadIdx.x < 16) cnt[threadIdx.x] = 0;
-  __syncthreads();
-  size_t pix = (size_t)blockIdx.x * PB + threadIdx.x;
-  int cid = pix < n ? fid2cid[tri_id[pix]] : -1;
-  for (int c = 0; c < 16; ++c) {
-    unsigned m = __ballot_sync(0xffffffffu, cid == c);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&cnt[c], __popc(m));
-  }
-  __syncthreads();
-  if (threadIdx.x < 16) blk_count[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = cnt[threadIdx.x];    // [16][nblk]
-}
-
-// scans the [16][nblk] counts as ONE sequence -> pixel lists are laid out cluster after cluster; also emits base/count
-__global__ void __launch_bounds__(1024) k_pool_scan(const int* __restrict__ in, int* __restrict__ out, int nblk, int* __restrict__ base, int* __restrict__ count) {
-  __shared__ int sh[1024];
-  __shared__ int carry;
-  int n = 16 * nblk;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (int b0 = 0; b0 < n; b0 += 1024 * 4) {
-    int i0 = b0 + threadIdx.x * 4;
-    int v[4], s = 0;
-    for (int k = 0; k < 4; ++k) { v[k] = (i0 + k < n) ? in[i0 + k] : 0; s += v[k]; }
-    sh[threadIdx.x] = s;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-      int t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
-      __syncthreads();
-      sh[threadIdx.x] += t;
-      __syncthreads();
-    }
-    int excl = sh[threadIdx.x] - s + carry;
-    for (int k = 0; k < 4; ++k) { if (i0 + k < n) out[i0 + k] = excl; excl += v[k]; }
-    __syncthreads();
-    if (threadIdx.x == 1023) carry += sh[1023];
-    __syncthreads();
-  }
-  __syncthreads();
-  if (threadIdx.x < 16) {
-    int c = threadIdx.x;
-    int b = out[(size_t)c * nblk];
-    int e = c < 15 ? out[(size_t)(c + 1) * nblk] : carry;
-    base[c] = b; count[c] = e - b;
-  }
-}
-
-__global__ void __launch_bounds__(PB) k_pool_scatter(const int* __restrict__ tri_id, const uint8_t* __restrict__ fid2cid, size_t n,
-                                                     const int* __restrict__ blk_off, int* __restrict__ pool_list) {
-  __shared__ int wcnt[16][PB / 32];
-  size_t pix = (size_t)blockIdx.x * PB + threadIdx.x;
-  int cid = pix < n ? fid2cid[tri_id[pix]] : -1;
-  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  int rank = 0;
-  for (int c = 0; c < 16; ++c) {
-    unsigned m = __ballot_sync(0xffffffffu, cid == c);
-    if (cid == c) rank = __popc(m & ((1u << lane) - 1));
-    if (lane == 0) wcnt[c][w] = __popc(m);
-  }
-  __syncthreads();
-  if (cid >= 0) {
-    int before = 0;
-    for (int k = 0; k < w; ++k) before += wcnt[cid][k];
-    pool_list[blk_off[(size_t)cid * gridDim.x + blockIdx.x] + before + rank] = (int)pix;
-  }
-}
-
 __global__ void __launch_bounds__(PB) k_passB(PassArgs P, float* __restrict__ partials) {
   __shared__ float sh[8 * 2];
   const RenderArgs& A = P.R;
-  size_t pix = (size_t)blockIdx.x * PB + threadIdx.x, n = (size_t)A.B * A.H * A.W;
+  int n = A.B * A.H * A.W;
   float acc[2] = {0.f, 0.f};
-  if (pix < n) {
-    int x = pix % A.W, y = (pix / A.W) % A.H, b = pix / ((size_t)A.W * A.H);
+  for (int pix = blockIdx.x * PB + threadIdx.x; pix < n; pix += gridDim.x * PB) {
+    int x = pix % A.W, y = (pix / A.W) % A.H, b = pix / (A.W * A.H);
     passB_body(P, b, y, x, acc);
   }
   block_reduce_store<2>(acc, sh, partials + (size_t)blockIdx.x * VH_NPART + 2);
 }
 
-// sums the per-block partial rows (columns 0..3) into acc[ACC_VARSUM, ACC_NFGPIX, ACC_ABSERR, ACC_NFG]
-__global__ void __launch_bounds__(1024) k_reduce_partials(const float* __restrict__ partials, int rows, int ncol, float* __restrict__ out, const int* __restrict__ slot) {
-  __shared__ float sh[32];
-  for (int c = 0; c < ncol; ++c) {
-    float s = 0.f;
-    for (int r = threadIdx.x; r < rows; r += blockDim.x) s += partials[(size_t)r * VH_NPART + c];
-    s = warp_sum_r(s);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x < 32) { float t = sh[threadIdx.x]; t = warp_sum_r(t); if (threadIdx.x == 0) out[slot[c]] += t; }
-  }
-}
-
 __global__ void __launch_bounds__(PB) k_passC(PassArgs P, const float* __restrict__ ext_grad, float* __restrict__ partials) {
   __shared__ float sh[8 * 27];
   const RenderArgs& A = P.R;
-  size_t pix = (size_t)blockIdx.x * PB + threadIdx.x, n = (size_t)A.B * A.H * A.W;
+  int n_fg = A.B * A.H * A.W - P.pool_count[0];
+  const int* list = P.pool_list + P.pool_base[1];
   float gl[27];
 #pragma unroll
   for (int i = 0; i < 27; ++i) gl[i] = 0.f;
-  if (pix < n) {
-    int x = pix % A.W, y = (pix / A.W) % A.H, b = pix / ((size_t)A.W * A.H);
+  for (int i = blockIdx.x * PB + threadIdx.x; i < n_fg; i += gridDim.x * PB) {
+    int pix = list[i];
+    int x = pix % A.W, y = (pix / A.W) % A.H, b = pix / (A.W * A.H);
     passC_body(P, b, y, x, ext_grad, gl);
   }
   block_reduce_store<27>(gl, sh, partials + (size_t)blockIdx.x * VH_NPART + 4);
 }
 
+// column sums of the [rows][VH_NPART] partial matrix: dst[slot ? slot[c] : c] += sum_r partials[r][col0 + c]
+__global__ void __launch_bounds__(256) k_reduce_cols(const float* __restrict__ partials, int rows, int col0, int ncol, float* __restrict__ dst,
+                                                     const int* __restrict__ slot) {
+  __shared__ float sh[8][32];
+  int c = threadIdx.x & 31, g = threadIdx.x >> 5;
+  float s = 0.f;
+  if (c < ncol)
+    for (int r = blockIdx.x * 8 + g; r < rows; r += gridDim.x * 8) s += partials[(size_t)r * VH_NPART + col0 + c];
+  sh[g][c] = s;
+  __syncthreads();
+  if (g == 0 && c < ncol) {
+    for (int k = 1; k < 8; ++k) s += sh[k][c];
+    atomicAdd(dst + (slot ? slot[c] : c), s);
+  }
+}
+
 // reduce_slab layout (floats): [0] sum |err|  [1] n(alpha_aa>0)  [2] sum var_c(diffuse) incl. background  [3] max diffuse
-//                              [4] this rank's arg-max index (int bits; -1 = background)  [5] local max (to find the owner)
+//                              [4] this rank's arg-max index (int bits; -1 = background)  [5] local max (to find the owner)  [6] n background px
 __global__ void k_forward_slab(const float* __restrict__ acc, const unsigned long long* __restrict__ maxslot, const float* __restrict__ lights,
                                float n_pix_total, float* __restrict__ slab) {
   float nfgpix = acc[ACC_NFGPIX], n_bg = n_pix_total - nfgpix;
@@ -224,14 +228,6 @@ __global__ void k_finalize(const float* __restrict__ slab, const float* __restri
   }
 }
 
-__global__ void k_lights_reduce(const float* __restrict__ partials, int rows, float* __restrict__ g_lights) {
-  int i = threadIdx.x;      // 27 active threads per block, blocks stride over rows
-  if (i >= 27) return;
-  float s = 0.f;
-  for (int r = blockIdx.x; r < rows; r += gridDim.x) s += partials[(size_t)r * VH_NPART + 4 + i];
-  atomicAdd(g_lights + i, s);
-}
-
 // flips a raster-orientation float4 plane into image orientation
 __global__ void k_flip_plane(const float4* __restrict__ in, float4* __restrict__ out, int B, int H, int W) {
   size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n = (size_t)B * H * W;
@@ -276,31 +272,38 @@ void fill_render_args(vhap_ctx* c, PassArgs& P, const vhap_frame_batch* fb, cons
   P.scal = c->scal; P.g_clip = c->g_clip; P.g_vnorm = c->g_vnorm; P.g_tex = nullptr;
 }
 
+static int* slot_table(vhap_ctx* c) {      // device copy of the acc[] slots of partial columns 0..3
+  static int* d_slot[16] = {nullptr};
+  int dev = c->device & 15;
+  if (!d_slot[dev]) {
+    static const int h_slot[4] = {ACC_VARSUM, ACC_NFGPIX, ACC_ABSERR, ACC_NFG};
+    cudaMalloc(&d_slot[dev], sizeof(h_slot));
+    cudaMemcpy(d_slot[dev], h_slot, sizeof(h_slot), cudaMemcpyHostToDevice);
+  }
+  return d_slot[dev];
+}
+
 void launch_render_forward(vhap_ctx* c, PassArgs& P, cudaStream_t s) {
   const RenderArgs& A = P.R;
   size_t n = (size_t)A.B * A.H * A.W;
   int nblk = (int)((n + PB - 1) / PB);
+  int* slots = slot_table(c);
   cudaMemsetAsync(c->maxslot, 0, sizeof(unsigned long long), s);
-  LAUNCH(c, KID_PASSA, s, k_passA<<<nblk, PB, 0, s>>>(P, c->partials, c->maxslot));
-  if (P.disturb) {
-    LAUNCH(c, KID_POOL_COUNT, s, k_pool_count<<<nblk, PB, 0, s>>>(A.tri_id, A.fid2cid, n, c->pool_blk_count));
-    LAUNCH(c, KID_POOL_SCAN, s, k_pool_scan<<<1, 1024, 0, s>>>(c->pool_blk_count, c->pool_blk_off, nblk, c->pool_base, c->pool_count));
-    LAUNCH(c, KID_POOL_SCATTER, s, k_pool_scatter<<<nblk, PB, 0, s>>>(A.tri_id, A.fid2cid, n, c->pool_blk_off, c->pool_list));
+  if (c->want_planes) {
+    cudaMemsetAsync(c->plane_albedo, 0, n * 16, s); cudaMemsetAsync(c->plane_normal, 0, n * 16, s); cudaMemsetAsync(c->plane_diffuse, 0, n * 16, s);
   }
-  LAUNCH(c, KID_PASSB, s, k_passB<<<nblk, PB, 0, s>>>(P, c->partials));
-  static const int h_slot[4] = {ACC_VARSUM, ACC_NFGPIX, ACC_ABSERR, ACC_NFG};
-  static int* d_slot = nullptr;
-  if (!d_slot) { cudaMalloc(&d_slot, sizeof(h_slot)); cudaMemcpy(d_slot, h_slot, sizeof(h_slot), cudaMemcpyHostToDevice); }
-  LAUNCH(c, KID_REDUCE, s, k_reduce_partials<<<1, 1024, 0, s>>>(c->partials, nblk, 4, c->acc, d_slot));
+  LAUNCH(c, KID_POOL_COUNT, s, k_pool_count<<<nblk, PB, 0, s>>>(A.tri_id, A.fid2cid, n, c->pool_blk_count));
+  LAUNCH(c, KID_POOL_SCAN, s, k_pool_scan<<<1, 1024, 0, s>>>(c->pool_blk_count, c->pool_blk_off, nblk, c->pool_base, c->pool_count));
+  LAUNCH(c, KID_POOL_SCATTER, s, k_pool_scatter<<<nblk, PB, 0, s>>>(A.tri_id, A.fid2cid, n, c->pool_blk_off, c->pool_list));
+  int grid = nblk < NPERSIST ? nblk : NPERSIST;
+  LAUNCH(c, KID_PASSA, s, k_passA<<<grid, PB, 0, s>>>(P, c->partials, c->maxslot));
+  LAUNCH(c, KID_PASSB, s, k_passB<<<grid, PB, 0, s>>>(P, c->partials));
+  LAUNCH(c, KID_REDUCE, s, k_reduce_cols<<<16, 256, 0, s>>>(c->partials, grid, 0, 4, c->acc, slots));
 }
 
 void launch_forward_slab(vhap_ctx* c, const PassArgs& P, const float* lights, float* slab, cudaStream_t s) {
   const RenderArgs& A = P.R;
   LAUNCH(c, KID_SLAB, s, k_forward_slab<<<1, 1, 0, s>>>(c->acc, c->maxslot, lights, (float)((size_t)A.B * A.H * A.W), slab));
-}
-
-void launch_render_finalize(vhap_ctx* c, PassArgs& P, const vhap_stage_cfg* cfg, const float* reduce_slab, int global_B, const float* lights, cudaStream_t s) {
-  (void)c; (void)P; (void)cfg; (void)reduce_slab; (void)global_B; (void)lights; (void)s;
 }
 
 void launch_finalize(vhap_ctx* c, const PassArgs& P, const vhap_stage_cfg* cfg, const float* slab_global, const float* slab_local, int global_B,
@@ -314,6 +317,7 @@ void launch_render_backward(vhap_ctx* c, PassArgs& P, const vhap_stage_cfg* cfg,
   const RenderArgs& A = P.R;
   size_t n = (size_t)A.B * A.H * A.W;
   int nblk = (int)((n + PB - 1) / PB);
-  LAUNCH(c, KID_PASSC, s, k_passC<<<nblk, PB, 0, s>>>(P, ext_grad, c->partials));
-  if (g_lights) LAUNCH(c, KID_LIGHTS_REDUCE, s, k_lights_reduce<<<64, 32, 0, s>>>(c->partials, nblk, g_lights));
+  int grid = nblk < NPERSIST ? nblk : NPERSIST;
+  LAUNCH(c, KID_PASSC, s, k_passC<<<grid, PB, 0, s>>>(P, ext_grad, c->partials));
+  if (g_lights) LAUNCH(c, KID_LIGHTS_REDUCE, s, k_reduce_cols<<<16, 256, 0, s>>>(c->partials, grid, 4, 27, g_lights, nullptr));
 }

@@ -276,6 +276,10 @@ VH_HD void passC_body(const PassArgs& P, int b, int y, int x, const float* ext_g
   const RenderArgs& A = P.R;
   size_t pix = ((size_t)b * A.H + y) * A.W + x;
   int id = A.tri_id[pix];
+  // Only FOREGROUND pixels are visited (the kernel walks the compacted foreground list): a background pixel has no
+  // parameters behind its colour, and the position gradient of a (foreground, background) pair is owned by its
+  // foreground pixel; (foreground, foreground) pairs are owned by their pixel 0.
+  if (id <= 0) return;
   float scale = P.scal[0];
   f3 gp = ext_grad ? mk3(ext_grad[pix * 4], ext_grad[pix * 4 + 1], ext_grad[pix * 4 + 2]) : sign_grad(P.signs[pix], scale);
   float own_w;
@@ -301,8 +305,8 @@ VH_HD void passC_body(const PassArgs& P, int b, int y, int x, const float* ext_g
     f3 gq = ext_grad ? mk3(ext_grad[qpix * 4], ext_grad[qpix * 4 + 1], ext_grad[qpix * 4 + 2]) : sign_grad(P.signs[qpix], scale);
     if (modifies_p) self_w -= a;                  // final(p) = D(p) + a (D(q) - D(p))
     else { gD.x += a * gq.x; gD.y += a * gq.y; gD.z += a * gq.z; }   // final(q) = D(q) + a (D(p) - D(q))
-    // position gradient: handled once per pair, by its pixel 0
-    if (p_is0 && P.g_clip) {
+    // position gradient: handled once per pair (see the ownership rule above)
+    if ((p_is0 || idq <= 0) && P.g_clip) {
       f4 Dq = disturbed_color(P, b, qy, qx, idq, nullptr);
       // target of the blend and the "other" colour
       f3 g_t = modifies_p ? gp : gq;
@@ -317,7 +321,6 @@ VH_HD void passC_body(const PassArgs& P, int b, int y, int x, const float* ext_g
     }
   }
   gD.x += self_w * gp.x; gD.y += self_w * gp.y; gD.z += self_w * gp.z;
-  if (id <= 0) return;                             // background: constant colour, no parameters behind it
   f3 g_rgb = gD * own_w;
   // reg_diffuse on diffuse_detach_normal (tracker.py:547-550): variance term + global max term
   f3 g_dd = mk3(0, 0, 0);

@@ -17,22 +17,50 @@ __global__ void k_tex_level0(const float* __restrict__ painted, const float* __r
   out[i] = v;
 }
 
-// 2x2 box filter, one level
-__global__ void k_mip_down(const f4* __restrict__ src, f4* __restrict__ dst, int sd) {   // sd = destination size
-  int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= sd || y >= sd) return;
-  int ss = sd * 2;
-  f4 a = src[(size_t)(2 * y) * ss + 2 * x], b = src[(size_t)(2 * y + 1) * ss + 2 * x];
-  f4 c = src[(size_t)(2 * y) * ss + 2 * x + 1], d = src[(size_t)(2 * y + 1) * ss + 2 * x + 1];
+// 2x2 box-filter pyramid, up to 5 levels per launch: each CTA loads a 32x32 tile of the source level into shared memory and
+// emits the 16x16, 8x8, 4x4, 2x2 and 1x1 reductions of that tile to the next levels (dst level k has size ssz >> (k+1)).
+__device__ __forceinline__ f4 avg4(const f4& a, const f4& b, const f4& c, const f4& d) {
   f4 o = {0.25f * (a.x + b.x + c.x + d.x), 0.25f * (a.y + b.y + c.y + d.y), 0.25f * (a.z + b.z + c.z + d.z), 0.f};
-  dst[(size_t)y * sd + x] = o;
+  return o;
+}
+__global__ void __launch_bounds__(256) k_mip_down(const f4* __restrict__ src, f4* __restrict__ pyr_base, int ssz, int nlev,
+                                                  int o1, int o2, int o3, int o4, int o5) {
+  __shared__ f4 A[32][33];
+  __shared__ f4 Bf[16][17];
+  int tile = ssz < 32 ? ssz : 32;                  // source tile edge handled by this CTA
+  int tx0 = blockIdx.x * tile, ty0 = blockIdx.y * tile;
+  for (int i = threadIdx.x; i < tile * tile; i += blockDim.x) {
+    int x = i % tile, y = i / tile;
+    A[y][x] = src[(size_t)(ty0 + y) * ssz + tx0 + x];
+  }
+  __syncthreads();
+  const int offs[5] = {o1, o2, o3, o4, o5};
+  int cur = tile;                                   // edge of the data currently in A (even levels) / Bf (odd levels)
+  for (int k = 0; k < nlev; ++k) {
+    int nxt = cur >> 1, dsz = ssz >> (k + 1);
+    f4* dst = pyr_base + offs[k];
+    int dx0 = tx0 >> (k + 1), dy0 = ty0 >> (k + 1);
+    for (int i = threadIdx.x; i < nxt * nxt; i += blockDim.x) {
+      int x = i % nxt, y = i / nxt;
+      f4 o = (k & 1) ? avg4(Bf[2 * y][2 * x], Bf[2 * y + 1][2 * x], Bf[2 * y][2 * x + 1], Bf[2 * y + 1][2 * x + 1])
+                     : avg4(A[2 * y][2 * x], A[2 * y + 1][2 * x], A[2 * y][2 * x + 1], A[2 * y + 1][2 * x + 1]);
+      dst[(size_t)(dy0 + y) * dsz + dx0 + x] = o;
+      if (k & 1) A[y][x] = o; else Bf[y][x] = o;
+    }
+    __syncthreads();
+    cur = nxt;
+  }
 }
 
 static void build_mips(vhap_ctx* c, f4* pyr, cudaStream_t s) {
-  for (int l = 1; l <= c->max_level; ++l) {
-    int sd = c->T >> l;
-    dim3 blk(16, 16), grd((sd + 15) / 16, (sd + 15) / 16);
-    LAUNCH(c, KID_MIP, s, k_mip_down<<<grd, blk, 0, s>>>(pyr + c->mip_off[l - 1], pyr + c->mip_off[l], sd));
+  int l = 0;
+  while (l < c->max_level) {
+    int ssz = c->T >> l, nlev = c->max_level - l < 5 ? c->max_level - l : 5;
+    int tile = ssz < 32 ? ssz : 32, g = ssz / tile;
+    int o[5] = {0, 0, 0, 0, 0};
+    for (int k = 0; k < nlev; ++k) o[k] = c->mip_off[l + 1 + k];
+    LAUNCH(c, KID_MIP, s, k_mip_down<<<dim3(g, g), 256, 0, s>>>(pyr + c->mip_off[l], pyr, ssz, nlev, o[0], o[1], o[2], o[3], o[4]));
+    l += nlev;
   }
 }
 
@@ -171,6 +199,29 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
   float mi = 0.9f * m[i] + 0.1f * gi, vi = 0.999f * v[i] + 0.001f * gi * gi;
   m[i] = mi; v[i] = vi;
   p[i] -= step_size * mi / (sqrtf(vi) / bc2_sqrt + 1e-8f);
+}
+
+struct AdamSegs { int n_seg; int off[24]; int len[24]; float lr[24]; };
+__global__ void k_adam_multi(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, AdamSegs sg, int total,
+                             float inv_bc1, float bc2_sqrt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int k = 0, base = 0;
+  while (k < sg.n_seg - 1 && i >= base + sg.len[k]) { base += sg.len[k]; ++k; }
+  int j = sg.off[k] + (i - base);
+  float gi = g[j];
+  float mi = 0.9f * m[j] + 0.1f * gi, vi = 0.999f * v[j] + 0.001f * gi * gi;
+  m[j] = mi; v[j] = vi;
+  p[j] -= sg.lr[k] * inv_bc1 * mi / (sqrtf(vi) / bc2_sqrt + 1e-8f);
+}
+void launch_adam_multi(vhap_ctx* c, float* p, const float* g, float* m, float* v, int n_seg, const int64_t* off, const int64_t* len, const float* lr,
+                       int step, cudaStream_t s) {
+  AdamSegs sg; memset(&sg, 0, sizeof(sg));
+  sg.n_seg = n_seg > 24 ? 24 : n_seg;
+  int total = 0;
+  for (int k = 0; k < sg.n_seg; ++k) { sg.off[k] = (int)off[k]; sg.len[k] = (int)len[k]; sg.lr[k] = lr[k]; total += (int)len[k]; }
+  float bc1 = 1.f - powf(0.9f, (float)step), bc2s = sqrtf(1.f - powf(0.999f, (float)step));
+  if (total > 0) LAUNCH(c, KID_ADAM, s, k_adam_multi<<<(total + 255) / 256, 256, 0, s>>>(p, g, m, v, sg, total, 1.f / bc1, bc2s));
 }
 
 void launch_adam(vhap_ctx* c, float* p, const float* g, float* m, float* v, int64_t n, float lr, int step, cudaStream_t s) {

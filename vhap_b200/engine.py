@@ -318,10 +318,13 @@ class Engine:
                 self.rebuild_texture()
         if allreduce_fn is not None:
             allreduce_fn(self.grad)
-        for name in groups:
-            o, n = self.layout[name]
-            self._ck(self.L.vhap_adam(self.ctx, self.slab[o:o + n].data_ptr(), self.grad[o:o + n].data_ptr(), self.m[o:o + n].data_ptr(),
-                                      self.v[o:o + n].data_ptr(), n, self._lr(name), self.step_count, s), None)
+        if groups:
+            off = np.asarray([self.layout[g][0] for g in groups], np.int64)
+            ln = np.asarray([self.layout[g][1] for g in groups], np.int64)
+            lr = np.asarray([self._lr(g) for g in groups], np.float32)
+            hp = lambda a: a.ctypes.data_as(C.c_void_p)
+            self._ck(self.L.vhap_adam_multi(self.ctx, self.slab.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                            len(groups), hp(off), hp(ln), hp(lr), self.step_count, s), None)
 
     def step(self, batch: Batch) -> torch.Tensor:
         """One optimisation iteration (tracker.py:1418-1435): zero_grad, energy + backward, Adam."""
