@@ -140,6 +140,8 @@ extern "C" int vhap_ctx_create(vhap_ctx** out, const vhap_mesh_desc* m, int32_t 
   UP(ctx->overflow_flag, (const int*)nullptr, (size_t)1);
   UP(ctx->pool_base, (const int*)nullptr, (size_t)16);
   UP(ctx->pool_count, (const int*)nullptr, (size_t)16);
+  UP(ctx->scan_aux, (const int*)nullptr, (size_t)1024);
+  UP(ctx->scan_total, (const int*)nullptr, (size_t)1);
   return 0;
 }
 

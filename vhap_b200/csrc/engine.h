@@ -51,6 +51,7 @@ struct vhap_ctx {
   float* acc;                                     // [64] misc accumulators (loss sums, focal grad...)
   const uint8_t* inj_w; const float* inj_u;
   struct VhProf* prof;
+  int *scan_aux, *scan_total;                     // [1024], [1]
 };
 
 void vh_set_error(vhap_ctx* ctx, const char* what, const char* msg);
@@ -93,6 +94,7 @@ void launch_regs(vhap_ctx* c, const vhap_params* p, const vhap_frame_batch* fb, 
 // raster.cu
 void launch_raster(vhap_ctx* c, const f4* clip, i4* snap, int B, int H, int W, int* tri_id, int cull_backface, int need_snap, cudaStream_t s);
 void launch_rast_out(vhap_ctx* c, const f4* clip, int B, int H, int W, const int* tri_id, float* rast, float* rast_db, cudaStream_t s);
+void launch_scan(vhap_ctx* c, const int* in, int* out, int n, int* total, cudaStream_t s);
 // render.cu
 void fill_render_args(vhap_ctx* c, PassArgs& P, const vhap_frame_batch* fb, const vhap_stage_cfg* cfg, const float* lights);
 void launch_render_forward(vhap_ctx* c, PassArgs& P, cudaStream_t s);

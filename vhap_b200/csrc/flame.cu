@@ -338,6 +338,7 @@ __global__ void __launch_bounds__(128) k_skin_bwd(const float* __restrict__ v_po
                                                   float* __restrict__ gA, float* __restrict__ gpf, float* __restrict__ acc) {
   __shared__ float shA[NB][60];
   __shared__ float shr[33];
+  __shared__ float red[60][128];
   int b0 = blockIdx.y * NB, nb = min(NB, B - b0);
   for (int i = threadIdx.x; i < nb * 60; i += blockDim.x) shA[i / 60][i % 60] = ((const float*)posebuf[b0 + i / 60].A)[i % 60];
   int v = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
@@ -378,24 +379,33 @@ __global__ void __launch_bounds__(128) k_skin_bwd(const float* __restrict__ v_po
       float* o = g_vshaped + (size_t)b * M + 3 * v; o[0] = gvp[0]; o[1] = gvp[1]; o[2] = gvp[2];
       goff[0] += gvp[0]; goff[1] += gvp[1]; goff[2] += gvp[2];
     }
-    // warp-level reductions, one atomic per warp and value.  g_A[j][r][ci] (lbs.py:185: T = W A)
-    for (int j = 0; j < 5; ++j)
+    // block reductions through shared memory: every thread deposits its values column-wise (red[value][thread], conflict
+    // free), then each warp sums a quarter of the rows (4 strided reads + a warp reduction) and issues one atomic per row
+    int warp = threadIdx.x >> 5;
+    __syncthreads();
+    for (int j = 0; j < 5; ++j)                         // g_A[j][r][ci]  (lbs.py:185: T = W A)
       for (int r = 0; r < 3; ++r)
-        for (int ci = 0; ci < 4; ++ci) {
-          float val = warp_sum(w[j] * g[r] * (ci < 3 ? vp[ci] : 1.f));
-          if (lane == 0 && val != 0.f) atomicAdd(gA + (size_t)b * 60 + j * 12 + r * 4 + ci, val);
-        }
+        for (int ci = 0; ci < 4; ++ci) red[j * 12 + r * 4 + ci][threadIdx.x] = w[j] * g[r] * (ci < 3 ? vp[ci] : 1.f);
+    __syncthreads();
+    for (int row = warp; row < 60; row += 4) {
+      float val = warp_sum(red[row][lane] + red[row][lane + 32] + red[row][lane + 64] + red[row][lane + 96]);
+      if (lane == 0 && val != 0.f) atomicAdd(gA + (size_t)b * 60 + row, val);
+    }
+    __syncthreads();
     for (int p = 0; p < 36; ++p) {                      // g_pose_feature[p] (lbs.py:166); loads coalesced over vertices
       float val = 0.f;
       if (on) { const float* pd = posedirs + (size_t)p * M + 3 * v; val = pd[0] * gvp[0] + pd[1] * gvp[1] + pd[2] * gvp[2]; }
-      val = warp_sum(val);
-      if (lane == 0 && val != 0.f) atomicAdd(gpf + (size_t)b * 36 + p, val);
+      red[p][threadIdx.x] = val;
     }
-    if (g_transl)
-      for (int cc = 0; cc < 3; ++cc) {                  // translation (flame.py:624)
-        float val = warp_sum(g[cc]);
-        if (lane == 0 && val != 0.f) atomicAdd(g_transl + (size_t)ts[b] * 3 + cc, val);
+    for (int cc = 0; cc < 3; ++cc) red[36 + cc][threadIdx.x] = g[cc];     // translation (flame.py:624)
+    __syncthreads();
+    for (int row = warp; row < 39; row += 4) {
+      float val = warp_sum(red[row][lane] + red[row][lane + 32] + red[row][lane + 64] + red[row][lane + 96]);
+      if (lane == 0 && val != 0.f) {
+        if (row < 36) atomicAdd(gpf + (size_t)b * 36 + row, val);
+        else if (g_transl) atomicAdd(g_transl + (size_t)ts[b] * 3 + (row - 36), val);
       }
+    }
   }
   if (g_offset && on) { atomicAdd(g_offset + 3 * v, goff[0]); atomicAdd(g_offset + 3 * v + 1, goff[1]); atomicAdd(g_offset + 3 * v + 2, goff[2]); }
   if (opt_cam) {

@@ -69,14 +69,14 @@ __global__ void __launch_bounds__(256) k_bin(const i4* __restrict__ snap, const 
     }
 }
 
-// exclusive scan of n ints by one block: each thread sums a contiguous chunk, the 1024 chunk sums are scanned in shared
-// memory, then every thread rewrites its chunk
-__global__ void __launch_bounds__(1024) k_scan(const int* __restrict__ in, int* __restrict__ out, int n) {
+// exclusive scan of n ints in three small launches: 1024-thread blocks scan 4096 coalesced elements each and emit
+// their totals, one block scans the totals, the totals are added back (n up to 4 Mi elements)
+__global__ void __launch_bounds__(1024) k_scan_local(const int* __restrict__ in, int* __restrict__ out, int* __restrict__ aux, int n) {
   __shared__ int sh[1024];
-  int chunk = (n + 1023) / 1024;
-  int i0 = threadIdx.x * chunk, i1 = min(i0 + chunk, n);
-  int s = 0;
-  for (int i = i0; i < i1; ++i) s += in[i];
+  int i0 = (blockIdx.x * 1024 + threadIdx.x) * 4;
+  int v[4], s = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { v[k] = (i0 + k < n) ? in[i0 + k] : 0; s += v[k]; }
   sh[threadIdx.x] = s;
   __syncthreads();
   for (int o = 1; o < 1024; o <<= 1) {
@@ -85,8 +85,35 @@ __global__ void __launch_bounds__(1024) k_scan(const int* __restrict__ in, int* 
     sh[threadIdx.x] += t;
     __syncthreads();
   }
-  int run = sh[threadIdx.x] - s;
-  for (int i = i0; i < i1; ++i) { int v = in[i]; out[i] = run; run += v; }
+  int excl = sh[threadIdx.x] - s;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { if (i0 + k < n) out[i0 + k] = excl; excl += v[k]; }
+  if (threadIdx.x == 1023) aux[blockIdx.x] = sh[1023];
+}
+__global__ void __launch_bounds__(1024) k_scan_aux(int* __restrict__ aux, int naux, int* __restrict__ total) {
+  __shared__ int sh[1024];
+  int s = threadIdx.x < naux ? aux[threadIdx.x] : 0;
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    int t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+    __syncthreads();
+    sh[threadIdx.x] += t;
+    __syncthreads();
+  }
+  if (threadIdx.x < naux) aux[threadIdx.x] = sh[threadIdx.x] - s;
+  if (threadIdx.x == 1023 && total) *total = sh[1023];
+}
+__global__ void __launch_bounds__(1024) k_scan_add(int* __restrict__ out, const int* __restrict__ aux, int n) {
+  int i0 = (blockIdx.x * 1024 + threadIdx.x) * 4, a = aux[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) if (i0 + k < n) out[i0 + k] += a;
+}
+void launch_scan(vhap_ctx* c, const int* in, int* out, int n, int* total, cudaStream_t s) {
+  int nb = (n + 4095) / 4096;
+  LAUNCH(c, KID_SCAN, s, k_scan_local<<<nb, 1024, 0, s>>>(in, out, c->scan_aux, n));
+  LAUNCH(c, KID_SCAN, s, k_scan_aux<<<1, 1024, 0, s>>>(c->scan_aux, nb, total));
+  LAUNCH(c, KID_SCAN, s, k_scan_add<<<nb, 1024, 0, s>>>(out, c->scan_aux, n));
 }
 
 struct FineTri {        // shared-memory record, struct of arrays
@@ -201,7 +228,7 @@ void launch_raster(vhap_ctx* c, const f4* clip, i4* snap, int B, int H, int W, i
   cudaMemsetAsync(c->tile_cursor, 0, sizeof(int) * ntiles, s);
   dim3 g((F + 255) / 256, B);
   LAUNCH(c, KID_BIN, s, k_bin<false><<<g, 256, 0, s>>>(snap, c->faces, V, F, B, H, W, tiles_x, tiles_y, cull_backface, c->tile_count, nullptr, nullptr, nullptr, 0, c->overflow_flag));
-  LAUNCH(c, KID_SCAN, s, k_scan<<<1, 1024, 0, s>>>(c->tile_count, c->tile_off, ntiles));
+  launch_scan(c, c->tile_count, c->tile_off, ntiles, nullptr, s);
   LAUNCH(c, KID_BIN, s, k_bin<true><<<g, 256, 0, s>>>(snap, c->faces, V, F, B, H, W, tiles_x, tiles_y, cull_backface, c->tile_count, c->tile_off, c->tile_cursor, c->tile_list,
                                 c->tile_cap, c->overflow_flag));
   LAUNCH(c, KID_FINE, s, k_fine<<<ntiles, 128, 0, s>>>(snap, c->faces, c->tile_count, c->tile_off, c->tile_list, c->tile_cap, V, H, W, tiles_x, tiles_y, cull_backface, tri_id));

@@ -63,31 +63,13 @@ __global__ void __launch_bounds__(PB) k_pool_count(const int* __restrict__ tri_i
   if (threadIdx.x < 16) blk_count[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = cnt[threadIdx.x];    // [16][nblk]
 }
 
-// exclusive scan of the [16][nblk] counts as ONE sequence (pixel lists are laid out cluster after cluster) by a single
-// block: every thread sums a contiguous chunk, the 1024 chunk sums are scanned in shared memory, chunks are rewritten.
-__global__ void __launch_bounds__(1024) k_pool_scan(const int* __restrict__ in, int* __restrict__ out, int nblk, int* __restrict__ base, int* __restrict__ count) {
-  __shared__ int sh[1024];
-  int n = 16 * nblk, chunk = (n + 1023) / 1024;
-  int i0 = threadIdx.x * chunk, i1 = min(i0 + chunk, n);
-  int s = 0;
-  for (int i = i0; i < i1; ++i) s += in[i];
-  sh[threadIdx.x] = s;
-  __syncthreads();
-  for (int o = 1; o < 1024; o <<= 1) {
-    int t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
-    __syncthreads();
-    sh[threadIdx.x] += t;
-    __syncthreads();
-  }
-  int run = sh[threadIdx.x] - s;
-  for (int i = i0; i < i1; ++i) { int v = in[i]; out[i] = run; run += v; }
-  __syncthreads();
-  if (threadIdx.x < 16) {
-    int c = threadIdx.x;
-    int b = out[(size_t)c * nblk];
-    int e = c < 15 ? out[(size_t)(c + 1) * nblk] : sh[1023];
-    base[c] = b; count[c] = e - b;
-  }
+// base / count of every cluster from the scanned [16][nblk] offsets (scanned as ONE sequence: lists laid out cluster after cluster)
+__global__ void k_pool_bases(const int* __restrict__ off, int nblk, const int* __restrict__ total, int* __restrict__ base, int* __restrict__ count) {
+  int c = threadIdx.x;
+  if (c >= 16) return;
+  int b = off[(size_t)c * nblk];
+  int e = c < 15 ? off[(size_t)(c + 1) * nblk] : *total;
+  base[c] = b; count[c] = e - b;
 }
 
 __global__ void __launch_bounds__(PB) k_pool_scatter(const int* __restrict__ tri_id, const uint8_t* __restrict__ fid2cid, size_t n,
@@ -293,7 +275,8 @@ void launch_render_forward(vhap_ctx* c, PassArgs& P, cudaStream_t s) {
     cudaMemsetAsync(c->plane_albedo, 0, n * 16, s); cudaMemsetAsync(c->plane_normal, 0, n * 16, s); cudaMemsetAsync(c->plane_diffuse, 0, n * 16, s);
   }
   LAUNCH(c, KID_POOL_COUNT, s, k_pool_count<<<nblk, PB, 0, s>>>(A.tri_id, A.fid2cid, n, c->pool_blk_count));
-  LAUNCH(c, KID_POOL_SCAN, s, k_pool_scan<<<1, 1024, 0, s>>>(c->pool_blk_count, c->pool_blk_off, nblk, c->pool_base, c->pool_count));
+  launch_scan(c, c->pool_blk_count, c->pool_blk_off, 16 * nblk, c->scan_total, s);
+  LAUNCH(c, KID_POOL_SCAN, s, k_pool_bases<<<1, 32, 0, s>>>(c->pool_blk_off, nblk, c->scan_total, c->pool_base, c->pool_count));
   LAUNCH(c, KID_POOL_SCATTER, s, k_pool_scatter<<<nblk, PB, 0, s>>>(A.tri_id, A.fid2cid, n, c->pool_blk_off, c->pool_list));
   int grid = nblk < NPERSIST ? nblk : NPERSIST;
   LAUNCH(c, KID_PASSA, s, k_passA<<<grid, PB, 0, s>>>(P, c->partials, c->maxslot));
