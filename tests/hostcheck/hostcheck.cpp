@@ -41,6 +41,7 @@ int hc_render(int B, int H, int W, int V, int F, int T, int max_level,
   for (int i = 0; i <= max_level; ++i) A.mip_off[i] = mip_off[i];
   A.tri_id = tri_id; A.face_flags = face_flags; A.vert_flags = vert_flags; A.fid2cid = fid2cid; A.adj_opp = adj_opp4;
   P.target = target; P.pre = (f4*)pre; P.final_rgba = final_rgba;
+  A.zwbuf = pre;
   std::vector<uint8_t> signs((size_t)B * H * W);
   P.signs = signs.data();
   P.disturb = disturb; P.rate_fg = 0.5f; P.rate_bg = 0.5f; P.inj_w = inj_w; P.inj_u = inj_u;

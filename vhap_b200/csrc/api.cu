@@ -148,7 +148,7 @@ extern "C" int vhap_ctx_create(vhap_ctx** out, const vhap_mesh_desc* m, int32_t 
 #define FREE(p) do { if (p) { cudaFree(p); p = nullptr; } } while (0)
 
 static void free_batch(vhap_ctx* c) {
-  FREE(c->v_shaped); FREE(c->v_posed); FREE(c->g_vshaped); FREE(c->verts); FREE(c->clip); FREE(c->vnorm); FREE(c->vnraw); FREE(c->snap);
+  FREE(c->v_shaped); FREE(c->v_posed); FREE(c->g_vshaped); FREE(c->verts); FREE(c->clip); FREE(c->vnorm); FREE(c->vnraw); FREE(c->snap); FREE(c->ndc);
   FREE(c->g_clip); FREE(c->g_vnorm); FREE(c->g_verts); FREE(c->posebuf); FREE(c->poses); FREE(c->gA); FREE(c->gpf); FREE(c->gJ); FREE(c->gbetas);
   FREE(c->betas); FREE(c->cam); FREE(c->tri_id); FREE(c->pre); FREE(c->signs); FREE(c->pool_list); FREE(c->final_rgba); FREE(c->plane_albedo);
   FREE(c->plane_normal); FREE(c->plane_diffuse); FREE(c->tile_count); FREE(c->tile_off); FREE(c->tile_cursor); FREE(c->tile_list);
@@ -162,7 +162,7 @@ extern "C" int vhap_ctx_reserve(vhap_ctx* ctx, int32_t B, int32_t H, int32_t W) 
   size_t V = ctx->V, M = 3 * V, n = (size_t)B * H * W;
   UP(ctx->v_shaped, (const float*)nullptr, B * M); UP(ctx->v_posed, (const float*)nullptr, B * M); UP(ctx->g_vshaped, (const float*)nullptr, B * M);
   UP(ctx->verts, (const f4*)nullptr, B * V); UP(ctx->clip, (const f4*)nullptr, B * V); UP(ctx->vnorm, (const f4*)nullptr, B * V);
-  UP(ctx->vnraw, (const f4*)nullptr, B * V); UP(ctx->snap, (const i4*)nullptr, B * V);
+  UP(ctx->vnraw, (const f4*)nullptr, B * V); UP(ctx->snap, (const i4*)nullptr, B * V); UP(ctx->ndc, (const float*)nullptr, B * V * 2);
   UP(ctx->g_clip, (const float*)nullptr, B * V * 4); UP(ctx->g_vnorm, (const float*)nullptr, B * V * 4); UP(ctx->g_verts, (const float*)nullptr, B * V * 4);
   UP(ctx->posebuf, (const PoseFwd*)nullptr, (size_t)B); UP(ctx->poses, (const float*)nullptr, (size_t)B * 15);
   UP(ctx->gA, (const float*)nullptr, (size_t)B * 60); UP(ctx->gpf, (const float*)nullptr, (size_t)B * 36); UP(ctx->gJ, (const float*)nullptr, (size_t)B * 15);

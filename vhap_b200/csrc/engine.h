@@ -32,6 +32,7 @@ struct vhap_ctx {
   int maxB, maxH, maxW, curB, curH, curW;
   float *v_shaped, *v_posed, *g_vshaped;          // [B][3V]
   f4 *verts, *clip, *vnorm, *vnraw; i4* snap;     // [B][V]
+  float* ndc;                                     // [B][V][2] clip.xy / clip.w
   float *g_clip, *g_vnorm, *g_verts;              // [B][V][4]
   PoseFwd* posebuf; float* poses;                 // [B], [B][15]
   float *gA, *gpf, *gJ, *gbetas, *betas;          // [B][60], [B][36], [B][15], [B][K], [B][K]

@@ -133,7 +133,7 @@ template <int NB>
 __global__ void __launch_bounds__(128) k_skin_fwd(const float* __restrict__ v_shaped, const float* __restrict__ posedirs, const float* __restrict__ lbs_w,
                                                   const PoseFwd* __restrict__ posebuf, const float* __restrict__ transl, const int* __restrict__ ts,
                                                   const CamParams* __restrict__ cam, int V, int B, int H, int W,
-                                                  float* __restrict__ v_posed, f4* __restrict__ verts, f4* __restrict__ clip, i4* __restrict__ snap) {
+                                                  float* __restrict__ v_posed, f4* __restrict__ verts, f4* __restrict__ clip, i4* __restrict__ snap, float* __restrict__ ndc) {
   __shared__ float shpf[NB][36];
   __shared__ float shA[NB][60];
   int b0 = blockIdx.y * NB, nb = min(NB, B - b0);
@@ -187,6 +187,7 @@ __global__ void __launch_bounds__(128) k_skin_fwd(const float* __restrict__ v_sh
       sn.z = __float_as_int(__fdiv_rn(cl.z, cl.w)); sn.w = 1;
     }
     snap[(size_t)b * V + v] = sn;
+    ndc[((size_t)b * V + v) * 2] = cl.x / cl.w; ndc[((size_t)b * V + v) * 2 + 1] = cl.y / cl.w;
   }
 }
 
@@ -200,7 +201,7 @@ void launch_flame_forward(vhap_ctx* c, const vhap_params* p, const vhap_frame_ba
                                                                                   c->n_shape, B, c->v_shaped));
   dim3 g2((V + 127) / 128, (B + 7) / 8);
   LAUNCH(c, KID_SKIN_FWD, s, k_skin_fwd<8><<<g2, 128, 0, s>>>(c->v_shaped, c->posedirs, c->lbs_w, c->posebuf, p->translation, fb->timesteps, c->cam, V, B, fb->H, fb->W,
-                                   c->v_posed, c->verts, c->clip, c->snap));
+                                   c->v_posed, c->verts, c->clip, c->snap, c->ndc));
 }
 
 // ------------------------------------------------------------------------------------------------ landmarks

@@ -22,6 +22,8 @@ struct RenderArgs {
   const uint8_t* vert_flags;  // [V] bit0: clip position detached inside antialias (align_boundary_except_vid)
   const uint8_t* fid2cid;     // [F+1]
   const int* adj_opp;         // [F*4] opposite vertex per edge (x,y,z), -1 boundary, -2 non-manifold
+  const float* ndc;           // optional [B,V,2] = clip.xy / clip.w (saves the divisions in the antialias analysis)
+  const float* zwbuf;         // optional [B,H,W,4]: .w of foreground pixels holds their z/w (written by pass A)
 };
 
 struct TriSetup {

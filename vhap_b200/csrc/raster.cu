@@ -11,7 +11,7 @@
 #define SNAP_GUARD 131072.f
 #define FINE_CHUNK 128
 
-__global__ void k_snap(const f4* __restrict__ clip, i4* __restrict__ snap, int n, int H, int W) {
+__global__ void k_snap(const f4* __restrict__ clip, i4* __restrict__ snap, float* __restrict__ ndc, int n, int H, int W) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   f4 cl = clip[i];
@@ -25,6 +25,7 @@ __global__ void k_snap(const f4* __restrict__ clip, i4* __restrict__ snap, int n
     sn.z = __float_as_int(__fdiv_rn(cl.z, cl.w)); sn.w = 1;
   }
   snap[i] = sn;
+  if (ndc) { ndc[2 * i] = cl.x / cl.w; ndc[2 * i + 1] = cl.y / cl.w; }
 }
 
 __device__ __forceinline__ int floordiv16(int a) { return a >> 4; }       // arithmetic shift = floor for negatives
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(128) k_fine(const i4* __restrict__ snap, const
 
 void launch_raster(vhap_ctx* c, const f4* clip, i4* snap, int B, int H, int W, int* tri_id, int cull_backface, int need_snap, cudaStream_t s) {
   int V = c->V, F = c->F;
-  if (need_snap) LAUNCH(c, KID_SNAP, s, k_snap<<<(B * V + 255) / 256, 256, 0, s>>>(clip, snap, B * V, H, W));
+  if (need_snap) LAUNCH(c, KID_SNAP, s, k_snap<<<(B * V + 255) / 256, 256, 0, s>>>(clip, snap, c->ndc, B * V, H, W));
   int tiles_x = (W + VH_TILE - 1) / VH_TILE, tiles_y = (H + VH_TILE - 1) / VH_TILE, ntiles = B * tiles_x * tiles_y;
   cudaMemsetAsync(c->tile_count, 0, sizeof(int) * ntiles, s);
   cudaMemsetAsync(c->tile_cursor, 0, sizeof(int) * ntiles, s);

@@ -67,7 +67,7 @@ VH_HD void philox4x32(uint64_t key, uint64_t ctr_lo, uint64_t ctr_hi, uint32_t o
 VH_HD f4 pre_color(const PassArgs& P, int b, int y, int x, int id) {
   const RenderArgs& A = P.R;
   size_t pix = ((size_t)b * A.H + y) * A.W + x;
-  if (id > 0) return P.pre[pix];
+  if (id > 0) { f4 c = P.pre[pix]; c.w = 1.f; return c; }      // .w of the buffer holds z/w, the colour's alpha is 1
   f4 c; c.w = 0.f;
   if (P.bg_mode == 0) {
     const uint16_t* t = P.target + (((size_t)b * A.H + (A.H - 1 - y)) * A.W + x) * 4;
@@ -91,11 +91,13 @@ VH_HD f4 disturbed_color(const PassArgs& P, int b, int y, int x, int id, float* 
     w = cid == 0 ? ((P.inj_w[pix] >> 1) & 1) : (P.inj_w[pix] & 1);
     u = P.inj_u[pix];
   } else {
-    uint32_t r[4];
-    philox4x32(P.seed, (uint64_t)pix, P.step, r);
-    float ub = (cid == 0 ? r[1] : r[0]) * 2.3283064365386963e-10f;      // [0,1)
+    // counter-based generator (splitmix64 of (pixel, step, seed)); the reference's torch Philox stream cannot be reproduced
+    // anyway (different consumption order), see DESIGN.md "Disturbance randomness"
+    uint64_t z = (uint64_t)pix * 0x9E3779B97F4A7C15ull + P.step * 0xD1B54A32D192ED03ull + P.seed;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+    float ub = (float)((uint32_t)z >> 8) * 5.9604644775390625e-08f;      // 24-bit uniform in [0,1)
     w = rate >= 0.f && ub < rate;
-    u = (r[2] >> 8) * 5.9604644775390625e-08f;                           // 24-bit uniform in [0,1)
+    u = (float)((uint32_t)(z >> 40)) * 5.9604644775390625e-08f;          // independent 24 bits
   }
   if (rate < 0.f) w = false;
   int n = P.pool_count[cid];
@@ -126,7 +128,10 @@ VH_HD void aa_analyze(const RenderArgs& A, int b, int x0, int y0, int d, int id0
   int t0 = id0 - 1, t1 = id1 - 1;
   int x1 = x0 + (d == 0), y1 = y0 + (d == 1);
   bool use0;
-  if (t0 >= 0 && t1 >= 0) use0 = tri_zw(A, b, x0, y0, t0) < tri_zw(A, b, x1, y1, t1);
+  if (t0 >= 0 && t1 >= 0) {
+    if (A.zwbuf) use0 = A.zwbuf[(((size_t)b * A.H + y0) * A.W + x0) * 4 + 3] < A.zwbuf[(((size_t)b * A.H + y1) * A.W + x1) * 4 + 3];
+    else use0 = tri_zw(A, b, x0, y0, t0) < tri_zw(A, b, x1, y1, t1);
+  }
   else use0 = t0 >= 0;
   r.near0 = use0;
   int tri = use0 ? t0 : t1;
@@ -137,10 +142,12 @@ VH_HD void aa_analyze(const RenderArgs& A, int b, int x0, int y0, int d, int id0
   i4 f = A.faces[tri];
   int vi[3] = {f.x, f.y, f.z};
   const f4* cl = A.clip + (size_t)b * A.V;
-  f4 p[3] = {cl[vi[0]], cl[vi[1]], cl[vi[2]]};
+  const float* nd = A.ndc ? A.ndc + (size_t)b * A.V * 2 : nullptr;
   float sx[3], sy[3];
   for (int k = 0; k < 3; ++k) {
-    float qx = p[k].x / p[k].w - fx, qy = p[k].y / p[k].w - fy;
+    float qx, qy;
+    if (nd) { qx = nd[vi[k] * 2] - fx; qy = nd[vi[k] * 2 + 1] - fy; }
+    else { f4 pk = cl[vi[k]]; qx = pk.x / pk.w - fx; qy = pk.y / pk.w - fy; }
     sx[k] = d == 0 ? qx : qy; sy[k] = d == 0 ? qy : qx;
   }
   float pitch = (d == 0 ? 2.f / A.W : 2.f / A.H) * sgn;
@@ -156,8 +163,9 @@ VH_HD void aa_analyze(const RenderArgs& A, int b, int x0, int y0, int d, int id0
     int op = adj[k];
     bool sil = op == -1;
     if (op >= 0) {
-      f4 po = cl[op];
-      float qx = po.x / po.w - fx, qy = po.y / po.w - fy;
+      float qx, qy;
+      if (nd) { qx = nd[op * 2] - fx; qy = nd[op * 2 + 1] - fy; }
+      else { f4 po = cl[op]; qx = po.x / po.w - fx; qy = po.y / po.w - fy; }
       float ox = d == 0 ? qx : qy, oy = d == 0 ? qy : qx;
       float ex = bx - ax, ey = by - ay;
       float side_c = ex * (sy[ic] - ay) - ey * (sx[ic] - ax);
@@ -166,7 +174,7 @@ VH_HD void aa_analyze(const RenderArgs& A, int b, int x0, int y0, int d, int id0
     }
     if (!sil) continue;
     r.found = true; r.alpha = t - 0.5f; r.va = vi[ia]; r.vb = vi[ib];
-    r.ax = ax; r.ay = ay; r.bx = bx; r.by = by; r.pitch = pitch; r.pa = p[ia]; r.pb = p[ib];
+    r.ax = ax; r.ay = ay; r.bx = bx; r.by = by; r.pitch = pitch; r.pa = cl[vi[ia]]; r.pb = cl[vi[ib]];
     return;
   }
 }
@@ -204,7 +212,7 @@ VH_HD void passA_body(const PassArgs& P, int b, int y, int x, float* acc, float&
   }
   PixShade s;
   shade_pixel(A, b, x, y, id - 1, s);
-  f4 c; c.x = s.rgb.x; c.y = s.rgb.y; c.z = s.rgb.z; c.w = 1.f;
+  f4 c; c.x = s.rgb.x; c.y = s.rgb.y; c.z = s.rgb.z; c.w = s.ts.zw;      // .w: z/w for the antialias depth comparison
   P.pre[pix] = c;
   float m = (s.diffuse.x + s.diffuse.y + s.diffuse.z) * (1.f / 3.f);
   float dx = s.diffuse.x - m, dy = s.diffuse.y - m, dz = s.diffuse.z - m;
