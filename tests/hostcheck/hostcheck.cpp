@@ -56,6 +56,14 @@ int hc_render(int B, int H, int W, int V, int F, int T, int max_level,
   for (int c = 1; c < 16; ++c) base[c] = base[c - 1] + count[c - 1];
   { std::vector<int> cur(base); for (int i = 0; i < N; ++i) list[cur[fid2cid[tri_id[i]]]++] = i; }
   P.pool_list = list.data(); P.pool_base = base.data(); P.pool_count = count.data();
+  // pair analysis
+  std::vector<float> aa_code((size_t)N * 2, 0.f);
+  P.aa_code = aa_code.data();
+  for (int b = 0; b < B; ++b) for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) {
+    int i = (b * H + y) * W + x;
+    if (x + 1 < W && tri_id[i] != tri_id[i + 1]) aa_pair_body(P, b, y, x, 0);
+    if (y + 1 < H && tri_id[i] != tri_id[i + W]) aa_pair_body(P, b, y, x, 1);
+  }
   // pass B
   float accB[2] = {0, 0};
   for (int b = 0; b < B; ++b) for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) passB_body(P, b, y, x, accB);

@@ -72,11 +72,27 @@ __global__ void k_pool_bases(const int* __restrict__ off, int nblk, const int* _
   base[c] = b; count[c] = e - b;
 }
 
-__global__ void __launch_bounds__(PB) k_pool_scatter(const int* __restrict__ tri_id, const uint8_t* __restrict__ fid2cid, size_t n,
-                                                     const int* __restrict__ blk_off, int* __restrict__ pool_list) {
+// also emits the list of adjacent pixel pairs with different ids (pair = pixel0 * 2 + direction) for the antialias analysis
+__global__ void __launch_bounds__(PB) k_pool_scatter(const int* __restrict__ tri_id, const uint8_t* __restrict__ fid2cid, size_t n, int H, int W,
+                                                     const int* __restrict__ blk_off, int* __restrict__ pool_list,
+                                                     int* __restrict__ pair_list, int* __restrict__ pair_count) {
   __shared__ int wcnt[16][PB / 32];
   size_t pix = (size_t)blockIdx.x * PB + threadIdx.x;
-  int cid = pix < n ? fid2cid[tri_id[pix]] : -1;
+  int id = pix < n ? tri_id[pix] : -1;
+  int cid = pix < n ? fid2cid[id] : -1;
+  {
+    int x = pix % W, y = (pix / W) % H;
+    bool h0 = pix < n && x + 1 < W && tri_id[pix + 1] != id;
+    bool h1 = pix < n && y + 1 < H && tri_id[pix + W] != id;
+    unsigned m0 = __ballot_sync(0xffffffffu, h0), m1 = __ballot_sync(0xffffffffu, h1);
+    int lane_ = threadIdx.x & 31, tot = __popc(m0) + __popc(m1), base = 0;
+    if (tot) {
+      if (lane_ == 0) base = atomicAdd(pair_count, tot);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (h0) pair_list[base + __popc(m0 & ((1u << lane_) - 1))] = (int)pix * 2;
+      if (h1) pair_list[base + __popc(m0) + __popc(m1 & ((1u << lane_) - 1))] = (int)pix * 2 + 1;
+    }
+  }
   int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   int rank = 0;
   unsigned any = __ballot_sync(0xffffffffu, cid > 0);
@@ -94,6 +110,16 @@ __global__ void __launch_bounds__(PB) k_pool_scatter(const int* __restrict__ tri
 }
 
 // ---------------------------------------------------------------------------------------------- passes
+__global__ void __launch_bounds__(PB) k_aa_pairs(PassArgs P, const int* __restrict__ pair_list, const int* __restrict__ pair_count) {
+  const RenderArgs& A = P.R;
+  int n = *pair_count;
+  for (int i = blockIdx.x * PB + threadIdx.x; i < n; i += gridDim.x * PB) {
+    int pr = pair_list[i], pix = pr >> 1, d = pr & 1;
+    int x = pix % A.W, y = (pix / A.W) % A.H, b = pix / (A.W * A.H);
+    aa_pair_body(P, b, y, x, d);
+  }
+}
+
 __global__ void __launch_bounds__(PB) k_passA(PassArgs P, float* __restrict__ partials, unsigned long long* __restrict__ maxslot) {
   __shared__ float sh[8 * 2];
   __shared__ unsigned long long shm[8];
@@ -251,7 +277,7 @@ void fill_render_args(vhap_ctx* c, PassArgs& P, const vhap_frame_batch* fb, cons
   P.rate_fg = cfg->disturb_rate_fg; P.rate_bg = cfg->disturb_rate_bg;
   P.inj_w = c->inj_w; P.inj_u = c->inj_u; P.seed = cfg->rng_seed; P.step = cfg->rng_step;
   P.bg_mode = cfg->bg_mode; P.bg_color[0] = cfg->bg_color[0]; P.bg_color[1] = cfg->bg_color[1]; P.bg_color[2] = cfg->bg_color[2];
-  P.scal = c->scal; P.g_clip = c->g_clip; P.g_vnorm = c->g_vnorm; P.g_tex = nullptr;
+  P.scal = c->scal; P.g_clip = c->g_clip; P.g_vnorm = c->g_vnorm; P.g_tex = nullptr; P.aa_code = c->aa_code;
 }
 
 static int* slot_table(vhap_ctx* c) {      // device copy of the acc[] slots of partial columns 0..3
@@ -277,9 +303,11 @@ void launch_render_forward(vhap_ctx* c, PassArgs& P, cudaStream_t s) {
   LAUNCH(c, KID_POOL_COUNT, s, k_pool_count<<<nblk, PB, 0, s>>>(A.tri_id, A.fid2cid, n, c->pool_blk_count));
   launch_scan(c, c->pool_blk_count, c->pool_blk_off, 16 * nblk, c->scan_total, s);
   LAUNCH(c, KID_POOL_SCAN, s, k_pool_bases<<<1, 32, 0, s>>>(c->pool_blk_off, nblk, c->scan_total, c->pool_base, c->pool_count));
-  LAUNCH(c, KID_POOL_SCATTER, s, k_pool_scatter<<<nblk, PB, 0, s>>>(A.tri_id, A.fid2cid, n, c->pool_blk_off, c->pool_list));
+  cudaMemsetAsync(c->pair_count, 0, sizeof(int), s);
+  LAUNCH(c, KID_POOL_SCATTER, s, k_pool_scatter<<<nblk, PB, 0, s>>>(A.tri_id, A.fid2cid, n, A.H, A.W, c->pool_blk_off, c->pool_list, c->pair_list, c->pair_count));
   int grid = nblk < NPERSIST ? nblk : NPERSIST;
   LAUNCH(c, KID_PASSA, s, k_passA<<<grid, PB, 0, s>>>(P, c->partials, c->maxslot));
+  LAUNCH(c, KID_AA_PAIRS, s, k_aa_pairs<<<grid, PB, 0, s>>>(P, c->pair_list, c->pair_count));
   LAUNCH(c, KID_PASSB, s, k_passB<<<grid, PB, 0, s>>>(P, c->partials));
   LAUNCH(c, KID_REDUCE, s, k_reduce_cols<<<16, 256, 0, s>>>(c->partials, grid, 0, 4, c->acc, slots));
 }

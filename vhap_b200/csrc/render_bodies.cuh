@@ -35,6 +35,9 @@ struct PassArgs {
   float* g_tex;               // gradient pyramid (float4 layout) or NULL
   // optional debug planes (raster orientation), NULL to skip
   f4* plane_albedo; f4* plane_normal; f4* plane_diffuse;
+  // antialias pair cache, one float per (pixel 0 of the pair, direction d): 0 = no blend, else sign = near surface is pixel 0's,
+  // |code| - 1 = alpha (written by the pair-analysis pass for EVERY pair of adjacent pixels with different ids)
+  float* aa_code;             // [B,H,W,2]
 };
 
 // ------------------------------------------------------------------------------------------ small utilities
@@ -229,6 +232,27 @@ VH_HD void passA_body(const PassArgs& P, int b, int y, int x, float* acc, float&
   }
 }
 
+// ------------------------------------------------------------------------------------------ pair analysis (pass B1)
+// one call per pair of adjacent pixels with different ids; pix0 = (b,y0,x0), d = 0 horizontal / 1 vertical
+VH_HD void aa_pair_body(const PassArgs& P, int b, int y0, int x0, int d) {
+  const RenderArgs& A = P.R;
+  size_t p0 = ((size_t)b * A.H + y0) * A.W + x0, p1 = p0 + (d == 0 ? 1 : A.W);
+  AAPair r;
+  aa_analyze(A, b, x0, y0, d, A.tri_id[p0], A.tri_id[p1], r);
+  P.aa_code[p0 * 2 + d] = r.found ? (r.alpha + 1.f) * (r.near0 ? 1.f : -1.f) : 0.f;
+}
+// cached result of the pair (p, q) seen from pixel p; returns false if the pair produces no blend
+VH_HD bool aa_lookup(const PassArgs& P, size_t pix, size_t qpix, int d, bool p_is0, bool& modifies_p, float& a, float& alpha) {
+  float code = P.aa_code[(p_is0 ? pix : qpix) * 2 + d];
+  if (code == 0.f) return false;
+  bool near0 = code > 0.f;
+  alpha = fabsf(code) - 1.f;
+  bool p_near = (near0 == p_is0);
+  modifies_p = (alpha > 0.f) ? !p_near : p_near;      // alpha > 0 modifies the FAR pixel, otherwise the NEAR pixel
+  a = fabsf(alpha);
+  return true;
+}
+
 // ------------------------------------------------------------------------------------------ pass B
 // Gather-form antialias: the final colour of p is D(p) plus the blends of the (up to 4) pixel pairs p belongs to for
 // which p is the pixel being modified.  acc[0] += sum_c |gt - pred|, acc[1] += (alpha_aa > 0).
@@ -246,15 +270,9 @@ VH_HD void passB_body(const PassArgs& P, int b, int y, int x, float* acc) {
     if (idq == id) continue;
     int d = k >> 1;
     bool p_is0 = (k & 1);                       // k=1: p left of q; k=3: p below q
-    AAPair r;
-    if (p_is0) aa_analyze(A, b, x, y, d, id, idq, r);
-    else aa_analyze(A, b, qx, qy, d, idq, id, r);
-    if (!r.found) continue;
-    bool p_near = (r.near0 == p_is0);
-    // alpha > 0 modifies the FAR pixel, otherwise the NEAR pixel
-    bool modifies_p = (r.alpha > 0.f) ? !p_near : p_near;
+    bool modifies_p; float a, alpha;
+    if (!aa_lookup(P, pix, ((size_t)b * A.H + qy) * A.W + qx, d, p_is0, modifies_p, a, alpha)) continue;
     if (!modifies_p) continue;
-    float a = fabsf(r.alpha);
     f4 Dq = disturbed_color(P, b, qy, qx, idq, nullptr);
     out.x += a * (Dq.x - Dp.x); out.y += a * (Dq.y - Dp.y); out.z += a * (Dq.z - Dp.z); out.w += a * (Dq.w - Dp.w);
   }
@@ -303,13 +321,8 @@ VH_HD void passC_body(const PassArgs& P, int b, int y, int x, const float* ext_g
     if (idq == id) continue;
     int d = k >> 1;
     bool p_is0 = (k & 1);
-    AAPair r;
-    if (p_is0) aa_analyze(A, b, x, y, d, id, idq, r);
-    else aa_analyze(A, b, qx, qy, d, idq, id, r);
-    if (!r.found) continue;
-    bool p_near = (r.near0 == p_is0);
-    bool modifies_p = (r.alpha > 0.f) ? !p_near : p_near;
-    float a = fabsf(r.alpha);
+    bool modifies_p; float a, alpha;
+    if (!aa_lookup(P, pix, qpix, d, p_is0, modifies_p, a, alpha)) continue;
     f3 gq = ext_grad ? mk3(ext_grad[qpix * 4], ext_grad[qpix * 4 + 1], ext_grad[qpix * 4 + 2]) : sign_grad(P.signs[qpix], scale);
     if (modifies_p) self_w -= a;                  // final(p) = D(p) + a (D(q) - D(p))
     else { gD.x += a * gq.x; gD.y += a * gq.y; gD.z += a * gq.z; }   // final(q) = D(q) + a (D(p) - D(q))
@@ -324,8 +337,11 @@ VH_HD void passC_body(const PassArgs& P, int b, int y, int x, const float* ext_g
         float ga_t = modifies_p ? ext_grad[pix * 4 + 3] : ext_grad[qpix * 4 + 3];
         g_abs += ga_t * (modifies_p ? (Dq.w - Dp.w) : (Dp.w - Dq.w));
       }
-      float g_alpha = r.alpha > 0.f ? g_abs : -g_abs;
-      aa_bwd(P, b, r, g_alpha);
+      float g_alpha = alpha > 0.f ? g_abs : -g_abs;
+      AAPair r;                                   // geometry of the (rare) blending pair, recomputed for the adjoint
+      if (p_is0) aa_analyze(A, b, x, y, d, id, idq, r);
+      else aa_analyze(A, b, qx, qy, d, idq, id, r);
+      if (r.found) aa_bwd(P, b, r, g_alpha);
     }
   }
   gD.x += self_w * gp.x; gD.y += self_w * gp.y; gD.z += self_w * gp.z;
