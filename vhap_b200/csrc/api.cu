@@ -32,7 +32,7 @@ extern "C" int vhap_abi_version(void) { return 1; }
 
 static const char* const KID_NAMES[KID_COUNT] = {
     "cam_setup", "pose_fwd", "blend_fwd", "skin_fwd", "landmarks", "vnormals", "vnormals_bwd", "skin_bwd", "pose_bwd", "joff_bwd", "blend_bwd",
-    "betas_scatter", "regs", "snap", "bin", "scan", "fine_raster", "rast_out", "passA_shade", "pool_count", "pool_scan", "pool_scatter", "aa_pairs",
+    "betas_scatter", "regs", "snap", "bin", "scan", "fine_raster", "rast_out", "passA_shade", "pool_count", "pool_scan", "pool_scatter",
     "aa_pairs", "passB_disturb_aa_loss", "reduce_partials", "forward_slab", "finalize", "passC_backward", "lights_reduce", "tex_level0", "mip_down",
     "tex_fold_reg_adam", "tex_loss_reduce", "adam", "assemble_losses", "misc"};
 
