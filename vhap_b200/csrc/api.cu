@@ -143,13 +143,15 @@ extern "C" int vhap_ctx_create(vhap_ctx** out, const vhap_mesh_desc* m, int32_t 
   UP(ctx->scan_aux, (const int*)nullptr, (size_t)1024);
   UP(ctx->scan_total, (const int*)nullptr, (size_t)1);
   UP(ctx->pair_count, (const int*)nullptr, (size_t)1);
+  UP(ctx->tex_l0_flag, (const int*)nullptr, (size_t)1);
+  { int one = 1; cudaMemcpy(ctx->tex_l0_flag, &one, sizeof(int), cudaMemcpyHostToDevice); }
   return 0;
 }
 
 #define FREE(p) do { if (p) { cudaFree(p); p = nullptr; } } while (0)
 
 static void free_batch(vhap_ctx* c) {
-  FREE(c->v_shaped); FREE(c->v_posed); FREE(c->g_vshaped); FREE(c->verts); FREE(c->clip); FREE(c->vnorm); FREE(c->vnraw); FREE(c->snap); FREE(c->ndc);
+  FREE(c->v_shaped); FREE(c->v_shaped_part); FREE(c->v_posed); FREE(c->g_vshaped); FREE(c->verts); FREE(c->clip); FREE(c->vnorm); FREE(c->vnraw); FREE(c->snap); FREE(c->ndc);
   FREE(c->g_clip); FREE(c->g_vnorm); FREE(c->g_verts); FREE(c->posebuf); FREE(c->poses); FREE(c->gA); FREE(c->gpf); FREE(c->gJ); FREE(c->gbetas);
   FREE(c->betas); FREE(c->cam); FREE(c->tri_id); FREE(c->pre); FREE(c->signs); FREE(c->pool_list); FREE(c->final_rgba); FREE(c->plane_albedo);
   FREE(c->plane_normal); FREE(c->plane_diffuse); FREE(c->tile_count); FREE(c->tile_off); FREE(c->tile_cursor); FREE(c->tile_list);
@@ -161,7 +163,7 @@ extern "C" int vhap_ctx_reserve(vhap_ctx* ctx, int32_t B, int32_t H, int32_t W) 
   CK(cudaSetDevice(ctx->device));
   free_batch(ctx);
   size_t V = ctx->V, M = 3 * V, n = (size_t)B * H * W;
-  UP(ctx->v_shaped, (const float*)nullptr, B * M); UP(ctx->v_posed, (const float*)nullptr, B * M); UP(ctx->g_vshaped, (const float*)nullptr, B * M);
+  UP(ctx->v_shaped, (const float*)nullptr, B * M); UP(ctx->v_shaped_part, (const float*)nullptr, 8 * B * M); UP(ctx->v_posed, (const float*)nullptr, B * M); UP(ctx->g_vshaped, (const float*)nullptr, B * M);
   UP(ctx->verts, (const f4*)nullptr, B * V); UP(ctx->clip, (const f4*)nullptr, B * V); UP(ctx->vnorm, (const f4*)nullptr, B * V);
   UP(ctx->vnraw, (const f4*)nullptr, B * V); UP(ctx->snap, (const i4*)nullptr, B * V); UP(ctx->ndc, (const float*)nullptr, B * V * 2);
   UP(ctx->g_clip, (const float*)nullptr, B * V * 4); UP(ctx->g_vnorm, (const float*)nullptr, B * V * 4); UP(ctx->g_verts, (const float*)nullptr, B * V * 4);

@@ -28,8 +28,11 @@ VH_HD f3 cross3(f3 a, f3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x 
 // Atomic accumulation to distinct-address arrays (vertex / texel gradients).
 #if defined(__CUDA_ARCH__)
 #define VH_ATOMIC_ADD(ptr, val) atomicAdd((ptr), (val))
+// one 16-byte vector reduction (red.global.add.v4.f32, sm_90+) instead of 3-4 scalar ones; ptr must be 16-byte aligned
+#define VH_ATOMIC_ADD4(ptr, x, y, z, w) atomicAdd(reinterpret_cast<float4*>(ptr), make_float4((x), (y), (z), (w)))
 #else
 #define VH_ATOMIC_ADD(ptr, val) (*(ptr) += (val))
+#define VH_ATOMIC_ADD4(ptr, x, y, z, w) do { (ptr)[0] += (x); (ptr)[1] += (y); (ptr)[2] += (z); (ptr)[3] += (w); } while (0)
 #endif
 
 #ifndef VH_HOST_CHECK

@@ -31,6 +31,7 @@ struct vhap_ctx {
   // ---- per-batch scratch
   int maxB, maxH, maxW, curB, curH, curW;
   float *v_shaped, *v_posed, *g_vshaped;          // [B][3V]
+  float* v_shaped_part;                           // [8][B][3V] K-slice partial sums of the blend-shape contraction
   f4 *verts, *clip, *vnorm, *vnraw; i4* snap;     // [B][V]
   float* ndc;                                     // [B][V][2] clip.xy / clip.w
   float *g_clip, *g_vnorm, *g_verts;              // [B][V][4]
@@ -54,6 +55,7 @@ struct vhap_ctx {
   struct VhProf* prof;
   int *scan_aux, *scan_total;                     // [1024], [1]
   float* aa_code; int *pair_list, *pair_count;    // [2N], [2N], [1]
+  int* tex_l0_flag;                               // [1]
 };
 
 void vh_set_error(vhap_ctx* ctx, const char* what, const char* msg);

@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(128) k_blend_fwd(const float* __restrict__ S, 
     for (int i = 0; i < NB; ++i) acc[i] += sv * shb[i * K + k];
   }
 #pragma unroll
-  for (int i = 0; i < NB; ++i) if (i < nb) atomicAdd(out + (size_t)(b0 + i) * M + m, common + acc[i]);
+  for (int i = 0; i < NB; ++i) if (i < nb) out[((size_t)blockIdx.z * B + b0 + i) * M + m] = common + acc[i];   // per-slice partial, summed by k_skin_fwd
 }
 
 // ------------------------------------------------------------------------------------------------ skin + project + snap
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(128) k_blend_fwd(const float* __restrict__ S, 
 // (render_nvdiffrast.py:162-197) and the rasteriser's fixed-point snap (oracle/raster.py snap_vertices), one pass.
 #define SNAP_GUARD 131072.f
 template <int NB>
-__global__ void __launch_bounds__(128) k_skin_fwd(const float* __restrict__ v_shaped, const float* __restrict__ posedirs, const float* __restrict__ lbs_w,
+__global__ void __launch_bounds__(128) k_skin_fwd(const float* __restrict__ v_part, int KS, float* __restrict__ v_shaped, const float* __restrict__ posedirs, const float* __restrict__ lbs_w,
                                                   const PoseFwd* __restrict__ posebuf, const float* __restrict__ transl, const int* __restrict__ ts,
                                                   const CamParams* __restrict__ cam, int V, int B, int H, int W,
                                                   float* __restrict__ v_posed, f4* __restrict__ verts, f4* __restrict__ clip, i4* __restrict__ snap, float* __restrict__ ndc) {
@@ -146,7 +146,12 @@ __global__ void __launch_bounds__(128) k_skin_fwd(const float* __restrict__ v_sh
   float vp[NB][3];
 #pragma unroll
   for (int i = 0; i < NB; ++i) {
-    if (i < nb) { const float* s = v_shaped + (size_t)(b0 + i) * M + 3 * v; vp[i][0] = s[0]; vp[i][1] = s[1]; vp[i][2] = s[2]; }
+    if (i < nb) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+      for (int z = 0; z < KS; ++z) { const float* s = v_part + ((size_t)z * B + b0 + i) * M + 3 * v; a0 += s[0]; a1 += s[1]; a2 += s[2]; }
+      float* o = v_shaped + (size_t)(b0 + i) * M + 3 * v; o[0] = a0; o[1] = a1; o[2] = a2;
+      vp[i][0] = a0; vp[i][1] = a1; vp[i][2] = a2;
+    }
     else vp[i][0] = vp[i][1] = vp[i][2] = 0.f;
   }
   for (int p = 0; p < 36; ++p) {
@@ -196,11 +201,10 @@ void launch_flame_forward(vhap_ctx* c, const vhap_params* p, const vhap_frame_ba
   LAUNCH(c, KID_POSE_FWD, s, k_pose_fwd<<<B, 256, 0, s>>>(p->shape, p->expr, p->rotation, p->neck_pose, p->jaw_pose, p->eyes_pose, p->static_offset, fb->timesteps,
                                c->JS, c->Jt, c->Jreg, V, c->K, c->n_shape, c->betas, c->posebuf, c->poses));
   dim3 g1((M + 127) / 128, (B + VH_MAXB_CHUNK - 1) / VH_MAXB_CHUNK, BLEND_KS);
-  cudaMemsetAsync(c->v_shaped, 0, (size_t)B * M * sizeof(float), s);
   LAUNCH(c, KID_BLEND_FWD, s, k_blend_fwd<VH_MAXB_CHUNK><<<g1, 128, VH_MAXB_CHUNK * c->K * sizeof(float), s>>>(c->S_fwd, c->v_template, p->static_offset, c->betas, M, c->K,
-                                                                                  c->n_shape, B, c->v_shaped));
+                                                                                  c->n_shape, B, c->v_shaped_part));
   dim3 g2((V + 127) / 128, (B + 7) / 8);
-  LAUNCH(c, KID_SKIN_FWD, s, k_skin_fwd<8><<<g2, 128, 0, s>>>(c->v_shaped, c->posedirs, c->lbs_w, c->posebuf, p->translation, fb->timesteps, c->cam, V, B, fb->H, fb->W,
+  LAUNCH(c, KID_SKIN_FWD, s, k_skin_fwd<8><<<g2, 128, 0, s>>>(c->v_shaped_part, BLEND_KS, c->v_shaped, c->posedirs, c->lbs_w, c->posebuf, p->translation, fb->timesteps, c->cam, V, B, fb->H, fb->W,
                                    c->v_posed, c->verts, c->clip, c->snap, c->ndc));
 }
 
@@ -498,8 +502,8 @@ __global__ void k_betas_scatter(const float* __restrict__ gbetas, const int* __r
 void launch_flame_backward(vhap_ctx* c, const vhap_params* p, const vhap_frame_batch* fb, const vhap_grads* g, int opt_cam, cudaStream_t s) {
   int B = fb->B, V = c->V, M = 3 * V;
   bool need_betas = g->shape || g->expr;
-  dim3 g1((V + 127) / 128, (B + 7) / 8);
-  LAUNCH(c, KID_SKIN_BWD, s, k_skin_bwd<8><<<g1, 128, 0, s>>>(c->v_posed, c->verts, c->posedirs, c->lbs_w, c->posebuf, c->cam, fb->timesteps, c->g_verts, c->g_clip, V, B, fb->H, fb->W,
+  dim3 g1((V + 127) / 128, (B + 1) / 2);
+  LAUNCH(c, KID_SKIN_BWD, s, k_skin_bwd<2><<<g1, 128, 0, s>>>(c->v_posed, c->verts, c->posedirs, c->lbs_w, c->posebuf, c->cam, fb->timesteps, c->g_verts, c->g_clip, V, B, fb->H, fb->W,
                                    opt_cam, c->g_vshaped, g->static_offset, g->translation, c->gA, c->gpf, c->acc));
   LAUNCH(c, KID_POSE_BWD, s, k_pose_bwd<<<B, 128, 0, s>>>(c->poses, c->posebuf, c->gA, c->gpf, fb->timesteps, c->JS, c->K, g->rotation, g->neck_pose, g->jaw_pose, g->eyes_pose,
                                c->gJ, need_betas ? c->gbetas : nullptr));
@@ -635,37 +639,42 @@ __global__ void __launch_bounds__(1024) k_regs(RegArgs a) {
   if (c.opt_static_offset && a.p.static_offset) {
     const float* off = a.p.static_offset;
     int V = a.V;
-    if (sec == 1 && c.w_reg_offset >= 0.f) {
-      float l = 0.f, w = c.shared_scale * c.w_reg_offset / (3.f * V);
-      for (int i = threadIdx.x; i < 3 * V; i += blockDim.x) {
-        float wv = a.w_off ? a.w_off[i / 3] : 1.f, o = off[i];
-        l += w * wv * fabsf(o);
-        if (a.g.static_offset && o != 0.f) atomicAdd(a.g.static_offset + i, w * wv * (o > 0.f ? 1.f : -1.f));
-      }
-      l = block_sum(l, sh); if (threadIdx.x == 0) a.acc[ACC_REG_OFFSET] += l;
-    }
-    if (sec == 2 && c.w_reg_offset_lap >= 0.f) {
-      // L(base + off) - L(base) == L off  (uniform Laplacian is linear; tracker.py:682-690, flame.py:196-201)
-      float l = 0.f, w = c.shared_scale * c.w_reg_offset_lap / V;
-      for (int i = threadIdx.x; i < V; i += blockDim.x) {
-        float y[3] = {0, 0, 0};
-        for (int q = a.lap_indptr[i]; q < a.lap_indptr[i + 1]; ++q) {
-          int j = a.lap_idx[q]; float lv = a.lap_val[q];
-          y[0] += lv * off[3 * j]; y[1] += lv * off[3 * j + 1]; y[2] += lv * off[3 * j + 2];
-        }
-        float wv = a.w_off_lap ? a.w_off_lap[i] : 1.f;
-        l += w * wv * (y[0] * y[0] + y[1] * y[1] + y[2] * y[2]);
-        a.lap_y[3 * i] = 2.f * w * wv * y[0]; a.lap_y[3 * i + 1] = 2.f * w * wv * y[1]; a.lap_y[3 * i + 2] = 2.f * w * wv * y[2];
-      }
-      __syncthreads();
-      if (a.g.static_offset)
-        for (int i = threadIdx.x; i < V; i += blockDim.x)
-          for (int q = a.lap_indptr[i]; q < a.lap_indptr[i + 1]; ++q) {
-            int j = a.lap_idx[q]; float lv = a.lap_val[q];
-            atomicAdd(a.g.static_offset + 3 * j, lv * a.lap_y[3 * i]); atomicAdd(a.g.static_offset + 3 * j + 1, lv * a.lap_y[3 * i + 1]);
-            atomicAdd(a.g.static_offset + 3 * j + 2, lv * a.lap_y[3 * i + 2]);
+    // sections >= 4: one thread per vertex over a grid of helper blocks (no single-SM atomic bottleneck)
+    if (sec >= 4) {
+      int j = (sec - 4) * blockDim.x + threadIdx.x;
+      float l1 = 0.f, l2 = 0.f;
+      if (j < V) {
+        if (c.w_reg_offset >= 0.f) {                                           // tracker.py:576-587
+          float w = c.shared_scale * c.w_reg_offset / (3.f * V), wv = a.w_off ? a.w_off[j] : 1.f;
+          for (int cc = 0; cc < 3; ++cc) {
+            float o = off[3 * j + cc];
+            l1 += w * wv * fabsf(o);
+            if (a.g.static_offset && o != 0.f) atomicAdd(a.g.static_offset + 3 * j + cc, w * wv * (o > 0.f ? 1.f : -1.f));
           }
-      l = block_sum(l, sh); if (threadIdx.x == 0) a.acc[ACC_REG_OFFSET_LAP] += l;
+        }
+        if (c.w_reg_offset_lap >= 0.f) {
+          // L(base + off) - L(base) == L off (the uniform Laplacian is linear; tracker.py:682-690, flame.py:196-201).
+          // gradient in gather form: g_j = sum_i L_ij * 2 w wv_i (L off)_i over the (symmetric) sparsity pattern of row j
+          float w = c.shared_scale * c.w_reg_offset_lap / V;
+          float gj[3] = {0, 0, 0};
+          for (int qi = a.lap_indptr[j]; qi < a.lap_indptr[j + 1]; ++qi) {
+            int i = a.lap_idx[qi];
+            float y[3] = {0, 0, 0}, Lij = 0.f;
+            for (int q = a.lap_indptr[i]; q < a.lap_indptr[i + 1]; ++q) {
+              int k = a.lap_idx[q]; float lv = a.lap_val[q];
+              y[0] += lv * off[3 * k]; y[1] += lv * off[3 * k + 1]; y[2] += lv * off[3 * k + 2];
+              if (k == j) Lij = lv;
+            }
+            float wv = a.w_off_lap ? a.w_off_lap[i] : 1.f;
+            if (i == j) l2 += w * wv * (y[0] * y[0] + y[1] * y[1] + y[2] * y[2]);
+            float sc = 2.f * w * wv * Lij;
+            gj[0] += sc * y[0]; gj[1] += sc * y[1]; gj[2] += sc * y[2];
+          }
+          if (a.g.static_offset) { atomicAdd(a.g.static_offset + 3 * j, gj[0]); atomicAdd(a.g.static_offset + 3 * j + 1, gj[1]); atomicAdd(a.g.static_offset + 3 * j + 2, gj[2]); }
+        }
+      }
+      l1 = block_sum(l1, sh); l2 = block_sum(l2, sh);
+      if (threadIdx.x == 0) { if (l1 != 0.f) atomicAdd(a.acc + ACC_REG_OFFSET, l1); if (l2 != 0.f) atomicAdd(a.acc + ACC_REG_OFFSET_LAP, l2); }
     }
     if (sec == 3 && c.w_reg_offset_rigid >= 0.f && a.n_rigid > 0) {
       float ltot = 0.f;
@@ -702,5 +711,5 @@ void launch_regs(vhap_ctx* c, const vhap_params* p, const vhap_frame_batch* fb, 
   a.ts = fb->timesteps; a.B = fb->B; a.V = c->V; a.n_shape = c->n_shape; a.n_expr = c->n_expr; a.global_B = global_B;
   a.w_off = c->w_off; a.w_off_lap = c->w_off_lap; a.lap_indptr = c->lap_indptr; a.lap_idx = c->lap_idx; a.lap_val = c->lap_val; a.lap_y = c->lap_y;
   a.rigid_indptr = c->rigid_indptr; a.rigid_vids = c->rigid_vids; a.n_rigid = c->n_rigid; a.acc = c->acc;
-  LAUNCH(c, KID_REGS, s, k_regs<<<4, 1024, 0, s>>>(a));
+  LAUNCH(c, KID_REGS, s, k_regs<<<4 + (c->V + 1023) / 1024, 1024, 0, s>>>(a));
 }

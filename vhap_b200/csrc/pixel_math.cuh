@@ -24,6 +24,7 @@ struct RenderArgs {
   const int* adj_opp;         // [F*4] opposite vertex per edge (x,y,z), -1 boundary, -2 non-manifold
   const float* ndc;           // optional [B,V,2] = clip.xy / clip.w (saves the divisions in the antialias analysis)
   const float* zwbuf;         // optional [B,H,W,4]: .w of foreground pixels holds their z/w (written by pass A)
+  int* tex_l0_flag;           // optional: raised when the backward scatters into level 0 of the texel-gradient pyramid
 };
 
 struct TriSetup {
@@ -218,7 +219,7 @@ VH_HD void bilin_scatter(float* gl, const Bilin& q, f3 g) {
   const float ww[4] = {w00, w10, w01, w11};
   for (int k = 0; k < 4; ++k) {
     float* t = gl + (size_t)idx[k] * 4;
-    VH_ATOMIC_ADD(t + 0, g.x * ww[k]); VH_ATOMIC_ADD(t + 1, g.y * ww[k]); VH_ATOMIC_ADD(t + 2, g.z * ww[k]);
+    VH_ATOMIC_ADD4(t, g.x * ww[k], g.y * ww[k], g.z * ww[k], 0.f);
   }
 }
 
@@ -322,13 +323,14 @@ VH_HD void shade_pixel_bwd(const RenderArgs& A, int b, int tri, const PixShade& 
     const f3 gg[3] = {g_raw * b0, g_raw * b1, g_raw * b2};
     for (int k = 0; k < 3; ++k) {
       float* t = gv + (size_t)s.ts.vi[k] * 4;
-      VH_ATOMIC_ADD(t + 0, gg[k].x); VH_ATOMIC_ADD(t + 1, gg[k].y); VH_ATOMIC_ADD(t + 2, gg[k].z);
+      VH_ATOMIC_ADD4(t, gg[k].x, gg[k].y, gg[k].z, 0.f);
     }
   }
   float g_b0 = dot3(g_raw, s.n0 - s.n2), g_b1 = dot3(g_raw, s.n1 - s.n2);
   // texture
   float g_u, g_v, g_da[4];
   tex_sample_bwd(A, s.u, s.v, s.tx, g_alb, grad_pyr, g_u, g_v, g_da);
+  if (grad_pyr && A.tex_l0_flag && s.tx.l0 == 0) *A.tex_l0_flag = 1;
   float d0u = s.t0[0] - s.t2[0], d1u = s.t1[0] - s.t2[0], d0v = s.t0[1] - s.t2[1], d1v = s.t1[1] - s.t2[1];
   bool detach_uv = A.face_flags && (A.face_flags[tri] & 1);
   if (!detach_uv) { g_b0 += g_u * d0u + g_v * d0v; g_b1 += g_u * d1u + g_v * d1v; }
@@ -342,7 +344,7 @@ VH_HD void shade_pixel_bwd(const RenderArgs& A, int b, int tri, const PixShade& 
     float* gc = g_clip + (size_t)b * A.V * 4;
     for (int k = 0; k < 3; ++k) {
       float* t = gc + (size_t)s.ts.vi[k] * 4;
-      VH_ATOMIC_ADD(t + 0, gp[k].x); VH_ATOMIC_ADD(t + 1, gp[k].y); VH_ATOMIC_ADD(t + 3, gp[k].w);
+      VH_ATOMIC_ADD4(t, gp[k].x, gp[k].y, 0.f, gp[k].w);
     }
   }
 }

@@ -197,9 +197,7 @@ VH_HD void aa_bwd(const PassArgs& P, int b, const AAPair& r, float g_alpha) {
     float g_qx = r.d == 0 ? gsx[k] : gsy[k], g_qy = r.d == 0 ? gsy[k] : gsx[k];
     float iw = 1.f / pp[k].w;
     float* t = P.g_clip + ((size_t)b * A.V + vid[k]) * 4;
-    VH_ATOMIC_ADD(t + 0, g_qx * iw);
-    VH_ATOMIC_ADD(t + 1, g_qy * iw);
-    VH_ATOMIC_ADD(t + 3, -(g_qx * pp[k].x + g_qy * pp[k].y) * iw * iw);
+    VH_ATOMIC_ADD4(t, g_qx * iw, g_qy * iw, 0.f, -(g_qx * pp[k].x + g_qy * pp[k].y) * iw * iw);
   }
 }
 

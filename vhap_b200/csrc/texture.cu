@@ -79,6 +79,7 @@ struct TexFoldArgs {
   float w_tv, w_res;            // already divided by their mean() denominators and scaled by shared_scale
   float lr, bc1, bc2_sqrt;      // Adam: step size lr/bc1, sqrt(bias correction 2)
   int do_adam;
+  const int* l0_flag;
 };
 
 __device__ __forceinline__ float chan(const f4& t, int c) { return c == 0 ? t.x : (c == 1 ? t.y : t.z); }
@@ -94,14 +95,17 @@ __global__ void __launch_bounds__(256) k_tex_fold(TexFoldArgs a, float* __restri
     // photometric gradient: fold every pyramid level back to level 0 (box-filter adjoint: 1/4 per level)
     float g[3] = {0.f, 0.f, 0.f};
     if (a.g_pyr) {
-      float sc = 1.f;
-      for (int l = 0; l <= a.max_level; ++l) {
+      // level 0 of the gradient pyramid is only touched under magnification (mip level < 1); the backward pass raises
+      // l0_flag when it scatters there, otherwise the 16 B/texel read + re-zero of that level is skipped
+      bool l0 = a.l0_flag ? (*a.l0_flag != 0) : true;
+      float sc = l0 ? 1.f : 0.25f;
+      for (int l = l0 ? 0 : 1; l <= a.max_level; ++l) {
         int s = T >> l;
         const float* p = a.g_pyr + ((size_t)a.mip_off[l] + (size_t)(y >> l) * s + (x >> l)) * 4;
         g[0] += p[0] * sc; g[1] += p[1] * sc; g[2] += p[2] * sc;
         sc *= 0.25f;
       }
-      float* p0 = a.g_pyr + i * 4; p0[0] = 0.f; p0[1] = 0.f; p0[2] = 0.f;      // level 0 is re-zeroed here, coarser levels by a memset
+      if (l0) { float4* p0 = (float4*)(a.g_pyr + i * 4); *p0 = make_float4(0.f, 0.f, 0.f, 0.f); }   // coarser levels: memset after the kernel
     }
     f4 t = a.tex_old[i];
     float ex[3] = {a.extra[i], a.extra[n + i], a.extra[2 * n + i]};
@@ -175,7 +179,7 @@ void launch_tex_fold(vhap_ctx* c, float* tex_extra, float* g_out, float* m, floa
   a.T = T; a.max_level = c->max_level;
   for (int i = 0; i < VH_MAX_MIPS; ++i) a.mip_off[i] = c->mip_off[i];
   a.tex_old = c->mips[c->cur_mip]; a.tex_new = c->mips[c->cur_mip ^ 1]; a.g_pyr = c->g_tex;
-  a.extra = tex_extra; a.g_out = g_out; a.m = m; a.v = v; a.mask = c->uvmask_res;
+  a.extra = tex_extra; a.g_out = g_out; a.m = m; a.v = v; a.mask = c->uvmask_res; a.l0_flag = c->tex_l0_flag;
   float sh = cfg->shared_scale;
   // tv.mean(): (T-1)*T elements per channel, 3 channels (tracker.py:529-533); w already includes scale_factor^2 / ds^2
   a.w_tv = (cfg->training && cfg->opt_texture && cfg->w_reg_tex_tv >= 0.f) ? sh * cfg->w_reg_tex_tv / (3.f * (float)(T - 1) * (float)T) : 0.f;
@@ -186,6 +190,7 @@ void launch_tex_fold(vhap_ctx* c, float* tex_extra, float* g_out, float* m, floa
   int nblk = (int)((n + 255) / 256);
   LAUNCH(c, KID_TEX_FOLD, s, k_tex_fold<<<nblk, 256, 0, s>>>(a, c->tv_partials));
   LAUNCH(c, KID_TEX_LOSS, s, k_tex_loss_reduce<<<1, 1024, 0, s>>>(c->tv_partials, nblk, c->acc));
+  cudaMemsetAsync(c->tex_l0_flag, 0, sizeof(int), s);
   if (c->g_tex && c->max_level >= 1)                                      // coarser gradient levels
     cudaMemsetAsync(c->g_tex + (size_t)c->mip_off[1] * 4, 0, (c->mip_total - c->mip_off[1]) * 4 * sizeof(float), s);
   if (a.do_adam) { c->cur_mip ^= 1; build_mips(c, c->mips[c->cur_mip], s); }
