@@ -167,6 +167,11 @@ int vhap_render_photometric(vhap_ctx* ctx, const vhap_params* p, const vhap_fram
                             const float* verts_clip /*[B,V,4]*/, const float* vnorm /*[B,V,3]*/, float* losses_out,
                             float* g_clip /*[B,V,4]*/, float* g_vnorm /*[B,V,3]*/, float* g_lights /*[27]*/, float* g_tex_pyramid, void* stream);
 
+/* adjoint of the 'rgba' output of the last vhap_render_photometric forward for an external upstream gradient g_rgba
+ * [B,H,W,4] (image orientation): lets NVDiffRenderer.render_rgba be used as a torch.autograd.Function */
+int vhap_render_rgba_backward(vhap_ctx* ctx, const vhap_params* p, const vhap_frame_batch* fb, const vhap_stage_cfg* cfg,
+                              const float* g_rgba, float* g_clip, float* g_vnorm, float* g_lights, float* g_tex_pyramid, void* stream);
+
 /* debug / logging planes of the last forward (render_out dict, render_nvdiffrast.py:476-483), image orientation.
  * which: 0 rgba (after AA), 1 rgba before AA, 2 albedo, 3 normal, 4 diffuse, 5 cid.  out [B,H,W,4] float. */
 int vhap_get_plane(vhap_ctx* ctx, int32_t which, float* out, void* stream);

@@ -82,6 +82,7 @@ def lib() -> C.CDLL:
         "vhap_vertex_normals": (i32, [vp, vp, i32, vp, vp]),
         "vhap_vertex_normals_backward": (i32, [vp, vp, vp, i32, vp, vp]),
         "vhap_render_photometric": (i32, [vp, P(Params), P(FrameBatch), P(StageCfg), vp, vp, vp, vp, vp, vp, vp, vp]),
+        "vhap_render_rgba_backward": (i32, [vp, P(Params), P(FrameBatch), P(StageCfg), vp, vp, vp, vp, vp, vp]),
         "vhap_set_want_planes": (i32, [vp, i32]),
         "vhap_profile_enable": (i32, [vp, i32]),
         "vhap_profile_kernel_count": (i32, []),
@@ -110,4 +111,4 @@ EXPORTED = ["vhap_abi_version", "vhap_last_error", "vhap_ctx_create", "vhap_ctx_
             "vhap_energy_forward", "vhap_energy_backward", "vhap_get_plane", "vhap_get_geometry", "vhap_profile_enable", "vhap_profile_kernel_count", "vhap_profile_kernel_name",
             "vhap_profile_read", "vhap_set_want_planes", "vhap_overflow_flag",
             "vhap_set_injected_random", "vhap_project_backward", "vhap_vertex_normals",
-            "vhap_vertex_normals_backward", "vhap_render_photometric", "vhap_tex_grad_ptr", "vhap_set_tex_painted", "vhap_tex_rebuild", "vhap_tex_reg_fold_adam", "vhap_adam", "vhap_adam_multi"]
+            "vhap_vertex_normals_backward", "vhap_render_photometric", "vhap_render_rgba_backward", "vhap_tex_grad_ptr", "vhap_set_tex_painted", "vhap_tex_rebuild", "vhap_tex_reg_fold_adam", "vhap_adam", "vhap_adam_multi"]

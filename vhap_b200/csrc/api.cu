@@ -162,6 +162,9 @@ extern "C" int vhap_ctx_reserve(vhap_ctx* ctx, int32_t B, int32_t H, int32_t W) 
   if (B <= ctx->maxB && H <= ctx->maxH && W <= ctx->maxW && (size_t)B * H * W <= (size_t)ctx->maxB * ctx->maxH * ctx->maxW) return 0;
   CK(cudaSetDevice(ctx->device));
   free_batch(ctx);
+  if (B < ctx->maxB) B = ctx->maxB;            // never shrink a dimension: callers alternate between small and large shapes
+  if (H < ctx->maxH) H = ctx->maxH;
+  if (W < ctx->maxW) W = ctx->maxW;
   size_t V = ctx->V, M = 3 * V, n = (size_t)B * H * W;
   UP(ctx->v_shaped, (const float*)nullptr, B * M); UP(ctx->v_shaped_part, (const float*)nullptr, 8 * B * M); UP(ctx->v_posed, (const float*)nullptr, B * M); UP(ctx->g_vshaped, (const float*)nullptr, B * M);
   UP(ctx->verts, (const f4*)nullptr, B * V); UP(ctx->clip, (const f4*)nullptr, B * V); UP(ctx->vnorm, (const f4*)nullptr, B * V);
@@ -551,6 +554,27 @@ extern "C" int vhap_render_photometric(vhap_ctx* ctx, const vhap_params* p, cons
     if (g_vnorm) LAUNCH(ctx, KID_MISC, s, k_4to3<<<GRID1(n), 0, s>>>(ctx->g_vnorm, g_vnorm, n));
   }
   LAUNCH(ctx, KID_ASSEMBLE, s, k_assemble_losses<<<1, 32, 0, s>>>(ctx->acc, *cfg, 0.f, nullptr, 0, losses_out));
+  LAST();
+  return 0;
+}
+
+// backward of the last vhap_render_photometric forward for an EXTERNAL upstream gradient d L / d rgba_aa ([B,H,W,4], image
+// orientation, e.g. from autograd): the adjoint of NVDiffRenderer.render_rgba's 'rgba' output (render_nvdiffrast.py:476-483)
+extern "C" int vhap_render_rgba_backward(vhap_ctx* ctx, const vhap_params* p, const vhap_frame_batch* fb, const vhap_stage_cfg* cfg,
+                                         const float* g_rgba, float* g_clip, float* g_vnorm, float* g_lights, float* g_tex_pyramid, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (check_batch(ctx, fb)) return -4;
+  size_t n = (size_t)fb->B * ctx->V;
+  zero_backward_scratch(ctx, fb->B, s);
+  launch_flip_plane(ctx, g_rgba, ctx->final_rgba, fb->B, fb->H, fb->W, s);      // image -> raster orientation (scratch plane)
+  cudaMemsetAsync(ctx->scal, 0, 8 * sizeof(float), s);                           // no photometric scale / reg_diffuse terms
+  PassArgs P;
+  fill_render_args(ctx, P, fb, cfg, p->lights);
+  P.g_tex = g_tex_pyramid;
+  if (g_lights) cudaMemsetAsync(g_lights, 0, 27 * sizeof(float), s);
+  launch_render_backward(ctx, P, cfg, p->lights, g_lights, ctx->final_rgba, s);
+  if (g_clip) cudaMemcpyAsync(g_clip, ctx->g_clip, n * 4 * sizeof(float), cudaMemcpyDeviceToDevice, s);
+  if (g_vnorm) k_4to3<<<GRID1(n), 0, s>>>(ctx->g_vnorm, g_vnorm, n);
   LAST();
   return 0;
 }
