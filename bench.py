@@ -134,6 +134,7 @@ def build_workload(size, B, n_batches, rank, seed=0):
 
 def run_ours(args):
     import torch.distributed as dist
+    from vhap_b200.parallel import DataParallelStep
     world = int(os.environ.get("WORLD_SIZE", 1))
     rank = int(os.environ.get("RANK", 0))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -146,33 +147,29 @@ def run_ours(args):
     dev = eng.dev
     gB = B * world
     resident = [eng.stage_sample(t, l, ts.numpy()) for (t, l, ts) in batches]
-
-    def reduce_slab(local_slab, out):
-        out.copy_(local_slab)
-        if world > 1:
-            s = out[:3].clone(); dist.all_reduce(s); out[:3] = s
-            mx = out[3:4].clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX); out[3:4] = mx
-
-    def allreduce(t):
-        if world > 1:
-            dist.all_reduce(t)
-
-    def one_step(batch):
-        eng.zero_grad()
-        eng.energy(batch, backward=True, training=True, global_B=gB, reduce_fn=reduce_slab if world > 1 else None)
-        eng.adam_step(allreduce_fn=allreduce if world > 1 else None)
-        eng.global_step += 1
+    dp = DataParallelStep(eng)
+    use_graph = (world == 1) and not args.no_graph
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident timing
+    def maxms(ms):
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- warm-up (eager), then the timed region with inputs resident in HBM
     for i in range(args.warmup):
-        one_step(resident[i % n_batches])
+        dp.step(resident[i % n_batches])
     barrier()
-    eng.L.vhap_profile_enable(eng.ctx, 1)
+    if use_graph:
+        eng.graph_begin(resident)                     # one CUDA graph per (batch, texture parity); replay = one launch per step
+        for i in range(3):
+            eng.graph_step(i % n_batches)
+        barrier()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -180,54 +177,68 @@ def run_ours(args):
     barrier()
     ev0.record()
     for i in range(args.steps):
-        one_step(resident[i % n_batches])
+        if use_graph:
+            eng.graph_step(i % n_batches)
+        else:
+            dp.step(resident[i % n_batches])
     ev1.record()
     barrier()
-    ms = ev0.elapsed_time(ev1)
-    nk = eng.L.vhap_profile_kernel_count()
-    avg = (C.c_float * nk)(); cnt = (C.c_uint64 * nk)()
-    eng.L.vhap_profile_read(eng.ctx, avg, cnt)
-    eng.L.vhap_profile_enable(eng.ctx, 0)
+    ms = maxms(ev0.elapsed_time(ev1))
     clk = clocks.stop() if rank == 0 else None
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
     losses = eng.loss_dict()
 
     # ---------------- end to end: pinned host -> device copy of every step's inputs + device -> host read of the loss
     host_loss = torch.empty(24, dtype=torch.float32).pin_memory()
-    for i in range(min(args.warmup, 3)):
-        t_, l_, ts_ = batches[i % n_batches]
-        one_step(eng.stage_sample(t_, l_, ts_.numpy()))
-    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
     e0.record()
     for i in range(args.steps):
         t_, l_, ts_ = batches[i % n_batches]
-        bt = eng.stage_sample(t_, l_, ts_.numpy())          # H2D from pinned memory on the compute stream
-        one_step(bt)
+        bt = resident[i % n_batches]
+        bt.target.copy_(t_, non_blocking=True)              # H2D from pinned memory into the staged device buffers
+        bt.lmk2d.copy_(l_, non_blocking=True)
+        bt.timesteps.copy_(ts_, non_blocking=True)
+        if use_graph:
+            eng.graph_step(i % n_batches)
+        else:
+            dp.step(bt)
         host_loss.copy_(eng.losses, non_blocking=True)      # D2H of the step's loss vector
     e1.record()
     barrier()
-    ms_e2e = e0.elapsed_time(e1)
-    t = torch.tensor([ms_e2e], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_e2e = float(t.item())
+    ms_e2e = maxms(e0.elapsed_time(e1))
     h2d = batches[0][0].numel() * 2 + batches[0][1].numel() * 4 + batches[0][2].numel() * 4
     d2h = 24 * 4
+    if use_graph:
+        eng.graph_end()
+
+    # ---------------- per-kernel device time: the same steps launched eagerly with CUDA events around every kernel (the graph
+    # replay cannot be bracketed per kernel); shares and the dominant kernel's roofline come from this region
+    eng.L.vhap_profile_enable(eng.ctx, 1)
+    barrier()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    nprof = min(args.steps, 20)
+    for i in range(nprof):
+        dp.step(resident[i % n_batches])
+    p1.record()
+    barrier()
+    ms_prof = p0.elapsed_time(p1)
+    nk = eng.L.vhap_profile_kernel_count()
+    avg = (C.c_float * nk)(); cnt = (C.c_uint64 * nk)()
+    eng.L.vhap_profile_read(eng.ctx, avg, cnt)
+    eng.L.vhap_profile_enable(eng.ctx, 0)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     names = [eng.L.vhap_profile_kernel_name(k).decode() for k in range(nk)]
-    per_step = {names[k]: float(avg[k]) * cnt[k] / args.steps for k in range(nk) if cnt[k]}
-    launches = int(sum(cnt[k] for k in range(nk)))
+    per_step = {names[k]: float(avg[k]) * cnt[k] / nprof for k in range(nk) if cnt[k]}
+    launches_per_step = int(sum(cnt[k] for k in range(nk))) // nprof
+    ksum = sum(per_step.values())
     P = B * size * size
     peak, peak_src = peaks()
-    # algorithmic bytes per launch (SURVEY.md 8d / DESIGN.md "Roofline"): fused backward = 20 B/px read + 30 rho B/px texel RMW
+    # algorithmic bytes per launch (SURVEY.md 8d / DESIGN.md section 4): fused backward = 20 B/px read + 30 rho B/px texel RMW
     algo = {
         "passC_backward": P * (20 + 30 * fg),
         "passB_disturb_aa_loss": P * 20,
@@ -236,8 +247,7 @@ def run_ours(args):
         "tex_fold_reg_adam": 3 * 2048 * 2048 * 4 * 7 + 2048 * 2048 * 16,
     }
     dom = max(per_step, key=per_step.get)
-    dom_avg = float(avg[names.index(dom)])
-    kern = {k: {"ms_per_step": round(v, 4), "share": round(v / (ms / args.steps), 3)} for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])[:12]}
+    kern = {k: {"ms_per_step": round(v, 4), "share": round(v / ksum, 3)} for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])[:12]}
     roof_k = dom if dom in algo else "passC_backward"
     k_avg = float(avg[names.index(roof_k)])
     ach = algo[roof_k] / (k_avg * 1e-3) / 1e9 if k_avg > 0 else 0.0
@@ -248,16 +258,18 @@ def run_ours(args):
         "config": {"workload": f"monocular {size}x{size} batch_size={B} per GPU photometric tracking (BASELINE configs[{1 if size == 512 else 3}]), "
                                f"stage rgb_global_tracking, Adam on all groups incl. 2048^2 texture",
                    "global_batch": gB, "image": [size, size], "tex": 2048, "foreground_fraction": round(fg, 3),
-                   "parallelism": f"dp{world} frame-sharded, 1 allreduce(shared grads)+1 allreduce(texture grad) per step" if world > 1 else "single GPU",
+                   "parallelism": f"dp{world} frame-sharded, slab reduce + allreduce(param grads) + allreduce(texture grad) per step" if world > 1 else "single GPU",
+                   "launch": "CUDA graph replay (1 graph launch per step)" if use_graph else "eager (one launch per kernel)",
                    "l2": "inputs larger than L2: 4 rotating batches; per-step working set ~0.7 GB (texture, Adam state, targets)"},
         "e2e": {"value": round(gB * args.steps / (ms_e2e * 1e-3), 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": round(ms_e2e / args.steps, 4)},
-        "gpu_launches": launches,
+        "gpu_launches": launches_per_step * args.steps,
         "clocks": clk,
         "roofline": {"bound": "hbm", "kernel": roof_k, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
                      "traffic": None, "peak_source": peak_src, "avg_launch_ms": round(k_avg, 4),
-                     "algorithmic_bytes_per_launch": int(algo[roof_k]), "dominant_kernel": dom, "dominant_avg_ms": round(dom_avg, 4)},
-        "kernels": kern,
+                     "algorithmic_bytes_per_launch": int(algo[roof_k]), "dominant_kernel": dom,
+                     "timed": f"CUDA events around every launch over {nprof} eagerly launched steps ({round(ms_prof / nprof, 4)} ms/step eager)"},
+        "kernels": kern, "kernel_launches_per_step": launches_per_step,
         "losses": {k: round(v, 5) for k, v in losses.items() if k in ("total", "photo", "lmk")},
     }
     if not args.no_cpu and world == 1:
@@ -350,6 +362,7 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

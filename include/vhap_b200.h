@@ -198,6 +198,13 @@ int vhap_profile_kernel_count(void);
 const char* vhap_profile_kernel_name(int32_t kid);
 int vhap_profile_read(vhap_ctx* ctx, float* avg_ms_host, uint64_t* launches_host);   /* arrays of vhap_profile_kernel_count(); synchronises */
 
+/* ---- CUDA-graph support: with device-resident step counters no kernel argument varies from step to step, so a whole step
+ *      (forward, backward, regularisers, Adam) can be captured once per (batch, texture ping-pong parity) and replayed ------ */
+int vhap_step_counters(vhap_ctx* ctx, int32_t on, int32_t adam_step, int32_t global_step, void* stream);
+int vhap_step_advance(vhap_ctx* ctx, void* stream);
+int vhap_get_cur_mip(vhap_ctx* ctx);
+int vhap_set_cur_mip(vhap_ctx* ctx, int32_t v);
+
 /* ---- fused Adam on small parameter slabs (torch.optim.Adam, tracker.py:159-211) ------------------------------ */
 /* all parameter groups of one slab in a single launch: segment k = [off[k], off[k]+len[k]) with learning rate lr[k] (HOST arrays, <= 24) */
 int vhap_adam_multi(vhap_ctx* ctx, float* param, const float* grad, float* m, float* v, int32_t n_seg, const int64_t* off_host,

@@ -143,6 +143,7 @@ extern "C" int vhap_ctx_create(vhap_ctx** out, const vhap_mesh_desc* m, int32_t 
   UP(ctx->scan_aux, (const int*)nullptr, (size_t)1024);
   UP(ctx->scan_total, (const int*)nullptr, (size_t)1);
   UP(ctx->pair_count, (const int*)nullptr, (size_t)1);
+  UP(ctx->dev_step, (const int*)nullptr, (size_t)2);
   UP(ctx->tex_l0_flag, (const int*)nullptr, (size_t)1);
   { int one = 1; cudaMemcpy(ctx->tex_l0_flag, &one, sizeof(int), cudaMemcpyHostToDevice); }
   return 0;
@@ -578,6 +579,25 @@ extern "C" int vhap_render_rgba_backward(vhap_ctx* ctx, const vhap_params* p, co
   LAST();
   return 0;
 }
+
+// ---- device-resident step counters: make a whole optimisation step replayable as a CUDA graph (no host-varying kernel arguments)
+__global__ void k_step_set(int* d, int adam_step, int global_step) { d[0] = adam_step; d[1] = global_step; }
+__global__ void k_step_advance(int* d) { d[0] += 1; d[1] += 1; }
+// on != 0: kernels read the Adam step ([0], 1-based) and the global RNG step ([1]) from device memory instead of their arguments
+extern "C" int vhap_step_counters(vhap_ctx* ctx, int32_t on, int32_t adam_step, int32_t global_step, void* stream) {
+  ctx->use_dev_step = on;
+  LAUNCH(ctx, KID_MISC, (cudaStream_t)stream, k_step_set<<<1, 1, 0, (cudaStream_t)stream>>>(ctx->dev_step, adam_step, global_step));
+  LAST();
+  return 0;
+}
+extern "C" int vhap_step_advance(vhap_ctx* ctx, void* stream) {
+  LAUNCH(ctx, KID_MISC, (cudaStream_t)stream, k_step_advance<<<1, 1, 0, (cudaStream_t)stream>>>(ctx->dev_step));
+  LAST();
+  return 0;
+}
+// texture pyramid ping-pong index (0/1): which level-0 buffer is current; needed when graphs captured per parity are replayed
+extern "C" int vhap_get_cur_mip(vhap_ctx* ctx) { return ctx->cur_mip; }
+extern "C" int vhap_set_cur_mip(vhap_ctx* ctx, int32_t v) { ctx->cur_mip = v & 1; return 0; }
 
 // copies the engine's own geometry of the last forward: which = 0 world vertices [B,V,4], 1 clip positions [B,V,4], 2 vertex normals [B,V,4]
 extern "C" int vhap_get_geometry(vhap_ctx* ctx, int32_t which, float* out, void* stream) {

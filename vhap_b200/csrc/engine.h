@@ -56,6 +56,7 @@ struct vhap_ctx {
   int *scan_aux, *scan_total;                     // [1024], [1]
   float* aa_code; int *pair_list, *pair_count;    // [2N], [2N], [1]
   int* tex_l0_flag;                               // [1]
+  int* dev_step; int use_dev_step;                // device counters [0] Adam step (1-based), [1] global step; used when use_dev_step
 };
 
 void vh_set_error(vhap_ctx* ctx, const char* what, const char* msg);

@@ -25,6 +25,7 @@ struct PassArgs {
   const uint8_t* inj_w;       // injected Bernoulli draws (bit0 fg, bit1 bg) or NULL -> Philox
   const float* inj_u;         // injected uniform for the pool index or NULL -> Philox
   uint64_t seed, step;
+  const int* step_ptr;        // optional device-resident step counter ([1] = global step) used instead of `step` (CUDA-graph replay)
   int bg_mode; float bg_color[3];
   // scalars produced by the finalize step, consumed by pass C
   const float* scal;          // [0] photo_scale = w_photo/(3 n_fg)  [1] g_var = w_regdiff/(B_glob*H*W)  [2] g_max (w_regdiff if max>1 else 0)
@@ -96,7 +97,8 @@ VH_HD f4 disturbed_color(const PassArgs& P, int b, int y, int x, int id, float* 
   } else {
     // counter-based generator (splitmix64 of (pixel, step, seed)); the reference's torch Philox stream cannot be reproduced
     // anyway (different consumption order), see DESIGN.md "Disturbance randomness"
-    uint64_t z = (uint64_t)pix * 0x9E3779B97F4A7C15ull + P.step * 0xD1B54A32D192ED03ull + P.seed;
+    uint64_t stp = P.step_ptr ? (uint64_t)P.step_ptr[1] : P.step;
+    uint64_t z = (uint64_t)pix * 0x9E3779B97F4A7C15ull + stp * 0xD1B54A32D192ED03ull + P.seed;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
     float ub = (float)((uint32_t)z >> 8) * 5.9604644775390625e-08f;      // 24-bit uniform in [0,1)
     w = rate >= 0.f && ub < rate;

@@ -80,6 +80,7 @@ struct TexFoldArgs {
   float lr, bc1, bc2_sqrt;      // Adam: step size lr/bc1, sqrt(bias correction 2)
   int do_adam;
   const int* l0_flag;
+  const int* step_ptr;          // device Adam step (CUDA-graph replay) or NULL
 };
 
 __device__ __forceinline__ float chan(const f4& t, int c) { return c == 0 ? t.x : (c == 1 ? t.y : t.z); }
@@ -123,13 +124,15 @@ __global__ void __launch_bounds__(256) k_tex_fold(TexFoldArgs a, float* __restri
     }
     if (a.g_out) { a.g_out[i] = g[0]; a.g_out[n + i] = g[1]; a.g_out[2 * n + i] = g[2]; }
     if (a.do_adam) {
+      float bc1 = a.bc1, bc2s = a.bc2_sqrt;
+      if (a.step_ptr) { float st = (float)a.step_ptr[0]; bc1 = 1.f - powf(0.9f, st); bc2s = sqrtf(1.f - powf(0.999f, st)); }
       f4 o = t;
       for (int c = 0; c < 3; ++c) {
         size_t k = c * n + i;
         float m = 0.9f * a.m[k] + 0.1f * g[c];
         float v = 0.999f * a.v[k] + 0.001f * g[c] * g[c];
         a.m[k] = m; a.v[k] = v;
-        float upd = (a.lr / a.bc1) * m / (sqrtf(v) / a.bc2_sqrt + 1e-8f);
+        float upd = (a.lr / bc1) * m / (sqrtf(v) / bc2s + 1e-8f);
         float ne = ex[c] - upd;
         a.extra[k] = ne;
         float base = chan(t, c) - ex[c];                                          // painted part
@@ -179,7 +182,7 @@ void launch_tex_fold(vhap_ctx* c, float* tex_extra, float* g_out, float* m, floa
   a.T = T; a.max_level = c->max_level;
   for (int i = 0; i < VH_MAX_MIPS; ++i) a.mip_off[i] = c->mip_off[i];
   a.tex_old = c->mips[c->cur_mip]; a.tex_new = c->mips[c->cur_mip ^ 1]; a.g_pyr = c->g_tex;
-  a.extra = tex_extra; a.g_out = g_out; a.m = m; a.v = v; a.mask = c->uvmask_res; a.l0_flag = c->tex_l0_flag;
+  a.extra = tex_extra; a.g_out = g_out; a.m = m; a.v = v; a.mask = c->uvmask_res; a.l0_flag = c->tex_l0_flag; a.step_ptr = c->use_dev_step ? c->dev_step : nullptr;
   float sh = cfg->shared_scale;
   // tv.mean(): (T-1)*T elements per channel, 3 channels (tracker.py:529-533); w already includes scale_factor^2 / ds^2
   a.w_tv = (cfg->training && cfg->opt_texture && cfg->w_reg_tex_tv >= 0.f) ? sh * cfg->w_reg_tex_tv / (3.f * (float)(T - 1) * (float)T) : 0.f;
@@ -208,9 +211,10 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
 
 struct AdamSegs { int n_seg; int off[24]; int len[24]; float lr[24]; };
 __global__ void k_adam_multi(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, AdamSegs sg, int total,
-                             float inv_bc1, float bc2_sqrt) {
+                             float inv_bc1, float bc2_sqrt, const int* __restrict__ step_ptr) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
+  if (step_ptr) { float st = (float)step_ptr[0]; inv_bc1 = 1.f / (1.f - powf(0.9f, st)); bc2_sqrt = sqrtf(1.f - powf(0.999f, st)); }
   int k = 0, base = 0;
   while (k < sg.n_seg - 1 && i >= base + sg.len[k]) { base += sg.len[k]; ++k; }
   int j = sg.off[k] + (i - base);
@@ -226,7 +230,7 @@ void launch_adam_multi(vhap_ctx* c, float* p, const float* g, float* m, float* v
   int total = 0;
   for (int k = 0; k < sg.n_seg; ++k) { sg.off[k] = (int)off[k]; sg.len[k] = (int)len[k]; sg.lr[k] = lr[k]; total += (int)len[k]; }
   float bc1 = 1.f - powf(0.9f, (float)step), bc2s = sqrtf(1.f - powf(0.999f, (float)step));
-  if (total > 0) LAUNCH(c, KID_ADAM, s, k_adam_multi<<<(total + 255) / 256, 256, 0, s>>>(p, g, m, v, sg, total, 1.f / bc1, bc2s));
+  if (total > 0) LAUNCH(c, KID_ADAM, s, k_adam_multi<<<(total + 255) / 256, 256, 0, s>>>(p, g, m, v, sg, total, 1.f / bc1, bc2s, c->use_dev_step ? c->dev_step : nullptr));
 }
 
 void launch_adam(vhap_ctx* c, float* p, const float* g, float* m, float* v, int64_t n, float lr, int step, cudaStream_t s) {

@@ -334,6 +334,43 @@ class Engine:
         self.global_step += 1
         return losses
 
+    # ------------------------------------------------------------------ CUDA-graph replay of whole steps
+    def graph_begin(self, batches):
+        """Capture one optimisation step per (batch, texture ping-pong parity) as CUDA graphs.  All step-dependent values
+        (Adam step, RNG step) live in device memory (vhap_step_counters), so the graphs are replayable indefinitely."""
+        s = self._stream()
+        self._ck(self.L.vhap_step_counters(self.ctx, 1, self.step_count + 1, self.global_step, s))
+        torch.cuda.synchronize(self.dev)
+        self._graphs = {}
+        parity0 = self.L.vhap_get_cur_mip(self.ctx)
+        step_save, gstep_save = self.step_count, self.global_step
+        side = torch.cuda.Stream(self.dev)
+        for bi, batch in enumerate(batches):
+            for par in (0, 1):
+                self.L.vhap_set_cur_mip(self.ctx, par)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    self.zero_grad()
+                    self.energy(batch, backward=True, training=True)
+                    self.adam_step()
+                    self._ck(self.L.vhap_step_advance(self.ctx, self._stream()))
+                self._graphs[(bi, par)] = g
+        self.step_count, self.global_step = step_save, gstep_save       # capture executed nothing
+        self._parity = parity0
+        self.L.vhap_set_cur_mip(self.ctx, parity0)
+
+    def graph_step(self, bi: int):
+        self._graphs[(bi, self._parity)].replay()
+        self._parity ^= 1
+        self.step_count += 1
+        self.global_step += 1
+
+    def graph_end(self):
+        torch.cuda.synchronize(self.dev)
+        self.L.vhap_set_cur_mip(self.ctx, self._parity)
+        self._ck(self.L.vhap_step_counters(self.ctx, 0, 0, 0, self._stream()))
+        self._graphs = {}
+
     # ------------------------------------------------------------------ logging planes (render_out dict)
     def render_planes(self, batch: Batch, training=False) -> Dict[str, torch.Tensor]:
         self.L.vhap_set_want_planes(self.ctx, 1)
