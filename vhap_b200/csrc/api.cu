@@ -144,6 +144,8 @@ extern "C" int vhap_ctx_create(vhap_ctx** out, const vhap_mesh_desc* m, int32_t 
   UP(ctx->scan_total, (const int*)nullptr, (size_t)1);
   UP(ctx->pair_count, (const int*)nullptr, (size_t)1);
   UP(ctx->dev_step, (const int*)nullptr, (size_t)2);
+  for (int i = 0; i < 2; ++i) CK(cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking));
+  for (int i = 0; i < 4; ++i) CK(cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming));
   UP(ctx->tex_l0_flag, (const int*)nullptr, (size_t)1);
   { int one = 1; cudaMemcpy(ctx->tex_l0_flag, &one, sizeof(int), cudaMemcpyHostToDevice); }
   return 0;
@@ -383,10 +385,19 @@ extern "C" int vhap_energy_backward(vhap_ctx* ctx, const vhap_params* p, const v
   const vhap_grads* gg = g ? g : &none;
   int opt_cam = (gg->focal_length != nullptr) && (fb->K == nullptr);
   // landmark energy (tracker.py:712-719): mean over global_B * n landmarks
+  // fork: the parameter-space regularisers only need the parameters and the (already zeroed) gradient slab -> aux stream 0,
+  // concurrent with the render backward (works eagerly and inside CUDA-graph capture: fork/join through events)
+  if (cfg->training) {
+    cudaEventRecord(ctx->ev[0], s);
+    cudaStreamWaitEvent(ctx->aux[0], ctx->ev[0], 0);
+    launch_regs(ctx, p, fb, cfg, g, global_B, ctx->aux[0]);
+    cudaEventRecord(ctx->ev[1], ctx->aux[0]);
+  }
   if (cfg->w_landmark >= 0.f) {
     int nl = cfg->jawline_off ? 51 : 68;
     launch_landmarks(ctx, fb, cfg->w_landmark / ((float)global_B * nl), cfg->jawline_off, nullptr, nullptr, 1, opt_cam, global_B, s);
   }
+  ctx->tex_fork_pending = 0;
   if (photo) {
     PassArgs P;
     fill_render_args(ctx, P, fb, cfg, p->lights);
@@ -394,11 +405,13 @@ extern "C" int vhap_energy_backward(vhap_ctx* ctx, const vhap_params* p, const v
     if (g) {
       P.g_tex = gg->tex_grad_pyramid;
       launch_render_backward(ctx, P, cfg, p->lights, gg->lights, nullptr, s);
+      cudaEventRecord(ctx->ev[2], s);          // texel gradients complete: the texture update may start (see vhap_tex_reg_fold_adam)
+      ctx->tex_fork_pending = 1;
       launch_vnormals_bwd(ctx, fb->B, s);
     }
   }
   if (g) launch_flame_backward(ctx, p, fb, gg, opt_cam, s);
-  if (cfg->training) launch_regs(ctx, p, fb, cfg, g, global_B, s);
+  if (cfg->training) cudaStreamWaitEvent(s, ctx->ev[1], 0);        // join the regularisers
   float max_hw = (float)(fb->H > fb->W ? fb->H : fb->W);
   LAUNCH(ctx, KID_ASSEMBLE, s, k_assemble_losses<<<1, 32, 0, s>>>(ctx->acc, *cfg, max_hw, gg->focal_length, opt_cam, losses_out));
   LAST();
@@ -434,7 +447,18 @@ extern "C" int vhap_get_plane(vhap_ctx* ctx, int32_t which, float* out, void* st
 extern "C" int vhap_tex_reg_fold_adam(vhap_ctx* ctx, float* tex_extra, float* g_out, float* adam_m, float* adam_v, float lr, int32_t step,
                                       const vhap_stage_cfg* cfg, float photo_scale, float* losses_out, void* stream) {
   (void)photo_scale;
-  launch_tex_fold(ctx, tex_extra, g_out, adam_m, adam_v, lr, step, cfg, losses_out, (cudaStream_t)stream);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (ctx->tex_fork_pending) {
+    // the texture fold / Adam / mip rebuild only depends on the texel gradients (event 2, recorded right after the fused
+    // backward): run it on aux stream 1 concurrently with the geometry backward that was enqueued after that event, then join
+    ctx->tex_fork_pending = 0;
+    cudaStreamWaitEvent(ctx->aux[1], ctx->ev[2], 0);
+    launch_tex_fold(ctx, tex_extra, g_out, adam_m, adam_v, lr, step, cfg, losses_out, ctx->aux[1]);
+    cudaEventRecord(ctx->ev[3], ctx->aux[1]);
+    cudaStreamWaitEvent(s, ctx->ev[3], 0);
+  } else {
+    launch_tex_fold(ctx, tex_extra, g_out, adam_m, adam_v, lr, step, cfg, losses_out, s);
+  }
   if (losses_out) {
     // add the two texture terms to the loss vector produced by vhap_energy_backward
     LAUNCH(ctx, KID_ASSEMBLE, (cudaStream_t)stream, k_assemble_losses<<<1, 32, 0, (cudaStream_t)stream>>>(ctx->acc, *cfg, 0.f, nullptr, 0, losses_out));

@@ -56,6 +56,7 @@ struct vhap_ctx {
   int *scan_aux, *scan_total;                     // [1024], [1]
   float* aa_code; int *pair_list, *pair_count;    // [2N], [2N], [1]
   int* tex_l0_flag;                               // [1]
+  cudaStream_t aux[2]; cudaEvent_t ev[4]; int tex_fork_pending;   // fork/join of independent kernel chains
   int* dev_step; int use_dev_step;                // device counters [0] Adam step (1-based), [1] global step; used when use_dev_step
 };
 
