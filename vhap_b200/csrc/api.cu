@@ -448,7 +448,8 @@ extern "C" int vhap_tex_reg_fold_adam(vhap_ctx* ctx, float* tex_extra, float* g_
                                       const vhap_stage_cfg* cfg, float photo_scale, float* losses_out, void* stream) {
   (void)photo_scale;
   cudaStream_t s = (cudaStream_t)stream;
-  if (ctx->tex_fork_pending) {
+  if (ctx->tex_fork_pending && g_out == nullptr) {
+    // (with a caller-owned dense output the call stays on the caller's stream: ordering w.r.t. the caller's own work on g_out)
     // the texture fold / Adam / mip rebuild only depends on the texel gradients (event 2, recorded right after the fused
     // backward): run it on aux stream 1 concurrently with the geometry backward that was enqueued after that event, then join
     ctx->tex_fork_pending = 0;
@@ -457,6 +458,7 @@ extern "C" int vhap_tex_reg_fold_adam(vhap_ctx* ctx, float* tex_extra, float* g_
     cudaEventRecord(ctx->ev[3], ctx->aux[1]);
     cudaStreamWaitEvent(s, ctx->ev[3], 0);
   } else {
+    ctx->tex_fork_pending = 0;
     launch_tex_fold(ctx, tex_extra, g_out, adam_m, adam_v, lr, step, cfg, losses_out, s);
   }
   if (losses_out) {
