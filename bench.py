@@ -148,7 +148,7 @@ def run_ours(args):
     gB = B * world
     resident = [eng.stage_sample(t, l, ts.numpy()) for (t, l, ts) in batches]
     dp = DataParallelStep(eng)
-    use_graph = (world == 1) and not args.no_graph
+    use_graph = not args.no_graph
 
     def barrier():
         if world > 1:
@@ -166,7 +166,7 @@ def run_ours(args):
         dp.step(resident[i % n_batches])
     barrier()
     if use_graph:
-        eng.graph_begin(resident)                     # one CUDA graph per (batch, texture parity); replay = one launch per step
+        eng.graph_begin(resident, body=dp.body if world > 1 else None)   # one CUDA graph per (batch, texture parity)
         for i in range(3):
             eng.graph_step(i % n_batches)
         barrier()

@@ -335,9 +335,10 @@ class Engine:
         return losses
 
     # ------------------------------------------------------------------ CUDA-graph replay of whole steps
-    def graph_begin(self, batches):
+    def graph_begin(self, batches, body=None):
         """Capture one optimisation step per (batch, texture ping-pong parity) as CUDA graphs.  All step-dependent values
-        (Adam step, RNG step) live in device memory (vhap_step_counters), so the graphs are replayable indefinitely."""
+        (Adam step, RNG step) live in device memory (vhap_step_counters), so the graphs are replayable indefinitely.
+        `body(batch)` overrides the captured step (e.g. the data-parallel step incl. its NCCL collectives)."""
         s = self._stream()
         self._ck(self.L.vhap_step_counters(self.ctx, 1, self.step_count + 1, self.global_step, s))
         torch.cuda.synchronize(self.dev)
@@ -350,9 +351,12 @@ class Engine:
                 self.L.vhap_set_cur_mip(self.ctx, par)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=side):
-                    self.zero_grad()
-                    self.energy(batch, backward=True, training=True)
-                    self.adam_step()
+                    if body is not None:
+                        body(batch)
+                    else:
+                        self.zero_grad()
+                        self.energy(batch, backward=True, training=True)
+                        self.adam_step()
                     self._ck(self.L.vhap_step_advance(self.ctx, self._stream()))
                 self._graphs[(bi, par)] = g
         self.step_count, self.global_step = step_save, gstep_save       # capture executed nothing

@@ -47,6 +47,15 @@ class DataParallelStep:
         self.e, self.group = engine, group
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
 
+    def body(self, batch):
+        """the step without host-side counters: what gets captured into a CUDA graph (Engine.graph_begin(body=...))"""
+        e = self.e
+        e.zero_grad()
+        gB = batch.B * self.world
+        red = (lambda a, b: reduce_forward_slab(a, b, self.group)) if self.world > 1 else None
+        e.energy(batch, backward=True, training=True, global_B=gB, reduce_fn=red)
+        e.adam_step(allreduce_fn=(lambda t: allreduce_sum(t, self.group)) if self.world > 1 else None)
+
     def step(self, batch):
         e = self.e
         e.zero_grad()
