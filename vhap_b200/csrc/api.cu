@@ -33,7 +33,7 @@ extern "C" int vhap_abi_version(void) { return 1; }
 static const char* const KID_NAMES[KID_COUNT] = {
     "cam_setup", "pose_fwd", "blend_fwd", "skin_fwd", "landmarks", "vnormals", "vnormals_bwd", "skin_bwd", "pose_bwd", "joff_bwd", "blend_bwd",
     "betas_scatter", "regs", "snap", "bin", "scan", "fine_raster", "rast_out", "passA_shade", "pool_count", "pool_scan", "pool_scatter",
-    "aa_pairs", "passB_disturb_aa_loss", "reduce_partials", "forward_slab", "finalize", "passC_backward", "lights_reduce", "tex_level0", "mip_down",
+    "aa_pairs", "passB_disturb_aa_loss", "reduce_partials", "forward_slab", "finalize", "passC1_color_adjoint", "passC_backward", "lights_reduce", "tex_level0", "mip_down",
     "tex_fold_reg_adam", "tex_loss_reduce", "adam", "assemble_losses", "misc"};
 
 // per-kernel device time, measured with CUDA events on the launching stream (see LAUNCH in engine.h)
@@ -158,7 +158,7 @@ static void free_batch(vhap_ctx* c) {
   FREE(c->g_clip); FREE(c->g_vnorm); FREE(c->g_verts); FREE(c->posebuf); FREE(c->poses); FREE(c->gA); FREE(c->gpf); FREE(c->gJ); FREE(c->gbetas);
   FREE(c->betas); FREE(c->cam); FREE(c->tri_id); FREE(c->pre); FREE(c->signs); FREE(c->pool_list); FREE(c->final_rgba); FREE(c->plane_albedo);
   FREE(c->plane_normal); FREE(c->plane_diffuse); FREE(c->tile_count); FREE(c->tile_off); FREE(c->tile_cursor); FREE(c->tile_list);
-  FREE(c->pool_blk_count); FREE(c->pool_blk_off); FREE(c->partials); FREE(c->aa_code); FREE(c->pair_list);
+  FREE(c->pool_blk_count); FREE(c->pool_blk_off); FREE(c->partials); FREE(c->aa_code); FREE(c->pair_list); FREE(c->grgb);
 }
 
 extern "C" int vhap_ctx_reserve(vhap_ctx* ctx, int32_t B, int32_t H, int32_t W) {
@@ -178,7 +178,7 @@ extern "C" int vhap_ctx_reserve(vhap_ctx* ctx, int32_t B, int32_t H, int32_t W) 
   UP(ctx->gbetas, (const float*)nullptr, (size_t)B * ctx->K); UP(ctx->betas, (const float*)nullptr, (size_t)B * ctx->K);
   UP(ctx->cam, (const CamParams*)nullptr, (size_t)B);
   UP(ctx->tri_id, (const int*)nullptr, n); UP(ctx->pre, (const f4*)nullptr, n); UP(ctx->signs, (const uint8_t*)nullptr, n);
-  UP(ctx->pool_list, (const int*)nullptr, n); UP(ctx->aa_code, (const float*)nullptr, n * 2); UP(ctx->pair_list, (const int*)nullptr, n * 2);
+  UP(ctx->pool_list, (const int*)nullptr, n); UP(ctx->aa_code, (const float*)nullptr, n * 2); UP(ctx->pair_list, (const int*)nullptr, n * 2); UP(ctx->grgb, (const f4*)nullptr, n);
   UP(ctx->final_rgba, (const float*)nullptr, n * 4); UP(ctx->plane_albedo, (const f4*)nullptr, n); UP(ctx->plane_normal, (const f4*)nullptr, n);
   UP(ctx->plane_diffuse, (const f4*)nullptr, n);
   int tiles = B * ((H + VH_TILE - 1) / VH_TILE) * ((W + VH_TILE - 1) / VH_TILE);

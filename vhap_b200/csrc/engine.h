@@ -55,6 +55,7 @@ struct vhap_ctx {
   struct VhProf* prof;
   int *scan_aux, *scan_total;                     // [1024], [1]
   float* aa_code; int *pair_list, *pair_count;    // [2N], [2N], [1]
+  f4* grgb;                                       // [N] d L / d rgb of the compacted foreground pixels
   int* tex_l0_flag;                               // [1]
   cudaStream_t aux[2]; cudaEvent_t ev[4]; int tex_fork_pending;   // fork/join of independent kernel chains
   int* dev_step; int use_dev_step;                // device counters [0] Adam step (1-based), [1] global step; used when use_dev_step
@@ -67,7 +68,7 @@ void vh_set_error(vhap_ctx* ctx, const char* what, const char* msg);
 // report per-kernel device time measured live inside its timed region.
 enum { KID_CAM = 0, KID_POSE_FWD, KID_BLEND_FWD, KID_SKIN_FWD, KID_LMK, KID_VNORM, KID_VNORM_BWD, KID_SKIN_BWD, KID_POSE_BWD, KID_JOFF_BWD,
        KID_BLEND_BWD, KID_BETAS_SCATTER, KID_REGS, KID_SNAP, KID_BIN, KID_SCAN, KID_FINE, KID_RAST_OUT, KID_PASSA, KID_POOL_COUNT,
-       KID_POOL_SCAN, KID_POOL_SCATTER, KID_AA_PAIRS, KID_PASSB, KID_REDUCE, KID_SLAB, KID_FINALIZE, KID_PASSC, KID_LIGHTS_REDUCE, KID_TEX_L0, KID_MIP,
+       KID_POOL_SCAN, KID_POOL_SCATTER, KID_AA_PAIRS, KID_PASSB, KID_REDUCE, KID_SLAB, KID_FINALIZE, KID_PASSC1, KID_PASSC, KID_LIGHTS_REDUCE, KID_TEX_L0, KID_MIP,
        KID_TEX_FOLD, KID_TEX_LOSS, KID_ADAM, KID_ASSEMBLE, KID_MISC, KID_COUNT };
 #define VH_PROF_SLOTS 128
 struct VhProf {

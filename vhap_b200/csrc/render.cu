@@ -155,7 +155,20 @@ __global__ void __launch_bounds__(PB) k_passB(PassArgs P, float* __restrict__ pa
   block_reduce_store<2>(acc, sh, partials + (size_t)blockIdx.x * VH_NPART + 2);
 }
 
-__global__ void __launch_bounds__(PB, 2) k_passC(PassArgs P, const float* __restrict__ ext_grad, float* __restrict__ partials) {
+__global__ void __launch_bounds__(PB) k_passC1(PassArgs P, const float* __restrict__ ext_grad, f4* __restrict__ grgb) {
+  const RenderArgs& A = P.R;
+  int n_fg = A.B * A.H * A.W - P.pool_count[0];
+  const int* list = P.pool_list + P.pool_base[1];
+  for (int i = blockIdx.x * PB + threadIdx.x; i < n_fg; i += gridDim.x * PB) {
+    int pix = list[i];
+    int x = pix % A.W, y = (pix / A.W) % A.H, b = pix / (A.W * A.H);
+    f3 g = passC1_body(P, b, y, x, ext_grad);
+    f4 o = {g.x, g.y, g.z, 0.f};
+    grgb[i] = o;                                    // indexed by list position: coalesced
+  }
+}
+
+__global__ void __launch_bounds__(PB, 2) k_passC2(PassArgs P, const f4* __restrict__ grgb, float* __restrict__ partials) {
   __shared__ float sh[8 * 27];
   const RenderArgs& A = P.R;
   int n_fg = A.B * A.H * A.W - P.pool_count[0];
@@ -166,7 +179,8 @@ __global__ void __launch_bounds__(PB, 2) k_passC(PassArgs P, const float* __rest
   for (int i = blockIdx.x * PB + threadIdx.x; i < n_fg; i += gridDim.x * PB) {
     int pix = list[i];
     int x = pix % A.W, y = (pix / A.W) % A.H, b = pix / (A.W * A.H);
-    passC_body(P, b, y, x, ext_grad, gl);
+    f4 g = grgb[i];
+    passC2_body(P, b, y, x, mk3(g.x, g.y, g.z), gl);
   }
   block_reduce_store<27>(gl, sh, partials + (size_t)blockIdx.x * VH_NPART + 4);
 }
@@ -329,6 +343,7 @@ void launch_render_backward(vhap_ctx* c, PassArgs& P, const vhap_stage_cfg* cfg,
   size_t n = (size_t)A.B * A.H * A.W;
   int nblk = (int)((n + PB - 1) / PB);
   int grid = nblk < NPERSIST ? nblk : NPERSIST;
-  LAUNCH(c, KID_PASSC, s, k_passC<<<grid, PB, 0, s>>>(P, ext_grad, c->partials));
+  LAUNCH(c, KID_PASSC1, s, k_passC1<<<grid, PB, 0, s>>>(P, ext_grad, c->grgb));
+  LAUNCH(c, KID_PASSC, s, k_passC2<<<grid, PB, 0, s>>>(P, c->grgb, c->partials));
   if (g_lights) LAUNCH(c, KID_LIGHTS_REDUCE, s, k_reduce_cols<<<16, 256, 0, s>>>(c->partials, grid, 4, 27, g_lights, nullptr));
 }

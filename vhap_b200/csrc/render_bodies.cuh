@@ -298,14 +298,16 @@ VH_HD f3 sign_grad(uint8_t sg, float scale) {
 // ------------------------------------------------------------------------------------------ pass C
 // g_lights_local[27] accumulates the light gradient of this pixel.  ext_grad (optional, [B,H,W,4] raster orientation)
 // replaces the L1-loss gradient with a caller-provided d L / d rgba_aa (modular render_rgba backward).
-VH_HD void passC_body(const PassArgs& P, int b, int y, int x, const float* ext_grad, float* g_lights_local) {
+// Split in two so that each kernel stays small (registers, instruction cache): C1 = colour-gradient bookkeeping through the
+// antialias / disturbance adjoints (+ the rare silhouette position gradients) -> d L / d rgb of the pixel; C2 = shading adjoint.
+VH_HD f3 passC1_body(const PassArgs& P, int b, int y, int x, const float* ext_grad) {
   const RenderArgs& A = P.R;
   size_t pix = ((size_t)b * A.H + y) * A.W + x;
   int id = A.tri_id[pix];
   // Only FOREGROUND pixels are visited (the kernel walks the compacted foreground list): a background pixel has no
   // parameters behind its colour, and the position gradient of a (foreground, background) pair is owned by its
   // foreground pixel; (foreground, foreground) pairs are owned by their pixel 0.
-  if (id <= 0) return;
+  if (id <= 0) return mk3(0, 0, 0);
   float scale = P.scal[0];
   f3 gp = ext_grad ? mk3(ext_grad[pix * 4], ext_grad[pix * 4 + 1], ext_grad[pix * 4 + 2]) : sign_grad(P.signs[pix], scale);
   float own_w;
@@ -345,7 +347,14 @@ VH_HD void passC_body(const PassArgs& P, int b, int y, int x, const float* ext_g
     }
   }
   gD.x += self_w * gp.x; gD.y += self_w * gp.y; gD.z += self_w * gp.z;
-  f3 g_rgb = gD * own_w;
+  return gD * own_w;
+}
+
+VH_HD void passC2_body(const PassArgs& P, int b, int y, int x, f3 g_rgb, float* g_lights_local) {
+  const RenderArgs& A = P.R;
+  size_t pix = ((size_t)b * A.H + y) * A.W + x;
+  int id = A.tri_id[pix];
+  if (id <= 0) return;
   // reg_diffuse on diffuse_detach_normal (tracker.py:547-550): variance term + global max term
   f3 g_dd = mk3(0, 0, 0);
   PixShade s;
@@ -361,4 +370,9 @@ VH_HD void passC_body(const PassArgs& P, int b, int y, int x, const float* ext_g
     }
   }
   shade_pixel_bwd(A, b, id - 1, s, g_rgb, g_dd, P.g_clip, P.g_vnorm, P.g_tex, g_lights_local);
+}
+
+VH_HD void passC_body(const PassArgs& P, int b, int y, int x, const float* ext_grad, float* g_lights_local) {
+  f3 g = passC1_body(P, b, y, x, ext_grad);
+  passC2_body(P, b, y, x, g, g_lights_local);
 }
