@@ -8,7 +8,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 SO = HERE / "libvhap_b200.so"
-SOURCES = ["flame.cu", "raster.cu", "render.cu", "texture.cu", "api.cu"]
+SOURCES = ["flame.cu", "raster.cu", "render.cu", "texture.cu", "blend_tc.cu", "api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "--fmad=true"]
 
@@ -34,7 +34,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             print(r.stderr)
         return obj
 
-    with ThreadPoolExecutor(max_workers=5) as ex:
+    with ThreadPoolExecutor(max_workers=6) as ex:
         objs = list(ex.map(cc, SOURCES))
     cmd = [NVCC, "-shared", "-o", str(SO)] + [str(o) for o in objs] + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)

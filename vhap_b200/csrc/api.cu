@@ -81,6 +81,11 @@ extern "C" int vhap_ctx_create(vhap_ctx** out, const vhap_mesh_desc* m, int32_t 
     std::vector<float> st(M * K);
     for (size_t r = 0; r < M; ++r) for (int k = 0; k < K; ++k) st[(size_t)k * M + r] = m->shapedirs_host[r * K + k];
     UP(ctx->S_fwd, st.data(), M * K);                          // [K][3V]
+    ctx->Mpad = (int)((M + 3) & ~(size_t)3);
+    std::vector<float> stp((size_t)K * ctx->Mpad, 0.f);
+    for (int k = 0; k < K; ++k) memcpy(&stp[(size_t)k * ctx->Mpad], &st[(size_t)k * M], M * sizeof(float));
+    UP(ctx->S_fwd_pad, stp.data(), (size_t)K * ctx->Mpad);
+    { const char* e = getenv("VHAP_B200_BLEND"); ctx->use_tc_blend = !(e && strcmp(e, "simt") == 0); }
     // JS[k][j*3+c] = sum_v Jreg[j][v] S[v][c][k] ; Jt = Jreg template
     std::vector<float> js((size_t)K * 15, 0.f), jt(15, 0.f);
     for (int j = 0; j < 5; ++j)
@@ -169,7 +174,7 @@ extern "C" int vhap_ctx_reserve(vhap_ctx* ctx, int32_t B, int32_t H, int32_t W) 
   if (H < ctx->maxH) H = ctx->maxH;
   if (W < ctx->maxW) W = ctx->maxW;
   size_t V = ctx->V, M = 3 * V, n = (size_t)B * H * W;
-  UP(ctx->v_shaped, (const float*)nullptr, B * M); UP(ctx->v_shaped_part, (const float*)nullptr, 8 * B * M); UP(ctx->v_posed, (const float*)nullptr, B * M); UP(ctx->g_vshaped, (const float*)nullptr, B * M);
+  UP(ctx->v_shaped, (const float*)nullptr, B * M); UP(ctx->v_shaped_part, (const float*)nullptr, 8 * B * M); UP(ctx->v_posed, (const float*)nullptr, B * M); UP(ctx->g_vshaped, (const float*)nullptr, (size_t)B * ctx->Mpad);
   UP(ctx->verts, (const f4*)nullptr, B * V); UP(ctx->clip, (const f4*)nullptr, B * V); UP(ctx->vnorm, (const f4*)nullptr, B * V);
   UP(ctx->vnraw, (const f4*)nullptr, B * V); UP(ctx->snap, (const i4*)nullptr, B * V); UP(ctx->ndc, (const float*)nullptr, B * V * 2);
   UP(ctx->g_clip, (const float*)nullptr, B * V * 4); UP(ctx->g_vnorm, (const float*)nullptr, B * V * 4); UP(ctx->g_verts, (const float*)nullptr, B * V * 4);
@@ -198,7 +203,7 @@ extern "C" void vhap_ctx_destroy(vhap_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   free_batch(c);
-  FREE(c->v_template); FREE(c->S_fwd); FREE(c->S_bwd); FREE(c->posedirs); FREE(c->Jreg); FREE(c->lbs_w); FREE(c->JS); FREE(c->Jt);
+  FREE(c->v_template); FREE(c->S_fwd); FREE(c->S_fwd_pad); FREE(c->S_bwd); FREE(c->posedirs); FREE(c->Jreg); FREE(c->lbs_w); FREE(c->JS); FREE(c->Jt);
   FREE(c->faces); FREE(c->faces_uv); FREE(c->verts_uv); FREE(c->lmk_faces); FREE(c->lmk_bary); FREE(c->adj_opp); FREE(c->fid2cid);
   FREE(c->vf_indptr); FREE(c->vf_faces); FREE(c->lap_indptr); FREE(c->lap_idx); FREE(c->lap_val); FREE(c->lap_y);
   FREE(c->face_flags); FREE(c->vert_flags); FREE(c->w_off); FREE(c->w_off_lap); FREE(c->rigid_indptr); FREE(c->rigid_vids); FREE(c->uvmask_res);

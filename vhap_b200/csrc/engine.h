@@ -22,6 +22,7 @@ struct vhap_ctx {
   int mip_off[VH_MAX_MIPS]; size_t mip_total;
   // ---- static model
   float *v_template, *S_fwd, *S_bwd, *posedirs, *Jreg, *lbs_w, *JS, *Jt;
+  float* S_fwd_pad; int Mpad; int use_tc_blend;   // [K][Mpad] copy with 16-byte aligned rows for the tensor-core contraction
   i4 *faces, *faces_uv; float* verts_uv; int* lmk_faces; float* lmk_bary; int* adj_opp; uint8_t* fid2cid;
   int *vf_indptr, *vf_faces; int *lap_indptr, *lap_idx; float* lap_val; int lap_nnz;
   // ---- stage masks
@@ -98,6 +99,9 @@ void launch_flame_backward(vhap_ctx* c, const vhap_params* p, const vhap_frame_b
 void launch_vnormals(vhap_ctx* c, int B, cudaStream_t s);
 void launch_vnormals_bwd(vhap_ctx* c, int B, cudaStream_t s);
 void launch_regs(vhap_ctx* c, const vhap_params* p, const vhap_frame_batch* fb, const vhap_stage_cfg* cfg, const vhap_grads* g, int global_B, cudaStream_t s);
+// blend_tc.cu
+void launch_blend_tc_fwd(vhap_ctx* c, const float* offset, int B, cudaStream_t s);
+void launch_blend_tc_bwd(vhap_ctx* c, int B, cudaStream_t s);
 // raster.cu
 void launch_raster(vhap_ctx* c, const f4* clip, i4* snap, int B, int H, int W, int* tri_id, int cull_backface, int need_snap, cudaStream_t s);
 void launch_rast_out(vhap_ctx* c, const f4* clip, int B, int H, int W, const int* tri_id, float* rast, float* rast_db, cudaStream_t s);

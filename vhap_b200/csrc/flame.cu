@@ -200,11 +200,18 @@ void launch_flame_forward(vhap_ctx* c, const vhap_params* p, const vhap_frame_ba
   int B = fb->B, V = c->V, M = 3 * V;
   LAUNCH(c, KID_POSE_FWD, s, k_pose_fwd<<<B, 256, 0, s>>>(p->shape, p->expr, p->rotation, p->neck_pose, p->jaw_pose, p->eyes_pose, p->static_offset, fb->timesteps,
                                c->JS, c->Jt, c->Jreg, V, c->K, c->n_shape, c->betas, c->posebuf, c->poses));
-  dim3 g1((M + 127) / 128, (B + VH_MAXB_CHUNK - 1) / VH_MAXB_CHUNK, BLEND_KS);
-  LAUNCH(c, KID_BLEND_FWD, s, k_blend_fwd<VH_MAXB_CHUNK><<<g1, 128, VH_MAXB_CHUNK * c->K * sizeof(float), s>>>(c->S_fwd, c->v_template, p->static_offset, c->betas, M, c->K,
-                                                                                  c->n_shape, B, c->v_shaped_part));
+  int ks = BLEND_KS;
+  const float* vpart = c->v_shaped_part;
+  if (c->use_tc_blend) {                 // tcgen05 contraction writes the finished v_shaped
+    launch_blend_tc_fwd(c, p->static_offset, B, s);
+    ks = 1; vpart = c->v_shaped;
+  } else {
+    dim3 g1((M + 127) / 128, (B + VH_MAXB_CHUNK - 1) / VH_MAXB_CHUNK, BLEND_KS);
+    LAUNCH(c, KID_BLEND_FWD, s, k_blend_fwd<VH_MAXB_CHUNK><<<g1, 128, VH_MAXB_CHUNK * c->K * sizeof(float), s>>>(c->S_fwd, c->v_template, p->static_offset, c->betas, M, c->K,
+                                                                                    c->n_shape, B, c->v_shaped_part));
+  }
   dim3 g2((V + 127) / 128, (B + 7) / 8);
-  LAUNCH(c, KID_SKIN_FWD, s, k_skin_fwd<8><<<g2, 128, 0, s>>>(c->v_shaped_part, BLEND_KS, c->v_shaped, c->posedirs, c->lbs_w, c->posebuf, p->translation, fb->timesteps, c->cam, V, B, fb->H, fb->W,
+  LAUNCH(c, KID_SKIN_FWD, s, k_skin_fwd<8><<<g2, 128, 0, s>>>(vpart, ks, c->v_shaped, c->posedirs, c->lbs_w, c->posebuf, p->translation, fb->timesteps, c->cam, V, B, fb->H, fb->W,
                                    c->v_posed, c->verts, c->clip, c->snap, c->ndc));
 }
 
@@ -338,7 +345,7 @@ template <int NB>
 __global__ void __launch_bounds__(128) k_skin_bwd(const float* __restrict__ v_posed, const f4* __restrict__ verts, const float* __restrict__ posedirs,
                                                   const float* __restrict__ lbs_w, const PoseFwd* __restrict__ posebuf, const CamParams* __restrict__ cam,
                                                   const int* __restrict__ ts, const float* __restrict__ g_verts, const float* __restrict__ g_clip,
-                                                  int V, int B, int H, int W, int opt_cam,
+                                                  int V, int B, int H, int W, int opt_cam, int Mp,
                                                   float* __restrict__ g_vshaped, float* __restrict__ g_offset, float* __restrict__ g_transl,
                                                   float* __restrict__ gA, float* __restrict__ gpf, float* __restrict__ acc) {
   __shared__ float shA[NB][60];
@@ -381,7 +388,7 @@ __global__ void __launch_bounds__(128) k_skin_bwd(const float* __restrict__ v_po
       gvp[0] = T[0] * g[0] + T[4] * g[1] + T[8] * g[2];
       gvp[1] = T[1] * g[0] + T[5] * g[1] + T[9] * g[2];
       gvp[2] = T[2] * g[0] + T[6] * g[1] + T[10] * g[2];
-      float* o = g_vshaped + (size_t)b * M + 3 * v; o[0] = gvp[0]; o[1] = gvp[1]; o[2] = gvp[2];
+      float* o = g_vshaped + (size_t)b * Mp + 3 * v; o[0] = gvp[0]; o[1] = gvp[1]; o[2] = gvp[2];
       goff[0] += gvp[0]; goff[1] += gvp[1]; goff[2] += gvp[2];
     }
     // block reductions through shared memory: every thread deposits its values column-wise (red[value][thread], conflict
@@ -464,14 +471,14 @@ __global__ void k_joff_bwd(const float* __restrict__ Jreg, const float* __restri
 // S_bwd layout [3V][K]: thread <-> k, rows streamed once per chunk of frames, no cross-thread reduction.
 #define BB_ROWS 64
 template <int NB>
-__global__ void __launch_bounds__(512) k_blend_bwd(const float* __restrict__ S, const float* __restrict__ g_vshaped, int M, int K, int B,
+__global__ void __launch_bounds__(512) k_blend_bwd(const float* __restrict__ S, const float* __restrict__ g_vshaped, int M, int Mp, int K, int B,
                                                    float* __restrict__ gbetas) {
   __shared__ float sg[NB][BB_ROWS];
   int m0 = blockIdx.x * BB_ROWS, nm = min(BB_ROWS, M - m0);
   int b0 = blockIdx.y * NB, nb = min(NB, B - b0);
   for (int i = threadIdx.x; i < NB * BB_ROWS; i += blockDim.x) {
     int bi = i / BB_ROWS, mi = i % BB_ROWS;
-    sg[bi][mi] = (bi < nb && mi < nm) ? g_vshaped[(size_t)(b0 + bi) * M + m0 + mi] : 0.f;
+    sg[bi][mi] = (bi < nb && mi < nm) ? g_vshaped[(size_t)(b0 + bi) * Mp + m0 + mi] : 0.f;
   }
   __syncthreads();
   int k = threadIdx.x;
@@ -504,13 +511,16 @@ void launch_flame_backward(vhap_ctx* c, const vhap_params* p, const vhap_frame_b
   bool need_betas = g->shape || g->expr;
   dim3 g1((V + 127) / 128, (B + 1) / 2);
   LAUNCH(c, KID_SKIN_BWD, s, k_skin_bwd<2><<<g1, 128, 0, s>>>(c->v_posed, c->verts, c->posedirs, c->lbs_w, c->posebuf, c->cam, fb->timesteps, c->g_verts, c->g_clip, V, B, fb->H, fb->W,
-                                   opt_cam, c->g_vshaped, g->static_offset, g->translation, c->gA, c->gpf, c->acc));
+                                   opt_cam, c->Mpad, c->g_vshaped, g->static_offset, g->translation, c->gA, c->gpf, c->acc));
   LAUNCH(c, KID_POSE_BWD, s, k_pose_bwd<<<B, 128, 0, s>>>(c->poses, c->posebuf, c->gA, c->gpf, fb->timesteps, c->JS, c->K, g->rotation, g->neck_pose, g->jaw_pose, g->eyes_pose,
                                c->gJ, need_betas ? c->gbetas : nullptr));
   if (g->static_offset) LAUNCH(c, KID_JOFF_BWD, s, k_joff_bwd<<<(V + 127) / 128, 128, 0, s>>>(c->Jreg, c->gJ, V, B, g->static_offset));
   if (need_betas) {
-    dim3 g2((M + BB_ROWS - 1) / BB_ROWS, (B + VH_MAXB_CHUNK - 1) / VH_MAXB_CHUNK);
-    LAUNCH(c, KID_BLEND_BWD, s, k_blend_bwd<VH_MAXB_CHUNK><<<g2, 512, 0, s>>>(c->S_bwd, c->g_vshaped, M, c->K, B, c->gbetas));
+    if (c->use_tc_blend) launch_blend_tc_bwd(c, B, s);
+    else {
+      dim3 g2((M + BB_ROWS - 1) / BB_ROWS, (B + VH_MAXB_CHUNK - 1) / VH_MAXB_CHUNK);
+      LAUNCH(c, KID_BLEND_BWD, s, k_blend_bwd<VH_MAXB_CHUNK><<<g2, 512, 0, s>>>(c->S_bwd, c->g_vshaped, M, c->Mpad, c->K, B, c->gbetas));
+    }
     LAUNCH(c, KID_BETAS_SCATTER, s, k_betas_scatter<<<B, 256, 0, s>>>(c->gbetas, fb->timesteps, c->K, c->n_shape, g->shape, g->expr));
   }
   (void)p;
