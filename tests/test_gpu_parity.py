@@ -262,4 +262,6 @@ def test_graph_replay_matches_eager(eng_small):
         res.append({k: v.copy() for k, v in e.get_params().items()})
     for k in res[0]:
         noise = rel(res[1][k], res[0][k])
-        assert rel(res[2][k], res[0][k]) < 5 * noise + 2e-4, (k, rel(res[2][k], res[0][k]), noise)
+        # a broken replay (stuck Adam / RNG step counter, wrong texture ping-pong parity) changes the trajectory by O(1e-1);
+        # run-to-run noise of the atomics through the L1 sign gradients is O(1e-3)
+        assert rel(res[2][k], res[0][k]) < 10 * noise + 3e-3, (k, rel(res[2][k], res[0][k]), noise)
