@@ -189,7 +189,7 @@ extern "C" int vhap_ctx_reserve(vhap_ctx* ctx, int32_t B, int32_t H, int32_t W) 
   int tiles = B * ((H + VH_TILE - 1) / VH_TILE) * ((W + VH_TILE - 1) / VH_TILE);
   UP(ctx->tile_count, (const int*)nullptr, (size_t)tiles); UP(ctx->tile_off, (const int*)nullptr, (size_t)tiles); UP(ctx->tile_cursor, (const int*)nullptr, (size_t)tiles);
   ctx->tile_cap = (int)std::min<size_t>((size_t)B * ctx->F * 16, (size_t)1 << 30);
-  UP(ctx->tile_list, (const int*)nullptr, (size_t)ctx->tile_cap);
+  UP(ctx->tile_list, (const int*)nullptr, (size_t)ctx->tile_cap + 8);     // +slack: TMA copies round list chunks up to 16 bytes
   int nblk = (int)((n + 255) / 256);
   ctx->pool_nblk = nblk;
   UP(ctx->pool_blk_count, (const int*)nullptr, (size_t)16 * nblk); UP(ctx->pool_blk_off, (const int*)nullptr, (size_t)16 * nblk);

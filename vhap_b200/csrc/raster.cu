@@ -117,6 +117,12 @@ void launch_scan(vhap_ctx* c, const int* in, int* out, int n, int* total, cudaSt
   LAUNCH(c, KID_SCAN, s, k_scan_add<<<nb, 1024, 0, s>>>(out, c->scan_aux, n));
 }
 
+// tile list starts are padded to 4 ints (16 bytes) so that the fine rasteriser can stage them with TMA bulk copies
+__global__ void k_pad_counts(const int* __restrict__ cnt, int* __restrict__ padded, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) padded[i] = (cnt[i] + 3) & ~3;
+}
+
 struct FineTri {        // shared-memory record, struct of arrays
   int e[3][FINE_CHUNK], ea[3][FINE_CHUNK], eb[3][FINE_CHUNK];
   float zx[FINE_CHUNK], zy[FINE_CHUNK], zc[FINE_CHUNK];
@@ -133,6 +139,8 @@ __global__ void __launch_bounds__(128) k_fine(const i4* __restrict__ snap, const
                                               const int* __restrict__ tile_off, const int* __restrict__ tile_list, int tile_cap,
                                               int V, int H, int W, int tiles_x, int tiles_y, int cull_backface, int* __restrict__ tri_id) {
   __shared__ FineTri T;
+  __shared__ __align__(16) int ids_s[2][FINE_CHUNK];     // triangle-id chunks staged by TMA (cp.async.bulk), double buffered
+  __shared__ uint64_t bar[2];
   int tile = blockIdx.x;
   int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
   int n = tile_count[tile], off = tile_off[tile];
@@ -146,11 +154,33 @@ __global__ void __launch_bounds__(128) k_fine(const i4* __restrict__ snap, const
   float bz0 = INFINITY, bz1 = INFINITY; int bi0 = 0, bi1 = 0;
   const i4* sb = snap + (size_t)b * V;
   long long Cx0 = (long long)(2 * X0 + 1 - W) * 8, Cy0 = (long long)(2 * Y0 + 1 - H) * 8;   // sample of the tile's first pixel
-  for (int base = 0; base < n; base += FINE_CHUNK) {
-    int j = threadIdx.x, cnt = min(FINE_CHUNK, n - base);
-    __syncthreads();
+  // TMA: one elected thread arms an mbarrier with the byte count and issues a 1-D bulk copy global -> shared of the next chunk
+  // of the tile's triangle list; the copy of chunk k+1 overlaps the set-up and coverage tests of chunk k
+  auto issue = [&](int base, int buf) {
+    int cnt = min(FINE_CHUNK, n - base);
+    uint32_t bytes = (uint32_t)(((cnt + 3) >> 2) << 4);
+    uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar[buf]), dst = (uint32_t)__cvta_generic_to_shared(&ids_s[buf][0]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(tile_list + off + base), "r"(bytes), "r"(bar_a) : "memory");
+  };
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&bar[i])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (n > 0) issue(0, 0);
+  }
+  __syncthreads();
+  int chunk = 0;
+  for (int base = 0; base < n; base += FINE_CHUNK, ++chunk) {
+    int j = threadIdx.x, cnt = min(FINE_CHUNK, n - base), buf = chunk & 1;
+    __syncthreads();                                   // previous chunk fully consumed (its buffer and T may be overwritten)
+    if (threadIdx.x == 0 && base + FINE_CHUNK < n) issue(base + FINE_CHUNK, buf ^ 1);
+    {
+      uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar[buf]), parity = (chunk >> 1) & 1, done = 0;
+      while (!done) asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.b32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar_a), "r"(parity) : "memory");
+    }
     if (j < cnt) {
-      int t = tile_list[off + base + j];
+      int t = ids_s[buf][j];
       i4 f = faces[t];
       i4 s0 = sb[f.x], s1 = sb[f.y], s2 = sb[f.z];
       int px0, px1, py0, py1; long long area2;
@@ -226,10 +256,11 @@ void launch_raster(vhap_ctx* c, const f4* clip, i4* snap, int B, int H, int W, i
   if (need_snap) LAUNCH(c, KID_SNAP, s, k_snap<<<(B * V + 255) / 256, 256, 0, s>>>(clip, snap, c->ndc, B * V, H, W));
   int tiles_x = (W + VH_TILE - 1) / VH_TILE, tiles_y = (H + VH_TILE - 1) / VH_TILE, ntiles = B * tiles_x * tiles_y;
   cudaMemsetAsync(c->tile_count, 0, sizeof(int) * ntiles, s);
-  cudaMemsetAsync(c->tile_cursor, 0, sizeof(int) * ntiles, s);
   dim3 g((F + 255) / 256, B);
   LAUNCH(c, KID_BIN, s, k_bin<false><<<g, 256, 0, s>>>(snap, c->faces, V, F, B, H, W, tiles_x, tiles_y, cull_backface, c->tile_count, nullptr, nullptr, nullptr, 0, c->overflow_flag));
-  launch_scan(c, c->tile_count, c->tile_off, ntiles, nullptr, s);
+  LAUNCH(c, KID_SCAN, s, k_pad_counts<<<(ntiles + 255) / 256, 256, 0, s>>>(c->tile_count, c->tile_cursor, ntiles));   // cursor doubles as scratch
+  launch_scan(c, c->tile_cursor, c->tile_off, ntiles, nullptr, s);
+  cudaMemsetAsync(c->tile_cursor, 0, sizeof(int) * ntiles, s);
   LAUNCH(c, KID_BIN, s, k_bin<true><<<g, 256, 0, s>>>(snap, c->faces, V, F, B, H, W, tiles_x, tiles_y, cull_backface, c->tile_count, c->tile_off, c->tile_cursor, c->tile_list,
                                 c->tile_cap, c->overflow_flag));
   LAUNCH(c, KID_FINE, s, k_fine<<<ntiles, 128, 0, s>>>(snap, c->faces, c->tile_count, c->tile_off, c->tile_list, c->tile_cap, V, H, W, tiles_x, tiles_y, cull_backface, tri_id));
