@@ -10,7 +10,7 @@ CSRC = HERE / "csrc"
 SO = HERE / "libvhap_b200.so"
 SOURCES = ["flame.cu", "raster.cu", "render.cu", "texture.cu", "blend_tc.cu", "api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "--fmad=true"]
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "--fmad=true"] + os.environ.get("VH_EXTRA_FLAGS", "").split()
 
 
 def _newer(target: Path, deps) -> bool:

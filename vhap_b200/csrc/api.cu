@@ -150,7 +150,7 @@ extern "C" int vhap_ctx_create(vhap_ctx** out, const vhap_mesh_desc* m, int32_t 
   UP(ctx->pair_count, (const int*)nullptr, (size_t)1);
   UP(ctx->dev_step, (const int*)nullptr, (size_t)2);
   for (int i = 0; i < 2; ++i) CK(cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking));
-  for (int i = 0; i < 4; ++i) CK(cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming));
+  for (int i = 0; i < 8; ++i) CK(cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming));
   UP(ctx->tex_l0_flag, (const int*)nullptr, (size_t)1);
   { int one = 1; cudaMemcpy(ctx->tex_l0_flag, &one, sizeof(int), cudaMemcpyHostToDevice); }
   return 0;
@@ -368,8 +368,13 @@ extern "C" int vhap_energy_forward(vhap_ctx* ctx, const vhap_params* p, const vh
   launch_cam_setup(ctx, p, fb, s);
   launch_flame_forward(ctx, p, fb, s);
   if (cfg->photometric && cfg->w_photo >= 0.f) {
-    launch_vnormals(ctx, fb->B, s);
+    // fork: vertex normals (needed only by the shading pass) run on aux stream 0 while the rasteriser runs on the main stream
+    cudaEventRecord(ctx->ev[4], s);
+    cudaStreamWaitEvent(ctx->aux[0], ctx->ev[4], 0);
+    launch_vnormals(ctx, fb->B, ctx->aux[0]);
+    cudaEventRecord(ctx->ev[5], ctx->aux[0]);
     launch_raster(ctx, ctx->clip, ctx->snap, fb->B, fb->H, fb->W, ctx->tri_id, 0, 0, s);
+    cudaStreamWaitEvent(s, ctx->ev[5], 0);
     PassArgs P;
     fill_render_args(ctx, P, fb, cfg, p->lights);
     launch_render_forward(ctx, P, s);

@@ -58,7 +58,7 @@ struct vhap_ctx {
   float* aa_code; int *pair_list, *pair_count;    // [2N], [2N], [1]
   f4* grgb;                                       // [N] d L / d rgb of the compacted foreground pixels
   int* tex_l0_flag;                               // [1]
-  cudaStream_t aux[2]; cudaEvent_t ev[4]; int tex_fork_pending;   // fork/join of independent kernel chains
+  cudaStream_t aux[2]; cudaEvent_t ev[8]; int tex_fork_pending;   // fork/join of independent kernel chains
   int* dev_step; int use_dev_step;                // device counters [0] Adam step (1-based), [1] global step; used when use_dev_step
 };
 

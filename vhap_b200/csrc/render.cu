@@ -45,7 +45,7 @@ __device__ __forceinline__ float unpack_max_val(unsigned long long p) {
 }
 
 // ---------------------------------------------------------------------------------------------- cluster pools
-__global__ void __launch_bounds__(PB) k_pool_count(const int* __restrict__ tri_id, const uint8_t* __restrict__ fid2cid, size_t n, int* __restrict__ blk_count) {
+__global__ void __launch_bounds__(PB) k_pool_count(const int* __restrict__ tri_id, const uint8_t* __restrict__ fid2cid, size_t n, int ncl, int* __restrict__ blk_count) {
   __shared__ int cnt[16];
   if (threadIdx.x < 16) cnt[threadIdx.x] = 0;
   __syncthreads();
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(PB) k_pool_count(const int* __restrict__ tri_i
   unsigned m0 = __ballot_sync(0xffffffffu, cid == 0);
   if ((threadIdx.x & 31) == 0 && m0) atomicAdd(&cnt[0], __popc(m0));
   if (any)                                                       // warps that are all background skip the per-cluster ballots
-    for (int c = 1; c < 16; ++c) {
+    for (int c = 1; c < ncl; ++c) {
       unsigned m = __ballot_sync(0xffffffffu, cid == c);
       if ((threadIdx.x & 31) == 0 && m) atomicAdd(&cnt[c], __popc(m));
     }
@@ -73,7 +73,7 @@ __global__ void k_pool_bases(const int* __restrict__ off, int nblk, const int* _
 }
 
 // also emits the list of adjacent pixel pairs with different ids (pair = pixel0 * 2 + direction) for the antialias analysis
-__global__ void __launch_bounds__(PB) k_pool_scatter(const int* __restrict__ tri_id, const uint8_t* __restrict__ fid2cid, size_t n, int H, int W,
+__global__ void __launch_bounds__(PB) k_pool_scatter(const int* __restrict__ tri_id, const uint8_t* __restrict__ fid2cid, size_t n, int H, int W, int ncl,
                                                      const int* __restrict__ blk_off, int* __restrict__ pool_list,
                                                      int* __restrict__ pair_list, int* __restrict__ pair_count) {
   __shared__ int wcnt[16][PB / 32];
@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(PB) k_pool_scatter(const int* __restrict__ tri
   int rank = 0;
   unsigned any = __ballot_sync(0xffffffffu, cid > 0);
   for (int c = 0; c < 16; ++c) {
+    if (c >= ncl) { if (lane == 0) wcnt[c][w] = 0; continue; }
     unsigned m = (c == 0 || any) ? __ballot_sync(0xffffffffu, cid == c) : 0u;
     if (cid == c) rank = __popc(m & ((1u << lane) - 1));
     if (lane == 0) wcnt[c][w] = __popc(m);
@@ -168,7 +169,10 @@ __global__ void __launch_bounds__(PB) k_passC1(PassArgs P, const float* __restri
   }
 }
 
-__global__ void __launch_bounds__(PB, 2) k_passC2(PassArgs P, const f4* __restrict__ grgb, float* __restrict__ partials) {
+#ifndef VH_C2_MINBLOCKS
+#define VH_C2_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(PB, VH_C2_MINBLOCKS) k_passC2(PassArgs P, const f4* __restrict__ grgb, float* __restrict__ partials) {
   __shared__ float sh[8 * 27];
   const RenderArgs& A = P.R;
   int n_fg = A.B * A.H * A.W - P.pool_count[0];
@@ -314,11 +318,11 @@ void launch_render_forward(vhap_ctx* c, PassArgs& P, cudaStream_t s) {
   if (c->want_planes) {
     cudaMemsetAsync(c->plane_albedo, 0, n * 16, s); cudaMemsetAsync(c->plane_normal, 0, n * 16, s); cudaMemsetAsync(c->plane_diffuse, 0, n * 16, s);
   }
-  LAUNCH(c, KID_POOL_COUNT, s, k_pool_count<<<nblk, PB, 0, s>>>(A.tri_id, A.fid2cid, n, c->pool_blk_count));
+  LAUNCH(c, KID_POOL_COUNT, s, k_pool_count<<<nblk, PB, 0, s>>>(A.tri_id, A.fid2cid, n, c->n_clusters, c->pool_blk_count));
   launch_scan(c, c->pool_blk_count, c->pool_blk_off, 16 * nblk, c->scan_total, s);
   LAUNCH(c, KID_POOL_SCAN, s, k_pool_bases<<<1, 32, 0, s>>>(c->pool_blk_off, nblk, c->scan_total, c->pool_base, c->pool_count));
   cudaMemsetAsync(c->pair_count, 0, sizeof(int), s);
-  LAUNCH(c, KID_POOL_SCATTER, s, k_pool_scatter<<<nblk, PB, 0, s>>>(A.tri_id, A.fid2cid, n, A.H, A.W, c->pool_blk_off, c->pool_list, c->pair_list, c->pair_count));
+  LAUNCH(c, KID_POOL_SCATTER, s, k_pool_scatter<<<nblk, PB, 0, s>>>(A.tri_id, A.fid2cid, n, A.H, A.W, c->n_clusters, c->pool_blk_off, c->pool_list, c->pair_list, c->pair_count));
   int grid = nblk < NPERSIST ? nblk : NPERSIST;
   LAUNCH(c, KID_PASSA, s, k_passA<<<grid, PB, 0, s>>>(P, c->partials, c->maxslot));
   LAUNCH(c, KID_AA_PAIRS, s, k_aa_pairs<<<grid, PB, 0, s>>>(P, c->pair_list, c->pair_count));
