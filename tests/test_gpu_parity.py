@@ -243,7 +243,10 @@ def test_full_step_decreases_energy(eng_small):
 
 def test_graph_replay_matches_eager(eng_small):
     """whole-step CUDA-graph replay (device-resident step counters) == eager stepping, up to the run-to-run noise of the
-    floating-point atomics (measured by repeating the eager run)"""
+    floating-point atomics (measured by repeating the eager run).  Two steps only: both texture ping-pong parities and two
+    Adam bias corrections are exercised, while the trajectory has not yet reached the first discrete bifurcation (from the
+    third step on, last-bit differences of the atomics flip a coverage / arg-max decision and eager runs themselves split
+    into two deterministic branches, tools/debug_graph.py)."""
     e, sc = eng_small
     batch = e.stage_sample(sc["rgb16"].to(torch.float32), sc["lmk2d"], sc["ts"])
     res = []
@@ -254,7 +257,7 @@ def test_graph_replay_matches_eager(eng_small):
         e.global_step = 5
         if mode == "graph":
             e.graph_begin([batch])
-        for i in range(4):
+        for i in range(2):
             e.graph_step(0) if mode == "graph" else e.step(batch)
         if mode == "graph":
             e.graph_end()
@@ -262,6 +265,5 @@ def test_graph_replay_matches_eager(eng_small):
         res.append({k: v.copy() for k, v in e.get_params().items()})
     for k in res[0]:
         noise = rel(res[1][k], res[0][k])
-        # a broken replay (stuck Adam / RNG step counter, wrong texture ping-pong parity) changes the trajectory by O(1e-1);
-        # run-to-run noise of the atomics through the L1 sign gradients is O(1e-3)
-        assert rel(res[2][k], res[0][k]) < 10 * noise + 3e-3, (k, rel(res[2][k], res[0][k]), noise)
+        # a broken replay (stuck Adam / RNG step counter, wrong texture ping-pong parity) changes the trajectory by O(1e-1)
+        assert rel(res[2][k], res[0][k]) < 10 * noise + 1e-3, (k, rel(res[2][k], res[0][k]), noise)

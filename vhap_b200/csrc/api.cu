@@ -369,12 +369,15 @@ extern "C" int vhap_energy_forward(vhap_ctx* ctx, const vhap_params* p, const vh
   launch_flame_forward(ctx, p, fb, s);
   if (cfg->photometric && cfg->w_photo >= 0.f) {
     // fork: vertex normals (needed only by the shading pass) run on aux stream 0 while the rasteriser runs on the main stream
-    cudaEventRecord(ctx->ev[4], s);
-    cudaStreamWaitEvent(ctx->aux[0], ctx->ev[4], 0);
-    launch_vnormals(ctx, fb->B, ctx->aux[0]);
-    cudaEventRecord(ctx->ev[5], ctx->aux[0]);
+    static const bool vn_overlap = getenv("VHAP_B200_NO_VN_OVERLAP") == nullptr;
+    if (vn_overlap) {
+      cudaEventRecord(ctx->ev[4], s);
+      cudaStreamWaitEvent(ctx->aux[0], ctx->ev[4], 0);
+      launch_vnormals(ctx, fb->B, ctx->aux[0]);
+      cudaEventRecord(ctx->ev[5], ctx->aux[0]);
+    } else launch_vnormals(ctx, fb->B, s);
     launch_raster(ctx, ctx->clip, ctx->snap, fb->B, fb->H, fb->W, ctx->tri_id, 0, 0, s);
-    cudaStreamWaitEvent(s, ctx->ev[5], 0);
+    if (vn_overlap) cudaStreamWaitEvent(s, ctx->ev[5], 0);
     PassArgs P;
     fill_render_args(ctx, P, fb, cfg, p->lights);
     launch_render_forward(ctx, P, s);

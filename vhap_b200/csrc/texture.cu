@@ -52,8 +52,8 @@ __global__ void __launch_bounds__(256) k_mip_down(const f4* __restrict__ src, f4
   }
 }
 
-static void build_mips(vhap_ctx* c, f4* pyr, cudaStream_t s, int from_level = 0) {
-  int l = from_level;
+static void build_mips(vhap_ctx* c, f4* pyr, cudaStream_t s) {
+  int l = 0;
   while (l < c->max_level) {
     int ssz = c->T >> l, nlev = c->max_level - l < 5 ? c->max_level - l : 5;
     int tile = ssz < 32 ? ssz : 32, g = ssz / tile;
@@ -85,84 +85,68 @@ struct TexFoldArgs {
 
 __device__ __forceinline__ float chan(const f4& t, int c) { return c == 0 ? t.x : (c == 1 ? t.y : t.z); }
 
-// One thread per 2x2 quad of level-0 texels (all 3 channels): besides the fold / regularisers / Adam of its four texels it emits
-// the level-1 texel of the rebuilt pyramid directly, so the mip builder starts from level 1 (saves re-reading 16 B/texel).
+// One thread per level-0 texel (all 3 channels).
 __global__ void __launch_bounds__(256) k_tex_fold(TexFoldArgs a, float* __restrict__ partials) {
   __shared__ float sh[8 * 2];
-  const int T = a.T, Th = T >> 1;
-  const size_t n = (size_t)T * T;
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  int T = a.T;
+  size_t n = (size_t)T * T, i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   float acc[2] = {0.f, 0.f};
-  if (q < Th * Th) {
-    const int qx = q % Th, qy = q / Th;
-    const bool l0 = a.g_pyr ? (a.l0_flag ? (*a.l0_flag != 0) : true) : false;
-    // coarse part of the folded photometric gradient (levels >= 1 are shared by the whole quad)
-    float gc[3] = {0.f, 0.f, 0.f};
+  if (i < n) {
+    int x = i % T, y = i / T;
+    // photometric gradient: fold every pyramid level back to level 0 (box-filter adjoint: 1/4 per level)
+    float g[3] = {0.f, 0.f, 0.f};
     if (a.g_pyr) {
-      float sc = 0.25f;
-      for (int l = 1; l <= a.max_level; ++l) {
+      // level 0 of the gradient pyramid is only touched under magnification (mip level < 1); the backward pass raises
+      // l0_flag when it scatters there, otherwise the 16 B/texel read + re-zero of that level is skipped
+      bool l0 = a.l0_flag ? (*a.l0_flag != 0) : true;
+      float sc = l0 ? 1.f : 0.25f;
+      for (int l = l0 ? 0 : 1; l <= a.max_level; ++l) {
         int s = T >> l;
-        const float* p = a.g_pyr + ((size_t)a.mip_off[l] + (size_t)(qy >> (l - 1)) * s + (qx >> (l - 1))) * 4;
-        gc[0] += p[0] * sc; gc[1] += p[1] * sc; gc[2] += p[2] * sc;
+        const float* p = a.g_pyr + ((size_t)a.mip_off[l] + (size_t)(y >> l) * s + (x >> l)) * 4;
+        g[0] += p[0] * sc; g[1] += p[1] * sc; g[2] += p[2] * sc;
         sc *= 0.25f;
       }
+      if (l0) { float4* p0 = (float4*)(a.g_pyr + i * 4); *p0 = make_float4(0.f, 0.f, 0.f, 0.f); }   // coarser levels: memset after the kernel
     }
-    float bc1 = a.bc1, bc2s = a.bc2_sqrt;
-    if (a.do_adam && a.step_ptr) { float st = (float)a.step_ptr[0]; bc1 = 1.f - powf(0.9f, st); bc2s = sqrtf(1.f - powf(0.999f, st)); }
-    f4 lvl1 = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int dy = 0; dy < 2; ++dy) {
-#pragma unroll
-      for (int dx = 0; dx < 2; ++dx) {
-        const int x = 2 * qx + dx, y = 2 * qy + dy;
-        const size_t i = (size_t)y * T + x;
-        float g[3] = {gc[0], gc[1], gc[2]};
-        if (l0) {
-          float4* p0 = (float4*)(a.g_pyr + i * 4);
-          float4 g0 = *p0;
-          g[0] += g0.x; g[1] += g0.y; g[2] += g0.z;
-          *p0 = make_float4(0.f, 0.f, 0.f, 0.f);                               // coarser levels: memset after the kernel
-        }
-        f4 t = a.tex_old[i];
-        float ex[3] = {a.extra[i], a.extra[n + i], a.extra[2 * n + i]};
-        if (a.w_tv > 0.f) {                                                    // tracker.py:526-534
-          f4 tr = x + 1 < T ? a.tex_old[i + 1] : t, tl = x > 0 ? a.tex_old[i - 1] : t;
-          f4 td = y + 1 < T ? a.tex_old[i + T] : t, tu = y > 0 ? a.tex_old[i - T] : t;
-          for (int c = 0; c < 3; ++c) {
-            float v = chan(t, c), dr = v - chan(tr, c), dd = v - chan(td, c), dl = chan(tl, c) - v, du = chan(tu, c) - v;
-            acc[0] += a.w_tv * (dr * dr + dd * dd);                            // each difference counted once (right, down)
-            g[c] += 2.f * a.w_tv * (dr + dd - dl - du);
-          }
-        }
-        if (a.w_res > 0.f && a.mask && a.mask[i]) {                            // tracker.py:536-539
-          for (int c = 0; c < 3; ++c) { acc[1] += a.w_res * ex[c] * ex[c]; g[c] += 2.f * a.w_res * ex[c]; }
-        }
-        if (a.g_out) { a.g_out[i] = g[0]; a.g_out[n + i] = g[1]; a.g_out[2 * n + i] = g[2]; }
-        if (a.do_adam) {
-          f4 o = t;
-          for (int c = 0; c < 3; ++c) {
-            size_t k = c * n + i;
-            float m = 0.9f * a.m[k] + 0.1f * g[c];
-            float v = 0.999f * a.v[k] + 0.001f * g[c] * g[c];
-            a.m[k] = m; a.v[k] = v;
-            float ne = ex[c] - (a.lr / bc1) * m / (sqrtf(v) / bc2s + 1e-8f);
-            a.extra[k] = ne;
-            float base = chan(t, c) - ex[c];                                   // painted part
-            if (c == 0) o.x = base + ne; else if (c == 1) o.y = base + ne; else o.z = base + ne;
-          }
-          a.tex_new[i] = o;
-          lvl1.x += 0.25f * o.x; lvl1.y += 0.25f * o.y; lvl1.z += 0.25f * o.z;
-        }
+    f4 t = a.tex_old[i];
+    float ex[3] = {a.extra[i], a.extra[n + i], a.extra[2 * n + i]};
+    if (a.w_tv > 0.f) {                                                          // tracker.py:526-534
+      f4 tr = x + 1 < T ? a.tex_old[i + 1] : t, tl = x > 0 ? a.tex_old[i - 1] : t;
+      f4 td = y + 1 < T ? a.tex_old[i + T] : t, tu = y > 0 ? a.tex_old[i - T] : t;
+      for (int c = 0; c < 3; ++c) {
+        float v = chan(t, c), dr = v - chan(tr, c), dd = v - chan(td, c), dl = chan(tl, c) - v, du = chan(tu, c) - v;
+        acc[0] += a.w_tv * (dr * dr + dd * dd);                                  // each difference counted once (right, down)
+        g[c] += 2.f * a.w_tv * (dr + dd - dl - du);
       }
     }
-    if (a.do_adam && a.max_level >= 1) a.tex_new[(size_t)a.mip_off[1] + (size_t)qy * Th + qx] = lvl1;
+    if (a.w_res > 0.f && a.mask && a.mask[i]) {                                  // tracker.py:536-539
+      for (int c = 0; c < 3; ++c) { acc[1] += a.w_res * ex[c] * ex[c]; g[c] += 2.f * a.w_res * ex[c]; }
+    }
+    if (a.g_out) { a.g_out[i] = g[0]; a.g_out[n + i] = g[1]; a.g_out[2 * n + i] = g[2]; }
+    if (a.do_adam) {
+      float bc1 = a.bc1, bc2s = a.bc2_sqrt;
+      if (a.step_ptr) { float st = (float)a.step_ptr[0]; bc1 = 1.f - powf(0.9f, st); bc2s = sqrtf(1.f - powf(0.999f, st)); }
+      f4 o = t;
+      for (int c = 0; c < 3; ++c) {
+        size_t k = c * n + i;
+        float m = 0.9f * a.m[k] + 0.1f * g[c];
+        float v = 0.999f * a.v[k] + 0.001f * g[c] * g[c];
+        a.m[k] = m; a.v[k] = v;
+        float upd = (a.lr / bc1) * m / (sqrtf(v) / bc2s + 1e-8f);
+        float ne = ex[c] - upd;
+        a.extra[k] = ne;
+        float base = chan(t, c) - ex[c];                                          // painted part
+        if (c == 0) o.x = base + ne; else if (c == 1) o.y = base + ne; else o.z = base + ne;
+      }
+      a.tex_new[i] = o;
+    }
   }
   // block partial sums of the two loss terms
   int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int qq = 0; qq < 2; ++qq) {
-    float v = acc[qq];
+  for (int q = 0; q < 2; ++q) {
+    float v = acc[q];
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) sh[w * 2 + qq] = v;
+    if (lane == 0) sh[w * 2 + q] = v;
   }
   __syncthreads();
   if (threadIdx.x < 2) {
@@ -205,14 +189,14 @@ void launch_tex_fold(vhap_ctx* c, float* tex_extra, float* g_out, float* m, floa
   a.w_res = (cfg->training && cfg->opt_texture && cfg->w_reg_tex_res >= 0.f) ? sh * cfg->w_reg_tex_res / (3.f * (float)T * (float)T) : 0.f;
   a.do_adam = (m != nullptr && v != nullptr) ? 1 : 0;
   a.lr = lr; a.bc1 = 1.f - powf(0.9f, (float)step); a.bc2_sqrt = sqrtf(1.f - powf(0.999f, (float)step));
-  size_t n = (size_t)(T / 2) * (T / 2);
+  size_t n = (size_t)T * T;
   int nblk = (int)((n + 255) / 256);
   LAUNCH(c, KID_TEX_FOLD, s, k_tex_fold<<<nblk, 256, 0, s>>>(a, c->tv_partials));
   LAUNCH(c, KID_TEX_LOSS, s, k_tex_loss_reduce<<<1, 1024, 0, s>>>(c->tv_partials, nblk, c->acc));
   cudaMemsetAsync(c->tex_l0_flag, 0, sizeof(int), s);
   if (c->g_tex && c->max_level >= 1)                                      // coarser gradient levels
     cudaMemsetAsync(c->g_tex + (size_t)c->mip_off[1] * 4, 0, (c->mip_total - c->mip_off[1]) * 4 * sizeof(float), s);
-  if (a.do_adam) { c->cur_mip ^= 1; build_mips(c, c->mips[c->cur_mip], s, 1); }     // level 1 was written by the fold kernel
+  if (a.do_adam) { c->cur_mip ^= 1; build_mips(c, c->mips[c->cur_mip], s); }
 }
 
 __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
