@@ -193,10 +193,14 @@ int vhap_tex_reg_fold_adam(vhap_ctx* ctx, float* tex_extra, float* g_out, float*
 
 /* ---- per-kernel accounting: every kernel launch is counted; with profiling enabled CUDA events bracket each launch on the
  *      launching stream (used by bench.py to measure the dominant kernel live inside its timed region) --------------- */
-int vhap_profile_enable(vhap_ctx* ctx, int32_t on);            /* also resets counters */
+int vhap_profile_enable(vhap_ctx* ctx, int32_t on);            /* 1: on (resets counters); 2: on, and usable inside stream capture (events become
+                                                                  nodes of the graph); 0: off + reset; -1: off, keep the recorded slots */
+int vhap_set_overlap(vhap_ctx* ctx, int32_t on);               /* 0: no aux-stream fork/join (clean per-kernel timing); default 1 */
 int vhap_profile_kernel_count(void);
 const char* vhap_profile_kernel_name(int32_t kid);
 int vhap_profile_read(vhap_ctx* ctx, float* avg_ms_host, uint64_t* launches_host);   /* arrays of vhap_profile_kernel_count(); synchronises */
+/* start/end of every recorded launch in ms after the first recorded event (timeline of a graph replay in mode 2); returns n */
+int vhap_profile_timeline(vhap_ctx* ctx, int32_t* kid_out, float* t0_ms, float* t1_ms, int32_t max_n);
 
 /* ---- CUDA-graph support: with device-resident step counters no kernel argument varies from step to step, so a whole step
  *      (forward, backward, regularisers, Adam) can be captured once per (batch, texture ping-pong parity) and replayed ------ */

@@ -3,10 +3,11 @@ pointers, sizes and the CUDA stream handle.  Fails loudly if the library is miss
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
-_SO = _HERE / "libvhap_b200.so"
+_SO = Path(os.environ.get("VHAP_B200_SO", _HERE / "libvhap_b200.so"))     # override: experiment variants built by build_ext.py (dev only)
 
 c_float_p = C.c_void_p      # device pointers are passed as integers
 c_int_p = C.c_void_p
@@ -88,6 +89,8 @@ def lib() -> C.CDLL:
         "vhap_profile_kernel_count": (i32, []),
         "vhap_profile_kernel_name": (C.c_char_p, [i32]),
         "vhap_profile_read": (i32, [vp, vp, vp]),
+        "vhap_profile_timeline": (i32, [vp, vp, vp, vp, i32]),
+        "vhap_set_overlap": (i32, [vp, i32]),
         "vhap_get_geometry": (i32, [vp, i32, vp, vp]),
         "vhap_overflow_flag": (i32, [vp, P(i32)]),
         "vhap_set_injected_random": (i32, [vp, vp, vp]),
@@ -113,6 +116,6 @@ def lib() -> C.CDLL:
 EXPORTED = ["vhap_abi_version", "vhap_last_error", "vhap_ctx_create", "vhap_ctx_reserve", "vhap_ctx_destroy", "vhap_set_stage_masks",
             "vhap_flame_forward", "vhap_flame_backward", "vhap_project", "vhap_rasterize", "vhap_energy_forward_backward",
             "vhap_energy_forward", "vhap_energy_backward", "vhap_get_plane", "vhap_get_geometry", "vhap_profile_enable", "vhap_profile_kernel_count", "vhap_profile_kernel_name",
-            "vhap_profile_read", "vhap_set_want_planes", "vhap_overflow_flag",
+            "vhap_profile_read", "vhap_profile_timeline", "vhap_set_overlap", "vhap_set_want_planes", "vhap_overflow_flag",
             "vhap_set_injected_random", "vhap_project_backward", "vhap_vertex_normals",
             "vhap_vertex_normals_backward", "vhap_render_photometric", "vhap_render_rgba_backward", "vhap_tex_grad_ptr", "vhap_set_tex_painted", "vhap_tex_rebuild", "vhap_tex_reg_fold_adam", "vhap_adam", "vhap_adam_multi", "vhap_step_counters", "vhap_step_advance", "vhap_get_cur_mip", "vhap_set_cur_mip"]

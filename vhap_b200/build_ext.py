@@ -7,7 +7,7 @@ from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
-SO = HERE / "libvhap_b200.so"
+SO = Path(os.environ.get("VH_SO_OUT", HERE / "libvhap_b200.so"))      # VH_SO_OUT / VH_EXTRA_FLAGS: experiment variants (dev only)
 SOURCES = ["flame.cu", "raster.cu", "render.cu", "texture.cu", "blend_tc.cu", "api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "--fmad=true"] + os.environ.get("VH_EXTRA_FLAGS", "").split()
@@ -21,7 +21,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [HERE.parent / "include" / "vhap_b200.h"]
     if not force and not _newer(SO, deps):
         return SO
-    objdir = HERE / "build"
+    objdir = HERE / ("build" if "VH_SO_OUT" not in os.environ else "build_" + SO.stem)
     objdir.mkdir(exist_ok=True)
 
     def cc(src):

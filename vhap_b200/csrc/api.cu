@@ -42,9 +42,28 @@ extern "C" int vhap_profile_enable(vhap_ctx* ctx, int32_t on) {
   if (on && !p->ev[0][0][0])
     for (int k = 0; k < KID_COUNT; ++k) for (int i = 0; i < VH_PROF_SLOTS; ++i) { CK(cudaEventCreate(&p->ev[k][i][0])); CK(cudaEventCreate(&p->ev[k][i][1])); }
   p->on = on;
-  for (int k = 0; k < KID_COUNT; ++k) { p->n[k] = 0; p->launches[k] = 0; }
+  if (on >= 0) { for (int k = 0; k < KID_COUNT; ++k) { p->n[k] = 0; p->launches[k] = 0; } p->first = nullptr; }
+  else p->on = 0;                                  // on < 0: stop recording but keep the recorded slots (graph timeline)
   return 0;
 }
+// synchronises; start / end (ms after the first recorded event) of every recorded launch, in recording order per kernel.
+// With vhap_profile_enable(ctx, 2) during stream capture the events are nodes of the graph: after a replay this is the
+// device timeline of that replay (all streams), the tool for critical-path analysis of the overlapped step.
+extern "C" int vhap_profile_timeline(vhap_ctx* ctx, int32_t* kid_out, float* t0_ms, float* t1_ms, int32_t max_n) {
+  VhProf* p = ctx->prof;
+  CK(cudaDeviceSynchronize());
+  int n = 0;
+  if (!p->first) return 0;
+  for (int k = 0; k < KID_COUNT; ++k)
+    for (int i = 0; i < p->n[k] && n < max_n; ++i) {
+      float a = 0, b = 0;
+      if (cudaEventElapsedTime(&a, p->first, p->ev[k][i][0]) != cudaSuccess || cudaEventElapsedTime(&b, p->first, p->ev[k][i][1]) != cudaSuccess) { cudaGetLastError(); continue; }
+      kid_out[n] = k; t0_ms[n] = a; t1_ms[n] = b; ++n;
+    }
+  return n;
+}
+// 0: run every kernel chain on the caller's stream (per-kernel timing without co-running kernels); 1 (default): fork/join
+extern "C" int vhap_set_overlap(vhap_ctx* ctx, int32_t on) { ctx->no_overlap = on ? 0 : 1; return 0; }
 extern "C" int vhap_profile_kernel_count(void) { return KID_COUNT; }
 extern "C" const char* vhap_profile_kernel_name(int32_t kid) { return (kid >= 0 && kid < KID_COUNT) ? KID_NAMES[kid] : ""; }
 // synchronises; avg_ms[k] = mean device time of the recorded launches of kernel k, launches[k] = launches since enable/reset
@@ -137,7 +156,7 @@ extern "C" int vhap_ctx_create(vhap_ctx** out, const vhap_mesh_desc* m, int32_t 
   UP(ctx->mips[0], (const f4*)nullptr, off);
   UP(ctx->mips[1], (const f4*)nullptr, off);
   UP(ctx->g_tex, (const float*)nullptr, off * 4);
-  ctx->tv_nblocks = (int)(((size_t)T * T + 255) / 256);
+  ctx->tv_nblocks = (int)(((size_t)T * T + 255) / 256) + T;     // >= CTAs of the texture fold kernel for any T
   UP(ctx->tv_partials, (const float*)nullptr, (size_t)ctx->tv_nblocks * 2);
   UP(ctx->scal, (const float*)nullptr, (size_t)16);
   UP(ctx->acc, (const float*)nullptr, (size_t)ACC_COUNT);
@@ -150,9 +169,16 @@ extern "C" int vhap_ctx_create(vhap_ctx** out, const vhap_mesh_desc* m, int32_t 
   UP(ctx->pair_count, (const int*)nullptr, (size_t)1);
   UP(ctx->dev_step, (const int*)nullptr, (size_t)2);
   for (int i = 0; i < 2; ++i) CK(cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking));
-  for (int i = 0; i < 8; ++i) CK(cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming));
+  {
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    for (int i = 0; i < 2; ++i) CK(cudaStreamCreateWithPriority(&ctx->hp[i], cudaStreamNonBlocking, hi));
+  }
+  for (int i = 0; i < 12; ++i) CK(cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming));
   UP(ctx->tex_l0_flag, (const int*)nullptr, (size_t)1);
   { int one = 1; cudaMemcpy(ctx->tex_l0_flag, &one, sizeof(int), cudaMemcpyHostToDevice); }
+  CK(cudaMalloc(&ctx->scan_state, (VH_SCAN_MAX_BLOCKS + 1) * sizeof(unsigned long long)));
+  CK(cudaMalloc(&ctx->tex_counter, sizeof(unsigned))); CK(cudaMemset(ctx->tex_counter, 0, sizeof(unsigned)));
   return 0;
 }
 
@@ -161,7 +187,7 @@ extern "C" int vhap_ctx_create(vhap_ctx** out, const vhap_mesh_desc* m, int32_t 
 static void free_batch(vhap_ctx* c) {
   FREE(c->v_shaped); FREE(c->v_shaped_part); FREE(c->v_posed); FREE(c->g_vshaped); FREE(c->verts); FREE(c->clip); FREE(c->vnorm); FREE(c->vnraw); FREE(c->snap); FREE(c->ndc);
   FREE(c->g_clip); FREE(c->g_vnorm); FREE(c->g_verts); FREE(c->posebuf); FREE(c->poses); FREE(c->gA); FREE(c->gpf); FREE(c->gJ); FREE(c->gbetas);
-  FREE(c->betas); FREE(c->cam); FREE(c->tri_id); FREE(c->pre); FREE(c->signs); FREE(c->pool_list); FREE(c->final_rgba); FREE(c->plane_albedo);
+  FREE(c->betas); FREE(c->cam); FREE(c->tri_id); FREE(c->pre); FREE(c->signs); FREE(c->pool_list); FREE(c->pool_tri); FREE(c->final_rgba); FREE(c->plane_albedo);
   FREE(c->plane_normal); FREE(c->plane_diffuse); FREE(c->tile_count); FREE(c->tile_off); FREE(c->tile_cursor); FREE(c->tile_list);
   FREE(c->pool_blk_count); FREE(c->pool_blk_off); FREE(c->partials); FREE(c->aa_code); FREE(c->pair_list); FREE(c->grgb);
 }
@@ -183,7 +209,7 @@ extern "C" int vhap_ctx_reserve(vhap_ctx* ctx, int32_t B, int32_t H, int32_t W) 
   UP(ctx->gbetas, (const float*)nullptr, (size_t)B * ctx->K); UP(ctx->betas, (const float*)nullptr, (size_t)B * ctx->K);
   UP(ctx->cam, (const CamParams*)nullptr, (size_t)B);
   UP(ctx->tri_id, (const int*)nullptr, n); UP(ctx->pre, (const f4*)nullptr, n); UP(ctx->signs, (const uint8_t*)nullptr, n);
-  UP(ctx->pool_list, (const int*)nullptr, n); UP(ctx->aa_code, (const float*)nullptr, n * 2); UP(ctx->pair_list, (const int*)nullptr, n * 2); UP(ctx->grgb, (const f4*)nullptr, n);
+  UP(ctx->pool_list, (const int*)nullptr, n); UP(ctx->pool_tri, (const int*)nullptr, n); UP(ctx->aa_code, (const float*)nullptr, n * 2); UP(ctx->pair_list, (const int*)nullptr, n * 2); UP(ctx->grgb, (const f4*)nullptr, n);
   UP(ctx->final_rgba, (const float*)nullptr, n * 4); UP(ctx->plane_albedo, (const f4*)nullptr, n); UP(ctx->plane_normal, (const f4*)nullptr, n);
   UP(ctx->plane_diffuse, (const f4*)nullptr, n);
   int tiles = B * ((H + VH_TILE - 1) / VH_TILE) * ((W + VH_TILE - 1) / VH_TILE);
@@ -207,7 +233,7 @@ extern "C" void vhap_ctx_destroy(vhap_ctx* c) {
   FREE(c->faces); FREE(c->faces_uv); FREE(c->verts_uv); FREE(c->lmk_faces); FREE(c->lmk_bary); FREE(c->adj_opp); FREE(c->fid2cid);
   FREE(c->vf_indptr); FREE(c->vf_faces); FREE(c->lap_indptr); FREE(c->lap_idx); FREE(c->lap_val); FREE(c->lap_y);
   FREE(c->face_flags); FREE(c->vert_flags); FREE(c->w_off); FREE(c->w_off_lap); FREE(c->rigid_indptr); FREE(c->rigid_vids); FREE(c->uvmask_res);
-  FREE(c->mips[0]); FREE(c->mips[1]); FREE(c->tex_painted); FREE(c->g_tex); FREE(c->tv_partials); FREE(c->scal); FREE(c->acc); FREE(c->maxslot);
+  FREE(c->mips[0]); FREE(c->mips[1]); FREE(c->tex_painted); FREE(c->g_tex); FREE(c->tv_partials); FREE(c->tex_counter); FREE(c->scan_state); FREE(c->scal); FREE(c->acc); FREE(c->maxslot);
   FREE(c->overflow_flag); FREE(c->pool_base); FREE(c->pool_count);
   free(c);
 }
@@ -369,7 +395,7 @@ extern "C" int vhap_energy_forward(vhap_ctx* ctx, const vhap_params* p, const vh
   launch_flame_forward(ctx, p, fb, s);
   if (cfg->photometric && cfg->w_photo >= 0.f) {
     // fork: vertex normals (needed only by the shading pass) run on aux stream 0 while the rasteriser runs on the main stream
-    static const bool vn_overlap = getenv("VHAP_B200_NO_VN_OVERLAP") == nullptr;
+    const bool vn_overlap = !ctx->no_overlap;
     if (vn_overlap) {
       cudaEventRecord(ctx->ev[4], s);
       cudaStreamWaitEvent(ctx->aux[0], ctx->ev[4], 0);
@@ -400,17 +426,19 @@ extern "C" int vhap_energy_backward(vhap_ctx* ctx, const vhap_params* p, const v
   // landmark energy (tracker.py:712-719): mean over global_B * n landmarks
   // fork: the parameter-space regularisers only need the parameters and the (already zeroed) gradient slab -> aux stream 0,
   // concurrent with the render backward (works eagerly and inside CUDA-graph capture: fork/join through events)
-  if (cfg->training) {
+  const bool regs_forked = cfg->training && !ctx->no_overlap;
+  if (regs_forked) {
     cudaEventRecord(ctx->ev[0], s);
     cudaStreamWaitEvent(ctx->aux[0], ctx->ev[0], 0);
     launch_regs(ctx, p, fb, cfg, g, global_B, ctx->aux[0]);
     cudaEventRecord(ctx->ev[1], ctx->aux[0]);
-  }
+  } else if (cfg->training) launch_regs(ctx, p, fb, cfg, g, global_B, s);
   if (cfg->w_landmark >= 0.f) {
     int nl = cfg->jawline_off ? 51 : 68;
     launch_landmarks(ctx, fb, cfg->w_landmark / ((float)global_B * nl), cfg->jawline_off, nullptr, nullptr, 1, opt_cam, global_B, s);
   }
   ctx->tex_fork_pending = 0;
+  cudaStream_t gs = s;                         // stream of the geometry backward
   if (photo) {
     PassArgs P;
     fill_render_args(ctx, P, fb, cfg, p->lights);
@@ -420,11 +448,16 @@ extern "C" int vhap_energy_backward(vhap_ctx* ctx, const vhap_params* p, const v
       launch_render_backward(ctx, P, cfg, p->lights, gg->lights, nullptr, s);
       cudaEventRecord(ctx->ev[2], s);          // texel gradients complete: the texture update may start (see vhap_tex_reg_fold_adam)
       ctx->tex_fork_pending = 1;
-      launch_vnormals_bwd(ctx, fb->B, s);
+      // the geometry backward is a chain of small latency-bound kernels; the texture update that runs concurrently is one
+      // machine-filling streaming kernel.  Put the chain on a highest-priority stream so its CTAs are scheduled ahead of the
+      // bulk kernel's remaining CTAs instead of queueing behind all of them.
+      if (!ctx->no_overlap) { gs = ctx->hp[0]; cudaStreamWaitEvent(gs, ctx->ev[2], 0); }
+      launch_vnormals_bwd(ctx, fb->B, gs);
     }
   }
-  if (g) launch_flame_backward(ctx, p, fb, gg, opt_cam, s);
-  if (cfg->training) cudaStreamWaitEvent(s, ctx->ev[1], 0);        // join the regularisers
+  if (g) launch_flame_backward(ctx, p, fb, gg, opt_cam, gs);
+  if (gs != s) { cudaEventRecord(ctx->ev[6], gs); cudaStreamWaitEvent(s, ctx->ev[6], 0); }
+  if (regs_forked) cudaStreamWaitEvent(s, ctx->ev[1], 0);        // join the regularisers
   float max_hw = (float)(fb->H > fb->W ? fb->H : fb->W);
   LAUNCH(ctx, KID_ASSEMBLE, s, k_assemble_losses<<<1, 32, 0, s>>>(ctx->acc, *cfg, max_hw, gg->focal_length, opt_cam, losses_out));
   LAST();
@@ -461,7 +494,7 @@ extern "C" int vhap_tex_reg_fold_adam(vhap_ctx* ctx, float* tex_extra, float* g_
                                       const vhap_stage_cfg* cfg, float photo_scale, float* losses_out, void* stream) {
   (void)photo_scale;
   cudaStream_t s = (cudaStream_t)stream;
-  if (ctx->tex_fork_pending && g_out == nullptr) {
+  if (ctx->tex_fork_pending && g_out == nullptr && !ctx->no_overlap) {
     // (with a caller-owned dense output the call stays on the caller's stream: ordering w.r.t. the caller's own work on g_out)
     // the texture fold / Adam / mip rebuild only depends on the texel gradients (event 2, recorded right after the fused
     // backward): run it on aux stream 1 concurrently with the geometry backward that was enqueued after that event, then join

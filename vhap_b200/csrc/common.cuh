@@ -8,10 +8,28 @@
 #if defined(__CUDACC__)
 #define VH_HD __host__ __device__ __forceinline__
 #define VH_D __device__ __forceinline__
+#define VH_UNROLL _Pragma("unroll")
 #else
 #define VH_HD inline
 #define VH_D inline
+#define VH_UNROLL
 #endif
+
+#include <string.h>
+VH_HD float vh_i2f(int i) {
+#if defined(__CUDA_ARCH__)
+  return __int_as_float(i);
+#else
+  float f; memcpy(&f, &i, 4); return f;
+#endif
+}
+VH_HD int vh_f2i(float f) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_int(f);
+#else
+  int i; memcpy(&i, &f, 4); return i;
+#endif
+}
 
 struct f3 { float x, y, z; };
 struct f4 { float x, y, z, w; };

@@ -57,8 +57,12 @@ struct vhap_ctx {
   int *scan_aux, *scan_total;                     // [1024], [1]
   float* aa_code; int *pair_list, *pair_count;    // [2N], [2N], [1]
   f4* grgb;                                       // [N] d L / d rgb of the compacted foreground pixels
+  unsigned long long* scan_state;                 // [VH_SCAN_MAX_BLOCKS + 1] look-back words + ticket of the single-launch scan
+  int* pool_tri;                                  // rasterised id per pool_list entry
   int* tex_l0_flag;                               // [1]
-  cudaStream_t aux[2]; cudaEvent_t ev[8]; int tex_fork_pending;   // fork/join of independent kernel chains
+  unsigned* tex_counter;                          // [1] CTA completion counter of the texture fold kernel (self-resetting)
+  cudaStream_t aux[2]; cudaStream_t hp[2]; cudaEvent_t ev[12];   // hp: highest-priority streams for the latency-critical geometry backward
+  int tex_fork_pending, no_overlap;   // fork/join of independent kernel chains
   int* dev_step; int use_dev_step;                // device counters [0] Adam step (1-based), [1] global step; used when use_dev_step
 };
 
@@ -72,21 +76,29 @@ enum { KID_CAM = 0, KID_POSE_FWD, KID_BLEND_FWD, KID_SKIN_FWD, KID_LMK, KID_VNOR
        KID_POOL_SCAN, KID_POOL_SCATTER, KID_AA_PAIRS, KID_PASSB, KID_REDUCE, KID_SLAB, KID_FINALIZE, KID_PASSC1, KID_PASSC, KID_LIGHTS_REDUCE, KID_TEX_L0, KID_MIP,
        KID_TEX_FOLD, KID_TEX_LOSS, KID_ADAM, KID_ASSEMBLE, KID_MISC, KID_COUNT };
 #define VH_PROF_SLOTS 128
+#define VH_SCAN_MAX_BLOCKS 1024
 struct VhProf {
-  int on;
+  int on;                                         // 1: events around launches; 2: same, also valid inside stream capture (timeline of a graph replay)
+  cudaEvent_t first;
   unsigned long long launches[KID_COUNT];
   int n[KID_COUNT];
   cudaEvent_t ev[KID_COUNT][VH_PROF_SLOTS][2];
 };
 static inline VhProf* vh_prof(vhap_ctx* c) { return c->prof; }
+static inline void vh_prof_record(VhProf* p, cudaEvent_t e, cudaStream_t s) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (p->on == 2) cudaStreamIsCapturing(s, &st);
+  if (st == cudaStreamCaptureStatusActive) cudaEventRecordWithFlags(e, s, cudaEventRecordExternal);   // event-record node of the graph
+  else cudaEventRecord(e, s);
+}
 static inline void vh_prof_begin(vhap_ctx* c, int kid, cudaStream_t s) {
   VhProf* p = vh_prof(c);
   p->launches[kid]++;
-  if (p->on && p->n[kid] < VH_PROF_SLOTS) cudaEventRecord(p->ev[kid][p->n[kid]][0], s);
+  if (p->on && p->n[kid] < VH_PROF_SLOTS) { vh_prof_record(p, p->ev[kid][p->n[kid]][0], s); if (!p->first) p->first = p->ev[kid][p->n[kid]][0]; }
 }
 static inline void vh_prof_end(vhap_ctx* c, int kid, cudaStream_t s) {
   VhProf* p = vh_prof(c);
-  if (p->on && p->n[kid] < VH_PROF_SLOTS) { cudaEventRecord(p->ev[kid][p->n[kid]][1], s); p->n[kid]++; }
+  if (p->on && p->n[kid] < VH_PROF_SLOTS) { vh_prof_record(p, p->ev[kid][p->n[kid]][1], s); p->n[kid]++; }
 }
 #define LAUNCH(c, kid, s, ...) do { vh_prof_begin((c), (kid), (s)); __VA_ARGS__; vh_prof_end((c), (kid), (s)); } while (0)
 

@@ -512,15 +512,24 @@ void launch_flame_backward(vhap_ctx* c, const vhap_params* p, const vhap_frame_b
   dim3 g1((V + 127) / 128, (B + 1) / 2);
   LAUNCH(c, KID_SKIN_BWD, s, k_skin_bwd<2><<<g1, 128, 0, s>>>(c->v_posed, c->verts, c->posedirs, c->lbs_w, c->posebuf, c->cam, fb->timesteps, c->g_verts, c->g_clip, V, B, fb->H, fb->W,
                                    opt_cam, c->Mpad, c->g_vshaped, g->static_offset, g->translation, c->gA, c->gpf, c->acc));
+  // the blend-shape adjoint (tensor-core contraction of g_vshaped) only needs skin_bwd's output: it runs beside the serial
+  // pose_bwd -> joff_bwd pair on the second high-priority stream; both add into gbetas atomically
+  bool forked = need_betas && s == c->hp[0];
+  cudaStream_t s2 = forked ? c->hp[1] : s;
+  if (forked) { cudaEventRecord(c->ev[7], s); cudaStreamWaitEvent(s2, c->ev[7], 0); }
+  if (need_betas) {
+    if (c->use_tc_blend) launch_blend_tc_bwd(c, B, s2);
+    else {
+      dim3 g2((M + BB_ROWS - 1) / BB_ROWS, (B + VH_MAXB_CHUNK - 1) / VH_MAXB_CHUNK);
+      LAUNCH(c, KID_BLEND_BWD, s2, k_blend_bwd<VH_MAXB_CHUNK><<<g2, 512, 0, s2>>>(c->S_bwd, c->g_vshaped, M, c->Mpad, c->K, B, c->gbetas));
+    }
+    if (forked) cudaEventRecord(c->ev[8], s2);
+  }
   LAUNCH(c, KID_POSE_BWD, s, k_pose_bwd<<<B, 128, 0, s>>>(c->poses, c->posebuf, c->gA, c->gpf, fb->timesteps, c->JS, c->K, g->rotation, g->neck_pose, g->jaw_pose, g->eyes_pose,
                                c->gJ, need_betas ? c->gbetas : nullptr));
   if (g->static_offset) LAUNCH(c, KID_JOFF_BWD, s, k_joff_bwd<<<(V + 127) / 128, 128, 0, s>>>(c->Jreg, c->gJ, V, B, g->static_offset));
   if (need_betas) {
-    if (c->use_tc_blend) launch_blend_tc_bwd(c, B, s);
-    else {
-      dim3 g2((M + BB_ROWS - 1) / BB_ROWS, (B + VH_MAXB_CHUNK - 1) / VH_MAXB_CHUNK);
-      LAUNCH(c, KID_BLEND_BWD, s, k_blend_bwd<VH_MAXB_CHUNK><<<g2, 512, 0, s>>>(c->S_bwd, c->g_vshaped, M, c->Mpad, c->K, B, c->gbetas));
-    }
+    if (forked) cudaStreamWaitEvent(s, c->ev[8], 0);
     LAUNCH(c, KID_BETAS_SCATTER, s, k_betas_scatter<<<B, 256, 0, s>>>(c->gbetas, fb->timesteps, c->K, c->n_shape, g->shape, g->expr));
   }
   (void)p;

@@ -17,15 +17,15 @@ struct PoseFwd {
 };
 
 VH_HD void mat3_mul(const float* a, const float* b, float* c) {
-  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j)
+  VH_UNROLL for (int i = 0; i < 3; ++i) VH_UNROLL for (int j = 0; j < 3; ++j)
     c[i * 3 + j] = a[i * 3] * b[j] + a[i * 3 + 1] * b[3 + j] + a[i * 3 + 2] * b[6 + j];
 }
 VH_HD void mat3_mul_bt(const float* a, const float* b, float* c) {   // a * b^T
-  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j)
+  VH_UNROLL for (int i = 0; i < 3; ++i) VH_UNROLL for (int j = 0; j < 3; ++j)
     c[i * 3 + j] = a[i * 3] * b[j * 3] + a[i * 3 + 1] * b[j * 3 + 1] + a[i * 3 + 2] * b[j * 3 + 2];
 }
 VH_HD void mat3_mul_at(const float* a, const float* b, float* c) {   // a^T * b
-  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j)
+  VH_UNROLL for (int i = 0; i < 3; ++i) VH_UNROLL for (int j = 0; j < 3; ++j)
     c[i * 3 + j] = a[i] * b[j] + a[3 + i] * b[3 + j] + a[6 + i] * b[6 + j];
 }
 
@@ -36,7 +36,7 @@ VH_HD void rodrigues(const float* r, float* R) {
   float s = sinf(th), c = cosf(th);
   float K[9] = {0, -nz, ny, nz, 0, -nx, -ny, nx, 0}, M[9];
   mat3_mul(K, K, M);
-  for (int i = 0; i < 9; ++i) R[i] = s * K[i] + (1.f - c) * M[i];
+  VH_UNROLL for (int i = 0; i < 9; ++i) R[i] = s * K[i] + (1.f - c) * M[i];
   R[0] += 1.f; R[4] += 1.f; R[8] += 1.f;
 }
 
@@ -48,11 +48,11 @@ VH_HD void rodrigues_bwd(const float* r, const float* gR, float* g_r) {
   float K[9] = {0, -nz, ny, nz, 0, -nx, -ny, nx, 0}, M[9];
   mat3_mul(K, K, M);
   float g_s = 0, g_c = 0;
-  for (int i = 0; i < 9; ++i) { g_s += gR[i] * K[i]; g_c -= gR[i] * M[i]; }
+  VH_UNROLL for (int i = 0; i < 9; ++i) { g_s += gR[i] * K[i]; g_c -= gR[i] * M[i]; }
   float t1[9], t2[9], gK[9];
   mat3_mul_bt(gR, K, t1);      // gR K^T
   mat3_mul_at(K, gR, t2);      // K^T gR
-  for (int i = 0; i < 9; ++i) gK[i] = s * gR[i] + (1.f - c) * (t1[i] + t2[i]);
+  VH_UNROLL for (int i = 0; i < 9; ++i) gK[i] = s * gR[i] + (1.f - c) * (t1[i] + t2[i]);
   float g_th = g_s * c - g_c * s;
   float gnx = gK[7] - gK[5], gny = gK[2] - gK[6], gnz = gK[3] - gK[1];
   float ith = 1.f / th;
@@ -64,68 +64,68 @@ VH_HD void rodrigues_bwd(const float* r, const float* gR, float* g_r) {
 
 // pose[15] = (rotation, neck, jaw, eye_l, eye_r); J = rest joints
 VH_HD void pose_forward(const float* pose, PoseFwd& f) {
-  for (int j = 0; j < VH_NJ; ++j) rodrigues(pose + 3 * j, f.R[j]);
-  for (int j = 0; j < VH_NJ; ++j) {
+  VH_UNROLL for (int j = 0; j < VH_NJ; ++j) rodrigues(pose + 3 * j, f.R[j]);
+  VH_UNROLL for (int j = 0; j < VH_NJ; ++j) {
     int p = vh_parent(j);
     float rel[3];
-    for (int c = 0; c < 3; ++c) rel[c] = f.J[j][c] - (p >= 0 ? f.J[p][c] : 0.f);
+    VH_UNROLL for (int c = 0; c < 3; ++c) rel[c] = f.J[j][c] - (p >= 0 ? f.J[p][c] : 0.f);
     if (p < 0) {
-      for (int i = 0; i < 9; ++i) f.GR[j][i] = f.R[j][i];
-      for (int c = 0; c < 3; ++c) f.Gt[j][c] = rel[c];
+      VH_UNROLL for (int i = 0; i < 9; ++i) f.GR[j][i] = f.R[j][i];
+      VH_UNROLL for (int c = 0; c < 3; ++c) f.Gt[j][c] = rel[c];
     } else {
       mat3_mul(f.GR[p], f.R[j], f.GR[j]);
-      for (int c = 0; c < 3; ++c)
+      VH_UNROLL for (int c = 0; c < 3; ++c)
         f.Gt[j][c] = f.GR[p][c * 3] * rel[0] + f.GR[p][c * 3 + 1] * rel[1] + f.GR[p][c * 3 + 2] * rel[2] + f.Gt[p][c];
     }
   }
-  for (int j = 0; j < VH_NJ; ++j)
-    for (int r = 0; r < 3; ++r) {
+  VH_UNROLL for (int j = 0; j < VH_NJ; ++j)
+    VH_UNROLL for (int r = 0; r < 3; ++r) {
       const float* g = f.GR[j] + r * 3;
       f.A[j][r * 4 + 0] = g[0]; f.A[j][r * 4 + 1] = g[1]; f.A[j][r * 4 + 2] = g[2];
       f.A[j][r * 4 + 3] = f.Gt[j][r] - (g[0] * f.J[j][0] + g[1] * f.J[j][1] + g[2] * f.J[j][2]);
     }
-  for (int j = 1; j < VH_NJ; ++j)
-    for (int i = 0; i < 9; ++i) f.pf[(j - 1) * 9 + i] = f.R[j][i] - ((i == 0 || i == 4 || i == 8) ? 1.f : 0.f);
+  VH_UNROLL for (int j = 1; j < VH_NJ; ++j)
+    VH_UNROLL for (int i = 0; i < 9; ++i) f.pf[(j - 1) * 9 + i] = f.R[j][i] - ((i == 0 || i == 4 || i == 8) ? 1.f : 0.f);
 }
 
 // gA[5][12], gpf[36] -> g_pose[15], g_J[5][3]
 VH_HD void pose_backward(const float* pose, const PoseFwd& f, const float gA[VH_NJ][12], const float* gpf,
                          float* g_pose, float g_J[VH_NJ][3]) {
   float gGR[VH_NJ][9], gGt[VH_NJ][3], gR[VH_NJ][9];
-  for (int j = 0; j < VH_NJ; ++j) {
-    for (int c = 0; c < 3; ++c) g_J[j][c] = 0.f;
-    for (int i = 0; i < 9; ++i) gR[j][i] = 0.f;
+  VH_UNROLL for (int j = 0; j < VH_NJ; ++j) {
+    VH_UNROLL for (int c = 0; c < 3; ++c) g_J[j][c] = 0.f;
+    VH_UNROLL for (int i = 0; i < 9; ++i) gR[j][i] = 0.f;
   }
-  for (int j = 0; j < VH_NJ; ++j)
-    for (int r = 0; r < 3; ++r) {
+  VH_UNROLL for (int j = 0; j < VH_NJ; ++j)
+    VH_UNROLL for (int r = 0; r < 3; ++r) {
       float gt = gA[j][r * 4 + 3];
       gGt[j][r] = gt;
-      for (int c = 0; c < 3; ++c) {
+      VH_UNROLL for (int c = 0; c < 3; ++c) {
         gGR[j][r * 3 + c] = gA[j][r * 4 + c] - gt * f.J[j][c];
         g_J[j][c] -= f.GR[j][r * 3 + c] * gt;
       }
     }
-  for (int j = VH_NJ - 1; j >= 0; --j) {
+  VH_UNROLL for (int j = VH_NJ - 1; j >= 0; --j) {
     int p = vh_parent(j);
     float rel[3], g_rel[3];
-    for (int c = 0; c < 3; ++c) rel[c] = f.J[j][c] - (p >= 0 ? f.J[p][c] : 0.f);
+    VH_UNROLL for (int c = 0; c < 3; ++c) rel[c] = f.J[j][c] - (p >= 0 ? f.J[p][c] : 0.f);
     if (p < 0) {
-      for (int i = 0; i < 9; ++i) gR[j][i] += gGR[j][i];
-      for (int c = 0; c < 3; ++c) g_rel[c] = gGt[j][c];
+      VH_UNROLL for (int i = 0; i < 9; ++i) gR[j][i] += gGR[j][i];
+      VH_UNROLL for (int c = 0; c < 3; ++c) g_rel[c] = gGt[j][c];
     } else {
       float t[9];
       mat3_mul_bt(gGR[j], f.R[j], t);                 // g_GpR += gGR_j R_j^T
-      for (int i = 0; i < 9; ++i) gGR[p][i] += t[i];
+      VH_UNROLL for (int i = 0; i < 9; ++i) gGR[p][i] += t[i];
       mat3_mul_at(f.GR[p], gGR[j], t);                // g_R_j += GpR^T gGR_j
-      for (int i = 0; i < 9; ++i) gR[j][i] += t[i];
-      for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) gGR[p][r * 3 + c] += gGt[j][r] * rel[c];
-      for (int c = 0; c < 3; ++c) {
+      VH_UNROLL for (int i = 0; i < 9; ++i) gR[j][i] += t[i];
+      VH_UNROLL for (int r = 0; r < 3; ++r) VH_UNROLL for (int c = 0; c < 3; ++c) gGR[p][r * 3 + c] += gGt[j][r] * rel[c];
+      VH_UNROLL for (int c = 0; c < 3; ++c) {
         g_rel[c] = f.GR[p][c] * gGt[j][0] + f.GR[p][3 + c] * gGt[j][1] + f.GR[p][6 + c] * gGt[j][2];
         gGt[p][c] += gGt[j][c];
       }
     }
-    for (int c = 0; c < 3; ++c) { g_J[j][c] += g_rel[c]; if (p >= 0) g_J[p][c] -= g_rel[c]; }
+    VH_UNROLL for (int c = 0; c < 3; ++c) { g_J[j][c] += g_rel[c]; if (p >= 0) g_J[p][c] -= g_rel[c]; }
   }
-  for (int j = 1; j < VH_NJ; ++j) for (int i = 0; i < 9; ++i) gR[j][i] += gpf[(j - 1) * 9 + i];
-  for (int j = 0; j < VH_NJ; ++j) rodrigues_bwd(pose + 3 * j, gR[j], g_pose + 3 * j);
+  VH_UNROLL for (int j = 1; j < VH_NJ; ++j) VH_UNROLL for (int i = 0; i < 9; ++i) gR[j][i] += gpf[(j - 1) * 9 + i];
+  VH_UNROLL for (int j = 0; j < VH_NJ; ++j) rodrigues_bwd(pose + 3 * j, gR[j], g_pose + 3 * j);
 }

@@ -110,11 +110,75 @@ __global__ void __launch_bounds__(1024) k_scan_add(int* __restrict__ out, const 
 #pragma unroll
   for (int k = 0; k < 4; ++k) if (i0 + k < n) out[i0 + k] += a;
 }
+// Single-launch exclusive scan (decoupled look-back): blocks take a ticket (dynamic block id = forward progress), scan their
+// 4096 elements, publish (flag | aggregate) as ONE 64-bit word and the first warp looks back over the predecessors' words, 32 at
+// a time, until it meets an inclusive prefix.  state[0..nb) and the ticket (state[nb]) are zeroed by a memset node before.
+#define SCAN_FLAG_A 1ull
+#define SCAN_FLAG_P 2ull
+__global__ void __launch_bounds__(1024) k_scan_lb(const int* __restrict__ in, int* __restrict__ out, int n, unsigned long long* state, int nb, int* __restrict__ total) {
+  __shared__ int sh[32];
+  __shared__ int s_bid, s_prefix;
+  if (threadIdx.x == 0) s_bid = (int)atomicAdd((unsigned*)(state + nb), 1u);
+  __syncthreads();
+  const int bid = s_bid, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int i0 = (bid * 1024 + threadIdx.x) * 4;
+  int v[4], s = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { v[k] = (i0 + k < n) ? in[i0 + k] : 0; s += v[k]; }
+  int incl = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  if (lane == 31) sh[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    int x = sh[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += t; }
+    sh[lane] = x;
+  }
+  __syncthreads();
+  incl += w > 0 ? sh[w - 1] : 0;
+  const int block_total = sh[31];
+  if (w == 0) {
+    if (lane == 0) atomicExch(state + bid, ((bid == 0 ? SCAN_FLAG_P : SCAN_FLAG_A) << 32) | (unsigned)block_total);
+    int prefix = 0;
+    int j = bid - 1;                                   // nearest predecessor of this window
+    while (j >= 0) {
+      int idx = j - lane;
+      unsigned long long st = SCAN_FLAG_P << 32;       // lanes before block 0 act as an empty inclusive prefix
+      if (idx >= 0) { do { st = *(volatile unsigned long long*)(state + idx); } while ((st >> 32) == 0ull); }
+      unsigned pm = __ballot_sync(0xffffffffu, (st >> 32) == SCAN_FLAG_P);
+      int first = pm ? __ffs(pm) - 1 : 32;             // nearest predecessor holding an inclusive prefix
+      int val = (lane <= first && idx >= 0) ? (int)(unsigned)st : 0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+      prefix += val;
+      if (pm) break;
+      j -= 32;
+    }
+    if (lane == 0) {
+      if (bid > 0) atomicExch(state + bid, (SCAN_FLAG_P << 32) | (unsigned)(prefix + block_total));
+      s_prefix = prefix;
+      if (bid == nb - 1 && total) *total = prefix + block_total;
+    }
+  }
+  __syncthreads();
+  int excl = s_prefix + incl - s;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { if (i0 + k < n) out[i0 + k] = excl; excl += v[k]; }
+}
+
 void launch_scan(vhap_ctx* c, const int* in, int* out, int n, int* total, cudaStream_t s) {
   int nb = (n + 4095) / 4096;
-  LAUNCH(c, KID_SCAN, s, k_scan_local<<<nb, 1024, 0, s>>>(in, out, c->scan_aux, n));
-  LAUNCH(c, KID_SCAN, s, k_scan_aux<<<1, 1024, 0, s>>>(c->scan_aux, nb, total));
-  LAUNCH(c, KID_SCAN, s, k_scan_add<<<nb, 1024, 0, s>>>(out, c->scan_aux, n));
+  static const bool three_pass = getenv("VHAP_B200_SCAN3") != nullptr;       // previous three-launch scan, kept for A/B timing
+  if (three_pass || nb > VH_SCAN_MAX_BLOCKS) {
+    LAUNCH(c, KID_SCAN, s, k_scan_local<<<nb, 1024, 0, s>>>(in, out, c->scan_aux, n));
+    LAUNCH(c, KID_SCAN, s, k_scan_aux<<<1, 1024, 0, s>>>(c->scan_aux, nb, total));
+    LAUNCH(c, KID_SCAN, s, k_scan_add<<<nb, 1024, 0, s>>>(out, c->scan_aux, n));
+    return;
+  }
+  cudaMemsetAsync(c->scan_state, 0, (size_t)(nb + 1) * sizeof(unsigned long long), s);
+  LAUNCH(c, KID_SCAN, s, k_scan_lb<<<nb, 1024, 0, s>>>(in, out, n, c->scan_state, nb, total));
 }
 
 // tile list starts are padded to 4 ints (16 bytes) so that the fine rasteriser can stage them with TMA bulk copies

@@ -74,7 +74,7 @@ __global__ void k_pool_bases(const int* __restrict__ off, int nblk, const int* _
 
 // also emits the list of adjacent pixel pairs with different ids (pair = pixel0 * 2 + direction) for the antialias analysis
 __global__ void __launch_bounds__(PB) k_pool_scatter(const int* __restrict__ tri_id, const uint8_t* __restrict__ fid2cid, size_t n, int H, int W, int ncl,
-                                                     const int* __restrict__ blk_off, int* __restrict__ pool_list,
+                                                     const int* __restrict__ blk_off, int* __restrict__ pool_list, int* __restrict__ pool_tri,
                                                      int* __restrict__ pair_list, int* __restrict__ pair_count) {
   __shared__ int wcnt[16][PB / 32];
   size_t pix = (size_t)blockIdx.x * PB + threadIdx.x;
@@ -106,7 +106,9 @@ __global__ void __launch_bounds__(PB) k_pool_scatter(const int* __restrict__ tri
   if (cid >= 0) {
     int before = 0;
     for (int k = 0; k < w; ++k) before += wcnt[cid][k];
-    pool_list[blk_off[(size_t)cid * gridDim.x + blockIdx.x] + before + rank] = (int)pix;
+    int pos = blk_off[(size_t)cid * gridDim.x + blockIdx.x] + before + rank;
+    pool_list[pos] = (int)pix;
+    pool_tri[pos] = id;
   }
 }
 
@@ -127,11 +129,12 @@ __global__ void __launch_bounds__(PB) k_passA(PassArgs P, float* __restrict__ pa
   const RenderArgs& A = P.R;
   int n_fg = A.B * A.H * A.W - P.pool_count[0];
   const int* list = P.pool_list + P.pool_base[1];
+  const int* tris = P.pool_tri + P.pool_base[1];
   float acc[2] = {0.f, 0.f}; float mx = -INFINITY; int mxi = 0;
   for (int i = blockIdx.x * PB + threadIdx.x; i < n_fg; i += gridDim.x * PB) {
-    int pix = list[i];
+    int pix = list[i], id = tris[i];
     int x = pix % A.W, y = (pix / A.W) % A.H, b = pix / (A.W * A.H);
-    passA_body(P, b, y, x, acc, mx, mxi);
+    passA_body(P, b, y, x, acc, mx, mxi, id);
   }
   block_reduce_store<2>(acc, sh, partials + (size_t)blockIdx.x * VH_NPART);
   unsigned long long pm = mx > -INFINITY ? pack_max(mx, mxi) : 0ull;
@@ -160,10 +163,11 @@ __global__ void __launch_bounds__(PB) k_passC1(PassArgs P, const float* __restri
   const RenderArgs& A = P.R;
   int n_fg = A.B * A.H * A.W - P.pool_count[0];
   const int* list = P.pool_list + P.pool_base[1];
+  const int* tris = P.pool_tri + P.pool_base[1];
   for (int i = blockIdx.x * PB + threadIdx.x; i < n_fg; i += gridDim.x * PB) {
-    int pix = list[i];
+    int pix = list[i], id = tris[i];
     int x = pix % A.W, y = (pix / A.W) % A.H, b = pix / (A.W * A.H);
-    f3 g = passC1_body(P, b, y, x, ext_grad);
+    f3 g = passC1_body(P, b, y, x, ext_grad, id);
     f4 o = {g.x, g.y, g.z, 0.f};
     grgb[i] = o;                                    // indexed by list position: coalesced
   }
@@ -180,11 +184,12 @@ __global__ void __launch_bounds__(PB, VH_C2_MINBLOCKS) k_passC2(PassArgs P, cons
   float gl[27];
 #pragma unroll
   for (int i = 0; i < 27; ++i) gl[i] = 0.f;
+  const int* tris = P.pool_tri + P.pool_base[1];
   for (int i = blockIdx.x * PB + threadIdx.x; i < n_fg; i += gridDim.x * PB) {
-    int pix = list[i];
+    int pix = list[i], id = tris[i];
     int x = pix % A.W, y = (pix / A.W) % A.H, b = pix / (A.W * A.H);
     f4 g = grgb[i];
-    passC2_body(P, b, y, x, mk3(g.x, g.y, g.z), gl);
+    passC2_body(P, b, y, x, mk3(g.x, g.y, g.z), gl, id);
   }
   block_reduce_store<27>(gl, sh, partials + (size_t)blockIdx.x * VH_NPART + 4);
 }
@@ -290,7 +295,7 @@ void fill_render_args(vhap_ctx* c, PassArgs& P, const vhap_frame_batch* fb, cons
   P.final_rgba = c->want_planes ? c->final_rgba : nullptr;
   P.plane_albedo = c->want_planes ? c->plane_albedo : nullptr; P.plane_normal = c->want_planes ? c->plane_normal : nullptr;
   P.plane_diffuse = c->want_planes ? c->plane_diffuse : nullptr;
-  P.pool_list = c->pool_list; P.pool_base = c->pool_base; P.pool_count = c->pool_count;
+  P.pool_list = c->pool_list; P.pool_base = c->pool_base; P.pool_count = c->pool_count; P.pool_tri = c->pool_tri;
   P.disturb = cfg->training ? 1 : 0;                        // enable_disturbance = stage != None (tracker.py:427)
   P.rate_fg = cfg->disturb_rate_fg; P.rate_bg = cfg->disturb_rate_bg;
   P.inj_w = c->inj_w; P.inj_u = c->inj_u; P.seed = cfg->rng_seed; P.step = cfg->rng_step; P.step_ptr = c->use_dev_step ? c->dev_step : nullptr;
@@ -322,7 +327,7 @@ void launch_render_forward(vhap_ctx* c, PassArgs& P, cudaStream_t s) {
   launch_scan(c, c->pool_blk_count, c->pool_blk_off, 16 * nblk, c->scan_total, s);
   LAUNCH(c, KID_POOL_SCAN, s, k_pool_bases<<<1, 32, 0, s>>>(c->pool_blk_off, nblk, c->scan_total, c->pool_base, c->pool_count));
   cudaMemsetAsync(c->pair_count, 0, sizeof(int), s);
-  LAUNCH(c, KID_POOL_SCATTER, s, k_pool_scatter<<<nblk, PB, 0, s>>>(A.tri_id, A.fid2cid, n, A.H, A.W, c->n_clusters, c->pool_blk_off, c->pool_list, c->pair_list, c->pair_count));
+  LAUNCH(c, KID_POOL_SCATTER, s, k_pool_scatter<<<nblk, PB, 0, s>>>(A.tri_id, A.fid2cid, n, A.H, A.W, c->n_clusters, c->pool_blk_off, c->pool_list, c->pool_tri, c->pair_list, c->pair_count));
   int grid = nblk < NPERSIST ? nblk : NPERSIST;
   LAUNCH(c, KID_PASSA, s, k_passA<<<grid, PB, 0, s>>>(P, c->partials, c->maxslot));
   LAUNCH(c, KID_AA_PAIRS, s, k_aa_pairs<<<grid, PB, 0, s>>>(P, c->pair_list, c->pair_count));

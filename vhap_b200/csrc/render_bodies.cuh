@@ -20,6 +20,7 @@ struct PassArgs {
   const int* pool_list;       // pixel indices grouped by cluster, ascending inside a cluster
   const int* pool_base;       // [16]
   const int* pool_count;      // [16]
+  const int* pool_tri;        // rasterised id of pool_list[i] (saves the dependent tri_id[pixel] access in the list-walking passes)
   int disturb;                // enable_disturbance
   float rate_fg, rate_bg;     // <0 = None
   const uint8_t* inj_w;       // injected Bernoulli draws (bit0 fg, bit1 bg) or NULL -> Philox
@@ -205,10 +206,10 @@ VH_HD void aa_bwd(const PassArgs& P, int b, const AAPair& r, float g_alpha) {
 
 // ------------------------------------------------------------------------------------------ pass A
 // acc[0] += var_c(diffuse) over fg pixels, acc[1] += 1 per fg pixel; (mx, mx_idx) running max of diffuse (fg only)
-VH_HD void passA_body(const PassArgs& P, int b, int y, int x, float* acc, float& mx, int& mx_idx) {
+VH_HD void passA_body(const PassArgs& P, int b, int y, int x, float* acc, float& mx, int& mx_idx, int id_known = -1) {
   const RenderArgs& A = P.R;
   size_t pix = ((size_t)b * A.H + y) * A.W + x;
-  int id = A.tri_id[pix];
+  int id = id_known >= 0 ? id_known : A.tri_id[pix];
   if (id <= 0) {
     if (P.plane_albedo) { f4 z = {0, 0, 0, 0}; P.plane_albedo[pix] = z; P.plane_normal[pix] = z; P.plane_diffuse[pix] = z; }
     return;
@@ -300,10 +301,10 @@ VH_HD f3 sign_grad(uint8_t sg, float scale) {
 // replaces the L1-loss gradient with a caller-provided d L / d rgba_aa (modular render_rgba backward).
 // Split in two so that each kernel stays small (registers, instruction cache): C1 = colour-gradient bookkeeping through the
 // antialias / disturbance adjoints (+ the rare silhouette position gradients) -> d L / d rgb of the pixel; C2 = shading adjoint.
-VH_HD f3 passC1_body(const PassArgs& P, int b, int y, int x, const float* ext_grad) {
+VH_HD f3 passC1_body(const PassArgs& P, int b, int y, int x, const float* ext_grad, int id_known = -1) {
   const RenderArgs& A = P.R;
   size_t pix = ((size_t)b * A.H + y) * A.W + x;
-  int id = A.tri_id[pix];
+  int id = id_known >= 0 ? id_known : A.tri_id[pix];
   // Only FOREGROUND pixels are visited (the kernel walks the compacted foreground list): a background pixel has no
   // parameters behind its colour, and the position gradient of a (foreground, background) pair is owned by its
   // foreground pixel; (foreground, foreground) pairs are owned by their pixel 0.
@@ -350,10 +351,10 @@ VH_HD f3 passC1_body(const PassArgs& P, int b, int y, int x, const float* ext_gr
   return gD * own_w;
 }
 
-VH_HD void passC2_body(const PassArgs& P, int b, int y, int x, f3 g_rgb, float* g_lights_local) {
+VH_HD void passC2_body(const PassArgs& P, int b, int y, int x, f3 g_rgb, float* g_lights_local, int id_known = -1) {
   const RenderArgs& A = P.R;
   size_t pix = ((size_t)b * A.H + y) * A.W + x;
-  int id = A.tri_id[pix];
+  int id = id_known >= 0 ? id_known : A.tri_id[pix];
   if (id <= 0) return;
   // reg_diffuse on diffuse_detach_normal (tracker.py:547-550): variance term + global max term
   f3 g_dd = mk3(0, 0, 0);

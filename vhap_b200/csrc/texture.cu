@@ -52,8 +52,8 @@ __global__ void __launch_bounds__(256) k_mip_down(const f4* __restrict__ src, f4
   }
 }
 
-static void build_mips(vhap_ctx* c, f4* pyr, cudaStream_t s) {
-  int l = 0;
+static void build_mips(vhap_ctx* c, f4* pyr, cudaStream_t s, int from_level = 0) {
+  int l = from_level;
   while (l < c->max_level) {
     int ssz = c->T >> l, nlev = c->max_level - l < 5 ? c->max_level - l : 5;
     int tile = ssz < 32 ? ssz : 32, g = ssz / tile;
@@ -85,92 +85,134 @@ struct TexFoldArgs {
 
 __device__ __forceinline__ float chan(const f4& t, int c) { return c == 0 ? t.x : (c == 1 ? t.y : t.z); }
 
-// One thread per level-0 texel (all 3 channels).
-__global__ void __launch_bounds__(256) k_tex_fold(TexFoldArgs a, float* __restrict__ partials) {
-  __shared__ float sh[8 * 2];
-  int T = a.T;
-  size_t n = (size_t)T * T, i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  float acc[2] = {0.f, 0.f};
-  if (i < n) {
-    int x = i % T, y = i / T;
-    // photometric gradient: fold every pyramid level back to level 0 (box-filter adjoint: 1/4 per level)
-    float g[3] = {0.f, 0.f, 0.f};
-    if (a.g_pyr) {
-      // level 0 of the gradient pyramid is only touched under magnification (mip level < 1); the backward pass raises
-      // l0_flag when it scatters there, otherwise the 16 B/texel read + re-zero of that level is skipped
-      bool l0 = a.l0_flag ? (*a.l0_flag != 0) : true;
-      float sc = l0 ? 1.f : 0.25f;
-      for (int l = l0 ? 0 : 1; l <= a.max_level; ++l) {
-        int s = T >> l;
-        const float* p = a.g_pyr + ((size_t)a.mip_off[l] + (size_t)(y >> l) * s + (x >> l)) * 4;
-        g[0] += p[0] * sc; g[1] += p[1] * sc; g[2] += p[2] * sc;
-        sc *= 0.25f;
-      }
-      if (l0) { float4* p0 = (float4*)(a.g_pyr + i * 4); *p0 = make_float4(0.f, 0.f, 0.f, 0.f); }   // coarser levels: memset after the kernel
-    }
-    f4 t = a.tex_old[i];
-    float ex[3] = {a.extra[i], a.extra[n + i], a.extra[2 * n + i]};
-    if (a.w_tv > 0.f) {                                                          // tracker.py:526-534
-      f4 tr = x + 1 < T ? a.tex_old[i + 1] : t, tl = x > 0 ? a.tex_old[i - 1] : t;
-      f4 td = y + 1 < T ? a.tex_old[i + T] : t, tu = y > 0 ? a.tex_old[i - T] : t;
-      for (int c = 0; c < 3; ++c) {
-        float v = chan(t, c), dr = v - chan(tr, c), dd = v - chan(td, c), dl = chan(tl, c) - v, du = chan(tu, c) - v;
-        acc[0] += a.w_tv * (dr * dr + dd * dd);                                  // each difference counted once (right, down)
-        g[c] += 2.f * a.w_tv * (dr + dd - dl - du);
-      }
-    }
-    if (a.w_res > 0.f && a.mask && a.mask[i]) {                                  // tracker.py:536-539
-      for (int c = 0; c < 3; ++c) { acc[1] += a.w_res * ex[c] * ex[c]; g[c] += 2.f * a.w_res * ex[c]; }
-    }
-    if (a.g_out) { a.g_out[i] = g[0]; a.g_out[n + i] = g[1]; a.g_out[2 * n + i] = g[2]; }
-    if (a.do_adam) {
-      float bc1 = a.bc1, bc2s = a.bc2_sqrt;
-      if (a.step_ptr) { float st = (float)a.step_ptr[0]; bc1 = 1.f - powf(0.9f, st); bc2s = sqrtf(1.f - powf(0.999f, st)); }
-      f4 o = t;
-      for (int c = 0; c < 3; ++c) {
-        size_t k = c * n + i;
-        float m = 0.9f * a.m[k] + 0.1f * g[c];
-        float v = 0.999f * a.v[k] + 0.001f * g[c] * g[c];
-        a.m[k] = m; a.v[k] = v;
-        float upd = (a.lr / bc1) * m / (sqrtf(v) / bc2s + 1e-8f);
-        float ne = ex[c] - upd;
-        a.extra[k] = ne;
-        float base = chan(t, c) - ex[c];                                          // painted part
-        if (c == 0) o.x = base + ne; else if (c == 1) o.y = base + ne; else o.z = base + ne;
-      }
-      a.tex_new[i] = o;
+// A CTA covers a (256 x 2)-texel strip of level 0: a thread owns the texels (x, y) and (x, y + 1), so every warp access is a
+// full line of one texture row and a CTA streams 1 KB-contiguous pieces of each planar array (DRAM-page friendly; square tiles
+// measured 1.4-3x slower).  In one pass over the texture:
+//   * fold of the texel-gradient pyramid back to level 0 (box-filter adjoint, 1/4 per level),
+//   * total-variation + residual regularisers (tracker.py:526-539), Adam (tracker.py:210), level 0 of the OTHER pyramid,
+//   * level 1 of the new pyramid (2x2 box filter = own two texels + the neighbour lane's, same arithmetic as k_mip_down):
+//     the separate mip rebuild (render_nvdiffrast.py:399) starts from level 1 and never re-reads the 64 MB of level 0,
+//   * the last CTA to finish sums the per-CTA loss partials in a fixed order (deterministic loss value, no extra launch).
+struct TexelIn { f4 t; float ex[3], g[3], m[3], v[3]; };
+
+__device__ __forceinline__ void fold_load(const TexFoldArgs& a, int x, int y, bool l0, TexelIn& r) {
+  const int T = a.T;
+  const size_t n = (size_t)T * T, i = (size_t)y * T + x;
+  r.g[0] = r.g[1] = r.g[2] = 0.f;
+  if (a.g_pyr) {
+    float sc = l0 ? 1.f : 0.25f;
+    for (int l = l0 ? 0 : 1; l <= a.max_level; ++l) {
+      int s = T >> l;
+      const float* p = a.g_pyr + ((size_t)a.mip_off[l] + (size_t)(y >> l) * s + (x >> l)) * 4;
+      r.g[0] += p[0] * sc; r.g[1] += p[1] * sc; r.g[2] += p[2] * sc;
+      sc *= 0.25f;
     }
   }
-  // block partial sums of the two loss terms
-  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  r.t = a.tex_old[i];
+  for (int c = 0; c < 3; ++c) { r.ex[c] = a.extra[c * n + i]; if (a.do_adam) { r.m[c] = a.m[c * n + i]; r.v[c] = a.v[c * n + i]; } }
+}
+
+__device__ __forceinline__ f4 fold_texel(const TexFoldArgs& a, int x, int y, bool l0, TexelIn& r, const f4& tu, const f4& td, float bc1, float bc2s, float* acc) {
+  const int T = a.T;
+  const size_t n = (size_t)T * T, i = (size_t)y * T + x;
+  const f4 t = r.t;
+  if (a.g_pyr && l0) { float4* p0 = (float4*)(a.g_pyr + i * 4); *p0 = make_float4(0.f, 0.f, 0.f, 0.f); }   // coarser levels: memset after the kernel
+  if (a.w_tv > 0.f) {                                                          // tracker.py:526-534
+    f4 tr = x + 1 < T ? a.tex_old[i + 1] : t, tl = x > 0 ? a.tex_old[i - 1] : t;
+    for (int c = 0; c < 3; ++c) {
+      float v = chan(t, c), dr = v - chan(tr, c), dd = v - chan(td, c), dl = chan(tl, c) - v, du = chan(tu, c) - v;
+      acc[0] += a.w_tv * (dr * dr + dd * dd);                                  // each difference counted once (right, down)
+      r.g[c] += 2.f * a.w_tv * (dr + dd - dl - du);
+    }
+  }
+  if (a.w_res > 0.f && a.mask && a.mask[i]) {                                  // tracker.py:536-539
+    for (int c = 0; c < 3; ++c) { acc[1] += a.w_res * r.ex[c] * r.ex[c]; r.g[c] += 2.f * a.w_res * r.ex[c]; }
+  }
+  if (a.g_out) { a.g_out[i] = r.g[0]; a.g_out[n + i] = r.g[1]; a.g_out[2 * n + i] = r.g[2]; }
+  f4 o = t;
+  if (a.do_adam) {
+    for (int c = 0; c < 3; ++c) {
+      size_t k = c * n + i;
+      float m = 0.9f * r.m[c] + 0.1f * r.g[c];
+      float v = 0.999f * r.v[c] + 0.001f * r.g[c] * r.g[c];
+      a.m[k] = m; a.v[k] = v;
+      float upd = (a.lr / bc1) * m / (sqrtf(v) / bc2s + 1e-8f);
+      float ne = r.ex[c] - upd;
+      a.extra[k] = ne;
+      float base = chan(t, c) - r.ex[c];                                        // painted part
+      if (c == 0) o.x = base + ne; else if (c == 1) o.y = base + ne; else o.z = base + ne;
+    }
+    a.tex_new[i] = o;
+  }
+  return o;
+}
+
+__global__ void __launch_bounds__(256, 4) k_tex_fold(TexFoldArgs a, float* __restrict__ partials, unsigned* __restrict__ counter, float* __restrict__ acc_out) {
+  __shared__ float sh[8 * 2];
+  __shared__ bool is_last;
+  const int T = a.T, tw = T < 256 ? T : 256, tpr = T / tw;
+  const int tid = threadIdx.x;
+  const int x = (blockIdx.x % tpr) * tw + tid, y = (blockIdx.x / tpr) * 2;
+  float acc[2] = {0.f, 0.f};
+  const bool on = tid < tw;
+  f4 o0 = {0, 0, 0, 0}, o1 = {0, 0, 0, 0};
+  if (on) {
+    // level 0 of the gradient pyramid is only touched under magnification (mip level < 1); the backward pass raises
+    // l0_flag when it scatters there, otherwise the 16 B/texel read + re-zero of that level is skipped
+    const bool l0 = a.g_pyr ? (a.l0_flag ? (*a.l0_flag != 0) : true) : false;
+    float bc1 = a.bc1, bc2s = a.bc2_sqrt;
+    if (a.do_adam && a.step_ptr) { float st = (float)a.step_ptr[0]; bc1 = 1.f - powf(0.9f, st); bc2s = sqrtf(1.f - powf(0.999f, st)); }
+    TexelIn r0, r1;
+    fold_load(a, x, y, l0, r0);                     // all loads of both texels are issued before the first dependent store
+    fold_load(a, x, y + 1, l0, r1);
+    const size_t i0 = (size_t)y * T + x;
+    f4 tu = r0.t, td = r1.t;
+    if (a.w_tv > 0.f) { if (y > 0) tu = a.tex_old[i0 - T]; if (y + 2 < T) td = a.tex_old[i0 + 2 * (size_t)T]; }
+    o0 = fold_texel(a, x, y, l0, r0, tu, r1.t, bc1, bc2s, acc);
+    o1 = fold_texel(a, x, y + 1, l0, r1, r0.t, td, bc1, bc2s, acc);
+  }
+  // level 1 of the new pyramid: avg4(A[2y][2x], A[2y+1][2x], A[2y][2x+1], A[2y+1][2x+1]) with the right neighbour's pair
+  {
+    f4 c, d;
+    c.x = __shfl_down_sync(0xffffffffu, o0.x, 1); c.y = __shfl_down_sync(0xffffffffu, o0.y, 1); c.z = __shfl_down_sync(0xffffffffu, o0.z, 1);
+    d.x = __shfl_down_sync(0xffffffffu, o1.x, 1); d.y = __shfl_down_sync(0xffffffffu, o1.y, 1); d.z = __shfl_down_sync(0xffffffffu, o1.z, 1);
+    c.w = d.w = 0.f;
+    if (on && a.do_adam && a.max_level >= 1 && !(tid & 1))
+      a.tex_new[(size_t)a.mip_off[1] + (size_t)(y >> 1) * (T >> 1) + (x >> 1)] = avg4(o0, o1, c, d);
+  }
+  // block partial sums of the two loss terms; the last CTA reduces all partials in a fixed order
+  int lane = tid & 31, w = tid >> 5;
   for (int q = 0; q < 2; ++q) {
     float v = acc[q];
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (lane == 0) sh[w * 2 + q] = v;
   }
   __syncthreads();
-  if (threadIdx.x < 2) {
-    float s = 0.f;
-    for (int k = 0; k < 8; ++k) s += sh[k * 2 + threadIdx.x];
-    partials[(size_t)blockIdx.x * 2 + threadIdx.x] = s;
+  if (tid < 2) {
+    float s2 = 0.f;
+    for (int k = 0; k < 8; ++k) s2 += sh[k * 2 + tid];
+    partials[(size_t)blockIdx.x * 2 + tid] = s2;
+    __threadfence();
   }
-}
-
-__global__ void __launch_bounds__(1024) k_tex_loss_reduce(const float* __restrict__ partials, int rows, float* __restrict__ acc) {
-  __shared__ float sh[32];
+  __syncthreads();
+  if (tid == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
   for (int q = 0; q < 2; ++q) {
-    float s = 0.f;
-    for (int r = threadIdx.x; r < rows; r += blockDim.x) s += partials[(size_t)r * 2 + q];
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    float s2 = 0.f;
+    for (int r = tid; r < (int)gridDim.x; r += 256) s2 += __ldcg(partials + (size_t)r * 2 + q);
+    for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
     __syncthreads();
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    if (lane == 0) sh[w] = s2;
     __syncthreads();
-    if (threadIdx.x < 32) {
-      float t = sh[threadIdx.x];
-      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      if (threadIdx.x == 0) acc[q == 0 ? ACC_REG_TEX_TV : ACC_REG_TEX_RES] += t;
+    if (tid == 0) {
+      float t = 0.f;
+      for (int k = 0; k < 8; ++k) t += sh[k];
+      acc_out[q == 0 ? ACC_REG_TEX_TV : ACC_REG_TEX_RES] += t;
     }
   }
+  if (tid == 0) *counter = 0u;
 }
 
 void launch_tex_fold(vhap_ctx* c, float* tex_extra, float* g_out, float* m, float* v, float lr, int step, const vhap_stage_cfg* cfg,
@@ -189,14 +231,12 @@ void launch_tex_fold(vhap_ctx* c, float* tex_extra, float* g_out, float* m, floa
   a.w_res = (cfg->training && cfg->opt_texture && cfg->w_reg_tex_res >= 0.f) ? sh * cfg->w_reg_tex_res / (3.f * (float)T * (float)T) : 0.f;
   a.do_adam = (m != nullptr && v != nullptr) ? 1 : 0;
   a.lr = lr; a.bc1 = 1.f - powf(0.9f, (float)step); a.bc2_sqrt = sqrtf(1.f - powf(0.999f, (float)step));
-  size_t n = (size_t)T * T;
-  int nblk = (int)((n + 255) / 256);
-  LAUNCH(c, KID_TEX_FOLD, s, k_tex_fold<<<nblk, 256, 0, s>>>(a, c->tv_partials));
-  LAUNCH(c, KID_TEX_LOSS, s, k_tex_loss_reduce<<<1, 1024, 0, s>>>(c->tv_partials, nblk, c->acc));
+  int tw = T < 256 ? T : 256, nblk = (T / tw) * (T / 2), L = c->max_level >= 1 ? 1 : 0;
+  LAUNCH(c, KID_TEX_FOLD, s, k_tex_fold<<<nblk, 256, 0, s>>>(a, c->tv_partials, c->tex_counter, c->acc));
   cudaMemsetAsync(c->tex_l0_flag, 0, sizeof(int), s);
   if (c->g_tex && c->max_level >= 1)                                      // coarser gradient levels
     cudaMemsetAsync(c->g_tex + (size_t)c->mip_off[1] * 4, 0, (c->mip_total - c->mip_off[1]) * 4 * sizeof(float), s);
-  if (a.do_adam) { c->cur_mip ^= 1; build_mips(c, c->mips[c->cur_mip], s); }
+  if (a.do_adam) { c->cur_mip ^= 1; build_mips(c, c->mips[c->cur_mip], s, L); }    // levels 1..L were written by the fold kernel
 }
 
 __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,

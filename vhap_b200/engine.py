@@ -306,16 +306,12 @@ class Engine:
         if opt["pose"]: groups += ["rotation", "translation"]
         if opt["joints"]: groups += ["neck_pose", "jaw_pose", "eyes_pose"]
         cs = self._c_stage(True)
-        if opt["texture"]:
-            if allreduce_fn is None:
-                self._ck(self.L.vhap_tex_reg_fold_adam(self.ctx, self.tex_extra.data_ptr(), None, self.tex_m.data_ptr(), self.tex_v.data_ptr(),
-                                                       self._lr("tex"), self.step_count, C.byref(cs), 1.0, self.losses.data_ptr(), s), None)
-            else:
-                g = self.texture_grad_dense()
-                allreduce_fn(g)
-                self._ck(self.L.vhap_adam(self.ctx, self.tex_extra.data_ptr(), g.data_ptr(), self.tex_m.data_ptr(), self.tex_v.data_ptr(),
-                                          g.numel(), self._lr("tex"), self.step_count, s), None)
-                self.rebuild_texture()
+        if opt["texture"] and allreduce_fn is not None:
+            g = self.texture_grad_dense()
+            allreduce_fn(g)
+            self._ck(self.L.vhap_adam(self.ctx, self.tex_extra.data_ptr(), g.data_ptr(), self.tex_m.data_ptr(), self.tex_v.data_ptr(),
+                                      g.numel(), self._lr("tex"), self.step_count, s), None)
+            self.rebuild_texture()
         if allreduce_fn is not None:
             allreduce_fn(self.grad)
         if groups:
@@ -325,6 +321,11 @@ class Engine:
             hp = lambda a: a.ctypes.data_as(C.c_void_p)
             self._ck(self.L.vhap_adam_multi(self.ctx, self.slab.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                                             len(groups), hp(off), hp(ln), hp(lr), self.step_count, s), None)
+        if opt["texture"] and allreduce_fn is None:
+            # issued last: the fold / Adam / mip rebuild itself runs on an aux stream right behind the fused backward
+            # (vhap_tex_reg_fold_adam waits only for the texel-gradient event); here only its join and the loss bookkeeping follow
+            self._ck(self.L.vhap_tex_reg_fold_adam(self.ctx, self.tex_extra.data_ptr(), None, self.tex_m.data_ptr(), self.tex_v.data_ptr(),
+                                                   self._lr("tex"), self.step_count, C.byref(cs), 1.0, self.losses.data_ptr(), s), None)
 
     def step(self, batch: Batch) -> torch.Tensor:
         """One optimisation iteration (tracker.py:1418-1435): zero_grad, energy + backward, Adam."""
