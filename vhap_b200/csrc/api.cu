@@ -220,7 +220,7 @@ extern "C" int vhap_ctx_reserve(vhap_ctx* ctx, int32_t B, int32_t H, int32_t W) 
   ctx->pool_nblk = nblk;
   UP(ctx->pool_blk_count, (const int*)nullptr, (size_t)16 * nblk); UP(ctx->pool_blk_off, (const int*)nullptr, (size_t)16 * nblk);
   ctx->n_partials_rows = nblk;
-  UP(ctx->partials, (const float*)nullptr, (size_t)nblk * VH_NPART);
+  UP(ctx->partials, (const float*)nullptr, (size_t)nblk * 4 * VH_NPART);        // x4: kernels with smaller CTAs use proportionally more rows
   ctx->maxB = B; ctx->maxH = H; ctx->maxW = W;
   return 0;
 }

@@ -25,7 +25,14 @@ struct RenderArgs {
   const float* ndc;           // optional [B,V,2] = clip.xy / clip.w (saves the divisions in the antialias analysis)
   const float* zwbuf;         // optional [B,H,W,4]: .w of foreground pixels holds their z/w (written by pass A)
   int* tex_l0_flag;           // optional: raised when the backward scatters into level 0 of the texel-gradient pyramid
+  int pow2, wshift, hshift;   // pow2 != 0: W = 1 << wshift, H = 1 << hshift (pixel index -> (b,y,x) without integer divisions)
 };
+
+// flat pixel index (b*H + y)*W + x -> (b, y, x)
+VH_HD void vh_unflatten(const RenderArgs& A, int pix, int& b, int& y, int& x) {
+  if (A.pow2) { x = pix & (A.W - 1); y = (pix >> A.wshift) & (A.H - 1); b = pix >> (A.wshift + A.hshift); }
+  else { x = pix % A.W; y = (pix / A.W) % A.H; b = pix / (A.W * A.H); }
+}
 
 struct TriSetup {
   int vi[3];

@@ -20,7 +20,7 @@ __device__ __forceinline__ float warp_sum_r(float v) {
 }
 
 // reduce N per-thread values across the block and write them to row[0..N); sh must hold 8*N floats (256 threads)
-template <int N>
+template <int N, int NT = PB>
 __device__ void block_reduce_store(float* vals, float* sh, float* row) {
   int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
@@ -28,7 +28,7 @@ __device__ void block_reduce_store(float* vals, float* sh, float* row) {
   __syncthreads();
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
     float s = 0.f;
-    for (int k = 0; k < PB / 32; ++k) s += sh[k * N + i];
+    for (int k = 0; k < NT / 32; ++k) s += sh[k * N + i];
     row[i] = s;
   }
 }
@@ -118,12 +118,26 @@ __global__ void __launch_bounds__(PB) k_aa_pairs(PassArgs P, const int* __restri
   int n = *pair_count;
   for (int i = blockIdx.x * PB + threadIdx.x; i < n; i += gridDim.x * PB) {
     int pr = pair_list[i], pix = pr >> 1, d = pr & 1;
-    int x = pix % A.W, y = (pix / A.W) % A.H, b = pix / (A.W * A.H);
+    int x, y, b; vh_unflatten(A, pix, b, y, x);
     aa_pair_body(P, b, y, x, d);
   }
 }
 
-__global__ void __launch_bounds__(PB) k_passA(PassArgs P, float* __restrict__ partials, unsigned long long* __restrict__ maxslot) {
+// resident CTAs per SM the register allocation is tuned for (measured on B200, tools/ab_variants.sh): these passes are bound by
+// the latency of dependent gathers, so pass B trades a few spilled registers for full occupancy (0.117 -> 0.093 ms), the colour
+// adjoint runs best at 4 CTAs (64 registers), the shading adjoint at 2 (128 registers; 3 was 25% slower), pass A unconstrained.
+#ifndef VH_B_MIN
+#define VH_B_MIN 8
+#endif
+#ifndef VH_C1_MIN
+#define VH_C1_MIN 4
+#endif
+#ifdef VH_A_MIN
+__global__ void __launch_bounds__(PB, VH_A_MIN) k_passA(
+#else
+__global__ void __launch_bounds__(PB) k_passA(
+#endif
+    PassArgs P, float* __restrict__ partials, unsigned long long* __restrict__ maxslot) {
   __shared__ float sh[8 * 2];
   __shared__ unsigned long long shm[8];
   const RenderArgs& A = P.R;
@@ -133,7 +147,7 @@ __global__ void __launch_bounds__(PB) k_passA(PassArgs P, float* __restrict__ pa
   float acc[2] = {0.f, 0.f}; float mx = -INFINITY; int mxi = 0;
   for (int i = blockIdx.x * PB + threadIdx.x; i < n_fg; i += gridDim.x * PB) {
     int pix = list[i], id = tris[i];
-    int x = pix % A.W, y = (pix / A.W) % A.H, b = pix / (A.W * A.H);
+    int x, y, b; vh_unflatten(A, pix, b, y, x);
     passA_body(P, b, y, x, acc, mx, mxi, id);
   }
   block_reduce_store<2>(acc, sh, partials + (size_t)blockIdx.x * VH_NPART);
@@ -147,26 +161,26 @@ __global__ void __launch_bounds__(PB) k_passA(PassArgs P, float* __restrict__ pa
   }
 }
 
-__global__ void __launch_bounds__(PB) k_passB(PassArgs P, float* __restrict__ partials) {
+__global__ void __launch_bounds__(PB, VH_B_MIN) k_passB(PassArgs P, float* __restrict__ partials) {
   __shared__ float sh[8 * 2];
   const RenderArgs& A = P.R;
   int n = A.B * A.H * A.W;
   float acc[2] = {0.f, 0.f};
   for (int pix = blockIdx.x * PB + threadIdx.x; pix < n; pix += gridDim.x * PB) {
-    int x = pix % A.W, y = (pix / A.W) % A.H, b = pix / (A.W * A.H);
+    int x, y, b; vh_unflatten(A, pix, b, y, x);
     passB_body(P, b, y, x, acc);
   }
   block_reduce_store<2>(acc, sh, partials + (size_t)blockIdx.x * VH_NPART + 2);
 }
 
-__global__ void __launch_bounds__(PB) k_passC1(PassArgs P, const float* __restrict__ ext_grad, f4* __restrict__ grgb) {
+__global__ void __launch_bounds__(PB, VH_C1_MIN) k_passC1(PassArgs P, const float* __restrict__ ext_grad, f4* __restrict__ grgb) {
   const RenderArgs& A = P.R;
   int n_fg = A.B * A.H * A.W - P.pool_count[0];
   const int* list = P.pool_list + P.pool_base[1];
   const int* tris = P.pool_tri + P.pool_base[1];
   for (int i = blockIdx.x * PB + threadIdx.x; i < n_fg; i += gridDim.x * PB) {
     int pix = list[i], id = tris[i];
-    int x = pix % A.W, y = (pix / A.W) % A.H, b = pix / (A.W * A.H);
+    int x, y, b; vh_unflatten(A, pix, b, y, x);
     f3 g = passC1_body(P, b, y, x, ext_grad, id);
     f4 o = {g.x, g.y, g.z, 0.f};
     grgb[i] = o;                                    // indexed by list position: coalesced
@@ -176,8 +190,11 @@ __global__ void __launch_bounds__(PB) k_passC1(PassArgs P, const float* __restri
 #ifndef VH_C2_MINBLOCKS
 #define VH_C2_MINBLOCKS 2
 #endif
-__global__ void __launch_bounds__(PB, VH_C2_MINBLOCKS) k_passC2(PassArgs P, const f4* __restrict__ grgb, float* __restrict__ partials) {
-  __shared__ float sh[8 * 27];
+#ifndef VH_C2_PB
+#define VH_C2_PB 256
+#endif
+__global__ void __launch_bounds__(VH_C2_PB, VH_C2_MINBLOCKS) k_passC2(PassArgs P, const f4* __restrict__ grgb, float* __restrict__ partials) {
+  __shared__ float sh[(VH_C2_PB / 32) * 27];
   const RenderArgs& A = P.R;
   int n_fg = A.B * A.H * A.W - P.pool_count[0];
   const int* list = P.pool_list + P.pool_base[1];
@@ -185,13 +202,13 @@ __global__ void __launch_bounds__(PB, VH_C2_MINBLOCKS) k_passC2(PassArgs P, cons
 #pragma unroll
   for (int i = 0; i < 27; ++i) gl[i] = 0.f;
   const int* tris = P.pool_tri + P.pool_base[1];
-  for (int i = blockIdx.x * PB + threadIdx.x; i < n_fg; i += gridDim.x * PB) {
+  for (int i = blockIdx.x * VH_C2_PB + threadIdx.x; i < n_fg; i += gridDim.x * VH_C2_PB) {
     int pix = list[i], id = tris[i];
-    int x = pix % A.W, y = (pix / A.W) % A.H, b = pix / (A.W * A.H);
+    int x, y, b; vh_unflatten(A, pix, b, y, x);
     f4 g = grgb[i];
     passC2_body(P, b, y, x, mk3(g.x, g.y, g.z), gl, id);
   }
-  block_reduce_store<27>(gl, sh, partials + (size_t)blockIdx.x * VH_NPART + 4);
+  block_reduce_store<27, VH_C2_PB>(gl, sh, partials + (size_t)blockIdx.x * VH_NPART + 4);
 }
 
 // column sums of the [rows][VH_NPART] partial matrix: dst[slot ? slot[c] : c] += sum_r partials[r][col0 + c]
@@ -286,6 +303,11 @@ void fill_render_args(vhap_ctx* c, PassArgs& P, const vhap_frame_batch* fb, cons
   memset(&P, 0, sizeof(P));
   RenderArgs& A = P.R;
   A.B = fb->B; A.H = fb->H; A.W = fb->W; A.V = c->V; A.F = c->F; A.T = c->T; A.max_level = c->max_level;
+  if ((A.W & (A.W - 1)) == 0 && (A.H & (A.H - 1)) == 0) {
+    A.pow2 = 1;
+    while ((1 << A.wshift) < A.W) ++A.wshift;
+    while ((1 << A.hshift) < A.H) ++A.hshift;
+  }
   A.faces = c->faces; A.faces_uv = c->faces_uv; A.verts_uv = c->verts_uv; A.clip = c->clip; A.vnorm = c->vnorm; A.lights = lights;
   A.mips = c->mips[c->cur_mip];
   for (int i = 0; i < VH_MAX_MIPS; ++i) A.mip_off[i] = c->mip_off[i];
@@ -353,6 +375,7 @@ void launch_render_backward(vhap_ctx* c, PassArgs& P, const vhap_stage_cfg* cfg,
   int nblk = (int)((n + PB - 1) / PB);
   int grid = nblk < NPERSIST ? nblk : NPERSIST;
   LAUNCH(c, KID_PASSC1, s, k_passC1<<<grid, PB, 0, s>>>(P, ext_grad, c->grgb));
-  LAUNCH(c, KID_PASSC, s, k_passC2<<<grid, PB, 0, s>>>(P, c->grgb, c->partials));
-  if (g_lights) LAUNCH(c, KID_LIGHTS_REDUCE, s, k_reduce_cols<<<16, 256, 0, s>>>(c->partials, grid, 4, 27, g_lights, nullptr));
+  int grid2 = grid * (PB / VH_C2_PB);
+  LAUNCH(c, KID_PASSC, s, k_passC2<<<grid2, VH_C2_PB, 0, s>>>(P, c->grgb, c->partials));
+  if (g_lights) LAUNCH(c, KID_LIGHTS_REDUCE, s, k_reduce_cols<<<16, 256, 0, s>>>(c->partials, grid2, 4, 27, g_lights, nullptr));
 }

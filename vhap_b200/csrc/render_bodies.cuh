@@ -111,9 +111,9 @@ VH_HD f4 disturbed_color(const PassArgs& P, int b, int y, int x, int id, float* 
   int idx = (int)(u * (float)n);
   if (idx > n - 1) idx = n - 1;
   int q = P.pool_list[P.pool_base[cid] + idx];
-  int qx = q % A.W, qy = (q / A.W) % A.H, qb = q / (A.W * A.H);
+  int qx, qy, qb; vh_unflatten(A, q, qb, qy, qx);
   if (own_weight) *own_weight = 0.f;
-  return pre_color(P, qb, qy, qx, A.tri_id[q]);
+  return pre_color(P, qb, qy, qx, cid > 0 ? 1 : 0);     // a pool of cluster cid >= 1 holds foreground pixels only, cluster 0 background only
 }
 
 // ------------------------------------------------------------------------------------------ antialias pair analysis

@@ -95,19 +95,12 @@ __device__ __forceinline__ float chan(const f4& t, int c) { return c == 0 ? t.x 
 //   * the last CTA to finish sums the per-CTA loss partials in a fixed order (deterministic loss value, no extra launch).
 struct TexelIn { f4 t; float ex[3], g[3], m[3], v[3]; };
 
-__device__ __forceinline__ void fold_load(const TexFoldArgs& a, int x, int y, bool l0, TexelIn& r) {
+// coarse = folded gradient of the levels >= 1 above this texel (shared memory, one entry per level-1 texel of the strip)
+__device__ __forceinline__ void fold_load(const TexFoldArgs& a, int x, int y, bool l0, const float* coarse, TexelIn& r) {
   const int T = a.T;
   const size_t n = (size_t)T * T, i = (size_t)y * T + x;
-  r.g[0] = r.g[1] = r.g[2] = 0.f;
-  if (a.g_pyr) {
-    float sc = l0 ? 1.f : 0.25f;
-    for (int l = l0 ? 0 : 1; l <= a.max_level; ++l) {
-      int s = T >> l;
-      const float* p = a.g_pyr + ((size_t)a.mip_off[l] + (size_t)(y >> l) * s + (x >> l)) * 4;
-      r.g[0] += p[0] * sc; r.g[1] += p[1] * sc; r.g[2] += p[2] * sc;
-      sc *= 0.25f;
-    }
-  }
+  r.g[0] = coarse[0]; r.g[1] = coarse[1]; r.g[2] = coarse[2];
+  if (l0) { float4 g0 = *(const float4*)(a.g_pyr + i * 4); r.g[0] += g0.x; r.g[1] += g0.y; r.g[2] += g0.z; }
   r.t = a.tex_old[i];
   for (int c = 0; c < 3; ++c) { r.ex[c] = a.extra[c * n + i]; if (a.do_adam) { r.m[c] = a.m[c * n + i]; r.v[c] = a.v[c * n + i]; } }
 }
@@ -149,10 +142,27 @@ __device__ __forceinline__ f4 fold_texel(const TexFoldArgs& a, int x, int y, boo
 
 __global__ void __launch_bounds__(256, 4) k_tex_fold(TexFoldArgs a, float* __restrict__ partials, unsigned* __restrict__ counter, float* __restrict__ acc_out) {
   __shared__ float sh[8 * 2];
+  __shared__ float coarse[128][3];
   __shared__ bool is_last;
   const int T = a.T, tw = T < 256 ? T : 256, tpr = T / tw;
   const int tid = threadIdx.x;
-  const int x = (blockIdx.x % tpr) * tw + tid, y = (blockIdx.x / tpr) * 2;
+  const int x0 = (blockIdx.x % tpr) * tw, x = x0 + tid, y = (blockIdx.x / tpr) * 2;
+  // photometric gradient of the pyramid levels >= 1 folded down to the strip's level-1 texels (box-filter adjoint: 1/4 per
+  // level), once per level-1 texel instead of once per texel: one float4 load per level for 128 threads
+  if (tid < (tw >> 1)) {
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+    if (a.g_pyr) {
+      float sc = 0.25f;
+      const int x1 = (x0 >> 1) + tid, y1 = y >> 1;
+      for (int l = 1; l <= a.max_level; ++l) {
+        float4 p = *(const float4*)(a.g_pyr + ((size_t)a.mip_off[l] + (size_t)(y1 >> (l - 1)) * (T >> l) + (x1 >> (l - 1))) * 4);
+        g0 += p.x * sc; g1 += p.y * sc; g2 += p.z * sc;
+        sc *= 0.25f;
+      }
+    }
+    coarse[tid][0] = g0; coarse[tid][1] = g1; coarse[tid][2] = g2;
+  }
+  __syncthreads();
   float acc[2] = {0.f, 0.f};
   const bool on = tid < tw;
   f4 o0 = {0, 0, 0, 0}, o1 = {0, 0, 0, 0};
@@ -163,8 +173,8 @@ __global__ void __launch_bounds__(256, 4) k_tex_fold(TexFoldArgs a, float* __res
     float bc1 = a.bc1, bc2s = a.bc2_sqrt;
     if (a.do_adam && a.step_ptr) { float st = (float)a.step_ptr[0]; bc1 = 1.f - powf(0.9f, st); bc2s = sqrtf(1.f - powf(0.999f, st)); }
     TexelIn r0, r1;
-    fold_load(a, x, y, l0, r0);                     // all loads of both texels are issued before the first dependent store
-    fold_load(a, x, y + 1, l0, r1);
+    fold_load(a, x, y, l0, coarse[tid >> 1], r0);   // all loads of both texels are issued before the first dependent store
+    fold_load(a, x, y + 1, l0, coarse[tid >> 1], r1);
     const size_t i0 = (size_t)y * T + x;
     f4 tu = r0.t, td = r1.t;
     if (a.w_tv > 0.f) { if (y > 0) tu = a.tex_old[i0 - T]; if (y + 2 < T) td = a.tex_old[i0 + 2 * (size_t)T]; }
