@@ -190,6 +190,12 @@ int vhap_tex_rebuild(vhap_ctx* ctx, const float* tex_extra /*[3,T,T]*/, void* st
  * if adam_m/adam_v given, applies one Adam step in place to tex_extra and rebuilds the pyramid in the same pass. */
 int vhap_tex_reg_fold_adam(vhap_ctx* ctx, float* tex_extra, float* g_out, float* adam_m, float* adam_v,
                            float lr, int32_t step, const vhap_stage_cfg* cfg, float photo_scale, float* losses_out, void* stream);
+/* data parallel: Adam + pyramid rebuild from the dense gradient produced by vhap_tex_reg_fold_adam(g_out) and summed across ranks */
+int vhap_tex_apply_grad(vhap_ctx* ctx, float* tex_extra, const float* g_dense, float* adam_m, float* adam_v, float lr, int32_t step,
+                        const vhap_stage_cfg* cfg, void* stream);
+/* on != 0: g_out of vhap_tex_reg_fold_adam is a persistent buffer only read after the call returns -> the fold may overlap the
+ * geometry backward on the library's aux stream */
+int vhap_set_tex_grad_persistent(vhap_ctx* ctx, int32_t on);
 
 /* ---- per-kernel accounting: every kernel launch is counted; with profiling enabled CUDA events bracket each launch on the
  *      launching stream (used by bench.py to measure the dominant kernel live inside its timed region) --------------- */

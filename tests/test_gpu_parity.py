@@ -142,9 +142,28 @@ def _oracle_energy(sc, stage, disturbance, P):
 
 @pytest.mark.parametrize("stage_name", ["rgb_global_tracking", "rgb_init_all", "lmk_init_all", None])
 def test_energy_and_gradients(eng_small, stage_name):
+    _check_energy_and_gradients(eng_small, stage_name)
+
+
+@pytest.fixture(scope="module")
+def eng_pow2():
+    from vhap_b200.engine import Engine
+    sc = make_scene(B=2, H=64, W=128, T=128, n_t=3, timesteps=[0, 2])
+    e = Engine(sc["m"], sc["cfg"], 3, tex_painted=sc["tex_painted"])
+    e.load_params(sc["params"])
+    yield e, sc
+    e.close()
+
+
+def test_energy_and_gradients_power_of_two_image(eng_pow2):
+    """power-of-two image sizes take the shift/mask pixel-index path of the per-pixel passes (the bench sizes 512 / 1024)"""
+    _check_energy_and_gradients(eng_pow2, "rgb_global_tracking")
+
+
+def _check_energy_and_gradients(eng, stage_name):
     from vhap_b200.config import STAGES
     from vhap_b200 import _lib
-    e, sc = eng_small
+    e, sc = eng
     stage = STAGES[stage_name] if stage_name else None
     P = _oracle_params(sc)
     dist = dict(w_fg=sc["w_fg"], w_bg=sc["w_bg"], u_rand=sc["u_rand"])
@@ -267,3 +286,31 @@ def test_graph_replay_matches_eager(eng_small):
         noise = rel(res[1][k], res[0][k])
         # a broken replay (stuck Adam / RNG step counter, wrong texture ping-pong parity) changes the trajectory by O(1e-1)
         assert rel(res[2][k], res[0][k]) < 10 * noise + 1e-3, (k, rel(res[2][k], res[0][k]), noise)
+
+
+def test_data_parallel_texture_path_matches_fused(eng_small):
+    """world_size 1 with an identity 'all-reduce': the data-parallel update (dense gradient -> reduce -> vhap_tex_apply_grad, gradient slab
+    reduce -> Adam) must reproduce the fused single-GPU step (same texture, same mip pyramid seen by the next forward)"""
+    from vhap_b200.parallel import DataParallelStep
+    e, sc = eng_small
+    batch = e.stage_sample(sc["rgb16"].to(torch.float32), sc["lmk2d"], sc["ts"])
+    res = []
+    for mode in ("fused", "dp"):
+        e.load_params(sc["params"])
+        e.set_stage("rgb_global_tracking")
+        e.inject_random(None, None, None)
+        e.global_step = 3
+        for i in range(2):
+            if mode == "fused":
+                e.step(batch)
+            else:
+                e.zero_grad()
+                e.energy(batch, backward=True, training=True, global_B=batch.B, reduce_fn=lambda a, b: b.copy_(a))
+                e.adam_step(allreduce_fn=lambda t: None)
+                e.global_step += 1
+        losses = e.energy(batch, backward=False, training=True).clone()      # forward through the rebuilt pyramid
+        torch.cuda.synchronize()
+        res.append(({k: v.copy() for k, v in e.get_params().items()}, losses.cpu().numpy()))
+    for k in res[0][0]:
+        assert rel(res[1][0][k], res[0][0][k]) < 2e-3, (k, rel(res[1][0][k], res[0][0][k]))
+    assert abs(res[1][1][0] - res[0][1][0]) < 1e-3 * abs(res[0][1][0])

@@ -494,8 +494,9 @@ extern "C" int vhap_tex_reg_fold_adam(vhap_ctx* ctx, float* tex_extra, float* g_
                                       const vhap_stage_cfg* cfg, float photo_scale, float* losses_out, void* stream) {
   (void)photo_scale;
   cudaStream_t s = (cudaStream_t)stream;
-  if (ctx->tex_fork_pending && g_out == nullptr && !ctx->no_overlap) {
-    // (with a caller-owned dense output the call stays on the caller's stream: ordering w.r.t. the caller's own work on g_out)
+  if (ctx->tex_fork_pending && (g_out == nullptr || ctx->tex_gout_persistent) && !ctx->no_overlap) {
+    // (with a caller-owned dense output the call stays on the caller's stream -- ordering w.r.t. the caller's own work on g_out --
+    // unless the caller declared the buffer persistent and untouched outside this library's calls, vhap_set_tex_grad_persistent)
     // the texture fold / Adam / mip rebuild only depends on the texel gradients (event 2, recorded right after the fused
     // backward): run it on aux stream 1 concurrently with the geometry backward that was enqueued after that event, then join
     ctx->tex_fork_pending = 0;
@@ -514,6 +515,20 @@ extern "C" int vhap_tex_reg_fold_adam(vhap_ctx* ctx, float* tex_extra, float* g_
   LAST();
   return 0;
 }
+
+// Data-parallel texture update: Adam from a dense, already folded + regularised + all-reduced gradient (the g_out of
+// vhap_tex_reg_fold_adam), then level 0 / level 1 of the other pyramid in the same pass and the remaining mip levels.
+extern "C" int vhap_tex_apply_grad(vhap_ctx* ctx, float* tex_extra, const float* g_dense, float* adam_m, float* adam_v, float lr, int32_t step,
+                                   const vhap_stage_cfg* cfg, void* stream) {
+  ctx->tex_apply_grad = g_dense;
+  launch_tex_fold(ctx, tex_extra, nullptr, adam_m, adam_v, lr, step, cfg, nullptr, (cudaStream_t)stream);
+  ctx->tex_apply_grad = nullptr;
+  LAST();
+  return 0;
+}
+// on != 0: the g_out buffer passed to vhap_tex_reg_fold_adam is persistent and only read by the caller AFTER that call returns
+// (on the same stream): the fold may then run on the aux stream beside the geometry backward, like the fused single-GPU update
+extern "C" int vhap_set_tex_grad_persistent(vhap_ctx* ctx, int32_t on) { ctx->tex_gout_persistent = on; return 0; }
 
 extern "C" int vhap_adam(vhap_ctx* ctx, float* param, const float* grad, float* m, float* v, int64_t n, float lr, int32_t step, void* stream) {
   launch_adam(ctx, param, grad, m, v, n, lr, step, (cudaStream_t)stream);

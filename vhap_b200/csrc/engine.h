@@ -60,6 +60,7 @@ struct vhap_ctx {
   unsigned long long* scan_state;                 // [VH_SCAN_MAX_BLOCKS + 1] look-back words + ticket of the single-launch scan
   int* pool_tri;                                  // rasterised id per pool_list entry
   int* tex_l0_flag;                               // [1]
+  const float* tex_apply_grad; int tex_gout_persistent;   // see vhap_tex_apply_grad / vhap_set_tex_grad_persistent
   unsigned* tex_counter;                          // [1] CTA completion counter of the texture fold kernel (self-resetting)
   cudaStream_t aux[2]; cudaStream_t hp[2]; cudaEvent_t ev[12];   // hp: highest-priority streams for the latency-critical geometry backward
   int tex_fork_pending, no_overlap;   // fork/join of independent kernel chains

@@ -75,6 +75,7 @@ struct TexFoldArgs {
   int T, max_level; int mip_off[VH_MAX_MIPS];
   const f4* tex_old; f4* tex_new; float* g_pyr;
   float* extra; float* g_out; float* m; float* v;
+  const float* g_in;            // optional dense [3,T,T] gradient that REPLACES the folded one (data parallel: the all-reduced gradient)
   const uint8_t* mask;
   float w_tv, w_res;            // already divided by their mean() denominators and scaled by shared_scale
   float lr, bc1, bc2_sqrt;      // Adam: step size lr/bc1, sqrt(bias correction 2)
@@ -101,6 +102,7 @@ __device__ __forceinline__ void fold_load(const TexFoldArgs& a, int x, int y, bo
   const size_t n = (size_t)T * T, i = (size_t)y * T + x;
   r.g[0] = coarse[0]; r.g[1] = coarse[1]; r.g[2] = coarse[2];
   if (l0) { float4 g0 = *(const float4*)(a.g_pyr + i * 4); r.g[0] += g0.x; r.g[1] += g0.y; r.g[2] += g0.z; }
+  if (a.g_in) { r.g[0] = a.g_in[i]; r.g[1] = a.g_in[n + i]; r.g[2] = a.g_in[2 * n + i]; }
   r.t = a.tex_old[i];
   for (int c = 0; c < 3; ++c) { r.ex[c] = a.extra[c * n + i]; if (a.do_adam) { r.m[c] = a.m[c * n + i]; r.v[c] = a.v[c * n + i]; } }
 }
@@ -234,15 +236,22 @@ void launch_tex_fold(vhap_ctx* c, float* tex_extra, float* g_out, float* m, floa
   a.T = T; a.max_level = c->max_level;
   for (int i = 0; i < VH_MAX_MIPS; ++i) a.mip_off[i] = c->mip_off[i];
   a.tex_old = c->mips[c->cur_mip]; a.tex_new = c->mips[c->cur_mip ^ 1]; a.g_pyr = c->g_tex;
-  a.extra = tex_extra; a.g_out = g_out; a.m = m; a.v = v; a.mask = c->uvmask_res; a.l0_flag = c->tex_l0_flag; a.step_ptr = c->use_dev_step ? c->dev_step : nullptr;
+  a.extra = tex_extra; a.g_out = g_out; a.m = m; a.v = v; a.g_in = c->tex_apply_grad;
+  if (a.g_in) a.g_pyr = nullptr;                       // apply mode: gradient already folded, regularised and reduced across ranks
+  a.mask = c->uvmask_res; a.l0_flag = c->tex_l0_flag; a.step_ptr = c->use_dev_step ? c->dev_step : nullptr;
   float sh = cfg->shared_scale;
   // tv.mean(): (T-1)*T elements per channel, 3 channels (tracker.py:529-533); w already includes scale_factor^2 / ds^2
   a.w_tv = (cfg->training && cfg->opt_texture && cfg->w_reg_tex_tv >= 0.f) ? sh * cfg->w_reg_tex_tv / (3.f * (float)(T - 1) * (float)T) : 0.f;
   a.w_res = (cfg->training && cfg->opt_texture && cfg->w_reg_tex_res >= 0.f) ? sh * cfg->w_reg_tex_res / (3.f * (float)T * (float)T) : 0.f;
+  if (a.g_in) { a.w_tv = 0.f; a.w_res = 0.f; }
   a.do_adam = (m != nullptr && v != nullptr) ? 1 : 0;
   a.lr = lr; a.bc1 = 1.f - powf(0.9f, (float)step); a.bc2_sqrt = sqrtf(1.f - powf(0.999f, (float)step));
   int tw = T < 256 ? T : 256, nblk = (T / tw) * (T / 2), L = c->max_level >= 1 ? 1 : 0;
   LAUNCH(c, KID_TEX_FOLD, s, k_tex_fold<<<nblk, 256, 0, s>>>(a, c->tv_partials, c->tex_counter, c->acc));
+  if (a.g_in) {                                                           // apply mode leaves the gradient pyramid alone
+    if (a.do_adam) { c->cur_mip ^= 1; build_mips(c, c->mips[c->cur_mip], s, L); }
+    return;
+  }
   cudaMemsetAsync(c->tex_l0_flag, 0, sizeof(int), s);
   if (c->g_tex && c->max_level >= 1)                                      // coarser gradient levels
     cudaMemsetAsync(c->g_tex + (size_t)c->mip_off[1] * 4, 0, (c->mip_total - c->mip_off[1]) * 4 * sizeof(float), s);

@@ -282,6 +282,8 @@ class Engine:
         """Folds the texel-gradient pyramid (+ TV / residual regularisers) into a dense [3,T,T] gradient (no Adam)."""
         if self.tex_grad_dense is None:
             self.tex_grad_dense = torch.zeros(3 * self.T * self.T, dtype=torch.float32, device=self.dev)
+            torch.cuda.current_stream(self.dev).synchronize()       # the zero fill must not race the library's aux stream
+            self.L.vhap_set_tex_grad_persistent(self.ctx, 1)        # persistent from here on: the fold may leave the caller's stream
         cs = self._c_stage(training)
         self._ck(self.L.vhap_tex_reg_fold_adam(self.ctx, self.tex_extra.data_ptr(), self.tex_grad_dense.data_ptr(), None, None, 0.0, 1,
                                                C.byref(cs), 1.0, self.losses.data_ptr(), self._stream()), None)
@@ -307,11 +309,10 @@ class Engine:
         if opt["joints"]: groups += ["neck_pose", "jaw_pose", "eyes_pose"]
         cs = self._c_stage(True)
         if opt["texture"] and allreduce_fn is not None:
-            g = self.texture_grad_dense()
+            g = self.texture_grad_dense()                  # fold + regularisers; runs beside the geometry backward (aux stream)
             allreduce_fn(g)
-            self._ck(self.L.vhap_adam(self.ctx, self.tex_extra.data_ptr(), g.data_ptr(), self.tex_m.data_ptr(), self.tex_v.data_ptr(),
-                                      g.numel(), self._lr("tex"), self.step_count, s), None)
-            self.rebuild_texture()
+            self._ck(self.L.vhap_tex_apply_grad(self.ctx, self.tex_extra.data_ptr(), g.data_ptr(), self.tex_m.data_ptr(), self.tex_v.data_ptr(),
+                                                self._lr("tex"), self.step_count, C.byref(cs), s), None)
         if allreduce_fn is not None:
             allreduce_fn(self.grad)
         if groups:
