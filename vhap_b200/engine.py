@@ -82,6 +82,11 @@ class Engine:
         self.slab, self.grad, self.m, self.v = z(off), z(off), z(off), z(off)
         nt = 3 * self.T * self.T
         self.tex_extra, self.tex_m, self.tex_v, self.tex_grad_dense = z(nt), z(nt), z(nt), None
+        self._dp_buf = None
+        if world_size > 1:
+            # data parallel: the dense texture gradient and the gradient slab live in ONE buffer -> one all-reduce per step
+            self._dp_buf = z(nt + off)
+            self.tex_grad_dense, self.grad = self._dp_buf[:nt], self._dp_buf[nt:]
         self.p = {k: self.slab[o:o + n] for k, (o, n) in self.layout.items()}
         self.g = {k: self.grad[o:o + n] for k, (o, n) in self.layout.items()}
         self.p["lights"][0:3] = float(np.sqrt(4 * np.pi))                  # tracker.py:1301-1304
@@ -282,8 +287,10 @@ class Engine:
         """Folds the texel-gradient pyramid (+ TV / residual regularisers) into a dense [3,T,T] gradient (no Adam)."""
         if self.tex_grad_dense is None:
             self.tex_grad_dense = torch.zeros(3 * self.T * self.T, dtype=torch.float32, device=self.dev)
+        if not getattr(self, "_tex_persist", False):
             torch.cuda.current_stream(self.dev).synchronize()       # the zero fill must not race the library's aux stream
             self.L.vhap_set_tex_grad_persistent(self.ctx, 1)        # persistent from here on: the fold may leave the caller's stream
+            self._tex_persist = True
         cs = self._c_stage(training)
         self._ck(self.L.vhap_tex_reg_fold_adam(self.ctx, self.tex_extra.data_ptr(), self.tex_grad_dense.data_ptr(), None, None, 0.0, 1,
                                                C.byref(cs), 1.0, self.losses.data_ptr(), self._stream()), None)
@@ -310,10 +317,13 @@ class Engine:
         cs = self._c_stage(True)
         if opt["texture"] and allreduce_fn is not None:
             g = self.texture_grad_dense()                  # fold + regularisers; runs beside the geometry backward (aux stream)
-            allreduce_fn(g)
+            if self._dp_buf is not None:
+                allreduce_fn(self._dp_buf)                 # texture gradient + gradient slab in one collective
+            else:
+                allreduce_fn(g)
             self._ck(self.L.vhap_tex_apply_grad(self.ctx, self.tex_extra.data_ptr(), g.data_ptr(), self.tex_m.data_ptr(), self.tex_v.data_ptr(),
                                                 self._lr("tex"), self.step_count, C.byref(cs), s), None)
-        if allreduce_fn is not None:
+        if allreduce_fn is not None and not (opt["texture"] and self._dp_buf is not None):
             allreduce_fn(self.grad)
         if groups:
             off = np.asarray([self.layout[g][0] for g in groups], np.int64)
