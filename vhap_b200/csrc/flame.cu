@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256) k_pose_fwd(
   for (int e = 0; e < 15; ++e) acc[e] = 0.f;
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
     float be = k < n_shape ? shape[k] : expr[(size_t)t * n_expr + (k - n_shape)];
-    betas_out[(size_t)b * K + k] = be;
+    if (betas_out) betas_out[(size_t)b * K + k] = be;
     const float* js = JS + (size_t)k * 15;
     for (int e = 0; e < 15; ++e) acc[e] += js[e] * be;
   }
@@ -196,10 +196,27 @@ __global__ void __launch_bounds__(128) k_skin_fwd(const float* __restrict__ v_pa
   }
 }
 
+#ifndef VH_SKIN_NB
+#define VH_SKIN_NB 2          // frames per CTA in the skinning kernel: 2 fills the machine at B=16 (8 left 82 CTAs for 148 SMs)
+#endif
+// blend-shape coefficients of the batch: beta[b] = [shape | expr[timestep[b]]]
+__global__ void k_betas_gather(const float* __restrict__ shape, const float* __restrict__ expr, const int* __restrict__ ts, int K, int n_shape,
+                               float* __restrict__ betas) {
+  int b = blockIdx.x, t = ts[b], n_expr = K - n_shape;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) betas[(size_t)b * K + k] = k < n_shape ? shape[k] : expr[(size_t)t * n_expr + (k - n_shape)];
+}
+
 void launch_flame_forward(vhap_ctx* c, const vhap_params* p, const vhap_frame_batch* fb, cudaStream_t s) {
   int B = fb->B, V = c->V, M = 3 * V;
-  LAUNCH(c, KID_POSE_FWD, s, k_pose_fwd<<<B, 256, 0, s>>>(p->shape, p->expr, p->rotation, p->neck_pose, p->jaw_pose, p->eyes_pose, p->static_offset, fb->timesteps,
-                               c->JS, c->Jt, c->Jreg, V, c->K, c->n_shape, c->betas, c->posebuf, c->poses));
+  // the joint / pose chain (latency-bound, one block per frame) only meets the blend shapes again in the skinning kernel: it runs
+  // on an aux stream beside the tensor-core contraction
+  const bool fork = !c->no_overlap;
+  cudaStream_t sp = fork ? c->aux[0] : s;
+  LAUNCH(c, KID_POSE_FWD, s, k_betas_gather<<<B, 128, 0, s>>>(p->shape, p->expr, fb->timesteps, c->K, c->n_shape, c->betas));
+  if (fork) { cudaEventRecord(c->ev[9], s); cudaStreamWaitEvent(sp, c->ev[9], 0); }
+  LAUNCH(c, KID_POSE_FWD, sp, k_pose_fwd<<<B, 256, 0, sp>>>(p->shape, p->expr, p->rotation, p->neck_pose, p->jaw_pose, p->eyes_pose, p->static_offset, fb->timesteps,
+                               c->JS, c->Jt, c->Jreg, V, c->K, c->n_shape, nullptr, c->posebuf, c->poses));
+  if (fork) cudaEventRecord(c->ev[10], sp);
   int ks = BLEND_KS;
   const float* vpart = c->v_shaped_part;
   if (c->use_tc_blend) {                 // tcgen05 contraction writes the finished v_shaped
@@ -210,8 +227,9 @@ void launch_flame_forward(vhap_ctx* c, const vhap_params* p, const vhap_frame_ba
     LAUNCH(c, KID_BLEND_FWD, s, k_blend_fwd<VH_MAXB_CHUNK><<<g1, 128, VH_MAXB_CHUNK * c->K * sizeof(float), s>>>(c->S_fwd, c->v_template, p->static_offset, c->betas, M, c->K,
                                                                                     c->n_shape, B, c->v_shaped_part));
   }
-  dim3 g2((V + 127) / 128, (B + 7) / 8);
-  LAUNCH(c, KID_SKIN_FWD, s, k_skin_fwd<8><<<g2, 128, 0, s>>>(vpart, ks, c->v_shaped, c->posedirs, c->lbs_w, c->posebuf, p->translation, fb->timesteps, c->cam, V, B, fb->H, fb->W,
+  if (fork) cudaStreamWaitEvent(s, c->ev[10], 0);
+  dim3 g2((V + 127) / 128, (B + VH_SKIN_NB - 1) / VH_SKIN_NB);
+  LAUNCH(c, KID_SKIN_FWD, s, k_skin_fwd<VH_SKIN_NB><<<g2, 128, 0, s>>>(vpart, ks, c->v_shaped, c->posedirs, c->lbs_w, c->posebuf, p->translation, fb->timesteps, c->cam, V, B, fb->H, fb->W,
                                    c->v_posed, c->verts, c->clip, c->snap, c->ndc));
 }
 
