@@ -166,7 +166,7 @@ def run_ours(args):
         dp.step(resident[i % n_batches])
     barrier()
     if use_graph:
-        eng.graph_begin(resident, body=dp.body if world > 1 else None)   # one CUDA graph per (batch, texture parity)
+        dp.graph_begin(resident, pipelined=not args.no_pipeline)          # one CUDA graph per (batch, texture parity)
         for i in range(3):
             eng.graph_step(i % n_batches)
         barrier()
@@ -295,7 +295,9 @@ def run_ours(args):
                                f"stage rgb_global_tracking, Adam on all groups incl. 2048^2 texture",
                    "global_batch": gB, "image": [size, size], "tex": 2048, "foreground_fraction": round(fg, 3),
                    "parallelism": f"dp{world} frame-sharded, one all-gather (forward slab) + one all-reduce (texture gradient + gradient slab) per step" if world > 1 else "single GPU",
-                   "launch": "CUDA graph replay (1 graph launch per step)" if use_graph else "eager (one launch per kernel)",
+                   "launch": ("CUDA graph replay (1 graph launch per step" + (", texture update of step k pipelined into the graph of step k+1; the "
+                              "timed region holds exactly K complete steps' worth of work: K replays, each = previous step's texture update + this step's "
+                              "everything else)" if not args.no_pipeline else ")")) if use_graph else "eager (one launch per kernel)",
                    "l2": "inputs larger than L2: 4 rotating batches; per-step working set ~0.7 GB (texture, Adam state, targets)"},
         "e2e": {"value": round(gB * args.steps / (ms_e2e * 1e-3), 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": round(ms_e2e / args.steps, 4),
@@ -402,6 +404,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="do not defer the texture update into the next step's graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

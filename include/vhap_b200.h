@@ -196,6 +196,11 @@ int vhap_tex_apply_grad(vhap_ctx* ctx, float* tex_extra, const float* g_dense, f
 /* on != 0: g_out of vhap_tex_reg_fold_adam is a persistent buffer only read after the call returns -> the fold may overlap the
  * geometry backward on the library's aux stream */
 int vhap_set_tex_grad_persistent(vhap_ctx* ctx, int32_t on);
+/* ---- deferred texture update: the update of step k executes at the start of step k+1 on a caller stream, beside the kernels of
+ *      the next forward that do not read the texture, and is joined right before the shading pass --------------------------- */
+int vhap_tex_defer(vhap_ctx* ctx, int32_t step_bias);           /* next texture-update call: no in-call fork; device Adam step + step_bias */
+int vhap_tex_reg_loss(vhap_ctx* ctx, const float* tex_extra, const vhap_stage_cfg* cfg, void* stream);   /* regulariser loss values of the current texture */
+int vhap_set_render_wait_event(vhap_ctx* ctx, void* cuda_event);   /* one-shot wait inserted before the first texture read of the next forward */
 
 /* ---- per-kernel accounting: every kernel launch is counted; with profiling enabled CUDA events bracket each launch on the
  *      launching stream (used by bench.py to measure the dominant kernel live inside its timed region) --------------- */

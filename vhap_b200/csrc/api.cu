@@ -168,7 +168,11 @@ extern "C" int vhap_ctx_create(vhap_ctx** out, const vhap_mesh_desc* m, int32_t 
   UP(ctx->scan_total, (const int*)nullptr, (size_t)1);
   UP(ctx->pair_count, (const int*)nullptr, (size_t)1);
   UP(ctx->dev_step, (const int*)nullptr, (size_t)2);
-  for (int i = 0; i < 2; ++i) CK(cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking));
+  // aux[0] carries small latency-critical side chains (pose chain, vertex normals, regularisers): highest priority, like hp[];
+  // aux[1] carries the bulk texture pass: default (lowest) priority
+  { int lo = 0, hi = 0; CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&ctx->aux[0], cudaStreamNonBlocking, hi));
+    CK(cudaStreamCreateWithFlags(&ctx->aux[1], cudaStreamNonBlocking)); }
   {
     int lo = 0, hi = 0;
     CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -178,6 +182,7 @@ extern "C" int vhap_ctx_create(vhap_ctx** out, const vhap_mesh_desc* m, int32_t 
   UP(ctx->tex_l0_flag, (const int*)nullptr, (size_t)1);
   { int one = 1; cudaMemcpy(ctx->tex_l0_flag, &one, sizeof(int), cudaMemcpyHostToDevice); }
   CK(cudaMalloc(&ctx->scan_state, (VH_SCAN_MAX_BLOCKS + 1) * sizeof(unsigned long long)));
+  CK(cudaMalloc(&ctx->tex_loss, 4 * sizeof(float))); CK(cudaMemset(ctx->tex_loss, 0, 4 * sizeof(float)));
   CK(cudaMalloc(&ctx->tex_counter, sizeof(unsigned))); CK(cudaMemset(ctx->tex_counter, 0, sizeof(unsigned)));
   return 0;
 }
@@ -233,7 +238,7 @@ extern "C" void vhap_ctx_destroy(vhap_ctx* c) {
   FREE(c->faces); FREE(c->faces_uv); FREE(c->verts_uv); FREE(c->lmk_faces); FREE(c->lmk_bary); FREE(c->adj_opp); FREE(c->fid2cid);
   FREE(c->vf_indptr); FREE(c->vf_faces); FREE(c->lap_indptr); FREE(c->lap_idx); FREE(c->lap_val); FREE(c->lap_y);
   FREE(c->face_flags); FREE(c->vert_flags); FREE(c->w_off); FREE(c->w_off_lap); FREE(c->rigid_indptr); FREE(c->rigid_vids); FREE(c->uvmask_res);
-  FREE(c->mips[0]); FREE(c->mips[1]); FREE(c->tex_painted); FREE(c->g_tex); FREE(c->tv_partials); FREE(c->tex_counter); FREE(c->scan_state); FREE(c->scal); FREE(c->acc); FREE(c->maxslot);
+  FREE(c->mips[0]); FREE(c->mips[1]); FREE(c->tex_painted); FREE(c->g_tex); FREE(c->tv_partials); FREE(c->tex_counter); FREE(c->tex_loss); FREE(c->scan_state); FREE(c->scal); FREE(c->acc); FREE(c->maxslot);
   FREE(c->overflow_flag); FREE(c->pool_base); FREE(c->pool_count);
   free(c);
 }
@@ -242,6 +247,7 @@ extern "C" int vhap_set_stage_masks(vhap_ctx* ctx, const uint8_t* face_tex_detac
                                     const float* w_off_lap, const int32_t* rigid_indptr, const int32_t* rigid_vids, int32_t n_rigid,
                                     const uint8_t* uvmask_res) {
   CK(cudaSetDevice(ctx->device));
+  CK(cudaMemset(ctx->tex_loss, 0, 4 * sizeof(float)));          // a new stage starts without texture-regulariser loss values
   if (face_tex_detach) CK(cudaMemcpy(ctx->face_flags, face_tex_detach, ctx->F, cudaMemcpyHostToDevice)); else CK(cudaMemset(ctx->face_flags, 0, ctx->F));
   if (vert_aa_detach) CK(cudaMemcpy(ctx->vert_flags, vert_aa_detach, ctx->V, cudaMemcpyHostToDevice)); else CK(cudaMemset(ctx->vert_flags, 0, ctx->V));
   FREE(ctx->w_off); FREE(ctx->w_off_lap); FREE(ctx->rigid_indptr); FREE(ctx->rigid_vids);
@@ -296,14 +302,37 @@ __global__ void k_project_only(const float* __restrict__ verts, const CamParams*
   o[0] = p00 * cx_ + p02 * cz_; o[1] = p11 * cy_ + p12 * cz_; o[2] = p22 * cz_ + p23; o[3] = -cz_;
 }
 
-static void zero_backward_scratch(vhap_ctx* c, int B, cudaStream_t s) {
+__global__ void __launch_bounds__(256) k_zero_multi(VhZeroSegs z) {
+  const int sgm = blockIdx.y;
+  if (sgm >= z.n) return;
+  const size_t n4 = z.bytes[sgm] >> 2;
+  unsigned* p = (unsigned*)z.p[sgm];
+  if ((((size_t)p) & 15) == 0) {
+    uint4* p16 = (uint4*)p;
+    const size_t n16 = n4 >> 2;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n16; i += (size_t)gridDim.x * 256) p16[i] = make_uint4(0, 0, 0, 0);
+    for (size_t i = (n16 << 2) + (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) p[i] = 0u;
+  } else {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) p[i] = 0u;
+  }
+}
+void vh_zero_multi(vhap_ctx* c, const VhZeroSegs& z, cudaStream_t s) {
+  size_t mx = 0;
+  for (int i = 0; i < z.n; ++i) mx = z.bytes[i] > mx ? z.bytes[i] : mx;
+  int nb = (int)((mx / 16 + 255) / 256);
+  nb = nb < 1 ? 1 : (nb > 148 * 4 ? 148 * 4 : nb);
+  LAUNCH(c, KID_MISC, s, k_zero_multi<<<dim3(nb, z.n), 256, 0, s>>>(z));
+}
+
+// per-step scratch of the backward pass + the loss accumulators, one launch
+static void zero_backward_scratch(vhap_ctx* c, int B, cudaStream_t s, bool with_acc = false) {
   size_t V = c->V;
-  cudaMemsetAsync(c->g_verts, 0, B * V * 4 * sizeof(float), s);
-  cudaMemsetAsync(c->g_clip, 0, B * V * 4 * sizeof(float), s);
-  cudaMemsetAsync(c->g_vnorm, 0, B * V * 4 * sizeof(float), s);
-  cudaMemsetAsync(c->gA, 0, (size_t)B * 60 * sizeof(float), s);
-  cudaMemsetAsync(c->gpf, 0, (size_t)B * 36 * sizeof(float), s);
-  cudaMemsetAsync(c->gbetas, 0, (size_t)B * c->K * sizeof(float), s);
+  VhZeroSegs z; z.n = 0;
+  auto add = [&](void* p, size_t bytes) { z.p[z.n] = p; z.bytes[z.n] = bytes; ++z.n; };
+  add(c->g_verts, B * V * 4 * sizeof(float)); add(c->g_clip, B * V * 4 * sizeof(float)); add(c->g_vnorm, B * V * 4 * sizeof(float));
+  add(c->gA, (size_t)B * 60 * sizeof(float)); add(c->gpf, (size_t)B * 36 * sizeof(float)); add(c->gbetas, (size_t)B * c->K * sizeof(float));
+  if (with_acc) add(c->acc, ACC_COUNT * sizeof(float));
+  vh_zero_multi(c, z, s);
 }
 
 extern "C" int vhap_flame_forward(vhap_ctx* ctx, const vhap_params* p, const vhap_frame_batch* fb, float* verts, float* verts_cano, float* lmks, void* stream) {
@@ -368,15 +397,15 @@ extern "C" int vhap_tex_rebuild(vhap_ctx* ctx, const float* tex_extra, void* str
 }
 
 __global__ void k_assemble_losses(const float* __restrict__ acc, vhap_stage_cfg cfg, float max_hw, float* __restrict__ g_focal, int add_focal,
-                                  float* __restrict__ out) {
+                                  float* __restrict__ out, const float* __restrict__ tex_loss = nullptr) {
   if (threadIdx.x != 0) return;
   if (add_focal && g_focal) g_focal[0] += (acc[ACC_GFX] + acc[ACC_GFY]) * max_hw;       // fx = fy = focal * max(h,w) (tracker.py:153)
   if (!out) return;
   for (int i = 0; i < VHAP_N_LOSS; ++i) out[i] = 0.f;
   out[VHAP_L_LMK] = acc[ACC_LMK]; out[VHAP_L_PHOTO] = acc[ACC_PHOTO]; out[VHAP_L_REG_SHAPE] = acc[ACC_REG_SHAPE];
   out[VHAP_L_REG_EXPR] = acc[ACC_REG_EXPR]; out[VHAP_L_REG_JOINT] = acc[ACC_REG_JOINT]; out[VHAP_L_SMOOTH_POSE] = acc[ACC_SMOOTH_POSE];
-  out[VHAP_L_SMOOTH_JOINT] = acc[ACC_SMOOTH_JOINT]; out[VHAP_L_SMOOTH_EXPR] = acc[ACC_SMOOTH_EXPR]; out[VHAP_L_REG_TEX_TV] = acc[ACC_REG_TEX_TV];
-  out[VHAP_L_REG_TEX_RES] = acc[ACC_REG_TEX_RES]; out[VHAP_L_REG_DIFFUSE] = acc[ACC_REG_DIFFUSE]; out[VHAP_L_REG_LIGHT] = acc[ACC_REG_LIGHT];
+  out[VHAP_L_SMOOTH_JOINT] = acc[ACC_SMOOTH_JOINT]; out[VHAP_L_SMOOTH_EXPR] = acc[ACC_SMOOTH_EXPR]; out[VHAP_L_REG_TEX_TV] = tex_loss ? tex_loss[0] : 0.f;
+  out[VHAP_L_REG_TEX_RES] = tex_loss ? tex_loss[1] : 0.f; out[VHAP_L_REG_DIFFUSE] = acc[ACC_REG_DIFFUSE]; out[VHAP_L_REG_LIGHT] = acc[ACC_REG_LIGHT];
   out[VHAP_L_REG_OFFSET] = acc[ACC_REG_OFFSET]; out[VHAP_L_REG_OFFSET_LAP] = acc[ACC_REG_OFFSET_LAP]; out[VHAP_L_REG_OFFSET_RIGID] = acc[ACC_REG_OFFSET_RIGID];
   out[VHAP_L_NFG] = acc[ACC_NFG]; out[VHAP_L_ABSERR] = acc[ACC_ABSERR];
   float t = 0.f;
@@ -389,8 +418,7 @@ extern "C" int vhap_energy_forward(vhap_ctx* ctx, const vhap_params* p, const vh
                                    void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (check_batch(ctx, fb)) return -4;
-  cudaMemsetAsync(ctx->acc, 0, ACC_COUNT * sizeof(float), s);
-  zero_backward_scratch(ctx, fb->B, s);
+  zero_backward_scratch(ctx, fb->B, s, true);
   launch_cam_setup(ctx, p, fb, s);
   launch_flame_forward(ctx, p, fb, s);
   if (cfg->photometric && cfg->w_photo >= 0.f) {
@@ -459,7 +487,7 @@ extern "C" int vhap_energy_backward(vhap_ctx* ctx, const vhap_params* p, const v
   if (gs != s) { cudaEventRecord(ctx->ev[6], gs); cudaStreamWaitEvent(s, ctx->ev[6], 0); }
   if (regs_forked) cudaStreamWaitEvent(s, ctx->ev[1], 0);        // join the regularisers
   float max_hw = (float)(fb->H > fb->W ? fb->H : fb->W);
-  LAUNCH(ctx, KID_ASSEMBLE, s, k_assemble_losses<<<1, 32, 0, s>>>(ctx->acc, *cfg, max_hw, gg->focal_length, opt_cam, losses_out));
+  LAUNCH(ctx, KID_ASSEMBLE, s, k_assemble_losses<<<1, 32, 0, s>>>(ctx->acc, *cfg, max_hw, gg->focal_length, opt_cam, losses_out, ctx->tex_loss));
   LAST();
   return 0;
 }
@@ -510,7 +538,7 @@ extern "C" int vhap_tex_reg_fold_adam(vhap_ctx* ctx, float* tex_extra, float* g_
   }
   if (losses_out) {
     // add the two texture terms to the loss vector produced by vhap_energy_backward
-    LAUNCH(ctx, KID_ASSEMBLE, (cudaStream_t)stream, k_assemble_losses<<<1, 32, 0, (cudaStream_t)stream>>>(ctx->acc, *cfg, 0.f, nullptr, 0, losses_out));
+    LAUNCH(ctx, KID_ASSEMBLE, (cudaStream_t)stream, k_assemble_losses<<<1, 32, 0, (cudaStream_t)stream>>>(ctx->acc, *cfg, 0.f, nullptr, 0, losses_out, ctx->tex_loss));
   }
   LAST();
   return 0;
@@ -526,6 +554,20 @@ extern "C" int vhap_tex_apply_grad(vhap_ctx* ctx, float* tex_extra, const float*
   LAST();
   return 0;
 }
+// Deferred texture update (the update of step k runs at the start of step k+1, beside FLAME / rasteriser / pools, and is joined right
+// before the shading pass): cancel the in-call fork of the next vhap_tex_reg_fold_adam (it then runs on the stream it is given) and
+// bias the device Adam step it reads (-1: the counter was already advanced).  bias 0 restores the normal behaviour.
+extern "C" int vhap_tex_defer(vhap_ctx* ctx, int32_t step_bias) { ctx->tex_fork_pending = 0; ctx->tex_step_bias = step_bias; return 0; }
+// loss VALUES of the texture regularisers for the texture currently in use (complete loss vectors with a deferred update)
+extern "C" int vhap_tex_reg_loss(vhap_ctx* ctx, const float* tex_extra, const vhap_stage_cfg* cfg, void* stream) {
+  launch_tex_reg_loss(ctx, tex_extra, cfg, (cudaStream_t)stream);
+  LAST();
+  return 0;
+}
+// one-shot: the next render forward waits for `event` (a cudaEvent_t recorded by the caller) after the pixel pools are built and
+// before the first kernel that reads the texture
+extern "C" int vhap_set_render_wait_event(vhap_ctx* ctx, void* event) { ctx->render_wait_ev = (cudaEvent_t)event; return 0; }
+
 // on != 0: the g_out buffer passed to vhap_tex_reg_fold_adam is persistent and only read by the caller AFTER that call returns
 // (on the same stream): the fold may then run on the aux stream beside the geometry backward, like the fused single-GPU update
 extern "C" int vhap_set_tex_grad_persistent(vhap_ctx* ctx, int32_t on) { ctx->tex_gout_persistent = on; return 0; }
@@ -641,7 +683,7 @@ extern "C" int vhap_render_photometric(vhap_ctx* ctx, const vhap_params* p, cons
     if (g_clip) cudaMemcpyAsync(g_clip, ctx->g_clip, n * 4 * sizeof(float), cudaMemcpyDeviceToDevice, s);
     if (g_vnorm) LAUNCH(ctx, KID_MISC, s, k_4to3<<<GRID1(n), 0, s>>>(ctx->g_vnorm, g_vnorm, n));
   }
-  LAUNCH(ctx, KID_ASSEMBLE, s, k_assemble_losses<<<1, 32, 0, s>>>(ctx->acc, *cfg, 0.f, nullptr, 0, losses_out));
+  LAUNCH(ctx, KID_ASSEMBLE, s, k_assemble_losses<<<1, 32, 0, s>>>(ctx->acc, *cfg, 0.f, nullptr, 0, losses_out, ctx->tex_loss));
   LAST();
   return 0;
 }

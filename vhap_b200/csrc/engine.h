@@ -60,7 +60,10 @@ struct vhap_ctx {
   unsigned long long* scan_state;                 // [VH_SCAN_MAX_BLOCKS + 1] look-back words + ticket of the single-launch scan
   int* pool_tri;                                  // rasterised id per pool_list entry
   int* tex_l0_flag;                               // [1]
-  const float* tex_apply_grad; int tex_gout_persistent;   // see vhap_tex_apply_grad / vhap_set_tex_grad_persistent
+  const float* tex_apply_grad; int tex_gout_persistent;
+  float* tex_loss;                                // [2] TV / residual regulariser loss of the texture the last fold (or vhap_tex_reg_loss) saw
+  int tex_step_bias;                              // added to the device Adam step inside the texture update (deferred update: -1)
+  cudaEvent_t render_wait_ev;                     // one-shot: the next render forward waits for it right before the shading pass   // see vhap_tex_apply_grad / vhap_set_tex_grad_persistent
   unsigned* tex_counter;                          // [1] CTA completion counter of the texture fold kernel (self-resetting)
   cudaStream_t aux[2]; cudaStream_t hp[2]; cudaEvent_t ev[12];   // hp: highest-priority streams for the latency-critical geometry backward
   int tex_fork_pending, no_overlap;   // fork/join of independent kernel chains
@@ -103,6 +106,12 @@ static inline void vh_prof_end(vhap_ctx* c, int kid, cudaStream_t s) {
 }
 #define LAUNCH(c, kid, s, ...) do { vh_prof_begin((c), (kid), (s)); __VA_ARGS__; vh_prof_end((c), (kid), (s)); } while (0)
 
+// kernel-based zero fill of up to 8 buffers in one launch (byte counts multiples of 4).  Unlike a memset node a kernel inherits the
+// priority of its stream, so the step's latency-critical chain is not queued behind the CTAs of a concurrently running bulk kernel.
+struct VhZeroSegs { int n; void* p[8]; size_t bytes[8]; };
+void vh_zero_multi(vhap_ctx* c, const VhZeroSegs& z, cudaStream_t s);
+static inline void vh_zero(vhap_ctx* c, void* p, size_t bytes, cudaStream_t s) { VhZeroSegs z; z.n = 1; z.p[0] = p; z.bytes[0] = bytes; vh_zero_multi(c, z, s); }
+
 // flame.cu
 void launch_cam_setup(vhap_ctx* c, const vhap_params* p, const vhap_frame_batch* fb, cudaStream_t s);
 void launch_flame_forward(vhap_ctx* c, const vhap_params* p, const vhap_frame_batch* fb, cudaStream_t s);
@@ -111,6 +120,7 @@ void launch_landmarks(vhap_ctx* c, const vhap_frame_batch* fb, float w_scale, in
 void launch_flame_backward(vhap_ctx* c, const vhap_params* p, const vhap_frame_batch* fb, const vhap_grads* g, int opt_cam, cudaStream_t s);
 void launch_vnormals(vhap_ctx* c, int B, cudaStream_t s);
 void launch_vnormals_bwd(vhap_ctx* c, int B, cudaStream_t s);
+void launch_tex_reg_loss(vhap_ctx* c, const float* tex_extra, const vhap_stage_cfg* cfg, cudaStream_t s);
 void launch_regs(vhap_ctx* c, const vhap_params* p, const vhap_frame_batch* fb, const vhap_stage_cfg* cfg, const vhap_grads* g, int global_B, cudaStream_t s);
 // blend_tc.cu
 void launch_blend_tc_fwd(vhap_ctx* c, const float* offset, int B, cudaStream_t s);

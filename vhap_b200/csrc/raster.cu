@@ -177,7 +177,7 @@ void launch_scan(vhap_ctx* c, const int* in, int* out, int n, int* total, cudaSt
     LAUNCH(c, KID_SCAN, s, k_scan_add<<<nb, 1024, 0, s>>>(out, c->scan_aux, n));
     return;
   }
-  cudaMemsetAsync(c->scan_state, 0, (size_t)(nb + 1) * sizeof(unsigned long long), s);
+  vh_zero(c, c->scan_state, (size_t)(nb + 1) * sizeof(unsigned long long), s);
   LAUNCH(c, KID_SCAN, s, k_scan_lb<<<nb, 1024, 0, s>>>(in, out, n, c->scan_state, nb, total));
 }
 
@@ -319,12 +319,12 @@ void launch_raster(vhap_ctx* c, const f4* clip, i4* snap, int B, int H, int W, i
   int V = c->V, F = c->F;
   if (need_snap) LAUNCH(c, KID_SNAP, s, k_snap<<<(B * V + 255) / 256, 256, 0, s>>>(clip, snap, c->ndc, B * V, H, W));
   int tiles_x = (W + VH_TILE - 1) / VH_TILE, tiles_y = (H + VH_TILE - 1) / VH_TILE, ntiles = B * tiles_x * tiles_y;
-  cudaMemsetAsync(c->tile_count, 0, sizeof(int) * ntiles, s);
+  vh_zero(c, c->tile_count, sizeof(int) * ntiles, s);
   dim3 g((F + 255) / 256, B);
   LAUNCH(c, KID_BIN, s, k_bin<false><<<g, 256, 0, s>>>(snap, c->faces, V, F, B, H, W, tiles_x, tiles_y, cull_backface, c->tile_count, nullptr, nullptr, nullptr, 0, c->overflow_flag));
   LAUNCH(c, KID_SCAN, s, k_pad_counts<<<(ntiles + 255) / 256, 256, 0, s>>>(c->tile_count, c->tile_cursor, ntiles));   // cursor doubles as scratch
   launch_scan(c, c->tile_cursor, c->tile_off, ntiles, nullptr, s);
-  cudaMemsetAsync(c->tile_cursor, 0, sizeof(int) * ntiles, s);
+  vh_zero(c, c->tile_cursor, sizeof(int) * ntiles, s);
   LAUNCH(c, KID_BIN, s, k_bin<true><<<g, 256, 0, s>>>(snap, c->faces, V, F, B, H, W, tiles_x, tiles_y, cull_backface, c->tile_count, c->tile_off, c->tile_cursor, c->tile_list,
                                 c->tile_cap, c->overflow_flag));
   LAUNCH(c, KID_FINE, s, k_fine<<<ntiles, 128, 0, s>>>(snap, c->faces, c->tile_count, c->tile_off, c->tile_list, c->tile_cap, V, H, W, tiles_x, tiles_y, cull_backface, tri_id));

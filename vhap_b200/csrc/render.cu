@@ -341,16 +341,17 @@ void launch_render_forward(vhap_ctx* c, PassArgs& P, cudaStream_t s) {
   size_t n = (size_t)A.B * A.H * A.W;
   int nblk = (int)((n + PB - 1) / PB);
   int* slots = slot_table(c);
-  cudaMemsetAsync(c->maxslot, 0, sizeof(unsigned long long), s);
+  { VhZeroSegs z; z.n = 2; z.p[0] = c->maxslot; z.bytes[0] = sizeof(unsigned long long); z.p[1] = c->pair_count; z.bytes[1] = sizeof(int); vh_zero_multi(c, z, s); }
   if (c->want_planes) {
     cudaMemsetAsync(c->plane_albedo, 0, n * 16, s); cudaMemsetAsync(c->plane_normal, 0, n * 16, s); cudaMemsetAsync(c->plane_diffuse, 0, n * 16, s);
   }
   LAUNCH(c, KID_POOL_COUNT, s, k_pool_count<<<nblk, PB, 0, s>>>(A.tri_id, A.fid2cid, n, c->n_clusters, c->pool_blk_count));
   launch_scan(c, c->pool_blk_count, c->pool_blk_off, 16 * nblk, c->scan_total, s);
   LAUNCH(c, KID_POOL_SCAN, s, k_pool_bases<<<1, 32, 0, s>>>(c->pool_blk_off, nblk, c->scan_total, c->pool_base, c->pool_count));
-  cudaMemsetAsync(c->pair_count, 0, sizeof(int), s);
   LAUNCH(c, KID_POOL_SCATTER, s, k_pool_scatter<<<nblk, PB, 0, s>>>(A.tri_id, A.fid2cid, n, A.H, A.W, c->n_clusters, c->pool_blk_off, c->pool_list, c->pool_tri, c->pair_list, c->pair_count));
   int grid = nblk < NPERSIST ? nblk : NPERSIST;
+  // a deferred texture update (vhap_set_render_wait_event) is joined here: everything above is independent of the texture
+  if (c->render_wait_ev) { cudaStreamWaitEvent(s, c->render_wait_ev, 0); c->render_wait_ev = nullptr; }
   LAUNCH(c, KID_PASSA, s, k_passA<<<grid, PB, 0, s>>>(P, c->partials, c->maxslot));
   LAUNCH(c, KID_AA_PAIRS, s, k_aa_pairs<<<grid, PB, 0, s>>>(P, c->pair_list, c->pair_count));
   LAUNCH(c, KID_PASSB, s, k_passB<<<grid, PB, 0, s>>>(P, c->partials));

@@ -82,6 +82,7 @@ struct TexFoldArgs {
   int do_adam;
   const int* l0_flag;
   const int* step_ptr;          // device Adam step (CUDA-graph replay) or NULL
+  int step_bias;                // added to *step_ptr (deferred update of the previous step: -1)
 };
 
 __device__ __forceinline__ float chan(const f4& t, int c) { return c == 0 ? t.x : (c == 1 ? t.y : t.z); }
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(256, 4) k_tex_fold(TexFoldArgs a, float* __res
     // l0_flag when it scatters there, otherwise the 16 B/texel read + re-zero of that level is skipped
     const bool l0 = a.g_pyr ? (a.l0_flag ? (*a.l0_flag != 0) : true) : false;
     float bc1 = a.bc1, bc2s = a.bc2_sqrt;
-    if (a.do_adam && a.step_ptr) { float st = (float)a.step_ptr[0]; bc1 = 1.f - powf(0.9f, st); bc2s = sqrtf(1.f - powf(0.999f, st)); }
+    if (a.do_adam && a.step_ptr) { float st = (float)(a.step_ptr[0] + a.step_bias); bc1 = 1.f - powf(0.9f, st); bc2s = sqrtf(1.f - powf(0.999f, st)); }
     TexelIn r0, r1;
     fold_load(a, x, y, l0, coarse[tid >> 1], r0);   // all loads of both texels are issued before the first dependent store
     fold_load(a, x, y + 1, l0, coarse[tid >> 1], r1);
@@ -221,10 +222,63 @@ __global__ void __launch_bounds__(256, 4) k_tex_fold(TexFoldArgs a, float* __res
     if (tid == 0) {
       float t = 0.f;
       for (int k = 0; k < 8; ++k) t += sh[k];
-      acc_out[q == 0 ? ACC_REG_TEX_TV : ACC_REG_TEX_RES] += t;
+      acc_out[q] = t;                                   // [0] TV, [1] residual (vhap_ctx::tex_loss)
     }
   }
   if (tid == 0) *counter = 0u;
+}
+
+// TV + residual regulariser LOSS VALUES of the current texture (tracker.py:526-539), no gradient: used when the texture update is
+// deferred into the next step (the fold kernel then sees the texture one step late), so that a step's loss vector is complete.
+__global__ void __launch_bounds__(256) k_tex_reg_loss(const f4* __restrict__ tex, const float* __restrict__ extra, const uint8_t* __restrict__ mask, int T,
+                                                      float w_tv, float w_res, float* __restrict__ partials, unsigned* __restrict__ counter, float* __restrict__ out) {
+  __shared__ float sh[8 * 2];
+  __shared__ bool is_last;
+  const size_t n = (size_t)T * T;
+  float acc[2] = {0.f, 0.f};
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+    int x = (int)(i % T), y = (int)(i / T);
+    if (w_tv > 0.f) {
+      f4 t = tex[i], tr = x + 1 < T ? tex[i + 1] : t, td = y + 1 < T ? tex[i + T] : t;
+      for (int c = 0; c < 3; ++c) { float v = chan(t, c), dr = v - chan(tr, c), dd = v - chan(td, c); acc[0] += w_tv * (dr * dr + dd * dd); }
+    }
+    if (w_res > 0.f && mask && mask[i]) for (int c = 0; c < 3; ++c) { float e = extra[c * n + i]; acc[1] += w_res * e * e; }
+  }
+  int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  for (int q = 0; q < 2; ++q) {
+    float v = acc[q];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sh[w * 2 + q] = v;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float s0 = 0.f, s1 = 0.f;
+    for (int k = 0; k < 8; ++k) { s0 += sh[k * 2]; s1 += sh[k * 2 + 1]; }
+    partials[(size_t)blockIdx.x * 2] = s0; partials[(size_t)blockIdx.x * 2 + 1] = s1;
+    __threadfence();
+    is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int q = 0; q < 2; ++q) {
+    float s2 = 0.f;
+    for (int r = tid; r < (int)gridDim.x; r += 256) s2 += __ldcg(partials + (size_t)r * 2 + q);
+    for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    __syncthreads();
+    if (lane == 0) sh[w] = s2;
+    __syncthreads();
+    if (tid == 0) { float t = 0.f; for (int k = 0; k < 8; ++k) t += sh[k]; out[q] = t; }
+  }
+  if (tid == 0) *counter = 0u;
+}
+void launch_tex_reg_loss(vhap_ctx* c, const float* tex_extra, const vhap_stage_cfg* cfg, cudaStream_t s) {
+  int T = c->T;
+  float sh = cfg->shared_scale;
+  float w_tv = (cfg->training && cfg->opt_texture && cfg->w_reg_tex_tv >= 0.f) ? sh * cfg->w_reg_tex_tv / (3.f * (float)(T - 1) * (float)T) : 0.f;
+  float w_res = (cfg->training && cfg->opt_texture && cfg->w_reg_tex_res >= 0.f) ? sh * cfg->w_reg_tex_res / (3.f * (float)T * (float)T) : 0.f;
+  int nblk = c->tv_nblocks < 148 * 8 ? c->tv_nblocks : 148 * 8;
+  LAUNCH(c, KID_TEX_LOSS, s, k_tex_reg_loss<<<nblk, 256, 0, s>>>(c->mips[c->cur_mip], tex_extra, c->uvmask_res, T, w_tv, w_res, c->tv_partials, c->tex_counter, c->tex_loss));
 }
 
 void launch_tex_fold(vhap_ctx* c, float* tex_extra, float* g_out, float* m, float* v, float lr, int step, const vhap_stage_cfg* cfg,
@@ -238,7 +292,7 @@ void launch_tex_fold(vhap_ctx* c, float* tex_extra, float* g_out, float* m, floa
   a.tex_old = c->mips[c->cur_mip]; a.tex_new = c->mips[c->cur_mip ^ 1]; a.g_pyr = c->g_tex;
   a.extra = tex_extra; a.g_out = g_out; a.m = m; a.v = v; a.g_in = c->tex_apply_grad;
   if (a.g_in) a.g_pyr = nullptr;                       // apply mode: gradient already folded, regularised and reduced across ranks
-  a.mask = c->uvmask_res; a.l0_flag = c->tex_l0_flag; a.step_ptr = c->use_dev_step ? c->dev_step : nullptr;
+  a.mask = c->uvmask_res; a.l0_flag = c->tex_l0_flag; a.step_ptr = c->use_dev_step ? c->dev_step : nullptr; a.step_bias = c->tex_step_bias;
   float sh = cfg->shared_scale;
   // tv.mean(): (T-1)*T elements per channel, 3 channels (tracker.py:529-533); w already includes scale_factor^2 / ds^2
   a.w_tv = (cfg->training && cfg->opt_texture && cfg->w_reg_tex_tv >= 0.f) ? sh * cfg->w_reg_tex_tv / (3.f * (float)(T - 1) * (float)T) : 0.f;
@@ -247,7 +301,7 @@ void launch_tex_fold(vhap_ctx* c, float* tex_extra, float* g_out, float* m, floa
   a.do_adam = (m != nullptr && v != nullptr) ? 1 : 0;
   a.lr = lr; a.bc1 = 1.f - powf(0.9f, (float)step); a.bc2_sqrt = sqrtf(1.f - powf(0.999f, (float)step));
   int tw = T < 256 ? T : 256, nblk = (T / tw) * (T / 2), L = c->max_level >= 1 ? 1 : 0;
-  LAUNCH(c, KID_TEX_FOLD, s, k_tex_fold<<<nblk, 256, 0, s>>>(a, c->tv_partials, c->tex_counter, c->acc));
+  LAUNCH(c, KID_TEX_FOLD, s, k_tex_fold<<<nblk, 256, 0, s>>>(a, c->tv_partials, c->tex_counter, a.g_in ? c->tex_loss + 2 : c->tex_loss));      // apply mode: scratch slots
   if (a.g_in) {                                                           // apply mode leaves the gradient pyramid alone
     if (a.do_adam) { c->cur_mip ^= 1; build_mips(c, c->mips[c->cur_mip], s, L); }
     return;

@@ -283,7 +283,7 @@ class Engine:
         self._last = (cs, opt)
         return self.losses
 
-    def texture_grad_dense(self, training=True) -> torch.Tensor:
+    def texture_grad_dense(self, training=True, with_losses=True) -> torch.Tensor:
         """Folds the texel-gradient pyramid (+ TV / residual regularisers) into a dense [3,T,T] gradient (no Adam)."""
         if self.tex_grad_dense is None:
             self.tex_grad_dense = torch.zeros(3 * self.T * self.T, dtype=torch.float32, device=self.dev)
@@ -293,7 +293,7 @@ class Engine:
             self._tex_persist = True
         cs = self._c_stage(training)
         self._ck(self.L.vhap_tex_reg_fold_adam(self.ctx, self.tex_extra.data_ptr(), self.tex_grad_dense.data_ptr(), None, None, 0.0, 1,
-                                               C.byref(cs), 1.0, self.losses.data_ptr(), self._stream()), None)
+                                               C.byref(cs), 1.0, self.losses.data_ptr() if with_losses else None, self._stream()), None)
         return self.tex_grad_dense.view(3, self.T, self.T)
 
     def _lr(self, name):
@@ -301,7 +301,33 @@ class Engine:
         table = {"translation": lr.translation, "expr": lr.expr, "lights": lr.light, "focal_length": lr.camera, "static_offset": lr.static_offset}
         return table.get(name, lr.base) * self.lr_scale
 
-    def adam_step(self, allreduce_fn=None):
+    def tex_update(self, allreduce_fn=None, deferred=False):
+        """Texture part of the Adam step on the CURRENT stream.  deferred=True: the update of the PREVIOUS step, executed at the start
+        of the next one (pipelined graph replay): no in-call fork, device Adam step - 1, no loss bookkeeping of the finished step, and
+        the regulariser loss values of the updated texture are produced for the step that is about to run."""
+        cs = self._c_stage(True)
+        s = self._stream()
+        if deferred:
+            self.L.vhap_tex_defer(self.ctx, -1)
+        if allreduce_fn is None:
+            # fused: fold + regularisers + Adam + pyramid; eagerly it runs on an aux stream right behind the fused backward
+            # (vhap_tex_reg_fold_adam waits only for the texel-gradient event), the call itself only joins
+            self._ck(self.L.vhap_tex_reg_fold_adam(self.ctx, self.tex_extra.data_ptr(), None, self.tex_m.data_ptr(), self.tex_v.data_ptr(),
+                                                   self._lr("tex"), self.step_count, C.byref(cs), 1.0,
+                                                   None if deferred else self.losses.data_ptr(), s), None)
+        else:
+            g = self.texture_grad_dense(with_losses=not deferred)   # fold + regularisers (beside the geometry backward when not deferred)
+            if self._dp_buf is not None and not deferred:
+                allreduce_fn(self._dp_buf)                 # texture gradient + gradient slab in one collective
+            else:
+                allreduce_fn(g.reshape(-1))
+            self._ck(self.L.vhap_tex_apply_grad(self.ctx, self.tex_extra.data_ptr(), g.data_ptr(), self.tex_m.data_ptr(), self.tex_v.data_ptr(),
+                                                self._lr("tex"), self.step_count, C.byref(cs), s), None)
+        if deferred:
+            self._ck(self.L.vhap_tex_reg_loss(self.ctx, self.tex_extra.data_ptr(), C.byref(cs), s), None)
+            self.L.vhap_tex_defer(self.ctx, 0)
+
+    def adam_step(self, allreduce_fn=None, texture=True):
         """torch.optim.Adam.step() over the parameter groups of the current stage (dense rows, tracker.py:1284-1293,210)."""
         opt = opt_dict_for(self.stage)
         self.step_count += 1
@@ -314,16 +340,10 @@ class Engine:
         if opt["expr"]: groups.append("expr")
         if opt["pose"]: groups += ["rotation", "translation"]
         if opt["joints"]: groups += ["neck_pose", "jaw_pose", "eyes_pose"]
-        cs = self._c_stage(True)
-        if opt["texture"] and allreduce_fn is not None:
-            g = self.texture_grad_dense()                  # fold + regularisers; runs beside the geometry backward (aux stream)
-            if self._dp_buf is not None:
-                allreduce_fn(self._dp_buf)                 # texture gradient + gradient slab in one collective
-            else:
-                allreduce_fn(g)
-            self._ck(self.L.vhap_tex_apply_grad(self.ctx, self.tex_extra.data_ptr(), g.data_ptr(), self.tex_m.data_ptr(), self.tex_v.data_ptr(),
-                                                self._lr("tex"), self.step_count, C.byref(cs), s), None)
-        if allreduce_fn is not None and not (opt["texture"] and self._dp_buf is not None):
+        tex = texture and opt["texture"]
+        if tex and allreduce_fn is not None:
+            self.tex_update(allreduce_fn)
+        if allreduce_fn is not None and not (tex and self._dp_buf is not None):
             allreduce_fn(self.grad)
         if groups:
             off = np.asarray([self.layout[g][0] for g in groups], np.int64)
@@ -332,11 +352,8 @@ class Engine:
             hp = lambda a: a.ctypes.data_as(C.c_void_p)
             self._ck(self.L.vhap_adam_multi(self.ctx, self.slab.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                                             len(groups), hp(off), hp(ln), hp(lr), self.step_count, s), None)
-        if opt["texture"] and allreduce_fn is None:
-            # issued last: the fold / Adam / mip rebuild itself runs on an aux stream right behind the fused backward
-            # (vhap_tex_reg_fold_adam waits only for the texel-gradient event); here only its join and the loss bookkeeping follow
-            self._ck(self.L.vhap_tex_reg_fold_adam(self.ctx, self.tex_extra.data_ptr(), None, self.tex_m.data_ptr(), self.tex_v.data_ptr(),
-                                                   self._lr("tex"), self.step_count, C.byref(cs), 1.0, self.losses.data_ptr(), s), None)
+        if tex and allreduce_fn is None:
+            self.tex_update(None)                          # issued last: only its join and the loss bookkeeping are on this stream
 
     def step(self, batch: Batch) -> torch.Tensor:
         """One optimisation iteration (tracker.py:1418-1435): zero_grad, energy + backward, Adam."""
@@ -347,17 +364,32 @@ class Engine:
         return losses
 
     # ------------------------------------------------------------------ CUDA-graph replay of whole steps
-    def graph_begin(self, batches, body=None):
+    def graph_begin(self, batches, body=None, reduce_fn=None, allreduce_fn=None, world=1, pipelined=True):
         """Capture one optimisation step per (batch, texture ping-pong parity) as CUDA graphs.  All step-dependent values
         (Adam step, RNG step) live in device memory (vhap_step_counters), so the graphs are replayable indefinitely.
-        `body(batch)` overrides the captured step (e.g. the data-parallel step incl. its NCCL collectives)."""
+        Data parallel: pass reduce_fn / allreduce_fn / world (the NCCL collectives are captured); `body(batch)` overrides the captured
+        step entirely (not pipelined).
+        pipelined (stages that optimise the texture photometrically): the texture update of step k -- one HBM-streaming pass, plus the
+        50 MB all-reduce when data parallel -- is the tail of the step, while the first third of the next step (FLAME, rasteriser,
+        pixel pools) never reads the texture.  The replayed graph therefore starts with the update of the PREVIOUS step on a side
+        stream and joins it right before the shading pass; the first graph_step runs an eager prologue, graph_end flushes the last
+        update.  Same arithmetic in the same order on every buffer, only the schedule differs."""
         s = self._stream()
         self._ck(self.L.vhap_step_counters(self.ctx, 1, self.step_count + 1, self.global_step, s))
         torch.cuda.synchronize(self.dev)
-        self._graphs = {}
+        opt = opt_dict_for(self.stage)
+        self._pipe = bool(pipelined and body is None and self.stage is not None and self.stage.photometric and opt["texture"])
+        self._hooks = (reduce_fn, allreduce_fn, world)
+        self._graph_batches = list(batches)
+        self._primed = False
+        self._graphs, self._graph_events = {}, []
+        if self._pipe and not hasattr(self, "_tex_stream"):
+            self._tex_stream = torch.cuda.Stream(self.dev)
         parity0 = self.L.vhap_get_cur_mip(self.ctx)
         step_save, gstep_save = self.step_count, self.global_step
-        side = torch.cuda.Stream(self.dev)
+        # the capture stream has a higher priority than the side stream of the deferred texture update (and the library's aux streams):
+        # the step's latency-bound kernel chain is scheduled ahead of the remaining CTAs of the machine-filling texture pass
+        side = torch.cuda.Stream(self.dev, priority=-1)
         for bi, batch in enumerate(batches):
             for par in (0, 1):
                 self.L.vhap_set_cur_mip(self.ctx, par)
@@ -365,27 +397,55 @@ class Engine:
                 with torch.cuda.graph(g, stream=side):
                     if body is not None:
                         body(batch)
+                        self._ck(self.L.vhap_step_advance(self.ctx, self._stream()))
                     else:
-                        self.zero_grad()
-                        self.energy(batch, backward=True, training=True)
-                        self.adam_step()
-                    self._ck(self.L.vhap_step_advance(self.ctx, self._stream()))
+                        self._step_body(batch, deferred_tex=self._pipe, texture_now=not self._pipe)
                 self._graphs[(bi, par)] = g
         self.step_count, self.global_step = step_save, gstep_save       # capture executed nothing
         self._parity = parity0
         self.L.vhap_set_cur_mip(self.ctx, parity0)
 
+    def _step_body(self, batch, deferred_tex: bool, texture_now: bool = False):
+        """one step with device-resident counters: [texture update of the previous step on a side stream] + zero_grad + energy +
+        backward + Adam of the small groups (+ the texture update right away when texture_now) + counter advance"""
+        reduce_fn, allreduce_fn, world = self._hooks
+        if deferred_tex:
+            cur = torch.cuda.current_stream(self.dev)
+            e0, e1 = torch.cuda.Event(), torch.cuda.Event()
+            e0.record(cur)
+            self._tex_stream.wait_event(e0)
+            with torch.cuda.stream(self._tex_stream):
+                self.tex_update(allreduce_fn, deferred=True)
+                e1.record(self._tex_stream)
+            self._graph_events += [e0, e1]
+            self.L.vhap_set_render_wait_event(self.ctx, C.c_void_p(e1.cuda_event))    # joined right before the shading pass
+        self.zero_grad()
+        self.energy(batch, backward=True, training=True, global_B=batch.B * world, reduce_fn=reduce_fn)
+        self.adam_step(allreduce_fn=allreduce_fn, texture=texture_now)
+        self._ck(self.L.vhap_step_advance(self.ctx, self._stream()))
+
     def graph_step(self, bi: int):
-        self._graphs[(bi, self._parity)].replay()
-        self._parity ^= 1
+        if self._pipe and not self._primed:
+            # prologue of the pipeline: the first step eagerly, leaving its texture update pending for the first replay
+            self._step_body(self._graph_batches[bi], deferred_tex=False)
+            self.step_count -= 1                           # (_step_body's adam_step counted on the host; counted below like a replay)
+            self._primed = True
+        else:
+            self._graphs[(bi, self._parity)].replay()
+            self._parity ^= 1
         self.step_count += 1
         self.global_step += 1
 
     def graph_end(self):
         torch.cuda.synchronize(self.dev)
         self.L.vhap_set_cur_mip(self.ctx, self._parity)
+        if self._pipe and self._primed:
+            self.tex_update(self._hooks[1], deferred=True)  # flush the pending texture update of the last step
+            self._parity ^= 1
+            torch.cuda.synchronize(self.dev)
         self._ck(self.L.vhap_step_counters(self.ctx, 0, 0, 0, self._stream()))
-        self._graphs = {}
+        self._graphs, self._graph_events = {}, []
+        self._primed = False
 
     # ------------------------------------------------------------------ logging planes (render_out dict)
     def render_planes(self, batch: Batch, training=False) -> Dict[str, torch.Tensor]:

@@ -58,6 +58,13 @@ class DataParallelStep:
         e.energy(batch, backward=True, training=True, global_B=gB, reduce_fn=red)
         e.adam_step(allreduce_fn=(lambda t: allreduce_sum(t, self.group)) if self.world > 1 else None)
 
+    def graph_begin(self, batches, pipelined=True):
+        """Engine.graph_begin with this group's collectives captured into the step graphs (pipelined: the texture all-reduce of step k
+        runs at the start of step k+1, hidden behind FLAME / rasteriser / pools)"""
+        red = (lambda a, b: reduce_forward_slab(a, b, self.group)) if self.world > 1 else None
+        allr = (lambda t: allreduce_sum(t, self.group)) if self.world > 1 else None
+        self.e.graph_begin(batches, reduce_fn=red, allreduce_fn=allr, world=self.world, pipelined=pipelined)
+
     def step(self, batch):
         e = self.e
         e.zero_grad()
