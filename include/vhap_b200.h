@@ -200,6 +200,7 @@ int vhap_set_tex_grad_persistent(vhap_ctx* ctx, int32_t on);
  *      the next forward that do not read the texture, and is joined right before the shading pass --------------------------- */
 int vhap_tex_defer(vhap_ctx* ctx, int32_t step_bias);           /* next texture-update call: no in-call fork; device Adam step + step_bias */
 int vhap_tex_reg_loss(vhap_ctx* ctx, const float* tex_extra, const vhap_stage_cfg* cfg, void* stream);   /* regulariser loss values of the current texture */
+int vhap_assemble_losses(vhap_ctx* ctx, const vhap_stage_cfg* cfg, float* losses_out, void* stream);   /* loss vector from the accumulators + vhap_tex_reg_loss values */
 int vhap_set_render_wait_event(vhap_ctx* ctx, void* cuda_event);   /* one-shot wait inserted before the first texture read of the next forward */
 
 /* ---- per-kernel accounting: every kernel launch is counted; with profiling enabled CUDA events bracket each launch on the

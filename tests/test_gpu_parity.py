@@ -277,12 +277,20 @@ def test_graph_replay_matches_eager(eng_small, pipelined):
         e.global_step = 5
         if mode == "graph":
             e.graph_begin([batch], pipelined=pipelined)
+        step_losses = []
         for i in range(2):                          # pipelined: eager prologue + 1 replay + flush in graph_end
             e.graph_step(0) if mode == "graph" else e.step(batch)
+            step_losses.append(e.loss_dict())
         if mode == "graph":
             e.graph_end()
         torch.cuda.synchronize()
         res.append({k: v.copy() for k, v in e.get_params().items()})
+        res[-1]["__losses__"] = step_losses
+    losses = [r.pop("__losses__") for r in res]
+    for i in range(2):                              # every step's loss vector is complete (incl. the texture regularisers) in graph mode too
+        for name in ("reg_tex_tv", "photo", "total"):
+            a, b = losses[2][i][name], losses[0][i][name]
+            assert abs(a - b) <= 2e-3 * max(abs(b), 1e-6), (i, name, a, b)
     for k in res[0]:
         noise = rel(res[1][k], res[0][k])
         # a broken replay (stuck Adam / RNG step counter, wrong texture ping-pong parity) changes the trajectory by O(1e-1)

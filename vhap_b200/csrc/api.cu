@@ -564,6 +564,12 @@ extern "C" int vhap_tex_reg_loss(vhap_ctx* ctx, const float* tex_extra, const vh
   LAST();
   return 0;
 }
+// re-assemble the loss vector of the step that just ran (accumulators + the current texture-regulariser loss values)
+extern "C" int vhap_assemble_losses(vhap_ctx* ctx, const vhap_stage_cfg* cfg, float* losses_out, void* stream) {
+  LAUNCH(ctx, KID_ASSEMBLE, (cudaStream_t)stream, k_assemble_losses<<<1, 32, 0, (cudaStream_t)stream>>>(ctx->acc, *cfg, 0.f, nullptr, 0, losses_out, ctx->tex_loss));
+  LAST();
+  return 0;
+}
 // one-shot: the next render forward waits for `event` (a cudaEvent_t recorded by the caller) after the pixel pools are built and
 // before the first kernel that reads the texture
 extern "C" int vhap_set_render_wait_event(vhap_ctx* ctx, void* event) { ctx->render_wait_ev = (cudaEvent_t)event; return 0; }

@@ -301,7 +301,7 @@ class Engine:
         table = {"translation": lr.translation, "expr": lr.expr, "lights": lr.light, "focal_length": lr.camera, "static_offset": lr.static_offset}
         return table.get(name, lr.base) * self.lr_scale
 
-    def tex_update(self, allreduce_fn=None, deferred=False):
+    def tex_update(self, allreduce_fn=None, deferred=False, reg_loss=True):
         """Texture part of the Adam step on the CURRENT stream.  deferred=True: the update of the PREVIOUS step, executed at the start
         of the next one (pipelined graph replay): no in-call fork, device Adam step - 1, no loss bookkeeping of the finished step, and
         the regulariser loss values of the updated texture are produced for the step that is about to run."""
@@ -324,7 +324,8 @@ class Engine:
             self._ck(self.L.vhap_tex_apply_grad(self.ctx, self.tex_extra.data_ptr(), g.data_ptr(), self.tex_m.data_ptr(), self.tex_v.data_ptr(),
                                                 self._lr("tex"), self.step_count, C.byref(cs), s), None)
         if deferred:
-            self._ck(self.L.vhap_tex_reg_loss(self.ctx, self.tex_extra.data_ptr(), C.byref(cs), s), None)
+            if reg_loss:
+                self._ck(self.L.vhap_tex_reg_loss(self.ctx, self.tex_extra.data_ptr(), C.byref(cs), s), None)
             self.L.vhap_tex_defer(self.ctx, 0)
 
     def adam_step(self, allreduce_fn=None, texture=True):
@@ -414,19 +415,29 @@ class Engine:
             e0, e1 = torch.cuda.Event(), torch.cuda.Event()
             e0.record(cur)
             self._tex_stream.wait_event(e0)
+            e2 = torch.cuda.Event()
+            cs = self._c_stage(True)
             with torch.cuda.stream(self._tex_stream):
-                self.tex_update(allreduce_fn, deferred=True)
-                e1.record(self._tex_stream)
-            self._graph_events += [e0, e1]
+                self.tex_update(allreduce_fn, deferred=True, reg_loss=False)
+                e1.record(self._tex_stream)               # the new pyramid is complete: what the shading pass waits for
+                # regulariser loss VALUES of the updated texture: only the loss vector needs them, joined at the end of the step
+                self._ck(self.L.vhap_tex_reg_loss(self.ctx, self.tex_extra.data_ptr(), C.byref(cs), self._stream()), None)
+                e2.record(self._tex_stream)
+            self._graph_events += [e0, e1, e2]
             self.L.vhap_set_render_wait_event(self.ctx, C.c_void_p(e1.cuda_event))    # joined right before the shading pass
         self.zero_grad()
         self.energy(batch, backward=True, training=True, global_B=batch.B * world, reduce_fn=reduce_fn)
         self.adam_step(allreduce_fn=allreduce_fn, texture=texture_now)
+        if deferred_tex:
+            torch.cuda.current_stream(self.dev).wait_event(e2)
+            self._ck(self.L.vhap_assemble_losses(self.ctx, C.byref(cs), self.losses.data_ptr(), self._stream()), None)
         self._ck(self.L.vhap_step_advance(self.ctx, self._stream()))
 
     def graph_step(self, bi: int):
         if self._pipe and not self._primed:
             # prologue of the pipeline: the first step eagerly, leaving its texture update pending for the first replay
+            cs = self._c_stage(True)
+            self._ck(self.L.vhap_tex_reg_loss(self.ctx, self.tex_extra.data_ptr(), C.byref(cs), self._stream()), None)   # its loss vector
             self._step_body(self._graph_batches[bi], deferred_tex=False)
             self.step_count -= 1                           # (_step_body's adam_step counted on the host; counted below like a replay)
             self._primed = True
