@@ -323,3 +323,29 @@ def test_data_parallel_texture_path_matches_fused(eng_small):
     for k in res[0][0]:
         assert rel(res[1][0][k], res[0][0][k]) < 2e-3, (k, rel(res[1][0][k], res[0][0][k]))
     assert abs(res[1][1][0] - res[0][1][0]) < 1e-3 * abs(res[0][1][0])
+
+
+def test_pipelined_replay_flushes_on_read(eng_small):
+    """reading the parameters in the middle of a pipelined replay applies the pending texture update and restarts the pipeline"""
+    e, sc = eng_small
+    batch = e.stage_sample(sc["rgb16"].to(torch.float32), sc["lmk2d"], sc["ts"])
+    res = []
+    for mode in ("eager", "graph"):
+        e.load_params(sc["params"])
+        e.set_stage("rgb_global_tracking")
+        e.inject_random(None, None, None)
+        e.global_step = 7
+        mid = None
+        if mode == "graph":
+            e.graph_begin([batch], pipelined=True)
+        for i in range(2):
+            e.graph_step(0) if mode == "graph" else e.step(batch)
+            if i == 0:
+                mid = e.get_params()["tex_extra"].copy()          # graph mode: flush + new prologue on the next step
+        if mode == "graph":
+            e.graph_end()
+        torch.cuda.synchronize()
+        res.append((mid, {k: v.copy() for k, v in e.get_params().items()}))
+    assert rel(res[1][0], res[0][0]) < 1e-3
+    for k in res[0][1]:
+        assert rel(res[1][1][k], res[0][1][k]) < 3e-3, (k, rel(res[1][1][k], res[0][1][k]))

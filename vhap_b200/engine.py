@@ -128,6 +128,7 @@ class Engine:
         self.rebuild_texture()
 
     def get_params(self) -> Dict[str, np.ndarray]:
+        self._flush_pending_tex()                  # (pipelined graph replay keeps one texture update in flight)
         out = {k: v.detach().cpu().numpy().copy() for k, v in self.p.items()}
         out["tex_extra"] = self.tex_extra.cpu().numpy().reshape(3, self.T, self.T)
         return out
@@ -447,19 +448,28 @@ class Engine:
         self.step_count += 1
         self.global_step += 1
 
+    def _flush_pending_tex(self):
+        """pipelined replay: apply the texture update that is still pending from the last replayed step (eagerly, on the current
+        stream).  The next graph_step then starts the pipeline again with its eager prologue."""
+        if getattr(self, "_pipe", False) and self._primed:
+            self.L.vhap_set_cur_mip(self.ctx, self._parity)     # the replays did not touch the host-side ping-pong index
+            self.tex_update(self._hooks[1], deferred=True)
+            self._parity ^= 1
+            self._primed = False
+
     def graph_end(self):
         torch.cuda.synchronize(self.dev)
+        self._flush_pending_tex()
         self.L.vhap_set_cur_mip(self.ctx, self._parity)
-        if self._pipe and self._primed:
-            self.tex_update(self._hooks[1], deferred=True)  # flush the pending texture update of the last step
-            self._parity ^= 1
-            torch.cuda.synchronize(self.dev)
+        torch.cuda.synchronize(self.dev)
         self._ck(self.L.vhap_step_counters(self.ctx, 0, 0, 0, self._stream()))
         self._graphs, self._graph_events = {}, []
         self._primed = False
+        self._pipe = False
 
     # ------------------------------------------------------------------ logging planes (render_out dict)
     def render_planes(self, batch: Batch, training=False) -> Dict[str, torch.Tensor]:
+        self._flush_pending_tex()
         self.L.vhap_set_want_planes(self.ctx, 1)
         self.energy(batch, backward=False, training=training)
         self.L.vhap_set_want_planes(self.ctx, 0)
