@@ -133,6 +133,19 @@ class Engine:
         out["tex_extra"] = self.tex_extra.cpu().numpy().reshape(3, self.T, self.T)
         return out
 
+    # ------------------------------------------------------------------ on-disk format (tracker.py:79-129, 1152-1218)
+    def save_result(self, out_dir, timestep_ids, n_processed_frames, image_size, fname=None, epoch=None):
+        """FlameTracker.save_result: writes tracked_flame_params[_<epoch>].npz with the reference's keys / shapes (vhap_b200/io_params.py)."""
+        from . import io_params
+        rep = io_params.engine_params_to_report(self.get_params(), timestep_ids, n_processed_frames, image_size, calibrated=self.cfg.calibrated)
+        return io_params.save_tracked_flame_params(out_dir, rep, fname, epoch)
+
+    def load_from_tracked_flame_params(self, fp, warn=print):
+        """FlameTracker.load_from_tracked_flame_params: the reference's loader semantics (first min(N_t, len) rows, optional keys)."""
+        from . import io_params
+        rep = io_params.load_tracked_flame_params(fp)
+        self.load_params(io_params.report_to_engine_params(rep, self.get_params(), self.n_t, calibrated=self.cfg.calibrated, warn=warn))
+
     def rebuild_texture(self):
         self._ck(self.L.vhap_tex_rebuild(self.ctx, self.tex_extra.data_ptr(), self._stream()), None)
 
