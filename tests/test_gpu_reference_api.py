@@ -94,6 +94,11 @@ def test_renderer_rasterize_and_render_rgba_autograd():
     assert (ids_ref != ids_got).sum() <= 4
     bad = (np.abs(out["rgba"].detach().cpu().numpy() - oo["rgba"].detach().numpy()).max(-1) > 2e-4)
     assert bad.mean() < 0.005
+    # 'aa' = pixels changed by the antialias (render_nvdiffrast.py:466), 3 identical float channels
+    aa_ref = ((oo["rgba_pre"] - oo["rgba"]) != 0).any(-1).numpy()
+    aa_got = out["aa"].cpu().numpy()
+    assert aa_got.shape == aa_ref.shape + (3,) and set(np.unique(aa_got)) <= {0.0, 1.0}
+    assert (aa_got[..., 0].astype(bool) != aa_ref).mean() < 0.005 and aa_ref.any()
     assert abs(loss.item() - lo_.item()) < 2e-3 * abs(lo_.item())
     assert rel(lights.grad.cpu().numpy(), lo.grad.numpy()) < 2e-3
     assert l2rel(tex.grad.cpu().numpy()[0], texo.grad.numpy()) < 2e-2

@@ -284,6 +284,8 @@ VH_HD void passB_body(const PassArgs& P, int b, int y, int x, float* acc) {
   uint8_t sg = (uint8_t)((e0 > 0.f ? 1 : (e0 < 0.f ? 2 : 0)) | ((e1 > 0.f ? 1 : (e1 < 0.f ? 2 : 0)) << 2) | ((e2 > 0.f ? 1 : (e2 < 0.f ? 2 : 0)) << 4));
   P.signs[pix] = sg;
   if (P.final_rgba) { float* o = P.final_rgba + pix * 4; o[0] = out.x; o[1] = out.y; o[2] = out.z; o[3] = out.w; }
+  // 'aa' plane of the reference's render_out (render_nvdiffrast.py:466: pixels the antialias changed), kept in the free .w of the albedo plane
+  if (P.plane_albedo) P.plane_albedo[pix].w = (out.x != Dp.x || out.y != Dp.y || out.z != Dp.z || out.w != Dp.w) ? 1.f : 0.f;
 }
 
 VH_HD f3 sign_grad(uint8_t sg, float scale) {

@@ -280,7 +280,7 @@ class B200Renderer(torch.nn.Module):
         tex_chw = tex[0] if tex.dim() == 4 else tex
         rgba, albedo, normal, diffuse, cid = _RenderFn.apply(self, verts_clip, v_normal, tex_chw, lights.reshape(9, 3), batch, cs)
         return {"albedo": albedo[..., :3], "normal": normal[..., :3], "diffuse": diffuse[..., :3], "diffuse_detach_normal": diffuse[..., :3].detach(),
-                "rgba": rgba, "aa": torch.zeros_like(rgba[..., :3]), "cid": cid[..., :1].long()}
+                "rgba": rgba, "aa": albedo[..., 3:4].detach().expand(-1, -1, -1, 3).contiguous(), "cid": cid[..., :1].long()}
 
 
 class _NormalsFn(torch.autograd.Function):
