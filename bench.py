@@ -5,8 +5,15 @@ A "step" is one optimisation iteration of FlameTracker.optimize_iter (vhap/model
 `rgb_global_tracking` (every parameter group optimised, base.py:291-295): FLAME forward -> landmark energy -> rasterise ->
 shade -> disturbance + antialias + L1 -> analytic backward -> regularisers -> Adam (2048^2 texture included), on one batch
 of synthetic frames.  Workload at N GPUs: configs[1] "monocular 512x512 batch_size=16 photometric tracking" PER GPU (weak
-scaling: global batch 16 N, frames sharded one shard per rank, one NCCL allreduce of the shared-parameter gradients per
-Adam step).  `--size 1024` selects the 1024^2 variant.
+scaling: global batch 16 N, frames sharded one shard per rank; per Adam step one 4-float all-gather and one all-reduce of the
+shared-parameter + texture gradients, captured into the step graphs).  `--size 1024` selects the 1024^2 variant.
+
+Timed regions (all CUDA events, max over ranks): (1) `value`: K CUDA-graph replays with the inputs resident in HBM, 4 rotating
+staged batches; by default the replay is PIPELINED (each replay = the texture update of the previous step beside the start of
+this step + everything else of this step; K replays = K complete steps of work; --no-pipeline for the plain order);
+(2) `e2e`: the same plus, every step, the pinned-host -> device copy of that step's inputs (prefetched one step ahead on a
+copy stream) and the device -> host read of the loss vector; (3) per-kernel times: the same steps launched eagerly with events
+around every kernel and the aux-stream overlap off (roofline of the dominant kernel; `traffic` from the committed ncu capture).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
