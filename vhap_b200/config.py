@@ -72,9 +72,18 @@ class StageConfig:                 # base.py:215-295
     align_boundary_except: Tuple[str, ...] = ("bottomline",)
 
 
+# step / epoch counts of the reference's pipeline (base.py:228-295): how many optimisation steps a stage runs per call
+STAGE_STEPS = {"lmk_init_rigid": 500, "lmk_init_all": 500, "lmk_sequential_tracking": 50, "rgb_init_texture": 500, "rgb_init_all": 500,
+               "rgb_init_offset": 500, "rgb_sequential_tracking": 50}
+STAGE_EPOCHS = {"lmk_global_tracking": 30, "rgb_global_tracking": 30}
+
+# (the reference also lists "dynamic_offset" for the two rgb tracking stages; dynamic offsets are off by default, base.py:69, and
+#  rejected by this engine)
 STAGES = {
     "lmk_init_rigid": StageConfig("lmk_init_rigid", ("cam", "pose"), False, False, (), ()),
     "lmk_init_all": StageConfig("lmk_init_all", ("cam", "pose", "shape", "joints", "expr"), False, False, (), ()),
+    "lmk_sequential_tracking": StageConfig("lmk_sequential_tracking", ("pose", "joints", "expr"), False, False, (), ()),
+    "lmk_global_tracking": StageConfig("lmk_global_tracking", ("cam", "pose", "shape", "joints", "expr"), False, False, (), ()),
     "rgb_init_texture": StageConfig("rgb_init_texture", ("cam", "shape", "texture", "lights"), True, False,
                                     ("hair", "boundary", "neck"), ("hair", "boundary")),
     "rgb_init_all": StageConfig("rgb_init_all", ("cam", "pose", "shape", "joints", "expr", "texture", "lights"), True, True,
