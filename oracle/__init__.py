@@ -10,6 +10,12 @@ Pinning status
     outputs of the reference's own `vhap/model/lbs.py` and `vhap/util/mesh.py`, imported unmodified
     in the authoring container; vectors in tests/golden/lbs_golden.npz, generator
     tests/golden/make_golden.py.
+  * camera transforms, vertex normals, SH shading, detach_by_indices (oracle/camera.py, oracle/render.py
+    compute_v_normals / sh_shading): PINNED against outputs and autograd gradients of the reference's own
+    `vhap/util/render_nvdiffrast.py` methods (imported unmodified, a stub standing in for its absent nvdiffrast
+    import); vectors in tests/golden/render_golden.npz, generator tests/golden/make_render_golden.py.
+  * loss weights / learning rates / stage table (vhap_b200/config.py): PINNED against the reference's dataclasses
+    (tests/golden/config_golden.json, generator tests/golden/make_config_golden.py).
   * rasterise / interpolate / texture / antialias (oracle/raster.py, oracle/render.py):
     PARITY UNPINNED.  The arithmetic lives in the third-party dependency `nvdiffrast`
     (ShenhanQian/nvdiffrast@backface-culling, pinned by branch name only at

@@ -25,21 +25,20 @@ def projection_from_intrinsics(K, image_size, near=0.1, far=10.0):
 
 
 def world_to_camera(vtx, RT):
-    """render_nvdiffrast.py:162-179.  vtx [B,V,3], RT [B,3,4] -> [B,V,4]."""
+    """render_nvdiffrast.py:162-179.  vtx [B,V,3], RT [B,3,4] -> [B,V,3] (a [B,4,4] RT gives [B,V,4], like the reference)."""
     B = vtx.shape[0]
-    mv = torch.zeros(B, 4, 4, dtype=vtx.dtype, device=vtx.device)
-    mv[:, :3, :] = RT.to(vtx.dtype).expand(B, -1, -1)
-    mv[:, 3, 3] = 1
+    RT = RT.to(vtx.dtype).expand(B, -1, -1)
     posw = torch.cat([vtx, torch.ones_like(vtx[..., :1])], -1)
-    return torch.bmm(posw, mv.transpose(-1, -2))
+    return torch.bmm(posw, RT.transpose(-1, -2))
 
 
 def camera_to_clip(vtx_cam, K, image_size):
-    """render_nvdiffrast.py:181-197."""
-    proj = projection_from_intrinsics(K, image_size)
-    if proj.shape[0] < vtx_cam.shape[0]:
-        proj = proj.expand(vtx_cam.shape[0], -1, -1)
-    return torch.bmm(vtx_cam, proj.transpose(-1, -2))
+    """render_nvdiffrast.py:181-197.  vtx_cam [B,V,3] (w = 1 appended) or [B,V,4]."""
+    proj = projection_from_intrinsics(K, image_size).to(vtx_cam.dtype)
+    posw = torch.cat([vtx_cam, torch.ones_like(vtx_cam[..., :1])], -1) if vtx_cam.shape[-1] == 3 else vtx_cam
+    if proj.shape[0] < posw.shape[0]:
+        proj = proj.expand(posw.shape[0], -1, -1)
+    return torch.bmm(posw, proj.transpose(-1, -2))
 
 
 def world_to_clip(vtx, RT, K, image_size):

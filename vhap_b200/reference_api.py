@@ -192,11 +192,9 @@ class B200Renderer(torch.nn.Module):
         return proj
 
     def world_to_camera(self, vtx, RT):
-        mv = torch.nn.functional.pad(RT, [0, 0, 0, 1]) if RT.shape[-2] == 3 else RT
-        if RT.shape[-2] == 3:
-            mv = mv.clone(); mv[..., 3, 3] = 1
+        # [B,3,4] extrinsics give [B,V,3], [B,4,4] give [B,V,4] (render_nvdiffrast.py:162-179)
         posw = torch.cat([vtx, torch.ones_like(vtx[..., :1])], -1) if vtx.shape[-1] == 3 else vtx
-        return torch.bmm(posw, mv.transpose(-1, -2))
+        return torch.bmm(posw, RT.transpose(-1, -2))
 
     def camera_to_clip(self, vtx, K, image_size):
         proj = self.projection_from_intrinsics(K, image_size)
