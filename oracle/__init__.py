@@ -14,6 +14,9 @@ Pinning status
     compute_v_normals / sh_shading): PINNED against outputs and autograd gradients of the reference's own
     `vhap/util/render_nvdiffrast.py` methods (imported unmodified, a stub standing in for its absent nvdiffrast
     import); vectors in tests/golden/render_golden.npz, generator tests/golden/make_render_golden.py.
+  * landmark energy and every regulariser (oracle/energy.py lmk_energy / regularization_energy): PINNED against values and
+    gradients of the reference's own FlameTracker.compute_lmk_energy / compute_regularization_energy (tracker.py:347-389,
+    480-690) run on a bare instance; tests/golden/energy_golden.npz, generator tests/golden/make_energy_golden.py.
   * loss weights / learning rates / stage table (vhap_b200/config.py): PINNED against the reference's dataclasses
     (tests/golden/config_golden.json, generator tests/golden/make_config_golden.py).
   * rasterise / interpolate / texture / antialias (oracle/raster.py, oracle/render.py):

@@ -77,6 +77,83 @@ def scale_vertex_weights_by_region(model_data, V, scale, regions, dtype):
     return w
 
 
+def regularization_energy(params, ts, stage, cfg, model_data, verts_cano=None, diffuse_detach_normal=None, lap=None, tex_painted=None,
+                          uvmask_res=None):
+    """compute_regularization_energy (tracker.py:480-605) + the helpers it calls (:607-690).  `diffuse_detach_normal` [B,3,H,W]
+    (render_out permuted like tracker.py:322) or None when the stage is not photometric.  Returns the log dict of weighted terms."""
+    from vhap_b200.config import opt_dict_for
+    w = cfg.w
+    dt = params["shape"].dtype
+    ts = torch.as_tensor(np.asarray(ts)).long()
+    idx_prev = (ts - 1).clamp(0, params["expr"].shape[0] - 1)
+    log = {}
+    opt = opt_dict_for(stage)
+    tracking = "tracking" in stage.name
+    if opt["pose"] and tracking:
+        log["smooth_pose"] = ((params["translation"][ts] - params["translation"][idx_prev].detach()) ** 2).mean() * w.smooth_trans \
+            + ((params["rotation"][ts] - params["rotation"][idx_prev].detach()) ** 2).mean() * w.smooth_rot
+    if opt["joints"]:
+        log["reg_joint"] = joint_L2_energy(params["neck_pose"][ts], params["jaw_pose"][ts], params["eyes_pose"][ts], w)
+        if tracking:
+            E = 0
+            for k, ww in (("neck_pose", w.smooth_neck), ("jaw_pose", w.smooth_jaw), ("eyes_pose", w.smooth_eyes)):
+                E = E + ((params[k][ts] - params[k][idx_prev].detach()) ** 2).mean() * ww
+            log["smooth_joint"] = E
+    if opt["expr"]:
+        log["reg_expr"] = w.reg_expr * (params["expr"][ts] ** 2).mean()
+        if tracking:
+            log["smooth_expr"] = ((params["expr"][ts] - params["expr"][idx_prev].detach()) ** 2).mean() * w.smooth_expr
+    if opt["shape"]:
+        log["reg_shape"] = w.reg_shape * (params["shape"] ** 2).mean()
+    if opt["texture"]:
+        if w.reg_tex_tv is not None:
+            tex = (tex_painted if tex_painted is not None else 0) + params["tex_extra"]
+            tv_y = (tex[..., :-1, :] - tex[..., 1:, :]) ** 2
+            tv_x = (tex[..., :, :-1] - tex[..., :, 1:]) ** 2
+            tv = tv_y.reshape(3, -1) + tv_x.reshape(3, -1)          # NB: only valid for square T (as in the reference)
+            w_tv = w.reg_tex_tv * cfg.scale_factor ** 2
+            if cfg.n_downsample_rgb is not None:
+                w_tv /= cfg.n_downsample_rgb ** 2
+            log["reg_tex_tv"] = w_tv * tv.mean()
+        if w.reg_tex_res_clusters is not None:
+            m = torch.as_tensor(uvmask_res) if uvmask_res is not None else torch.as_tensor(model_data.uvmask_res)
+            T = params["tex_extra"].shape[-1]
+            if m.shape[-1] != T:
+                m = m[:: m.shape[0] // T, :: m.shape[1] // T]
+            log["reg_tex_res_clusters"] = w.reg_tex_res_clusters * (params["tex_extra"] ** 2 * m[None].to(dt)).mean()
+    if opt["lights"]:
+        if w.reg_light is not None:
+            lu = torch.zeros(9, 3, dtype=dt)
+            lu[0] = np.sqrt(4 * np.pi)
+            log["reg_light"] = w.reg_light * ((params["lights"] - lu) ** 2).mean()
+        if w.reg_diffuse is not None and diffuse_detach_normal is not None:
+            diffuse = diffuse_detach_normal
+            log["reg_diffuse"] = w.reg_diffuse * (F.relu(diffuse.max() - 1) + diffuse.var(dim=1).mean())
+    if opt["static_offset"] and params.get("static_offset") is not None:
+        offset = params["static_offset"]
+        V = offset.shape[1]
+        if w.reg_offset_lap is not None:
+            Lm = lap if lap is not None else laplacian_dense(model_data, dt)
+            base = (verts_cano - offset).detach()
+            diff = ((Lm @ (base + offset)) - (Lm @ base).detach()) ** 2
+            diff = diff.sum(-1, keepdim=True)
+            if len(w.reg_offset_lap_relax_for) > 0:
+                diff = diff * scale_vertex_weights_by_region(model_data, V, w.reg_offset_lap_relax_coef, w.reg_offset_lap_relax_for, dt)
+            log["reg_offset_lap"] = w.reg_offset_lap * diff.mean()
+        if w.reg_offset is not None:
+            ro = offset.abs()
+            if len(w.reg_offset_relax_for) > 0:
+                ro = ro * scale_vertex_weights_by_region(model_data, V, w.reg_offset_relax_coef, w.reg_offset_relax_for, dt)
+            log["reg_offset"] = w.reg_offset * ro.mean()
+        if w.reg_offset_rigid is not None:
+            r = 0
+            for region in w.reg_offset_rigid_for:
+                vids = torch.as_tensor(model_data.get_vid_by_region([region]))
+                r = r + offset[:, vids, :].var(dim=-2).mean()
+            log["reg_offset_rigid"] = w.reg_offset_rigid * r
+    return log
+
+
 def compute_energy(params, sample, stage, cfg, model_data, model, lap=None, disturbance=None, tex_painted=None,
                    return_aux=False):
     """tracker.py:692-750.  `stage` is a vhap_b200.config.StageConfig or None (evaluation mode).
@@ -126,70 +203,8 @@ def compute_energy(params, sample, stage, cfg, model_data, model, lap=None, dist
         log["photo"] = w.photo * ((gt_rgb.to(dt) - pred_rgb).abs().sum() / n_fg)  # tracker.py:438-439
         aux.update(render=out, rast=rast, rast_db=rast_db, clip=clip, n_fg=n_fg)
     if stage is not None:
-        opt = opt_dict_for(stage)
-        tracking = "tracking" in stage.name
-        if opt["pose"] and tracking:
-            log["smooth_pose"] = ((params["translation"][ts] - params["translation"][idx_prev].detach()) ** 2).mean() * w.smooth_trans \
-                + ((params["rotation"][ts] - params["rotation"][idx_prev].detach()) ** 2).mean() * w.smooth_rot
-        if opt["joints"]:
-            log["reg_joint"] = joint_L2_energy(params["neck_pose"][ts], params["jaw_pose"][ts], params["eyes_pose"][ts], w)
-            if tracking:
-                E = 0
-                for k, ww in (("neck_pose", w.smooth_neck), ("jaw_pose", w.smooth_jaw), ("eyes_pose", w.smooth_eyes)):
-                    E = E + ((params[k][ts] - params[k][idx_prev].detach()) ** 2).mean() * ww
-                log["smooth_joint"] = E
-        if opt["expr"]:
-            log["reg_expr"] = w.reg_expr * (params["expr"][ts] ** 2).mean()
-            if tracking:
-                log["smooth_expr"] = ((params["expr"][ts] - params["expr"][idx_prev].detach()) ** 2).mean() * w.smooth_expr
-        if opt["shape"]:
-            log["reg_shape"] = w.reg_shape * (params["shape"] ** 2).mean()
-        if opt["texture"]:
-            if w.reg_tex_tv is not None:
-                tex = (tex_painted if tex_painted is not None else 0) + params["tex_extra"]
-                tv_y = (tex[..., :-1, :] - tex[..., 1:, :]) ** 2
-                tv_x = (tex[..., :, :-1] - tex[..., :, 1:]) ** 2
-                tv = tv_y.reshape(3, -1) + tv_x.reshape(3, -1)          # NB: only valid for square T (as in the reference)
-                w_tv = w.reg_tex_tv * cfg.scale_factor ** 2
-                if cfg.n_downsample_rgb is not None:
-                    w_tv /= cfg.n_downsample_rgb ** 2
-                log["reg_tex_tv"] = w_tv * tv.mean()
-            if w.reg_tex_res_clusters is not None:
-                m = torch.as_tensor(sample["uvmask_res"]) if "uvmask_res" in sample else torch.as_tensor(model_data.uvmask_res)
-                T = params["tex_extra"].shape[-1]
-                if m.shape[-1] != T:
-                    m = m[:: m.shape[0] // T, :: m.shape[1] // T]
-                log["reg_tex_res_clusters"] = w.reg_tex_res_clusters * (params["tex_extra"] ** 2 * m[None].to(dt)).mean()
-        if opt["lights"]:
-            if w.reg_light is not None:
-                lu = torch.zeros(9, 3, dtype=dt)
-                lu[0] = np.sqrt(4 * np.pi)
-                log["reg_light"] = w.reg_light * ((params["lights"] - lu) ** 2).mean()
-            if w.reg_diffuse is not None and photometric:
-                diffuse = aux["render"]["diffuse_detach_normal"].permute(0, 3, 1, 2)
-                log["reg_diffuse"] = w.reg_diffuse * (F.relu(diffuse.max() - 1) + diffuse.var(dim=1).mean())
-        if opt["static_offset"] and params.get("static_offset") is not None:
-            offset = params["static_offset"]
-            V = offset.shape[1]
-            if w.reg_offset_lap is not None:
-                Lm = lap if lap is not None else laplacian_dense(model_data, dt)
-                base = (verts_cano - offset).detach()
-                diff = ((Lm @ (base + offset)) - (Lm @ base).detach()) ** 2
-                diff = diff.sum(-1, keepdim=True)
-                if len(w.reg_offset_lap_relax_for) > 0:
-                    diff = diff * scale_vertex_weights_by_region(model_data, V, w.reg_offset_lap_relax_coef, w.reg_offset_lap_relax_for, dt)
-                log["reg_offset_lap"] = w.reg_offset_lap * diff.mean()
-            if w.reg_offset is not None:
-                ro = offset.abs()
-                if len(w.reg_offset_relax_for) > 0:
-                    ro = ro * scale_vertex_weights_by_region(model_data, V, w.reg_offset_relax_coef, w.reg_offset_relax_for, dt)
-                log["reg_offset"] = w.reg_offset * ro.mean()
-            if w.reg_offset_rigid is not None:
-                r = 0
-                for region in w.reg_offset_rigid_for:
-                    vids = torch.as_tensor(model_data.get_vid_by_region([region]))
-                    r = r + offset[:, vids, :].var(dim=-2).mean()
-                log["reg_offset_rigid"] = w.reg_offset_rigid * r
+        diff_dn = aux["render"]["diffuse_detach_normal"].permute(0, 3, 1, 2) if (photometric and "render" in aux) else None
+        log.update(regularization_energy(params, ts, stage, cfg, model_data, verts_cano, diff_dn, lap, tex_painted, sample.get("uvmask_res")))
     E_total = torch.stack([v for v in log.values()]).sum()
     log["total"] = E_total
     if return_aux:
