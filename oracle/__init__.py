@@ -17,6 +17,9 @@ Pinning status
   * landmark energy and every regulariser (oracle/energy.py lmk_energy / regularization_energy): PINNED against values and
     gradients of the reference's own FlameTracker.compute_lmk_energy / compute_regularization_energy (tracker.py:347-389,
     480-690) run on a bare instance; tests/golden/energy_golden.npz, generator tests/golden/make_energy_golden.py.
+  * photometric glue around the renderer (compute_energy: background modes, UV flip, align_*_except look-ups, disturbance flag,
+    L1 normalisation + gradient): PINNED against the reference's FlameTracker.compute_photometric_energy run with a recording fake
+    renderer; tests/golden/photo_golden.npz, generator tests/golden/make_photo_golden.py.
   * loss weights / learning rates / stage table (vhap_b200/config.py): PINNED against the reference's dataclasses
     (tests/golden/config_golden.json, generator tests/golden/make_config_golden.py).
   * rasterise / interpolate / texture / antialias (oracle/raster.py, oracle/render.py):
