@@ -22,7 +22,10 @@ Pinning status
     renderer; tests/golden/photo_golden.npz, generator tests/golden/make_photo_golden.py.
   * loss weights / learning rates / stage table (vhap_b200/config.py): PINNED against the reference's dataclasses
     (tests/golden/config_golden.json, generator tests/golden/make_config_golden.py).
-  * rasterise / interpolate / texture / antialias (oracle/raster.py, oracle/render.py):
+  * render_rgba minus the nvdiffrast ops (oracle/render.py render_rgba / disturb): PINNED against the reference's own
+    NVDiffRenderer.render_rgba run end to end with its dr.* calls served by this oracle's op restatements and its random draws
+    injected (values + gradients); tests/golden/rgba_golden.npz, generator tests/golden/make_rgba_golden.py.
+  * the nvdiffrast ops themselves -- rasterise / interpolate / texture / antialias (oracle/raster.py, oracle/render.py):
     PARITY UNPINNED.  The arithmetic lives in the third-party dependency `nvdiffrast`
     (ShenhanQian/nvdiffrast@backface-culling, pinned by branch name only at
     /root/reference/pyproject.toml:30) whose source is absent from /root/reference and which
