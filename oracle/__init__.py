@@ -10,6 +10,8 @@ Pinning status
     outputs of the reference's own `vhap/model/lbs.py` and `vhap/util/mesh.py`, imported unmodified
     in the authoring container; vectors in tests/golden/lbs_golden.npz, generator
     tests/golden/make_golden.py.
+  * FlameHead.forward / FlameTracker.forward_flame composition (oracle/lbs.py flame_forward): PINNED against the reference's own
+    methods run on bare instances with this repo's synthetic buffers; tests/golden/flame_golden.npz, make_flame_golden.py.
   * camera transforms, vertex normals, SH shading, detach_by_indices (oracle/camera.py, oracle/render.py
     compute_v_normals / sh_shading): PINNED against outputs and autograd gradients of the reference's own
     `vhap/util/render_nvdiffrast.py` methods (imported unmodified, a stub standing in for its absent nvdiffrast
