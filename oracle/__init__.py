@@ -27,6 +27,10 @@ Pinning status
   * render_rgba minus the nvdiffrast ops (oracle/render.py render_rgba / disturb): PINNED against the reference's own
     NVDiffRenderer.render_rgba run end to end with its dr.* calls served by this oracle's op restatements and its random draws
     injected (values + gradients); tests/golden/rgba_golden.npz, generator tests/golden/make_rgba_golden.py.
+  * the whole energy end to end (oracle/energy.py compute_energy: all terms, total, gradients w.r.t. every parameter): PINNED, modulo
+    the four nvdiffrast ops, against the reference's own FlameTracker.compute_energy run on CPU with all of its code unmodified
+    (tracker, FlameHead, lbs, NVDiffRenderer) and only dr.rasterize / interpolate / texture / antialias served by this oracle;
+    tests/golden/e2e_golden.npz, generator tests/golden/make_e2e_golden.py.
   * the nvdiffrast ops themselves -- rasterise / interpolate / texture / antialias (oracle/raster.py, oracle/render.py):
     PARITY UNPINNED.  The arithmetic lives in the third-party dependency `nvdiffrast`
     (ShenhanQian/nvdiffrast@backface-culling, pinned by branch name only at
