@@ -36,3 +36,41 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def optimizer_groups():
+    """{stage: {parameter name: lr}} from the reference's own get_train_parameters + configure_optimizer (tracker.py:1465-1513,159-211)
+    run on a bare tracker (no __init__), lr_scale 0.1 like global tracking (tracker.py:1385)."""
+    import types
+    import torch
+
+    def _stub(name, **attrs):
+        m = types.ModuleType(name); m.__dict__.update(attrs); sys.modules[name] = m; return m
+    _stub("nvdiffrast").torch = _stub("nvdiffrast.torch", RasterizeCudaContext=lambda *a, **k: object(), RasterizeGLContext=lambda *a, **k: object())
+    _stub("pytorch3d"); _stub("pytorch3d.io", load_obj=None); _stub("pytorch3d.structures"); _stub("pytorch3d.structures.meshes", Meshes=None)
+    _stub("matplotlib", cm=None); _stub("matplotlib.pyplot")
+    import vhap.model.tracker as RT
+    names = {"focal_length": (1,), "shape": (300,), "tex_extra": (3, 4, 4), "static_offset": (1, 7, 3), "lights": (9, 3), "translation": (2, 3), "rotation": (2, 3),
+             "eyes_pose": (2, 6), "neck_pose": (2, 3), "jaw_pose": (2, 3), "expr": (2, 100)}
+    res = {}
+    for stage, cls in STAGE_CLASSES.items():
+        trk = object.__new__(RT.GlobalTracker)            # get_train_parameters lives on the subclass (tracker.py:1221,1465)
+        trk.calibrated = False
+        trk.cfg = types.SimpleNamespace(pipeline={stage: cls()}, model=B.ModelConfig(), lr=B.LearningRateConfig())
+        tensors = {n: torch.zeros(*shp, requires_grad=True) for n, shp in names.items()}
+        for n, t in tensors.items():
+            setattr(trk, n, t)
+        trk.tex_pca = torch.zeros(100, requires_grad=True)
+        trk.dynamic_offset = None
+        optim = trk.configure_optimizer(trk.get_train_parameters(stage), lr_scale=0.1)
+        by_id = {id(t): n for n, t in tensors.items()}
+        res[stage] = {by_id[id(p)]: g["lr"] for g in optim.param_groups for p in g["params"]}
+    return res
+
+
+if __name__ == "__main__":
+    path = Path(__file__).with_name("config_golden.json")
+    d = json.loads(path.read_text())
+    d["optimizer_groups_lr_scale_0.1"] = optimizer_groups()
+    path.write_text(json.dumps(d, indent=1, sort_keys=True, default=str) + "\n")
+    print({k: v for k, v in d["optimizer_groups_lr_scale_0.1"].items() if k in ("rgb_global_tracking", "lmk_init_rigid")})

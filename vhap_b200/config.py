@@ -114,3 +114,24 @@ def opt_dict_for(stage: StageConfig) -> dict:
     """tracker.py:1465-1513 `get_train_parameters`: which parameter groups a stage optimises."""
     keys = ("cam", "pose", "shape", "joints", "expr", "texture", "lights", "static_offset", "dynamic_offset")
     return {k: (k in stage.optimizable_params) for k in keys}
+
+
+# engine parameter name -> name of its learning rate in LearningRateConfig (everything else uses `base`), tracker.py:159-211
+_LR_OF = {"translation": "translation", "expr": "expr", "lights": "light", "focal_length": "camera", "static_offset": "static_offset"}
+
+
+def adam_param_lrs(stage: StageConfig, lr: LearningRateConfig, lr_scale: float = 1.0, calibrated: bool = False) -> dict:
+    """The Adam parameter groups of a stage: {engine parameter name: learning rate}, i.e. what the reference builds with
+    get_train_parameters (tracker.py:1465-1513) + configure_optimizer (tracker.py:159-211); texture = `tex_extra`."""
+    opt = opt_dict_for(stage)
+    names = []
+    if opt["cam"] and not calibrated: names.append("focal_length")
+    if opt["shape"]: names.append("shape")
+    if opt["texture"]: names.append("tex_extra")
+    if opt["static_offset"]: names.append("static_offset")
+    if opt["lights"]: names.append("lights")
+    if opt["pose"]: names += ["translation", "rotation"]
+    if opt["joints"]: names += ["eyes_pose", "neck_pose", "jaw_pose"]
+    if opt["expr"]: names.append("expr")
+    return {n: getattr(lr, _LR_OF.get(n, "base")) * lr_scale for n in names}
+

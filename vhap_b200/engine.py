@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .config import EngineConfig, StageConfig, STAGES, opt_dict_for
+from .config import adam_param_lrs, EngineConfig, StageConfig, STAGES, opt_dict_for
 from .flame_model import FlameModelData
 
 PER_FRAME = (("expr", None), ("rotation", 3), ("neck_pose", 3), ("jaw_pose", 3), ("eyes_pose", 6), ("translation", 3))
@@ -311,9 +311,8 @@ class Engine:
         return self.tex_grad_dense.view(3, self.T, self.T)
 
     def _lr(self, name):
-        lr = self.cfg.lr                                                    # tracker.py:159-211
-        table = {"translation": lr.translation, "expr": lr.expr, "lights": lr.light, "focal_length": lr.camera, "static_offset": lr.static_offset}
-        return table.get(name, lr.base) * self.lr_scale
+        from .config import _LR_OF                                           # tracker.py:159-211 (pinned: tests/test_config_golden.py)
+        return getattr(self.cfg.lr, _LR_OF.get(name, "base")) * self.lr_scale
 
     def tex_update(self, allreduce_fn=None, deferred=False, reg_loss=True):
         """Texture part of the Adam step on the CURRENT stream.  deferred=True: the update of the PREVIOUS step, executed at the start
@@ -347,14 +346,11 @@ class Engine:
         opt = opt_dict_for(self.stage)
         self.step_count += 1
         s = self._stream()
-        groups = []
-        if opt["shape"]: groups.append("shape")
-        if opt["static_offset"]: groups.append("static_offset")
-        if opt["lights"]: groups.append("lights")
-        if opt["cam"] and not self.cfg.calibrated: groups.append("focal_length")
-        if opt["expr"]: groups.append("expr")
-        if opt["pose"]: groups += ["rotation", "translation"]
-        if opt["joints"]: groups += ["neck_pose", "jaw_pose", "eyes_pose"]
+        # parameter groups and learning rates of the stage (config.adam_param_lrs, pinned against the reference's get_train_parameters +
+        # configure_optimizer by tests/test_config_golden.py); slab order
+        lrs = adam_param_lrs(self.stage, self.cfg.lr, self.lr_scale, self.cfg.calibrated)
+        groups = [n for n in ("shape", "static_offset", "lights", "focal_length", "expr", "rotation", "translation", "neck_pose", "jaw_pose", "eyes_pose")
+                  if n in lrs]
         tex = texture and opt["texture"]
         if tex and allreduce_fn is not None:
             self.tex_update(allreduce_fn)
@@ -363,7 +359,7 @@ class Engine:
         if groups:
             off = np.asarray([self.layout[g][0] for g in groups], np.int64)
             ln = np.asarray([self.layout[g][1] for g in groups], np.int64)
-            lr = np.asarray([self._lr(g) for g in groups], np.float32)
+            lr = np.asarray([lrs[g] for g in groups], np.float32)
             hp = lambda a: a.ctypes.data_as(C.c_void_p)
             self._ck(self.L.vhap_adam_multi(self.ctx, self.slab.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                                             len(groups), hp(off), hp(ln), hp(lr), self.step_count, s), None)
