@@ -178,7 +178,7 @@ extern "C" int vhap_ctx_create(vhap_ctx** out, const vhap_mesh_desc* m, int32_t 
     CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     for (int i = 0; i < 2; ++i) CK(cudaStreamCreateWithPriority(&ctx->hp[i], cudaStreamNonBlocking, hi));
   }
-  for (int i = 0; i < 12; ++i) CK(cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming));
+  for (int i = 0; i < EV_COUNT; ++i) CK(cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming));
   UP(ctx->tex_l0_flag, (const int*)nullptr, (size_t)1);
   { int one = 1; cudaMemcpy(ctx->tex_l0_flag, &one, sizeof(int), cudaMemcpyHostToDevice); }
   CK(cudaMalloc(&ctx->scan_state, (VH_SCAN_MAX_BLOCKS + 1) * sizeof(unsigned long long)));
@@ -425,13 +425,13 @@ extern "C" int vhap_energy_forward(vhap_ctx* ctx, const vhap_params* p, const vh
     // fork: vertex normals (needed only by the shading pass) run on aux stream 0 while the rasteriser runs on the main stream
     const bool vn_overlap = !ctx->no_overlap;
     if (vn_overlap) {
-      cudaEventRecord(ctx->ev[4], s);
-      cudaStreamWaitEvent(ctx->aux[0], ctx->ev[4], 0);
+      cudaEventRecord(ctx->ev[EV_VN_FORK], s);
+      cudaStreamWaitEvent(ctx->aux[0], ctx->ev[EV_VN_FORK], 0);
       launch_vnormals(ctx, fb->B, ctx->aux[0]);
-      cudaEventRecord(ctx->ev[5], ctx->aux[0]);
+      cudaEventRecord(ctx->ev[EV_VN_DONE], ctx->aux[0]);
     } else launch_vnormals(ctx, fb->B, s);
     launch_raster(ctx, ctx->clip, ctx->snap, fb->B, fb->H, fb->W, ctx->tri_id, 0, 0, s);
-    if (vn_overlap) cudaStreamWaitEvent(s, ctx->ev[5], 0);
+    if (vn_overlap) cudaStreamWaitEvent(s, ctx->ev[EV_VN_DONE], 0);
     PassArgs P;
     fill_render_args(ctx, P, fb, cfg, p->lights);
     launch_render_forward(ctx, P, s);
@@ -456,10 +456,10 @@ extern "C" int vhap_energy_backward(vhap_ctx* ctx, const vhap_params* p, const v
   // concurrent with the render backward (works eagerly and inside CUDA-graph capture: fork/join through events)
   const bool regs_forked = cfg->training && !ctx->no_overlap;
   if (regs_forked) {
-    cudaEventRecord(ctx->ev[0], s);
-    cudaStreamWaitEvent(ctx->aux[0], ctx->ev[0], 0);
+    cudaEventRecord(ctx->ev[EV_REGS_FORK], s);
+    cudaStreamWaitEvent(ctx->aux[0], ctx->ev[EV_REGS_FORK], 0);
     launch_regs(ctx, p, fb, cfg, g, global_B, ctx->aux[0]);
-    cudaEventRecord(ctx->ev[1], ctx->aux[0]);
+    cudaEventRecord(ctx->ev[EV_REGS_DONE], ctx->aux[0]);
   } else if (cfg->training) launch_regs(ctx, p, fb, cfg, g, global_B, s);
   if (cfg->w_landmark >= 0.f) {
     int nl = cfg->jawline_off ? 51 : 68;
@@ -474,18 +474,18 @@ extern "C" int vhap_energy_backward(vhap_ctx* ctx, const vhap_params* p, const v
     if (g) {
       P.g_tex = gg->tex_grad_pyramid;
       launch_render_backward(ctx, P, cfg, p->lights, gg->lights, nullptr, s);
-      cudaEventRecord(ctx->ev[2], s);          // texel gradients complete: the texture update may start (see vhap_tex_reg_fold_adam)
+      cudaEventRecord(ctx->ev[EV_TEXGRAD_READY], s);          // texel gradients complete: the texture update may start (see vhap_tex_reg_fold_adam)
       ctx->tex_fork_pending = 1;
       // the geometry backward is a chain of small latency-bound kernels; the texture update that runs concurrently is one
       // machine-filling streaming kernel.  Put the chain on a highest-priority stream so its CTAs are scheduled ahead of the
       // bulk kernel's remaining CTAs instead of queueing behind all of them.
-      if (!ctx->no_overlap) { gs = ctx->hp[0]; cudaStreamWaitEvent(gs, ctx->ev[2], 0); }
+      if (!ctx->no_overlap) { gs = ctx->hp[0]; cudaStreamWaitEvent(gs, ctx->ev[EV_TEXGRAD_READY], 0); }
       launch_vnormals_bwd(ctx, fb->B, gs);
     }
   }
   if (g) launch_flame_backward(ctx, p, fb, gg, opt_cam, gs);
-  if (gs != s) { cudaEventRecord(ctx->ev[6], gs); cudaStreamWaitEvent(s, ctx->ev[6], 0); }
-  if (regs_forked) cudaStreamWaitEvent(s, ctx->ev[1], 0);        // join the regularisers
+  if (gs != s) { cudaEventRecord(ctx->ev[EV_GEOM_DONE], gs); cudaStreamWaitEvent(s, ctx->ev[EV_GEOM_DONE], 0); }
+  if (regs_forked) cudaStreamWaitEvent(s, ctx->ev[EV_REGS_DONE], 0);        // join the regularisers
   float max_hw = (float)(fb->H > fb->W ? fb->H : fb->W);
   LAUNCH(ctx, KID_ASSEMBLE, s, k_assemble_losses<<<1, 32, 0, s>>>(ctx->acc, *cfg, max_hw, gg->focal_length, opt_cam, losses_out, ctx->tex_loss));
   LAST();
@@ -528,10 +528,10 @@ extern "C" int vhap_tex_reg_fold_adam(vhap_ctx* ctx, float* tex_extra, float* g_
     // the texture fold / Adam / mip rebuild only depends on the texel gradients (event 2, recorded right after the fused
     // backward): run it on aux stream 1 concurrently with the geometry backward that was enqueued after that event, then join
     ctx->tex_fork_pending = 0;
-    cudaStreamWaitEvent(ctx->aux[1], ctx->ev[2], 0);
+    cudaStreamWaitEvent(ctx->aux[1], ctx->ev[EV_TEXGRAD_READY], 0);
     launch_tex_fold(ctx, tex_extra, g_out, adam_m, adam_v, lr, step, cfg, losses_out, ctx->aux[1]);
-    cudaEventRecord(ctx->ev[3], ctx->aux[1]);
-    cudaStreamWaitEvent(s, ctx->ev[3], 0);
+    cudaEventRecord(ctx->ev[EV_TEX_DONE], ctx->aux[1]);
+    cudaStreamWaitEvent(s, ctx->ev[EV_TEX_DONE], 0);
   } else {
     ctx->tex_fork_pending = 0;
     launch_tex_fold(ctx, tex_extra, g_out, adam_m, adam_v, lr, step, cfg, losses_out, s);

@@ -15,6 +15,10 @@
 
 struct CamParams { float RT[12]; float fx, fy, cx, cy; };
 
+// fork / join events of the side chains of a step (record on one stream, wait on another; valid eagerly and inside stream capture)
+enum { EV_REGS_FORK = 0, EV_REGS_DONE, EV_TEXGRAD_READY, EV_TEX_DONE, EV_VN_FORK, EV_VN_DONE, EV_GEOM_DONE, EV_BLEND_FORK, EV_BLEND_DONE,
+       EV_POSE_FORK, EV_POSE_DONE, EV_COUNT };
+
 struct vhap_ctx {
   char err[512];
   int device;
@@ -65,7 +69,7 @@ struct vhap_ctx {
   int tex_step_bias;                              // added to the device Adam step inside the texture update (deferred update: -1)
   cudaEvent_t render_wait_ev;                     // one-shot: the next render forward waits for it right before the shading pass   // see vhap_tex_apply_grad / vhap_set_tex_grad_persistent
   unsigned* tex_counter;                          // [1] CTA completion counter of the texture fold kernel (self-resetting)
-  cudaStream_t aux[2]; cudaStream_t hp[2]; cudaEvent_t ev[12];   // hp: highest-priority streams for the latency-critical geometry backward
+  cudaStream_t aux[2]; cudaStream_t hp[2]; cudaEvent_t ev[EV_COUNT];   // hp: highest-priority streams for the latency-critical geometry backward
   int tex_fork_pending, no_overlap;   // fork/join of independent kernel chains
   int* dev_step; int use_dev_step;                // device counters [0] Adam step (1-based), [1] global step; used when use_dev_step
 };

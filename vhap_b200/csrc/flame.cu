@@ -213,10 +213,10 @@ void launch_flame_forward(vhap_ctx* c, const vhap_params* p, const vhap_frame_ba
   const bool fork = !c->no_overlap;
   cudaStream_t sp = fork ? c->aux[0] : s;
   LAUNCH(c, KID_POSE_FWD, s, k_betas_gather<<<B, 128, 0, s>>>(p->shape, p->expr, fb->timesteps, c->K, c->n_shape, c->betas));
-  if (fork) { cudaEventRecord(c->ev[9], s); cudaStreamWaitEvent(sp, c->ev[9], 0); }
+  if (fork) { cudaEventRecord(c->ev[EV_POSE_FORK], s); cudaStreamWaitEvent(sp, c->ev[EV_POSE_FORK], 0); }
   LAUNCH(c, KID_POSE_FWD, sp, k_pose_fwd<<<B, 256, 0, sp>>>(p->shape, p->expr, p->rotation, p->neck_pose, p->jaw_pose, p->eyes_pose, p->static_offset, fb->timesteps,
                                c->JS, c->Jt, c->Jreg, V, c->K, c->n_shape, nullptr, c->posebuf, c->poses));
-  if (fork) cudaEventRecord(c->ev[10], sp);
+  if (fork) cudaEventRecord(c->ev[EV_POSE_DONE], sp);
   int ks = BLEND_KS;
   const float* vpart = c->v_shaped_part;
   if (c->use_tc_blend) {                 // tcgen05 contraction writes the finished v_shaped
@@ -227,7 +227,7 @@ void launch_flame_forward(vhap_ctx* c, const vhap_params* p, const vhap_frame_ba
     LAUNCH(c, KID_BLEND_FWD, s, k_blend_fwd<VH_MAXB_CHUNK><<<g1, 128, VH_MAXB_CHUNK * c->K * sizeof(float), s>>>(c->S_fwd, c->v_template, p->static_offset, c->betas, M, c->K,
                                                                                     c->n_shape, B, c->v_shaped_part));
   }
-  if (fork) cudaStreamWaitEvent(s, c->ev[10], 0);
+  if (fork) cudaStreamWaitEvent(s, c->ev[EV_POSE_DONE], 0);
   dim3 g2((V + 127) / 128, (B + VH_SKIN_NB - 1) / VH_SKIN_NB);
   LAUNCH(c, KID_SKIN_FWD, s, k_skin_fwd<VH_SKIN_NB><<<g2, 128, 0, s>>>(vpart, ks, c->v_shaped, c->posedirs, c->lbs_w, c->posebuf, p->translation, fb->timesteps, c->cam, V, B, fb->H, fb->W,
                                    c->v_posed, c->verts, c->clip, c->snap, c->ndc));
@@ -534,20 +534,20 @@ void launch_flame_backward(vhap_ctx* c, const vhap_params* p, const vhap_frame_b
   // pose_bwd -> joff_bwd pair on the second high-priority stream; both add into gbetas atomically
   bool forked = need_betas && s == c->hp[0];
   cudaStream_t s2 = forked ? c->hp[1] : s;
-  if (forked) { cudaEventRecord(c->ev[7], s); cudaStreamWaitEvent(s2, c->ev[7], 0); }
+  if (forked) { cudaEventRecord(c->ev[EV_BLEND_FORK], s); cudaStreamWaitEvent(s2, c->ev[EV_BLEND_FORK], 0); }
   if (need_betas) {
     if (c->use_tc_blend) launch_blend_tc_bwd(c, B, s2);
     else {
       dim3 g2((M + BB_ROWS - 1) / BB_ROWS, (B + VH_MAXB_CHUNK - 1) / VH_MAXB_CHUNK);
       LAUNCH(c, KID_BLEND_BWD, s2, k_blend_bwd<VH_MAXB_CHUNK><<<g2, 512, 0, s2>>>(c->S_bwd, c->g_vshaped, M, c->Mpad, c->K, B, c->gbetas));
     }
-    if (forked) cudaEventRecord(c->ev[8], s2);
+    if (forked) cudaEventRecord(c->ev[EV_BLEND_DONE], s2);
   }
   LAUNCH(c, KID_POSE_BWD, s, k_pose_bwd<<<B, 128, 0, s>>>(c->poses, c->posebuf, c->gA, c->gpf, fb->timesteps, c->JS, c->K, g->rotation, g->neck_pose, g->jaw_pose, g->eyes_pose,
                                c->gJ, need_betas ? c->gbetas : nullptr));
   if (g->static_offset) LAUNCH(c, KID_JOFF_BWD, s, k_joff_bwd<<<(V + 127) / 128, 128, 0, s>>>(c->Jreg, c->gJ, V, B, g->static_offset));
   if (need_betas) {
-    if (forked) cudaStreamWaitEvent(s, c->ev[8], 0);
+    if (forked) cudaStreamWaitEvent(s, c->ev[EV_BLEND_DONE], 0);
     LAUNCH(c, KID_BETAS_SCATTER, s, k_betas_scatter<<<B, 256, 0, s>>>(c->gbetas, fb->timesteps, c->K, c->n_shape, g->shape, g->expr));
   }
   (void)p;
