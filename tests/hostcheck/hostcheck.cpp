@@ -36,6 +36,11 @@ int hc_render(int B, int H, int W, int V, int F, int T, int max_level,
   memset(&P, 0, sizeof(P));
   RenderArgs& A = P.R;
   A.B = B; A.H = H; A.W = W; A.V = V; A.F = F; A.T = T; A.max_level = max_level;
+  if ((W & (W - 1)) == 0 && (H & (H - 1)) == 0) {          // like fill_render_args (render.cu): shift/mask pixel unflatten for power-of-two images
+    A.pow2 = 1;
+    while ((1 << A.wshift) < W) ++A.wshift;
+    while ((1 << A.hshift) < H) ++A.hshift;
+  }
   A.faces = (const i4*)faces4; A.faces_uv = (const i4*)faces_uv4; A.verts_uv = verts_uv;
   A.clip = (const f4*)clip; A.vnorm = (const f4*)vnorm; A.lights = lights; A.mips = (const f4*)mips;
   for (int i = 0; i <= max_level; ++i) A.mip_off[i] = mip_off[i];

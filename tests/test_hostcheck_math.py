@@ -63,9 +63,10 @@ def _render_setup(disturb, seed=0, B=2, H=64, W=64, T=128):
     return sc, clip32, vn32
 
 
-@pytest.mark.parametrize("disturb", [0, 1])
-def test_render_passes_match_oracle(lib, disturb):
-    sc, clip32, vn32 = _render_setup(disturb)
+@pytest.mark.parametrize("disturb,size", [(0, (64, 64)), (1, (64, 64)), (1, (48, 72))])
+def test_render_passes_match_oracle(lib, disturb, size):
+    """(64, 64) takes the shift/mask pixel-unflatten path of power-of-two images, (48, 72) the general one"""
+    sc, clip32, vn32 = _render_setup(disturb, H=size[0], W=size[1])
     m, model = sc["m"], sc["model"]
     B, H, W, T = sc["B"], sc["H"], sc["W"], sc["T"]
     dt = torch.float64
