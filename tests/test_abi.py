@@ -80,3 +80,32 @@ def test_stage_table_matches_reference_defaults():
     assert STAGES["rgb_init_texture"].optimizable_params == ("cam", "shape", "texture", "lights")
     assert opt_dict_for(STAGES["lmk_init_rigid"]) == dict(cam=True, pose=True, shape=False, joints=False, expr=False, texture=False,
                                                           lights=False, static_offset=False, dynamic_offset=False)
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under vhap_b200/ may import it (bench.py's cpu_baseline / --impl reference legs and
+    __graft_entry__.smoke are the only other users besides tests/)."""
+    import ast
+    root = Path(__file__).resolve().parents[1]
+    offenders = []
+    for py in (root / "vhap_b200").rglob("*.py"):
+        tree = ast.parse(py.read_text())
+        for node in ast.walk(tree):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom) and node.module:
+                names = [node.module]
+            if any(n == "oracle" or n.startswith("oracle.") for n in names):
+                offenders.append(str(py.relative_to(root)))
+    assert not offenders, offenders
+    # bench.py: only inside the two CPU-baseline functions
+    src = (root / "bench.py").read_text()
+    tree = ast.parse(src)
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef):
+            uses = any(isinstance(n, ast.ImportFrom) and n.module and n.module.startswith("oracle") for n in ast.walk(node))
+            if uses:
+                assert node.name in ("cpu_baseline", "run_reference"), node.name
+    for node in tree.body:                                   # no module-level import of the oracle
+        assert not (isinstance(node, (ast.Import, ast.ImportFrom)) and "oracle" in ast.dump(node))
