@@ -109,3 +109,14 @@ def test_product_never_imports_the_oracle():
                 assert node.name in ("cpu_baseline", "run_reference"), node.name
     for node in tree.body:                                   # no module-level import of the oracle
         assert not (isinstance(node, (ast.Import, ast.ImportFrom)) and "oracle" in ast.dump(node))
+
+
+def test_missing_library_fails_loudly():
+    """no silent fallback: with the shared library absent the binding raises (checked in a fresh interpreter)"""
+    import subprocess
+    import sys
+    code = ("import os; os.environ['VHAP_B200_SO'] = '/nonexistent/libvhap_b200.so'\n"
+            "from vhap_b200 import _lib\n"
+            "try:\n    _lib.lib()\nexcept RuntimeError as e:\n    print('RAISED', 'no CPU or PyTorch fallback' in str(e))\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(ROOT), timeout=120)
+    assert "RAISED True" in r.stdout, (r.stdout, r.stderr[-500:])
