@@ -328,8 +328,9 @@ def run_ours(args):
 
 
 def cpu_baseline(size, sample_frames=1, steps=1):
-    """The oracle (CPU port of the reference's path) timed on this box's host cores, bounded sample: `sample_frames` frame(s)
-    at size^2 with a 512^2 texture stand-in? no -- the full 2048^2 texture, one full iteration (energy + backward + Adam)."""
+    """The oracle (CPU port of the reference's path, pinned end to end against the reference's own compute_energy)
+    timed on this box's host cores on a bounded sample: `sample_frames` frame(s) at size^2 with the full 2048^2 texture, `steps` full
+    iterations (energy + backward + torch.optim.Adam), plus the landmark-only stage of configs[0]."""
     from oracle import energy as E, lbs as L, camera as Cm
     from vhap_b200 import synth
     from vhap_b200.config import EngineConfig, STAGES
