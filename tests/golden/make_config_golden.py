@@ -68,9 +68,40 @@ def optimizer_groups():
     return res
 
 
+def stage_schedules():
+    """[(batch index, lr of the `base` group / cfg.lr.base)] per iteration, from the reference's own optimize_stage (tracker.py:1391-1416)
+    run on a bare tracker with optimize_iter replaced by a recorder: a 3-sample "dataloader" for the two global stages (lr_scale 0.1,
+    ExponentialLR) and a single sample for two per-sample stages."""
+    import types
+    import torch
+    import vhap.model.tracker as RT
+    res = {}
+    for stage, cls, loader in (("rgb_global_tracking", B.StageRgbGlobalTrackingConfig, True), ("lmk_global_tracking", B.StageLmkGlobalTrackingConfig, True),
+                               ("rgb_init_texture", B.StageRgbInitTextureConfig, False), ("rgb_sequential_tracking", B.StageRgbSequentialTrackingConfig, False)):
+        trk = object.__new__(RT.GlobalTracker)
+        trk.calibrated = False
+        trk.logger = types.SimpleNamespace(info=lambda *a, **k: None)
+        trk.cfg = types.SimpleNamespace(pipeline={stage: cls()}, model=B.ModelConfig(), lr=B.LearningRateConfig())
+        for n, shp in {"focal_length": (1,), "shape": (300,), "tex_extra": (3, 4, 4), "static_offset": (1, 7, 3), "lights": (9, 3), "translation": (2, 3),
+                       "rotation": (2, 3), "eyes_pose": (2, 6), "neck_pose": (2, 3), "jaw_pose": (2, 3), "expr": (2, 100)}.items():
+            setattr(trk, n, torch.zeros(*shp, requires_grad=True))
+        trk.tex_pca = torch.zeros(100, requires_grad=True)
+        trk.dynamic_offset = None
+        rec = []
+        trk.optimize_iter = lambda sample, optimizer, st: rec.append((sample, optimizer.param_groups[-1]["lr"] / B.LearningRateConfig().base))
+        trk.evaluate = lambda *a, **k: None
+        if loader:
+            trk.optimize_stage(stage=stage, dataloader=[0, 1, 2], lr_scale=0.1)
+        else:
+            trk.optimize_stage(stage=stage, sample=0, lr_scale=1.0)
+        res[stage] = {"per_sample": not loader, "n_batches": 3 if loader else 1, "lr_scale": 0.1 if loader else 1.0, "schedule": rec}
+    return res
+
+
 if __name__ == "__main__":
     path = Path(__file__).with_name("config_golden.json")
     d = json.loads(path.read_text())
     d["optimizer_groups_lr_scale_0.1"] = optimizer_groups()
+    d["stage_schedules"] = stage_schedules()
     path.write_text(json.dumps(d, indent=1, sort_keys=True, default=str) + "\n")
     print({k: v for k, v in d["optimizer_groups_lr_scale_0.1"].items() if k in ("rgb_global_tracking", "lmk_init_rigid")})

@@ -135,3 +135,17 @@ def adam_param_lrs(stage: StageConfig, lr: LearningRateConfig, lr_scale: float =
     if opt["expr"]: names.append("expr")
     return {n: getattr(lr, _LR_OF.get(n, "base")) * lr_scale for n in names}
 
+
+def stage_schedule(stage_name: str, n_batches: int, lr_scale: float = 1.0, per_sample: bool = False):
+    """The iteration schedule of FlameTracker.optimize_stage (tracker.py:1391-1416) as a list of (batch index, learning-rate scale):
+    * per_sample (a single staged sample, the init / sequential stages): `num_steps` iterations on batch 0 at constant lr_scale;
+    * otherwise (a dataloader, the global stages): `num_epochs` passes over the batches in the order given (shuffling is the
+      loader's business) with torch's ExponentialLR(gamma=0.9) stepped after every epoch -- lr_scale * 0.9 ** epoch.
+    One fresh Adam state per call (tracker.py:1399), so the caller starts with Engine.set_stage(stage_name, lr_scale)."""
+    if per_sample:
+        return [(0, lr_scale)] * STAGE_STEPS[stage_name]
+    out = []
+    for epoch in range(STAGE_EPOCHS[stage_name]):
+        out += [(b, lr_scale * 0.9 ** epoch) for b in range(n_batches)]
+    return out
+

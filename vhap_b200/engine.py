@@ -374,6 +374,18 @@ class Engine:
         self.global_step += 1
         return losses
 
+    def optimize_stage(self, stage_name: str, batches, lr_scale: float = 1.0, per_sample: bool = False, on_step=None):
+        """FlameTracker.optimize_stage (tracker.py:1391-1416): fresh Adam state, then the schedule of config.stage_schedule (pinned against
+        the reference's own loop by tests/test_config_golden.py) -- eager steps; the learning-rate scale changes between epochs without
+        touching the Adam moments, like torch's ExponentialLR.  `on_step(i, losses)` is called after every iteration."""
+        from .config import stage_schedule
+        self.set_stage(stage_name, lr_scale)
+        for i, (b, scale) in enumerate(stage_schedule(stage_name, len(batches), lr_scale, per_sample)):
+            self.lr_scale = scale
+            losses = self.step(batches[b])
+            if on_step is not None:
+                on_step(i, losses)
+
     # ------------------------------------------------------------------ CUDA-graph replay of whole steps
     def graph_begin(self, batches, body=None, reduce_fn=None, allreduce_fn=None, world=1, pipelined=True):
         """Capture one optimisation step per (batch, texture ping-pong parity) as CUDA graphs.  All step-dependent values
