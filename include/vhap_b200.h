@@ -181,6 +181,9 @@ int vhap_set_want_planes(vhap_ctx* ctx, int32_t on);   /* make the next forward 
 int vhap_overflow_flag(vhap_ctx* ctx, int32_t* out_host);   /* 1 if a raster tile list overflowed its capacity (synchronises) */
 /* test hook: inject the disturbance randomness (w bits: bit0 = w_fg, bit1 = w_bg; u in [0,1)); NULL = Philox. */
 int vhap_set_injected_random(vhap_ctx* ctx, const uint8_t* w_bits /*[B,H,W]*/, const float* u /*[B,H,W]*/);
+/* test hook: per-pixel switch of the L1 photometric term of the next forwards ([B,H,W] device bytes, image orientation like
+ * `target`; 0 = pixel left out of sum|gt - pred|, the normaliser still counts it); NULL = every pixel (tracker.py:438-439). */
+int vhap_set_loss_mask(vhap_ctx* ctx, const uint8_t* mask);
 
 /* ---- texture: pyramid rebuild + regularisers + Adam (tracker.py:247-258 get_albedo, :526-539, torch.optim.Adam) -- */
 float* vhap_tex_grad_ptr(vhap_ctx* ctx);                 /* device pointer of the texture-gradient pyramid */
@@ -218,6 +221,9 @@ int vhap_profile_timeline(vhap_ctx* ctx, int32_t* kid_out, float* t0_ms, float* 
  *      (forward, backward, regularisers, Adam) can be captured once per (batch, texture ping-pong parity) and replayed ------ */
 int vhap_step_counters(vhap_ctx* ctx, int32_t on, int32_t adam_step, int32_t global_step, void* stream);
 int vhap_step_advance(vhap_ctx* ctx, void* stream);
+/* learning-rate scale of the Adam kernels while the device step counters are on (torch's ExponentialLR stepped between epochs,
+ * tracker.py:1407-1412): captured step graphs read it from device memory, so a replayed stage follows the reference's schedule */
+int vhap_set_lr_scale(vhap_ctx* ctx, float scale, void* stream);
 int vhap_get_cur_mip(vhap_ctx* ctx);
 int vhap_set_cur_mip(vhap_ctx* ctx, int32_t v);
 

@@ -170,9 +170,10 @@ def compute_energy(params, sample, stage, cfg, model_data, model, lap=None, dist
     verts, verts_cano, lmks = L.flame_forward(
         model, params["shape"][None].expand(B, -1), params["expr"][ts], params["rotation"][ts], params["neck_pose"][ts],
         params["jaw_pose"][ts], params["eyes_pose"][ts], params["translation"][ts], static_offset=params.get("static_offset"))
-    K, RT = fill_cam_params(params, B, H, W, sample.get("extrinsic"))
-    if "intrinsic" in sample:
-        K = sample["intrinsic"].to(dt)
+    ext = sample.get("extrinsic")
+    K, RT = fill_cam_params(params, B, H, W, None if ext is None else torch.as_tensor(ext).to(dt))
+    if sample.get("intrinsic") is not None:
+        K = torch.as_tensor(sample["intrinsic"]).to(dt)
     aux = {"verts": verts, "lmks": lmks, "verts_cano": verts_cano}
     if w.landmark is not None:
         dis = stage.disable_jawline_landmarks if (stage is not None and not w.always_enable_jawline_landmarks) else False
@@ -200,7 +201,10 @@ def compute_energy(params, sample, stage, cfg, model_data, model, lap=None, dist
         pred = out["rgba"].permute(0, 3, 1, 2)
         pred_rgb = pred[:, :3]
         n_fg = (pred[:, [3]].detach() > 0).expand(-1, 3, -1, -1).sum()
-        log["photo"] = w.photo * ((gt_rgb.to(dt) - pred_rgb).abs().sum() / n_fg)  # tracker.py:438-439
+        err = (gt_rgb.to(dt) - pred_rgb).abs()
+        if sample.get("loss_mask") is not None:                                    # test hook (vhap_set_loss_mask): [B,H,W], False = pixel left out
+            err = err * torch.as_tensor(sample["loss_mask"]).to(dt)[:, None]
+        log["photo"] = w.photo * (err.sum() / n_fg)                                # tracker.py:438-439
         aux.update(render=out, rast=rast, rast_db=rast_db, clip=clip, n_fg=n_fg)
     if stage is not None:
         diff_dn = aux["render"]["diffuse_detach_normal"].permute(0, 3, 1, 2) if (photometric and "render" in aux) else None

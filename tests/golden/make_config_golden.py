@@ -68,6 +68,21 @@ def optimizer_groups():
     return res
 
 
+def nersemble():
+    """the NeRSemble overrides (vhap/config/nersemble.py:23-82): data flags the engine reads, loss weights, the two overridden stages"""
+    from vhap.config import nersemble as N
+    data = N.NersembleDataConfig
+    out = {"w": dataclasses.asdict(N.NersembleLossWeightConfig()),
+           "data": {f.name: f.default for f in dataclasses.fields(data) if f.name in ("calibrated", "scale_factor", "n_downsample_rgb", "target_extrinsic_type",
+                                                                                       "background_color", "image_size_during_calibration")},
+           "stages": {}}
+    for name, cls in (("rgb_sequential_tracking", N.NersembleStageRgbSequentialTrackingConfig), ("rgb_global_tracking", N.NersembleStageRgbGlobalTrackingConfig)):
+        d = dataclasses.asdict(cls())
+        d["photometric"] = isinstance(cls(), B.PhotometricStageConfig)
+        out["stages"][name] = d
+    return out
+
+
 def stage_schedules():
     """[(batch index, lr of the `base` group / cfg.lr.base)] per iteration, from the reference's own optimize_stage (tracker.py:1391-1416)
     run on a bare tracker with optimize_iter replaced by a recorder: a 3-sample "dataloader" for the two global stages (lr_scale 0.1,
@@ -101,6 +116,7 @@ def stage_schedules():
 if __name__ == "__main__":
     path = Path(__file__).with_name("config_golden.json")
     d = json.loads(path.read_text())
+    d["nersemble"] = nersemble()
     d["optimizer_groups_lr_scale_0.1"] = optimizer_groups()
     d["stage_schedules"] = stage_schedules()
     path.write_text(json.dumps(d, indent=1, sort_keys=True, default=str) + "\n")

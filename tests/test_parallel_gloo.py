@@ -52,7 +52,23 @@ def _worker(rank, world, port, q):
     e.backward()
     g = torch.cat([P["shape"].grad.reshape(-1), P["rotation"].grad.reshape(-1), P["focal_length"].grad.reshape(-1)])
     allreduce_sum(g)
-    q.put((rank, ok1, ok2, g.numpy()))
+    # ---- uneven shards (5 frames over 2 ranks = 3 + 2): the global batch is the all-reduced sum of the local sizes, not B * world
+    from vhap_b200.parallel import global_batch_size
+    sc5 = make_scene(B=5, H=32, W=32, T=8, n_t=5, timesteps=[0, 1, 2, 3, 4])
+    lo5, hi5 = shard_frames(5, rank, world)
+    gB = global_batch_size(hi5 - lo5)
+    P5 = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in sc5["params"].items()}
+    ts5 = sc5["ts"][lo5:hi5]
+    nb = hi5 - lo5
+    _, _, lm5 = L.flame_forward(sc5["model"], P5["shape"][None].expand(nb, -1), P5["expr"][ts5], P5["rotation"][ts5], P5["neck_pose"][ts5],
+                                P5["jaw_pose"][ts5], P5["eyes_pose"][ts5], P5["translation"][ts5], static_offset=P5["static_offset"])
+    K5, RT5 = E.fill_cam_params(P5, nb, 32, 32)
+    e5 = w.landmark * E.lmk_energy(lm5, torch.tensor(sc5["lmk2d"][lo5:hi5]), K5, RT5, (32, 32)) * (nb / gB) \
+        + w.reg_expr * (P5["expr"][ts5] ** 2).sum() / (gB * P5["expr"].shape[1]) + (1.0 / world) * w.reg_shape * (P5["shape"] ** 2).mean()
+    e5.backward()
+    g5 = torch.cat([P5["shape"].grad.reshape(-1), P5["expr"].grad.reshape(-1), P5["rotation"].grad.reshape(-1)])
+    allreduce_sum(g5)
+    q.put((rank, ok1, ok2, g.numpy(), (gB, hi5 - lo5), g5.numpy()))
     dist.destroy_process_group()
 
 
@@ -82,3 +98,25 @@ def test_world_size_2_gloo():
     ref = torch.cat([P["shape"].grad.reshape(-1), P["rotation"].grad.reshape(-1), P["focal_length"].grad.reshape(-1)]).numpy()
     for r in res:
         np.testing.assert_allclose(r[3], ref, rtol=1e-9, atol=1e-12)
+    # uneven shards: global batch 5 on both ranks, shard sizes 3 + 2, summed gradients == single process
+    assert sorted(r[4][1] for r in res) == [2, 3] and all(r[4][0] == 5 for r in res)
+    sc5 = make_scene(B=5, H=32, W=32, T=8, n_t=5, timesteps=[0, 1, 2, 3, 4])
+    P5 = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in sc5["params"].items()}
+    ts5 = sc5["ts"]
+    _, _, lm5 = L.flame_forward(sc5["model"], P5["shape"][None].expand(5, -1), P5["expr"][ts5], P5["rotation"][ts5], P5["neck_pose"][ts5],
+                                P5["jaw_pose"][ts5], P5["eyes_pose"][ts5], P5["translation"][ts5], static_offset=P5["static_offset"])
+    K5, RT5 = E.fill_cam_params(P5, 5, 32, 32)
+    e5 = w.landmark * E.lmk_energy(lm5, torch.tensor(sc5["lmk2d"]), K5, RT5, (32, 32)) + w.reg_expr * (P5["expr"][ts5] ** 2).mean() \
+        + w.reg_shape * (P5["shape"] ** 2).mean()
+    e5.backward()
+    ref5 = torch.cat([P5["shape"].grad.reshape(-1), P5["expr"].grad.reshape(-1), P5["rotation"].grad.reshape(-1)]).numpy()
+    for r in res:
+        np.testing.assert_allclose(r[5], ref5, rtol=1e-9, atol=1e-12)
+
+
+def test_shard_frames_rejects_empty_shards():
+    import pytest
+    from vhap_b200.parallel import shard_frames
+    with pytest.raises(ValueError):
+        shard_frames(3, 0, 4)
+    assert [shard_frames(5, r, 4) for r in range(4)] == [(0, 2), (2, 3), (3, 4), (4, 5)]

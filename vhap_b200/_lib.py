@@ -94,6 +94,8 @@ def lib() -> C.CDLL:
         "vhap_get_geometry": (i32, [vp, i32, vp, vp]),
         "vhap_overflow_flag": (i32, [vp, P(i32)]),
         "vhap_set_injected_random": (i32, [vp, vp, vp]),
+        "vhap_set_loss_mask": (i32, [vp, vp]),
+        "vhap_set_lr_scale": (i32, [vp, f32, vp]),
         "vhap_tex_grad_ptr": (vp, [vp]),
         "vhap_set_tex_painted": (i32, [vp, vp, vp]),
         "vhap_tex_rebuild": (i32, [vp, vp, vp]),
@@ -123,5 +125,5 @@ EXPORTED = ["vhap_abi_version", "vhap_last_error", "vhap_ctx_create", "vhap_ctx_
             "vhap_flame_forward", "vhap_flame_backward", "vhap_project", "vhap_rasterize", "vhap_energy_forward_backward",
             "vhap_energy_forward", "vhap_energy_backward", "vhap_get_plane", "vhap_get_geometry", "vhap_profile_enable", "vhap_profile_kernel_count", "vhap_profile_kernel_name",
             "vhap_profile_read", "vhap_profile_timeline", "vhap_set_overlap", "vhap_set_want_planes", "vhap_overflow_flag",
-            "vhap_set_injected_random", "vhap_project_backward", "vhap_vertex_normals",
+            "vhap_set_injected_random", "vhap_set_loss_mask", "vhap_set_lr_scale", "vhap_project_backward", "vhap_vertex_normals",
             "vhap_vertex_normals_backward", "vhap_render_photometric", "vhap_render_rgba_backward", "vhap_tex_grad_ptr", "vhap_set_tex_painted", "vhap_tex_rebuild", "vhap_tex_reg_fold_adam", "vhap_tex_apply_grad", "vhap_set_tex_grad_persistent", "vhap_tex_defer", "vhap_tex_reg_loss", "vhap_set_render_wait_event", "vhap_assemble_losses", "vhap_adam", "vhap_adam_multi", "vhap_step_counters", "vhap_step_advance", "vhap_get_cur_mip", "vhap_set_cur_mip"]

@@ -149,3 +149,27 @@ def stage_schedule(stage_name: str, n_batches: int, lr_scale: float = 1.0, per_s
         out += [(b, lr_scale * 0.9 ** epoch) for b in range(n_batches)]
     return out
 
+
+
+# ---------------------------------------------------------------------------------------------- NeRSemble (calibrated multi-view)
+@dataclass
+class NersembleLossWeightConfig(LossWeightConfig):      # vhap/config/nersemble.py:36-42
+    landmark: Optional[float] = 3.0
+    always_enable_jawline_landmarks: bool = False
+    reg_expr: float = 1e-2
+    reg_tex_tv: Optional[float] = 1e5
+    smooth_expr: float = 0.0
+
+
+# the two stages NeRSemble overrides (nersemble.py:44-61); every other stage is the base one.  (rgb_sequential_tracking additionally drops
+# the texture group there, nersemble.py:46: ("pose", "joints", "expr", "dynamic_offset") -- dynamic offsets are off by default, base.py:69.)
+NERSEMBLE_STAGES = dict(STAGES)
+NERSEMBLE_STAGES["rgb_sequential_tracking"] = StageConfig("rgb_sequential_tracking", ("pose", "joints", "expr"), True, True, ("boundary",), ("boundary",))
+NERSEMBLE_STAGES["rgb_global_tracking"] = StageConfig("rgb_global_tracking", ("cam", "pose", "shape", "joints", "expr", "texture", "lights", "static_offset"),
+                                                      True, True, ("boundary",), ("boundary",))
+
+
+def nersemble_config(**overrides) -> EngineConfig:
+    """EngineConfig of NersembleTrackingConfig (vhap/config/nersemble.py:23-82): calibrated cameras (per-frame 'intrinsic' /
+    'extrinsic' in the sample, no focal-length parameter), the NeRSemble loss weights; stages from NERSEMBLE_STAGES."""
+    return EngineConfig(w=NersembleLossWeightConfig(), calibrated=True, **overrides)

@@ -168,6 +168,7 @@ extern "C" int vhap_ctx_create(vhap_ctx** out, const vhap_mesh_desc* m, int32_t 
   UP(ctx->scan_total, (const int*)nullptr, (size_t)1);
   UP(ctx->pair_count, (const int*)nullptr, (size_t)1);
   UP(ctx->dev_step, (const int*)nullptr, (size_t)2);
+  { float one = 1.f; UP(ctx->dev_lr_scale, &one, (size_t)1); }
   // aux[0] carries small latency-critical side chains (pose chain, vertex normals, regularisers): highest priority, like hp[];
   // aux[1] carries the bulk texture pass: default (lowest) priority
   { int lo = 0, hi = 0; CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -239,7 +240,7 @@ extern "C" void vhap_ctx_destroy(vhap_ctx* c) {
   FREE(c->vf_indptr); FREE(c->vf_faces); FREE(c->lap_indptr); FREE(c->lap_idx); FREE(c->lap_val); FREE(c->lap_y);
   FREE(c->face_flags); FREE(c->vert_flags); FREE(c->w_off); FREE(c->w_off_lap); FREE(c->rigid_indptr); FREE(c->rigid_vids); FREE(c->uvmask_res);
   FREE(c->mips[0]); FREE(c->mips[1]); FREE(c->tex_painted); FREE(c->g_tex); FREE(c->tv_partials); FREE(c->tex_counter); FREE(c->tex_loss); FREE(c->scan_state); FREE(c->scal); FREE(c->acc); FREE(c->maxslot);
-  FREE(c->overflow_flag); FREE(c->pool_base); FREE(c->pool_count);
+  FREE(c->overflow_flag); FREE(c->pool_base); FREE(c->pool_count); FREE(c->dev_lr_scale); FREE(c->dev_step);
   free(c);
 }
 
@@ -265,6 +266,8 @@ extern "C" int vhap_set_stage_masks(vhap_ctx* ctx, const uint8_t* face_tex_detac
 
 extern "C" int vhap_set_injected_random(vhap_ctx* ctx, const uint8_t* w_bits, const float* u) { ctx->inj_w = w_bits; ctx->inj_u = u; return 0; }
 extern "C" int vhap_set_want_planes(vhap_ctx* ctx, int32_t on) { ctx->want_planes = on; return 0; }
+// test hook: per-pixel switch of the L1 photometric term ([B,H,W] bytes, IMAGE orientation, 0 = pixel left out); NULL = all pixels
+extern "C" int vhap_set_loss_mask(vhap_ctx* ctx, const uint8_t* mask) { ctx->loss_mask = mask; return 0; }
 extern "C" float* vhap_tex_grad_ptr(vhap_ctx* ctx) { return ctx->g_tex; }
 
 static int check_batch(vhap_ctx* ctx, const vhap_frame_batch* fb) {
@@ -722,6 +725,14 @@ __global__ void k_step_advance(int* d) { d[0] += 1; d[1] += 1; }
 extern "C" int vhap_step_counters(vhap_ctx* ctx, int32_t on, int32_t adam_step, int32_t global_step, void* stream) {
   ctx->use_dev_step = on;
   LAUNCH(ctx, KID_MISC, (cudaStream_t)stream, k_step_set<<<1, 1, 0, (cudaStream_t)stream>>>(ctx->dev_step, adam_step, global_step));
+  LAST();
+  return 0;
+}
+__global__ void k_set_float(float* d, float v) { d[0] = v; }
+// learning-rate scale of the captured Adam kernels (torch's ExponentialLR between epochs, tracker.py:1407-1412): with device step
+// counters on, every Adam kernel multiplies its learning rate by this device scalar, so a captured step graph follows the schedule
+extern "C" int vhap_set_lr_scale(vhap_ctx* ctx, float scale, void* stream) {
+  LAUNCH(ctx, KID_MISC, (cudaStream_t)stream, k_set_float<<<1, 1, 0, (cudaStream_t)stream>>>(ctx->dev_lr_scale, scale));
   LAST();
   return 0;
 }

@@ -56,7 +56,7 @@ struct vhap_ctx {
   unsigned long long* maxslot;                    // packed (orderable float bits << 32 | idx)
   float* scal;                                    // [16] device scalars for pass C
   float* acc;                                     // [64] misc accumulators (loss sums, focal grad...)
-  const uint8_t* inj_w; const float* inj_u;
+  const uint8_t* inj_w; const float* inj_u; const uint8_t* loss_mask;
   struct VhProf* prof;
   int *scan_aux, *scan_total;                     // [1024], [1]
   float* aa_code; int *pair_list, *pair_count;    // [2N], [2N], [1]
@@ -72,6 +72,7 @@ struct vhap_ctx {
   cudaStream_t aux[2]; cudaStream_t hp[2]; cudaEvent_t ev[EV_COUNT];   // hp: highest-priority streams for the latency-critical geometry backward
   int tex_fork_pending, no_overlap;   // fork/join of independent kernel chains
   int* dev_step; int use_dev_step;                // device counters [0] Adam step (1-based), [1] global step; used when use_dev_step
+  float* dev_lr_scale;                            // [1] learning-rate scale read by the Adam kernels when use_dev_step (ExponentialLR between graph replays)
 };
 
 void vh_set_error(vhap_ctx* ctx, const char* what, const char* msg);

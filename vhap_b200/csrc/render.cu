@@ -320,6 +320,7 @@ void fill_render_args(vhap_ctx* c, PassArgs& P, const vhap_frame_batch* fb, cons
   P.pool_list = c->pool_list; P.pool_base = c->pool_base; P.pool_count = c->pool_count; P.pool_tri = c->pool_tri;
   P.disturb = cfg->training ? 1 : 0;                        // enable_disturbance = stage != None (tracker.py:427)
   P.rate_fg = cfg->disturb_rate_fg; P.rate_bg = cfg->disturb_rate_bg;
+  P.loss_mask = c->loss_mask;
   P.inj_w = c->inj_w; P.inj_u = c->inj_u; P.seed = cfg->rng_seed; P.step = cfg->rng_step; P.step_ptr = c->use_dev_step ? c->dev_step : nullptr;
   P.bg_mode = cfg->bg_mode; P.bg_color[0] = cfg->bg_color[0]; P.bg_color[1] = cfg->bg_color[1]; P.bg_color[2] = cfg->bg_color[2];
   P.scal = c->scal; P.g_clip = c->g_clip; P.g_vnorm = c->g_vnorm; P.g_tex = nullptr; P.aa_code = c->aa_code;

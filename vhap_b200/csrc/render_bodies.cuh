@@ -40,6 +40,7 @@ struct PassArgs {
   // antialias pair cache, one float per (pixel 0 of the pair, direction d): 0 = no blend, else sign = near surface is pixel 0's,
   // |code| - 1 = alpha (written by the pair-analysis pass for EVERY pair of adjacent pixels with different ids)
   float* aa_code;             // [B,H,W,2]
+  const uint8_t* loss_mask;   // optional test hook [B,H,W], IMAGE orientation: 0 = the pixel is left out of the L1 photometric sum (vhap_set_loss_mask)
 };
 
 // ------------------------------------------------------------------------------------------ small utilities
@@ -279,6 +280,7 @@ VH_HD void passB_body(const PassArgs& P, int b, int y, int x, float* acc) {
   }
   const uint16_t* t = P.target + (((size_t)b * A.H + (A.H - 1 - y)) * A.W + x) * 4;
   float e0 = half_bits_to_float(t[0]) - out.x, e1 = half_bits_to_float(t[1]) - out.y, e2 = half_bits_to_float(t[2]) - out.z;
+  if (P.loss_mask && !P.loss_mask[((size_t)b * A.H + (A.H - 1 - y)) * A.W + x]) { e0 = 0.f; e1 = 0.f; e2 = 0.f; }
   acc[0] += fabsf(e0) + fabsf(e1) + fabsf(e2);
   if (out.w > 0.f) acc[1] += 1.f;
   uint8_t sg = (uint8_t)((e0 > 0.f ? 1 : (e0 < 0.f ? 2 : 0)) | ((e1 > 0.f ? 1 : (e1 < 0.f ? 2 : 0)) << 2) | ((e2 > 0.f ? 1 : (e2 < 0.f ? 2 : 0)) << 4));

@@ -82,6 +82,7 @@ struct TexFoldArgs {
   int do_adam;
   const int* l0_flag;
   const int* step_ptr;          // device Adam step (CUDA-graph replay) or NULL
+  const float* lr_scale_ptr;    // device learning-rate scale, read together with step_ptr
   int step_bias;                // added to *step_ptr (deferred update of the previous step: -1)
 };
 
@@ -174,7 +175,10 @@ __global__ void __launch_bounds__(256, 4) k_tex_fold(TexFoldArgs a, float* __res
     // l0_flag when it scatters there, otherwise the 16 B/texel read + re-zero of that level is skipped
     const bool l0 = a.g_pyr ? (a.l0_flag ? (*a.l0_flag != 0) : true) : false;
     float bc1 = a.bc1, bc2s = a.bc2_sqrt;
-    if (a.do_adam && a.step_ptr) { float st = (float)(a.step_ptr[0] + a.step_bias); bc1 = 1.f - powf(0.9f, st); bc2s = sqrtf(1.f - powf(0.999f, st)); }
+    if (a.do_adam && a.step_ptr) {
+      float st = (float)(a.step_ptr[0] + a.step_bias); bc2s = sqrtf(1.f - powf(0.999f, st));
+      bc1 = (1.f - powf(0.9f, st)) / a.lr_scale_ptr[0];                       // fold_texel uses lr / bc1
+    }
     TexelIn r0, r1;
     fold_load(a, x, y, l0, coarse[tid >> 1], r0);   // all loads of both texels are issued before the first dependent store
     fold_load(a, x, y + 1, l0, coarse[tid >> 1], r1);
@@ -292,7 +296,7 @@ void launch_tex_fold(vhap_ctx* c, float* tex_extra, float* g_out, float* m, floa
   a.tex_old = c->mips[c->cur_mip]; a.tex_new = c->mips[c->cur_mip ^ 1]; a.g_pyr = c->g_tex;
   a.extra = tex_extra; a.g_out = g_out; a.m = m; a.v = v; a.g_in = c->tex_apply_grad;
   if (a.g_in) a.g_pyr = nullptr;                       // apply mode: gradient already folded, regularised and reduced across ranks
-  a.mask = c->uvmask_res; a.l0_flag = c->tex_l0_flag; a.step_ptr = c->use_dev_step ? c->dev_step : nullptr; a.step_bias = c->tex_step_bias;
+  a.mask = c->uvmask_res; a.l0_flag = c->tex_l0_flag; a.step_ptr = c->use_dev_step ? c->dev_step : nullptr; a.lr_scale_ptr = c->dev_lr_scale; a.step_bias = c->tex_step_bias;
   float sh = cfg->shared_scale;
   // tv.mean(): (T-1)*T elements per channel, 3 channels (tracker.py:529-533); w already includes scale_factor^2 / ds^2
   a.w_tv = (cfg->training && cfg->opt_texture && cfg->w_reg_tex_tv >= 0.f) ? sh * cfg->w_reg_tex_tv / (3.f * (float)(T - 1) * (float)T) : 0.f;
@@ -324,10 +328,10 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
 
 struct AdamSegs { int n_seg; int off[24]; int len[24]; float lr[24]; };
 __global__ void k_adam_multi(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, AdamSegs sg, int total,
-                             float inv_bc1, float bc2_sqrt, const int* __restrict__ step_ptr) {
+                             float inv_bc1, float bc2_sqrt, const int* __restrict__ step_ptr, const float* __restrict__ lr_scale_ptr) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  if (step_ptr) { float st = (float)step_ptr[0]; inv_bc1 = 1.f / (1.f - powf(0.9f, st)); bc2_sqrt = sqrtf(1.f - powf(0.999f, st)); }
+  if (step_ptr) { float st = (float)step_ptr[0]; inv_bc1 = lr_scale_ptr[0] / (1.f - powf(0.9f, st)); bc2_sqrt = sqrtf(1.f - powf(0.999f, st)); }
   int k = 0, base = 0;
   while (k < sg.n_seg - 1 && i >= base + sg.len[k]) { base += sg.len[k]; ++k; }
   int j = sg.off[k] + (i - base);
@@ -343,7 +347,7 @@ void launch_adam_multi(vhap_ctx* c, float* p, const float* g, float* m, float* v
   int total = 0;
   for (int k = 0; k < sg.n_seg; ++k) { sg.off[k] = (int)off[k]; sg.len[k] = (int)len[k]; sg.lr[k] = lr[k]; total += (int)len[k]; }
   float bc1 = 1.f - powf(0.9f, (float)step), bc2s = sqrtf(1.f - powf(0.999f, (float)step));
-  if (total > 0) LAUNCH(c, KID_ADAM, s, k_adam_multi<<<(total + 255) / 256, 256, 0, s>>>(p, g, m, v, sg, total, 1.f / bc1, bc2s, c->use_dev_step ? c->dev_step : nullptr));
+  if (total > 0) LAUNCH(c, KID_ADAM, s, k_adam_multi<<<(total + 255) / 256, 256, 0, s>>>(p, g, m, v, sg, total, 1.f / bc1, bc2s, c->use_dev_step ? c->dev_step : nullptr, c->dev_lr_scale));
 }
 
 void launch_adam(vhap_ctx* c, float* p, const float* g, float* m, float* v, int64_t n, float lr, int step, cudaStream_t s) {

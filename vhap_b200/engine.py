@@ -95,14 +95,43 @@ class Engine:
         self.slab_local, self.slab_global = z(8), z(8)
         self.tex_painted = None
         if tex_painted is not None:
-            self.tex_painted = torch.as_tensor(np.ascontiguousarray(tex_painted, np.float32), device=self.dev).reshape(-1)
+            tp = torch.as_tensor(np.ascontiguousarray(tex_painted, np.float32), device=self.dev)
+            if tp.dim() != 3 or tp.shape[0] != 3:
+                raise ValueError(f"tex_painted must be [3,T,T], got {tuple(tp.shape)}")
+            if tuple(tp.shape[1:]) != (self.T, self.T):                      # flame.py:655-657: resized to tex_resolution
+                tp = torch.nn.functional.interpolate(tp[None], (self.T, self.T), mode="bilinear", align_corners=False)[0]
+            self.tex_painted = tp.contiguous().reshape(-1)
             self._ck(self.L.vhap_set_tex_painted(self.ctx, self.tex_painted.data_ptr(), self._stream()))
+        if cfg.w.blur_iter != 0:
+            raise NotImplementedError("blur_iter != 0 (blurred region weights, tracker.py:607-614) is not supported by the b200 backend")
+        if tuple(cfg.w.reg_tex_res_for) != ("sclerae", "teeth"):
+            raise NotImplementedError("reg_tex_res_for other than ('sclerae', 'teeth'): the residual mask is the model's uvmask_res (flame.py:1042-1055)")
         self.stage: Optional[StageConfig] = None
         self.step_count = 0
         self.global_step = 0
-        self.lr_scale = 1.0
+        self._lr_scale = 1.0
+        self._graph_live = False
         self._inj = None
+        self._loss_mask = None
+        self._tex_persist = False
+        if world_size > 1:
+            # the dense texture gradient is a persistent buffer of this object: its fold may run on the library's aux stream
+            torch.cuda.current_stream(self.dev).synchronize()
+            self.L.vhap_set_tex_grad_persistent(self.ctx, 1)
+            self._tex_persist = True
         self.rebuild_texture()
+
+    # learning-rate scale (lr_scale of configure_optimizer, tracker.py:159-211, times ExponentialLR's 0.9 ** epoch, :1407-1412).  While
+    # step graphs are live the captured Adam kernels read it from device memory, so assigning it between replays takes effect.
+    @property
+    def lr_scale(self) -> float:
+        return self._lr_scale
+
+    @lr_scale.setter
+    def lr_scale(self, v: float):
+        self._lr_scale = float(v)
+        if self._graph_live:
+            self._ck(self.L.vhap_set_lr_scale(self.ctx, self._lr_scale, self._stream()))
 
     # ------------------------------------------------------------------ plumbing
     def _stream(self):
@@ -172,6 +201,8 @@ class Engine:
         """begin of FlameTracker.optimize_stage (tracker.py:1391-1416): new Adam state, stage masks."""
         if isinstance(stage, str):
             stage = STAGES[stage]
+        if getattr(self, "_graph_live", False):
+            raise RuntimeError("set_stage while step graphs are live: call graph_end() first")
         self.stage = stage
         self.lr_scale = lr_scale
         self.step_count = 0
@@ -197,6 +228,8 @@ class Engine:
         if mask is None:
             mask = np.zeros((self.T, self.T), bool)
         if mask.shape[0] != self.T:
+            if mask.shape[0] < self.T or mask.shape[0] % self.T or mask.shape[0] != mask.shape[1]:
+                raise ValueError(f"uvmask_res {mask.shape} cannot be subsampled to the texture resolution {self.T}")
             mask = mask[:: mask.shape[0] // self.T, :: mask.shape[1] // self.T]
         mask = np.ascontiguousarray(mask.astype(np.uint8))
         hp = lambda a: a.ctypes.data_as(C.c_void_p)
@@ -254,12 +287,48 @@ class Engine:
             B, _, H, W = rgb.shape
             r = rgb.to(self.dev, non_blocking=non_blocking)
             tgt = torch.cat([r.permute(0, 2, 3, 1), torch.zeros(B, H, W, 1, device=self.dev, dtype=r.dtype)], -1).to(torch.float16).contiguous()
-        lm = torch.as_tensor(lmk2d, dtype=torch.float32).to(self.dev, non_blocking=non_blocking).contiguous()
+        lm = torch.as_tensor(lmk2d, dtype=torch.float32)
+        if lm.dim() != 3 or lm.shape[0] != B or lm.shape[1] < 68 or lm.shape[2] != 3:
+            raise ValueError(f"lmk2d must be [B,>=68,3], got {tuple(lm.shape)}")
+        lm = lm[:, :68].to(self.dev, non_blocking=non_blocking).contiguous()                    # tracker.py:358-362 uses [:, :68]
         ts = torch.as_tensor(np.asarray(timesteps), dtype=torch.int32).to(self.dev, non_blocking=non_blocking)
-        RTd = None if RT is None else torch.as_tensor(RT, dtype=torch.float32).to(self.dev).contiguous()
-        Kd = None if K is None else torch.as_tensor(K, dtype=torch.float32).to(self.dev).contiguous()
+        if ts.shape != (B,):
+            raise ValueError(f"timestep_index must have {B} entries")
+        if self.cfg.calibrated and (RT is None or K is None):
+            raise AssertionError("calibrated data: 'intrinsic' and 'extrinsic' must be in the sample")   # tracker.py:145-147
+        RTd, Kd = None, None
+        if RT is not None:                                  # sample['extrinsic']: [B,3,4] or [B,4,4] world-to-camera (render_nvdiffrast.py:162-179)
+            RTd = torch.as_tensor(RT, dtype=torch.float32)
+            if RTd.dim() == 2:
+                RTd = RTd[None].expand(B, -1, -1)
+            if RTd.shape[-2:] not in ((3, 4), (4, 4)) or RTd.shape[0] != B:
+                raise ValueError(f"Expected RT to be (N, 3, 4) or (N, 4, 4) but got: {tuple(RTd.shape)}")
+            RTd = RTd[:, :3, :].to(self.dev).contiguous()
+        if K is not None:                                   # sample['intrinsic']: [B,3,3] matrices or [B,4] = (fx,fy,cx,cy) (render_nvdiffrast.py:133-141)
+            Kd = torch.as_tensor(K, dtype=torch.float32)
+            if Kd.dim() >= 2 and Kd.shape[-2:] == (3, 3):
+                Kd = Kd.reshape(-1, 3, 3)
+                Kd = torch.stack([Kd[:, 0, 0], Kd[:, 1, 1], Kd[:, 0, 2], Kd[:, 1, 2]], -1)
+            elif Kd.shape[-1] == 4:
+                Kd = Kd.reshape(-1, 4)
+            else:
+                raise ValueError(f"Expected K to be (N, 3, 3) or (N, 4) but got: {tuple(Kd.shape)}")   # render_nvdiffrast.py:141
+            if Kd.shape[0] == 1 and B > 1:
+                Kd = Kd.expand(B, -1)
+            if Kd.shape[0] != B:
+                raise ValueError(f"K has {Kd.shape[0]} rows for a batch of {B}")
+            Kd = Kd.to(self.dev).contiguous()
         self.reserve(B, H, W)
         return Batch(B, H, W, ts, tgt, lm, RTd, Kd)
+
+    def set_loss_mask(self, mask):
+        """test hook: [B,H,W] bool/uint8 (image orientation like sample['rgb']); False = pixel left out of the L1 photometric sum."""
+        if mask is None:
+            self._loss_mask = None
+            self.L.vhap_set_loss_mask(self.ctx, None)
+            return
+        self._loss_mask = torch.as_tensor(mask).to(torch.uint8).to(self.dev).contiguous()
+        self.L.vhap_set_loss_mask(self.ctx, self._loss_mask.data_ptr())
 
     def inject_random(self, w_fg, w_bg, u):
         """test hook: fix the disturbance randomness (render_nvdiffrast.py:429-435,455)."""
@@ -301,7 +370,9 @@ class Engine:
         """Folds the texel-gradient pyramid (+ TV / residual regularisers) into a dense [3,T,T] gradient (no Adam)."""
         if self.tex_grad_dense is None:
             self.tex_grad_dense = torch.zeros(3 * self.T * self.T, dtype=torch.float32, device=self.dev)
-        if not getattr(self, "_tex_persist", False):
+        if not self._tex_persist:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("texture_grad_dense: call it once eagerly (or construct the Engine with world_size > 1) before capturing")
             torch.cuda.current_stream(self.dev).synchronize()       # the zero fill must not race the library's aux stream
             self.L.vhap_set_tex_grad_persistent(self.ctx, 1)        # persistent from here on: the fold may leave the caller's stream
             self._tex_persist = True
@@ -310,9 +381,13 @@ class Engine:
                                                C.byref(cs), 1.0, self.losses.data_ptr() if with_losses else None, self._stream()), None)
         return self.tex_grad_dense.view(3, self.T, self.T)
 
+    def _host_lr_scale(self):
+        # with live step graphs the scale lives in device memory (vhap_set_lr_scale) and the kernels apply it themselves
+        return 1.0 if self._graph_live else self._lr_scale
+
     def _lr(self, name):
         from .config import _LR_OF                                           # tracker.py:159-211 (pinned: tests/test_config_golden.py)
-        return getattr(self.cfg.lr, _LR_OF.get(name, "base")) * self.lr_scale
+        return getattr(self.cfg.lr, _LR_OF.get(name, "base")) * self._host_lr_scale()
 
     def tex_update(self, allreduce_fn=None, deferred=False, reg_loss=True):
         """Texture part of the Adam step on the CURRENT stream.  deferred=True: the update of the PREVIOUS step, executed at the start
@@ -348,7 +423,7 @@ class Engine:
         s = self._stream()
         # parameter groups and learning rates of the stage (config.adam_param_lrs, pinned against the reference's get_train_parameters +
         # configure_optimizer by tests/test_config_golden.py); slab order
-        lrs = adam_param_lrs(self.stage, self.cfg.lr, self.lr_scale, self.cfg.calibrated)
+        lrs = adam_param_lrs(self.stage, self.cfg.lr, self._host_lr_scale(), self.cfg.calibrated)
         groups = [n for n in ("shape", "static_offset", "lights", "focal_length", "expr", "rotation", "translation", "neck_pose", "jaw_pose", "eyes_pose")
                   if n in lrs]
         tex = texture and opt["texture"]
@@ -387,7 +462,7 @@ class Engine:
                 on_step(i, losses)
 
     # ------------------------------------------------------------------ CUDA-graph replay of whole steps
-    def graph_begin(self, batches, body=None, reduce_fn=None, allreduce_fn=None, world=1, pipelined=True):
+    def graph_begin(self, batches, body=None, reduce_fn=None, allreduce_fn=None, world=1, pipelined=True, global_Bs=None):
         """Capture one optimisation step per (batch, texture ping-pong parity) as CUDA graphs.  All step-dependent values
         (Adam step, RNG step) live in device memory (vhap_step_counters), so the graphs are replayable indefinitely.
         Data parallel: pass reduce_fn / allreduce_fn / world (the NCCL collectives are captured); `body(batch)` overrides the captured
@@ -398,12 +473,18 @@ class Engine:
         stream and joins it right before the shading pass; the first graph_step runs an eager prologue, graph_end flushes the last
         update.  Same arithmetic in the same order on every buffer, only the schedule differs."""
         s = self._stream()
+        if allreduce_fn is not None and self.tex_grad_dense is None:
+            self.texture_grad_dense(with_losses=False)       # one-time eager set-up (allocation, stream hand-over) must not happen inside capture
         self._ck(self.L.vhap_step_counters(self.ctx, 1, self.step_count + 1, self.global_step, s))
+        self._graph_live = True
+        self.lr_scale = self._lr_scale                       # -> device
         torch.cuda.synchronize(self.dev)
         opt = opt_dict_for(self.stage)
         self._pipe = bool(pipelined and body is None and self.stage is not None and self.stage.photometric and opt["texture"])
         self._hooks = (reduce_fn, allreduce_fn, world)
         self._graph_batches = list(batches)
+        # true global batch size per staged batch (uneven shards: not B * world); parallel.DataParallelStep passes the all-reduced values
+        self._graph_gB = {id(b): (g if global_Bs is not None else b.B * world) for b, g in zip(self._graph_batches, global_Bs or [0] * len(self._graph_batches))}
         self._primed = False
         self._graphs, self._graph_events = {}, []
         if self._pipe and not hasattr(self, "_tex_stream"):
@@ -448,7 +529,7 @@ class Engine:
             self._graph_events += [e0, e1, e2]
             self.L.vhap_set_render_wait_event(self.ctx, C.c_void_p(e1.cuda_event))    # joined right before the shading pass
         self.zero_grad()
-        self.energy(batch, backward=True, training=True, global_B=batch.B * world, reduce_fn=reduce_fn)
+        self.energy(batch, backward=True, training=True, global_B=self._graph_gB.get(id(batch), batch.B * world), reduce_fn=reduce_fn)
         self.adam_step(allreduce_fn=allreduce_fn, texture=texture_now)
         if deferred_tex:
             torch.cuda.current_stream(self.dev).wait_event(e2)
@@ -484,6 +565,7 @@ class Engine:
         self.L.vhap_set_cur_mip(self.ctx, self._parity)
         torch.cuda.synchronize(self.dev)
         self._ck(self.L.vhap_step_counters(self.ctx, 0, 0, 0, self._stream()))
+        self._graph_live = False
         self._graphs, self._graph_events = {}, []
         self._primed = False
         self._pipe = False

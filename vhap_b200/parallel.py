@@ -36,10 +36,23 @@ def allreduce_sum(t: torch.Tensor, group=None) -> None:
 
 
 def shard_frames(n_frames: int, rank: int, world: int):
-    """Contiguous frame shard of rank `rank` (frames are independent units of the path)."""
-    per = (n_frames + world - 1) // world
-    lo = min(rank * per, n_frames)
-    return lo, min(lo + per, n_frames)
+    """Contiguous frame shard of rank `rank` (frames are independent units of the path): the first n_frames % world
+    ranks hold one frame more.  Every rank needs at least one frame (a rank with an empty batch has nothing to launch)."""
+    if n_frames < world:
+        raise ValueError(f"{n_frames} frames cannot be sharded over {world} ranks: every rank needs at least one frame")
+    per, extra = divmod(n_frames, world)
+    lo = rank * per + min(rank, extra)
+    return lo, lo + per + (1 if rank < extra else 0)
+
+
+def global_batch_size(local_B: int, device=None, group=None) -> int:
+    """sum of the per-rank batch sizes: the batch-global normalisers (landmark mean, per-frame regulariser means, (2 G B - 1) of the joint
+    prior, n_pix of reg_diffuse) need the TRUE global batch, which is not local_B * world when the shards are uneven"""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return int(local_B)
+    t = torch.tensor([int(local_B)], dtype=torch.int64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return int(t.item())
 
 
 class DataParallelStep:
@@ -48,12 +61,24 @@ class DataParallelStep:
     def __init__(self, engine, group=None):
         self.e, self.group = engine, group
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self._gB = {}
+
+    def global_B(self, batch) -> int:
+        """true global batch size of the step this batch belongs to (one host-side all-reduce per staged batch object, cached; must be
+        called by all ranks in the same order -- step() / graph_begin() do)"""
+        if batch.B < 1:
+            raise ValueError("data parallel: every rank needs at least one frame per step")
+        k = id(batch)
+        if k not in self._gB:
+            dev = self.e.dev if getattr(self.e, "dev", None) is not None and dist.is_initialized() and dist.get_backend(self.group) == "nccl" else None
+            self._gB[k] = global_batch_size(batch.B, dev, self.group)
+        return self._gB[k]
 
     def body(self, batch):
         """the step without host-side counters: what gets captured into a CUDA graph (Engine.graph_begin(body=...))"""
         e = self.e
         e.zero_grad()
-        gB = batch.B * self.world
+        gB = self.global_B(batch)
         red = (lambda a, b: reduce_forward_slab(a, b, self.group)) if self.world > 1 else None
         e.energy(batch, backward=True, training=True, global_B=gB, reduce_fn=red)
         e.adam_step(allreduce_fn=(lambda t: allreduce_sum(t, self.group)) if self.world > 1 else None)
@@ -63,12 +88,13 @@ class DataParallelStep:
         runs at the start of step k+1, hidden behind FLAME / rasteriser / pools)"""
         red = (lambda a, b: reduce_forward_slab(a, b, self.group)) if self.world > 1 else None
         allr = (lambda t: allreduce_sum(t, self.group)) if self.world > 1 else None
-        self.e.graph_begin(batches, reduce_fn=red, allreduce_fn=allr, world=self.world, pipelined=pipelined)
+        gBs = [self.global_B(b) for b in batches]            # host-side collectives: before the capture
+        self.e.graph_begin(batches, reduce_fn=red, allreduce_fn=allr, world=self.world, pipelined=pipelined, global_Bs=gBs)
 
     def step(self, batch):
         e = self.e
         e.zero_grad()
-        gB = batch.B * self.world
+        gB = self.global_B(batch)
         red = (lambda a, b: reduce_forward_slab(a, b, self.group)) if self.world > 1 else None
         losses = e.energy(batch, backward=True, training=True, global_B=gB, reduce_fn=red)
         e.adam_step(allreduce_fn=(lambda t: allreduce_sum(t, self.group)) if self.world > 1 else None)

@@ -110,6 +110,20 @@ class B200FlameHead(torch.nn.Module):
         return ret if len(ret) > 1 else ret[0]
 
 
+# constant factors of the first three SH bands (render_nvdiffrast.py:83-96)
+_SH_CONST = (0.28209479177387814, 1.0233267079464885, 1.0233267079464885, 1.0233267079464885, 0.8580855308097834, 0.8580855308097834,
+             0.8580855308097834, 0.4290427654048917, 0.24770795610037571)
+
+
+def _sh_shade(normal: torch.Tensor, lights: torch.Tensor) -> torch.Tensor:
+    """get_SH_shading (render_nvdiffrast.py:19-53) on a [B,H,W,3] normal plane, lights [9,3]: a tiny torch op that keeps the
+    autograd edge to `lights` -- used for `diffuse_detach_normal` (render_nvdiffrast.py:403), the input of reg_diffuse (tracker.py:547-550)."""
+    x, y, z = normal[..., 0], normal[..., 1], normal[..., 2]
+    basis = torch.stack([torch.ones_like(x), x, y, z, x * y, x * z, y * z, x * x - y * y, 3 * z * z - 1], -1)
+    basis = basis * torch.tensor(_SH_CONST, dtype=normal.dtype, device=normal.device)
+    return basis @ lights.to(normal.dtype).reshape(9, 3)
+
+
 class _RenderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, rnd, verts_clip, v_normal, tex, lights, batch, cs):
@@ -175,6 +189,21 @@ class B200Renderer(torch.nn.Module):
     def clear_cache(self):
         self.fragment_cache = None
 
+    def _check_topology(self, faces=None, verts_uv=None, faces_uv=None):
+        """the engine renders the mesh it was built with (static tables on the device): a caller passing another topology gets an error
+        instead of a silently different picture.  verts_uv arrives with v already flipped by the tracker (tracker.py:315-316)."""
+        m = self.model
+        if faces is not None and (tuple(faces.shape[-2:]) != m.faces.shape or not np.array_equal(faces.reshape(-1, 3).cpu().numpy(), m.faces)):
+            raise ValueError("faces differ from the FLAME topology this B200Renderer was built with")
+        if faces_uv is not None and (tuple(faces_uv.shape[-2:]) != m.faces_uv.shape or not np.array_equal(faces_uv.reshape(-1, 3).cpu().numpy(), m.faces_uv)):
+            raise ValueError("faces_uv differ from the FLAME topology this B200Renderer was built with")
+        if verts_uv is not None:
+            vuv = verts_uv.reshape(-1, 2).detach().cpu().numpy()
+            ref = m.verts_uv.astype(np.float32).copy()
+            ref[:, 1] = 1.0 - ref[:, 1]
+            if vuv.shape != ref.shape or not np.allclose(vuv, ref, atol=1e-6):
+                raise ValueError("verts_uv differ from the (v-flipped) FLAME texture coordinates this B200Renderer was built with")
+
     # ---- camera (render_nvdiffrast.py:117-214); tiny host-side tensor algebra, kept in torch like the reference
     def projection_from_intrinsics(self, K, image_size, near=0.1, far=10.0):
         B = K.shape[0]
@@ -212,6 +241,7 @@ class B200Renderer(torch.nn.Module):
 
     # ---- rasterize (render_nvdiffrast.py:216-260)
     def rasterize(self, verts, faces, RT, K, image_size, use_cache=False, require_grad=False):
+        self._check_topology(faces)
         verts_camera = self.world_to_camera(verts, RT)
         verts_clip = self.camera_to_clip(verts_camera, K, image_size)
         if not use_cache or self.fragment_cache is None:
@@ -239,6 +269,7 @@ class B200Renderer(torch.nn.Module):
     def render_rgba(self, rast_dict, verts, faces, verts_uv, faces_uv, tex, lights, background_color=[1.0, 1.0, 1.0],
                     align_texture_except_fid=None, align_boundary_except_vid=None, enable_disturbance=False):
         eng = self.eng
+        self._check_topology(faces, verts_uv, faces_uv)
         verts_clip = rast_dict["verts_clip"]
         B = verts_clip.shape[0]
         H, W = rast_dict["rast_out"].shape[1:3]
@@ -277,7 +308,10 @@ class B200Renderer(torch.nn.Module):
         v_normal = _NormalsFn.apply(eng, rast_dict["verts"])
         tex_chw = tex[0] if tex.dim() == 4 else tex
         rgba, albedo, normal, diffuse, cid = _RenderFn.apply(self, verts_clip, v_normal, tex_chw, lights.reshape(9, 3), batch, cs)
-        return {"albedo": albedo[..., :3], "normal": normal[..., :3], "diffuse": diffuse[..., :3], "diffuse_detach_normal": diffuse[..., :3].detach(),
+        # diffuse_detach_normal keeps its gradient w.r.t. the lights (only the normal is detached, render_nvdiffrast.py:402-403):
+        # SH shading of the (non-differentiable) normal plane in torch; background pixels have normal 0 like the reference's
+        return {"albedo": albedo[..., :3], "normal": normal[..., :3], "diffuse": diffuse[..., :3],
+                "diffuse_detach_normal": _sh_shade(normal[..., :3].detach(), lights.reshape(9, 3)),
                 "rgba": rgba, "aa": albedo[..., 3:4].detach().expand(-1, -1, -1, 3).contiguous(), "cid": cid[..., :1].long()}
 
 

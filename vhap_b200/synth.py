@@ -80,3 +80,29 @@ def landmarks_px(lmks_ndc_flipped: np.ndarray, H: int, W: int, seed: int = 0, no
     y = y + ny
     conf = rng.uniform(0.6, 1.0, x.shape)
     return np.stack([x, y, conf], -1).astype(np.float32)
+
+
+def ring_cameras(model, n_views: int, H: int, W: int, head_centre, radius: float = 1.0, yaw_span_deg: float = 120.0, pitch_deg: float = 8.0,
+                 fill: float = 1.0, seed: int = 0):
+    """Calibrated multi-view rig standing in for NeRSemble's 16 cameras (nersemble_dataset.py:75-127: one shared intrinsic matrix, one
+    world-to-camera extrinsic per camera, OpenGL convention): cameras on an arc of `yaw_span_deg` around the head at `radius`,
+    alternating +-pitch, all looking at `head_centre`; principal point slightly off-centre.  Returns (RT [n,3,4], K [n,3,3]) float32,
+    i.e. sample['extrinsic'] / sample['intrinsic'] of n_views frames of ONE timestep (video_dataset.py:216-217)."""
+    rng = np.random.default_rng(seed + 31)
+    c = np.asarray(head_centre, np.float64)
+    height = float(model.v_template[:, 1].max() - model.v_template[:, 1].min())
+    f_px = fill * min(H, W) * radius / height
+    RT = np.zeros((n_views, 3, 4), np.float64)
+    K = np.zeros((n_views, 3, 3), np.float64)
+    yaws = np.deg2rad(np.linspace(-0.5 * yaw_span_deg, 0.5 * yaw_span_deg, n_views)) if n_views > 1 else np.zeros(1)
+    for i, yaw in enumerate(yaws):
+        pitch = np.deg2rad(pitch_deg) * (1 if i % 2 == 0 else -1)
+        z = np.array([np.sin(yaw) * np.cos(pitch), np.sin(pitch), np.cos(yaw) * np.cos(pitch)])     # camera looks down -z (OpenGL)
+        o = c + radius * z
+        x = np.cross(np.array([0.0, 1.0, 0.0]), z); x /= np.linalg.norm(x)
+        y = np.cross(z, x)
+        R = np.stack([x, y, z], 0)
+        RT[i, :, :3] = R
+        RT[i, :, 3] = -R @ o
+        K[i] = np.array([[f_px, 0, 0.5 * W + rng.uniform(-0.02, 0.02) * W], [0, f_px, 0.5 * H + rng.uniform(-0.02, 0.02) * H], [0, 0, 1]])
+    return RT.astype(np.float32), K.astype(np.float32)
