@@ -4,9 +4,13 @@
 A "step" is one optimisation iteration of FlameTracker.optimize_iter (vhap/model/tracker.py:1418-1435) in stage
 `rgb_global_tracking` (every parameter group optimised, base.py:291-295): FLAME forward -> landmark energy -> rasterise ->
 shade -> disturbance + antialias + L1 -> analytic backward -> regularisers -> Adam (2048^2 texture included), on one batch
-of synthetic frames.  Workload at N GPUs: configs[1] "monocular 512x512 batch_size=16 photometric tracking" PER GPU (weak
-scaling: global batch 16 N, frames sharded one shard per rank; per Adam step one 4-float all-gather and one all-reduce of the
-shared-parameter + texture gradients, captured into the step graphs).  `--size 1024` selects the 1024^2 variant.
+of synthetic frames.  Workloads (`--config`, `--size`):
+  monocular (default)  BASELINE configs[1]: 512x512, batch 16 PER GPU (weak scaling: global batch 16 N over N ranks, every rank
+                       optimises its own DISTINCT frames of one global parameter set; per Adam step one 4-float all-gather and the
+                       gradient reduction, captured into the step graphs).  `--size 1024` = the per-GPU share of configs[3].
+  nersemble            BASELINE configs[2] / [4]: 16 calibrated views (802x550, per-view extrinsic / intrinsic) of one timestep per
+                       step, NeRSemble loss weights (tex-TV 1e5) and stage; at N GPUs every rank takes different timesteps.
+The default run also measures the other two single-GPU workloads in the same process and reports them under `extra_configs`.
 
 Timed regions (all CUDA events, max over ranks): (1) `value`: K CUDA-graph replays with the inputs resident in HBM, 4 rotating
 staged batches; by default the replay is PIPELINED (each replay = the texture update of the previous step beside the start of
@@ -15,7 +19,7 @@ this step + everything else of this step; K replays = K complete steps of work; 
 copy stream) and the device -> host read of the loss vector; (3) per-kernel times: the same steps launched eagerly with events
 around every kernel and the aux-stream overlap off (roofline of the dominant kernel; `traffic` from the committed ncu capture).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config monocular|nersemble] [--size 512|1024]
 
 `--impl reference` times the CPU restatement of the reference's path (oracle/, kind "port": the reference's own GPU path
 needs nvdiffrast, absent here) on a bounded sample of the same workload.
@@ -38,6 +42,7 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "photometric frames*iters/sec"
 UNIT = "frame*iter/s"
+NERSEMBLE_HW = (802, 550)
 
 
 def peaks():
@@ -85,75 +90,89 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
-def build_workload(size, B, n_batches, rank, seed=0):
+def workload_shape(config, size):
+    return NERSEMBLE_HW if config == "nersemble" else (size, size)
+
+
+def build_workload(size, B, n_batches, rank, world=1, config="monocular", seed=0):
     """Synthetic tracking inputs: real FLAME topology, seeded smooth bases, per-frame parameters, procedural
-    2048^2 texture; targets = the engine's own render of a perturbed parameter set (+ noise), stored fp16 RGBA."""
+    2048^2 texture; targets = the engine's own render of a perturbed parameter set (+ noise), stored fp16 RGBA.
+    ONE global parameter set of n_t = (frames of all ranks) timesteps, identical on every rank; rank r stages only its own frames
+    (monocular: B distinct timesteps per batch; nersemble: B calibrated views of ONE timestep per batch), so the data-parallel
+    gradient reduction sums DISTINCT rows like a sharded 16 N-frame batch (BASELINE configs[3] / [4])."""
     from vhap_b200 import synth
-    from vhap_b200.config import EngineConfig
+    from vhap_b200.config import EngineConfig, nersemble_config, NERSEMBLE_STAGES, STAGES
     from vhap_b200.flame_model import FlameModelData
     from vhap_b200.engine import Engine
+    from vhap_b200.staging import pin_sample
     m = FlameModelData.synthetic()
-    cfg = EngineConfig()
-    n_t = B * n_batches
+    views = config == "nersemble"
+    cfg = nersemble_config() if views else EngineConfig()
+    H, W = workload_shape(config, size)
+    n_t = (n_batches if views else B * n_batches) * world
     dev = f"cuda:{int(os.environ.get('LOCAL_RANK', 0))}"
-    world = int(os.environ.get("WORLD_SIZE", 1))
     eng = Engine(m, cfg, n_t, device=dev, tex_painted=synth.procedural_texture(cfg.tex_resolution, seed), world_size=world)
     # "ground truth" parameters -> target images and landmarks, rendered by the engine in evaluation mode
-    gt = synth.init_params(m, n_t, cfg.tex_resolution, seed=seed + 100 + rank)
+    gt = synth.init_params(m, n_t, cfg.tex_resolution, seed=seed + 100)
     eng.load_params(gt)
     eng.set_stage(None)
-    H = W = size
+    RT = K = None
+    if views:
+        c = m.v_template.mean(0) + gt["translation"].mean(0)
+        RT, K = synth.ring_cameras(m, B, H, W, c, seed=seed)
     batches = []
-    rng = np.random.default_rng(seed + rank)
+    fg = 0.0
     for i in range(n_batches):
-        ts = np.arange(i * B, (i + 1) * B)
+        gi = rank * n_batches + i
+        ts = np.full(B, gi) if views else np.arange(gi * B, (gi + 1) * B)
         blank = torch.zeros(B, H, W, 4, dtype=torch.float16)
-        bt = eng.stage_sample(blank, np.zeros((B, 68, 3), np.float32), ts)
+        bt = eng.stage_sample(blank, np.zeros((B, 68, 3), np.float32), ts, RT=RT, K=K)
         # render with a white background, then use it (plus noise) as the target
         eng.cfg.render.background_eval = "white"
         planes = eng.render_planes(bt, training=False)
         eng.cfg.render.background_eval = "target"
         rgb = planes["rgba"][..., :3].clamp(0, 1)
         rgb = (rgb + 0.02 * torch.randn_like(rgb)).clamp(0, 1)
-        tgt = torch.cat([rgb, torch.ones_like(rgb[..., :1])], -1).to(torch.float16).cpu()
+        tgt = (rgb * 255.0).round().to(torch.uint8).cpu()          # what an image decoder hands to the tracker: [B,H,W,3] uint8
         lm = torch.empty(B, 70, 3, device=eng.dev)
         cp = eng._c_params()
         eng._ck(eng.L.vhap_flame_forward(eng.ctx, C.byref(cp), C.byref(bt.c), None, None, lm.data_ptr(), eng._stream()))
-        # project landmarks like world_to_ndc(flip_y=True) with the default camera
-        f = 1.5 * max(H, W)
-        l = lm.cpu().numpy()
-        z = -(l[..., 2] - 1.0)
-        ndc = np.stack([(2 * f / W) * l[..., 0] / z, -(2 * f / H) * l[..., 1] / z], -1)
-        lmk2d = synth.landmarks_px(ndc, H, W, seed + i)
-        batches.append((tgt.pin_memory(), torch.tensor(lmk2d).pin_memory(), torch.tensor(ts, dtype=torch.int32).pin_memory()))
-        fg = float((planes["cid"][..., 1] > 0).float().mean())
-    # start the optimisation from a perturbed parameter set
-    start = synth.init_params(m, n_t, cfg.tex_resolution, seed=seed + 100 + rank)
-    prng = np.random.default_rng(seed + 7 + rank)
+        ndc = synth.project_ndc(lm.cpu().numpy(), RT, K, H, W, focal=1.5)
+        lmk2d = synth.landmarks_px(ndc, H, W, seed + gi)
+        batches.append(pin_sample(tgt, lmk2d, ts, RT=RT, K=K))
+        fg += float((planes["cid"][..., 1] > 0).float().mean()) / n_batches
+    # start the optimisation from a perturbed parameter set (same on every rank)
+    start = synth.init_params(m, n_t, cfg.tex_resolution, seed=seed + 100)
+    prng = np.random.default_rng(seed + 7)
     for k in ("shape", "expr", "rotation", "neck_pose", "jaw_pose", "eyes_pose", "translation"):
         start[k] = (start[k] + prng.normal(0, 0.02, start[k].shape) * (0.2 if k == "translation" else 1.0)).astype(np.float32)
     start["tex_extra"] = np.zeros_like(start["tex_extra"])
     start["static_offset"] = np.zeros_like(start["static_offset"])
     eng.load_params(start)
-    eng.set_stage("rgb_global_tracking", lr_scale=0.1)              # tracker.py:1385
+    eng.set_stage((NERSEMBLE_STAGES if views else STAGES)["rgb_global_tracking"], lr_scale=0.1)              # tracker.py:1385
     return eng, batches, fg
 
 
-def run_ours(args):
+def stage_all(eng, batches):
+    from vhap_b200.staging import InputRing
+    return InputRing(eng, batches)
+
+
+def measure(args, config, size, B, full):
+    """one workload on this rank's GPU: (1) device-resident replays, (2) end to end, (3, full only) per-kernel eager profile"""
     import torch.distributed as dist
     from vhap_b200.parallel import DataParallelStep
     world = int(os.environ.get("WORLD_SIZE", 1))
     rank = int(os.environ.get("RANK", 0))
     local = int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    B, size = args.batch, args.size
     n_batches = 4
-    eng, batches, fg = build_workload(size, B, n_batches, rank)
+    steps = args.steps if full else max(10, min(args.steps, 20))
+    eng, batches, fg = build_workload(size, B, n_batches, rank, world, config)
     dev = eng.dev
+    H, W = workload_shape(config, size)
     gB = B * world
-    resident = [eng.stage_sample(t, l, ts.numpy()) for (t, l, ts) in batches]
+    ring = stage_all(eng, batches)          # device slots with fixed addresses (graphs are captured per slot)
+    resident = ring.batches
     dp = DataParallelStep(eng)
     use_graph = not args.no_graph
 
@@ -178,12 +197,12 @@ def run_ours(args):
             eng.graph_step(i % n_batches)
         barrier()
     clocks = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and full:
         clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
-    for i in range(args.steps):
+    for i in range(steps):
         if use_graph:
             eng.graph_step(i % n_batches)
         else:
@@ -191,147 +210,175 @@ def run_ours(args):
     ev1.record()
     barrier()
     ms = maxms(ev0.elapsed_time(ev1))
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop() if (rank == 0 and full) else None
     losses = eng.loss_dict()
 
     # ---------------- end to end: pinned host -> device copy of every step's inputs + device -> host read of the loss
     host_loss = torch.empty(24, dtype=torch.float32).pin_memory()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # the next step's inputs are prefetched on a copy stream while the current step computes (what a pinned-memory DataLoader
-    # with non_blocking copies does): slot j of the staged device buffers is refilled only after the step that used it finished
-    cur = torch.cuda.current_stream()
-    copy_stream = torch.cuda.Stream()
-    ready = [torch.cuda.Event() for _ in range(n_batches)]
-    freed = [None] * n_batches
-
-    def prefetch(j):
-        t_, l_, ts_ = batches[j]
-        bt = resident[j]
-        with torch.cuda.stream(copy_stream):
-            if freed[j] is not None:
-                copy_stream.wait_event(freed[j])
-            bt.target.copy_(t_, non_blocking=True)          # H2D from pinned memory into the staged device buffers
-            bt.lmk2d.copy_(l_, non_blocking=True)
-            bt.timesteps.copy_(ts_, non_blocking=True)
-            ready[j].record(copy_stream)
-
+    # the next step's inputs are prefetched on the ring's copy stream while the current step computes (vhap_b200/staging.py: what a
+    # pinned-memory DataLoader with non_blocking copies does); a slot is refilled only after the step that used it finished
     barrier()
     e0.record()
-    prefetch(0)
-    for i in range(args.steps):
+    ring.prefetch(0, batches[0])
+    for i in range(steps):
         j = i % n_batches
-        if i + 1 < args.steps:
-            prefetch((i + 1) % n_batches)
-        cur.wait_event(ready[j])
+        if i + 1 < steps:
+            ring.prefetch((i + 1) % n_batches, batches[(i + 1) % n_batches])
+        ring.acquire(j)
         if use_graph:
             eng.graph_step(j)
         else:
             dp.step(resident[j])
-        freed[j] = torch.cuda.Event()
-        freed[j].record(cur)
+        ring.release(j)
         host_loss.copy_(eng.losses, non_blocking=True)      # D2H of the step's loss vector
     e1.record()
     barrier()
     ms_e2e = maxms(e0.elapsed_time(e1))
-    h2d = batches[0][0].numel() * 2 + batches[0][1].numel() * 4 + batches[0][2].numel() * 4
+    h2d = ring.bytes_per_step()
     d2h = 24 * 4
     if use_graph:
         eng.graph_end()
+    name = {"monocular": f"monocular {size}x{size} batch_size={B}", "nersemble": f"nersemble {B} views {H}x{W} single timestep"}[config]
+    res = {"name": name, "value": round(gB * steps / (ms * 1e-3), 2), "ms_per_step": round(ms / steps, 4), "steps": steps, "global_batch": gB, "image": [H, W],
+           "foreground_fraction": round(fg, 3), "clocks": clk, "losses": {k: round(v, 5) for k, v in losses.items() if k in ("total", "photo", "lmk")},
+           "e2e": {"value": round(gB * steps / (ms_e2e * 1e-3), 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                   "ms_per_step": round(ms_e2e / steps, 4)}}
+    if full:
+        # ---------------- per-kernel device time: the same steps launched eagerly with CUDA events around every kernel (the graph
+        # replay cannot be bracketed per kernel); shares and the dominant kernel's roofline come from this region
+        eng.L.vhap_profile_enable(eng.ctx, 1)
+        eng.L.vhap_set_overlap(eng.ctx, 0)                      # no co-running kernels from the aux streams while timing each kernel
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        nprof = min(steps, 20)
+        for i in range(nprof):
+            dp.step(resident[i % n_batches])
+        p1.record()
+        barrier()
+        nk = eng.L.vhap_profile_kernel_count()
+        avg = (C.c_float * nk)(); cnt = (C.c_uint64 * nk)()
+        eng.L.vhap_profile_read(eng.ctx, avg, cnt)
+        eng.L.vhap_profile_enable(eng.ctx, 0)
+        eng.L.vhap_set_overlap(eng.ctx, 1)
+        names = [eng.L.vhap_profile_kernel_name(k).decode() for k in range(nk)]
+        res["prof"] = dict(names=names, avg=[float(a) for a in avg], cnt=[int(c) for c in cnt], nprof=nprof, ms_eager=p0.elapsed_time(p1) / nprof)
+    eng.close()
+    del eng, resident, batches, ring
+    torch.cuda.empty_cache()
+    return res
 
-    # ---------------- per-kernel device time: the same steps launched eagerly with CUDA events around every kernel (the graph
-    # replay cannot be bracketed per kernel); shares and the dominant kernel's roofline come from this region
-    eng.L.vhap_profile_enable(eng.ctx, 1)
-    eng.L.vhap_set_overlap(eng.ctx, 0)                      # no co-running kernels from the aux streams while timing each kernel
-    barrier()
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    p0.record()
-    nprof = min(args.steps, 20)
-    for i in range(nprof):
-        dp.step(resident[i % n_batches])
-    p1.record()
-    barrier()
-    ms_prof = p0.elapsed_time(p1)
-    nk = eng.L.vhap_profile_kernel_count()
-    avg = (C.c_float * nk)(); cnt = (C.c_uint64 * nk)()
-    eng.L.vhap_profile_read(eng.ctx, avg, cnt)
-    eng.L.vhap_profile_enable(eng.ctx, 0)
-    eng.L.vhap_set_overlap(eng.ctx, 1)
 
+def run_ours(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    B, size, config = args.batch, args.size, args.config
+    main = measure(args, config, size, B, full=True)
+    extras = {}
+    if not args.no_extra:
+        # the other BASELINE configurations that fit one GPU per rank, same process, fewer steps
+        todo = [("monocular", 512), ("monocular", 1024), ("nersemble", 0)]
+        for cfg_name, sz in todo:
+            if (cfg_name, sz if cfg_name == "monocular" else 0) == (config, size if config == "monocular" else 0):
+                continue
+            r = measure(args, cfg_name, sz or 512, 16, full=False)
+            extras[r["name"]] = {k: r[k] for k in ("value", "ms_per_step", "steps", "global_batch", "image", "foreground_fraction", "e2e", "losses")}
+            extras[r["name"]]["unit"] = UNIT
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    names = [eng.L.vhap_profile_kernel_name(k).decode() for k in range(nk)]
-    per_step = {names[k]: float(avg[k]) * cnt[k] / nprof for k in range(nk) if cnt[k]}
-    launches_per_step = int(sum(cnt[k] for k in range(nk))) // nprof
+    H, W = workload_shape(config, size)
+    prof = main.pop("prof")
+    names, avg, cnt, nprof = prof["names"], prof["avg"], prof["cnt"], prof["nprof"]
+    nk = len(names)
+    per_step = {names[k]: avg[k] * cnt[k] / nprof for k in range(nk) if cnt[k]}
+    launches_per_step = int(sum(cnt)) // nprof
     ksum = sum(per_step.values())
-    P = B * size * size
+    fg = main["foreground_fraction"]
+    P = B * H * W
     peak, peak_src = peaks()
+    T = 2048
     # algorithmic bytes per launch (SURVEY.md 8d / DESIGN.md section 4): fused backward = 20 B/px read + 30 rho B/px texel RMW
     algo = {
         "passC_backward": P * (20 + 30 * fg),
         "passB_disturb_aa_loss": P * 20,
         "passA_shade": P * (4 + (16 + 15) * fg),
         "fine_raster": P * 4,
-        "tex_fold_reg_adam": 3 * 2048 * 2048 * 4 * 7 + 2048 * 2048 * 16,
+        "tex_fold_reg_adam": 3 * T * T * 4 * 7 + T * T * 16,
     }
     dom = max(per_step, key=per_step.get)
     kern = {k: {"ms_per_step": round(v, 4), "share": round(v / ksum, 3)} for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])[:12]}
     roof_k = dom if dom in algo else "passC_backward"
-    k_avg = float(avg[names.index(roof_k)])
+    k_avg = avg[names.index(roof_k)]
     ach = algo[roof_k] / (k_avg * 1e-3) / 1e9 if k_avg > 0 else 0.0
     # DRAM traffic per launch from the committed ncu --set full capture (profiles/), only for the workload it was captured on
     traffic, traffic_src, others = None, None, {}
-    try:
-        tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_traffic.json")))
-        if tj["workload"] == f"monocular {size}x{size} batch_size={B}":
-            traffic = tj["kernels"].get(roof_k, {}).get("dram_bytes_per_launch")
-            traffic_src = tj["source"]
-            for kn, rec in tj["kernels"].items():          # the other profiled kernels, for context
-                if kn != roof_k and kn in algo and kn in names and float(avg[names.index(kn)]) > 0:
-                    a_ = algo[kn] / (float(avg[names.index(kn)]) * 1e-3) / 1e9
-                    others[kn] = {"achieved": round(a_, 1), "frac": round(a_ / peak, 4), "traffic": rec["dram_bytes_per_launch"],
-                                  "avg_launch_ms": round(float(avg[names.index(kn)]), 4), "algorithmic_bytes_per_launch": int(algo[kn])}
-    except Exception:
-        pass
+    for fn in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):
+        try:
+            tj = json.load(open(ROOT / "profiles" / fn))
+        except Exception:
+            continue
+        if tj["workload"] != f"monocular {size}x{size} batch_size={B}" or config != "monocular":
+            continue
+        traffic = tj["kernels"].get(roof_k, {}).get("dram_bytes_per_launch")
+        traffic_src = tj["source"]
+        for kn, rec in tj["kernels"].items():          # the other profiled kernels, for context
+            if kn != roof_k and kn in algo and kn in names and avg[names.index(kn)] > 0:
+                a_ = algo[kn] / (avg[names.index(kn)] * 1e-3) / 1e9
+                others[kn] = {"achieved": round(a_, 1), "frac": round(a_ / peak, 4), "traffic": rec["dram_bytes_per_launch"],
+                              "avg_launch_ms": round(avg[names.index(kn)], 4), "algorithmic_bytes_per_launch": int(algo[kn])}
+        break
+    if config == "monocular":
+        wl = (f"monocular {size}x{size} batch_size={B} per GPU photometric tracking (BASELINE configs[{1 if size == 512 else 3}]), "
+              f"stage rgb_global_tracking, Adam on all groups incl. 2048^2 texture")
+    else:
+        wl = (f"NeRSemble {B}-view {H}x{W} calibrated single-timestep photometric fit per GPU (BASELINE configs[2]; at N GPUs every rank takes "
+              f"different timesteps = configs[4]), NeRSemble weights (tex-TV 1e5) and stage rgb_global_tracking, Adam on all groups incl. 2048^2 texture")
+    gB = main["global_batch"]
     out = {
-        "metric": METRIC, "value": round(gB * args.steps / (ms * 1e-3), 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic (real FLAME topology, seeded bases, procedural 2048^2 texture, engine-rendered targets + noise, fp16 RGBA)",
-        "config": {"workload": f"monocular {size}x{size} batch_size={B} per GPU photometric tracking (BASELINE configs[{1 if size == 512 else 3}]), "
-                               f"stage rgb_global_tracking, Adam on all groups incl. 2048^2 texture",
-                   "global_batch": gB, "image": [size, size], "tex": 2048, "foreground_fraction": round(fg, 3),
-                   "parallelism": f"dp{world} frame-sharded, one all-gather (forward slab) + one all-reduce (texture gradient + gradient slab) per step" if world > 1 else "single GPU",
+        "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic (real FLAME topology, seeded bases, procedural 2048^2 texture, engine-rendered targets + noise, uint8 RGB like decoded frames)",
+        "config": {"workload": wl,
+                   "global_batch": gB, "image": [H, W], "tex": T, "foreground_fraction": fg,
+                   "parallelism": (f"dp{world}: one global parameter set, every rank optimises its own {B} distinct frames per step; one all-gather (forward slab) "
+                                   f"+ the gradient reduction (texture + parameter slab) per step") if world > 1 else "single GPU",
                    "launch": ("CUDA graph replay (1 graph launch per step" + (", texture update of step k pipelined into the graph of step k+1; the "
                               "timed region holds exactly K complete steps' worth of work: K replays, each = previous step's texture update + this step's "
-                              "everything else)" if not args.no_pipeline else ")")) if use_graph else "eager (one launch per kernel)",
+                              "everything else)" if not args.no_pipeline else ")")) if not args.no_graph else "eager (one launch per kernel)",
                    "l2": "inputs larger than L2: 4 rotating batches; per-step working set ~0.7 GB (texture, Adam state, targets)"},
-        "e2e": {"value": round(gB * args.steps / (ms_e2e * 1e-3), 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": round(ms_e2e / args.steps, 4),
-                "pipeline": "every step: pinned-host -> device copy of that step's fp16 targets + landmarks + timestep ids (copy stream, "
-                            "prefetched one step ahead into a 4-slot ring), graph replay of the step, device -> host copy of the loss vector"},
+        "e2e": dict(main["e2e"], pipeline="every step: pinned-host -> device copy of that step's uint8 RGB targets + landmarks + timestep ids (copy stream, "
+                    "prefetched one step ahead into a 4-slot ring), graph replay of the step, device -> host copy of the loss vector"),
         "gpu_launches": launches_per_step * args.steps,
-        "clocks": clk,
+        "clocks": main["clocks"],
         "roofline": {"bound": "hbm", "kernel": roof_k, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "avg_launch_ms": round(k_avg, 4),
                      "other_kernels": others,
                      "algorithmic_bytes_per_launch": int(algo[roof_k]), "dominant_kernel": dom,
-                     "timed": f"CUDA events around every launch over {nprof} eagerly launched steps ({round(ms_prof / nprof, 4)} ms/step eager)"},
+                     "timed": f"CUDA events around every launch over {nprof} eagerly launched steps ({round(prof['ms_eager'], 4)} ms/step eager)"},
         "kernels": kern, "kernel_launches_per_step": launches_per_step,
-        "losses": {k: round(v, 5) for k, v in losses.items() if k in ("total", "photo", "lmk")},
+        "losses": main["losses"],
+        "extra_configs": extras,
     }
     if not args.no_cpu and world == 1:
-        out["cpu_baseline"] = cpu_baseline(size, sample_frames=1)
+        out["cpu_baseline"] = cpu_baseline(H, W)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_baseline(size, sample_frames=1, steps=1):
+def cpu_baseline(H, W, sample_frames=4, steps=3, warmup=1):
     """The oracle (CPU port of the reference's path, pinned end to end against the reference's own compute_energy)
-    timed on this box's host cores on a bounded sample: `sample_frames` frame(s) at size^2 with the full 2048^2 texture, `steps` full
-    iterations (energy + backward + torch.optim.Adam), plus the landmark-only stage of configs[0]."""
-    from oracle import energy as E, lbs as L, camera as Cm
+    timed on this box's host cores on a bounded sample: `sample_frames` frames per step at HxW with the full 2048^2 texture, `warmup`
+    untimed + `steps` timed full iterations (energy + backward + torch.optim.Adam), plus the landmark-only stage of configs[0]."""
+    from oracle import energy as E, lbs as L
     from vhap_b200 import synth
     from vhap_b200.config import EngineConfig, STAGES
     from vhap_b200.flame_model import FlameModelData
@@ -342,13 +389,14 @@ def cpu_baseline(size, sample_frames=1, steps=1):
     T = cfg.tex_resolution
     dt = torch.float32
     model = L.model_tensors(m, dt)
-    B, H, W = sample_frames, size, size
+    B = sample_frames
     p = synth.init_params(m, B, T, seed=100)
     P = {k: torch.tensor(v, dtype=dt, requires_grad=True) for k, v in p.items()}
     rgb = torch.tensor(synth.procedural_image(B, H, W)).to(torch.float16).to(dt)
     ts = np.arange(B)
     lmk2d = torch.zeros(B, 68, 3)
-    lmk2d[..., :2] = size / 2
+    lmk2d[..., 0] = W / 2
+    lmk2d[..., 1] = H / 2
     lmk2d[..., 2] = 1
     g = torch.Generator().manual_seed(0)
     dist_ = dict(w_fg=torch.rand(B, H, W, generator=g) < 0.5, w_bg=torch.rand(B, H, W, generator=g) < 0.5, u_rand=torch.rand(B, H, W, generator=g))
@@ -356,8 +404,10 @@ def cpu_baseline(size, sample_frames=1, steps=1):
     sample = dict(rgb=rgb, lmk2d=lmk2d, timestep_index=ts)
     lap = E.laplacian_dense(m, dt)
     opt = torch.optim.Adam([v for v in P.values()], lr=5e-3)
-    t0 = time.perf_counter()
-    for _ in range(steps):
+    t0 = 0.0
+    for it in range(warmup + steps):
+        if it == warmup:
+            t0 = time.perf_counter()
         opt.zero_grad()
         Et, _ = E.compute_energy(P, sample, STAGES["rgb_global_tracking"], cfg, m, model, lap=lap, disturbance=dist_, tex_painted=tp)
         Et.backward()
@@ -378,8 +428,9 @@ def cpu_baseline(size, sample_frames=1, steps=1):
         o1.step()
     d1 = time.perf_counter() - t1
     return {"value": round(B * steps / dtm, 4), "unit": UNIT, "cores": ncores, "kind": "port",
-            "sample": f"{B} frame x {steps} iteration at {size}x{size}, 2048^2 texture, full energy+backward+Adam (oracle/, torch CPU fp32, "
-                      f"{ncores} of {os.cpu_count()} host threads; python-loop rasteriser); {dtm:.1f} s",
+            "sample": f"{B} frames per step x {steps} timed iterations after {warmup} warm-up at {H}x{W}, 2048^2 texture, full energy+backward+Adam (oracle/, torch CPU "
+                      f"fp32, {ncores} of {os.cpu_count()} host threads; per-triangle numpy rasteriser); {dtm:.1f} s; NOTE the bench batch is 16 frames per step: "
+                      f"the per-step 2048^2 texture cost (TV, mip pyramid, Adam) is amortised over {B} frames here instead of 16",
             "landmark_stage_iters_per_s": round(n1 / d1, 2),
             "landmark_stage_sample": f"configs[0]: 1 frame 256x256 lmk_init_all, {n1} iterations, {ncores} threads"}
 
@@ -388,16 +439,13 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    vals = []
-    base = None
-    for _ in range(max(1, min(args.steps, 3))):
-        base = cpu_baseline(args.size, sample_frames=1)
-        vals.append(base["value"])
-    v = float(np.mean(vals))
-    base["value"] = v
-    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": len(vals),
-           "warmup": 0, "ms_per_step": round(1e3 / v, 2) if v else None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-           "data": "synthetic", "config": {"workload": f"monocular {args.size}x{args.size} photometric tracking, bounded sample: 1 frame per step"},
+    H, W = workload_shape(args.config, args.size)
+    steps = max(1, min(args.steps, 3))
+    base = cpu_baseline(H, W, sample_frames=4, steps=steps, warmup=min(args.warmup, 1))
+    v = base["value"]
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": steps,
+           "warmup": min(args.warmup, 1), "ms_per_step": round(4e3 / v, 2) if v else None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic", "config": {"workload": f"{args.config} {H}x{W} photometric tracking, bounded sample: 4 frames per step (bench batch: 16)"},
            "cpu_baseline": base, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
@@ -408,9 +456,11 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="monocular", choices=["monocular", "nersemble"])
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other single-GPU workloads (extra_configs)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="do not defer the texture update into the next step's graph")
     args = ap.parse_args()

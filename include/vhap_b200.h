@@ -75,8 +75,10 @@ typedef struct vhap_grads {
 
 typedef struct vhap_frame_batch {
   int32_t B, H, W;
+  int32_t target_format;       /* 0: target is [B,H,W,4] fp16 RGBA; 1: [B,H,W,3] uint8 RGB exactly as the dataset decodes it -- the
+                                  kernels divide by 255 in fp32 like F.to_tensor (video_dataset.py:256-260); 3 B/px instead of 8 on the wire */
   const int32_t* timesteps;    /* [B] device */
-  const void*    target;       /* [B,H,W,4] fp16 RGBA, image orientation (row 0 top); sample["rgb"] (tracker.py:405) */
+  const void*    target;       /* image orientation (row 0 top); sample["rgb"] (tracker.py:405) */
   const float*   lmk2d;        /* [B,68,3] (x_px,y_px,conf)  sample["lmk2d"] (tracker.py:358) */
   const float*   RT;           /* [B,3,4] or NULL = [I|(0,0,-1)] (tracker.py:1335-1337) */
   const float*   K;            /* [B,4]=(fx,fy,cx,cy) or NULL = from focal_length (tracker.py:141-157) */

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(so):
 def test_abi_version_and_struct_sizes(so):
     from vhap_b200 import _lib
     L = _lib.lib()
-    assert L.vhap_abi_version() == 1
+    assert L.vhap_abi_version() == 2
     assert ctypes.sizeof(_lib.StageCfg) == 176
     assert ctypes.sizeof(_lib.FrameBatch) == 56
 

@@ -34,7 +34,7 @@ def _oracle_params(sc, dt=torch.float64, grad=True):
 def test_library_loaded_is_cuda():
     from vhap_b200 import _lib
     L = _lib.lib()
-    assert L.vhap_abi_version() == 1
+    assert L.vhap_abi_version() == 2
 
 
 def test_flame_forward_backward(eng_small):

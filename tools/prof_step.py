@@ -18,8 +18,8 @@ def main():
     ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--config", default="monocular")
     a = ap.parse_args()
-    eng, batches, fg = bench.build_workload(a.size, a.batch, 2, 0)
-    resident = [eng.stage_sample(t, l, ts.numpy()) for (t, l, ts) in batches]
+    eng, batches, fg = bench.build_workload(a.size, a.batch, 2, 0, 1, a.config)
+    resident = bench.stage_all(eng, batches).batches
     for i in range(4):
         eng.step(resident[i % 2])
     torch.cuda.synchronize()

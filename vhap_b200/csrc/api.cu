@@ -28,7 +28,7 @@ static int upload(vhap_ctx* ctx, T** dst, const T* src, size_t n) {
 }
 #define UP(dst, src, n) do { if (upload(ctx, &(dst), (src), (n))) return -2; } while (0)
 
-extern "C" int vhap_abi_version(void) { return 1; }
+extern "C" int vhap_abi_version(void) { return 2; }   // 2: vhap_frame_batch::target_format (took the padding after W), loss mask, lr scale
 
 static const char* const KID_NAMES[KID_COUNT] = {
     "cam_setup", "pose_fwd", "blend_fwd", "skin_fwd", "landmarks", "vnormals", "vnormals_bwd", "skin_bwd", "pose_bwd", "joff_bwd", "blend_bwd",
@@ -105,6 +105,7 @@ extern "C" int vhap_ctx_create(vhap_ctx** out, const vhap_mesh_desc* m, int32_t 
     for (int k = 0; k < K; ++k) memcpy(&stp[(size_t)k * ctx->Mpad], &st[(size_t)k * M], M * sizeof(float));
     UP(ctx->S_fwd_pad, stp.data(), (size_t)K * ctx->Mpad);
     { const char* e = getenv("VHAP_B200_BLEND"); ctx->use_tc_blend = !(e && strcmp(e, "simt") == 0); }
+    { const char* e = getenv("VHAP_B200_TEXFOLD"); ctx->tex_fold_v1 = (e && strcmp(e, "v1") == 0); }
     // JS[k][j*3+c] = sum_v Jreg[j][v] S[v][c][k] ; Jt = Jreg template
     std::vector<float> js((size_t)K * 15, 0.f), jt(15, 0.f);
     for (int j = 0; j < 5; ++j)
@@ -275,6 +276,7 @@ static int check_batch(vhap_ctx* ctx, const vhap_frame_batch* fb) {
     vh_set_error(ctx, "batch", "exceeds vhap_ctx_reserve() shape");
     return -4;
   }
+  if (fb->target_format != 0 && fb->target_format != 1) { vh_set_error(ctx, "batch", "unknown target_format"); return -4; }
   ctx->curB = fb->B; ctx->curH = fb->H; ctx->curW = fb->W;
   return 0;
 }

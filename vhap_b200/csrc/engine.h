@@ -26,6 +26,7 @@ struct vhap_ctx {
   int mip_off[VH_MAX_MIPS]; size_t mip_total;
   // ---- static model
   float *v_template, *S_fwd, *S_bwd, *posedirs, *Jreg, *lbs_w, *JS, *Jt;
+  int tex_fold_v1;                                // VHAP_B200_TEXFOLD=v1: the round-1 2-row-strip fold kernel (A/B aid)
   float* S_fwd_pad; int Mpad; int use_tc_blend;   // [K][Mpad] copy with 16-byte aligned rows for the tensor-core contraction
   i4 *faces, *faces_uv; float* verts_uv; int* lmk_faces; float* lmk_bary; int* adj_opp; uint8_t* fid2cid;
   int *vf_indptr, *vf_faces; int *lap_indptr, *lap_idx; float* lap_val; int lap_nnz;

@@ -313,7 +313,7 @@ void fill_render_args(vhap_ctx* c, PassArgs& P, const vhap_frame_batch* fb, cons
   for (int i = 0; i < VH_MAX_MIPS; ++i) A.mip_off[i] = c->mip_off[i];
   A.tri_id = c->tri_id; A.face_flags = cfg->training ? c->face_flags : nullptr; A.vert_flags = cfg->training ? c->vert_flags : nullptr;
   A.fid2cid = c->fid2cid; A.adj_opp = c->adj_opp; A.ndc = c->ndc; A.zwbuf = (const float*)c->pre; A.tex_l0_flag = c->tex_l0_flag;
-  P.target = (const uint16_t*)fb->target; P.pre = c->pre; P.signs = c->signs;
+  P.target = (const uint16_t*)fb->target; P.target_u8 = fb->target_format == 1; P.pre = c->pre; P.signs = c->signs;
   P.final_rgba = c->want_planes ? c->final_rgba : nullptr;
   P.plane_albedo = c->want_planes ? c->plane_albedo : nullptr; P.plane_normal = c->want_planes ? c->plane_normal : nullptr;
   P.plane_diffuse = c->want_planes ? c->plane_diffuse : nullptr;

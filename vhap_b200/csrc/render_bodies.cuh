@@ -12,7 +12,8 @@
 
 struct PassArgs {
   RenderArgs R;
-  const uint16_t* target;     // [B,H,W,4] fp16 bits, IMAGE orientation (row 0 = top)
+  const uint16_t* target;     // [B,H,W,4] fp16 bits, IMAGE orientation (row 0 = top); or, target_u8 != 0: [B,H,W,3] uint8 RGB as decoded
+  int target_u8;              // vhap_frame_batch::target_format
   f4* pre;                    // [B,H,W] composite colour of fg pixels (rgb,1) in raster orientation
   uint8_t* signs;             // [B,H,W] 2 bits per channel: 0 zero, 1 positive, 2 negative  (sign of gt - pred)
   float* final_rgba;          // optional [B,H,W,4] debug plane (after AA), raster orientation, or NULL
@@ -69,6 +70,17 @@ VH_HD void philox4x32(uint64_t key, uint64_t ctr_lo, uint64_t ctr_hi, uint32_t o
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+// target pixel (image-orientation pixel index) as float RGB.  uint8 targets are what the reference's dataset decodes; F.to_tensor divides
+// by 255 in fp32 (video_dataset.py:256-260) -- the same IEEE division happens here, so no host-side float image is ever materialised
+VH_HD f3 load_target(const PassArgs& P, size_t ipix) {
+  if (P.target_u8) {
+    const uint8_t* t = (const uint8_t*)P.target + ipix * 3;
+    return mk3((float)t[0] / 255.f, (float)t[1] / 255.f, (float)t[2] / 255.f);
+  }
+  const uint16_t* t = P.target + ipix * 4;
+  return mk3(half_bits_to_float(t[0]), half_bits_to_float(t[1]), half_bits_to_float(t[2]));
+}
+
 // composite colour before disturbance: fg -> pass-A buffer, bg -> target image (flipped, render_nvdiffrast.py:419) or constant
 VH_HD f4 pre_color(const PassArgs& P, int b, int y, int x, int id) {
   const RenderArgs& A = P.R;
@@ -76,8 +88,8 @@ VH_HD f4 pre_color(const PassArgs& P, int b, int y, int x, int id) {
   if (id > 0) { f4 c = P.pre[pix]; c.w = 1.f; return c; }      // .w of the buffer holds z/w, the colour's alpha is 1
   f4 c; c.w = 0.f;
   if (P.bg_mode == 0) {
-    const uint16_t* t = P.target + (((size_t)b * A.H + (A.H - 1 - y)) * A.W + x) * 4;
-    c.x = half_bits_to_float(t[0]); c.y = half_bits_to_float(t[1]); c.z = half_bits_to_float(t[2]);
+    f3 t = load_target(P, ((size_t)b * A.H + (A.H - 1 - y)) * A.W + x);
+    c.x = t.x; c.y = t.y; c.z = t.z;
   } else { c.x = P.bg_color[0]; c.y = P.bg_color[1]; c.z = P.bg_color[2]; }
   return c;
 }
@@ -278,8 +290,8 @@ VH_HD void passB_body(const PassArgs& P, int b, int y, int x, float* acc) {
     f4 Dq = disturbed_color(P, b, qy, qx, idq, nullptr);
     out.x += a * (Dq.x - Dp.x); out.y += a * (Dq.y - Dp.y); out.z += a * (Dq.z - Dp.z); out.w += a * (Dq.w - Dp.w);
   }
-  const uint16_t* t = P.target + (((size_t)b * A.H + (A.H - 1 - y)) * A.W + x) * 4;
-  float e0 = half_bits_to_float(t[0]) - out.x, e1 = half_bits_to_float(t[1]) - out.y, e2 = half_bits_to_float(t[2]) - out.z;
+  const f3 t = load_target(P, ((size_t)b * A.H + (A.H - 1 - y)) * A.W + x);
+  float e0 = t.x - out.x, e1 = t.y - out.y, e2 = t.z - out.z;
   if (P.loss_mask && !P.loss_mask[((size_t)b * A.H + (A.H - 1 - y)) * A.W + x]) { e0 = 0.f; e1 = 0.f; e2 = 0.f; }
   acc[0] += fabsf(e0) + fabsf(e1) + fabsf(e2);
   if (out.w > 0.f) acc[1] += 1.f;

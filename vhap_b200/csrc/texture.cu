@@ -232,6 +232,202 @@ __global__ void __launch_bounds__(256, 4) k_tex_fold(TexFoldArgs a, float* __res
   if (tid == 0) *counter = 0u;
 }
 
+// ---- version 2 of the fold kernel: a CTA walks a band of TF_ROWS texture rows of a 256-wide strip top to bottom, one row per
+// iteration, with the loads of row y+1 in flight while row y is processed (software pipeline of depth 1 in registers):
+//   * the rows above / below a texel (total variation) are the previous / next iteration's register values: the halo is 2 rows per
+//     TF_ROWS instead of 2 per 2 (v1 re-read both neighbour rows of every 2-row strip: +16 B/texel of the 16 B/texel level 0),
+//   * left / right neighbours come from warp shuffles (only lanes 0 / 31 load their outside neighbour),
+//   * the coarse levels of the gradient pyramid are folded hierarchically per band (levels >= 3 once per 8x8 block, level 2 once
+//     per 4x4, level 1 once per 2x2) instead of 11 dependent loads per level-1 texel.
+// Same arithmetic per texel as v1 (fold_texel); the coarse fold sums the levels in a different association (1e-7 relative).
+#ifndef TF_ROWS
+#define TF_ROWS 8
+#endif
+#ifndef TF_MINB
+#define TF_MINB 4
+#endif
+struct RowIn { f4 t; float ex[3], m[3], v[3], g[3]; unsigned char msk; };
+
+__device__ __forceinline__ void row_load(const TexFoldArgs& a, int x, int y, bool l0, RowIn& r) {
+  const size_t n = (size_t)a.T * a.T, i = (size_t)y * a.T + x;
+  r.t = a.tex_old[i];
+  r.g[0] = r.g[1] = r.g[2] = 0.f;
+  if (a.g_in) { r.g[0] = a.g_in[i]; r.g[1] = a.g_in[n + i]; r.g[2] = a.g_in[2 * n + i]; }
+  else if (l0) { float4 g0 = *(const float4*)(a.g_pyr + i * 4); r.g[0] = g0.x; r.g[1] = g0.y; r.g[2] = g0.z; }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { r.ex[c] = a.extra[c * n + i]; if (a.do_adam) { r.m[c] = a.m[c * n + i]; r.v[c] = a.v[c * n + i]; } }
+  r.msk = (a.w_res > 0.f && a.mask) ? a.mask[i] : 0;
+}
+
+__global__ void __launch_bounds__(256, TF_MINB) k_tex_fold2(TexFoldArgs a, float* __restrict__ partials, unsigned* __restrict__ counter, float* __restrict__ acc_out) {
+  __shared__ float sh[8 * 2];
+  __shared__ float c1[(TF_ROWS / 2) * 128][3];        // folded gradient of levels >= 1 per level-1 texel of the band
+  __shared__ float c2[((TF_ROWS + 3) / 4) * 64][3];
+  __shared__ float c3[((TF_ROWS + 7) / 8) * 32][3];
+  __shared__ bool is_last;
+  const int T = a.T, tw = T < 256 ? T : 256, tpr = T / tw, R = T < TF_ROWS ? T : TF_ROWS;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int x0 = (blockIdx.x % tpr) * tw, x = x0 + tid, y0 = (blockIdx.x / tpr) * R;
+  const int n1x = tw >> 1, n1y = R >> 1, n2x = tw >> 2 ? tw >> 2 : 1, n2y = R >> 2 ? R >> 2 : 1, n3x = tw >> 3 ? tw >> 3 : 1, n3y = R >> 3 ? R >> 3 : 1;
+  const bool fold = a.g_pyr != nullptr && a.g_in == nullptr;
+  // ---- hierarchical fold of the coarse gradient levels (box-filter adjoint: 1/4 per level)
+  for (int j = tid; j < n3x * n3y; j += 256) {
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+    if (fold) {
+      const int X = (x0 >> 3) + j % n3x, Y = (y0 >> 3) + j / n3x;
+      float sc = 1.f / 64.f;
+      for (int l = 3; l <= a.max_level; ++l) {
+        float4 p = *(const float4*)(a.g_pyr + ((size_t)a.mip_off[l] + (size_t)(Y >> (l - 3)) * (T >> l) + (X >> (l - 3))) * 4);
+        g0 += p.x * sc; g1 += p.y * sc; g2 += p.z * sc;
+        sc *= 0.25f;
+      }
+    }
+    c3[j][0] = g0; c3[j][1] = g1; c3[j][2] = g2;
+  }
+  __syncthreads();
+  for (int j = tid; j < n2x * n2y; j += 256) {
+    const int jx = j % n2x, jy = j / n2x;
+    const int p3 = ((jy >> 1) < n3y ? (jy >> 1) : n3y - 1) * n3x + ((jx >> 1) < n3x ? (jx >> 1) : n3x - 1);
+    float g0 = c3[p3][0], g1 = c3[p3][1], g2 = c3[p3][2];
+    if (fold && a.max_level >= 2) {
+      const int X = (x0 >> 2) + jx, Y = (y0 >> 2) + jy;
+      float4 p = *(const float4*)(a.g_pyr + ((size_t)a.mip_off[2] + (size_t)Y * (T >> 2) + X) * 4);
+      g0 += p.x * (1.f / 16.f); g1 += p.y * (1.f / 16.f); g2 += p.z * (1.f / 16.f);
+    }
+    c2[j][0] = g0; c2[j][1] = g1; c2[j][2] = g2;
+  }
+  __syncthreads();
+  for (int j = tid; j < n1x * n1y; j += 256) {
+    const int jx = j % n1x, jy = j / n1x;
+    const int p2 = ((jy >> 1) < n2y ? (jy >> 1) : n2y - 1) * n2x + ((jx >> 1) < n2x ? (jx >> 1) : n2x - 1);
+    float g0 = c2[p2][0], g1 = c2[p2][1], g2 = c2[p2][2];
+    if (fold && a.max_level >= 1) {
+      const int X = (x0 >> 1) + jx, Y = (y0 >> 1) + jy;
+      float4 p = *(const float4*)(a.g_pyr + ((size_t)a.mip_off[1] + (size_t)Y * (T >> 1) + X) * 4);
+      g0 += p.x * 0.25f; g1 += p.y * 0.25f; g2 += p.z * 0.25f;
+    }
+    c1[j][0] = g0; c1[j][1] = g1; c1[j][2] = g2;
+  }
+  __syncthreads();
+  float acc[2] = {0.f, 0.f};
+  const bool on = tid < tw;
+  const bool l0 = fold ? (a.l0_flag ? (*a.l0_flag != 0) : true) : false;
+  float bc1 = a.bc1, bc2s = a.bc2_sqrt;
+  if (a.do_adam && a.step_ptr) {
+    float st = (float)(a.step_ptr[0] + a.step_bias); bc2s = sqrtf(1.f - powf(0.999f, st));
+    bc1 = (1.f - powf(0.9f, st)) / a.lr_scale_ptr[0];
+  }
+  const size_t n = (size_t)T * T;
+  const bool tv = a.w_tv > 0.f;
+  RowIn cur = {}, nxt;
+  f4 t_up = {0, 0, 0, 0}, o_prev = {0, 0, 0, 0};
+  if (on) {
+    row_load(a, x, y0, l0, cur);
+    t_up = (tv && y0 > 0) ? a.tex_old[(size_t)(y0 - 1) * T + x] : cur.t;
+  }
+  nxt = cur;
+#pragma unroll 1
+  for (int r = 0; r < R; ++r) {
+    const int y = y0 + r;
+    const size_t i = (size_t)y * T + x;
+    f4 t_dn = cur.t;
+    if (on) {
+      if (r + 1 < R) { row_load(a, x, y + 1, l0, nxt); t_dn = nxt.t; }           // next row's loads are in flight during this row's arithmetic
+      else if (tv && y + 1 < T) t_dn = a.tex_old[i + T];
+    }
+    f4 o = {0, 0, 0, 0};
+    // left / right neighbours of this row through the warp; the strip's outside neighbours by lanes 0 / 31
+    f4 tl, tr;
+    tl.x = __shfl_up_sync(0xffffffffu, cur.t.x, 1); tl.y = __shfl_up_sync(0xffffffffu, cur.t.y, 1); tl.z = __shfl_up_sync(0xffffffffu, cur.t.z, 1);
+    tr.x = __shfl_down_sync(0xffffffffu, cur.t.x, 1); tr.y = __shfl_down_sync(0xffffffffu, cur.t.y, 1); tr.z = __shfl_down_sync(0xffffffffu, cur.t.z, 1);
+    if (on) {
+      const f4 t = cur.t;
+      if (tv) {
+        if (lane == 0) tl = x > 0 ? a.tex_old[i - 1] : t;
+        if (lane == 31 || x + 1 >= T || tid + 1 >= tw) tr = x + 1 < T ? a.tex_old[i + 1] : t;
+      }
+      const float* cg = c1[(r >> 1) * n1x + (tid >> 1)];
+      float g[3] = {cur.g[0], cur.g[1], cur.g[2]};
+      if (fold) { g[0] += cg[0]; g[1] += cg[1]; g[2] += cg[2]; }
+      if (l0) *(float4*)(a.g_pyr + i * 4) = make_float4(0.f, 0.f, 0.f, 0.f);       // coarser levels: memset after the kernel
+      if (tv) {                                                                      // tracker.py:526-534
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float v = chan(t, c), dr = v - chan(tr, c), dd = v - chan(t_dn, c), dl = chan(tl, c) - v, du = chan(t_up, c) - v;
+          acc[0] += a.w_tv * (dr * dr + dd * dd);
+          g[c] += 2.f * a.w_tv * (dr + dd - dl - du);
+        }
+      }
+      if (cur.msk) {                                                                 // tracker.py:536-539
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { acc[1] += a.w_res * cur.ex[c] * cur.ex[c]; g[c] += 2.f * a.w_res * cur.ex[c]; }
+      }
+      if (a.g_out) { a.g_out[i] = g[0]; a.g_out[n + i] = g[1]; a.g_out[2 * n + i] = g[2]; }
+      o = t;
+      if (a.do_adam) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const size_t k = c * n + i;
+          float m = 0.9f * cur.m[c] + 0.1f * g[c];
+          float v = 0.999f * cur.v[c] + 0.001f * g[c] * g[c];
+          a.m[k] = m; a.v[k] = v;
+          float upd = (a.lr / bc1) * m / (sqrtf(v) / bc2s + 1e-8f);
+          float ne = cur.ex[c] - upd;
+          a.extra[k] = ne;
+          float base = chan(t, c) - cur.ex[c];                                        // painted part
+          if (c == 0) o.x = base + ne; else if (c == 1) o.y = base + ne; else o.z = base + ne;
+        }
+        a.tex_new[i] = o;
+      }
+    }
+    // level 1 of the new pyramid on odd rows: avg4(A[2y][2x], A[2y+1][2x], A[2y][2x+1], A[2y+1][2x+1]), same order as k_mip_down
+    if (r & 1) {
+      f4 c, d;
+      c.x = __shfl_down_sync(0xffffffffu, o_prev.x, 1); c.y = __shfl_down_sync(0xffffffffu, o_prev.y, 1); c.z = __shfl_down_sync(0xffffffffu, o_prev.z, 1);
+      d.x = __shfl_down_sync(0xffffffffu, o.x, 1); d.y = __shfl_down_sync(0xffffffffu, o.y, 1); d.z = __shfl_down_sync(0xffffffffu, o.z, 1);
+      c.w = d.w = 0.f;
+      if (on && a.do_adam && a.max_level >= 1 && !(tid & 1))
+        a.tex_new[(size_t)a.mip_off[1] + (size_t)(y >> 1) * (T >> 1) + (x >> 1)] = avg4(o_prev, o, c, d);
+    }
+    o_prev = o;
+    t_up = cur.t;
+    cur = nxt;
+  }
+  // block partial sums of the two loss terms; the last CTA reduces all partials in a fixed order
+  const int w = tid >> 5;
+  for (int q = 0; q < 2; ++q) {
+    float v = acc[q];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sh[w * 2 + q] = v;
+  }
+  __syncthreads();
+  if (tid < 2) {
+    float s2 = 0.f;
+    for (int k = 0; k < 8; ++k) s2 += sh[k * 2 + tid];
+    partials[(size_t)blockIdx.x * 2 + tid] = s2;
+    __threadfence();
+  }
+  __syncthreads();
+  if (tid == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int q = 0; q < 2; ++q) {
+    float s2 = 0.f;
+    for (int r = tid; r < (int)gridDim.x; r += 256) s2 += __ldcg(partials + (size_t)r * 2 + q);
+    for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    __syncthreads();
+    if (lane == 0) sh[w] = s2;
+    __syncthreads();
+    if (tid == 0) {
+      float t = 0.f;
+      for (int k = 0; k < 8; ++k) t += sh[k];
+      acc_out[q] = t;
+    }
+  }
+  if (tid == 0) *counter = 0u;
+}
+
 // TV + residual regulariser LOSS VALUES of the current texture (tracker.py:526-539), no gradient: used when the texture update is
 // deferred into the next step (the fold kernel then sees the texture one step late), so that a step's loss vector is complete.
 __global__ void __launch_bounds__(256) k_tex_reg_loss(const f4* __restrict__ tex, const float* __restrict__ extra, const uint8_t* __restrict__ mask, int T,
@@ -305,7 +501,13 @@ void launch_tex_fold(vhap_ctx* c, float* tex_extra, float* g_out, float* m, floa
   a.do_adam = (m != nullptr && v != nullptr) ? 1 : 0;
   a.lr = lr; a.bc1 = 1.f - powf(0.9f, (float)step); a.bc2_sqrt = sqrtf(1.f - powf(0.999f, (float)step));
   int tw = T < 256 ? T : 256, nblk = (T / tw) * (T / 2), L = c->max_level >= 1 ? 1 : 0;
-  LAUNCH(c, KID_TEX_FOLD, s, k_tex_fold<<<nblk, 256, 0, s>>>(a, c->tv_partials, c->tex_counter, a.g_in ? c->tex_loss + 2 : c->tex_loss));      // apply mode: scratch slots
+  if (c->tex_fold_v1) {
+    LAUNCH(c, KID_TEX_FOLD, s, k_tex_fold<<<nblk, 256, 0, s>>>(a, c->tv_partials, c->tex_counter, a.g_in ? c->tex_loss + 2 : c->tex_loss));      // apply mode: scratch slots
+  } else {
+    int R = T < TF_ROWS ? T : TF_ROWS;
+    nblk = (T / tw) * (T / R);
+    LAUNCH(c, KID_TEX_FOLD, s, k_tex_fold2<<<nblk, 256, 0, s>>>(a, c->tv_partials, c->tex_counter, a.g_in ? c->tex_loss + 2 : c->tex_loss));
+  }
   if (a.g_in) {                                                           // apply mode leaves the gradient pyramid alone
     if (a.do_adam) { c->cur_mip ^= 1; build_mips(c, c->mips[c->cur_mip], s, L); }
     return;

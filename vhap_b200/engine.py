@@ -28,7 +28,8 @@ class Batch:
     def __init__(self, B, H, W, timesteps, target, lmk2d, RT=None, K=None):
         self.B, self.H, self.W = B, H, W
         self.timesteps, self.target, self.lmk2d, self.RT, self.K = timesteps, target, lmk2d, RT, K
-        self.c = _lib.FrameBatch(B, H, W, _ptr(timesteps), _ptr(target), _ptr(lmk2d), _ptr(RT), _ptr(K))
+        fmt = 1 if (target is not None and target.dtype == torch.uint8) else 0      # uint8 RGB as decoded / fp16 RGBA
+        self.c = _lib.FrameBatch(B, H, W, fmt, _ptr(timesteps), _ptr(target), _ptr(lmk2d), _ptr(RT), _ptr(K))
 
 
 class Engine:
@@ -280,7 +281,14 @@ class Engine:
     def stage_sample(self, rgb, lmk2d, timesteps, RT=None, K=None, non_blocking=True) -> Batch:
         """rgb: [B,3,H,W] float (host or device, like sample['rgb']) or an already packed [B,H,W,4] fp16 tensor
         (host pinned memory for the end-to-end path).  Returns device-resident Batch."""
-        if rgb.dtype == torch.float16 and rgb.dim() == 4 and rgb.shape[-1] == 4:
+        if rgb.dtype == torch.uint8:
+            # the image as the dataset decodes it, [B,H,W,3] uint8 (video_dataset.py:209-241 before F.to_tensor): 3 bytes per pixel over
+            # PCIe, the /255 of to_tensor happens inside the kernels
+            if rgb.dim() != 4 or rgb.shape[-1] != 3:
+                raise ValueError(f"uint8 targets must be [B,H,W,3], got {tuple(rgb.shape)}")
+            tgt = rgb.to(self.dev, non_blocking=non_blocking).contiguous()
+            B, H, W = tgt.shape[:3]
+        elif rgb.dtype == torch.float16 and rgb.dim() == 4 and rgb.shape[-1] == 4:
             tgt = rgb.to(self.dev, non_blocking=non_blocking)
             B, H, W = tgt.shape[:3]
         else:

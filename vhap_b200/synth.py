@@ -82,6 +82,28 @@ def landmarks_px(lmks_ndc_flipped: np.ndarray, H: int, W: int, seed: int = 0, no
     return np.stack([x, y, conf], -1).astype(np.float32)
 
 
+def project_ndc(pts: np.ndarray, RT, K, H: int, W: int, focal: float = 1.5) -> np.ndarray:
+    """world points [B,N,3] -> NDC (x, y flipped) like NVDiffRenderer.world_to_ndc(flip_y=True) (render_nvdiffrast.py:117-214).
+    RT [B,3,4] / K [B,3,3] or [B,4]; None = the uncalibrated default camera (tracker.py:141-157,1333-1337: RT = [I | (0,0,-1)],
+    fx = fy = focal * max(H, W), principal point at the image centre)."""
+    B = pts.shape[0]
+    if RT is None:
+        RT = np.tile(np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, -1]], np.float64), (B, 1, 1))
+    if K is None:
+        f = focal * max(H, W)
+        K = np.tile(np.array([f, f, 0.5 * W, 0.5 * H], np.float64), (B, 1))
+    K = np.asarray(K, np.float64)
+    if K.shape[-2:] == (3, 3):
+        K = np.stack([K[:, 0, 0], K[:, 1, 1], K[:, 0, 2], K[:, 1, 2]], -1)
+    RT = np.asarray(RT, np.float64)
+    cam = np.einsum("bij,bnj->bni", RT[:, :, :3], pts.astype(np.float64)) + RT[:, None, :, 3]
+    fx, fy, cx, cy = (K[:, None, i] for i in range(4))
+    clip_x = (2 * fx / W) * cam[..., 0] + ((W - 2 * cx) / W) * cam[..., 2]
+    clip_y = (2 * fy / H) * cam[..., 1] + ((H - 2 * cy) / H) * cam[..., 2]
+    w = -cam[..., 2]
+    return np.stack([clip_x / w, -(clip_y / w)], -1)
+
+
 def ring_cameras(model, n_views: int, H: int, W: int, head_centre, radius: float = 1.0, yaw_span_deg: float = 120.0, pitch_deg: float = 8.0,
                  fill: float = 1.0, seed: int = 0):
     """Calibrated multi-view rig standing in for NeRSemble's 16 cameras (nersemble_dataset.py:75-127: one shared intrinsic matrix, one
