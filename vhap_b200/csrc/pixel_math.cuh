@@ -314,8 +314,11 @@ VH_HD void shade_pixel(const RenderArgs& A, int b, int px, int py, int tri, PixS
 //   g_clip  [B,V,4]  atomics          g_vnorm [B,V,4] atomics        grad_pyr texture-gradient pyramid (float4) or NULL
 //   g_lights_local[27] per-thread accumulator (reduced by the caller)
 //   g_dd: extra gradient on diffuse_detach_normal (reg_diffuse), flows to the lights only.
+// vg != NULL: the per-vertex gradients of this pixel are RETURNED (for a warp-level reduction over the pixels of one triangle,
+// k_passC2) instead of being added to g_clip / g_vnorm with one vector reduction per vertex per pixel.
+struct VertGrad { f3 gn[3]; f3 gc[3]; };      // d/d vertex normal (xyz), d/d clip position (x, y, w) of the triangle's three vertices
 VH_HD void shade_pixel_bwd(const RenderArgs& A, int b, int tri, const PixShade& s, f3 g_rgb, f3 g_dd,
-                           float* g_clip, float* g_vnorm, float* grad_pyr, float* g_lights_local) {
+                           float* g_clip, float* g_vnorm, float* grad_pyr, float* g_lights_local, VertGrad* vg = nullptr) {
   f3 g_alb = g_rgb * s.diffuse, g_dif = g_rgb * s.albedo;
   for (int k = 0; k < 9; ++k) {
     g_lights_local[k * 3 + 0] += s.Bk[k] * (g_dif.x + g_dd.x);
@@ -325,7 +328,8 @@ VH_HD void shade_pixel_bwd(const RenderArgs& A, int b, int tri, const PixShade& 
   f3 g_n = sh_bwd_normal(s.n, A.lights, g_dif);
   f3 g_raw = s.n_free ? (g_n - s.n * dot3(s.n, g_n)) * s.inv_len : g_n * s.inv_len;
   float b0 = s.ts.b0, b1 = s.ts.b1, b2 = 1.f - b0 - b1;
-  if (g_vnorm) {
+  if (vg) { vg->gn[0] = g_raw * b0; vg->gn[1] = g_raw * b1; vg->gn[2] = g_raw * b2; }
+  else if (g_vnorm) {
     float* gv = g_vnorm + (size_t)b * A.V * 4;
     const f3 gg[3] = {g_raw * b0, g_raw * b1, g_raw * b2};
     for (int k = 0; k < 3; ++k) {
@@ -347,7 +351,8 @@ VH_HD void shade_pixel_bwd(const RenderArgs& A, int b, int tri, const PixShade& 
   float g_dvdy = g_da[1] * d1u + g_da[3] * d1v;
   f4 gp[3];
   tri_setup_bwd(A, s.ts, g_b0, g_b1, g_dudx, g_dudy, g_dvdx, g_dvdy, gp);
-  if (g_clip) {
+  if (vg) { for (int k = 0; k < 3; ++k) vg->gc[k] = mk3(gp[k].x, gp[k].y, gp[k].w); }
+  else if (g_clip) {
     float* gc = g_clip + (size_t)b * A.V * 4;
     for (int k = 0; k < 3; ++k) {
       float* t = gc + (size_t)s.ts.vi[k] * 4;

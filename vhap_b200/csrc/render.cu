@@ -193,6 +193,9 @@ __global__ void __launch_bounds__(PB, VH_C1_MIN) k_passC1(PassArgs P, const floa
 #ifndef VH_C2_PB
 #define VH_C2_PB 256
 #endif
+#ifndef VH_C2_AGG
+#define VH_C2_AGG 1            // warp-level reduction of the per-vertex gradients over the pixels of one triangle (0: one reduction per pixel)
+#endif
 __global__ void __launch_bounds__(VH_C2_PB, VH_C2_MINBLOCKS) k_passC2(PassArgs P, const f4* __restrict__ grgb, float* __restrict__ partials) {
   __shared__ float sh[(VH_C2_PB / 32) * 27];
   const RenderArgs& A = P.R;
@@ -202,12 +205,64 @@ __global__ void __launch_bounds__(VH_C2_PB, VH_C2_MINBLOCKS) k_passC2(PassArgs P
 #pragma unroll
   for (int i = 0; i < 27; ++i) gl[i] = 0.f;
   const int* tris = P.pool_tri + P.pool_base[1];
+#if VH_C2_AGG
+  // The foreground list is in pixel order, so the pixels of one triangle on a scan line are neighbouring lanes: their per-vertex
+  // gradients are summed with a segmented warp reduction (suffix sums over the run of equal (frame, triangle) keys, 5 shuffle steps)
+  // and leave as ONE vector reduction per vertex per run instead of one per pixel (the L1 reduction path was 65 % busy, ncu r02 base).
+  const int lane = threadIdx.x & 31;
+  const int n_round = (n_fg + 31) & ~31;
+  for (int i = blockIdx.x * VH_C2_PB + threadIdx.x; i < n_round; i += gridDim.x * VH_C2_PB) {
+    const bool on = i < n_fg;
+    int id = 0, b = 0, key = -1 - lane;                 // inactive lanes: unique negative keys (runs of length 1, skipped)
+    VertGrad vg;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { vg.gn[k] = mk3(0, 0, 0); vg.gc[k] = mk3(0, 0, 0); }
+    if (on) {
+      int pix = list[i]; id = tris[i];
+      int x, y; vh_unflatten(A, pix, b, y, x);
+      f4 g = grgb[i];
+      passC2_body(P, b, y, x, mk3(g.x, g.y, g.z), gl, id, &vg);
+      key = b * (A.F + 1) + id;
+    }
+    const int kprev = __shfl_up_sync(0xffffffffu, key, 1);
+    const bool head = lane == 0 || key != kprev;
+    const unsigned heads = __ballot_sync(0xffffffffu, head);
+    const int run = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));       // lane of this run's head
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int run_d = __shfl_down_sync(0xffffffffu, run, d);
+      const bool take = (lane + d < 32) && run_d == run;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        float t;
+        t = __shfl_down_sync(0xffffffffu, vg.gn[k].x, d); if (take) vg.gn[k].x += t;
+        t = __shfl_down_sync(0xffffffffu, vg.gn[k].y, d); if (take) vg.gn[k].y += t;
+        t = __shfl_down_sync(0xffffffffu, vg.gn[k].z, d); if (take) vg.gn[k].z += t;
+        t = __shfl_down_sync(0xffffffffu, vg.gc[k].x, d); if (take) vg.gc[k].x += t;
+        t = __shfl_down_sync(0xffffffffu, vg.gc[k].y, d); if (take) vg.gc[k].y += t;
+        t = __shfl_down_sync(0xffffffffu, vg.gc[k].z, d); if (take) vg.gc[k].z += t;
+      }
+    }
+    if (on && head) {
+      const i4 f = A.faces[id - 1];
+      const int vi[3] = {f.x, f.y, f.z};
+      float* gv = P.g_vnorm + (size_t)b * A.V * 4;
+      float* gc = P.g_clip + (size_t)b * A.V * 4;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (P.g_vnorm) VH_ATOMIC_ADD4(gv + (size_t)vi[k] * 4, vg.gn[k].x, vg.gn[k].y, vg.gn[k].z, 0.f);
+        if (P.g_clip) VH_ATOMIC_ADD4(gc + (size_t)vi[k] * 4, vg.gc[k].x, vg.gc[k].y, 0.f, vg.gc[k].z);
+      }
+    }
+  }
+#else
   for (int i = blockIdx.x * VH_C2_PB + threadIdx.x; i < n_fg; i += gridDim.x * VH_C2_PB) {
     int pix = list[i], id = tris[i];
     int x, y, b; vh_unflatten(A, pix, b, y, x);
     f4 g = grgb[i];
     passC2_body(P, b, y, x, mk3(g.x, g.y, g.z), gl, id);
   }
+#endif
   block_reduce_store<27, VH_C2_PB>(gl, sh, partials + (size_t)blockIdx.x * VH_NPART + 4);
 }
 

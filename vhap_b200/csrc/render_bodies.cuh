@@ -367,7 +367,7 @@ VH_HD f3 passC1_body(const PassArgs& P, int b, int y, int x, const float* ext_gr
   return gD * own_w;
 }
 
-VH_HD void passC2_body(const PassArgs& P, int b, int y, int x, f3 g_rgb, float* g_lights_local, int id_known = -1) {
+VH_HD void passC2_body(const PassArgs& P, int b, int y, int x, f3 g_rgb, float* g_lights_local, int id_known = -1, VertGrad* vg = nullptr) {
   const RenderArgs& A = P.R;
   size_t pix = ((size_t)b * A.H + y) * A.W + x;
   int id = id_known >= 0 ? id_known : A.tri_id[pix];
@@ -386,7 +386,7 @@ VH_HD void passC2_body(const PassArgs& P, int b, int y, int x, f3 g_rgb, float* 
       if (am / 3 == (int)pix) { int ch = am % 3; if (ch == 0) g_dd.x += g_max; else if (ch == 1) g_dd.y += g_max; else g_dd.z += g_max; }
     }
   }
-  shade_pixel_bwd(A, b, id - 1, s, g_rgb, g_dd, P.g_clip, P.g_vnorm, P.g_tex, g_lights_local);
+  shade_pixel_bwd(A, b, id - 1, s, g_rgb, g_dd, P.g_clip, P.g_vnorm, P.g_tex, g_lights_local, vg);
 }
 
 VH_HD void passC_body(const PassArgs& P, int b, int y, int x, const float* ext_grad, float* g_lights_local) {
