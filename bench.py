@@ -173,7 +173,7 @@ def measure(args, config, size, B, full):
     gB = B * world
     ring = stage_all(eng, batches)          # device slots with fixed addresses (graphs are captured per slot)
     resident = ring.batches
-    dp = DataParallelStep(eng)
+    dp = DataParallelStep(eng, texture=args.dp_texture)
     use_graph = not args.no_graph
 
     def barrier():
@@ -348,8 +348,10 @@ def run_ours(args):
         "data": "synthetic (real FLAME topology, seeded bases, procedural 2048^2 texture, engine-rendered targets + noise, uint8 RGB like decoded frames)",
         "config": {"workload": wl,
                    "global_batch": gB, "image": [H, W], "tex": T, "foreground_fraction": fg,
-                   "parallelism": (f"dp{world}: one global parameter set, every rank optimises its own {B} distinct frames per step; one all-gather (forward slab) "
-                                   f"+ the gradient reduction (texture + parameter slab) per step") if world > 1 else "single GPU",
+                   "parallelism": (f"dp{world}: one global parameter set, every rank optimises its own {B} distinct frames per step; per step one all-gather (forward "
+                                   f"slab), one all-reduce (parameter-gradient slab) and the texture update ("
+                                   + ("reduce-scatter of the folded texel gradient by row band -> Adam on 1/N of the texture per rank -> all-gather of the updated rows"
+                                      if args.dp_texture == "shard" else "dense all-reduce of the texel gradient, full-texture Adam on every rank") + ")") if world > 1 else "single GPU",
                    "launch": ("CUDA graph replay (1 graph launch per step" + (", texture update of step k pipelined into the graph of step k+1; the "
                               "timed region holds exactly K complete steps' worth of work: K replays, each = previous step's texture update + this step's "
                               "everything else)" if not args.no_pipeline else ")")) if not args.no_graph else "eager (one launch per kernel)",
@@ -461,6 +463,8 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the other single-GPU workloads (extra_configs)")
+    ap.add_argument("--dp-texture", default="shard", choices=["shard", "allreduce"],
+                    help="data-parallel texture update: reduce-scatter -> 1/N Adam -> all-gather (default) or the round-1 dense all-reduce")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="do not defer the texture update into the next step's graph")
     args = ap.parse_args()

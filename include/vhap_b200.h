@@ -198,6 +198,18 @@ int vhap_tex_reg_fold_adam(vhap_ctx* ctx, float* tex_extra, float* g_out, float*
 /* data parallel: Adam + pyramid rebuild from the dense gradient produced by vhap_tex_reg_fold_adam(g_out) and summed across ranks */
 int vhap_tex_apply_grad(vhap_ctx* ctx, float* tex_extra, const float* g_dense, float* adam_m, float* adam_v, float lr, int32_t step,
                         const vhap_stage_cfg* cfg, void* stream);
+/* ---- sharded texture update (data parallel; the reference has no multi-GPU path): per step
+ *   vhap_tex_fold_grad_rm  photometric part of the texel gradient, dense, ROW-MAJOR g_rm[(y*3 + c)*T + x] so that a row band is contiguous
+ *   (caller)               reduce-scatter of g_rm by row band over the ranks
+ *   vhap_tex_band_adam     rows [y_begin, y_end) of this rank: + TV / residual gradients (rank-invariant: computed once, by the owner), Adam
+ *                          on this band's rows of tex_extra / adam_m / adam_v only, updated rows also to ex_band_out[((y-y_begin)*3+c)*T+x]
+ *   (caller)               all-gather of the bands into ex_rm[(y*3 + c)*T + x]
+ *   vhap_tex_rebuild_rm    planar tex_extra + level 0 / 1 + mips of the new pyramid from ex_rm (get_albedo, tracker.py:247-258)
+ * y_begin and the band height must be multiples of 8. */
+int vhap_tex_fold_grad_rm(vhap_ctx* ctx, float* tex_extra, float* g_rm, void* stream);
+int vhap_tex_band_adam(vhap_ctx* ctx, float* tex_extra, const float* g_band, int32_t y_begin, int32_t y_end, float* adam_m, float* adam_v,
+                       float lr, int32_t step, const vhap_stage_cfg* cfg, float* ex_band_out, void* stream);
+int vhap_tex_rebuild_rm(vhap_ctx* ctx, float* tex_extra, const float* ex_rm, void* stream);
 /* on != 0: g_out of vhap_tex_reg_fold_adam is a persistent buffer only read after the call returns -> the fold may overlap the
  * geometry backward on the library's aux stream */
 int vhap_set_tex_grad_persistent(vhap_ctx* ctx, int32_t on);

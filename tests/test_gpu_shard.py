@@ -1,0 +1,86 @@
+"""Sharded (data-parallel) texture update: fold -> reduce-scatter by row band -> band owner's regularisers + Adam -> all-gather ->
+pyramid rebuild.  (1) On one GPU, with a LocalShardComm that owns all `world` bands, the result must equal the fused single-GPU update
+(same texture, same Adam state, same pyramid seen by the next forward).  (2) With two GPUs (skipped otherwise) tools/dp_parity.py runs
+the real thing under torchrun: data parallel over NCCL == one process on the union of the frames."""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from tests.scene import make_scene
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.mark.parametrize("world", [1, 4])
+def test_sharded_update_equals_fused(world):
+    from vhap_b200.engine import Engine
+    from vhap_b200.parallel import LocalShardComm
+    sc = make_scene(B=2, H=96, W=96, T=256, n_t=3, timesteps=[1, 2])
+    e = Engine(sc["m"], sc["cfg"], 3, tex_painted=sc["tex_painted"])
+    try:
+        batch = e.stage_sample(sc["rgb16"].to(torch.float32), sc["lmk2d"], sc["ts"])
+        res = []
+        for mode in ("fused", "shard"):
+            e.load_params(sc["params"])
+            e.set_stage("rgb_global_tracking")
+            e.inject_random(sc["w_fg"], sc["w_bg"], sc["u_rand"])
+            comm = LocalShardComm(world) if mode == "shard" else None
+            for it in range(2):                         # two steps: both pyramid parities, Adam moments carried over
+                e.zero_grad()
+                e.energy(batch, backward=True, training=True)
+                e.adam_step(tex_comm=comm)
+                loss = e.loss_dict()                    # complete after the texture update (TV / residual of the texture this step used)
+                e.global_step += 1
+                if it == 0:
+                    first = dict(loss)
+            after = e.energy(batch, backward=False, training=True).clone().cpu().numpy()      # forward through the rebuilt pyramid
+            torch.cuda.synchronize()
+            res.append(dict(tex=e.tex_extra.clone().cpu().numpy(), m=e.tex_m.clone().cpu().numpy(), v=e.tex_v.clone().cpu().numpy(), after=after,
+                            first=first))
+        # the photometric texel gradients come from float atomics (order differs run to run): Adam's first steps are ~ lr * sign(g), so
+        # compare in units of the learning rate; a wrong band / layout / regulariser share changes whole rows by O(lr)
+        lr = 5e-3
+        d = np.abs(res[1]["tex"] - res[0]["tex"])
+        assert np.quantile(d, 0.999) < 1e-3 * lr and (d > 0.1 * lr).mean() < 1e-4, (np.quantile(d, 0.999) / lr, (d > 0.1 * lr).mean())
+        assert rel(res[1]["m"], res[0]["m"]) < 1e-3 and rel(res[1]["v"], res[0]["v"]) < 1e-3
+        for k in ("reg_tex_tv", "reg_tex_res_clusters", "photo", "total"):
+            assert abs(res[1]["first"][k] - res[0]["first"][k]) <= 1e-5 * max(abs(res[0]["first"][k]), 1e-6), (k, res[1]["first"][k], res[0]["first"][k])
+        assert abs(res[1]["after"][0] - res[0]["after"][0]) < 1e-4 * abs(res[0]["after"][0])
+    finally:
+        e.close()
+
+
+def test_band_adam_rejects_bad_bands():
+    from vhap_b200.engine import Engine
+    sc = make_scene(B=1, H=32, W=32, T=64, n_t=2, timesteps=[0])
+    e = Engine(sc["m"], sc["cfg"], 2, tex_painted=sc["tex_painted"])
+    try:
+        e.set_stage("rgb_global_tracking")
+        cs = e._c_stage(True)
+        import ctypes as C
+        g = torch.zeros(3 * 64 * 64, device=e.dev)
+        r = e.L.vhap_tex_band_adam(e.ctx, e.tex_extra.data_ptr(), g.data_ptr(), 4, 36, e.tex_m.data_ptr(), e.tex_v.data_ptr(), 1e-3, 1, C.byref(cs), None, e._stream())
+        assert r != 0
+    finally:
+        e.close()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("texture", ["shard", "allreduce"])
+def test_two_gpu_data_parallel_equals_single_process(texture):
+    env = dict(os.environ, VHAP_DP_TEXTURE=texture)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29611",
+                          str(ROOT / "tools" / "dp_parity.py")], capture_output=True, text=True, timeout=600, env=env, cwd=str(ROOT))
+    print(out.stdout[-3000:], out.stderr[-3000:])
+    assert out.returncode == 0 and "DP_PARITY_OK" in out.stdout

@@ -4,7 +4,7 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 rm -f gpurun_out/parity_r02.jsonl
 timeout 1500 python -m pytest tests -m gpu -q -p no:cacheprovider -x --deselect tests/test_gpu_bench_configs.py --deselect tests/test_gpu_dropin_tracker.py > gpurun_out/r2_pytest_old.log 2>&1
-timeout 1500 python -m pytest tests/test_gpu_bench_configs.py tests/test_gpu_dropin_tracker.py tests/test_gpu_staging.py -q -p no:cacheprovider > gpurun_out/r2_pytest_new.log 2>&1
+timeout 1500 python -m pytest tests/test_gpu_bench_configs.py tests/test_gpu_dropin_tracker.py tests/test_gpu_staging.py tests/test_gpu_shard.py -q -p no:cacheprovider > gpurun_out/r2_pytest_new.log 2>&1
 timeout 900 python bench.py --steps 30 --warmup 5 > gpurun_out/r2_bench.json 2> gpurun_out/r2_bench.err
 ab() { timeout 300 env $2 python bench.py --steps 40 --warmup 5 --no-cpu --no-extra 2>>gpurun_out/r2_ab.err | tail -1 | python -c "
 import sys,json

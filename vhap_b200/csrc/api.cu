@@ -559,6 +559,28 @@ extern "C" int vhap_tex_apply_grad(vhap_ctx* ctx, float* tex_extra, const float*
   LAST();
   return 0;
 }
+// ---- sharded texture update for data-parallel runs (texture.cu "sharded texture update"): the three compute pieces around the caller's
+// reduce-scatter / all-gather.  All run on the stream they are given (no internal fork).
+extern "C" int vhap_tex_fold_grad_rm(vhap_ctx* ctx, float* tex_extra, float* g_rm, void* stream) {
+  ctx->tex_fork_pending = 0;
+  if (ctx->tex_fold_v1) { vh_set_error(ctx, "vhap_tex_fold_grad_rm", "needs the v2 fold kernel"); return -3; }
+  launch_tex_fold_grad_rm(ctx, tex_extra, g_rm, (cudaStream_t)stream);
+  LAST();
+  return 0;
+}
+extern "C" int vhap_tex_band_adam(vhap_ctx* ctx, float* tex_extra, const float* g_band, int32_t y_begin, int32_t y_end, float* adam_m, float* adam_v,
+                                  float lr, int32_t step, const vhap_stage_cfg* cfg, float* ex_band_out, void* stream) {
+  if (launch_tex_band_adam(ctx, tex_extra, g_band, y_begin, y_end, adam_m, adam_v, lr, step, cfg, ex_band_out, (cudaStream_t)stream)) {
+    vh_set_error(ctx, "vhap_tex_band_adam", "row band must be a non-empty multiple of 8 rows inside the texture"); return -3;
+  }
+  LAST();
+  return 0;
+}
+extern "C" int vhap_tex_rebuild_rm(vhap_ctx* ctx, float* tex_extra, const float* ex_rm, void* stream) {
+  launch_tex_rebuild_rm(ctx, tex_extra, ex_rm, (cudaStream_t)stream);
+  LAST();
+  return 0;
+}
 // Deferred texture update (the update of step k runs at the start of step k+1, beside FLAME / rasteriser / pools, and is joined right
 // before the shading pass): cancel the in-call fork of the next vhap_tex_reg_fold_adam (it then runs on the stream it is given) and
 // bias the device Adam step it reads (-1: the counter was already advanced).  bias 0 restores the normal behaviour.

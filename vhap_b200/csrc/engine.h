@@ -144,4 +144,8 @@ void launch_render_backward(vhap_ctx* c, PassArgs& P, const vhap_stage_cfg* cfg,
 void launch_tex_rebuild(vhap_ctx* c, const float* tex_extra, cudaStream_t s);
 void launch_tex_fold(vhap_ctx* c, float* tex_extra, float* g_out, float* m, float* v, float lr, int step, const vhap_stage_cfg* cfg,
                      float* losses_out, cudaStream_t s);
+void launch_tex_fold_grad_rm(vhap_ctx* c, float* tex_extra, float* g_rm, cudaStream_t s);
+int launch_tex_band_adam(vhap_ctx* c, float* tex_extra, const float* g_band, int y_begin, int y_end, float* m, float* v, float lr, int step,
+                         const vhap_stage_cfg* cfg, float* ex_band_out, cudaStream_t s);
+void launch_tex_rebuild_rm(vhap_ctx* c, float* tex_extra, const float* ex_rm, cudaStream_t s);
 void launch_adam(vhap_ctx* c, float* p, const float* g, float* m, float* v, int64_t n, float lr, int step, cudaStream_t s);

@@ -84,6 +84,12 @@ struct TexFoldArgs {
   const int* step_ptr;          // device Adam step (CUDA-graph replay) or NULL
   const float* lr_scale_ptr;    // device learning-rate scale, read together with step_ptr
   int step_bias;                // added to *step_ptr (deferred update of the previous step: -1)
+  // ---- sharded (data-parallel) texture update, k_tex_fold2 only
+  int y_begin, y_end;           // rows handled by this launch (a row band; whole texture: 0, T)
+  int rm;                       // row-major exchange layout: g_out[(y*3 + c)*T + x] over the whole texture (the reduce-scatter input, a rank's band is
+                                // contiguous), g_in[((y - y_begin)*3 + c)*T + x] over the band (the reduce-scatter output)
+  float* ex_band_out;           // optional: updated tex_extra of the band, row-major band-local (the all-gather input)
+  int no_pyramid;               // do not write level 0 / 1 of the new pyramid (the band owner only updates tex_extra; vhap_tex_rebuild_rm rebuilds)
 };
 
 __device__ __forceinline__ float chan(const f4& t, int c) { return c == 0 ? t.x : (c == 1 ? t.y : t.z); }
@@ -252,7 +258,10 @@ __device__ __forceinline__ void row_load(const TexFoldArgs& a, int x, int y, boo
   const size_t n = (size_t)a.T * a.T, i = (size_t)y * a.T + x;
   r.t = a.tex_old[i];
   r.g[0] = r.g[1] = r.g[2] = 0.f;
-  if (a.g_in) { r.g[0] = a.g_in[i]; r.g[1] = a.g_in[n + i]; r.g[2] = a.g_in[2 * n + i]; }
+  if (a.g_in) {
+    if (a.rm) { const float* gi = a.g_in + ((size_t)(y - a.y_begin) * 3) * a.T + x; r.g[0] = gi[0]; r.g[1] = gi[a.T]; r.g[2] = gi[2 * (size_t)a.T]; }
+    else { r.g[0] = a.g_in[i]; r.g[1] = a.g_in[n + i]; r.g[2] = a.g_in[2 * n + i]; }
+  }
   else if (l0) { float4 g0 = *(const float4*)(a.g_pyr + i * 4); r.g[0] = g0.x; r.g[1] = g0.y; r.g[2] = g0.z; }
 #pragma unroll
   for (int c = 0; c < 3; ++c) { r.ex[c] = a.extra[c * n + i]; if (a.do_adam) { r.m[c] = a.m[c * n + i]; r.v[c] = a.v[c * n + i]; } }
@@ -267,7 +276,7 @@ __global__ void __launch_bounds__(256, TF_MINB) k_tex_fold2(TexFoldArgs a, float
   __shared__ bool is_last;
   const int T = a.T, tw = T < 256 ? T : 256, tpr = T / tw, R = T < TF_ROWS ? T : TF_ROWS;
   const int tid = threadIdx.x, lane = tid & 31;
-  const int x0 = (blockIdx.x % tpr) * tw, x = x0 + tid, y0 = (blockIdx.x / tpr) * R;
+  const int x0 = (blockIdx.x % tpr) * tw, x = x0 + tid, y0 = a.y_begin + (blockIdx.x / tpr) * R;     // (y_begin is a multiple of R: host check)
   const int n1x = tw >> 1, n1y = R >> 1, n2x = tw >> 2 ? tw >> 2 : 1, n2y = R >> 2 ? R >> 2 : 1, n3x = tw >> 3 ? tw >> 3 : 1, n3y = R >> 3 ? R >> 3 : 1;
   const bool fold = a.g_pyr != nullptr && a.g_in == nullptr;
   // ---- hierarchical fold of the coarse gradient levels (box-filter adjoint: 1/4 per level)
@@ -362,7 +371,10 @@ __global__ void __launch_bounds__(256, TF_MINB) k_tex_fold2(TexFoldArgs a, float
 #pragma unroll
         for (int c = 0; c < 3; ++c) { acc[1] += a.w_res * cur.ex[c] * cur.ex[c]; g[c] += 2.f * a.w_res * cur.ex[c]; }
       }
-      if (a.g_out) { a.g_out[i] = g[0]; a.g_out[n + i] = g[1]; a.g_out[2 * n + i] = g[2]; }
+      if (a.g_out) {
+        if (a.rm) { float* go = a.g_out + ((size_t)y * 3) * T + x; go[0] = g[0]; go[T] = g[1]; go[2 * (size_t)T] = g[2]; }
+        else { a.g_out[i] = g[0]; a.g_out[n + i] = g[1]; a.g_out[2 * n + i] = g[2]; }
+      }
       o = t;
       if (a.do_adam) {
 #pragma unroll
@@ -374,10 +386,11 @@ __global__ void __launch_bounds__(256, TF_MINB) k_tex_fold2(TexFoldArgs a, float
           float upd = (a.lr / bc1) * m / (sqrtf(v) / bc2s + 1e-8f);
           float ne = cur.ex[c] - upd;
           a.extra[k] = ne;
+          if (a.ex_band_out) a.ex_band_out[((size_t)(y - a.y_begin) * 3 + c) * T + x] = ne;
           float base = chan(t, c) - cur.ex[c];                                        // painted part
           if (c == 0) o.x = base + ne; else if (c == 1) o.y = base + ne; else o.z = base + ne;
         }
-        a.tex_new[i] = o;
+        if (!a.no_pyramid) a.tex_new[i] = o;
       }
     }
     // level 1 of the new pyramid on odd rows: avg4(A[2y][2x], A[2y+1][2x], A[2y][2x+1], A[2y+1][2x+1]), same order as k_mip_down
@@ -386,7 +399,7 @@ __global__ void __launch_bounds__(256, TF_MINB) k_tex_fold2(TexFoldArgs a, float
       c.x = __shfl_down_sync(0xffffffffu, o_prev.x, 1); c.y = __shfl_down_sync(0xffffffffu, o_prev.y, 1); c.z = __shfl_down_sync(0xffffffffu, o_prev.z, 1);
       d.x = __shfl_down_sync(0xffffffffu, o.x, 1); d.y = __shfl_down_sync(0xffffffffu, o.y, 1); d.z = __shfl_down_sync(0xffffffffu, o.z, 1);
       c.w = d.w = 0.f;
-      if (on && a.do_adam && a.max_level >= 1 && !(tid & 1))
+      if (on && a.do_adam && !a.no_pyramid && a.max_level >= 1 && !(tid & 1))
         a.tex_new[(size_t)a.mip_off[1] + (size_t)(y >> 1) * (T >> 1) + (x >> 1)] = avg4(o_prev, o, c, d);
     }
     o_prev = o;
@@ -500,6 +513,7 @@ void launch_tex_fold(vhap_ctx* c, float* tex_extra, float* g_out, float* m, floa
   if (a.g_in) { a.w_tv = 0.f; a.w_res = 0.f; }
   a.do_adam = (m != nullptr && v != nullptr) ? 1 : 0;
   a.lr = lr; a.bc1 = 1.f - powf(0.9f, (float)step); a.bc2_sqrt = sqrtf(1.f - powf(0.999f, (float)step));
+  a.y_begin = 0; a.y_end = T;
   int tw = T < 256 ? T : 256, nblk = (T / tw) * (T / 2), L = c->max_level >= 1 ? 1 : 0;
   if (c->tex_fold_v1) {
     LAUNCH(c, KID_TEX_FOLD, s, k_tex_fold<<<nblk, 256, 0, s>>>(a, c->tv_partials, c->tex_counter, a.g_in ? c->tex_loss + 2 : c->tex_loss));      // apply mode: scratch slots
@@ -516,6 +530,79 @@ void launch_tex_fold(vhap_ctx* c, float* tex_extra, float* g_out, float* m, floa
   if (c->g_tex && c->max_level >= 1)                                      // coarser gradient levels
     cudaMemsetAsync(c->g_tex + (size_t)c->mip_off[1] * 4, 0, (c->mip_total - c->mip_off[1]) * 4 * sizeof(float), s);
   if (a.do_adam) { c->cur_mip ^= 1; build_mips(c, c->mips[c->cur_mip], s, L); }    // levels 1..L were written by the fold kernel
+}
+
+// ---------------------------------------------------------------------------------------------- sharded texture update (data parallel)
+// Per step and rank: (1) photometric fold of the local texel-gradient pyramid into a dense row-major gradient (vhap_tex_fold_grad_rm);
+// (2) reduce-scatter by row band (NCCL, caller); (3) the band owner adds the total-variation / residual gradients -- rank-invariant, so
+// computed ONCE, by the owner, at full weight -- and runs Adam on its T/N rows only (vhap_tex_band_adam: Adam state traffic / N);
+// (4) all-gather of the updated bands (NCCL, caller); (5) every rank rebuilds level 0 / 1 + mips from the gathered texture
+// (vhap_tex_rebuild_rm).  Replaces fold(+regularisers) -> 50 MB all-reduce -> full-texture Adam on every rank.
+static void fill_fold_args(vhap_ctx* c, TexFoldArgs& a, float* tex_extra) {
+  memset(&a, 0, sizeof(a));
+  a.T = c->T; a.max_level = c->max_level;
+  for (int i = 0; i < VH_MAX_MIPS; ++i) a.mip_off[i] = c->mip_off[i];
+  a.tex_old = c->mips[c->cur_mip]; a.tex_new = c->mips[c->cur_mip ^ 1]; a.g_pyr = c->g_tex;
+  a.extra = tex_extra; a.mask = c->uvmask_res; a.l0_flag = c->tex_l0_flag;
+  a.step_ptr = c->use_dev_step ? c->dev_step : nullptr; a.lr_scale_ptr = c->dev_lr_scale; a.step_bias = c->tex_step_bias;
+  a.y_begin = 0; a.y_end = c->T;
+}
+static int fold_grid(const vhap_ctx* c, int rows) { int T = c->T, tw = T < 256 ? T : 256, R = T < TF_ROWS ? T : TF_ROWS; return (T / tw) * (rows / R); }
+
+void launch_tex_fold_grad_rm(vhap_ctx* c, float* tex_extra, float* g_rm, cudaStream_t s) {
+  TexFoldArgs a; fill_fold_args(c, a, tex_extra);
+  a.g_out = g_rm; a.rm = 1; a.do_adam = 0; a.w_tv = 0.f; a.w_res = 0.f; a.mask = nullptr;
+  LAUNCH(c, KID_TEX_FOLD, s, k_tex_fold2<<<fold_grid(c, c->T), 256, 0, s>>>(a, c->tv_partials, c->tex_counter, c->tex_loss + 2));
+  cudaMemsetAsync(c->tex_l0_flag, 0, sizeof(int), s);
+  if (c->g_tex && c->max_level >= 1)
+    cudaMemsetAsync(c->g_tex + (size_t)c->mip_off[1] * 4, 0, (c->mip_total - c->mip_off[1]) * 4 * sizeof(float), s);
+}
+
+int launch_tex_band_adam(vhap_ctx* c, float* tex_extra, const float* g_band, int y_begin, int y_end, float* m, float* v, float lr, int step,
+                         const vhap_stage_cfg* cfg, float* ex_band_out, cudaStream_t s) {
+  int T = c->T, R = T < TF_ROWS ? T : TF_ROWS;
+  if (y_begin < 0 || y_end > T || y_begin >= y_end || (y_begin % R) || ((y_end - y_begin) % R)) return -1;
+  TexFoldArgs a; fill_fold_args(c, a, tex_extra);
+  a.g_pyr = nullptr; a.g_in = g_band; a.rm = 1; a.y_begin = y_begin; a.y_end = y_end; a.m = m; a.v = v; a.do_adam = 1; a.ex_band_out = ex_band_out; a.no_pyramid = 1;
+  // the regularisers are rank-invariant: the band owner computes them, at full weight (no 1/world share)
+  a.w_tv = (cfg->training && cfg->opt_texture && cfg->w_reg_tex_tv >= 0.f) ? cfg->w_reg_tex_tv / (3.f * (float)(T - 1) * (float)T) : 0.f;
+  a.w_res = (cfg->training && cfg->opt_texture && cfg->w_reg_tex_res >= 0.f) ? cfg->w_reg_tex_res / (3.f * (float)T * (float)T) : 0.f;
+  a.lr = lr; a.bc1 = 1.f - powf(0.9f, (float)step); a.bc2_sqrt = sqrtf(1.f - powf(0.999f, (float)step));
+  LAUNCH(c, KID_TEX_FOLD, s, k_tex_fold2<<<fold_grid(c, y_end - y_begin), 256, 0, s>>>(a, c->tv_partials, c->tex_counter, c->tex_loss + 2));
+  return 0;
+}
+
+// level 0 (painted + extra) and level 1 of the OTHER pyramid from the gathered row-major texture, planar tex_extra refreshed on the way
+__global__ void __launch_bounds__(256) k_tex_rebuild_rm(const float* __restrict__ ex_rm, const float* __restrict__ painted, int T, float* __restrict__ extra,
+                                                        f4* __restrict__ lvl0, f4* __restrict__ lvl1, int has_l1) {
+  const int tw = T < 256 ? T : 256, tpr = T / tw, tid = threadIdx.x;
+  const int x = (blockIdx.x % tpr) * tw + tid, y = (blockIdx.x / tpr) * 2;
+  const size_t n = (size_t)T * T;
+  f4 o[2] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+  if (tid < tw) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const size_t i = (size_t)(y + r) * T + x;
+      const float* e = ex_rm + ((size_t)(y + r) * 3) * T + x;
+      float e0 = e[0], e1 = e[T], e2 = e[2 * (size_t)T];
+      extra[i] = e0; extra[n + i] = e1; extra[2 * n + i] = e2;
+      o[r].x = (painted ? painted[i] : 0.f) + e0; o[r].y = (painted ? painted[n + i] : 0.f) + e1; o[r].z = (painted ? painted[2 * n + i] : 0.f) + e2;
+      lvl0[i] = o[r];
+    }
+  }
+  f4 c, d;
+  c.x = __shfl_down_sync(0xffffffffu, o[0].x, 1); c.y = __shfl_down_sync(0xffffffffu, o[0].y, 1); c.z = __shfl_down_sync(0xffffffffu, o[0].z, 1);
+  d.x = __shfl_down_sync(0xffffffffu, o[1].x, 1); d.y = __shfl_down_sync(0xffffffffu, o[1].y, 1); d.z = __shfl_down_sync(0xffffffffu, o[1].z, 1);
+  c.w = d.w = 0.f;
+  if (tid < tw && has_l1 && !(tid & 1)) lvl1[(size_t)(y >> 1) * (T >> 1) + (x >> 1)] = avg4(o[0], o[1], c, d);
+}
+void launch_tex_rebuild_rm(vhap_ctx* c, float* tex_extra, const float* ex_rm, cudaStream_t s) {
+  int T = c->T, tw = T < 256 ? T : 256;
+  f4* pyr = c->mips[c->cur_mip ^ 1];
+  int has_l1 = c->max_level >= 1;
+  LAUNCH(c, KID_TEX_L0, s, k_tex_rebuild_rm<<<(T / tw) * (T / 2), 256, 0, s>>>(ex_rm, c->tex_painted, T, tex_extra, pyr, pyr + c->mip_off[has_l1 ? 1 : 0], has_l1));
+  c->cur_mip ^= 1;
+  build_mips(c, c->mips[c->cur_mip], s, has_l1);
 }
 
 __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,

@@ -397,15 +397,44 @@ class Engine:
         from .config import _LR_OF                                           # tracker.py:159-211 (pinned: tests/test_config_golden.py)
         return getattr(self.cfg.lr, _LR_OF.get(name, "base")) * self._host_lr_scale()
 
-    def tex_update(self, allreduce_fn=None, deferred=False, reg_loss=True):
+    def _shard_bufs(self, comm):
+        """exchange buffers of the sharded texture update (row-major [T,3,T] so that a rank's row band is one contiguous chunk)"""
+        key = (comm.world, tuple(comm.owned()))
+        if getattr(self, "_shard_key", None) != key:
+            if self.T % (comm.world * 8):
+                raise ValueError(f"sharded texture update: texture size {self.T} must be a multiple of 8 * world ({comm.world})")
+            nt, nb = 3 * self.T * self.T, 3 * self.T * self.T // comm.world
+            z = lambda n: torch.zeros(n, dtype=torch.float32, device=self.dev)
+            self._shard = dict(g_rm=z(nt), ex_rm=z(nt), g={i: z(nb) for i in comm.owned()}, ex={i: z(nb) for i in comm.owned()})
+            self._shard_key = key
+        return self._shard
+
+    def tex_update(self, allreduce_fn=None, deferred=False, reg_loss=True, tex_comm=None):
         """Texture part of the Adam step on the CURRENT stream.  deferred=True: the update of the PREVIOUS step, executed at the start
         of the next one (pipelined graph replay): no in-call fork, device Adam step - 1, no loss bookkeeping of the finished step, and
-        the regulariser loss values of the updated texture are produced for the step that is about to run."""
+        the regulariser loss values of the updated texture are produced for the step that is about to run.
+        tex_comm (data parallel, parallel.TexShardComm): the SHARDED update -- photometric fold -> reduce-scatter by row band -> the band
+        owner adds TV / residual gradients and runs Adam on its T/world rows -> all-gather of the updated rows -> pyramid rebuild;
+        allreduce_fn without tex_comm: the round-1 path (fold + regularisers -> dense all-reduce -> full-texture Adam on every rank)."""
         cs = self._c_stage(True)
         s = self._stream()
         if deferred:
             self.L.vhap_tex_defer(self.ctx, -1)
-        if allreduce_fn is None:
+        if tex_comm is not None:
+            sh = self._shard_bufs(tex_comm)
+            if not deferred:
+                # loss values of the texture regularisers for the texture this step rendered with (the fused path gets them from its fold)
+                self._ck(self.L.vhap_tex_reg_loss(self.ctx, self.tex_extra.data_ptr(), C.byref(cs), s))
+                self._ck(self.L.vhap_assemble_losses(self.ctx, C.byref(cs), self.losses.data_ptr(), s))
+            self._ck(self.L.vhap_tex_fold_grad_rm(self.ctx, self.tex_extra.data_ptr(), sh["g_rm"].data_ptr(), s))
+            tex_comm.reduce_scatter(sh["g_rm"], sh["g"])
+            rows = self.T // tex_comm.world
+            for i in tex_comm.owned():
+                self._ck(self.L.vhap_tex_band_adam(self.ctx, self.tex_extra.data_ptr(), sh["g"][i].data_ptr(), i * rows, (i + 1) * rows, self.tex_m.data_ptr(),
+                                                   self.tex_v.data_ptr(), self._lr("tex"), self.step_count, C.byref(cs), sh["ex"][i].data_ptr(), s))
+            tex_comm.all_gather(sh["ex_rm"], sh["ex"])
+            self._ck(self.L.vhap_tex_rebuild_rm(self.ctx, self.tex_extra.data_ptr(), sh["ex_rm"].data_ptr(), s))
+        elif allreduce_fn is None:
             # fused: fold + regularisers + Adam + pyramid; eagerly it runs on an aux stream right behind the fused backward
             # (vhap_tex_reg_fold_adam waits only for the texel-gradient event), the call itself only joins
             self._ck(self.L.vhap_tex_reg_fold_adam(self.ctx, self.tex_extra.data_ptr(), None, self.tex_m.data_ptr(), self.tex_v.data_ptr(),
@@ -424,7 +453,7 @@ class Engine:
                 self._ck(self.L.vhap_tex_reg_loss(self.ctx, self.tex_extra.data_ptr(), C.byref(cs), s), None)
             self.L.vhap_tex_defer(self.ctx, 0)
 
-    def adam_step(self, allreduce_fn=None, texture=True):
+    def adam_step(self, allreduce_fn=None, texture=True, tex_comm=None):
         """torch.optim.Adam.step() over the parameter groups of the current stage (dense rows, tracker.py:1284-1293,210)."""
         opt = opt_dict_for(self.stage)
         self.step_count += 1
@@ -435,9 +464,10 @@ class Engine:
         groups = [n for n in ("shape", "static_offset", "lights", "focal_length", "expr", "rotation", "translation", "neck_pose", "jaw_pose", "eyes_pose")
                   if n in lrs]
         tex = texture and opt["texture"]
-        if tex and allreduce_fn is not None:
-            self.tex_update(allreduce_fn)
-        if allreduce_fn is not None and not (tex and self._dp_buf is not None):
+        dp = allreduce_fn is not None or tex_comm is not None
+        if tex and dp:
+            self.tex_update(allreduce_fn, tex_comm=tex_comm)
+        if allreduce_fn is not None and not (tex and tex_comm is None and self._dp_buf is not None):
             allreduce_fn(self.grad)
         if groups:
             off = np.asarray([self.layout[g][0] for g in groups], np.int64)
@@ -446,7 +476,7 @@ class Engine:
             hp = lambda a: a.ctypes.data_as(C.c_void_p)
             self._ck(self.L.vhap_adam_multi(self.ctx, self.slab.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                                             len(groups), hp(off), hp(ln), hp(lr), self.step_count, s), None)
-        if tex and allreduce_fn is None:
+        if tex and not dp:
             self.tex_update(None)                          # issued last: only its join and the loss bookkeeping are on this stream
 
     def step(self, batch: Batch) -> torch.Tensor:
@@ -470,7 +500,7 @@ class Engine:
                 on_step(i, losses)
 
     # ------------------------------------------------------------------ CUDA-graph replay of whole steps
-    def graph_begin(self, batches, body=None, reduce_fn=None, allreduce_fn=None, world=1, pipelined=True, global_Bs=None):
+    def graph_begin(self, batches, body=None, reduce_fn=None, allreduce_fn=None, world=1, pipelined=True, global_Bs=None, tex_comm=None):
         """Capture one optimisation step per (batch, texture ping-pong parity) as CUDA graphs.  All step-dependent values
         (Adam step, RNG step) live in device memory (vhap_step_counters), so the graphs are replayable indefinitely.
         Data parallel: pass reduce_fn / allreduce_fn / world (the NCCL collectives are captured); `body(batch)` overrides the captured
@@ -481,7 +511,9 @@ class Engine:
         stream and joins it right before the shading pass; the first graph_step runs an eager prologue, graph_end flushes the last
         update.  Same arithmetic in the same order on every buffer, only the schedule differs."""
         s = self._stream()
-        if allreduce_fn is not None and self.tex_grad_dense is None:
+        if tex_comm is not None:
+            self._shard_bufs(tex_comm)                        # allocations must not happen inside capture
+        elif allreduce_fn is not None and self.tex_grad_dense is None:
             self.texture_grad_dense(with_losses=False)       # one-time eager set-up (allocation, stream hand-over) must not happen inside capture
         self._ck(self.L.vhap_step_counters(self.ctx, 1, self.step_count + 1, self.global_step, s))
         self._graph_live = True
@@ -489,7 +521,7 @@ class Engine:
         torch.cuda.synchronize(self.dev)
         opt = opt_dict_for(self.stage)
         self._pipe = bool(pipelined and body is None and self.stage is not None and self.stage.photometric and opt["texture"])
-        self._hooks = (reduce_fn, allreduce_fn, world)
+        self._hooks = (reduce_fn, allreduce_fn, world, tex_comm)
         self._graph_batches = list(batches)
         # true global batch size per staged batch (uneven shards: not B * world); parallel.DataParallelStep passes the all-reduced values
         self._graph_gB = {id(b): (g if global_Bs is not None else b.B * world) for b, g in zip(self._graph_batches, global_Bs or [0] * len(self._graph_batches))}
@@ -520,7 +552,7 @@ class Engine:
     def _step_body(self, batch, deferred_tex: bool, texture_now: bool = False):
         """one step with device-resident counters: [texture update of the previous step on a side stream] + zero_grad + energy +
         backward + Adam of the small groups (+ the texture update right away when texture_now) + counter advance"""
-        reduce_fn, allreduce_fn, world = self._hooks
+        reduce_fn, allreduce_fn, world, tex_comm = self._hooks
         if deferred_tex:
             cur = torch.cuda.current_stream(self.dev)
             e0, e1 = torch.cuda.Event(), torch.cuda.Event()
@@ -529,7 +561,7 @@ class Engine:
             e2 = torch.cuda.Event()
             cs = self._c_stage(True)
             with torch.cuda.stream(self._tex_stream):
-                self.tex_update(allreduce_fn, deferred=True, reg_loss=False)
+                self.tex_update(allreduce_fn, deferred=True, reg_loss=False, tex_comm=tex_comm)
                 e1.record(self._tex_stream)               # the new pyramid is complete: what the shading pass waits for
                 # regulariser loss VALUES of the updated texture: only the loss vector needs them, joined at the end of the step
                 self._ck(self.L.vhap_tex_reg_loss(self.ctx, self.tex_extra.data_ptr(), C.byref(cs), self._stream()), None)
@@ -538,7 +570,7 @@ class Engine:
             self.L.vhap_set_render_wait_event(self.ctx, C.c_void_p(e1.cuda_event))    # joined right before the shading pass
         self.zero_grad()
         self.energy(batch, backward=True, training=True, global_B=self._graph_gB.get(id(batch), batch.B * world), reduce_fn=reduce_fn)
-        self.adam_step(allreduce_fn=allreduce_fn, texture=texture_now)
+        self.adam_step(allreduce_fn=allreduce_fn, texture=texture_now, tex_comm=tex_comm)
         if deferred_tex:
             torch.cuda.current_stream(self.dev).wait_event(e2)
             self._ck(self.L.vhap_assemble_losses(self.ctx, C.byref(cs), self.losses.data_ptr(), self._stream()), None)
@@ -563,7 +595,7 @@ class Engine:
         stream).  The next graph_step then starts the pipeline again with its eager prologue."""
         if getattr(self, "_pipe", False) and self._primed:
             self.L.vhap_set_cur_mip(self.ctx, self._parity)     # the replays did not touch the host-side ping-pong index
-            self.tex_update(self._hooks[1], deferred=True)
+            self.tex_update(self._hooks[1], deferred=True, tex_comm=self._hooks[3])
             self._parity ^= 1
             self._primed = False
 

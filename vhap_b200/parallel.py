@@ -55,13 +55,58 @@ def global_batch_size(local_B: int, device=None, group=None) -> int:
     return int(t.item())
 
 
+class TexShardComm:
+    """collectives of the sharded texture update (Engine.tex_update): rank r owns the rows [r T/world, (r+1) T/world) of the texture.
+    On its own communicator: the texture chain runs on a side stream beside the step's other collectives."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+
+    def owned(self):
+        return [self.rank]
+
+    def reduce_scatter(self, g_rm: torch.Tensor, bands: dict) -> None:
+        dist.reduce_scatter_tensor(bands[self.rank], g_rm, op=dist.ReduceOp.SUM, group=self.group)
+
+    def all_gather(self, ex_rm: torch.Tensor, bands: dict) -> None:
+        dist.all_gather_into_tensor(ex_rm, bands[self.rank], group=self.group)
+
+
+class LocalShardComm:
+    """the same interface inside ONE process that owns all `world` bands (sum over one rank = copy): exercises the band arithmetic of the
+    sharded update without a second GPU (tests)"""
+
+    def __init__(self, world: int):
+        self.world, self.rank, self.group = world, 0, None
+
+    def owned(self):
+        return list(range(self.world))
+
+    def reduce_scatter(self, g_rm, bands):
+        n = g_rm.numel() // self.world
+        for i, b in bands.items():
+            b.copy_(g_rm[i * n:(i + 1) * n])
+
+    def all_gather(self, ex_rm, bands):
+        n = ex_rm.numel() // self.world
+        for i, b in bands.items():
+            ex_rm[i * n:(i + 1) * n].copy_(b)
+
+
 class DataParallelStep:
     """Wraps an Engine: step(batch) = zero_grad, forward, slab reduce, backward, grad allreduce, Adam."""
 
-    def __init__(self, engine, group=None):
+    def __init__(self, engine, group=None, texture="shard"):
+        """texture: "shard" (default: reduce-scatter -> 1/world Adam -> all-gather, TexShardComm on its own communicator) or "allreduce"
+        (round-1 baseline: dense all-reduce of the regularised gradient, full-texture Adam on every rank)"""
         self.e, self.group = engine, group
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         self._gB = {}
+        self.tex_comm = None
+        if self.world > 1 and texture == "shard":
+            ranks = dist.get_process_group_ranks(group) if group is not None else None
+            self.tex_comm = TexShardComm(dist.new_group(ranks=ranks))
 
     def global_B(self, batch) -> int:
         """true global batch size of the step this batch belongs to (one host-side all-reduce per staged batch object, cached; must be
@@ -81,7 +126,7 @@ class DataParallelStep:
         gB = self.global_B(batch)
         red = (lambda a, b: reduce_forward_slab(a, b, self.group)) if self.world > 1 else None
         e.energy(batch, backward=True, training=True, global_B=gB, reduce_fn=red)
-        e.adam_step(allreduce_fn=(lambda t: allreduce_sum(t, self.group)) if self.world > 1 else None)
+        e.adam_step(allreduce_fn=(lambda t: allreduce_sum(t, self.group)) if self.world > 1 else None, tex_comm=self.tex_comm)
 
     def graph_begin(self, batches, pipelined=True):
         """Engine.graph_begin with this group's collectives captured into the step graphs (pipelined: the texture all-reduce of step k
@@ -89,7 +134,7 @@ class DataParallelStep:
         red = (lambda a, b: reduce_forward_slab(a, b, self.group)) if self.world > 1 else None
         allr = (lambda t: allreduce_sum(t, self.group)) if self.world > 1 else None
         gBs = [self.global_B(b) for b in batches]            # host-side collectives: before the capture
-        self.e.graph_begin(batches, reduce_fn=red, allreduce_fn=allr, world=self.world, pipelined=pipelined, global_Bs=gBs)
+        self.e.graph_begin(batches, reduce_fn=red, allreduce_fn=allr, world=self.world, pipelined=pipelined, global_Bs=gBs, tex_comm=self.tex_comm)
 
     def step(self, batch):
         e = self.e
@@ -97,6 +142,6 @@ class DataParallelStep:
         gB = self.global_B(batch)
         red = (lambda a, b: reduce_forward_slab(a, b, self.group)) if self.world > 1 else None
         losses = e.energy(batch, backward=True, training=True, global_B=gB, reduce_fn=red)
-        e.adam_step(allreduce_fn=(lambda t: allreduce_sum(t, self.group)) if self.world > 1 else None)
+        e.adam_step(allreduce_fn=(lambda t: allreduce_sum(t, self.group)) if self.world > 1 else None, tex_comm=self.tex_comm)
         e.global_step += 1
         return losses
