@@ -20,11 +20,11 @@ def fill_cam_params(params, B, H, W, RT=None):
     """tracker.py:141-157 (uncalibrated): K = [f,f,cx,cy], f = focal*max(h,w); RT = [I | (0,0,-1)] (:1335-1337)."""
     f = params["focal_length"] * max(H, W)
     dt = f.dtype
-    cx = torch.full((1,), 0.5 * W, dtype=dt)
-    cy = torch.full((1,), 0.5 * H, dtype=dt)
+    cx = torch.full((1,), 0.5 * W, dtype=dt, device=f.device)
+    cy = torch.full((1,), 0.5 * H, dtype=dt, device=f.device)
     K = torch.stack([f, f, cx, cy], dim=1).expand(B, -1)
     if RT is None:
-        RT = torch.eye(3, 4, dtype=dt)
+        RT = torch.eye(3, 4, dtype=dt, device=f.device)
         RT[2, 3] = -1
         RT = RT[None].expand(B, -1, -1)
     return K, RT
@@ -32,7 +32,7 @@ def fill_cam_params(params, B, H, W, RT=None):
 
 def lmk_energy(lmks, lmk2d, K, RT, img_size, always_enable_jawline=True, disable_jawline=False):
     """tracker.py:347-389.  lmks [B,70,3]; lmk2d [B,68,3] (x_px, y_px, confidence)."""
-    gt = lmk2d.clone().to(lmks.dtype)
+    gt = lmk2d.clone().to(device=lmks.device, dtype=lmks.dtype)
     xy, conf = gt[:, :, :2], gt[:, :, 2]
     u, v = C.normalize_image_points(xy[:, :, 0], xy[:, :, 1], img_size)
     gt2 = torch.stack([u, v], -1)
@@ -70,9 +70,9 @@ def laplacian_dense(model_data, dtype):
     return Lm
 
 
-def scale_vertex_weights_by_region(model_data, V, scale, regions, dtype):
+def scale_vertex_weights_by_region(model_data, V, scale, regions, dtype, device="cpu"):
     """tracker.py:607-614 with blur_iter = 0."""
-    w = torch.ones(V, 1, dtype=dtype)
+    w = torch.ones(V, 1, dtype=dtype, device=device)
     w[torch.as_tensor(model_data.get_vid_by_region(list(regions)))] *= scale
     return w
 
@@ -120,10 +120,10 @@ def regularization_energy(params, ts, stage, cfg, model_data, verts_cano=None, d
             T = params["tex_extra"].shape[-1]
             if m.shape[-1] != T:
                 m = m[:: m.shape[0] // T, :: m.shape[1] // T]
-            log["reg_tex_res_clusters"] = w.reg_tex_res_clusters * (params["tex_extra"] ** 2 * m[None].to(dt)).mean()
+            log["reg_tex_res_clusters"] = w.reg_tex_res_clusters * (params["tex_extra"] ** 2 * m[None].to(params["tex_extra"])).mean()
     if opt["lights"]:
         if w.reg_light is not None:
-            lu = torch.zeros(9, 3, dtype=dt)
+            lu = torch.zeros(9, 3, dtype=dt, device=params["lights"].device)
             lu[0] = np.sqrt(4 * np.pi)
             log["reg_light"] = w.reg_light * ((params["lights"] - lu) ** 2).mean()
         if w.reg_diffuse is not None and diffuse_detach_normal is not None:
@@ -133,17 +133,17 @@ def regularization_energy(params, ts, stage, cfg, model_data, verts_cano=None, d
         offset = params["static_offset"]
         V = offset.shape[1]
         if w.reg_offset_lap is not None:
-            Lm = lap if lap is not None else laplacian_dense(model_data, dt)
+            Lm = lap if lap is not None else laplacian_dense(model_data, dt).to(offset.device)
             base = (verts_cano - offset).detach()
             diff = ((Lm @ (base + offset)) - (Lm @ base).detach()) ** 2
             diff = diff.sum(-1, keepdim=True)
             if len(w.reg_offset_lap_relax_for) > 0:
-                diff = diff * scale_vertex_weights_by_region(model_data, V, w.reg_offset_lap_relax_coef, w.reg_offset_lap_relax_for, dt)
+                diff = diff * scale_vertex_weights_by_region(model_data, V, w.reg_offset_lap_relax_coef, w.reg_offset_lap_relax_for, dt, offset.device)
             log["reg_offset_lap"] = w.reg_offset_lap * diff.mean()
         if w.reg_offset is not None:
             ro = offset.abs()
             if len(w.reg_offset_relax_for) > 0:
-                ro = ro * scale_vertex_weights_by_region(model_data, V, w.reg_offset_relax_coef, w.reg_offset_relax_for, dt)
+                ro = ro * scale_vertex_weights_by_region(model_data, V, w.reg_offset_relax_coef, w.reg_offset_relax_for, dt, offset.device)
             log["reg_offset"] = w.reg_offset * ro.mean()
         if w.reg_offset_rigid is not None:
             r = 0
@@ -155,7 +155,7 @@ def regularization_energy(params, ts, stage, cfg, model_data, verts_cano=None, d
 
 
 def compute_energy(params, sample, stage, cfg, model_data, model, lap=None, disturbance=None, tex_painted=None,
-                   return_aux=False):
+                   return_aux=False, rasterize_fn=None):
     """tracker.py:692-750.  `stage` is a vhap_b200.config.StageConfig or None (evaluation mode).
     sample: rgb [B,3,H,W], lmk2d [B,68,3], timestep_index (array of ints).  Returns E_total, log_dict(, aux)."""
     from vhap_b200.config import opt_dict_for
@@ -183,7 +183,7 @@ def compute_energy(params, sample, stage, cfg, model_data, model, lap=None, dist
         faces = model["faces"]
         cam = C.world_to_camera(verts, RT)
         clip = C.camera_to_clip(cam, K, (H, W))
-        rast, rast_db = RA.rasterize(clip, faces, (H, W))
+        rast, rast_db = (rasterize_fn or RA.rasterize)(clip, faces, (H, W))      # (rasterize_fn: bench.py's GPU stand-in feeds ids from the B200 rasteriser)
         verts_uv = model["verts_uv"].clone()
         verts_uv[:, 1] = 1 - verts_uv[:, 1]                                      # tracker.py:315-316
         tex = (tex_painted if tex_painted is not None else 0) + params["tex_extra"]   # tracker.py:247-258
@@ -194,7 +194,7 @@ def compute_energy(params, sample, stage, cfg, model_data, model, lap=None, dist
             bg = [1.0, 1.0, 1.0] if bg_mode == "white" else [0.0, 0.0, 0.0]
         tex_exc = model_data.get_fid_by_region(list(stage.align_texture_except)) if stage is not None else None
         bnd_exc = model_data.get_vid_by_region(list(stage.align_boundary_except)) if stage is not None else None
-        fid2cid = torch.as_tensor(np.concatenate([[0], model_data.fid2cid(cfg.tex_clusters)]))   # render_nvdiffrast.py:77-79
+        fid2cid = torch.as_tensor(np.concatenate([[0], model_data.fid2cid(cfg.tex_clusters)])).to(verts.device)   # render_nvdiffrast.py:77-79
         out = RE.render_rgba(rast, rast_db, verts, clip, faces, verts_uv, model["faces_uv"], tex, params["lights"], bg,
                              model_data.face_adjacency_opposite(), fid2cid, tex_exc, bnd_exc,
                              disturbance if stage is not None else None)

@@ -280,14 +280,14 @@ def render_rgba(rast, rast_db, verts, verts_clip, faces, verts_uv, faces_uv, tex
     bi, yi, xi = torch.nonzero(fg, as_tuple=True)
     alb_fg = texture_sample(mips, texc[bi, yi, xi], texd[bi, yi, xi])
     # nvdiffrast samples every pixel; empty pixels have uv = 0, uv_da = 0 -> level 0 at uv (0,0)
-    alb_bg = _bilinear_wrap(mips[0], torch.zeros(1, dtype=dt), torch.zeros(1, dtype=dt))[0]
+    alb_bg = _bilinear_wrap(mips[0], torch.zeros(1, dtype=dt, device=rast.device), torch.zeros(1, dtype=dt, device=rast.device))[0]
     albedo = alb_bg.expand(B, H, W, 3).clone().index_put((bi, yi, xi), alb_fg)
     diffuse = sh_shading(normal, lights)
     diffuse_detach_normal = sh_shading(normal.detach(), lights)
     rgb = albedo * diffuse
     rgba = torch.cat([rgb, fg[..., None].to(dt)], -1)
     if isinstance(background, (list, tuple)):
-        rgba_bg = torch.tensor(list(background) + [0], dtype=dt).expand(B, H, W, 4)
+        rgba_bg = torch.tensor(list(background) + [0], dtype=dt, device=rast.device).expand(B, H, W, 4)
     elif isinstance(background, torch.Tensor):
         rgba_bg = torch.cat([background.to(dt), torch.zeros_like(background[..., :1], dtype=dt)], -1)
     else:

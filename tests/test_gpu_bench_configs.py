@@ -29,11 +29,14 @@ ROOT = Path(__file__).resolve().parents[1]
 # itself (the engine's, and nvdiffrast's) is conditioned worse: a texture coordinate carries ~1e-7 of rounding from the fp32 barycentrics,
 # i.e. 2e-4 texel at T = 2048, which enters the bilinear weights and, multiplied by the texel pitch, the uv gradient; barycentrics of
 # small triangles cancel.  Measured against the float64 oracle (profiles/r02_parity.txt): identical inputs 512^2 / T=2048: rgba 1e-4,
-# d/d clip 6e-4; from the parameters: every gradient 1e-3 .. 5e-3 (max norm), texture 5e-5 in L2.  The bounds below sit 2-3x above the
-# measured values; a wrong term or a dropped factor shows up at O(1e-1 .. 1).
-TOL = 1e-2                      # end to end from the parameters, fp32 engine vs fp64 oracle, masked (max norm relative to the largest component)
+# d/d clip 6e-4; from the parameters: interior pixels 2e-4 .. 1e-3, all pixels 1e-3 .. 1.6e-2 in max norm (the tail is carried by the
+# antialias adjoint of silhouette pairs whose edge is almost parallel to the pixel pair: d alpha / d position ~ 1 / (by - ay)^2), 1e-3 ..
+# 8e-3 in L2, texture 5e-5 in L2 (probe in profiles/r02_parity.txt).  The bounds below sit 2x above the measured values; a wrong term or a
+# dropped factor shows up at O(1e-1 .. 1) -- the round-1 bound was 0.2 in L2.
+TOL = 3e-2                      # end to end from the parameters, fp32 engine vs fp64 oracle, masked: max norm relative to the largest component
+TOL_L2 = 1.5e-2                 # ... and in relative L2
 TOL_IDENTICAL = 2e-3            # identical fp32 inputs at 512^2 / T=2048
-MAX_MASKED = 2e-3               # at most 0.2 % of the pixels may be masked (the discrete differences themselves are < 0.05 %)
+MAX_MASKED = 1e-3               # at most 0.1 % of the pixels may be masked (measured 0.05 .. 0.09 %)
 
 
 def rel(a, b):
@@ -110,7 +113,10 @@ def masked_e2e(sc, stage_name, label, tol=TOL, probe=False):
         # values on the unmasked pixels (+ the planes of render_out: albedo / normal / diffuse, render_nvdiffrast.py:476-483)
         val_err = float(derr[keep].max())
         fgk = keep & (ids_ref > 0) & ~dilate(ids_ref == 0)
-        plane_err = {k: float(np.abs(planes[k][..., :3].cpu().numpy() - aux["render"][k].detach().numpy())[fgk].max()) for k in ("albedo", "normal", "diffuse")}
+        plane_err = {}
+        for k in ("albedo", "normal", "diffuse"):          # [99.9 % quantile, max]: the max sits on sliver triangles (fp32 barycentrics)
+            dk = np.abs(planes[k][..., :3].cpu().numpy() - aux["render"][k].detach().numpy()).max(-1)[fgk]
+            plane_err[k] = [float(np.quantile(dk, 0.999)), float(dk.max())]
         val_q = [float(np.quantile(derr[keep], q)) for q in (0.5, 0.999)]
         # ---- gradients with the mask on both sides
         pred = aux["render"]["rgba"].permute(0, 3, 1, 2)[:, :3]
@@ -152,9 +158,9 @@ def masked_e2e(sc, stage_name, label, tol=TOL, probe=False):
         record(entry)
         assert frac_masked < MAX_MASKED, entry
         assert val_err <= 1e-3 and val_q[1] < 2e-4, entry
-        assert all(v < 2e-3 for v in plane_err.values()), entry
+        assert all(v[0] < 5e-4 and v[1] < 3e-2 for v in plane_err.values()), entry
         assert all(v < 2e-4 for v in loss_err.values()), entry
-        bad_g = {k: v for k, v in errs.items() if not v < tol}
+        bad_g = {k: (v, errs2[k]) for k, v in errs.items() if not (v < tol and errs2[k] < TOL_L2)}
         assert not bad_g, entry
     finally:
         e.set_loss_mask(None)
@@ -245,12 +251,12 @@ def test_calibrated_cameras_landmark_stage():
         got = e.loss_dict()
         for k, v in log.items():
             if k != "total":
-                assert abs(got[k] - float(v)) <= 2e-5 * max(abs(float(v)), 1e-3), (k, got[k], float(v))
+                assert abs(got[k] - float(v)) <= 1e-4 * max(abs(float(v)), 1e-3), (k, got[k], float(v))
         errs = {}
         for n in ("shape", "expr", "rotation", "translation", "neck_pose", "jaw_pose", "eyes_pose"):
             errs[n] = rel(e.g[n].cpu().numpy(), P[n].grad.numpy().reshape(-1))
         record(dict(test="calibrated_lmk_stage", grad_rel_max={k: float("%.3g" % v) for k, v in errs.items()}))
-        assert all(v < 3e-4 for v in errs.values()), errs
+        assert all(v < 1e-3 for v in errs.values()), errs      # cameras at unit distance: fp32 view transforms of O(1) coordinates
         assert float(e.g["focal_length"].abs().sum()) == 0.0          # calibrated: no focal length to optimise (tracker.py:1330-1339)
     finally:
         e.close()

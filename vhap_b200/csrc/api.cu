@@ -459,18 +459,21 @@ extern "C" int vhap_energy_backward(vhap_ctx* ctx, const vhap_params* p, const v
   // landmark energy (tracker.py:712-719): mean over global_B * n landmarks
   // fork: the parameter-space regularisers only need the parameters and the (already zeroed) gradient slab -> aux stream 0,
   // concurrent with the render backward (works eagerly and inside CUDA-graph capture: fork/join through events)
-  const bool regs_forked = cfg->training && !ctx->no_overlap;
-  if (regs_forked) {
-    cudaEventRecord(ctx->ev[EV_REGS_FORK], s);
-    cudaStreamWaitEvent(ctx->aux[0], ctx->ev[EV_REGS_FORK], 0);
-    launch_regs(ctx, p, fb, cfg, g, global_B, ctx->aux[0]);
-    cudaEventRecord(ctx->ev[EV_REGS_DONE], ctx->aux[0]);
-  } else if (cfg->training) launch_regs(ctx, p, fb, cfg, g, global_B, s);
-  if (cfg->w_landmark >= 0.f) {
+  // The landmark energy (tracker.py:712-719) rides on the same side chain, ahead of the regularisers: its vertex gradients are only
+  // needed by the skinning adjoint (joined there through EV_LMK_DONE).
+  const bool lmk = cfg->w_landmark >= 0.f;
+  const bool regs_forked = (cfg->training || lmk) && !ctx->no_overlap;
+  cudaStream_t ss = regs_forked ? ctx->aux[0] : s;
+  if (regs_forked) { cudaEventRecord(ctx->ev[EV_REGS_FORK], s); cudaStreamWaitEvent(ss, ctx->ev[EV_REGS_FORK], 0); }
+  if (lmk) {
     int nl = cfg->jawline_off ? 51 : 68;
-    launch_landmarks(ctx, fb, cfg->w_landmark / ((float)global_B * nl), cfg->jawline_off, nullptr, nullptr, 1, opt_cam, global_B, s);
+    launch_landmarks(ctx, fb, cfg->w_landmark / ((float)global_B * nl), cfg->jawline_off, nullptr, nullptr, 1, opt_cam, global_B, ss);
+    if (regs_forked) cudaEventRecord(ctx->ev[EV_LMK_DONE], ss);
   }
+  if (cfg->training) launch_regs(ctx, p, fb, cfg, g, global_B, ss);
+  if (regs_forked) cudaEventRecord(ctx->ev[EV_REGS_DONE], ss);
   ctx->tex_fork_pending = 0;
+  bool lights_joined = true;
   cudaStream_t gs = s;                         // stream of the geometry backward
   if (photo) {
     PassArgs P;
@@ -478,8 +481,10 @@ extern "C" int vhap_energy_backward(vhap_ctx* ctx, const vhap_params* p, const v
     launch_finalize(ctx, P, cfg, reduce_slab, local_slab, global_B, p->lights, gg->lights, s);
     if (g) {
       P.g_tex = gg->tex_grad_pyramid;
-      launch_render_backward(ctx, P, cfg, p->lights, gg->lights, nullptr, s);
-      cudaEventRecord(ctx->ev[EV_TEXGRAD_READY], s);          // texel gradients complete: the texture update may start (see vhap_tex_reg_fold_adam)
+      const bool lights_side = regs_forked && gg->lights != nullptr;
+      launch_render_backward(ctx, P, cfg, p->lights, gg->lights, nullptr, s, lights_side ? ctx->aux[0] : nullptr);
+      if (!lights_side) cudaEventRecord(ctx->ev[EV_TEXGRAD_READY], s);   // texel gradients complete: the texture update may start (see vhap_tex_reg_fold_adam)
+      lights_joined = !lights_side;
       ctx->tex_fork_pending = 1;
       // the geometry backward is a chain of small latency-bound kernels; the texture update that runs concurrently is one
       // machine-filling streaming kernel.  Put the chain on a highest-priority stream so its CTAs are scheduled ahead of the
@@ -488,9 +493,11 @@ extern "C" int vhap_energy_backward(vhap_ctx* ctx, const vhap_params* p, const v
       launch_vnormals_bwd(ctx, fb->B, gs);
     }
   }
+  if (g && lmk && regs_forked) cudaStreamWaitEvent(gs, ctx->ev[EV_LMK_DONE], 0);      // the skinning adjoint reads the landmark term's vertex gradients
   if (g) launch_flame_backward(ctx, p, fb, gg, opt_cam, gs);
   if (gs != s) { cudaEventRecord(ctx->ev[EV_GEOM_DONE], gs); cudaStreamWaitEvent(s, ctx->ev[EV_GEOM_DONE], 0); }
-  if (regs_forked) cudaStreamWaitEvent(s, ctx->ev[EV_REGS_DONE], 0);        // join the regularisers
+  if (regs_forked) cudaStreamWaitEvent(s, ctx->ev[EV_REGS_DONE], 0);        // join the side chain (landmarks, regularisers)
+  if (!lights_joined) cudaStreamWaitEvent(s, ctx->ev[EV_LIGHTS_DONE], 0);   // ... and the light-gradient reduction
   float max_hw = (float)(fb->H > fb->W ? fb->H : fb->W);
   LAUNCH(ctx, KID_ASSEMBLE, s, k_assemble_losses<<<1, 32, 0, s>>>(ctx->acc, *cfg, max_hw, gg->focal_length, opt_cam, losses_out, ctx->tex_loss));
   LAST();

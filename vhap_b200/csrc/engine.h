@@ -17,7 +17,7 @@ struct CamParams { float RT[12]; float fx, fy, cx, cy; };
 
 // fork / join events of the side chains of a step (record on one stream, wait on another; valid eagerly and inside stream capture)
 enum { EV_REGS_FORK = 0, EV_REGS_DONE, EV_TEXGRAD_READY, EV_TEX_DONE, EV_VN_FORK, EV_VN_DONE, EV_GEOM_DONE, EV_BLEND_FORK, EV_BLEND_DONE,
-       EV_POSE_FORK, EV_POSE_DONE, EV_COUNT };
+       EV_POSE_FORK, EV_POSE_DONE, EV_LMK_DONE, EV_LIGHTS_DONE, EV_COUNT };
 
 struct vhap_ctx {
   char err[512];
@@ -139,7 +139,8 @@ void launch_scan(vhap_ctx* c, const int* in, int* out, int n, int* total, cudaSt
 void fill_render_args(vhap_ctx* c, PassArgs& P, const vhap_frame_batch* fb, const vhap_stage_cfg* cfg, const float* lights);
 void launch_render_forward(vhap_ctx* c, PassArgs& P, cudaStream_t s);
 void launch_render_finalize(vhap_ctx* c, PassArgs& P, const vhap_stage_cfg* cfg, const float* reduce_slab, int global_B, const float* lights, cudaStream_t s);
-void launch_render_backward(vhap_ctx* c, PassArgs& P, const vhap_stage_cfg* cfg, const float* lights, float* g_lights, const float* ext_grad, cudaStream_t s);
+void launch_render_backward(vhap_ctx* c, PassArgs& P, const vhap_stage_cfg* cfg, const float* lights, float* g_lights, const float* ext_grad, cudaStream_t s,
+                            cudaStream_t side = nullptr);
 // texture.cu
 void launch_tex_rebuild(vhap_ctx* c, const float* tex_extra, cudaStream_t s);
 void launch_tex_fold(vhap_ctx* c, float* tex_extra, float* g_out, float* m, float* v, float lr, int step, const vhap_stage_cfg* cfg,

@@ -284,9 +284,28 @@ __global__ void __launch_bounds__(256) k_reduce_cols(const float* __restrict__ p
 
 // reduce_slab layout (floats): [0] sum |err|  [1] n(alpha_aa>0)  [2] sum var_c(diffuse) incl. background  [3] max diffuse
 //                              [4] this rank's arg-max index (int bits; -1 = background)  [5] local max (to find the owner)  [6] n background px
-__global__ void k_forward_slab(const float* __restrict__ acc, const unsigned long long* __restrict__ maxslot, const float* __restrict__ lights,
-                               float n_pix_total, float* __restrict__ slab) {
-  float nfgpix = acc[ACC_NFGPIX], n_bg = n_pix_total - nfgpix;
+// One CTA: column sums of the per-CTA partial rows of passes A / B (the former k_reduce_cols launch) into acc[], then the slab.
+__global__ void __launch_bounds__(256) k_forward_slab(const float* __restrict__ partials, int rows, float* __restrict__ acc,
+                               const unsigned long long* __restrict__ maxslot, const float* __restrict__ lights, float n_pix_total, float* __restrict__ slab) {
+  __shared__ float shs[64][4];
+  __shared__ float tot[4];
+  {
+    const int col = threadIdx.x & 3, r0 = threadIdx.x >> 2;
+    float s = 0.f;
+    for (int r = r0; r < rows; r += 64) s += partials[(size_t)r * VH_NPART + col];
+    shs[r0][col] = s;
+    __syncthreads();
+    if (threadIdx.x < 4) {
+      float t = 0.f;
+      for (int k = 0; k < 64; ++k) t += shs[k][threadIdx.x];
+      const int slot = threadIdx.x == 0 ? ACC_VARSUM : (threadIdx.x == 1 ? ACC_NFGPIX : (threadIdx.x == 2 ? ACC_ABSERR : ACC_NFG));
+      t += acc[slot];
+      acc[slot] = t; tot[threadIdx.x] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+  }
+  float nfgpix = tot[1], n_bg = n_pix_total - nfgpix;
   float dbg[3], mbg = 0.f;
   for (int c = 0; c < 3; ++c) { dbg[c] = VH_SH_C0 * lights[c] - VH_SH_C4 * lights[24 + c]; mbg += dbg[c] * (1.f / 3.f); }
   float vbg = 0.f, mxbg = fmaxf(dbg[0], fmaxf(dbg[1], dbg[2]));
@@ -295,7 +314,7 @@ __global__ void k_forward_slab(const float* __restrict__ acc, const unsigned lon
   float mxfg = pm ? unpack_max_val(pm) : -INFINITY;
   int idx = pm ? (int)(unsigned)(pm & 0xffffffffu) : -1;
   bool bg_is_max = n_bg > 0.f && mxbg > mxfg;
-  slab[0] = acc[ACC_ABSERR]; slab[1] = acc[ACC_NFG]; slab[2] = acc[ACC_VARSUM] + n_bg * vbg;
+  slab[0] = tot[2]; slab[1] = tot[3]; slab[2] = tot[0] + n_bg * vbg;
   slab[3] = bg_is_max ? mxbg : mxfg;
   ((int*)slab)[4] = bg_is_max ? -1 : idx;
   slab[5] = slab[3];
@@ -411,12 +430,14 @@ void launch_render_forward(vhap_ctx* c, PassArgs& P, cudaStream_t s) {
   LAUNCH(c, KID_PASSA, s, k_passA<<<grid, PB, 0, s>>>(P, c->partials, c->maxslot));
   LAUNCH(c, KID_AA_PAIRS, s, k_aa_pairs<<<grid, PB, 0, s>>>(P, c->pair_list, c->pair_count));
   LAUNCH(c, KID_PASSB, s, k_passB<<<grid, PB, 0, s>>>(P, c->partials));
-  LAUNCH(c, KID_REDUCE, s, k_reduce_cols<<<16, 256, 0, s>>>(c->partials, grid, 0, 4, c->acc, slots));
+  (void)slots;                              // the partial rows are summed by k_forward_slab (launch_forward_slab)
 }
 
 void launch_forward_slab(vhap_ctx* c, const PassArgs& P, const float* lights, float* slab, cudaStream_t s) {
   const RenderArgs& A = P.R;
-  LAUNCH(c, KID_SLAB, s, k_forward_slab<<<1, 1, 0, s>>>(c->acc, c->maxslot, lights, (float)((size_t)A.B * A.H * A.W), slab));
+  size_t n = (size_t)A.B * A.H * A.W;
+  int nblk = (int)((n + PB - 1) / PB), rows = nblk < NPERSIST ? nblk : NPERSIST;          // grid of passes A / B (launch_render_forward)
+  LAUNCH(c, KID_SLAB, s, k_forward_slab<<<1, 256, 0, s>>>(c->partials, rows, c->acc, c->maxslot, lights, (float)n, slab));
 }
 
 void launch_finalize(vhap_ctx* c, const PassArgs& P, const vhap_stage_cfg* cfg, const float* slab_global, const float* slab_local, int global_B,
@@ -425,7 +446,8 @@ void launch_finalize(vhap_ctx* c, const PassArgs& P, const vhap_stage_cfg* cfg, 
   LAUNCH(c, KID_FINALIZE, s, k_finalize<<<1, 1, 0, s>>>(slab_global, slab_local, *cfg, lights, (float)((size_t)global_B * A.H * A.W), c->scal, c->acc, g_lights));
 }
 
-void launch_render_backward(vhap_ctx* c, PassArgs& P, const vhap_stage_cfg* cfg, const float* lights, float* g_lights, const float* ext_grad, cudaStream_t s) {
+void launch_render_backward(vhap_ctx* c, PassArgs& P, const vhap_stage_cfg* cfg, const float* lights, float* g_lights, const float* ext_grad, cudaStream_t s,
+                            cudaStream_t side) {
   (void)cfg; (void)lights;
   const RenderArgs& A = P.R;
   size_t n = (size_t)A.B * A.H * A.W;
@@ -434,5 +456,10 @@ void launch_render_backward(vhap_ctx* c, PassArgs& P, const vhap_stage_cfg* cfg,
   LAUNCH(c, KID_PASSC1, s, k_passC1<<<grid, PB, 0, s>>>(P, ext_grad, c->grgb));
   int grid2 = grid * (PB / VH_C2_PB);
   LAUNCH(c, KID_PASSC, s, k_passC2<<<grid2, VH_C2_PB, 0, s>>>(P, c->grgb, c->partials));
-  if (g_lights) LAUNCH(c, KID_LIGHTS_REDUCE, s, k_reduce_cols<<<16, 256, 0, s>>>(c->partials, grid2, 4, 27, g_lights, nullptr));
+  // side != NULL: the reduction of the light-gradient partials (only the Adam step needs it) leaves the step's critical chain; the caller
+  // joins EV_LIGHTS_DONE.  EV_TEXGRAD_READY doubles as "pass C complete".
+  cudaStream_t ls = s;
+  if (side) { cudaEventRecord(c->ev[EV_TEXGRAD_READY], s); cudaStreamWaitEvent(side, c->ev[EV_TEXGRAD_READY], 0); ls = side; }
+  if (g_lights) LAUNCH(c, KID_LIGHTS_REDUCE, ls, k_reduce_cols<<<16, 256, 0, ls>>>(c->partials, grid2, 4, 27, g_lights, nullptr));
+  if (side) cudaEventRecord(c->ev[EV_LIGHTS_DONE], side);
 }

@@ -364,11 +364,11 @@ class Engine:
         s = self._stream()
         gB = batch.B if global_B is None else global_B
         self._ck(self.L.vhap_energy_forward(self.ctx, C.byref(cp), C.byref(batch.c), C.byref(cs), self.slab_local.data_ptr(), s), None)
+        gslab = self.slab_local                        # single process: the local slab IS the global one (no copy kernel on the critical chain)
         if reduce_fn is not None:
             reduce_fn(self.slab_local, self.slab_global)
-        else:
-            self.slab_global.copy_(self.slab_local)
-        self._ck(self.L.vhap_energy_backward(self.ctx, C.byref(cp), C.byref(batch.c), C.byref(cs), self.slab_global.data_ptr(),
+            gslab = self.slab_global
+        self._ck(self.L.vhap_energy_backward(self.ctx, C.byref(cp), C.byref(batch.c), C.byref(cs), gslab.data_ptr(),
                                              self.slab_local.data_ptr(), gB, C.byref(cg) if cg is not None else None,
                                              self.losses.data_ptr(), s), None)
         self._last = (cs, opt)
