@@ -173,7 +173,7 @@ def measure(args, config, size, B, full):
     gB = B * world
     ring = stage_all(eng, batches)          # device slots with fixed addresses (graphs are captured per slot)
     resident = ring.batches
-    dp = DataParallelStep(eng, texture=args.dp_texture)
+    dp = DataParallelStep(eng, texture=args.dp_texture, slab=args.dp_slab)
     use_graph = not args.no_graph
 
     def barrier():
@@ -348,8 +348,9 @@ def run_ours(args):
         "data": "synthetic (real FLAME topology, seeded bases, procedural 2048^2 texture, engine-rendered targets + noise, uint8 RGB like decoded frames)",
         "config": {"workload": wl,
                    "global_batch": gB, "image": [H, W], "tex": T, "foreground_fraction": fg,
-                   "parallelism": (f"dp{world}: one global parameter set, every rank optimises its own {B} distinct frames per step; per step one all-gather (forward "
-                                   f"slab), one all-reduce (parameter-gradient slab) and the texture update ("
+                   "parallelism": (f"dp{world}: one global parameter set, every rank optimises its own {B} distinct frames per step; per step the forward slab exchange ("
+                                   + ("peer mailboxes over NVLink, written / read by the engine's own kernels" if args.dp_slab == "peer" else "NCCL all-gather") +
+                                   "), one all-reduce (parameter-gradient slab) and the texture update ("
                                    + ("reduce-scatter of the folded texel gradient by row band -> Adam on 1/N of the texture per rank -> all-gather of the updated rows"
                                       if args.dp_texture == "shard" else "dense all-reduce of the texel gradient, full-texture Adam on every rank") + ")") if world > 1 else "single GPU",
                    "launch": ("CUDA graph replay (1 graph launch per step" + (", texture update of step k pipelined into the graph of step k+1; the "
@@ -529,6 +530,8 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the other single-GPU workloads (extra_configs)")
     ap.add_argument("--dp-texture", default="shard", choices=["shard", "allreduce"],
                     help="data-parallel texture update: reduce-scatter -> 1/N Adam -> all-gather (default) or the round-1 dense all-reduce")
+    ap.add_argument("--dp-slab", default="peer", choices=["peer", "nccl"],
+                    help="mid-step exchange of the batch-global scalars: CUDA-IPC peer mailboxes written by the engine's kernels (default) or an NCCL all-gather")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="do not defer the texture update into the next step's graph")
     args = ap.parse_args()

@@ -198,6 +198,15 @@ int vhap_tex_reg_fold_adam(vhap_ctx* ctx, float* tex_extra, float* g_out, float*
 /* data parallel: Adam + pyramid rebuild from the dense gradient produced by vhap_tex_reg_fold_adam(g_out) and summed across ranks */
 int vhap_tex_apply_grad(vhap_ctx* ctx, float* tex_extra, const float* g_dense, float* adam_m, float* adam_v, float lr, int32_t step,
                         const vhap_stage_cfg* cfg, void* stream);
+/* ---- data-parallel exchange of the step's batch-global scalars over peer memory (one node, CUDA IPC; the reference has no multi-GPU path).
+ * vhap_dp_init: allocate this rank's mailbox, return its 64-byte IPC handle; the caller all-gathers the handles of all ranks and passes
+ * them to vhap_dp_connect.  Afterwards vhap_energy_forward pushes this rank's [sum|err|, n_fg, sum var, max diffuse] into every peer's
+ * mailbox and vhap_energy_backward gathers them -- no collective between the halves of a step (their reduce_slab arguments are ignored).
+ * All ranks must then call vhap_energy_forward / vhap_energy_backward the same number of times. */
+int vhap_dp_init(vhap_ctx* ctx, int32_t rank, int32_t world, unsigned char* handle_out_host /*64 bytes*/);
+int vhap_dp_connect(vhap_ctx* ctx, const unsigned char* handles_host /*[world][64]*/);
+int vhap_dp_status(vhap_ctx* ctx, int32_t* out_host);   /* 0 ok, 1 = a peer did not answer within ~4 s (synchronises) */
+
 /* ---- sharded texture update (data parallel; the reference has no multi-GPU path): per step
  *   vhap_tex_fold_grad_rm  photometric part of the texel gradient, dense, ROW-MAJOR g_rm[(y*3 + c)*T + x] so that a row band is contiguous
  *   (caller)               reduce-scatter of g_rm by row band over the ranks

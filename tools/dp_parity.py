@@ -30,6 +30,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     texture = os.environ.get("VHAP_DP_TEXTURE", "shard")
+    slab = os.environ.get("VHAP_DP_SLAB", "peer")
     Bl, H, W, T = 2, 128, 128, 256
     B = Bl * world
     sc = make_scene(B=B, H=H, W=W, T=T, n_t=B + 1, timesteps=list(range(1, B + 1)))
@@ -61,7 +62,8 @@ def main():
     e = Engine(sc["m"], cfg, B + 1, device=f"cuda:{local}", tex_painted=sc["tex_painted"], world_size=world)
     sl = slice(rank * Bl, (rank + 1) * Bl)
     mine = e.stage_sample(rgb[sl], sc["lmk2d"][sl], sc["ts"][sl])
-    dp = DataParallelStep(e, texture=texture)
+    dp = DataParallelStep(e, texture=texture, slab=slab)
+    texture = f"{texture}+{slab}"
     results = {}
     results["eager"] = run(e, lambda: dp.step(mine))
 
@@ -105,9 +107,10 @@ def main():
     dist.all_reduce(mx, op=dist.ReduceOp.MAX)
     dist.all_reduce(mn, op=dist.ReduceOp.MIN)
     sync = float((mx - mn).abs().max())
+    st = e.dp_status()
     if rank == 0:
-        print("replica divergence (max over all parameters):", sync)
-        ok &= sync == 0.0
+        print("replica divergence (max over all parameters):", sync, "| peer mailbox status:", st)
+        ok &= sync == 0.0 and st == 0
         print("DP_PARITY_OK" if ok else "DP_PARITY_FAILED")
     e.close()
     dist.destroy_process_group()

@@ -105,7 +105,7 @@ extern "C" int vhap_ctx_create(vhap_ctx** out, const vhap_mesh_desc* m, int32_t 
     for (int k = 0; k < K; ++k) memcpy(&stp[(size_t)k * ctx->Mpad], &st[(size_t)k * M], M * sizeof(float));
     UP(ctx->S_fwd_pad, stp.data(), (size_t)K * ctx->Mpad);
     { const char* e = getenv("VHAP_B200_BLEND"); ctx->use_tc_blend = !(e && strcmp(e, "simt") == 0); }
-    { const char* e = getenv("VHAP_B200_TEXFOLD"); ctx->tex_fold_v1 = (e && strcmp(e, "v1") == 0); }
+    { const char* e = getenv("VHAP_B200_TEXFOLD"); ctx->tex_fold_reg = (e && strcmp(e, "reg") == 0); }
     // JS[k][j*3+c] = sum_v Jreg[j][v] S[v][c][k] ; Jt = Jreg template
     std::vector<float> js((size_t)K * 15, 0.f), jt(15, 0.f);
     for (int j = 0; j < 5; ++j)
@@ -181,8 +181,8 @@ extern "C" int vhap_ctx_create(vhap_ctx** out, const vhap_mesh_desc* m, int32_t 
     for (int i = 0; i < 2; ++i) CK(cudaStreamCreateWithPriority(&ctx->hp[i], cudaStreamNonBlocking, hi));
   }
   for (int i = 0; i < EV_COUNT; ++i) CK(cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming));
-  UP(ctx->tex_l0_flag, (const int*)nullptr, (size_t)1);
-  { int one = 1; cudaMemcpy(ctx->tex_l0_flag, &one, sizeof(int), cudaMemcpyHostToDevice); }
+  ctx->n_l0_regions = (tex_size >= 8 ? tex_size / 8 : 1) * (tex_size >= 256 ? tex_size / 256 : 1);
+  { std::vector<int> ones((size_t)ctx->n_l0_regions, 1); UP(ctx->tex_l0_flag, ones.data(), (size_t)ctx->n_l0_regions); }   // conservative first fold
   CK(cudaMalloc(&ctx->scan_state, (VH_SCAN_MAX_BLOCKS + 1) * sizeof(unsigned long long)));
   CK(cudaMalloc(&ctx->tex_loss, 4 * sizeof(float))); CK(cudaMemset(ctx->tex_loss, 0, 4 * sizeof(float)));
   CK(cudaMalloc(&ctx->tex_counter, sizeof(unsigned))); CK(cudaMemset(ctx->tex_counter, 0, sizeof(unsigned)));
@@ -241,6 +241,8 @@ extern "C" void vhap_ctx_destroy(vhap_ctx* c) {
   FREE(c->vf_indptr); FREE(c->vf_faces); FREE(c->lap_indptr); FREE(c->lap_idx); FREE(c->lap_val); FREE(c->lap_y);
   FREE(c->face_flags); FREE(c->vert_flags); FREE(c->w_off); FREE(c->w_off_lap); FREE(c->rigid_indptr); FREE(c->rigid_vids); FREE(c->uvmask_res);
   FREE(c->mips[0]); FREE(c->mips[1]); FREE(c->tex_painted); FREE(c->g_tex); FREE(c->tv_partials); FREE(c->tex_counter); FREE(c->tex_loss); FREE(c->scan_state); FREE(c->scal); FREE(c->acc); FREE(c->maxslot);
+  for (int r = 0; r < VH_DP_MAX; ++r) if (c->dp_peers_host[r]) cudaIpcCloseMemHandle(c->dp_peers_host[r]);
+  FREE(c->dp_box); FREE(c->dp_epoch); FREE(c->dp_peers_dev);
   FREE(c->overflow_flag); FREE(c->pool_base); FREE(c->pool_count); FREE(c->dev_lr_scale); FREE(c->dev_step);
   free(c);
 }
@@ -566,11 +568,53 @@ extern "C" int vhap_tex_apply_grad(vhap_ctx* ctx, float* tex_extra, const float*
   LAST();
   return 0;
 }
+// ---- data-parallel peer exchange of the forward slab (render.cu k_forward_slab / k_finalize): CUDA IPC mailboxes, one per rank, mapped by
+// every rank of the node.  vhap_dp_init allocates this rank's mailbox and returns its IPC handle (64 bytes); the caller all-gathers the
+// handles (any transport) and hands all of them to vhap_dp_connect.  From then on vhap_energy_forward / _backward exchange the batch-global
+// scalars themselves (the reduce_slab arguments are ignored) -- no collective call and no host glue between the two halves of a step.
+extern "C" int vhap_dp_init(vhap_ctx* ctx, int32_t rank, int32_t world, unsigned char* handle_out_host /*64*/) {
+  if (world < 1 || world > VH_DP_MAX || rank < 0 || rank >= world) { vh_set_error(ctx, "vhap_dp_init", "rank / world out of range (max 16 ranks)"); return -3; }
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->dp_box) {
+    CK(cudaMalloc((void**)&ctx->dp_box, VH_DP_BOX_FLOATS * sizeof(float)));
+    CK(cudaMalloc((void**)&ctx->dp_epoch, 2 * sizeof(int)));
+    ctx->dp_err = ctx->dp_epoch + 1;
+  }
+  CK(cudaMemset(ctx->dp_box, 0, VH_DP_BOX_FLOATS * sizeof(float)));
+  { int init[2] = {1, 0}; CK(cudaMemcpy(ctx->dp_epoch, init, sizeof(init), cudaMemcpyHostToDevice)); }
+  ctx->dp_rank = rank; ctx->dp_world = world;
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, ctx->dp_box));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  memcpy(handle_out_host, &h, 64);
+  return 0;
+}
+extern "C" int vhap_dp_connect(vhap_ctx* ctx, const unsigned char* handles_host /*[world][64]*/) {
+  if (!ctx->dp_box) { vh_set_error(ctx, "vhap_dp_connect", "call vhap_dp_init first"); return -3; }
+  CK(cudaSetDevice(ctx->device));
+  float* table[VH_DP_MAX] = {nullptr};
+  for (int r = 0; r < ctx->dp_world; ++r) {
+    if (r == ctx->dp_rank) { table[r] = ctx->dp_box; continue; }
+    cudaIpcMemHandle_t h; memcpy(&h, handles_host + (size_t)r * 64, 64);
+    void* p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->dp_peers_host[r] = p; table[r] = (float*)p;
+  }
+  if (!ctx->dp_peers_dev) CK(cudaMalloc((void**)&ctx->dp_peers_dev, VH_DP_MAX * sizeof(float*)));
+  CK(cudaMemcpy(ctx->dp_peers_dev, table, sizeof(table), cudaMemcpyHostToDevice));
+  return 0;
+}
+// 0 = fine, 1 = a peer's flag did not arrive within the spin budget (synchronises)
+extern "C" int vhap_dp_status(vhap_ctx* ctx, int32_t* out_host) {
+  *out_host = 0;
+  if (ctx->dp_err) CK(cudaMemcpy(out_host, ctx->dp_err, sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 // ---- sharded texture update for data-parallel runs (texture.cu "sharded texture update"): the three compute pieces around the caller's
 // reduce-scatter / all-gather.  All run on the stream they are given (no internal fork).
 extern "C" int vhap_tex_fold_grad_rm(vhap_ctx* ctx, float* tex_extra, float* g_rm, void* stream) {
   ctx->tex_fork_pending = 0;
-  if (ctx->tex_fold_v1) { vh_set_error(ctx, "vhap_tex_fold_grad_rm", "needs the v2 fold kernel"); return -3; }
   launch_tex_fold_grad_rm(ctx, tex_extra, g_rm, (cudaStream_t)stream);
   LAST();
   return 0;

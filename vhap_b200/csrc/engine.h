@@ -11,7 +11,9 @@
 
 #define VH_TILE 16                 // raster tile edge in pixels
 #define VH_NPART 40                // floats per block-partial row (>= 27 + a few)
-#define VH_MAXB_CHUNK 16           // frames processed per pass of the blend-shape kernels
+#define VH_MAXB_CHUNK 16
+#define VH_DP_MAX 16                // ranks of one node
+#define VH_DP_BOX_FLOATS (2 * VH_DP_MAX * 8 + VH_DP_MAX)   // mailbox: float slot[2][VH_DP_MAX][8], int flag[VH_DP_MAX]           // frames processed per pass of the blend-shape kernels
 
 struct CamParams { float RT[12]; float fx, fy, cx, cy; };
 
@@ -26,7 +28,7 @@ struct vhap_ctx {
   int mip_off[VH_MAX_MIPS]; size_t mip_total;
   // ---- static model
   float *v_template, *S_fwd, *S_bwd, *posedirs, *Jreg, *lbs_w, *JS, *Jt;
-  int tex_fold_v1;                                // VHAP_B200_TEXFOLD=v1: the round-1 2-row-strip fold kernel (A/B aid)
+  int tex_fold_reg;                               // VHAP_B200_TEXFOLD=reg: the register-pipelined fold kernel also for T >= 256 (A/B aid; default: TMA-staged)
   float* S_fwd_pad; int Mpad; int use_tc_blend;   // [K][Mpad] copy with 16-byte aligned rows for the tensor-core contraction
   i4 *faces, *faces_uv; float* verts_uv; int* lmk_faces; float* lmk_bary; int* adj_opp; uint8_t* fid2cid;
   int *vf_indptr, *vf_faces; int *lap_indptr, *lap_idx; float* lap_val; int lap_nnz;
@@ -64,7 +66,7 @@ struct vhap_ctx {
   f4* grgb;                                       // [N] d L / d rgb of the compacted foreground pixels
   unsigned long long* scan_state;                 // [VH_SCAN_MAX_BLOCKS + 1] look-back words + ticket of the single-launch scan
   int* pool_tri;                                  // rasterised id per pool_list entry
-  int* tex_l0_flag;                               // [1]
+  int* tex_l0_flag; int n_l0_regions;             // [regions] level-0 flags of the texel-gradient pyramid (texture.cu)
   const float* tex_apply_grad; int tex_gout_persistent;
   float* tex_loss;                                // [2] TV / residual regulariser loss of the texture the last fold (or vhap_tex_reg_loss) saw
   int tex_step_bias;                              // added to the device Adam step inside the texture update (deferred update: -1)
@@ -73,6 +75,9 @@ struct vhap_ctx {
   cudaStream_t aux[2]; cudaStream_t hp[2]; cudaEvent_t ev[EV_COUNT];   // hp: highest-priority streams for the latency-critical geometry backward
   int tex_fork_pending, no_overlap;   // fork/join of independent kernel chains
   int* dev_step; int use_dev_step;                // device counters [0] Adam step (1-based), [1] global step; used when use_dev_step
+  // data-parallel peer exchange of the forward slab over NVLink (CUDA IPC mailboxes, render.cu k_forward_slab / k_finalize): replaces the
+  // mid-step NCCL all-gather + its host-side glue kernels on the step's critical chain
+  int dp_rank, dp_world; float* dp_box; float** dp_peers_dev; void* dp_peers_host[VH_DP_MAX]; int* dp_epoch; int* dp_err;
   float* dev_lr_scale;                            // [1] learning-rate scale read by the Adam kernels when use_dev_step (ExponentialLR between graph replays)
 };
 

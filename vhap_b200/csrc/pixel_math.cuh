@@ -24,7 +24,7 @@ struct RenderArgs {
   const int* adj_opp;         // [F*4] opposite vertex per edge (x,y,z), -1 boundary, -2 non-manifold
   const float* ndc;           // optional [B,V,2] = clip.xy / clip.w (saves the divisions in the antialias analysis)
   const float* zwbuf;         // optional [B,H,W,4]: .w of foreground pixels holds their z/w (written by pass A)
-  int* tex_l0_flag;           // optional: raised when the backward scatters into level 0 of the texel-gradient pyramid
+  int* tex_l0_flag;           // optional [regions]: raised where the backward scatters into level 0 of the texel-gradient pyramid
   int pow2, wshift, hshift;   // pow2 != 0: W = 1 << wshift, H = 1 << hshift (pixel index -> (b,y,x) without integer divisions)
 };
 
@@ -341,7 +341,13 @@ VH_HD void shade_pixel_bwd(const RenderArgs& A, int b, int tri, const PixShade& 
   // texture
   float g_u, g_v, g_da[4];
   tex_sample_bwd(A, s.u, s.v, s.tx, g_alb, grad_pyr, g_u, g_v, g_da);
-  if (grad_pyr && A.tex_l0_flag && s.tx.l0 == 0) *A.tex_l0_flag = 1;
+  if (grad_pyr && A.tex_l0_flag && s.tx.l0 == 0) {
+    // level 0 of the gradient pyramid was touched: raise the flags of the (8-row x 256-column) regions of the four texels (texture.cu)
+    Bilin q0; bilin_setup(s.u, s.v, A.T, q0);
+    const int tpr = A.T >= 256 ? A.T >> 8 : 1;
+    const int idx[4] = {q0.i00, q0.i10, q0.i01, q0.i11};
+    for (int k = 0; k < 4; ++k) { int ty = idx[k] / A.T, tx = idx[k] - ty * A.T; A.tex_l0_flag[(ty >> 3) * tpr + (tx >> 8)] = 1; }
+  }
   float d0u = s.t0[0] - s.t2[0], d1u = s.t1[0] - s.t2[0], d0v = s.t0[1] - s.t2[1], d1v = s.t1[1] - s.t2[1];
   bool detach_uv = A.face_flags && (A.face_flags[tri] & 1);
   if (!detach_uv) { g_b0 += g_u * d0u + g_v * d0v; g_b1 += g_u * d1u + g_v * d1v; }

@@ -285,8 +285,15 @@ __global__ void __launch_bounds__(256) k_reduce_cols(const float* __restrict__ p
 // reduce_slab layout (floats): [0] sum |err|  [1] n(alpha_aa>0)  [2] sum var_c(diffuse) incl. background  [3] max diffuse
 //                              [4] this rank's arg-max index (int bits; -1 = background)  [5] local max (to find the owner)  [6] n background px
 // One CTA: column sums of the per-CTA partial rows of passes A / B (the former k_reduce_cols launch) into acc[], then the slab.
+// Data parallel (dp.world > 1): the four batch-global scalars of the slab are exchanged through per-rank MAILBOXES that every peer maps over
+// NVLink (CUDA IPC): this kernel stores its slab into slot [epoch & 1][rank] of every rank's mailbox and then raises flag[rank] = epoch
+// there; k_finalize spins on its own mailbox's flags and reduces the slots in rank order (identical result on every rank).  Two slot
+// parities make the reuse safe: a rank can only write epoch e + 2 after it passed k_finalize(e + 1), which needed every peer's flag e + 1,
+// raised after that peer's k_finalize(e) had finished reading the slots of epoch e.
+struct DpBox { int rank, world; float* const* peers; int* epoch; int* err; float* mine; };
 __global__ void __launch_bounds__(256) k_forward_slab(const float* __restrict__ partials, int rows, float* __restrict__ acc,
-                               const unsigned long long* __restrict__ maxslot, const float* __restrict__ lights, float n_pix_total, float* __restrict__ slab) {
+                               const unsigned long long* __restrict__ maxslot, const float* __restrict__ lights, float n_pix_total, float* __restrict__ slab,
+                               DpBox dp) {
   __shared__ float shs[64][4];
   __shared__ float tot[4];
   {
@@ -319,15 +326,39 @@ __global__ void __launch_bounds__(256) k_forward_slab(const float* __restrict__ 
   ((int*)slab)[4] = bg_is_max ? -1 : idx;
   slab[5] = slab[3];
   slab[6] = n_bg; slab[7] = 0.f;
+  if (dp.world > 1) {
+    const int e = *dp.epoch;
+    for (int p = 0; p < dp.world; ++p) {
+      float* box = dp.peers[p];
+      float4* dst = (float4*)(box + ((size_t)(e & 1) * VH_DP_MAX + dp.rank) * 8);
+      dst[0] = make_float4(slab[0], slab[1], slab[2], slab[3]);
+    }
+    __threadfence_system();
+    for (int p = 0; p < dp.world; ++p) ((volatile int*)(dp.peers[p] + 2 * VH_DP_MAX * 8))[dp.rank] = e;
+  }
 }
 
 // consumes the (possibly cross-rank reduced) slab: scal[] for pass C, loss values, background share of the light gradient
 __global__ void k_finalize(const float* __restrict__ slab, const float* __restrict__ local_slab, vhap_stage_cfg cfg, const float* __restrict__ lights,
-                           float n_pix_global, float* __restrict__ scal, float* __restrict__ acc, float* __restrict__ g_lights) {
+                           float n_pix_global, float* __restrict__ scal, float* __restrict__ acc, float* __restrict__ g_lights, DpBox dp) {
   float abs_sum = slab[0], nfg = slab[1], varsum = slab[2], mx = slab[3];
+  if (dp.world > 1) {                                        // gather the peers' slabs from this rank's mailbox (see k_forward_slab)
+    const int e = *dp.epoch;
+    volatile int* flags = (volatile int*)(dp.mine + 2 * VH_DP_MAX * 8);
+    const long long t0 = clock64();
+    abs_sum = 0.f; nfg = 0.f; varsum = 0.f; mx = -INFINITY;
+    for (int j = 0; j < dp.world; ++j) {
+      while (flags[j] - e < 0) { if (clock64() - t0 > (1ll << 33)) { *dp.err = 1; break; } }      // ~4 s: a dead peer must not hang the GPU
+      __threadfence_system();
+      const volatile float* sl = dp.mine + ((size_t)(e & 1) * VH_DP_MAX + j) * 8;
+      abs_sum += sl[0]; nfg += sl[1]; varsum += sl[2]; mx = fmaxf(mx, sl[3]);
+    }
+    *dp.epoch = e + 1;
+  }
   float photo_scale = (cfg.w_photo >= 0.f && nfg > 0.f) ? cfg.w_photo / (3.f * nfg) : 0.f;
   scal[0] = photo_scale;
-  acc[ACC_PHOTO] = (cfg.w_photo >= 0.f && nfg > 0.f) ? cfg.w_photo * abs_sum / (3.f * nfg) : 0.f;
+  // loss VALUES of batch-global terms: every rank holds the global value; its share is 1 / world so that the loss vectors sum to the total
+  acc[ACC_PHOTO] = (cfg.w_photo >= 0.f && nfg > 0.f) ? cfg.shared_scale * cfg.w_photo * abs_sum / (3.f * nfg) : 0.f;
   bool regd = cfg.training && cfg.opt_lights && cfg.w_reg_diffuse >= 0.f;
   float g_var = regd ? cfg.w_reg_diffuse / n_pix_global : 0.f;
   float g_max = (regd && mx > 1.f) ? cfg.w_reg_diffuse : 0.f;
@@ -336,7 +367,7 @@ __global__ void k_finalize(const float* __restrict__ slab, const float* __restri
   scal[1] = g_var;
   scal[2] = (owner && am >= 0) ? g_max : 0.f;
   ((int*)scal)[3] = am;
-  acc[ACC_REG_DIFFUSE] = regd ? cfg.w_reg_diffuse * (fmaxf(mx - 1.f, 0.f) + varsum / n_pix_global) : 0.f;
+  acc[ACC_REG_DIFFUSE] = regd ? cfg.shared_scale * cfg.w_reg_diffuse * (fmaxf(mx - 1.f, 0.f) + varsum / n_pix_global) : 0.f;
   if (regd && g_lights) {                                    // background pixels: normal = 0 -> basis {C0, 0,..., -C4}
     float n_bg = local_slab[6];
     float dbg[3], mbg = 0.f;
@@ -433,17 +464,21 @@ void launch_render_forward(vhap_ctx* c, PassArgs& P, cudaStream_t s) {
   (void)slots;                              // the partial rows are summed by k_forward_slab (launch_forward_slab)
 }
 
+static DpBox dp_box_of(vhap_ctx* c) {
+  DpBox d; d.rank = c->dp_rank; d.world = c->dp_peers_dev ? c->dp_world : 1; d.peers = c->dp_peers_dev; d.epoch = c->dp_epoch; d.err = c->dp_err; d.mine = c->dp_box;
+  return d;
+}
 void launch_forward_slab(vhap_ctx* c, const PassArgs& P, const float* lights, float* slab, cudaStream_t s) {
   const RenderArgs& A = P.R;
   size_t n = (size_t)A.B * A.H * A.W;
   int nblk = (int)((n + PB - 1) / PB), rows = nblk < NPERSIST ? nblk : NPERSIST;          // grid of passes A / B (launch_render_forward)
-  LAUNCH(c, KID_SLAB, s, k_forward_slab<<<1, 256, 0, s>>>(c->partials, rows, c->acc, c->maxslot, lights, (float)n, slab));
+  LAUNCH(c, KID_SLAB, s, k_forward_slab<<<1, 256, 0, s>>>(c->partials, rows, c->acc, c->maxslot, lights, (float)n, slab, dp_box_of(c)));
 }
 
 void launch_finalize(vhap_ctx* c, const PassArgs& P, const vhap_stage_cfg* cfg, const float* slab_global, const float* slab_local, int global_B,
                      const float* lights, float* g_lights, cudaStream_t s) {
   const RenderArgs& A = P.R;
-  LAUNCH(c, KID_FINALIZE, s, k_finalize<<<1, 1, 0, s>>>(slab_global, slab_local, *cfg, lights, (float)((size_t)global_B * A.H * A.W), c->scal, c->acc, g_lights));
+  LAUNCH(c, KID_FINALIZE, s, k_finalize<<<1, 1, 0, s>>>(slab_global, slab_local, *cfg, lights, (float)((size_t)global_B * A.H * A.W), c->scal, c->acc, g_lights, dp_box_of(c)));
 }
 
 void launch_render_backward(vhap_ctx* c, PassArgs& P, const vhap_stage_cfg* cfg, const float* lights, float* g_lights, const float* ext_grad, cudaStream_t s,

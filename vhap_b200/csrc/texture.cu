@@ -80,7 +80,7 @@ struct TexFoldArgs {
   float w_tv, w_res;            // already divided by their mean() denominators and scaled by shared_scale
   float lr, bc1, bc2_sqrt;      // Adam: step size lr/bc1, sqrt(bias correction 2)
   int do_adam;
-  const int* l0_flag;
+  int* l0_flag;                 // [regions] level-0 flags of the gradient pyramid, region = (y >> 3) * max(T / 256, 1) + (x >> 8)
   const int* step_ptr;          // device Adam step (CUDA-graph replay) or NULL
   const float* lr_scale_ptr;    // device learning-rate scale, read together with step_ptr
   int step_bias;                // added to *step_ptr (deferred update of the previous step: -1)
@@ -94,158 +94,19 @@ struct TexFoldArgs {
 
 __device__ __forceinline__ float chan(const f4& t, int c) { return c == 0 ? t.x : (c == 1 ? t.y : t.z); }
 
-// A CTA covers a (256 x 2)-texel strip of level 0: a thread owns the texels (x, y) and (x, y + 1), so every warp access is a
-// full line of one texture row and a CTA streams 1 KB-contiguous pieces of each planar array (DRAM-page friendly; square tiles
-// measured 1.4-3x slower).  In one pass over the texture:
-//   * fold of the texel-gradient pyramid back to level 0 (box-filter adjoint, 1/4 per level),
-//   * total-variation + residual regularisers (tracker.py:526-539), Adam (tracker.py:210), level 0 of the OTHER pyramid,
-//   * level 1 of the new pyramid (2x2 box filter = own two texels + the neighbour lane's, same arithmetic as k_mip_down):
-//     the separate mip rebuild (render_nvdiffrast.py:399) starts from level 1 and never re-reads the 64 MB of level 0,
-//   * the last CTA to finish sums the per-CTA loss partials in a fixed order (deterministic loss value, no extra launch).
-struct TexelIn { f4 t; float ex[3], g[3], m[3], v[3]; };
-
-// coarse = folded gradient of the levels >= 1 above this texel (shared memory, one entry per level-1 texel of the strip)
-__device__ __forceinline__ void fold_load(const TexFoldArgs& a, int x, int y, bool l0, const float* coarse, TexelIn& r) {
-  const int T = a.T;
-  const size_t n = (size_t)T * T, i = (size_t)y * T + x;
-  r.g[0] = coarse[0]; r.g[1] = coarse[1]; r.g[2] = coarse[2];
-  if (l0) { float4 g0 = *(const float4*)(a.g_pyr + i * 4); r.g[0] += g0.x; r.g[1] += g0.y; r.g[2] += g0.z; }
-  if (a.g_in) { r.g[0] = a.g_in[i]; r.g[1] = a.g_in[n + i]; r.g[2] = a.g_in[2 * n + i]; }
-  r.t = a.tex_old[i];
-  for (int c = 0; c < 3; ++c) { r.ex[c] = a.extra[c * n + i]; if (a.do_adam) { r.m[c] = a.m[c * n + i]; r.v[c] = a.v[c * n + i]; } }
-}
-
-__device__ __forceinline__ f4 fold_texel(const TexFoldArgs& a, int x, int y, bool l0, TexelIn& r, const f4& tu, const f4& td, float bc1, float bc2s, float* acc) {
-  const int T = a.T;
-  const size_t n = (size_t)T * T, i = (size_t)y * T + x;
-  const f4 t = r.t;
-  if (a.g_pyr && l0) { float4* p0 = (float4*)(a.g_pyr + i * 4); *p0 = make_float4(0.f, 0.f, 0.f, 0.f); }   // coarser levels: memset after the kernel
-  if (a.w_tv > 0.f) {                                                          // tracker.py:526-534
-    f4 tr = x + 1 < T ? a.tex_old[i + 1] : t, tl = x > 0 ? a.tex_old[i - 1] : t;
-    for (int c = 0; c < 3; ++c) {
-      float v = chan(t, c), dr = v - chan(tr, c), dd = v - chan(td, c), dl = chan(tl, c) - v, du = chan(tu, c) - v;
-      acc[0] += a.w_tv * (dr * dr + dd * dd);                                  // each difference counted once (right, down)
-      r.g[c] += 2.f * a.w_tv * (dr + dd - dl - du);
-    }
-  }
-  if (a.w_res > 0.f && a.mask && a.mask[i]) {                                  // tracker.py:536-539
-    for (int c = 0; c < 3; ++c) { acc[1] += a.w_res * r.ex[c] * r.ex[c]; r.g[c] += 2.f * a.w_res * r.ex[c]; }
-  }
-  if (a.g_out) { a.g_out[i] = r.g[0]; a.g_out[n + i] = r.g[1]; a.g_out[2 * n + i] = r.g[2]; }
-  f4 o = t;
-  if (a.do_adam) {
-    for (int c = 0; c < 3; ++c) {
-      size_t k = c * n + i;
-      float m = 0.9f * r.m[c] + 0.1f * r.g[c];
-      float v = 0.999f * r.v[c] + 0.001f * r.g[c] * r.g[c];
-      a.m[k] = m; a.v[k] = v;
-      float upd = (a.lr / bc1) * m / (sqrtf(v) / bc2s + 1e-8f);
-      float ne = r.ex[c] - upd;
-      a.extra[k] = ne;
-      float base = chan(t, c) - r.ex[c];                                        // painted part
-      if (c == 0) o.x = base + ne; else if (c == 1) o.y = base + ne; else o.z = base + ne;
-    }
-    a.tex_new[i] = o;
-  }
-  return o;
-}
-
-__global__ void __launch_bounds__(256, 4) k_tex_fold(TexFoldArgs a, float* __restrict__ partials, unsigned* __restrict__ counter, float* __restrict__ acc_out) {
-  __shared__ float sh[8 * 2];
-  __shared__ float coarse[128][3];
-  __shared__ bool is_last;
-  const int T = a.T, tw = T < 256 ? T : 256, tpr = T / tw;
-  const int tid = threadIdx.x;
-  const int x0 = (blockIdx.x % tpr) * tw, x = x0 + tid, y = (blockIdx.x / tpr) * 2;
-  // photometric gradient of the pyramid levels >= 1 folded down to the strip's level-1 texels (box-filter adjoint: 1/4 per
-  // level), once per level-1 texel instead of once per texel: one float4 load per level for 128 threads
-  if (tid < (tw >> 1)) {
-    float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-    if (a.g_pyr) {
-      float sc = 0.25f;
-      const int x1 = (x0 >> 1) + tid, y1 = y >> 1;
-      for (int l = 1; l <= a.max_level; ++l) {
-        float4 p = *(const float4*)(a.g_pyr + ((size_t)a.mip_off[l] + (size_t)(y1 >> (l - 1)) * (T >> l) + (x1 >> (l - 1))) * 4);
-        g0 += p.x * sc; g1 += p.y * sc; g2 += p.z * sc;
-        sc *= 0.25f;
-      }
-    }
-    coarse[tid][0] = g0; coarse[tid][1] = g1; coarse[tid][2] = g2;
-  }
-  __syncthreads();
-  float acc[2] = {0.f, 0.f};
-  const bool on = tid < tw;
-  f4 o0 = {0, 0, 0, 0}, o1 = {0, 0, 0, 0};
-  if (on) {
-    // level 0 of the gradient pyramid is only touched under magnification (mip level < 1); the backward pass raises
-    // l0_flag when it scatters there, otherwise the 16 B/texel read + re-zero of that level is skipped
-    const bool l0 = a.g_pyr ? (a.l0_flag ? (*a.l0_flag != 0) : true) : false;
-    float bc1 = a.bc1, bc2s = a.bc2_sqrt;
-    if (a.do_adam && a.step_ptr) {
-      float st = (float)(a.step_ptr[0] + a.step_bias); bc2s = sqrtf(1.f - powf(0.999f, st));
-      bc1 = (1.f - powf(0.9f, st)) / a.lr_scale_ptr[0];                       // fold_texel uses lr / bc1
-    }
-    TexelIn r0, r1;
-    fold_load(a, x, y, l0, coarse[tid >> 1], r0);   // all loads of both texels are issued before the first dependent store
-    fold_load(a, x, y + 1, l0, coarse[tid >> 1], r1);
-    const size_t i0 = (size_t)y * T + x;
-    f4 tu = r0.t, td = r1.t;
-    if (a.w_tv > 0.f) { if (y > 0) tu = a.tex_old[i0 - T]; if (y + 2 < T) td = a.tex_old[i0 + 2 * (size_t)T]; }
-    o0 = fold_texel(a, x, y, l0, r0, tu, r1.t, bc1, bc2s, acc);
-    o1 = fold_texel(a, x, y + 1, l0, r1, r0.t, td, bc1, bc2s, acc);
-  }
-  // level 1 of the new pyramid: avg4(A[2y][2x], A[2y+1][2x], A[2y][2x+1], A[2y+1][2x+1]) with the right neighbour's pair
-  {
-    f4 c, d;
-    c.x = __shfl_down_sync(0xffffffffu, o0.x, 1); c.y = __shfl_down_sync(0xffffffffu, o0.y, 1); c.z = __shfl_down_sync(0xffffffffu, o0.z, 1);
-    d.x = __shfl_down_sync(0xffffffffu, o1.x, 1); d.y = __shfl_down_sync(0xffffffffu, o1.y, 1); d.z = __shfl_down_sync(0xffffffffu, o1.z, 1);
-    c.w = d.w = 0.f;
-    if (on && a.do_adam && a.max_level >= 1 && !(tid & 1))
-      a.tex_new[(size_t)a.mip_off[1] + (size_t)(y >> 1) * (T >> 1) + (x >> 1)] = avg4(o0, o1, c, d);
-  }
-  // block partial sums of the two loss terms; the last CTA reduces all partials in a fixed order
-  int lane = tid & 31, w = tid >> 5;
-  for (int q = 0; q < 2; ++q) {
-    float v = acc[q];
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) sh[w * 2 + q] = v;
-  }
-  __syncthreads();
-  if (tid < 2) {
-    float s2 = 0.f;
-    for (int k = 0; k < 8; ++k) s2 += sh[k * 2 + tid];
-    partials[(size_t)blockIdx.x * 2 + tid] = s2;
-    __threadfence();
-  }
-  __syncthreads();
-  if (tid == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  for (int q = 0; q < 2; ++q) {
-    float s2 = 0.f;
-    for (int r = tid; r < (int)gridDim.x; r += 256) s2 += __ldcg(partials + (size_t)r * 2 + q);
-    for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-    __syncthreads();
-    if (lane == 0) sh[w] = s2;
-    __syncthreads();
-    if (tid == 0) {
-      float t = 0.f;
-      for (int k = 0; k < 8; ++k) t += sh[k];
-      acc_out[q] = t;                                   // [0] TV, [1] residual (vhap_ctx::tex_loss)
-    }
-  }
-  if (tid == 0) *counter = 0u;
-}
-
-// ---- version 2 of the fold kernel: a CTA walks a band of TF_ROWS texture rows of a 256-wide strip top to bottom, one row per
-// iteration, with the loads of row y+1 in flight while row y is processed (software pipeline of depth 1 in registers):
-//   * the rows above / below a texel (total variation) are the previous / next iteration's register values: the halo is 2 rows per
-//     TF_ROWS instead of 2 per 2 (v1 re-read both neighbour rows of every 2-row strip: +16 B/texel of the 16 B/texel level 0),
-//   * left / right neighbours come from warp shuffles (only lanes 0 / 31 load their outside neighbour),
-//   * the coarse levels of the gradient pyramid are folded hierarchically per band (levels >= 3 once per 8x8 block, level 2 once
-//     per 4x4, level 1 once per 2x2) instead of 11 dependent loads per level-1 texel.
-// Same arithmetic per texel as v1 (fold_texel); the coarse fold sums the levels in a different association (1e-7 relative).
+// ---- The fold kernels.  In ONE pass over the texture: fold of the texel-gradient pyramid back to level 0 (box-filter adjoint, 1/4 per
+// level), total-variation + residual regularisers (tracker.py:526-539), Adam (tracker.py:210), level 0 AND level 1 of the OTHER pyramid
+// (the mip rebuild of render_nvdiffrast.py:399 then starts from level 1), loss partials reduced by the last CTA (deterministic order).
+// A CTA walks a band of TF_ROWS rows of a 256-texel-wide strip top to bottom (wide strips: 1 KB-contiguous pieces of every planar array,
+// DRAM-page friendly; square tiles measured 1.4-3x slower in round 1):
+//   * rows above / below a texel (total variation) come from the previous / next iteration: the halo is 2 rows per TF_ROWS (the round-1
+//     kernel re-read both neighbour rows of every 2-row strip: +16 B/texel),
+//   * the coarse gradient levels are folded hierarchically per band (levels >= 3 once per 8x8 block, level 2 per 4x4, level 1 per 2x2),
+//   * level 0 of the gradient pyramid (32 B/texel of read + re-zero) is only touched where the backward scattered into it: one flag per
+//     (8-row, 256-column) region, raised by tex_sample_bwd, cleared here.
+// k_tex_fold2: register pipeline (loads of row y+1 in flight while row y is processed), any T.  k_tex_fold3 (T >= 256): the rows are
+// staged in shared memory by TMA 1-D bulk copies (cp.async.bulk + mbarrier expect-tx), TF3_NS rows deep, so that ~2 rows x 17 KB per CTA
+// are in flight regardless of the register budget; the arithmetic is identical.
 #ifndef TF_ROWS
 #define TF_ROWS 8
 #endif
@@ -320,7 +181,8 @@ __global__ void __launch_bounds__(256, TF_MINB) k_tex_fold2(TexFoldArgs a, float
   __syncthreads();
   float acc[2] = {0.f, 0.f};
   const bool on = tid < tw;
-  const bool l0 = fold ? (a.l0_flag ? (*a.l0_flag != 0) : true) : false;
+  int* l0p = (fold && a.l0_flag) ? a.l0_flag + (y0 >> 3) * tpr + (x0 >> 8) : nullptr;      // this CTA's region flag
+  const bool l0 = fold ? (l0p ? (*l0p != 0) : true) : false;
   float bc1 = a.bc1, bc2s = a.bc2_sqrt;
   if (a.do_adam && a.step_ptr) {
     float st = (float)(a.step_ptr[0] + a.step_bias); bc2s = sqrtf(1.f - powf(0.999f, st));
@@ -328,6 +190,8 @@ __global__ void __launch_bounds__(256, TF_MINB) k_tex_fold2(TexFoldArgs a, float
   }
   const size_t n = (size_t)T * T;
   const bool tv = a.w_tv > 0.f;
+  __syncthreads();
+  if (tid == 0 && l0p) *l0p = 0;
   RowIn cur = {}, nxt;
   f4 t_up = {0, 0, 0, 0}, o_prev = {0, 0, 0, 0};
   if (on) {
@@ -441,6 +305,241 @@ __global__ void __launch_bounds__(256, TF_MINB) k_tex_fold2(TexFoldArgs a, float
   if (tid == 0) *counter = 0u;
 }
 
+
+// ---- TMA-staged version (T >= 256, 256-wide strips)
+#define TF3_NS 3
+struct __align__(16) TF3Row {
+  f4 t[258];                  // texture row incl. the left / right neighbour columns of the strip
+  float ex[3][256], m[3][256], v[3][256];
+  f4 g[256];                  // level 0 of the gradient pyramid (fold mode) or, as float[3][256], the dense input gradient (apply / band mode)
+  unsigned char msk[256];
+};
+__device__ __forceinline__ void tf3_wait(uint64_t* bar, unsigned parity) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar), done = 0;
+  while (!done) asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.b32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tf3_copy(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+// row q of the band (q == R: the halo row below the band, texture values only) into ring slot `slot`
+__device__ void tf3_issue(const TexFoldArgs& a, TF3Row* rows, uint64_t* bars, int slot, int x0, int y, bool full, bool l0, bool want_mask) {
+  const int T = a.T;
+  const size_t n = (size_t)T * T, i = (size_t)y * T + x0;
+  TF3Row& r = rows[slot];
+  uint64_t* bar = bars + slot;
+  const int left = x0 > 0 ? 1 : 0, right = x0 + 256 < T ? 1 : 0;
+  unsigned bytes = (unsigned)(256 + left + right) * 16u;
+  if (full) {
+    bytes += 3u * 1024u;
+    if (a.do_adam) bytes += 6u * 1024u;
+    if (a.g_in) bytes += 3u * 1024u; else if (l0) bytes += 4096u;
+    if (want_mask) bytes += 256u;
+  }
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+  tf3_copy(&r.t[1 - left], a.tex_old + i - left, (unsigned)(256 + left + right) * 16u, bar);
+  if (!full) return;
+  for (int c = 0; c < 3; ++c) {
+    tf3_copy(r.ex[c], a.extra + c * n + i, 1024u, bar);
+    if (a.do_adam) { tf3_copy(r.m[c], a.m + c * n + i, 1024u, bar); tf3_copy(r.v[c], a.v + c * n + i, 1024u, bar); }
+    if (a.g_in) {
+      const float* gi = a.rm ? a.g_in + ((size_t)(y - a.y_begin) * 3 + c) * T + x0 : a.g_in + c * n + i;
+      tf3_copy((float*)r.g + c * 256, gi, 1024u, bar);
+    }
+  }
+  if (!a.g_in && l0) tf3_copy(r.g, a.g_pyr + i * 4, 4096u, bar);
+  if (want_mask) tf3_copy(r.msk, a.mask + i, 256u, bar);
+}
+
+__global__ void __launch_bounds__(256, 3) k_tex_fold3(TexFoldArgs a, float* __restrict__ partials, unsigned* __restrict__ counter, float* __restrict__ acc_out) {
+  extern __shared__ __align__(128) unsigned char tf3_smem[];
+  TF3Row* rows = (TF3Row*)tf3_smem;
+  __shared__ uint64_t bars[TF3_NS];
+  __shared__ float sh[8 * 2];
+  __shared__ float c1[(TF_ROWS / 2) * 128][3];
+  __shared__ float c2[((TF_ROWS + 3) / 4) * 64][3];
+  __shared__ float c3[((TF_ROWS + 7) / 8) * 32][3];
+  __shared__ bool is_last;
+  const int T = a.T, tpr = T >> 8, R = TF_ROWS;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int x0 = (blockIdx.x % tpr) << 8, x = x0 + tid, y0 = a.y_begin + (blockIdx.x / tpr) * R;
+  const bool fold = a.g_pyr != nullptr && a.g_in == nullptr;
+  const bool tv = a.w_tv > 0.f;
+  const bool want_mask = a.w_res > 0.f && a.mask != nullptr;
+  int* l0p = (fold && a.l0_flag) ? a.l0_flag + (y0 >> 3) * tpr + (x0 >> 8) : nullptr;
+  const bool l0 = fold ? (l0p ? (*l0p != 0) : true) : false;
+  const bool halo_dn = tv && (y0 + R < T);
+  const int q_last = halo_dn ? R : R - 1;                      // last row of the pipeline (the halo row carries the texture only)
+  if (tid == 0) {
+    for (int i = 0; i < TF3_NS; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&bars[i])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int q = 0; q < TF3_NS && q <= q_last; ++q) tf3_issue(a, rows, bars, q, x0, y0 + q, q < R, l0, want_mask);
+    if (l0p) *l0p = 0;
+  }
+  // ---- hierarchical fold of the coarse gradient levels while the first rows are in flight
+  for (int j = tid; j < 32; j += 256) {
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+    if (fold) {
+      const int X = (x0 >> 3) + j, Y = y0 >> 3;
+      float sc = 1.f / 64.f;
+      for (int l = 3; l <= a.max_level; ++l) {
+        float4 p = *(const float4*)(a.g_pyr + ((size_t)a.mip_off[l] + (size_t)(Y >> (l - 3)) * (T >> l) + (X >> (l - 3))) * 4);
+        g0 += p.x * sc; g1 += p.y * sc; g2 += p.z * sc;
+        sc *= 0.25f;
+      }
+    }
+    c3[j][0] = g0; c3[j][1] = g1; c3[j][2] = g2;
+  }
+  __syncthreads();
+  for (int j = tid; j < 128; j += 256) {
+    const int jx = j & 63, jy = j >> 6;
+    const int p3 = jx >> 1;
+    float g0 = c3[p3][0], g1 = c3[p3][1], g2 = c3[p3][2];
+    if (fold && a.max_level >= 2) {
+      float4 p = *(const float4*)(a.g_pyr + ((size_t)a.mip_off[2] + (size_t)((y0 >> 2) + jy) * (T >> 2) + (x0 >> 2) + jx) * 4);
+      g0 += p.x * (1.f / 16.f); g1 += p.y * (1.f / 16.f); g2 += p.z * (1.f / 16.f);
+    }
+    c2[j][0] = g0; c2[j][1] = g1; c2[j][2] = g2;
+  }
+  __syncthreads();
+  for (int j = tid; j < 512; j += 256) {
+    const int jx = j & 127, jy = j >> 7;
+    const int p2 = (jy >> 1) * 64 + (jx >> 1);
+    float g0 = c2[p2][0], g1 = c2[p2][1], g2 = c2[p2][2];
+    if (fold && a.max_level >= 1) {
+      float4 p = *(const float4*)(a.g_pyr + ((size_t)a.mip_off[1] + (size_t)((y0 >> 1) + jy) * (T >> 1) + (x0 >> 1) + jx) * 4);
+      g0 += p.x * 0.25f; g1 += p.y * 0.25f; g2 += p.z * 0.25f;
+    }
+    c1[j][0] = g0; c1[j][1] = g1; c1[j][2] = g2;
+  }
+  __syncthreads();
+  float acc[2] = {0.f, 0.f};
+  float bc1 = a.bc1, bc2s = a.bc2_sqrt;
+  if (a.do_adam && a.step_ptr) {
+    float st = (float)(a.step_ptr[0] + a.step_bias); bc2s = sqrtf(1.f - powf(0.999f, st));
+    bc1 = (1.f - powf(0.9f, st)) / a.lr_scale_ptr[0];
+  }
+  const size_t n = (size_t)T * T;
+  f4 t_up = {0, 0, 0, 0}, o_prev = {0, 0, 0, 0};
+  const bool halo_up = tv && y0 > 0;
+  if (halo_up) t_up = a.tex_old[(size_t)(y0 - 1) * T + x];
+#pragma unroll 1
+  for (int r = 0; r < R; ++r) {
+    const int y = y0 + r, slot = r % TF3_NS;
+    const size_t i = (size_t)y * T + x;
+    tf3_wait(&bars[slot], (unsigned)((r / TF3_NS) & 1));
+    const TF3Row& cur = rows[slot];
+    const f4 t = cur.t[tid + 1];
+    f4 t_dn = t;
+    if (r + 1 <= q_last) {
+      tf3_wait(&bars[(r + 1) % TF3_NS], (unsigned)(((r + 1) / TF3_NS) & 1));
+      t_dn = rows[(r + 1) % TF3_NS].t[tid + 1];
+    }
+    if (r == 0 && !halo_up) t_up = t;
+    const f4 tl = x > 0 ? cur.t[tid] : t, tr = x + 1 < T ? cur.t[tid + 2] : t;
+    float g[3] = {0.f, 0.f, 0.f};
+    if (a.g_in) { const float* gi = (const float*)cur.g; g[0] = gi[tid]; g[1] = gi[256 + tid]; g[2] = gi[512 + tid]; }
+    else if (l0) { const f4 g0 = cur.g[tid]; g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; }
+    if (fold) { const float* cg = c1[(r >> 1) * 128 + (tid >> 1)]; g[0] += cg[0]; g[1] += cg[1]; g[2] += cg[2]; }
+    if (l0) *(float4*)(a.g_pyr + i * 4) = make_float4(0.f, 0.f, 0.f, 0.f);       // coarser levels: memset after the kernel
+    float ex[3] = {cur.ex[0][tid], cur.ex[1][tid], cur.ex[2][tid]};
+    if (tv) {                                                                      // tracker.py:526-534
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float v = chan(t, c), dr = v - chan(tr, c), dd = v - chan(t_dn, c), dl = chan(tl, c) - v, du = chan(t_up, c) - v;
+        acc[0] += a.w_tv * (dr * dr + dd * dd);
+        g[c] += 2.f * a.w_tv * (dr + dd - dl - du);
+      }
+    }
+    if (want_mask && cur.msk[tid]) {                                               // tracker.py:536-539
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { acc[1] += a.w_res * ex[c] * ex[c]; g[c] += 2.f * a.w_res * ex[c]; }
+    }
+    if (a.g_out) {
+      if (a.rm) { float* go = a.g_out + ((size_t)y * 3) * T + x; go[0] = g[0]; go[T] = g[1]; go[2 * (size_t)T] = g[2]; }
+      else { a.g_out[i] = g[0]; a.g_out[n + i] = g[1]; a.g_out[2 * n + i] = g[2]; }
+    }
+    f4 o = t;
+    if (a.do_adam) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const size_t k = c * n + i;
+        float m = 0.9f * cur.m[c][tid] + 0.1f * g[c];
+        float v = 0.999f * cur.v[c][tid] + 0.001f * g[c] * g[c];
+        a.m[k] = m; a.v[k] = v;
+        float upd = (a.lr / bc1) * m / (sqrtf(v) / bc2s + 1e-8f);
+        float ne = ex[c] - upd;
+        a.extra[k] = ne;
+        if (a.ex_band_out) a.ex_band_out[((size_t)(y - a.y_begin) * 3 + c) * T + x] = ne;
+        float base = chan(t, c) - ex[c];                                            // painted part
+        if (c == 0) o.x = base + ne; else if (c == 1) o.y = base + ne; else o.z = base + ne;
+      }
+      if (!a.no_pyramid) a.tex_new[i] = o;
+    }
+    if (r & 1) {                                       // level 1: avg4(A[2y][2x], A[2y+1][2x], A[2y][2x+1], A[2y+1][2x+1]), same order as k_mip_down
+      f4 c, d;
+      c.x = __shfl_down_sync(0xffffffffu, o_prev.x, 1); c.y = __shfl_down_sync(0xffffffffu, o_prev.y, 1); c.z = __shfl_down_sync(0xffffffffu, o_prev.z, 1);
+      d.x = __shfl_down_sync(0xffffffffu, o.x, 1); d.y = __shfl_down_sync(0xffffffffu, o.y, 1); d.z = __shfl_down_sync(0xffffffffu, o.z, 1);
+      c.w = d.w = 0.f;
+      if (a.do_adam && !a.no_pyramid && a.max_level >= 1 && !(tid & 1))
+        a.tex_new[(size_t)a.mip_off[1] + (size_t)(y >> 1) * (T >> 1) + (x >> 1)] = avg4(o_prev, o, c, d);
+    }
+    o_prev = o;
+    t_up = t;
+    __syncthreads();                                   // every thread is done with ring slot `slot`: refill it with row r + TF3_NS
+    if (tid == 0 && r + TF3_NS <= q_last) tf3_issue(a, rows, bars, slot, x0, y0 + r + TF3_NS, r + TF3_NS < R, l0, want_mask);
+  }
+  // block partial sums of the two loss terms; the last CTA reduces all partials in a fixed order
+  const int w = tid >> 5;
+  for (int q = 0; q < 2; ++q) {
+    float v = acc[q];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sh[w * 2 + q] = v;
+  }
+  __syncthreads();
+  if (tid < 2) {
+    float s2 = 0.f;
+    for (int k = 0; k < 8; ++k) s2 += sh[k * 2 + tid];
+    partials[(size_t)blockIdx.x * 2 + tid] = s2;
+    __threadfence();
+  }
+  __syncthreads();
+  if (tid == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int q = 0; q < 2; ++q) {
+    float s2 = 0.f;
+    for (int r = tid; r < (int)gridDim.x; r += 256) s2 += __ldcg(partials + (size_t)r * 2 + q);
+    for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    __syncthreads();
+    if (lane == 0) sh[w] = s2;
+    __syncthreads();
+    if (tid == 0) {
+      float t = 0.f;
+      for (int k = 0; k < 8; ++k) t += sh[k];
+      acc_out[q] = t;
+    }
+  }
+  if (tid == 0) *counter = 0u;
+}
+
+// launches the fold kernel for `rows` rows starting at a.y_begin: TMA-staged for T >= 256 (VHAP_B200_TEXFOLD=reg: register pipeline)
+static void launch_fold_kernel(vhap_ctx* c, const TexFoldArgs& a, int rows, float* acc_out, cudaStream_t s) {
+  const int T = c->T, tw = T < 256 ? T : 256, R = T < TF_ROWS ? T : TF_ROWS, nblk = (T / tw) * (rows / R);
+  if (T >= 256 && !c->tex_fold_reg) {
+    static bool attr_set = false;
+    const int smem = (int)(TF3_NS * sizeof(TF3Row));
+    if (!attr_set) { cudaFuncSetAttribute(k_tex_fold3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
+    LAUNCH(c, KID_TEX_FOLD, s, k_tex_fold3<<<nblk, 256, smem, s>>>(a, c->tv_partials, c->tex_counter, acc_out));
+  } else {
+    LAUNCH(c, KID_TEX_FOLD, s, k_tex_fold2<<<nblk, 256, 0, s>>>(a, c->tv_partials, c->tex_counter, acc_out));
+  }
+}
+
 // TV + residual regulariser LOSS VALUES of the current texture (tracker.py:526-539), no gradient: used when the texture update is
 // deferred into the next step (the fold kernel then sees the texture one step late), so that a step's loss vector is complete.
 __global__ void __launch_bounds__(256) k_tex_reg_loss(const f4* __restrict__ tex, const float* __restrict__ extra, const uint8_t* __restrict__ mask, int T,
@@ -514,20 +613,13 @@ void launch_tex_fold(vhap_ctx* c, float* tex_extra, float* g_out, float* m, floa
   a.do_adam = (m != nullptr && v != nullptr) ? 1 : 0;
   a.lr = lr; a.bc1 = 1.f - powf(0.9f, (float)step); a.bc2_sqrt = sqrtf(1.f - powf(0.999f, (float)step));
   a.y_begin = 0; a.y_end = T;
-  int tw = T < 256 ? T : 256, nblk = (T / tw) * (T / 2), L = c->max_level >= 1 ? 1 : 0;
-  if (c->tex_fold_v1) {
-    LAUNCH(c, KID_TEX_FOLD, s, k_tex_fold<<<nblk, 256, 0, s>>>(a, c->tv_partials, c->tex_counter, a.g_in ? c->tex_loss + 2 : c->tex_loss));      // apply mode: scratch slots
-  } else {
-    int R = T < TF_ROWS ? T : TF_ROWS;
-    nblk = (T / tw) * (T / R);
-    LAUNCH(c, KID_TEX_FOLD, s, k_tex_fold2<<<nblk, 256, 0, s>>>(a, c->tv_partials, c->tex_counter, a.g_in ? c->tex_loss + 2 : c->tex_loss));
-  }
+  const int L = c->max_level >= 1 ? 1 : 0;
+  launch_fold_kernel(c, a, T, a.g_in ? c->tex_loss + 2 : c->tex_loss, s);      // apply mode: scratch slots
   if (a.g_in) {                                                           // apply mode leaves the gradient pyramid alone
     if (a.do_adam) { c->cur_mip ^= 1; build_mips(c, c->mips[c->cur_mip], s, L); }
     return;
   }
-  cudaMemsetAsync(c->tex_l0_flag, 0, sizeof(int), s);
-  if (c->g_tex && c->max_level >= 1)                                      // coarser gradient levels
+  if (c->g_tex && c->max_level >= 1)                                      // coarser gradient levels (level 0: cleared in-kernel, per region)
     cudaMemsetAsync(c->g_tex + (size_t)c->mip_off[1] * 4, 0, (c->mip_total - c->mip_off[1]) * 4 * sizeof(float), s);
   if (a.do_adam) { c->cur_mip ^= 1; build_mips(c, c->mips[c->cur_mip], s, L); }    // levels 1..L were written by the fold kernel
 }
@@ -547,13 +639,10 @@ static void fill_fold_args(vhap_ctx* c, TexFoldArgs& a, float* tex_extra) {
   a.step_ptr = c->use_dev_step ? c->dev_step : nullptr; a.lr_scale_ptr = c->dev_lr_scale; a.step_bias = c->tex_step_bias;
   a.y_begin = 0; a.y_end = c->T;
 }
-static int fold_grid(const vhap_ctx* c, int rows) { int T = c->T, tw = T < 256 ? T : 256, R = T < TF_ROWS ? T : TF_ROWS; return (T / tw) * (rows / R); }
-
 void launch_tex_fold_grad_rm(vhap_ctx* c, float* tex_extra, float* g_rm, cudaStream_t s) {
   TexFoldArgs a; fill_fold_args(c, a, tex_extra);
   a.g_out = g_rm; a.rm = 1; a.do_adam = 0; a.w_tv = 0.f; a.w_res = 0.f; a.mask = nullptr;
-  LAUNCH(c, KID_TEX_FOLD, s, k_tex_fold2<<<fold_grid(c, c->T), 256, 0, s>>>(a, c->tv_partials, c->tex_counter, c->tex_loss + 2));
-  cudaMemsetAsync(c->tex_l0_flag, 0, sizeof(int), s);
+  launch_fold_kernel(c, a, c->T, c->tex_loss + 2, s);
   if (c->g_tex && c->max_level >= 1)
     cudaMemsetAsync(c->g_tex + (size_t)c->mip_off[1] * 4, 0, (c->mip_total - c->mip_off[1]) * 4 * sizeof(float), s);
 }
@@ -568,7 +657,7 @@ int launch_tex_band_adam(vhap_ctx* c, float* tex_extra, const float* g_band, int
   a.w_tv = (cfg->training && cfg->opt_texture && cfg->w_reg_tex_tv >= 0.f) ? cfg->w_reg_tex_tv / (3.f * (float)(T - 1) * (float)T) : 0.f;
   a.w_res = (cfg->training && cfg->opt_texture && cfg->w_reg_tex_res >= 0.f) ? cfg->w_reg_tex_res / (3.f * (float)T * (float)T) : 0.f;
   a.lr = lr; a.bc1 = 1.f - powf(0.9f, (float)step); a.bc2_sqrt = sqrtf(1.f - powf(0.999f, (float)step));
-  LAUNCH(c, KID_TEX_FOLD, s, k_tex_fold2<<<fold_grid(c, y_end - y_begin), 256, 0, s>>>(a, c->tv_partials, c->tex_counter, c->tex_loss + 2));
+  launch_fold_kernel(c, a, y_end - y_begin, c->tex_loss + 2, s);
   return 0;
 }
 

@@ -114,6 +114,7 @@ class Engine:
         self._graph_live = False
         self._inj = None
         self._loss_mask = None
+        self._peer_slab = False
         self._tex_persist = False
         if world_size > 1:
             # the dense texture gradient is a persistent buffer of this object: its fold may run on the library's aux stream
@@ -329,6 +330,23 @@ class Engine:
         self.reserve(B, H, W)
         return Batch(B, H, W, ts, tgt, lm, RTd, Kd)
 
+    def dp_connect(self, rank: int, world: int, gather_bytes) -> None:
+        """data parallel: map every rank's slab mailbox over NVLink (CUDA IPC).  `gather_bytes(b)` returns the list of every rank's bytes
+        (e.g. torch.distributed.all_gather_object).  Afterwards energy() needs no reduce_fn: see include/vhap_b200.h vhap_dp_init."""
+        h = (C.c_ubyte * 64)()
+        self._ck(self.L.vhap_dp_init(self.ctx, rank, world, h))
+        handles = gather_bytes(bytes(h))
+        if len(handles) != world or any(len(x) != 64 for x in handles):
+            raise RuntimeError("dp_connect: gather_bytes must return one 64-byte handle per rank")
+        buf = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles))
+        self._ck(self.L.vhap_dp_connect(self.ctx, buf))
+        self._peer_slab = world > 1
+
+    def dp_status(self) -> int:
+        out = C.c_int32(0)
+        self._ck(self.L.vhap_dp_status(self.ctx, C.byref(out)))
+        return out.value
+
     def set_loss_mask(self, mask):
         """test hook: [B,H,W] bool/uint8 (image orientation like sample['rgb']); False = pixel left out of the L1 photometric sum."""
         if mask is None:
@@ -365,7 +383,7 @@ class Engine:
         gB = batch.B if global_B is None else global_B
         self._ck(self.L.vhap_energy_forward(self.ctx, C.byref(cp), C.byref(batch.c), C.byref(cs), self.slab_local.data_ptr(), s), None)
         gslab = self.slab_local                        # single process: the local slab IS the global one (no copy kernel on the critical chain)
-        if reduce_fn is not None:
+        if reduce_fn is not None and not self._peer_slab:      # (peer mailboxes: the two kernels exchange the slab themselves, dp_connect)
             reduce_fn(self.slab_local, self.slab_global)
             gslab = self.slab_global
         self._ck(self.L.vhap_energy_backward(self.ctx, C.byref(cp), C.byref(batch.c), C.byref(cs), gslab.data_ptr(),

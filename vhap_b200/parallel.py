@@ -97,13 +97,23 @@ class LocalShardComm:
 class DataParallelStep:
     """Wraps an Engine: step(batch) = zero_grad, forward, slab reduce, backward, grad allreduce, Adam."""
 
-    def __init__(self, engine, group=None, texture="shard"):
+    def __init__(self, engine, group=None, texture="shard", slab="peer"):
         """texture: "shard" (default: reduce-scatter -> 1/world Adam -> all-gather, TexShardComm on its own communicator) or "allreduce"
-        (round-1 baseline: dense all-reduce of the regularised gradient, full-texture Adam on every rank)"""
+        (round-1 baseline: dense all-reduce of the regularised gradient, full-texture Adam on every rank).
+        slab: "peer" (default: the mid-step batch-global scalars travel through CUDA-IPC mailboxes written / read by the engine's own
+        kernels over NVLink, Engine.dp_connect) or "nccl" (round-1 baseline: an all-gather + host-side reduction between the halves)"""
         self.e, self.group = engine, group
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         self._gB = {}
         self.tex_comm = None
+        self.peer_slab = False
+        if self.world > 1 and slab == "peer" and hasattr(engine, "dp_connect"):
+            def gather(b):
+                out = [None] * self.world
+                dist.all_gather_object(out, b, group=group)
+                return out
+            engine.dp_connect(dist.get_rank(group), self.world, gather)
+            self.peer_slab = True
         if self.world > 1 and texture == "shard":
             ranks = dist.get_process_group_ranks(group) if group is not None else None
             self.tex_comm = TexShardComm(dist.new_group(ranks=ranks))
@@ -124,14 +134,14 @@ class DataParallelStep:
         e = self.e
         e.zero_grad()
         gB = self.global_B(batch)
-        red = (lambda a, b: reduce_forward_slab(a, b, self.group)) if self.world > 1 else None
+        red = (lambda a, b: reduce_forward_slab(a, b, self.group)) if (self.world > 1 and not self.peer_slab) else None
         e.energy(batch, backward=True, training=True, global_B=gB, reduce_fn=red)
         e.adam_step(allreduce_fn=(lambda t: allreduce_sum(t, self.group)) if self.world > 1 else None, tex_comm=self.tex_comm)
 
     def graph_begin(self, batches, pipelined=True):
         """Engine.graph_begin with this group's collectives captured into the step graphs (pipelined: the texture all-reduce of step k
         runs at the start of step k+1, hidden behind FLAME / rasteriser / pools)"""
-        red = (lambda a, b: reduce_forward_slab(a, b, self.group)) if self.world > 1 else None
+        red = (lambda a, b: reduce_forward_slab(a, b, self.group)) if (self.world > 1 and not self.peer_slab) else None
         allr = (lambda t: allreduce_sum(t, self.group)) if self.world > 1 else None
         gBs = [self.global_B(b) for b in batches]            # host-side collectives: before the capture
         self.e.graph_begin(batches, reduce_fn=red, allreduce_fn=allr, world=self.world, pipelined=pipelined, global_Bs=gBs, tex_comm=self.tex_comm)
@@ -140,7 +150,7 @@ class DataParallelStep:
         e = self.e
         e.zero_grad()
         gB = self.global_B(batch)
-        red = (lambda a, b: reduce_forward_slab(a, b, self.group)) if self.world > 1 else None
+        red = (lambda a, b: reduce_forward_slab(a, b, self.group)) if (self.world > 1 and not self.peer_slab) else None
         losses = e.energy(batch, backward=True, training=True, global_B=gB, reduce_fn=red)
         e.adam_step(allreduce_fn=(lambda t: allreduce_sum(t, self.group)) if self.world > 1 else None, tex_comm=self.tex_comm)
         e.global_step += 1
