@@ -82,6 +82,12 @@ typedef struct vhap_frame_batch {
   const float*   lmk2d;        /* [B,68,3] (x_px,y_px,conf)  sample["lmk2d"] (tracker.py:358) */
   const float*   RT;           /* [B,3,4] or NULL = [I|(0,0,-1)] (tracker.py:1335-1337) */
   const float*   K;            /* [B,4]=(fx,fy,cx,cy) or NULL = from focal_length (tracker.py:141-157) */
+  /* optional view sharing (calibrated multi-view batches: all cameras of one timestep carry the SAME FLAME parameters, tracker.py:213-235
+   * evaluates FLAME once per frame anyway): geometry is evaluated once per distinct timestep and only projected per view.
+   * geo[b] = index of frame b's timestep in geo_timesteps[n_geo]; NULL = every frame its own geometry. */
+  const int32_t* geo;          /* [B] device or NULL */
+  const int32_t* geo_timesteps;/* [n_geo] device */
+  int32_t n_geo;
 } vhap_frame_batch;
 
 /* Loss weights and stage switches (vhap/config/base.py:126-195, :215-295).  A negative weight = term disabled (None). */

@@ -32,7 +32,7 @@ def test_abi_version_and_struct_sizes(so):
     L = _lib.lib()
     assert L.vhap_abi_version() == 2
     assert ctypes.sizeof(_lib.StageCfg) == 176
-    assert ctypes.sizeof(_lib.FrameBatch) == 56
+    assert ctypes.sizeof(_lib.FrameBatch) == 80
 
 
 def test_sass_is_sm100(so):

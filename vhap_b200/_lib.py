@@ -38,7 +38,7 @@ class Grads(C.Structure):
 
 class FrameBatch(C.Structure):
     _fields_ = [("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("target_format", C.c_int32), ("timesteps", C.c_void_p), ("target", C.c_void_p), ("lmk2d", C.c_void_p),
-                ("RT", C.c_void_p), ("K", C.c_void_p)]
+                ("RT", C.c_void_p), ("K", C.c_void_p), ("geo", C.c_void_p), ("geo_timesteps", C.c_void_p), ("n_geo", C.c_int32)]
 
 
 class StageCfg(C.Structure):

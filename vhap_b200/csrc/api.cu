@@ -279,6 +279,7 @@ static int check_batch(vhap_ctx* ctx, const vhap_frame_batch* fb) {
     return -4;
   }
   if (fb->target_format != 0 && fb->target_format != 1) { vh_set_error(ctx, "batch", "unknown target_format"); return -4; }
+  if (fb->geo && (fb->n_geo < 1 || fb->n_geo > fb->B || !fb->geo_timesteps)) { vh_set_error(ctx, "batch", "view sharing: n_geo / geo_timesteps inconsistent"); return -4; }
   ctx->curB = fb->B; ctx->curH = fb->H; ctx->curW = fb->W;
   return 0;
 }
@@ -434,9 +435,9 @@ extern "C" int vhap_energy_forward(vhap_ctx* ctx, const vhap_params* p, const vh
     if (vn_overlap) {
       cudaEventRecord(ctx->ev[EV_VN_FORK], s);
       cudaStreamWaitEvent(ctx->aux[0], ctx->ev[EV_VN_FORK], 0);
-      launch_vnormals(ctx, fb->B, ctx->aux[0]);
+      launch_vnormals(ctx, fb->geo ? fb->n_geo : fb->B, ctx->aux[0]);
       cudaEventRecord(ctx->ev[EV_VN_DONE], ctx->aux[0]);
-    } else launch_vnormals(ctx, fb->B, s);
+    } else launch_vnormals(ctx, fb->geo ? fb->n_geo : fb->B, s);
     launch_raster(ctx, ctx->clip, ctx->snap, fb->B, fb->H, fb->W, ctx->tri_id, 0, 0, s);
     if (vn_overlap) cudaStreamWaitEvent(s, ctx->ev[EV_VN_DONE], 0);
     PassArgs P;
@@ -492,7 +493,7 @@ extern "C" int vhap_energy_backward(vhap_ctx* ctx, const vhap_params* p, const v
       // machine-filling streaming kernel.  Put the chain on a highest-priority stream so its CTAs are scheduled ahead of the
       // bulk kernel's remaining CTAs instead of queueing behind all of them.
       if (!ctx->no_overlap) { gs = ctx->hp[0]; cudaStreamWaitEvent(gs, ctx->ev[EV_TEXGRAD_READY], 0); }
-      launch_vnormals_bwd(ctx, fb->B, gs);
+      launch_vnormals_bwd(ctx, fb->geo ? fb->n_geo : fb->B, gs);
     }
   }
   if (g && lmk && regs_forked) cudaStreamWaitEvent(gs, ctx->ev[EV_LMK_DONE], 0);      // the skinning adjoint reads the landmark term's vertex gradients

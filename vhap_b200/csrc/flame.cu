@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(128) k_skin_fwd(const float* __restrict__ v_pa
     float* o = v_posed + (size_t)b * M + 3 * v; o[0] = vp[i][0]; o[1] = vp[i][1]; o[2] = vp[i][2];
     f4 vw = {x, y, z, 1.f};
     verts[(size_t)b * V + v] = vw;
+    if (!cam) continue;                           // view sharing: projected per view by k_project_views
     CamParams c = cam[b];
     float cx_ = c.RT[0] * x + c.RT[1] * y + c.RT[2] * z + c.RT[3];
     float cy_ = c.RT[4] * x + c.RT[5] * y + c.RT[6] * z + c.RT[7];
@@ -196,6 +197,63 @@ __global__ void __launch_bounds__(128) k_skin_fwd(const float* __restrict__ v_pa
   }
 }
 
+// view sharing: clip positions, raster snap and NDC of view b from the world vertices of its geometry geo[b] (the projection half of
+// k_skin_fwd, identical arithmetic)
+__global__ void __launch_bounds__(128) k_project_views(const f4* __restrict__ verts, const int* __restrict__ geo, const CamParams* __restrict__ cam, int V, int H, int W,
+                                                        f4* __restrict__ clip, i4* __restrict__ snap, float* __restrict__ ndc) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (v >= V) return;
+  f4 vw = verts[(size_t)geo[b] * V + v];
+  float x = vw.x, y = vw.y, z = vw.z;
+  CamParams c = cam[b];
+  float cx_ = c.RT[0] * x + c.RT[1] * y + c.RT[2] * z + c.RT[3];
+  float cy_ = c.RT[4] * x + c.RT[5] * y + c.RT[6] * z + c.RT[7];
+  float cz_ = c.RT[8] * x + c.RT[9] * y + c.RT[10] * z + c.RT[11];
+  Proj P = make_proj(c, H, W);
+  f4 cl = {P.p00 * cx_ + P.p02 * cz_, P.p11 * cy_ + P.p12 * cz_, P.p22 * cz_ + P.p23, -cz_};
+  clip[(size_t)b * V + v] = cl;
+  bool valid = isfinite(cl.x) && isfinite(cl.y) && isfinite(cl.z) && isfinite(cl.w) && cl.w > 0.f;
+  i4 sn = {0, 0, 0, 0};
+  if (valid) {
+    float sx = __fmul_rn(__fdiv_rn(cl.x, cl.w), (float)(W * 8));
+    float sy = __fmul_rn(__fdiv_rn(cl.y, cl.w), (float)(H * 8));
+    sx = fminf(fmaxf(sx, -SNAP_GUARD), SNAP_GUARD); sy = fminf(fmaxf(sy, -SNAP_GUARD), SNAP_GUARD);
+    sn.x = __float2int_rn(sx); sn.y = __float2int_rn(sy);
+    sn.z = __float_as_int(__fdiv_rn(cl.z, cl.w)); sn.w = 1;
+  }
+  snap[(size_t)b * V + v] = sn;
+  ndc[((size_t)b * V + v) * 2] = cl.x / cl.w; ndc[((size_t)b * V + v) * 2 + 1] = cl.y / cl.w;
+}
+// adjoint: g_verts[geo[b]] += (d clip_b / d world)^T g_clip[b]; focal-length terms into acc (uncalibrated cameras)
+__global__ void __launch_bounds__(128) k_project_views_bwd(const f4* __restrict__ verts, const int* __restrict__ geo, const CamParams* __restrict__ cam, const float* __restrict__ g_clip,
+                                                            int V, int H, int W, int opt_cam, float* __restrict__ g_verts, float* __restrict__ acc) {
+  __shared__ float shr[33];
+  int v = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  float gfx = 0.f, gfy = 0.f;
+  if (v < V) {
+    const float* gc = g_clip + ((size_t)b * V + v) * 4;
+    float gcx = gc[0], gcy = gc[1], gcz = gc[2], gcw = gc[3];
+    if (gcx != 0.f || gcy != 0.f || gcz != 0.f || gcw != 0.f) {
+      CamParams c = cam[b];
+      Proj P = make_proj(c, H, W);
+      const int g = geo[b];
+      f4 x = verts[(size_t)g * V + v];
+      float cx_ = c.RT[0] * x.x + c.RT[1] * x.y + c.RT[2] * x.z + c.RT[3];
+      float cy_ = c.RT[4] * x.x + c.RT[5] * x.y + c.RT[6] * x.z + c.RT[7];
+      float g_cx = P.p00 * gcx, g_cy = P.p11 * gcy, g_cz = P.p02 * gcx + P.p12 * gcy + P.p22 * gcz - gcw;
+      gfx = gcx * cx_ * (2.f / W); gfy = gcy * cy_ * (2.f / H);
+      float* o = g_verts + ((size_t)g * V + v) * 4;
+      atomicAdd(o + 0, c.RT[0] * g_cx + c.RT[4] * g_cy + c.RT[8] * g_cz);
+      atomicAdd(o + 1, c.RT[1] * g_cx + c.RT[5] * g_cy + c.RT[9] * g_cz);
+      atomicAdd(o + 2, c.RT[2] * g_cx + c.RT[6] * g_cy + c.RT[10] * g_cz);
+    }
+  }
+  if (opt_cam) {
+    float s1 = block_sum(gfx, shr), s2 = block_sum(gfy, shr);
+    if (threadIdx.x == 0) { atomicAdd(acc + ACC_GFX, s1); atomicAdd(acc + ACC_GFY, s2); }
+  }
+}
+
 #ifndef VH_SKIN_NB
 #define VH_SKIN_NB 2          // frames per CTA in the skinning kernel: 2 fills the machine at B=16 (8 left 82 CTAs for 148 SMs)
 #endif
@@ -207,14 +265,18 @@ __global__ void k_betas_gather(const float* __restrict__ shape, const float* __r
 }
 
 void launch_flame_forward(vhap_ctx* c, const vhap_params* p, const vhap_frame_batch* fb, cudaStream_t s) {
-  int B = fb->B, V = c->V, M = 3 * V;
+  // view sharing (fb->geo): FLAME runs once per distinct timestep (G geometries), the B views are only projected
+  const bool shared = fb->geo != nullptr;
+  const int nviews = fb->B;
+  const int* ts = shared ? fb->geo_timesteps : fb->timesteps;
+  int B = shared ? fb->n_geo : fb->B, V = c->V, M = 3 * V;
   // the joint / pose chain (latency-bound, one block per frame) only meets the blend shapes again in the skinning kernel: it runs
   // on an aux stream beside the tensor-core contraction
   const bool fork = !c->no_overlap;
   cudaStream_t sp = fork ? c->aux[0] : s;
-  LAUNCH(c, KID_POSE_FWD, s, k_betas_gather<<<B, 128, 0, s>>>(p->shape, p->expr, fb->timesteps, c->K, c->n_shape, c->betas));
+  LAUNCH(c, KID_POSE_FWD, s, k_betas_gather<<<B, 128, 0, s>>>(p->shape, p->expr, ts, c->K, c->n_shape, c->betas));
   if (fork) { cudaEventRecord(c->ev[EV_POSE_FORK], s); cudaStreamWaitEvent(sp, c->ev[EV_POSE_FORK], 0); }
-  LAUNCH(c, KID_POSE_FWD, sp, k_pose_fwd<<<B, 256, 0, sp>>>(p->shape, p->expr, p->rotation, p->neck_pose, p->jaw_pose, p->eyes_pose, p->static_offset, fb->timesteps,
+  LAUNCH(c, KID_POSE_FWD, sp, k_pose_fwd<<<B, 256, 0, sp>>>(p->shape, p->expr, p->rotation, p->neck_pose, p->jaw_pose, p->eyes_pose, p->static_offset, ts,
                                c->JS, c->Jt, c->Jreg, V, c->K, c->n_shape, nullptr, c->posebuf, c->poses));
   if (fork) cudaEventRecord(c->ev[EV_POSE_DONE], sp);
   int ks = BLEND_KS;
@@ -229,8 +291,12 @@ void launch_flame_forward(vhap_ctx* c, const vhap_params* p, const vhap_frame_ba
   }
   if (fork) cudaStreamWaitEvent(s, c->ev[EV_POSE_DONE], 0);
   dim3 g2((V + 127) / 128, (B + VH_SKIN_NB - 1) / VH_SKIN_NB);
-  LAUNCH(c, KID_SKIN_FWD, s, k_skin_fwd<VH_SKIN_NB><<<g2, 128, 0, s>>>(vpart, ks, c->v_shaped, c->posedirs, c->lbs_w, c->posebuf, p->translation, fb->timesteps, c->cam, V, B, fb->H, fb->W,
+  LAUNCH(c, KID_SKIN_FWD, s, k_skin_fwd<VH_SKIN_NB><<<g2, 128, 0, s>>>(vpart, ks, c->v_shaped, c->posedirs, c->lbs_w, c->posebuf, p->translation, ts, shared ? nullptr : c->cam, V, B, fb->H, fb->W,
                                    c->v_posed, c->verts, c->clip, c->snap, c->ndc));
+  if (shared) {
+    dim3 g3((V + 127) / 128, nviews);
+    LAUNCH(c, KID_SKIN_FWD, s, k_project_views<<<g3, 128, 0, s>>>(c->verts, fb->geo, c->cam, V, fb->H, fb->W, c->clip, c->snap, c->ndc));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ landmarks
@@ -240,13 +306,14 @@ __global__ void __launch_bounds__(96) k_landmarks(const f4* __restrict__ verts, 
                                                   const float* __restrict__ lmk_bary, const float* __restrict__ lmk2d, const CamParams* __restrict__ cam,
                                                   int V, int n_lmk, int H, int W, float w_scale, int jawline_off, int compute_loss, int opt_cam,
                                                   float* __restrict__ lmks_out, const float* __restrict__ g_lmk_in, float* __restrict__ g_verts,
-                                                  float* __restrict__ acc) {
+                                                  float* __restrict__ acc, const int* __restrict__ geo) {
   __shared__ float sh[33];
   int b = blockIdx.x, l = threadIdx.x;
+  const int gb = geo ? geo[b] : b;               // geometry of this view
   float loss = 0.f, gfx = 0.f, gfy = 0.f;
   if (l < n_lmk) {
     i4 f = faces[lmk_faces[l]];
-    const f4* vb = verts + (size_t)b * V;
+    const f4* vb = verts + (size_t)gb * V;
     f4 a = vb[f.x], c1 = vb[f.y], d = vb[f.z];
     float b0 = lmk_bary[l * 3], b1 = lmk_bary[l * 3 + 1], b2 = lmk_bary[l * 3 + 2];
     float x = a.x * b0 + c1.x * b1 + d.x * b2, y = a.y * b0 + c1.y * b1 + d.y * b2, z = a.z * b0 + c1.z * b1 + d.z * b2;
@@ -280,7 +347,7 @@ __global__ void __launch_bounds__(96) k_landmarks(const f4* __restrict__ verts, 
       gz += c.RT[2] * g_cx + c.RT[6] * g_cy + c.RT[10] * g_cz;
     }
     if (g_verts && (gx != 0.f || gy != 0.f || gz != 0.f)) {
-      float* gv = g_verts + (size_t)b * V * 4;
+      float* gv = g_verts + (size_t)gb * V * 4;
       const int vid[3] = {f.x, f.y, f.z};
       const float bb[3] = {b0, b1, b2};
       for (int k = 0; k < 3; ++k) {
@@ -298,7 +365,7 @@ void launch_landmarks(vhap_ctx* c, const vhap_frame_batch* fb, float w_scale, in
                       int compute_loss, int opt_cam, int global_B, cudaStream_t s) {
   (void)global_B;
   LAUNCH(c, KID_LMK, s, k_landmarks<<<fb->B, 96, 0, s>>>(c->verts, c->faces, c->lmk_faces, c->lmk_bary, fb->lmk2d, c->cam, c->V, c->n_lmk, fb->H, fb->W, w_scale, jawline_off,
-                                   compute_loss, opt_cam, lmks_out, g_lmk_in, c->g_verts, c->acc));
+                                   compute_loss, opt_cam, lmks_out, g_lmk_in, c->g_verts, c->acc, fb->geo));
 }
 
 // ------------------------------------------------------------------------------------------------ vertex normals
@@ -385,8 +452,8 @@ __global__ void __launch_bounds__(128) k_skin_bwd(const float* __restrict__ v_po
     if (on) {
       const float* gv = g_verts + ((size_t)b * V + v) * 4;
       g[0] = gv[0]; g[1] = gv[1]; g[2] = gv[2];
-      const float* gc = g_clip + ((size_t)b * V + v) * 4;
-      float gcx = gc[0], gcy = gc[1], gcz = gc[2], gcw = gc[3];
+      float gcx = 0.f, gcy = 0.f, gcz = 0.f, gcw = 0.f;
+      if (g_clip) { const float* gc = g_clip + ((size_t)b * V + v) * 4; gcx = gc[0]; gcy = gc[1]; gcz = gc[2]; gcw = gc[3]; }   // (view sharing: already in g_verts)
       if (gcx != 0.f || gcy != 0.f || gcz != 0.f || gcw != 0.f) {
         CamParams c = cam[b];
         Proj P = make_proj(c, H, W);
@@ -525,11 +592,17 @@ __global__ void k_betas_scatter(const float* __restrict__ gbetas, const int* __r
 }
 
 void launch_flame_backward(vhap_ctx* c, const vhap_params* p, const vhap_frame_batch* fb, const vhap_grads* g, int opt_cam, cudaStream_t s) {
-  int B = fb->B, V = c->V, M = 3 * V;
+  const bool shared = fb->geo != nullptr;
+  const int* ts = shared ? fb->geo_timesteps : fb->timesteps;
+  int B = shared ? fb->n_geo : fb->B, V = c->V, M = 3 * V;
   bool need_betas = g->shape || g->expr;
+  if (shared) {                                   // projection adjoint of every view into its geometry's world-space gradient
+    dim3 g0((V + 127) / 128, fb->B);
+    LAUNCH(c, KID_SKIN_BWD, s, k_project_views_bwd<<<g0, 128, 0, s>>>(c->verts, fb->geo, c->cam, c->g_clip, V, fb->H, fb->W, opt_cam, c->g_verts, c->acc));
+  }
   dim3 g1((V + 127) / 128, (B + 1) / 2);
-  LAUNCH(c, KID_SKIN_BWD, s, k_skin_bwd<2><<<g1, 128, 0, s>>>(c->v_posed, c->verts, c->posedirs, c->lbs_w, c->posebuf, c->cam, fb->timesteps, c->g_verts, c->g_clip, V, B, fb->H, fb->W,
-                                   opt_cam, c->Mpad, c->g_vshaped, g->static_offset, g->translation, c->gA, c->gpf, c->acc));
+  LAUNCH(c, KID_SKIN_BWD, s, k_skin_bwd<2><<<g1, 128, 0, s>>>(c->v_posed, c->verts, c->posedirs, c->lbs_w, c->posebuf, c->cam, ts, c->g_verts, shared ? nullptr : c->g_clip, V, B, fb->H, fb->W,
+                                   shared ? 0 : opt_cam, c->Mpad, c->g_vshaped, g->static_offset, g->translation, c->gA, c->gpf, c->acc));
   // the blend-shape adjoint (tensor-core contraction of g_vshaped) only needs skin_bwd's output: it runs beside the serial
   // pose_bwd -> joff_bwd pair on the second high-priority stream; both add into gbetas atomically
   bool forked = need_betas && s == c->hp[0];
@@ -543,12 +616,12 @@ void launch_flame_backward(vhap_ctx* c, const vhap_params* p, const vhap_frame_b
     }
     if (forked) cudaEventRecord(c->ev[EV_BLEND_DONE], s2);
   }
-  LAUNCH(c, KID_POSE_BWD, s, k_pose_bwd<<<B, 128, 0, s>>>(c->poses, c->posebuf, c->gA, c->gpf, fb->timesteps, c->JS, c->K, g->rotation, g->neck_pose, g->jaw_pose, g->eyes_pose,
+  LAUNCH(c, KID_POSE_BWD, s, k_pose_bwd<<<B, 128, 0, s>>>(c->poses, c->posebuf, c->gA, c->gpf, ts, c->JS, c->K, g->rotation, g->neck_pose, g->jaw_pose, g->eyes_pose,
                                c->gJ, need_betas ? c->gbetas : nullptr));
   if (g->static_offset) LAUNCH(c, KID_JOFF_BWD, s, k_joff_bwd<<<(V + 127) / 128, 128, 0, s>>>(c->Jreg, c->gJ, V, B, g->static_offset));
   if (need_betas) {
     if (forked) cudaStreamWaitEvent(s, c->ev[EV_BLEND_DONE], 0);
-    LAUNCH(c, KID_BETAS_SCATTER, s, k_betas_scatter<<<B, 256, 0, s>>>(c->gbetas, fb->timesteps, c->K, c->n_shape, g->shape, g->expr));
+    LAUNCH(c, KID_BETAS_SCATTER, s, k_betas_scatter<<<B, 256, 0, s>>>(c->gbetas, ts, c->K, c->n_shape, g->shape, g->expr));
   }
   (void)p;
 }

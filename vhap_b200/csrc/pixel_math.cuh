@@ -25,6 +25,7 @@ struct RenderArgs {
   const float* ndc;           // optional [B,V,2] = clip.xy / clip.w (saves the divisions in the antialias analysis)
   const float* zwbuf;         // optional [B,H,W,4]: .w of foreground pixels holds their z/w (written by pass A)
   int* tex_l0_flag;           // optional [regions]: raised where the backward scatters into level 0 of the texel-gradient pyramid
+  const int* geo;             // optional [B]: view sharing, frame b uses the vertex normals of geometry geo[b] (clip positions stay per view)
   int pow2, wshift, hshift;   // pow2 != 0: W = 1 << wshift, H = 1 << hshift (pixel index -> (b,y,x) without integer divisions)
 };
 
@@ -283,7 +284,7 @@ struct PixShade {
 
 VH_HD void shade_pixel(const RenderArgs& A, int b, int px, int py, int tri, PixShade& s) {
   tri_setup(A, b, px, py, tri, s.ts);
-  const f4* vn = A.vnorm + (size_t)b * A.V;
+  const f4* vn = A.vnorm + (size_t)(A.geo ? A.geo[b] : b) * A.V;
   f4 a = vn[s.ts.vi[0]], c = vn[s.ts.vi[1]], d = vn[s.ts.vi[2]];
   s.n0 = mk3(a.x, a.y, a.z); s.n1 = mk3(c.x, c.y, c.z); s.n2 = mk3(d.x, d.y, d.z);
   float b0 = s.ts.b0, b1 = s.ts.b1, b2 = 1.f - b0 - b1;
@@ -330,7 +331,7 @@ VH_HD void shade_pixel_bwd(const RenderArgs& A, int b, int tri, const PixShade& 
   float b0 = s.ts.b0, b1 = s.ts.b1, b2 = 1.f - b0 - b1;
   if (vg) { vg->gn[0] = g_raw * b0; vg->gn[1] = g_raw * b1; vg->gn[2] = g_raw * b2; }
   else if (g_vnorm) {
-    float* gv = g_vnorm + (size_t)b * A.V * 4;
+    float* gv = g_vnorm + (size_t)(A.geo ? A.geo[b] : b) * A.V * 4;
     const f3 gg[3] = {g_raw * b0, g_raw * b1, g_raw * b2};
     for (int k = 0; k < 3; ++k) {
       float* t = gv + (size_t)s.ts.vi[k] * 4;

@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(VH_C2_PB, VH_C2_MINBLOCKS) k_passC2(PassArgs P
     if (on && head) {
       const i4 f = A.faces[id - 1];
       const int vi[3] = {f.x, f.y, f.z};
-      float* gv = P.g_vnorm + (size_t)b * A.V * 4;
+      float* gv = P.g_vnorm + (size_t)(A.geo ? A.geo[b] : b) * A.V * 4;
       float* gc = P.g_clip + (size_t)b * A.V * 4;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
@@ -416,6 +416,7 @@ void fill_render_args(vhap_ctx* c, PassArgs& P, const vhap_frame_batch* fb, cons
   A.faces = c->faces; A.faces_uv = c->faces_uv; A.verts_uv = c->verts_uv; A.clip = c->clip; A.vnorm = c->vnorm; A.lights = lights;
   A.mips = c->mips[c->cur_mip];
   for (int i = 0; i < VH_MAX_MIPS; ++i) A.mip_off[i] = c->mip_off[i];
+  A.geo = fb->geo;
   A.tri_id = c->tri_id; A.face_flags = cfg->training ? c->face_flags : nullptr; A.vert_flags = cfg->training ? c->vert_flags : nullptr;
   A.fid2cid = c->fid2cid; A.adj_opp = c->adj_opp; A.ndc = c->ndc; A.zwbuf = (const float*)c->pre; A.tex_l0_flag = c->tex_l0_flag;
   P.target = (const uint16_t*)fb->target; P.target_u8 = fb->target_format == 1; P.pre = c->pre; P.signs = c->signs;

@@ -25,11 +25,13 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 class Batch:
     """One staged batch of frames (the reference's `sample` dict, video_dataset.py:209-241)."""
 
-    def __init__(self, B, H, W, timesteps, target, lmk2d, RT=None, K=None):
+    def __init__(self, B, H, W, timesteps, target, lmk2d, RT=None, K=None, geo=None, geo_ts=None):
         self.B, self.H, self.W = B, H, W
         self.timesteps, self.target, self.lmk2d, self.RT, self.K = timesteps, target, lmk2d, RT, K
+        self.geo, self.geo_ts = geo, geo_ts              # view sharing (see vhap_frame_batch): FLAME once per distinct timestep
         fmt = 1 if (target is not None and target.dtype == torch.uint8) else 0      # uint8 RGB as decoded / fp16 RGBA
-        self.c = _lib.FrameBatch(B, H, W, fmt, _ptr(timesteps), _ptr(target), _ptr(lmk2d), _ptr(RT), _ptr(K))
+        self.c = _lib.FrameBatch(B, H, W, fmt, _ptr(timesteps), _ptr(target), _ptr(lmk2d), _ptr(RT), _ptr(K), _ptr(geo), _ptr(geo_ts),
+                                 0 if geo_ts is None else int(geo_ts.numel()))
 
 
 class Engine:
@@ -279,7 +281,7 @@ class Engine:
         return s
 
     # ------------------------------------------------------------------ input staging
-    def stage_sample(self, rgb, lmk2d, timesteps, RT=None, K=None, non_blocking=True) -> Batch:
+    def stage_sample(self, rgb, lmk2d, timesteps, RT=None, K=None, non_blocking=True, share_views=None) -> Batch:
         """rgb: [B,3,H,W] float (host or device, like sample['rgb']) or an already packed [B,H,W,4] fp16 tensor
         (host pinned memory for the end-to-end path).  Returns device-resident Batch."""
         if rgb.dtype == torch.uint8:
@@ -328,7 +330,17 @@ class Engine:
                 raise ValueError(f"K has {Kd.shape[0]} rows for a batch of {B}")
             Kd = Kd.to(self.dev).contiguous()
         self.reserve(B, H, W)
-        return Batch(B, H, W, ts, tgt, lm, RTd, Kd)
+        # view sharing: several cameras of one timestep (NeRSemble: all 16 views of a batch) share one FLAME evaluation.  Default: on
+        # whenever timesteps repeat inside a batch with per-frame cameras; the arithmetic per view is unchanged (tests/test_gpu_views.py)
+        geo = geo_ts = None
+        tsn = np.asarray(timesteps).reshape(-1)
+        uniq, inv = np.unique(tsn, return_inverse=True)
+        if share_views is None:
+            share_views = RTd is not None and len(uniq) < B
+        if share_views and len(uniq) < B:
+            geo = torch.as_tensor(inv.astype(np.int32)).to(self.dev)
+            geo_ts = torch.as_tensor(uniq.astype(np.int32)).to(self.dev)
+        return Batch(B, H, W, ts, tgt, lm, RTd, Kd, geo, geo_ts)
 
     def dp_connect(self, rank: int, world: int, gather_bytes) -> None:
         """data parallel: map every rank's slab mailbox over NVLink (CUDA IPC).  `gather_bytes(b)` returns the list of every rank's bytes

@@ -43,7 +43,7 @@ class _FlameFn(torch.autograd.Function):
                     translation=f32(translation), off=f32(static_offset))
         ts = torch.arange(B, dtype=torch.int32, device=eng.dev)
         eng.reserve(max(B, 1), 16, 16)
-        fb = _lib.FrameBatch(B, 16, 16, 0, ts.data_ptr(), None, None, None, None)
+        fb = _lib.FrameBatch(B, 16, 16, 0, ts.data_ptr(), None, None, None, None, None, None, 0)
         p = _lib.Params(_ptr(tens["shape"]), _ptr(tens["expr"]), _ptr(tens["rotation"]), _ptr(tens["neck"]), _ptr(tens["jaw"]), _ptr(tens["eyes"]),
                         _ptr(tens["translation"]), _ptr(tens["off"]), _ptr(eng.p["lights"]), _ptr(eng.p["focal_length"]), None, B)
         verts = torch.empty(B, eng.V, 3, device=eng.dev); cano = torch.empty(B, eng.V, 3, device=eng.dev); lmks = torch.empty(B, 70, 3, device=eng.dev)
@@ -58,7 +58,7 @@ class _FlameFn(torch.autograd.Function):
         z = lambda like: torch.zeros_like(like)
         g = dict(shape=z(t["shape"]), expr=z(t["expr"]), rotation=z(t["rotation"]), neck=z(t["neck"]), jaw=z(t["jaw"]), eyes=z(t["eyes"]),
                  translation=z(t["translation"]), off=z(t["off"]) if ctx.has_off else None)
-        fb = _lib.FrameBatch(B, 16, 16, 0, ctx.ts.data_ptr(), None, None, None, None)
+        fb = _lib.FrameBatch(B, 16, 16, 0, ctx.ts.data_ptr(), None, None, None, None, None, None, 0)
         p = _lib.Params(_ptr(t["shape"]), _ptr(t["expr"]), _ptr(t["rotation"]), _ptr(t["neck"]), _ptr(t["jaw"]), _ptr(t["eyes"]),
                         _ptr(t["translation"]), _ptr(t["off"]), _ptr(eng.p["lights"]), _ptr(eng.p["focal_length"]), None, B)
         cg = _lib.Grads(_ptr(g["shape"]), _ptr(g["expr"]), _ptr(g["rotation"]), _ptr(g["neck"]), _ptr(g["jaw"]), _ptr(g["eyes"]), _ptr(g["translation"]),

@@ -21,6 +21,10 @@ def pin_sample(rgb, lmk2d, timesteps, RT=None, K=None) -> Dict[str, torch.Tensor
         raise ValueError("pin_sample: rgb must be uint8 [B,H,W,3] or fp16 [B,H,W,4]")
     out = dict(rgb=t.contiguous().pin_memory(), lmk2d=torch.as_tensor(np.asarray(lmk2d), dtype=torch.float32)[:, :68].contiguous().pin_memory(),
                ts=torch.as_tensor(np.asarray(timesteps), dtype=torch.int32).pin_memory(), RT=RT, K=K)
+    # view sharing (Engine.stage_sample): distinct timesteps of the batch + the inverse map, staged with the sample
+    uniq, inv = np.unique(np.asarray(timesteps).reshape(-1), return_inverse=True)
+    out["geo_ts"] = torch.as_tensor(uniq.astype(np.int32)).pin_memory()
+    out["geo"] = torch.as_tensor(inv.astype(np.int32)).pin_memory()
     return out
 
 
@@ -57,6 +61,11 @@ class InputRing:
             bt.target.copy_(sample["rgb"], non_blocking=True)
             bt.lmk2d.copy_(sample["lmk2d"], non_blocking=True)
             bt.timesteps.copy_(sample["ts"], non_blocking=True)
+            if bt.geo is not None:                       # view sharing: the slot's geometry map follows the new timesteps
+                if sample["geo_ts"].numel() != bt.geo_ts.numel():
+                    raise ValueError("InputRing.prefetch: the number of distinct timesteps differs from the slot's")
+                bt.geo.copy_(sample["geo"], non_blocking=True)
+                bt.geo_ts.copy_(sample["geo_ts"], non_blocking=True)
             self.ready[j].record(self.copy_stream)
 
     def acquire(self, j: int):
