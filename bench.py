@@ -240,7 +240,7 @@ def measure(args, config, size, B, full):
     if use_graph:
         eng.graph_end()
     name = {"monocular": f"monocular {size}x{size} batch_size={B}", "nersemble": f"nersemble {B} views {H}x{W} single timestep"}[config]
-    res = {"name": name, "value": round(gB * steps / (ms * 1e-3), 2), "ms_per_step": round(ms / steps, 4), "steps": steps, "global_batch": gB, "image": [H, W],
+    res = {"name": name, "dp_texture_mode": dp.texture_mode, "value": round(gB * steps / (ms * 1e-3), 2), "ms_per_step": round(ms / steps, 4), "steps": steps, "global_batch": gB, "image": [H, W],
            "foreground_fraction": round(fg, 3), "clocks": clk, "losses": {k: round(v, 5) for k, v in losses.items() if k in ("total", "photo", "lmk")},
            "e2e": {"value": round(gB * steps / (ms_e2e * 1e-3), 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                    "ms_per_step": round(ms_e2e / steps, 4)}}
@@ -351,8 +351,9 @@ def run_ours(args):
                    "parallelism": (f"dp{world}: one global parameter set, every rank optimises its own {B} distinct frames per step; per step the forward slab exchange ("
                                    + ("peer mailboxes over NVLink, written / read by the engine's own kernels" if args.dp_slab == "peer" else "NCCL all-gather") +
                                    "), one all-reduce (parameter-gradient slab) and the texture update ("
-                                   + ("reduce-scatter of the folded texel gradient by row band -> Adam on 1/N of the texture per rank -> all-gather of the updated rows"
-                                      if args.dp_texture == "shard" else "dense all-reduce of the texel gradient, full-texture Adam on every rank") + ")") if world > 1 else "single GPU",
+                                   + main.get("dp_texture_mode", args.dp_texture) + ": "
+                                   + ("dense all-reduce of the texel gradient, full-texture Adam on every rank" if args.dp_texture == "allreduce" else
+                                      "reduction of the folded texel gradient by row band -> Adam on 1/N of the texture per rank -> broadcast of the updated rows") + ")") if world > 1 else "single GPU",
                    "launch": ("CUDA graph replay (1 graph launch per step" + (", texture update of step k pipelined into the graph of step k+1; the "
                               "timed region holds exactly K complete steps' worth of work: K replays, each = previous step's texture update + this step's "
                               "everything else)" if not args.no_pipeline else ")")) if not args.no_graph else "eager (one launch per kernel)",
@@ -528,8 +529,8 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the other single-GPU workloads (extra_configs)")
-    ap.add_argument("--dp-texture", default="shard", choices=["shard", "allreduce"],
-                    help="data-parallel texture update: reduce-scatter -> 1/N Adam -> all-gather (default) or the round-1 dense all-reduce")
+    ap.add_argument("--dp-texture", default="auto", choices=["auto", "peer", "shard", "allreduce"],
+                    help="data-parallel texture update: peer memory / NVLS (default via auto), NCCL reduce-scatter -> 1/N Adam -> all-gather, or the round-1 dense all-reduce")
     ap.add_argument("--dp-slab", default="peer", choices=["peer", "nccl"],
                     help="mid-step exchange of the batch-global scalars: CUDA-IPC peer mailboxes written by the engine's kernels (default) or an NCCL all-gather")
     ap.add_argument("--no-graph", action="store_true")

@@ -211,7 +211,13 @@ int vhap_tex_apply_grad(vhap_ctx* ctx, float* tex_extra, const float* g_dense, f
  * All ranks must then call vhap_energy_forward / vhap_energy_backward the same number of times. */
 int vhap_dp_init(vhap_ctx* ctx, int32_t rank, int32_t world, unsigned char* handle_out_host /*64 bytes*/);
 int vhap_dp_connect(vhap_ctx* ctx, const unsigned char* handles_host /*[world][64]*/);
-int vhap_dp_status(vhap_ctx* ctx, int32_t* out_host);   /* 0 ok, 1 = a peer did not answer within ~4 s (synchronises) */
+int vhap_dp_status(vhap_ctx* ctx, int32_t* out_host);   /* 0 ok, 1 / 2 = a peer did not answer within ~4 s (slab / texture barrier; synchronises) */
+/* Peer-memory texture update: fold -> barrier -> in-switch reduction of this rank's row band (multimem.ld_reduce through the NVSwitch
+ * multicast mapping; peer loads without one) -> regularisers + Adam on the band -> multicast store of the updated rows to every rank ->
+ * barrier -> pyramid rebuild; no collective library.  g_rm / ex_rm ([T][3][T] floats) are SYMMETRIC buffers allocated by the caller on
+ * every rank: *_ptrs_host = every rank's device pointer (HOST array of `world`), *_multicast = the multicast address or NULL. */
+int vhap_dp_tex_connect(vhap_ctx* ctx, void* const* grm_ptrs_host, void* grm_multicast, void* const* exrm_ptrs_host, void* exrm_multicast);
+int vhap_dp_tex_update(vhap_ctx* ctx, float* tex_extra, float* adam_m, float* adam_v, float lr, int32_t step, const vhap_stage_cfg* cfg, void* stream);
 
 /* ---- sharded texture update (data parallel; the reference has no multi-GPU path): per step
  *   vhap_tex_fold_grad_rm  photometric part of the texel gradient, dense, ROW-MAJOR g_rm[(y*3 + c)*T + x] so that a row band is contiguous

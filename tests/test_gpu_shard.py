@@ -77,9 +77,10 @@ def test_band_adam_rejects_bad_bands():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
-@pytest.mark.parametrize("texture,slab", [("shard", "peer"), ("allreduce", "nccl")])
+@pytest.mark.parametrize("texture,slab", [("peer", "peer"), ("shard", "peer"), ("allreduce", "nccl")])
 def test_two_gpu_data_parallel_equals_single_process(texture, slab):
-    """default path (sharded texture update + peer-mailbox slab exchange) and the round-1 baseline (dense all-reduce + NCCL all-gather)"""
+    """default path (peer-memory / NVLS texture update + peer-mailbox slab exchange), the NCCL reduce-scatter / all-gather variant of the
+    same dataflow, and the round-1 baseline (dense all-reduce + NCCL all-gather)"""
     env = dict(os.environ, VHAP_DP_TEXTURE=texture, VHAP_DP_SLAB=slab)
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29611",
                           str(ROOT / "tools" / "dp_parity.py")], capture_output=True, text=True, timeout=600, env=env, cwd=str(ROOT))

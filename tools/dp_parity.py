@@ -63,7 +63,7 @@ def main():
     sl = slice(rank * Bl, (rank + 1) * Bl)
     mine = e.stage_sample(rgb[sl], sc["lmk2d"][sl], sc["ts"][sl])
     dp = DataParallelStep(e, texture=texture, slab=slab)
-    texture = f"{texture}+{slab}"
+    texture = f"{dp.texture_mode}+{slab}"
     results = {}
     results["eager"] = run(e, lambda: dp.step(mine))
 

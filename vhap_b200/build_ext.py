@@ -8,7 +8,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 SO = Path(os.environ.get("VH_SO_OUT", HERE / "libvhap_b200.so"))      # VH_SO_OUT / VH_EXTRA_FLAGS: experiment variants (dev only)
-SOURCES = ["flame.cu", "raster.cu", "render.cu", "texture.cu", "blend_tc.cu", "api.cu"]
+SOURCES = ["flame.cu", "raster.cu", "render.cu", "texture.cu", "blend_tc.cu", "dp_tex.cu", "api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "--fmad=true"] + os.environ.get("VH_EXTRA_FLAGS", "").split()
 

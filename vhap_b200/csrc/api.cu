@@ -242,7 +242,7 @@ extern "C" void vhap_ctx_destroy(vhap_ctx* c) {
   FREE(c->face_flags); FREE(c->vert_flags); FREE(c->w_off); FREE(c->w_off_lap); FREE(c->rigid_indptr); FREE(c->rigid_vids); FREE(c->uvmask_res);
   FREE(c->mips[0]); FREE(c->mips[1]); FREE(c->tex_painted); FREE(c->g_tex); FREE(c->tv_partials); FREE(c->tex_counter); FREE(c->tex_loss); FREE(c->scan_state); FREE(c->scal); FREE(c->acc); FREE(c->maxslot);
   for (int r = 0; r < VH_DP_MAX; ++r) if (c->dp_peers_host[r]) cudaIpcCloseMemHandle(c->dp_peers_host[r]);
-  FREE(c->dp_box); FREE(c->dp_epoch); FREE(c->dp_peers_dev);
+  FREE(c->dp_box); FREE(c->dp_epoch); FREE(c->dp_peers_dev); FREE(c->dp_grm_peers_dev); FREE(c->dp_exrm_peers_dev); FREE(c->dp_gband); FREE(c->dp_exband);
   FREE(c->overflow_flag); FREE(c->pool_base); FREE(c->pool_count); FREE(c->dev_lr_scale); FREE(c->dev_step);
   free(c);
 }
@@ -578,11 +578,11 @@ extern "C" int vhap_dp_init(vhap_ctx* ctx, int32_t rank, int32_t world, unsigned
   CK(cudaSetDevice(ctx->device));
   if (!ctx->dp_box) {
     CK(cudaMalloc((void**)&ctx->dp_box, VH_DP_BOX_FLOATS * sizeof(float)));
-    CK(cudaMalloc((void**)&ctx->dp_epoch, 2 * sizeof(int)));
+    CK(cudaMalloc((void**)&ctx->dp_epoch, 4 * sizeof(int)));       // [0] slab epoch, [1] error flag, [2] [3] epochs of the texture barriers A / B
     ctx->dp_err = ctx->dp_epoch + 1;
   }
   CK(cudaMemset(ctx->dp_box, 0, VH_DP_BOX_FLOATS * sizeof(float)));
-  { int init[2] = {1, 0}; CK(cudaMemcpy(ctx->dp_epoch, init, sizeof(init), cudaMemcpyHostToDevice)); }
+  { int init[4] = {1, 0, 0, 0}; CK(cudaMemcpy(ctx->dp_epoch, init, sizeof(init), cudaMemcpyHostToDevice)); }
   ctx->dp_rank = rank; ctx->dp_world = world;
   cudaIpcMemHandle_t h;
   CK(cudaIpcGetMemHandle(&h, ctx->dp_box));
@@ -603,6 +603,42 @@ extern "C" int vhap_dp_connect(vhap_ctx* ctx, const unsigned char* handles_host 
   }
   if (!ctx->dp_peers_dev) CK(cudaMalloc((void**)&ctx->dp_peers_dev, VH_DP_MAX * sizeof(float*)));
   CK(cudaMemcpy(ctx->dp_peers_dev, table, sizeof(table), cudaMemcpyHostToDevice));
+  return 0;
+}
+// Peer-memory texture update (dp_tex.cu).  The caller allocates g_rm and ex_rm ([T][3][T] floats each) as SYMMETRIC memory on every rank
+// (torch.distributed._symmetric_memory) and passes: the table of every rank's device pointer to it (HOST arrays of `world` pointers, own entry
+// included) and the multicast (NVLS) address of the buffer, or NULL when the fabric has no multicast -- then the kernels loop over the peers.
+extern "C" int vhap_dp_tex_connect(vhap_ctx* ctx, void* const* grm_ptrs_host, void* grm_multicast, void* const* exrm_ptrs_host, void* exrm_multicast) {
+  if (!ctx->dp_peers_dev || ctx->dp_world < 2) { vh_set_error(ctx, "vhap_dp_tex_connect", "call vhap_dp_init / vhap_dp_connect first (world >= 2)"); return -3; }
+  if (ctx->T % (ctx->dp_world * 8)) { vh_set_error(ctx, "vhap_dp_tex_connect", "texture size must be a multiple of 8 * world"); return -3; }
+  CK(cudaSetDevice(ctx->device));
+  const size_t nb = (size_t)3 * ctx->T * ctx->T / ctx->dp_world;
+  if (!ctx->dp_grm_peers_dev) {
+    CK(cudaMalloc((void**)&ctx->dp_grm_peers_dev, VH_DP_MAX * sizeof(float*)));
+    CK(cudaMalloc((void**)&ctx->dp_exrm_peers_dev, VH_DP_MAX * sizeof(float*)));
+    CK(cudaMalloc((void**)&ctx->dp_gband, nb * sizeof(float)));
+    CK(cudaMalloc((void**)&ctx->dp_exband, nb * sizeof(float)));
+  }
+  CK(cudaMemcpy(ctx->dp_grm_peers_dev, grm_ptrs_host, ctx->dp_world * sizeof(void*), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->dp_exrm_peers_dev, exrm_ptrs_host, ctx->dp_world * sizeof(void*), cudaMemcpyHostToDevice));
+  ctx->dp_grm = (float*)grm_ptrs_host[ctx->dp_rank]; ctx->dp_exrm = (float*)exrm_ptrs_host[ctx->dp_rank];
+  ctx->dp_grm_mc = (float*)grm_multicast; ctx->dp_exrm_mc = (float*)exrm_multicast;
+  return 0;
+}
+// one call = the whole chain of dp_tex.cu on `stream`: fold -> barrier -> reduce (NVLS) -> band Adam -> broadcast -> barrier -> rebuild
+extern "C" int vhap_dp_tex_update(vhap_ctx* ctx, float* tex_extra, float* adam_m, float* adam_v, float lr, int32_t step, const vhap_stage_cfg* cfg, void* stream) {
+  if (!ctx->dp_grm) { vh_set_error(ctx, "vhap_dp_tex_update", "call vhap_dp_tex_connect first"); return -3; }
+  cudaStream_t s = (cudaStream_t)stream;
+  ctx->tex_fork_pending = 0;
+  const int rows = ctx->T / ctx->dp_world, y0 = ctx->dp_rank * rows;
+  launch_tex_fold_grad_rm(ctx, tex_extra, ctx->dp_grm, s);
+  launch_dp_barrier(ctx, 0, s);
+  launch_dp_reduce_band(ctx, ctx->dp_gband, s);
+  if (launch_tex_band_adam(ctx, tex_extra, ctx->dp_gband, y0, y0 + rows, adam_m, adam_v, lr, step, cfg, ctx->dp_exband, s)) { vh_set_error(ctx, "vhap_dp_tex_update", "bad band"); return -3; }
+  launch_dp_bcast_band(ctx, ctx->dp_exband, s);
+  launch_dp_barrier(ctx, 1, s);
+  launch_tex_rebuild_rm(ctx, tex_extra, ctx->dp_exrm, s);
+  LAST();
   return 0;
 }
 // 0 = fine, 1 = a peer's flag did not arrive within the spin budget (synchronises)

@@ -13,7 +13,7 @@
 #define VH_NPART 40                // floats per block-partial row (>= 27 + a few)
 #define VH_MAXB_CHUNK 16
 #define VH_DP_MAX 16                // ranks of one node
-#define VH_DP_BOX_FLOATS (2 * VH_DP_MAX * 8 + VH_DP_MAX)   // mailbox: float slot[2][VH_DP_MAX][8], int flag[VH_DP_MAX]           // frames processed per pass of the blend-shape kernels
+#define VH_DP_BOX_FLOATS (2 * VH_DP_MAX * 8 + 3 * VH_DP_MAX)   // mailbox: float slot[2][VH_DP_MAX][8], int flag[VH_DP_MAX] (slab), flagA / flagB[VH_DP_MAX] (texture barriers)           // frames processed per pass of the blend-shape kernels
 
 struct CamParams { float RT[12]; float fx, fy, cx, cy; };
 
@@ -78,6 +78,8 @@ struct vhap_ctx {
   // data-parallel peer exchange of the forward slab over NVLink (CUDA IPC mailboxes, render.cu k_forward_slab / k_finalize): replaces the
   // mid-step NCCL all-gather + its host-side glue kernels on the step's critical chain
   int dp_rank, dp_world; float* dp_box; float** dp_peers_dev; void* dp_peers_host[VH_DP_MAX]; int* dp_epoch; int* dp_err;
+  // peer-memory texture update (dp_tex.cu): caller-allocated symmetric buffers g_rm / ex_rm [T][3][T], their NVSwitch multicast mappings (or NULL)
+  float *dp_grm, *dp_grm_mc, **dp_grm_peers_dev, *dp_exrm, *dp_exrm_mc, **dp_exrm_peers_dev, *dp_gband, *dp_exband;
   float* dev_lr_scale;                            // [1] learning-rate scale read by the Adam kernels when use_dev_step (ExponentialLR between graph replays)
 };
 
@@ -154,4 +156,8 @@ void launch_tex_fold_grad_rm(vhap_ctx* c, float* tex_extra, float* g_rm, cudaStr
 int launch_tex_band_adam(vhap_ctx* c, float* tex_extra, const float* g_band, int y_begin, int y_end, float* m, float* v, float lr, int step,
                          const vhap_stage_cfg* cfg, float* ex_band_out, cudaStream_t s);
 void launch_tex_rebuild_rm(vhap_ctx* c, float* tex_extra, const float* ex_rm, cudaStream_t s);
+// dp_tex.cu
+void launch_dp_barrier(vhap_ctx* c, int which, cudaStream_t s);
+void launch_dp_reduce_band(vhap_ctx* c, float* g_band, cudaStream_t s);
+void launch_dp_bcast_band(vhap_ctx* c, const float* ex_band, cudaStream_t s);
 void launch_adam(vhap_ctx* c, float* p, const float* g, float* m, float* v, int64_t n, float lr, int step, cudaStream_t s);

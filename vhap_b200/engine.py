@@ -354,6 +354,13 @@ class Engine:
         self._ck(self.L.vhap_dp_connect(self.ctx, buf))
         self._peer_slab = world > 1
 
+    def dp_tex_connect(self, grm_ptrs, grm_mc, exrm_ptrs, exrm_mc) -> None:
+        """hand the symmetric exchange buffers of the peer-memory texture update to the library (include/vhap_b200.h vhap_dp_tex_connect)"""
+        n = len(grm_ptrs)
+        a = (C.c_void_p * n)(*[int(p) for p in grm_ptrs])
+        b = (C.c_void_p * n)(*[int(p) for p in exrm_ptrs])
+        self._ck(self.L.vhap_dp_tex_connect(self.ctx, a, C.c_void_p(int(grm_mc) or None), b, C.c_void_p(int(exrm_mc) or None)))
+
     def dp_status(self) -> int:
         out = C.c_int32(0)
         self._ck(self.L.vhap_dp_status(self.ctx, C.byref(out)))
@@ -450,7 +457,14 @@ class Engine:
         s = self._stream()
         if deferred:
             self.L.vhap_tex_defer(self.ctx, -1)
-        if tex_comm is not None:
+        if tex_comm is not None and getattr(tex_comm, "peer", False):
+            # peer-memory update (csrc/dp_tex.cu): fold -> barrier -> in-switch band reduction -> band Adam -> multicast store -> barrier -> rebuild
+            if not deferred:
+                self._ck(self.L.vhap_tex_reg_loss(self.ctx, self.tex_extra.data_ptr(), C.byref(cs), s))
+                self._ck(self.L.vhap_assemble_losses(self.ctx, C.byref(cs), self.losses.data_ptr(), s))
+            self._ck(self.L.vhap_dp_tex_update(self.ctx, self.tex_extra.data_ptr(), self.tex_m.data_ptr(), self.tex_v.data_ptr(), self._lr("tex"), self.step_count,
+                                               C.byref(cs), s))
+        elif tex_comm is not None:
             sh = self._shard_bufs(tex_comm)
             if not deferred:
                 # loss values of the texture regularisers for the texture this step rendered with (the fused path gets them from its fold)
@@ -541,7 +555,7 @@ class Engine:
         stream and joins it right before the shading pass; the first graph_step runs an eager prologue, graph_end flushes the last
         update.  Same arithmetic in the same order on every buffer, only the schedule differs."""
         s = self._stream()
-        if tex_comm is not None:
+        if tex_comm is not None and not getattr(tex_comm, "peer", False):
             self._shard_bufs(tex_comm)                        # allocations must not happen inside capture
         elif allreduce_fn is not None and self.tex_grad_dense is None:
             self.texture_grad_dense(with_losses=False)       # one-time eager set-up (allocation, stream hand-over) must not happen inside capture

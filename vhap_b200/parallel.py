@@ -73,6 +73,34 @@ class TexShardComm:
         dist.all_gather_into_tensor(ex_rm, bands[self.rank], group=self.group)
 
 
+class TexPeerComm:
+    """peer-memory texture update (csrc/dp_tex.cu): the exchange buffers are torch symmetric memory (one allocation per rank, mapped by
+    every rank; with NVSwitch multicast the in-switch reduction / replication of NVLS is used), the kernels and barriers are the engine's
+    own -- no collective call on the path.  Needs Engine.dp_connect (the barrier mailboxes) first."""
+    peer = True
+
+    def __init__(self, engine, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        nt = 3 * engine.T * engine.T
+        g = group if group is not None else dist.group.WORLD
+        try:
+            symm_mem.enable_symm_mem_for_group(g.group_name)
+        except Exception:
+            pass                                             # newer torch: enabled implicitly
+        self.g_rm = symm_mem.empty(nt, dtype=torch.float32, device=engine.dev)
+        self.ex_rm = symm_mem.empty(nt, dtype=torch.float32, device=engine.dev)
+        self.g_rm.zero_(); self.ex_rm.zero_()
+        hg, hx = symm_mem.rendezvous(self.g_rm, g), symm_mem.rendezvous(self.ex_rm, g)
+        self.handles = (hg, hx)
+        mg, mx = int(getattr(hg, "multicast_ptr", 0) or 0), int(getattr(hx, "multicast_ptr", 0) or 0)
+        self.multicast = bool(mg and mx)
+        engine.dp_tex_connect(list(hg.buffer_ptrs), mg if self.multicast else 0, list(hx.buffer_ptrs), mx if self.multicast else 0)
+
+    def owned(self):
+        return [self.rank]
+
+
 class LocalShardComm:
     """the same interface inside ONE process that owns all `world` bands (sum over one rank = copy): exercises the band arithmetic of the
     sharded update without a second GPU (tests)"""
@@ -97,9 +125,11 @@ class LocalShardComm:
 class DataParallelStep:
     """Wraps an Engine: step(batch) = zero_grad, forward, slab reduce, backward, grad allreduce, Adam."""
 
-    def __init__(self, engine, group=None, texture="shard", slab="peer"):
-        """texture: "shard" (default: reduce-scatter -> 1/world Adam -> all-gather, TexShardComm on its own communicator) or "allreduce"
-        (round-1 baseline: dense all-reduce of the regularised gradient, full-texture Adam on every rank).
+    def __init__(self, engine, group=None, texture="auto", slab="peer"):
+        """texture: "peer" (fold -> in-switch band reduction over NVSwitch multicast -> Adam on 1/world of the rows -> multicast store ->
+        rebuild, all in the engine's own kernels over symmetric memory), "shard" (the same dataflow with NCCL reduce-scatter / all-gather,
+        TexShardComm on its own communicator), "allreduce" (round-1 baseline: dense all-reduce of the regularised gradient, full-texture Adam
+        on every rank) or "auto" (default: "peer", falling back to "shard" when symmetric memory cannot be set up; see .texture_mode).
         slab: "peer" (default: the mid-step batch-global scalars travel through CUDA-IPC mailboxes written / read by the engine's own
         kernels over NVLink, Engine.dp_connect) or "nccl" (round-1 baseline: an all-gather + host-side reduction between the halves)"""
         self.e, self.group = engine, group
@@ -114,6 +144,19 @@ class DataParallelStep:
                 return out
             engine.dp_connect(dist.get_rank(group), self.world, gather)
             self.peer_slab = True
+        self.texture_mode = "single" if self.world == 1 else texture
+        if self.world > 1 and texture in ("peer", "auto"):
+            # peer-memory update (NVLS when the fabric has multicast): needs the barrier mailboxes of the peer slab exchange
+            try:
+                if not self.peer_slab:
+                    raise RuntimeError("texture='peer' needs slab='peer' (the barrier mailboxes)")
+                self.tex_comm = TexPeerComm(engine, group)
+                self.texture_mode = "peer+nvls" if self.tex_comm.multicast else "peer"
+            except Exception as ex:
+                if texture == "peer":
+                    raise
+                self.texture_mode = f"shard (peer path unavailable: {type(ex).__name__}: {str(ex)[:120]})"
+                texture = "shard"
         if self.world > 1 and texture == "shard":
             ranks = dist.get_process_group_ranks(group) if group is not None else None
             self.tex_comm = TexShardComm(dist.new_group(ranks=ranks))
