@@ -21,6 +21,8 @@ def test_uint8_targets_are_to_tensor_exact():
         e.set_stage("rgb_global_tracking")
         e.inject_random(sc["w_fg"], sc["w_bg"], sc["u_rand"])
         u8 = (sc["rgb16"].to(torch.float32).permute(0, 2, 3, 1) * 255).round().clamp(0, 255).to(torch.uint8).contiguous()
+        yy, xx = torch.meshgrid(torch.arange(96), torch.arange(96), indexing="ij")
+        u8[1] = ((xx + 3 * yy)[..., None] + torch.tensor([0, 85, 170])).remainder(256).to(torch.uint8)     # frame 1: every byte value occurs
         b8 = e.stage_sample(u8, sc["lmk2d"], sc["ts"])
         assert b8.c.target_format == 1 and b8.target.dtype == torch.uint8
         planes = e.render_planes(b8, training=False)
@@ -29,6 +31,7 @@ def test_uint8_targets_are_to_tensor_exact():
         assert bg.float().mean() > 0.3
         ref = u8.to(torch.float32).div(255).to(e.dev)
         assert torch.equal(planes["rgba"][..., :3][bg], ref[bg])
+        assert len(torch.unique(u8[1][bg[1].cpu()])) == 256
         l8 = e.energy(b8, backward=False, training=True).clone()
         bf = e.stage_sample(u8.to(torch.float32).div(255).permute(0, 3, 1, 2), sc["lmk2d"], sc["ts"])      # fp16-staged floats
         assert bf.c.target_format == 0
