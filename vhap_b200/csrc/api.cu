@@ -242,7 +242,7 @@ extern "C" void vhap_ctx_destroy(vhap_ctx* c) {
   FREE(c->face_flags); FREE(c->vert_flags); FREE(c->w_off); FREE(c->w_off_lap); FREE(c->rigid_indptr); FREE(c->rigid_vids); FREE(c->uvmask_res);
   FREE(c->mips[0]); FREE(c->mips[1]); FREE(c->tex_painted); FREE(c->g_tex); FREE(c->tv_partials); FREE(c->tex_counter); FREE(c->tex_loss); FREE(c->scan_state); FREE(c->scal); FREE(c->acc); FREE(c->maxslot);
   for (int r = 0; r < VH_DP_MAX; ++r) if (c->dp_peers_host[r]) cudaIpcCloseMemHandle(c->dp_peers_host[r]);
-  FREE(c->dp_box); FREE(c->dp_epoch); FREE(c->dp_peers_dev); FREE(c->dp_grm_peers_dev); FREE(c->dp_exrm_peers_dev); FREE(c->dp_gband); FREE(c->dp_exband);
+  FREE(c->dp_box); FREE(c->dp_epoch); FREE(c->dp_peers_dev); FREE(c->dp_grm_peers_dev); FREE(c->dp_exrm_peers_dev); FREE(c->dp_gband); FREE(c->dp_exband); FREE(c->dp_counter);
   FREE(c->overflow_flag); FREE(c->pool_base); FREE(c->pool_count); FREE(c->dev_lr_scale); FREE(c->dev_step);
   free(c);
 }
@@ -616,6 +616,7 @@ extern "C" int vhap_dp_tex_connect(vhap_ctx* ctx, void* const* grm_ptrs_host, vo
   if (!ctx->dp_grm_peers_dev) {
     CK(cudaMalloc((void**)&ctx->dp_grm_peers_dev, VH_DP_MAX * sizeof(float*)));
     CK(cudaMalloc((void**)&ctx->dp_exrm_peers_dev, VH_DP_MAX * sizeof(float*)));
+    CK(cudaMalloc((void**)&ctx->dp_counter, sizeof(unsigned))); CK(cudaMemset(ctx->dp_counter, 0, sizeof(unsigned)));
     CK(cudaMalloc((void**)&ctx->dp_gband, nb * sizeof(float)));
     CK(cudaMalloc((void**)&ctx->dp_exband, nb * sizeof(float)));
   }
@@ -632,11 +633,9 @@ extern "C" int vhap_dp_tex_update(vhap_ctx* ctx, float* tex_extra, float* adam_m
   ctx->tex_fork_pending = 0;
   const int rows = ctx->T / ctx->dp_world, y0 = ctx->dp_rank * rows;
   launch_tex_fold_grad_rm(ctx, tex_extra, ctx->dp_grm, s);
-  launch_dp_barrier(ctx, 0, s);
-  launch_dp_reduce_band(ctx, ctx->dp_gband, s);
+  launch_dp_reduce_band(ctx, ctx->dp_gband, s);                // (carries barrier A)
   if (launch_tex_band_adam(ctx, tex_extra, ctx->dp_gband, y0, y0 + rows, adam_m, adam_v, lr, step, cfg, ctx->dp_exband, s)) { vh_set_error(ctx, "vhap_dp_tex_update", "bad band"); return -3; }
-  launch_dp_bcast_band(ctx, ctx->dp_exband, s);
-  launch_dp_barrier(ctx, 1, s);
+  launch_dp_bcast_band(ctx, ctx->dp_exband, s);                // (signals barrier B and waits for it)
   launch_tex_rebuild_rm(ctx, tex_extra, ctx->dp_exrm, s);
   LAST();
   return 0;

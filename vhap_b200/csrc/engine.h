@@ -19,7 +19,7 @@ struct CamParams { float RT[12]; float fx, fy, cx, cy; };
 
 // fork / join events of the side chains of a step (record on one stream, wait on another; valid eagerly and inside stream capture)
 enum { EV_REGS_FORK = 0, EV_REGS_DONE, EV_TEXGRAD_READY, EV_TEX_DONE, EV_VN_FORK, EV_VN_DONE, EV_GEOM_DONE, EV_BLEND_FORK, EV_BLEND_DONE,
-       EV_POSE_FORK, EV_POSE_DONE, EV_LMK_DONE, EV_LIGHTS_DONE, EV_COUNT };
+       EV_POSE_FORK, EV_POSE_DONE, EV_LMK_DONE, EV_LIGHTS_DONE, EV_C1_DONE, EV_C2TEX_DONE, EV_COUNT };
 
 struct vhap_ctx {
   char err[512];
@@ -79,6 +79,7 @@ struct vhap_ctx {
   // mid-step NCCL all-gather + its host-side glue kernels on the step's critical chain
   int dp_rank, dp_world; float* dp_box; float** dp_peers_dev; void* dp_peers_host[VH_DP_MAX]; int* dp_epoch; int* dp_err;
   // peer-memory texture update (dp_tex.cu): caller-allocated symmetric buffers g_rm / ex_rm [T][3][T], their NVSwitch multicast mappings (or NULL)
+  unsigned* dp_counter;
   float *dp_grm, *dp_grm_mc, **dp_grm_peers_dev, *dp_exrm, *dp_exrm_mc, **dp_exrm_peers_dev, *dp_gband, *dp_exband;
   float* dev_lr_scale;                            // [1] learning-rate scale read by the Adam kernels when use_dev_step (ExponentialLR between graph replays)
 };
@@ -157,7 +158,6 @@ int launch_tex_band_adam(vhap_ctx* c, float* tex_extra, const float* g_band, int
                          const vhap_stage_cfg* cfg, float* ex_band_out, cudaStream_t s);
 void launch_tex_rebuild_rm(vhap_ctx* c, float* tex_extra, const float* ex_rm, cudaStream_t s);
 // dp_tex.cu
-void launch_dp_barrier(vhap_ctx* c, int which, cudaStream_t s);
 void launch_dp_reduce_band(vhap_ctx* c, float* g_band, cudaStream_t s);
 void launch_dp_bcast_band(vhap_ctx* c, const float* ex_band, cudaStream_t s);
 void launch_adam(vhap_ctx* c, float* p, const float* g, float* m, float* v, int64_t n, float lr, int step, cudaStream_t s);

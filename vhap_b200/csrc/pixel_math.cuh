@@ -197,7 +197,8 @@ VH_HD f3 bilin_fetch(const f4* lvl, const Bilin& q, f3* ddx = nullptr, f3* ddy =
 }
 
 // linear-mipmap-linear sample (oracle/render.py mip_level / texture_sample)
-VH_HD void tex_sample(const RenderArgs& A, float u, float v, float dudx, float dudy, float dvdx, float dvdy, TexSample& s) {
+// level selection only (no texel fetch): lvl, l0, l1, f, lvl_free and the LOD intermediates
+VH_HD void tex_level(const RenderArgs& A, float dudx, float dudy, float dvdx, float dvdy, TexSample& s) {
   float T = (float)A.T;
   s.dsdx = dudx * T; s.dsdy = dudy * T; s.dtdx = dvdx * T; s.dtdy = dvdy * T;
   float Aq = s.dsdx * s.dsdx + s.dtdx * s.dtdx;
@@ -213,6 +214,9 @@ VH_HD void tex_sample(const RenderArgs& A, float u, float v, float dudx, float d
   s.l0 = (int)floorf(s.lvl); if (s.l0 > A.max_level) s.l0 = A.max_level;
   s.l1 = s.l0 + 1 < A.max_level ? s.l0 + 1 : A.max_level;
   s.f = s.lvl - (float)s.l0;
+}
+VH_HD void tex_sample(const RenderArgs& A, float u, float v, float dudx, float dudy, float dvdx, float dvdy, TexSample& s) {
+  tex_level(A, dudx, dudy, dvdx, dvdy, s);
   Bilin q0, q1;
   bilin_setup(u, v, A.T >> s.l0, q0);
   s.c0 = bilin_fetch(A.mips + A.mip_off[s.l0], q0);
@@ -315,6 +319,45 @@ VH_HD void shade_pixel(const RenderArgs& A, int b, int px, int py, int tri, PixS
 //   g_clip  [B,V,4]  atomics          g_vnorm [B,V,4] atomics        grad_pyr texture-gradient pyramid (float4) or NULL
 //   g_lights_local[27] per-thread accumulator (reduced by the caller)
 //   g_dd: extra gradient on diffuse_detach_normal (reg_diffuse), flows to the lights only.
+// raise the level-0 region flags of the four texels of a level-0 bilinear footprint (texture.cu: one flag per 8-row x 256-column region)
+VH_HD void tex_flag_l0(const RenderArgs& A, float u, float v) {
+  Bilin q0; bilin_setup(u, v, A.T, q0);
+  const int tpr = A.T >= 256 ? A.T >> 8 : 1;
+  const int idx[4] = {q0.i00, q0.i10, q0.i01, q0.i11};
+  for (int k = 0; k < 4; ++k) { int ty = idx[k] / A.T, tx = idx[k] - ty * A.T; A.tex_l0_flag[(ty >> 3) * tpr + (tx >> 8)] = 1; }
+}
+
+// The TEXEL-GRADIENT half of the shading adjoint of one foreground pixel, on its own: d L / d albedo = g_rgb * diffuse scattered into the
+// gradient pyramid with the trilinear weights.  Needs the barycentrics / uv derivatives (level of detail) and the shaded diffuse term, but
+// neither the texel values nor any vertex gradient -- k_passC2<1> runs it beside the geometry half (k_passC2<2>) on a second stream.
+VH_HD void shade_pixel_texgrad(const RenderArgs& A, int b, int px, int py, int tri, f3 g_rgb, float* grad_pyr) {
+  TriSetup ts;
+  tri_setup(A, b, px, py, tri, ts);
+  const f4* vn = A.vnorm + (size_t)(A.geo ? A.geo[b] : b) * A.V;
+  f4 a = vn[ts.vi[0]], c = vn[ts.vi[1]], d = vn[ts.vi[2]];
+  float b0 = ts.b0, b1 = ts.b1, b2 = 1.f - b0 - b1;
+  f3 nraw = mk3(a.x, a.y, a.z) * b0 + mk3(c.x, c.y, c.z) * b1 + mk3(d.x, d.y, d.z) * b2;
+  f3 n = nraw * (1.f / sqrtf(fmaxf(dot3(nraw, nraw), 1e-20f)));
+  float Bk[9];
+  sh_basis(n, Bk);
+  f3 g_alb = g_rgb * sh_eval(Bk, A.lights);
+  i4 fu = A.faces_uv[tri];
+  float t0u = A.verts_uv[fu.x * 2], t0v = A.verts_uv[fu.x * 2 + 1], t1u = A.verts_uv[fu.y * 2], t1v = A.verts_uv[fu.y * 2 + 1];
+  float t2u = A.verts_uv[fu.z * 2], t2v = A.verts_uv[fu.z * 2 + 1];
+  float u = b0 * t0u + b1 * t1u + b2 * t2u, v = b0 * t0v + b1 * t1v + b2 * t2v;
+  float d0u = t0u - t2u, d1u = t1u - t2u, d0v = t0v - t2v, d1v = t1v - t2v;
+  TexSample tx;
+  tex_level(A, ts.dudx * d0u + ts.dvdx * d1u, ts.dudy * d0u + ts.dvdy * d1u, ts.dudx * d0v + ts.dvdx * d1v, ts.dudy * d0v + ts.dvdy * d1v, tx);
+  Bilin q0, q1;
+  bilin_setup(u, v, A.T >> tx.l0, q0);
+  if (tx.l1 != tx.l0) {
+    bilin_scatter(grad_pyr + (size_t)A.mip_off[tx.l0] * 4, q0, g_alb * (1.f - tx.f));
+    bilin_setup(u, v, A.T >> tx.l1, q1);
+    bilin_scatter(grad_pyr + (size_t)A.mip_off[tx.l1] * 4, q1, g_alb * tx.f);
+  } else bilin_scatter(grad_pyr + (size_t)A.mip_off[tx.l0] * 4, q0, g_alb);
+  if (A.tex_l0_flag && tx.l0 == 0) tex_flag_l0(A, u, v);
+}
+
 // vg != NULL: the per-vertex gradients of this pixel are RETURNED (for a warp-level reduction over the pixels of one triangle,
 // k_passC2) instead of being added to g_clip / g_vnorm with one vector reduction per vertex per pixel.
 struct VertGrad { f3 gn[3]; f3 gc[3]; };      // d/d vertex normal (xyz), d/d clip position (x, y, w) of the triangle's three vertices
@@ -342,13 +385,7 @@ VH_HD void shade_pixel_bwd(const RenderArgs& A, int b, int tri, const PixShade& 
   // texture
   float g_u, g_v, g_da[4];
   tex_sample_bwd(A, s.u, s.v, s.tx, g_alb, grad_pyr, g_u, g_v, g_da);
-  if (grad_pyr && A.tex_l0_flag && s.tx.l0 == 0) {
-    // level 0 of the gradient pyramid was touched: raise the flags of the (8-row x 256-column) regions of the four texels (texture.cu)
-    Bilin q0; bilin_setup(s.u, s.v, A.T, q0);
-    const int tpr = A.T >= 256 ? A.T >> 8 : 1;
-    const int idx[4] = {q0.i00, q0.i10, q0.i01, q0.i11};
-    for (int k = 0; k < 4; ++k) { int ty = idx[k] / A.T, tx = idx[k] - ty * A.T; A.tex_l0_flag[(ty >> 3) * tpr + (tx >> 8)] = 1; }
-  }
+  if (grad_pyr && A.tex_l0_flag && s.tx.l0 == 0) tex_flag_l0(A, s.u, s.v);
   float d0u = s.t0[0] - s.t2[0], d1u = s.t1[0] - s.t2[0], d0v = s.t0[1] - s.t2[1], d1v = s.t1[1] - s.t2[1];
   bool detach_uv = A.face_flags && (A.face_flags[tri] & 1);
   if (!detach_uv) { g_b0 += g_u * d0u + g_v * d0v; g_b1 += g_u * d1u + g_v * d1v; }

@@ -193,9 +193,26 @@ __global__ void __launch_bounds__(PB, VH_C1_MIN) k_passC1(PassArgs P, const floa
 #ifndef VH_C2_PB
 #define VH_C2_PB 256
 #endif
+#ifndef VH_C2_SPLIT
+#define VH_C2_SPLIT 1          // texel-gradient half of pass C2 as a concurrent kernel on a second stream (0: one kernel)
+#endif
 #ifndef VH_C2_AGG
 #define VH_C2_AGG 1            // warp-level reduction of the per-vertex gradients over the pixels of one triangle (0: one reduction per pixel)
 #endif
+// texel-gradient half of the shading adjoint (see shade_pixel_texgrad): a light kernel that only issues the 8 vector reductions per pixel
+__global__ void __launch_bounds__(PB, 4) k_passC2_tex(PassArgs P, const f4* __restrict__ grgb) {
+  const RenderArgs& A = P.R;
+  int n_fg = A.B * A.H * A.W - P.pool_count[0];
+  const int* list = P.pool_list + P.pool_base[1];
+  const int* tris = P.pool_tri + P.pool_base[1];
+  for (int i = blockIdx.x * PB + threadIdx.x; i < n_fg; i += gridDim.x * PB) {
+    int pix = list[i], id = tris[i];
+    int x, y, b; vh_unflatten(A, pix, b, y, x);
+    f4 g = grgb[i];
+    if (id > 0) shade_pixel_texgrad(A, b, x, y, id - 1, mk3(g.x, g.y, g.z), P.g_tex);
+  }
+}
+
 __global__ void __launch_bounds__(VH_C2_PB, VH_C2_MINBLOCKS) k_passC2(PassArgs P, const f4* __restrict__ grgb, float* __restrict__ partials) {
   __shared__ float sh[(VH_C2_PB / 32) * 27];
   const RenderArgs& A = P.R;
@@ -491,6 +508,19 @@ void launch_render_backward(vhap_ctx* c, PassArgs& P, const vhap_stage_cfg* cfg,
   int grid = nblk < NPERSIST ? nblk : NPERSIST;
   LAUNCH(c, KID_PASSC1, s, k_passC1<<<grid, PB, 0, s>>>(P, ext_grad, c->grgb));
   int grid2 = grid * (PB / VH_C2_PB);
+#if VH_C2_SPLIT
+  // the texel-gradient scatter (8 of the 10 vector reductions per pixel, no texel reads) runs as its own light kernel on a second
+  // high-priority stream BESIDE the geometry half: two latency-bound kernels share the machine instead of one at 25 % occupancy
+  if (side && P.g_tex) {
+    cudaEventRecord(c->ev[EV_C1_DONE], s);
+    cudaStreamWaitEvent(c->hp[1], c->ev[EV_C1_DONE], 0);
+    LAUNCH(c, KID_PASSC1, c->hp[1], k_passC2_tex<<<grid, PB, 0, c->hp[1]>>>(P, c->grgb));
+    cudaEventRecord(c->ev[EV_C2TEX_DONE], c->hp[1]);
+    PassArgs Pg = P; Pg.g_tex = nullptr;
+    LAUNCH(c, KID_PASSC, s, k_passC2<<<grid2, VH_C2_PB, 0, s>>>(Pg, c->grgb, c->partials));
+    cudaStreamWaitEvent(s, c->ev[EV_C2TEX_DONE], 0);
+  } else
+#endif
   LAUNCH(c, KID_PASSC, s, k_passC2<<<grid2, VH_C2_PB, 0, s>>>(P, c->grgb, c->partials));
   // side != NULL: the reduction of the light-gradient partials (only the Adam step needs it) leaves the step's critical chain; the caller
   // joins EV_LIGHTS_DONE.  EV_TEXGRAD_READY doubles as "pass C complete".

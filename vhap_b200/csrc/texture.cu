@@ -117,7 +117,8 @@ struct RowIn { f4 t; float ex[3], m[3], v[3], g[3]; unsigned char msk; };
 
 __device__ __forceinline__ void row_load(const TexFoldArgs& a, int x, int y, bool l0, RowIn& r) {
   const size_t n = (size_t)a.T * a.T, i = (size_t)y * a.T + x;
-  r.t = a.tex_old[i];
+  const bool need_t = a.w_tv > 0.f || a.do_adam, need_ex = a.do_adam || (a.w_res > 0.f && a.mask);
+  if (need_t) r.t = a.tex_old[i];
   r.g[0] = r.g[1] = r.g[2] = 0.f;
   if (a.g_in) {
     if (a.rm) { const float* gi = a.g_in + ((size_t)(y - a.y_begin) * 3) * a.T + x; r.g[0] = gi[0]; r.g[1] = gi[a.T]; r.g[2] = gi[2 * (size_t)a.T]; }
@@ -125,7 +126,7 @@ __device__ __forceinline__ void row_load(const TexFoldArgs& a, int x, int y, boo
   }
   else if (l0) { float4 g0 = *(const float4*)(a.g_pyr + i * 4); r.g[0] = g0.x; r.g[1] = g0.y; r.g[2] = g0.z; }
 #pragma unroll
-  for (int c = 0; c < 3; ++c) { r.ex[c] = a.extra[c * n + i]; if (a.do_adam) { r.m[c] = a.m[c * n + i]; r.v[c] = a.v[c * n + i]; } }
+  for (int c = 0; c < 3; ++c) { if (need_ex) r.ex[c] = a.extra[c * n + i]; if (a.do_adam) { r.m[c] = a.m[c * n + i]; r.v[c] = a.v[c * n + i]; } }
   r.msk = (a.w_res > 0.f && a.mask) ? a.mask[i] : 0;
 }
 
@@ -329,18 +330,21 @@ __device__ void tf3_issue(const TexFoldArgs& a, TF3Row* rows, uint64_t* bars, in
   TF3Row& r = rows[slot];
   uint64_t* bar = bars + slot;
   const int left = x0 > 0 ? 1 : 0, right = x0 + 256 < T ? 1 : 0;
-  unsigned bytes = (unsigned)(256 + left + right) * 16u;
+  // what this launch needs per row: the texture values for TV / the new pyramid, tex_extra for Adam / the residual term, ... (the pure
+  // gradient fold of the sharded update, vhap_tex_fold_grad_rm, needs none of them: it only streams the flagged level-0 gradient rows)
+  const bool need_t = a.w_tv > 0.f || a.do_adam, need_ex = a.do_adam || want_mask;
+  unsigned bytes = need_t ? (unsigned)(256 + left + right) * 16u : 0u;
   if (full) {
-    bytes += 3u * 1024u;
+    if (need_ex) bytes += 3u * 1024u;
     if (a.do_adam) bytes += 6u * 1024u;
     if (a.g_in) bytes += 3u * 1024u; else if (l0) bytes += 4096u;
     if (want_mask) bytes += 256u;
   }
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
-  tf3_copy(&r.t[1 - left], a.tex_old + i - left, (unsigned)(256 + left + right) * 16u, bar);
+  if (need_t) tf3_copy(&r.t[1 - left], a.tex_old + i - left, (unsigned)(256 + left + right) * 16u, bar);
   if (!full) return;
   for (int c = 0; c < 3; ++c) {
-    tf3_copy(r.ex[c], a.extra + c * n + i, 1024u, bar);
+    if (need_ex) tf3_copy(r.ex[c], a.extra + c * n + i, 1024u, bar);
     if (a.do_adam) { tf3_copy(r.m[c], a.m + c * n + i, 1024u, bar); tf3_copy(r.v[c], a.v + c * n + i, 1024u, bar); }
     if (a.g_in) {
       const float* gi = a.rm ? a.g_in + ((size_t)(y - a.y_begin) * 3 + c) * T + x0 : a.g_in + c * n + i;
