@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(PB, VH_C1_MIN) k_passC1(PassArgs P, const floa
 #define VH_C2_PB 256
 #endif
 #ifndef VH_C2_SPLIT
-#define VH_C2_SPLIT 1          // texel-gradient half of pass C2 as a concurrent kernel on a second stream (0: one kernel)
+#define VH_C2_SPLIT 0          // 1: texel-gradient half of pass C2 as a concurrent kernel on a second stream -- measured SLOWER (0.757 vs 0.735 ms/step, r6)
 #endif
 #ifndef VH_C2_AGG
 #define VH_C2_AGG 1            // warp-level reduction of the per-vertex gradients over the pixels of one triangle (0: one reduction per pixel)
