@@ -633,9 +633,11 @@ extern "C" int vhap_dp_tex_update(vhap_ctx* ctx, float* tex_extra, float* adam_m
   ctx->tex_fork_pending = 0;
   const int rows = ctx->T / ctx->dp_world, y0 = ctx->dp_rank * rows;
   launch_tex_fold_grad_rm(ctx, tex_extra, ctx->dp_grm, s);
-  launch_dp_reduce_band(ctx, ctx->dp_gband, s);                // (carries barrier A)
+  launch_dp_barrier(ctx, 0, s);
+  launch_dp_reduce_band(ctx, ctx->dp_gband, s);
   if (launch_tex_band_adam(ctx, tex_extra, ctx->dp_gband, y0, y0 + rows, adam_m, adam_v, lr, step, cfg, ctx->dp_exband, s)) { vh_set_error(ctx, "vhap_dp_tex_update", "bad band"); return -3; }
-  launch_dp_bcast_band(ctx, ctx->dp_exband, s);                // (signals barrier B and waits for it)
+  launch_dp_bcast_band(ctx, ctx->dp_exband, s);
+  launch_dp_barrier(ctx, 1, s);
   launch_tex_rebuild_rm(ctx, tex_extra, ctx->dp_exrm, s);
   LAST();
   return 0;

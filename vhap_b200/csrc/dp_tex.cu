@@ -2,38 +2,36 @@
 //
 // Per step and rank (row-major exchange layout [T][3][T], rank r owns the rows [r T/N, (r+1) T/N)):
 //   fold          local photometric fold of the texel-gradient pyramid -> g_rm                       (texture.cu, k_tex_fold3)
-//   barrier A     every rank's g_rm is complete                                                       (mailbox flags, inside the reduce kernel)
+//   barrier A     every rank's g_rm is complete                                                       (mailbox flags, one-warp kernel k_dp_barrier)
 //   reduce        g_band = sum over ranks of g_rm[band]: ONE multimem.ld_reduce.add.v4.f32 per 16 bytes through the NVSwitch multicast
 //                 mapping of g_rm (in-switch reduction, NVLS) -- or, without multicast support, a loop of peer loads in rank order
 //   band Adam     + TV / residual gradients, Adam on the band's rows of tex_extra / m / v             (texture.cu, vhap_tex_band_adam)
 //   broadcast     the updated rows go to every rank's ex_rm with multimem.st (one store, the switch replicates) -- or peer stores
-//   barrier B     every band has landed everywhere                                                    (signalled by the broadcast kernel's last CTA)
+//   barrier B     every band has landed everywhere                                                    (k_dp_barrier)
 //   rebuild       level 0 / 1 + mips of the new pyramid from ex_rm, planar tex_extra refreshed       (texture.cu, vhap_tex_rebuild_rm)
 // The symmetric buffers (g_rm, ex_rm) and their multicast mappings are allocated by the caller (torch symmetric memory) and handed over
 // as raw pointers (vhap_dp_tex_connect); the barriers use the CUDA-IPC mailboxes of vhap_dp_init / vhap_dp_connect.
 // Replaces NCCL reduce-scatter + all-gather of parallel.TexShardComm; the reference has no multi-GPU path.
 #include "engine.h"
 
-// The two barriers ride inside the data kernels (no extra launches):
-//   A  "every rank's g_rm is complete": k_dp_reduce_band signals flagA[rank] = e in every mailbox on entry (the fold kernel precedes it in
-//      stream order) and every CTA waits for all flags of the own mailbox before its first remote read;
-//   B  "every band has landed everywhere": the last CTA of k_dp_bcast_band to finish signals flagB[rank] = e; vhap_tex_rebuild_rm's kernel
-//      waits for all of them on entry.
-// Reuse is safe: a rank overwrites its g_rm (next fold) only after its rebuild passed barrier B, i.e. after every peer finished reducing;
-// a rank writes into a peer's ex_rm (next broadcast) only after that peer signalled A again, i.e. after its rebuild of this step.
+// Barriers: one-warp kernels on the mailbox flags (a waiting rank must not occupy the machine: a version with the wait folded into the
+// many-CTA reduce kernel starved the forward chain that runs beside the texture update -- vertex normals 0.026 -> 0.087 ms, r7 timeline).
+//   A  "every rank's g_rm is complete", B  "every band has landed everywhere".
+// Reuse is safe: a rank overwrites its g_rm (next fold) only after it passed barrier B, i.e. after every peer finished reducing; a rank
+// writes into a peer's ex_rm (next broadcast) only after that peer passed barrier A again, i.e. after its rebuild of this step.
 #define DP_FLAG_OFF(which) ((size_t)2 * VH_DP_MAX * 8 + (size_t)(1 + (which)) * VH_DP_MAX)      // after the slab slots and the slab flags
-__device__ __forceinline__ void dp_wait_all(const float* mine, int which, int world, int e, int* err) {
+__global__ void k_dp_barrier(float* mine, float* const* peers, int rank, int world, int which, int* epoch, int* err) {
+  if (threadIdx.x != 0) return;
+  const int e = epoch[which] + 1;
+  epoch[which] = e;
+  __threadfence_system();
+  for (int p = 0; p < world; ++p) ((volatile int*)(peers[p] + DP_FLAG_OFF(which)))[rank] = e;
   volatile const int* flags = (volatile const int*)(mine + DP_FLAG_OFF(which));
   const long long t0 = clock64();
   for (int j = 0; j < world; ++j)
     while (flags[j] - e < 0) { if (clock64() - t0 > (1ll << 33)) { *err = 2; break; } }      // ~4 s: a dead peer must not hang the GPU
   __threadfence_system();
 }
-__device__ __forceinline__ void dp_signal_all(float* const* peers, int which, int rank, int world, int e) {
-  __threadfence_system();
-  for (int p = 0; p < world; ++p) ((volatile int*)(peers[p] + DP_FLAG_OFF(which)))[rank] = e;
-}
-struct DpSync { float* mine; float* const* peers; int rank, world; int* epoch; int* err; unsigned* counter; };
 
 __device__ __forceinline__ float4 mc_ld_reduce(const float* mc) {
   float4 v;
@@ -45,14 +43,7 @@ __device__ __forceinline__ void mc_st(float* mc, float4 v) {
 }
 
 // g_band[i] = sum_r g_rm_r[band_off + i]   (float4 granularity)
-__global__ void __launch_bounds__(256) k_dp_reduce_band(const float* mc, float* const* peers, int world, size_t band_off4, size_t n4, float4* __restrict__ out, DpSync sy) {
-  __shared__ bool is_last;
-  const int e = sy.epoch[0] + 1;                                                 // (advanced by the last CTA below)
-  if (threadIdx.x == 0) {
-    if (blockIdx.x == 0) dp_signal_all(sy.peers, 0, sy.rank, sy.world, e);       // barrier A: my g_rm is complete
-    dp_wait_all(sy.mine, 0, sy.world, e, sy.err);                                // ... and so is everybody's
-  }
-  __syncthreads();
+__global__ void __launch_bounds__(256) k_dp_reduce_band(const float* mc, float* const* peers, int world, size_t band_off4, size_t n4, float4* __restrict__ out) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     float4 s;
     if (mc) s = mc_ld_reduce(mc + (band_off4 + i) * 4);
@@ -65,46 +56,27 @@ __global__ void __launch_bounds__(256) k_dp_reduce_band(const float* mc, float* 
     }
     out[i] = s;
   }
-  __syncthreads();
-  if (threadIdx.x == 0) is_last = (atomicAdd(sy.counter, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (is_last && threadIdx.x == 0) { sy.epoch[0] = e; *sy.counter = 0u; }
 }
 // every rank's ex_rm[band_off + i] = ex_band[i]
-__global__ void __launch_bounds__(256) k_dp_bcast_band(float* mc, float* const* peers, int world, size_t band_off4, size_t n4, const float4* __restrict__ in, DpSync sy) {
-  __shared__ bool is_last;
+__global__ void __launch_bounds__(256) k_dp_bcast_band(float* mc, float* const* peers, int world, size_t band_off4, size_t n4, const float4* __restrict__ in) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     float4 v = in[i];
     if (mc) mc_st(mc + (band_off4 + i) * 4, v);
     else for (int r = 0; r < world; ++r) ((float4*)peers[r])[band_off4 + i] = v;
   }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) is_last = (atomicAdd(sy.counter, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (is_last && threadIdx.x == 0) {                                             // barrier B: my band has landed everywhere
-    const int e = sy.epoch[1] + 1;
-    dp_signal_all(sy.peers, 1, sy.rank, sy.world, e);
-    sy.epoch[1] = e; *sy.counter = 0u;
-  }
-}
-// entry of the rebuild: wait until every rank's band has landed in the own ex_rm (one thread; the rebuild kernel is launched after it)
-__global__ void k_dp_wait_b(DpSync sy) {
-  if (threadIdx.x == 0) dp_wait_all(sy.mine, 1, sy.world, sy.epoch[1], sy.err);
 }
 
-static DpSync dp_sync_of(vhap_ctx* c) {
-  DpSync y; y.mine = c->dp_box; y.peers = c->dp_peers_dev; y.rank = c->dp_rank; y.world = c->dp_world; y.epoch = c->dp_epoch + 2; y.err = c->dp_err; y.counter = c->dp_counter;
-  return y;
+void launch_dp_barrier(vhap_ctx* c, int which, cudaStream_t s) {
+  LAUNCH(c, KID_MISC, s, k_dp_barrier<<<1, 32, 0, s>>>(c->dp_box, c->dp_peers_dev, c->dp_rank, c->dp_world, which, c->dp_epoch + 2, c->dp_err));
 }
+// small grids: the two data kernels are bound by the NVLink / NVSwitch path, not by SM count, and run beside the next step's forward
 void launch_dp_reduce_band(vhap_ctx* c, float* g_band, cudaStream_t s) {
   const size_t nb4 = (size_t)3 * c->T * c->T / c->dp_world / 4;
-  const int grid = (int)((nb4 + 255) / 256 < 148 * 4 ? (nb4 + 255) / 256 : 148 * 4);       // all CTAs resident: CTA 0 carries the signal
-  LAUNCH(c, KID_MISC, s, k_dp_reduce_band<<<grid, 256, 0, s>>>(c->dp_grm_mc, c->dp_grm_peers_dev, c->dp_world, nb4 * c->dp_rank, nb4, (float4*)g_band, dp_sync_of(c)));
+  const int grid = (int)((nb4 + 255) / 256 < 148 ? (nb4 + 255) / 256 : 148);
+  LAUNCH(c, KID_MISC, s, k_dp_reduce_band<<<grid, 256, 0, s>>>(c->dp_grm_mc, c->dp_grm_peers_dev, c->dp_world, nb4 * c->dp_rank, nb4, (float4*)g_band));
 }
 void launch_dp_bcast_band(vhap_ctx* c, const float* ex_band, cudaStream_t s) {
   const size_t nb4 = (size_t)3 * c->T * c->T / c->dp_world / 4;
-  const int grid = (int)((nb4 + 255) / 256 < 148 * 4 ? (nb4 + 255) / 256 : 148 * 4);
-  LAUNCH(c, KID_MISC, s, k_dp_bcast_band<<<grid, 256, 0, s>>>(c->dp_exrm_mc, c->dp_exrm_peers_dev, c->dp_world, nb4 * c->dp_rank, nb4, (const float4*)ex_band, dp_sync_of(c)));
-  LAUNCH(c, KID_MISC, s, k_dp_wait_b<<<1, 32, 0, s>>>(dp_sync_of(c)));
+  const int grid = (int)((nb4 + 255) / 256 < 148 ? (nb4 + 255) / 256 : 148);
+  LAUNCH(c, KID_MISC, s, k_dp_bcast_band<<<grid, 256, 0, s>>>(c->dp_exrm_mc, c->dp_exrm_peers_dev, c->dp_world, nb4 * c->dp_rank, nb4, (const float4*)ex_band));
 }

@@ -158,6 +158,7 @@ int launch_tex_band_adam(vhap_ctx* c, float* tex_extra, const float* g_band, int
                          const vhap_stage_cfg* cfg, float* ex_band_out, cudaStream_t s);
 void launch_tex_rebuild_rm(vhap_ctx* c, float* tex_extra, const float* ex_rm, cudaStream_t s);
 // dp_tex.cu
+void launch_dp_barrier(vhap_ctx* c, int which, cudaStream_t s);
 void launch_dp_reduce_band(vhap_ctx* c, float* g_band, cudaStream_t s);
 void launch_dp_bcast_band(vhap_ctx* c, const float* ex_band, cudaStream_t s);
 void launch_adam(vhap_ctx* c, float* p, const float* g, float* m, float* v, int64_t n, float lr, int step, cudaStream_t s);
