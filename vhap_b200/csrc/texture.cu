@@ -308,7 +308,9 @@ __global__ void __launch_bounds__(256, TF_MINB) k_tex_fold2(TexFoldArgs a, float
 
 
 // ---- TMA-staged version (T >= 256, 256-wide strips)
+#ifndef TF3_NS
 #define TF3_NS 3
+#endif
 struct __align__(16) TF3Row {
   f4 t[258];                  // texture row incl. the left / right neighbour columns of the strip
   float ex[3][256], m[3][256], v[3][256];
