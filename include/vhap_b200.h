@@ -218,6 +218,12 @@ int vhap_dp_status(vhap_ctx* ctx, int32_t* out_host);   /* 0 ok, 1 / 2 = a peer 
  * every rank: *_ptrs_host = every rank's device pointer (HOST array of `world`), *_multicast = the multicast address or NULL. */
 int vhap_dp_tex_connect(vhap_ctx* ctx, void* const* grm_ptrs_host, void* grm_multicast, void* const* exrm_ptrs_host, void* exrm_multicast);
 int vhap_dp_tex_update(vhap_ctx* ctx, float* tex_extra, float* adam_m, float* adam_v, float lr, int32_t step, const vhap_stage_cfg* cfg, void* stream);
+/* the same in two parts for pipelined steps: part 1 (fold, barrier, band reduction) right after vhap_energy_backward -- it runs on the
+ * library's bulk stream beside the geometry backward, vhap_dp_tex_join makes `stream` wait for it --, part 2 (band Adam, multicast store,
+ * barrier, pyramid rebuild) whenever the caller wants the update applied (e.g. at the start of the next step) */
+int vhap_dp_tex_part1(vhap_ctx* ctx, float* tex_extra, void* stream);
+int vhap_dp_tex_join(vhap_ctx* ctx, void* stream);
+int vhap_dp_tex_part2(vhap_ctx* ctx, float* tex_extra, float* adam_m, float* adam_v, float lr, int32_t step, const vhap_stage_cfg* cfg, void* stream);
 
 /* ---- sharded texture update (data parallel; the reference has no multi-GPU path): per step
  *   vhap_tex_fold_grad_rm  photometric part of the texel gradient, dense, ROW-MAJOR g_rm[(y*3 + c)*T + x] so that a row band is contiguous

@@ -626,21 +626,49 @@ extern "C" int vhap_dp_tex_connect(vhap_ctx* ctx, void* const* grm_ptrs_host, vo
   ctx->dp_grm_mc = (float*)grm_multicast; ctx->dp_exrm_mc = (float*)exrm_multicast;
   return 0;
 }
-// one call = the whole chain of dp_tex.cu on `stream`: fold -> barrier -> reduce (NVLS) -> band Adam -> broadcast -> barrier -> rebuild
-extern "C" int vhap_dp_tex_update(vhap_ctx* ctx, float* tex_extra, float* adam_m, float* adam_v, float lr, int32_t step, const vhap_stage_cfg* cfg, void* stream) {
-  if (!ctx->dp_grm) { vh_set_error(ctx, "vhap_dp_tex_update", "call vhap_dp_tex_connect first"); return -3; }
+// The chain of dp_tex.cu in two parts, so that a pipelined step can run the first beside its own geometry backward and the second at the
+// start of the next step (Engine._step_body):
+//   part 1: fold -> barrier A -> in-switch reduction of this rank's band.  Right after vhap_energy_backward (texel gradients just completed)
+//           it forks onto the library's bulk stream behind the fused backward; vhap_dp_tex_join makes `stream` wait for it.
+//   part 2: regularisers + Adam on the band -> multicast store -> barrier B -> pyramid rebuild.
+extern "C" int vhap_dp_tex_part1(vhap_ctx* ctx, float* tex_extra, void* stream) {
+  if (!ctx->dp_grm) { vh_set_error(ctx, "vhap_dp_tex_part1", "call vhap_dp_tex_connect first"); return -3; }
   cudaStream_t s = (cudaStream_t)stream;
+  ctx->dp_tex_forked = 0;
+  if (ctx->tex_fork_pending && !ctx->no_overlap) {
+    cudaStreamWaitEvent(ctx->aux[1], ctx->ev[EV_TEXGRAD_READY], 0);
+    s = ctx->aux[1];
+    ctx->dp_tex_forked = 1;
+  }
   ctx->tex_fork_pending = 0;
-  const int rows = ctx->T / ctx->dp_world, y0 = ctx->dp_rank * rows;
   launch_tex_fold_grad_rm(ctx, tex_extra, ctx->dp_grm, s);
   launch_dp_barrier(ctx, 0, s);
   launch_dp_reduce_band(ctx, ctx->dp_gband, s);
-  if (launch_tex_band_adam(ctx, tex_extra, ctx->dp_gband, y0, y0 + rows, adam_m, adam_v, lr, step, cfg, ctx->dp_exband, s)) { vh_set_error(ctx, "vhap_dp_tex_update", "bad band"); return -3; }
+  if (ctx->dp_tex_forked) cudaEventRecord(ctx->ev[EV_TEX_DONE], s);
+  LAST();
+  return 0;
+}
+extern "C" int vhap_dp_tex_join(vhap_ctx* ctx, void* stream) {
+  if (ctx->dp_tex_forked) { cudaStreamWaitEvent((cudaStream_t)stream, ctx->ev[EV_TEX_DONE], 0); ctx->dp_tex_forked = 0; }
+  return 0;
+}
+extern "C" int vhap_dp_tex_part2(vhap_ctx* ctx, float* tex_extra, float* adam_m, float* adam_v, float lr, int32_t step, const vhap_stage_cfg* cfg, void* stream) {
+  if (!ctx->dp_grm) { vh_set_error(ctx, "vhap_dp_tex_part2", "call vhap_dp_tex_connect first"); return -3; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int rows = ctx->T / ctx->dp_world, y0 = ctx->dp_rank * rows;
+  if (launch_tex_band_adam(ctx, tex_extra, ctx->dp_gband, y0, y0 + rows, adam_m, adam_v, lr, step, cfg, ctx->dp_exband, s)) { vh_set_error(ctx, "vhap_dp_tex_part2", "bad band"); return -3; }
   launch_dp_bcast_band(ctx, ctx->dp_exband, s);
   launch_dp_barrier(ctx, 1, s);
   launch_tex_rebuild_rm(ctx, tex_extra, ctx->dp_exrm, s);
   LAST();
   return 0;
+}
+// one call = both parts on `stream`
+extern "C" int vhap_dp_tex_update(vhap_ctx* ctx, float* tex_extra, float* adam_m, float* adam_v, float lr, int32_t step, const vhap_stage_cfg* cfg, void* stream) {
+  ctx->tex_fork_pending = 0;
+  int r = vhap_dp_tex_part1(ctx, tex_extra, stream);
+  if (r) return r;
+  return vhap_dp_tex_part2(ctx, tex_extra, adam_m, adam_v, lr, step, cfg, stream);
 }
 // 0 = fine, 1 = a peer's flag did not arrive within the spin budget (synchronises)
 extern "C" int vhap_dp_status(vhap_ctx* ctx, int32_t* out_host) {

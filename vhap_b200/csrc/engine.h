@@ -79,7 +79,7 @@ struct vhap_ctx {
   // mid-step NCCL all-gather + its host-side glue kernels on the step's critical chain
   int dp_rank, dp_world; float* dp_box; float** dp_peers_dev; void* dp_peers_host[VH_DP_MAX]; int* dp_epoch; int* dp_err;
   // peer-memory texture update (dp_tex.cu): caller-allocated symmetric buffers g_rm / ex_rm [T][3][T], their NVSwitch multicast mappings (or NULL)
-  unsigned* dp_counter;
+  unsigned* dp_counter; int dp_tex_forked;
   float *dp_grm, *dp_grm_mc, **dp_grm_peers_dev, *dp_exrm, *dp_exrm_mc, **dp_exrm_peers_dev, *dp_gband, *dp_exband;
   float* dev_lr_scale;                            // [1] learning-rate scale read by the Adam kernels when use_dev_step (ExponentialLR between graph replays)
 };

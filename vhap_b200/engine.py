@@ -114,6 +114,7 @@ class Engine:
         self.global_step = 0
         self._lr_scale = 1.0
         self._graph_live = False
+        self._tex_split = False
         self._inj = None
         self._loss_mask = None
         self._peer_slab = False
@@ -446,7 +447,7 @@ class Engine:
             self._shard_key = key
         return self._shard
 
-    def tex_update(self, allreduce_fn=None, deferred=False, reg_loss=True, tex_comm=None):
+    def tex_update(self, allreduce_fn=None, deferred=False, reg_loss=True, tex_comm=None, second_half=False):
         """Texture part of the Adam step on the CURRENT stream.  deferred=True: the update of the PREVIOUS step, executed at the start
         of the next one (pipelined graph replay): no in-call fork, device Adam step - 1, no loss bookkeeping of the finished step, and
         the regulariser loss values of the updated texture are produced for the step that is about to run.
@@ -462,8 +463,10 @@ class Engine:
             if not deferred:
                 self._ck(self.L.vhap_tex_reg_loss(self.ctx, self.tex_extra.data_ptr(), C.byref(cs), s))
                 self._ck(self.L.vhap_assemble_losses(self.ctx, C.byref(cs), self.losses.data_ptr(), s))
-            self._ck(self.L.vhap_dp_tex_update(self.ctx, self.tex_extra.data_ptr(), self.tex_m.data_ptr(), self.tex_v.data_ptr(), self._lr("tex"), self.step_count,
-                                               C.byref(cs), s))
+            # second_half: the fold / band reduction of this update already ran at the end of the step that produced the gradients
+            # (vhap_dp_tex_part1 in _step_body, beside the geometry backward); what is left is Adam on the band, the multicast store, the rebuild
+            fn = self.L.vhap_dp_tex_part2 if second_half else self.L.vhap_dp_tex_update
+            self._ck(fn(self.ctx, self.tex_extra.data_ptr(), self.tex_m.data_ptr(), self.tex_v.data_ptr(), self._lr("tex"), self.step_count, C.byref(cs), s))
         elif tex_comm is not None:
             sh = self._shard_bufs(tex_comm)
             if not deferred:
@@ -565,6 +568,7 @@ class Engine:
         torch.cuda.synchronize(self.dev)
         opt = opt_dict_for(self.stage)
         self._pipe = bool(pipelined and body is None and self.stage is not None and self.stage.photometric and opt["texture"])
+        self._tex_split = bool(self._pipe and tex_comm is not None and getattr(tex_comm, "peer", False))
         self._hooks = (reduce_fn, allreduce_fn, world, tex_comm)
         self._graph_batches = list(batches)
         # true global batch size per staged batch (uneven shards: not B * world); parallel.DataParallelStep passes the all-reduced values
@@ -605,7 +609,7 @@ class Engine:
             e2 = torch.cuda.Event()
             cs = self._c_stage(True)
             with torch.cuda.stream(self._tex_stream):
-                self.tex_update(allreduce_fn, deferred=True, reg_loss=False, tex_comm=tex_comm)
+                self.tex_update(allreduce_fn, deferred=True, reg_loss=False, tex_comm=tex_comm, second_half=self._tex_split)
                 e1.record(self._tex_stream)               # the new pyramid is complete: what the shading pass waits for
                 # regulariser loss VALUES of the updated texture: only the loss vector needs them, joined at the end of the step
                 self._ck(self.L.vhap_tex_reg_loss(self.ctx, self.tex_extra.data_ptr(), C.byref(cs), self._stream()), None)
@@ -614,7 +618,15 @@ class Engine:
             self.L.vhap_set_render_wait_event(self.ctx, C.c_void_p(e1.cuda_event))    # joined right before the shading pass
         self.zero_grad()
         self.energy(batch, backward=True, training=True, global_B=self._graph_gB.get(id(batch), batch.B * world), reduce_fn=reduce_fn)
+        split = self._tex_split and not texture_now
+        if split:
+            # peer-memory texture update, first half (fold -> barrier -> in-switch band reduction): starts as soon as the texel gradients are
+            # complete, on the library's bulk stream beside the geometry backward / parameter all-reduce / Adam of THIS step; the second half
+            # (band Adam, multicast store, rebuild) opens the next step
+            self._ck(self.L.vhap_dp_tex_part1(self.ctx, self.tex_extra.data_ptr(), self._stream()))
         self.adam_step(allreduce_fn=allreduce_fn, texture=texture_now, tex_comm=tex_comm)
+        if split:
+            self._ck(self.L.vhap_dp_tex_join(self.ctx, self._stream()))
         if deferred_tex:
             torch.cuda.current_stream(self.dev).wait_event(e2)
             self._ck(self.L.vhap_assemble_losses(self.ctx, C.byref(cs), self.losses.data_ptr(), self._stream()), None)
@@ -639,7 +651,7 @@ class Engine:
         stream).  The next graph_step then starts the pipeline again with its eager prologue."""
         if getattr(self, "_pipe", False) and self._primed:
             self.L.vhap_set_cur_mip(self.ctx, self._parity)     # the replays did not touch the host-side ping-pong index
-            self.tex_update(self._hooks[1], deferred=True, tex_comm=self._hooks[3])
+            self.tex_update(self._hooks[1], deferred=True, tex_comm=self._hooks[3], second_half=self._tex_split)
             self._parity ^= 1
             self._primed = False
 
@@ -653,6 +665,7 @@ class Engine:
         self._graphs, self._graph_events = {}, []
         self._primed = False
         self._pipe = False
+        self._tex_split = False
 
     # ------------------------------------------------------------------ logging planes (render_out dict)
     def render_planes(self, batch: Batch, training=False) -> Dict[str, torch.Tensor]:
