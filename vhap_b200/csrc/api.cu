@@ -339,7 +339,7 @@ static void zero_backward_scratch(vhap_ctx* c, int B, cudaStream_t s, bool with_
   auto add = [&](void* p, size_t bytes) { z.p[z.n] = p; z.bytes[z.n] = bytes; ++z.n; };
   add(c->g_verts, B * V * 4 * sizeof(float)); add(c->g_clip, B * V * 4 * sizeof(float)); add(c->g_vnorm, B * V * 4 * sizeof(float));
   add(c->gA, (size_t)B * 60 * sizeof(float)); add(c->gpf, (size_t)B * 36 * sizeof(float)); add(c->gbetas, (size_t)B * c->K * sizeof(float));
-  if (with_acc) add(c->acc, ACC_COUNT * sizeof(float));
+  if (with_acc) { add(c->acc, ACC_COUNT * sizeof(float)); add(c->maxslot, sizeof(unsigned long long)); add(c->pair_count, sizeof(int)); }   // (12 segments max)
   vh_zero_multi(c, z, s);
 }
 
@@ -442,7 +442,7 @@ extern "C" int vhap_energy_forward(vhap_ctx* ctx, const vhap_params* p, const vh
     if (vn_overlap) cudaStreamWaitEvent(s, ctx->ev[EV_VN_DONE], 0);
     PassArgs P;
     fill_render_args(ctx, P, fb, cfg, p->lights);
-    launch_render_forward(ctx, P, s);
+    launch_render_forward(ctx, P, s, true);               // (maxslot / pair_count were cleared with the step's scratch above)
     launch_forward_slab(ctx, P, p->lights, reduce_slab, s);
   } else {
     cudaMemsetAsync(reduce_slab, 0, 8 * sizeof(float), s);

@@ -120,9 +120,9 @@ static inline void vh_prof_end(vhap_ctx* c, int kid, cudaStream_t s) {
 }
 #define LAUNCH(c, kid, s, ...) do { vh_prof_begin((c), (kid), (s)); __VA_ARGS__; vh_prof_end((c), (kid), (s)); } while (0)
 
-// kernel-based zero fill of up to 8 buffers in one launch (byte counts multiples of 4).  Unlike a memset node a kernel inherits the
+// kernel-based zero fill of up to 12 buffers in one launch (byte counts multiples of 4).  Unlike a memset node a kernel inherits the
 // priority of its stream, so the step's latency-critical chain is not queued behind the CTAs of a concurrently running bulk kernel.
-struct VhZeroSegs { int n; void* p[8]; size_t bytes[8]; };
+struct VhZeroSegs { int n; void* p[12]; size_t bytes[12]; };
 void vh_zero_multi(vhap_ctx* c, const VhZeroSegs& z, cudaStream_t s);
 static inline void vh_zero(vhap_ctx* c, void* p, size_t bytes, cudaStream_t s) { VhZeroSegs z; z.n = 1; z.p[0] = p; z.bytes[0] = bytes; vh_zero_multi(c, z, s); }
 
@@ -145,7 +145,7 @@ void launch_rast_out(vhap_ctx* c, const f4* clip, int B, int H, int W, const int
 void launch_scan(vhap_ctx* c, const int* in, int* out, int n, int* total, cudaStream_t s);
 // render.cu
 void fill_render_args(vhap_ctx* c, PassArgs& P, const vhap_frame_batch* fb, const vhap_stage_cfg* cfg, const float* lights);
-void launch_render_forward(vhap_ctx* c, PassArgs& P, cudaStream_t s);
+void launch_render_forward(vhap_ctx* c, PassArgs& P, cudaStream_t s, bool zeroed = false);   // zeroed: maxslot / pair_count already cleared by the caller
 void launch_render_finalize(vhap_ctx* c, PassArgs& P, const vhap_stage_cfg* cfg, const float* reduce_slab, int global_B, const float* lights, cudaStream_t s);
 void launch_render_backward(vhap_ctx* c, PassArgs& P, const vhap_stage_cfg* cfg, const float* lights, float* g_lights, const float* ext_grad, cudaStream_t s,
                             cudaStream_t side = nullptr);

@@ -63,20 +63,19 @@ __global__ void __launch_bounds__(PB) k_pool_count(const int* __restrict__ tri_i
   if (threadIdx.x < 16) blk_count[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = cnt[threadIdx.x];    // [16][nblk]
 }
 
-// base / count of every cluster from the scanned [16][nblk] offsets (scanned as ONE sequence: lists laid out cluster after cluster)
-__global__ void k_pool_bases(const int* __restrict__ off, int nblk, const int* __restrict__ total, int* __restrict__ base, int* __restrict__ count) {
-  int c = threadIdx.x;
-  if (c >= 16) return;
-  int b = off[(size_t)c * nblk];
-  int e = c < 15 ? off[(size_t)(c + 1) * nblk] : *total;
-  base[c] = b; count[c] = e - b;
-}
-
 // also emits the list of adjacent pixel pairs with different ids (pair = pixel0 * 2 + direction) for the antialias analysis
 __global__ void __launch_bounds__(PB) k_pool_scatter(const int* __restrict__ tri_id, const uint8_t* __restrict__ fid2cid, size_t n, int H, int W, int ncl,
                                                      const int* __restrict__ blk_off, int* __restrict__ pool_list, int* __restrict__ pool_tri,
-                                                     int* __restrict__ pair_list, int* __restrict__ pair_count) {
+                                                     int* __restrict__ pair_list, int* __restrict__ pair_count,
+                                                     const int* __restrict__ total, int* __restrict__ base, int* __restrict__ count) {
   __shared__ int wcnt[16][PB / 32];
+  // base / count of every cluster from the scanned [16][nblk] offsets (lists laid out cluster after cluster): read by the passes that
+  // follow this kernel, written here by the first CTA (was a launch of its own)
+  if (blockIdx.x == 0 && threadIdx.x < 16) {
+    const int c = threadIdx.x, nb = gridDim.x;
+    const int b = blk_off[(size_t)c * nb], e = c < 15 ? blk_off[(size_t)(c + 1) * nb] : *total;
+    base[c] = b; count[c] = e - b;
+  }
   size_t pix = (size_t)blockIdx.x * PB + threadIdx.x;
   int id = pix < n ? tri_id[pix] : -1;
   int cid = pix < n ? fid2cid[id] : -1;
@@ -460,19 +459,19 @@ static int* slot_table(vhap_ctx* c) {      // device copy of the acc[] slots of 
   return d_slot[dev];
 }
 
-void launch_render_forward(vhap_ctx* c, PassArgs& P, cudaStream_t s) {
+void launch_render_forward(vhap_ctx* c, PassArgs& P, cudaStream_t s, bool zeroed) {
   const RenderArgs& A = P.R;
   size_t n = (size_t)A.B * A.H * A.W;
   int nblk = (int)((n + PB - 1) / PB);
   int* slots = slot_table(c);
-  { VhZeroSegs z; z.n = 2; z.p[0] = c->maxslot; z.bytes[0] = sizeof(unsigned long long); z.p[1] = c->pair_count; z.bytes[1] = sizeof(int); vh_zero_multi(c, z, s); }
+  if (!zeroed) { VhZeroSegs z; z.n = 2; z.p[0] = c->maxslot; z.bytes[0] = sizeof(unsigned long long); z.p[1] = c->pair_count; z.bytes[1] = sizeof(int); vh_zero_multi(c, z, s); }
   if (c->want_planes) {
     cudaMemsetAsync(c->plane_albedo, 0, n * 16, s); cudaMemsetAsync(c->plane_normal, 0, n * 16, s); cudaMemsetAsync(c->plane_diffuse, 0, n * 16, s);
   }
   LAUNCH(c, KID_POOL_COUNT, s, k_pool_count<<<nblk, PB, 0, s>>>(A.tri_id, A.fid2cid, n, c->n_clusters, c->pool_blk_count));
   launch_scan(c, c->pool_blk_count, c->pool_blk_off, 16 * nblk, c->scan_total, s);
-  LAUNCH(c, KID_POOL_SCAN, s, k_pool_bases<<<1, 32, 0, s>>>(c->pool_blk_off, nblk, c->scan_total, c->pool_base, c->pool_count));
-  LAUNCH(c, KID_POOL_SCATTER, s, k_pool_scatter<<<nblk, PB, 0, s>>>(A.tri_id, A.fid2cid, n, A.H, A.W, c->n_clusters, c->pool_blk_off, c->pool_list, c->pool_tri, c->pair_list, c->pair_count));
+  LAUNCH(c, KID_POOL_SCATTER, s, k_pool_scatter<<<nblk, PB, 0, s>>>(A.tri_id, A.fid2cid, n, A.H, A.W, c->n_clusters, c->pool_blk_off, c->pool_list, c->pool_tri, c->pair_list, c->pair_count,
+                                                                   c->scan_total, c->pool_base, c->pool_count));
   int grid = nblk < NPERSIST ? nblk : NPERSIST;
   // a deferred texture update (vhap_set_render_wait_event) is joined here: everything above is independent of the texture
   if (c->render_wait_ev) { cudaStreamWaitEvent(s, c->render_wait_ev, 0); c->render_wait_ev = nullptr; }
