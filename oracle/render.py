@@ -310,3 +310,40 @@ def render_rgba(rast, rast_db, verts, verts_clip, faces, verts_uv, faces_uv, tex
     out.update(albedo=albedo.flip(1), normal=normal.flip(1), diffuse=diffuse.flip(1),
                diffuse_detach_normal=diffuse_detach_normal.flip(1), rgba=rgba_aa.flip(1), rgba_pre=rgba_pre.flip(1))
     return out
+
+
+def render_rgba_vis(rast, rast_db, verts, verts_clip, faces, adj_opp, background=(1.0, 1.0, 1.0), verts_uv=None, faces_uv=None, tex=None,
+                    lights=None):
+    """NVDiffRenderer.render_rgba_vis (render_nvdiffrast.py:486-567) for shade_smooth=True, lighting_space='world': the visualisation
+    render of the viewer / editor / NeRF export (flame_viewer.py:327, export_as_nerf_dataset.py:436).  Differences from render_rgba: no
+    disturbance and no detaches, `normal` and `diffuse` carry the background outside the mesh (:553-554), the albedo is 1 without a
+    texture (:531), and `lights=None` means lighting_type 'constant' (diffuse = 1, :332-333).  The per-vertex colour branch (:526-530) is
+    not restated (the engine has no such input).  Returns [B,H,W,C] planes in image orientation."""
+    B, H, W, _ = rast.shape
+    dt = rast.dtype
+    ids = rast[..., 3].long()
+    fg = (ids > 0)[..., None]
+    normal, _ = interpolate(compute_v_normals(verts, faces), rast, faces)
+    normal = safe_normalize(normal)
+    if verts_uv is not None and faces_uv is not None and tex is not None:
+        texc, texd = interpolate(verts_uv[None], rast, faces_uv, rast_db)
+        mips = build_mips(tex.permute(1, 2, 0))
+        bi, yi, xi = torch.nonzero(fg[..., 0], as_tuple=True)
+        alb_bg = _bilinear_wrap(mips[0], torch.zeros(1, dtype=dt, device=rast.device), torch.zeros(1, dtype=dt, device=rast.device))[0]
+        albedo = alb_bg.expand(B, H, W, 3).clone().index_put((bi, yi, xi), texture_sample(mips, texc[bi, yi, xi], texd[bi, yi, xi]))
+    else:
+        albedo = torch.ones_like(normal)
+    diffuse = sh_shading(normal, lights) if lights is not None else torch.ones_like(normal)
+    rgba = torch.cat([albedo * diffuse, fg.to(dt)], -1)
+    if isinstance(background, (list, tuple)):
+        rgba_bg = torch.tensor(list(background) + [0], dtype=dt, device=rast.device).expand(B, H, W, 4)
+    elif isinstance(background, torch.Tensor):
+        rgba_bg = torch.cat([background.to(dt), torch.zeros_like(background[..., :1], dtype=dt)], -1)
+    else:
+        raise ValueError(f"Unknown background type: {type(background)}")
+    rgba_bg = rgba_bg.flip(1)
+    normal = torch.where(fg, normal, rgba_bg[..., :3])
+    diffuse = torch.where(fg, diffuse, rgba_bg[..., :3])
+    rgba = torch.where(fg, rgba, rgba_bg)
+    rgba_aa = antialias(rgba, rast, verts_clip, faces, adj_opp)
+    return dict(albedo=albedo.flip(1), normal=normal.flip(1), diffuse=diffuse.flip(1), rgba=rgba_aa.flip(1), verts_clip=verts_clip)

@@ -103,3 +103,54 @@ def test_renderer_rasterize_and_render_rgba_autograd():
     assert rel(lights.grad.cpu().numpy(), lo.grad.numpy()) < 2e-3
     assert l2rel(tex.grad.cpu().numpy()[0], texo.grad.numpy()) < 2e-2
     assert l2rel(verts.grad.cpu().numpy(), vo.grad.numpy()) < 0.2       # sliver-pixel conditioning w.r.t. fp32 clip positions, see test_gpu_parity
+
+
+@pytest.mark.parametrize("case", ["tex_sh_img", "bare_black", "tex_sh_grey"])
+def test_render_rgba_vis_matches_oracle(case):
+    """B200Renderer.render_rgba_vis vs oracle/render.py:render_rgba_vis (pinned against the reference's code by
+    tests/golden/make_vis_golden.py) on the same fp32 vertices: planes to 2e-4 outside the pixels whose face id differs"""
+    from oracle import lbs as L, energy as E, camera as Cm, raster as RA, render as RE
+    from vhap_b200.reference_api import B200Renderer
+    sc = make_scene(B=2, H=96, W=128, T=128, n_t=3, timesteps=[0, 2])
+    m, model = sc["m"], sc["model"]
+    B, H, W = 2, 96, 128
+    dev = "cuda:0"
+    rnd = B200Renderer(model=m, tex_size=128)
+    ts = torch.as_tensor(sc["ts"]).long()
+    P = {k: torch.tensor(v, dtype=torch.float64) for k, v in sc["params"].items()}
+    with torch.no_grad():
+        v64, _, _ = L.flame_forward(model, P["shape"][None].expand(B, -1), P["expr"][ts], P["rotation"][ts], P["neck_pose"][ts], P["jaw_pose"][ts],
+                                    P["eyes_pose"][ts], P["translation"][ts], static_offset=P["static_offset"])
+    verts32 = v64.to(torch.float32)
+    K, RT = E.fill_cam_params(P, B, H, W)
+    faces = torch.as_tensor(m.faces.astype(np.int64), device=dev)
+    vuv = torch.as_tensor(m.verts_uv, device=dev).clone(); vuv[:, 1] = 1 - vuv[:, 1]
+    tex = torch.tensor(sc["tex_painted"] + sc["params"]["tex_extra"], device=dev)
+    lights = torch.tensor(sc["params"]["lights"], device=dev)
+    bg_img = sc["rgb16"].to(torch.float32).permute(0, 2, 3, 1).contiguous()
+    textured = case != "bare_black"
+    bg = {"tex_sh_img": bg_img.to(dev), "bare_black": [0.0, 0.0, 0.0], "tex_sh_grey": [0.5, 0.25, 0.75]}[case]
+    kw = dict(verts_uv=vuv, faces_uv=torch.as_tensor(m.faces_uv.astype(np.int64), device=dev), tex=tex[None], lights=lights[None]) if textured else {}
+    out = rnd.render_rgba_vis(verts32.to(dev), faces, RT.to(torch.float32).to(dev), K.to(torch.float32).to(dev), (H, W), bg, **kw)
+    assert set(out) == {"albedo", "normal", "diffuse", "rgba", "verts_clip"}
+    vo = verts32.to(torch.float64)
+    clip = Cm.world_to_clip(vo, RT, K, (H, W))
+    r, rdb = RA.rasterize(clip, model["faces"], (H, W))
+    vuv64 = model["verts_uv"].clone(); vuv64[:, 1] = 1 - vuv64[:, 1]
+    okw = dict(verts_uv=vuv64.to(torch.float32).to(torch.float64), faces_uv=model["faces_uv"], tex=tex.cpu().to(torch.float64), lights=lights.cpu().to(torch.float64)) if textured else {}
+    oo = RE.render_rgba_vis(r, rdb, vo, clip, model["faces"], m.face_adjacency_opposite(), bg_img.to(torch.float64) if case == "tex_sh_img" else bg, **okw)
+    assert np.abs(out["verts_clip"].cpu().numpy() - clip.numpy()).max() < 1e-5
+    fg = (r[..., 3] > 0).flip(1).numpy()
+    assert fg.mean() > 0.1
+    for k, tol in (("albedo", 2e-4), ("normal", 2e-4), ("diffuse", 2e-4), ("rgba", 2e-4)):
+        got, ref = out[k].cpu().numpy(), oo[k].numpy()
+        assert got.shape == ref.shape, k
+        d = np.abs(got - ref).max(-1)
+        if k == "albedo":
+            d = d[fg]                     # outside the mesh nvdiffrast samples texel (0,0); the engine's albedo plane is only defined on the mesh
+        assert (d > tol).mean() < 0.005, (k, (d > tol).mean(), d.max())
+    if not textured:
+        on = out["rgba"][..., 3].cpu().numpy() == 1.0
+        assert np.abs(out["rgba"][..., :3].cpu().numpy()[on] - 1.0).max() < 1e-6            # albedo 1 x constant lighting
+    with pytest.raises(NotImplementedError):
+        rnd.render_rgba_vis(verts32.to(dev), faces, RT.to(torch.float32).to(dev), K.to(torch.float32).to(dev), (H, W), v_color=torch.ones(5143, 3))

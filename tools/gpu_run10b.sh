@@ -8,6 +8,8 @@ timeout 600 python __graft_entry__.py smoke > gpurun_out/r10_smoke.log 2>&1
 timeout 900 python bench.py --steps 30 --warmup 5 > gpurun_out/r10_bench_n1.json 2> gpurun_out/r10_bench_n1.err
 timeout 300 python bench.py --steps 40 --warmup 5 --no-extra --no-cpu --no-pipeline > gpurun_out/r10_bench_n1_nopipe.json 2> gpurun_out/r10_bench_n1_nopipe.err
 VHAP_B200_SO=$PWD/vhap_b200/variants/ns4.so timeout 300 python bench.py --steps 40 --warmup 5 --no-extra --no-cpu > gpurun_out/r10_bench_n1_ns4.json 2> gpurun_out/r10_bench_n1_ns4.err
+VHAP_B200_TEXFOLD_PAD_KB=50 timeout 300 python bench.py --steps 40 --warmup 5 --no-extra --no-cpu > gpurun_out/r10_bench_n1_pad50.json 2> gpurun_out/r10_bench_n1_pad50.err
+VHAP_B200_TEXFOLD_PAD_KB=150 timeout 300 python bench.py --steps 40 --warmup 5 --no-extra --no-cpu > gpurun_out/r10_bench_n1_pad150.json 2> gpurun_out/r10_bench_n1_pad150.err
 timeout 300 python bench.py --steps 40 --warmup 5 --no-extra --no-cpu > gpurun_out/r10_bench_n1_again.json 2> gpurun_out/r10_bench_n1_again.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/r02_launches.csv python tools/prof_step.py --steps 2 > gpurun_out/r10_ncu_launches.log 2>&1
 timeout 300 python tools/timeline.py > gpurun_out/r10_timeline_n1.txt 2> gpurun_out/r10_timeline_n1.err

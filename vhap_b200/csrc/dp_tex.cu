@@ -44,15 +44,24 @@ __device__ __forceinline__ void mc_st(float* mc, float4 v) {
 
 // g_band[i] = sum_r g_rm_r[band_off + i]   (float4 granularity)
 __global__ void __launch_bounds__(256) k_dp_reduce_band(const float* mc, float* const* peers, int world, size_t band_off4, size_t n4, float4* __restrict__ out) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-    float4 s;
-    if (mc) s = mc_ld_reduce(mc + (band_off4 + i) * 4);
-    else {
-      s = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int r = 0; r < world; ++r) {
-        float4 v = __ldcv((const float4*)peers[r] + band_off4 + i);
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-      }
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (mc) {
+    // four independent in-switch reductions in flight per thread: the load-reduce round trip through the NVSwitch is several microseconds
+    // (one per thread at 148 CTAs measured 0.21 TB/s, r10 timeline)
+    for (; i + 3 * stride < n4; i += 4 * stride) {
+      float4 a = mc_ld_reduce(mc + (band_off4 + i) * 4), b = mc_ld_reduce(mc + (band_off4 + i + stride) * 4);
+      float4 c = mc_ld_reduce(mc + (band_off4 + i + 2 * stride) * 4), d = mc_ld_reduce(mc + (band_off4 + i + 3 * stride) * 4);
+      out[i] = a; out[i + stride] = b; out[i + 2 * stride] = c; out[i + 3 * stride] = d;
+    }
+    for (; i < n4; i += stride) out[i] = mc_ld_reduce(mc + (band_off4 + i) * 4);
+    return;
+  }
+  for (; i < n4; i += stride) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < world; ++r) {
+      float4 v = __ldcv((const float4*)peers[r] + band_off4 + i);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
     out[i] = s;
   }
@@ -69,14 +78,13 @@ __global__ void __launch_bounds__(256) k_dp_bcast_band(float* mc, float* const* 
 void launch_dp_barrier(vhap_ctx* c, int which, cudaStream_t s) {
   LAUNCH(c, KID_MISC, s, k_dp_barrier<<<1, 32, 0, s>>>(c->dp_box, c->dp_peers_dev, c->dp_rank, c->dp_world, which, c->dp_epoch + 2, c->dp_err));
 }
-// small grids: the two data kernels are bound by the NVLink / NVSwitch path, not by SM count, and run beside the next step's forward
 void launch_dp_reduce_band(vhap_ctx* c, float* g_band, cudaStream_t s) {
   const size_t nb4 = (size_t)3 * c->T * c->T / c->dp_world / 4;
-  const int grid = (int)((nb4 + 255) / 256 < 148 ? (nb4 + 255) / 256 : 148);
+  const int grid = (int)((nb4 + 1023) / 1024 < 148 * 4 ? (nb4 + 1023) / 1024 : 148 * 4);
   LAUNCH(c, KID_MISC, s, k_dp_reduce_band<<<grid, 256, 0, s>>>(c->dp_grm_mc, c->dp_grm_peers_dev, c->dp_world, nb4 * c->dp_rank, nb4, (float4*)g_band));
 }
 void launch_dp_bcast_band(vhap_ctx* c, const float* ex_band, cudaStream_t s) {
   const size_t nb4 = (size_t)3 * c->T * c->T / c->dp_world / 4;
-  const int grid = (int)((nb4 + 255) / 256 < 148 ? (nb4 + 255) / 256 : 148);
+  const int grid = (int)((nb4 + 255) / 256 < 148 * 4 ? (nb4 + 255) / 256 : 148 * 4);
   LAUNCH(c, KID_MISC, s, k_dp_bcast_band<<<grid, 256, 0, s>>>(c->dp_exrm_mc, c->dp_exrm_peers_dev, c->dp_world, nb4 * c->dp_rank, nb4, (const float4*)ex_band));
 }

@@ -3,6 +3,7 @@
 // frames instead of B expanded copies, tracker.py:234); fold of the texel-gradient pyramid to level 0, total-variation
 // and residual-cluster regularisers (tracker.py:526-539), Adam (torch.optim.Adam, tracker.py:210) and rebuild of level 0,
 // fused into one streaming pass over the 3*T*T texels.
+#include <stdlib.h>
 #include "engine.h"
 #include "accum.h"
 
@@ -538,7 +539,9 @@ static void launch_fold_kernel(vhap_ctx* c, const TexFoldArgs& a, int rows, floa
   const int T = c->T, tw = T < 256 ? T : 256, R = T < TF_ROWS ? T : TF_ROWS, nblk = (T / tw) * (rows / R);
   if (T >= 256 && !c->tex_fold_reg) {
     static bool attr_set = false;
-    const int smem = (int)(TF3_NS * sizeof(TF3Row));
+    static int pad = 0;
+    if (!attr_set) { const char* e = getenv("VHAP_B200_TEXFOLD_PAD_KB"); pad = e ? atoi(e) * 1024 : 0; }      // dev aid: fewer resident CTAs per SM
+    const int smem = (int)(TF3_NS * sizeof(TF3Row)) + pad;
     if (!attr_set) { cudaFuncSetAttribute(k_tex_fold3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
     LAUNCH(c, KID_TEX_FOLD, s, k_tex_fold3<<<nblk, 256, smem, s>>>(a, c->tv_partials, c->tex_counter, acc_out));
   } else {

@@ -314,6 +314,40 @@ class B200Renderer(torch.nn.Module):
                 "diffuse_detach_normal": _sh_shade(normal[..., :3].detach(), lights.reshape(9, 3)),
                 "rgba": rgba, "aa": albedo[..., 3:4].detach().expand(-1, -1, -1, 3).contiguous(), "cid": cid[..., :1].long()}
 
+    # ---- render_rgba_vis (render_nvdiffrast.py:486-567): the visualisation render of the viewer / editor / NeRF export
+    def render_rgba_vis(self, verts, faces, RT, K, image_size, background_color=[1.0, 1.0, 1.0], v_color=None, verts_uv=None, faces_uv=None,
+                        tex=None, lights=None):
+        """same keys as the reference ('albedo', 'normal', 'diffuse', 'rgba', 'verts_clip'), image orientation, no gradients (a
+        visualisation call).  Built from this class's rasterize + render_rgba: no texture -> albedo 1 (:531), no lights -> lighting_type
+        'constant' (diffuse 1, :332-333, realised as the SH vector (1 / c0, 0, ...)), normal / diffuse carry the background outside the
+        mesh (:553-554).  Constant backgrounds other than white / black go through the fp16 image path (rounded to fp16)."""
+        if v_color is not None:
+            raise NotImplementedError("render_rgba_vis: per-vertex colours (render_nvdiffrast.py:526-530) are not an input of the B200 engine")
+        eng = self.eng
+        with torch.no_grad():
+            rd = self.rasterize(verts, faces, RT, K, image_size)
+            B = verts.shape[0]
+            H, W = image_size
+            if tex is None or verts_uv is None or faces_uv is None:
+                tex_, verts_uv, faces_uv = torch.ones(3, eng.T, eng.T, device=eng.dev), None, None
+            else:
+                tex_ = tex
+            if lights is None:
+                lights_ = torch.zeros(9, 3, device=eng.dev); lights_[0] = 1.0 / _SH_CONST[0]
+            else:
+                lights_ = lights.reshape(9, 3)
+            bg = background_color
+            if isinstance(bg, (list, tuple)) and [float(v) for v in bg] not in ([1.0, 1.0, 1.0], [0.0, 0.0, 0.0]):
+                bg = torch.tensor([float(v) for v in bg], device=eng.dev).expand(B, H, W, 3)
+            out = self.render_rgba(rd, verts, faces, verts_uv, faces_uv, tex_, lights_, bg)
+            fg = (rd["rast_out"][..., 3:4] > 0).flip(1)
+            if isinstance(bg, torch.Tensor):
+                bg3 = bg.to(torch.float16).to(torch.float32)
+            else:
+                bg3 = torch.tensor([float(v) for v in bg], device=eng.dev).expand(B, H, W, 3)
+            return {"albedo": out["albedo"], "normal": torch.where(fg, out["normal"], bg3), "diffuse": torch.where(fg, out["diffuse"], bg3),
+                    "rgba": out["rgba"].detach(), "verts_clip": rd["verts_clip"]}
+
 
 class _NormalsFn(torch.autograd.Function):
     @staticmethod
