@@ -183,7 +183,7 @@ extern "C" int vhap_ctx_create(vhap_ctx** out, const vhap_mesh_desc* m, int32_t 
   for (int i = 0; i < EV_COUNT; ++i) CK(cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming));
   ctx->n_l0_regions = (tex_size >= 8 ? tex_size / 8 : 1) * (tex_size >= 256 ? tex_size / 256 : 1);
   { std::vector<int> ones((size_t)ctx->n_l0_regions, 1); UP(ctx->tex_l0_flag, ones.data(), (size_t)ctx->n_l0_regions); }   // conservative first fold
-  CK(cudaMalloc(&ctx->scan_state, (VH_SCAN_MAX_BLOCKS + 1) * sizeof(unsigned long long)));
+  CK(cudaMalloc(&ctx->scan_state, (VH_SCAN_MAX_BLOCKS + 2) * sizeof(unsigned long long))); CK(cudaMemset(ctx->scan_state, 0, (VH_SCAN_MAX_BLOCKS + 2) * sizeof(unsigned long long)));
   CK(cudaMalloc(&ctx->tex_loss, 4 * sizeof(float))); CK(cudaMemset(ctx->tex_loss, 0, 4 * sizeof(float)));
   CK(cudaMalloc(&ctx->tex_counter, sizeof(unsigned))); CK(cudaMemset(ctx->tex_counter, 0, sizeof(unsigned)));
   return 0;
@@ -285,17 +285,17 @@ static int check_batch(vhap_ctx* ctx, const vhap_frame_batch* fb) {
 }
 #define LAST() do { cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) { vh_set_error(ctx, "kernel launch", cudaGetErrorString(_e)); return -5; } } while (0)
 
-__global__ void k_copy_verts(const f4* __restrict__ v4, float* __restrict__ out, size_t n) {
+__global__ void k_copy_verts(const f4* __restrict__ v4, float* __restrict__ out, size_t n) { VH_PDL_SYNC();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   f4 v = v4[i]; out[i * 3] = v.x; out[i * 3 + 1] = v.y; out[i * 3 + 2] = v.z;
 }
-__global__ void k_load_gverts(const float* __restrict__ g3, float* __restrict__ g4, size_t n) {
+__global__ void k_load_gverts(const float* __restrict__ g3, float* __restrict__ g4, size_t n) { VH_PDL_SYNC();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   g4[i * 4] = g3[i * 3]; g4[i * 4 + 1] = g3[i * 3 + 1]; g4[i * 4 + 2] = g3[i * 3 + 2]; g4[i * 4 + 3] = 0.f;
 }
-__global__ void k_project_only(const float* __restrict__ verts, const CamParams* __restrict__ cam, int V, int H, int W, float* __restrict__ clip) {
+__global__ void k_project_only(const float* __restrict__ verts, const CamParams* __restrict__ cam, int V, int H, int W, float* __restrict__ clip) { VH_PDL_SYNC();
   int v = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
   if (v >= V) return;
   const float* p = verts + ((size_t)b * V + v) * 3;
@@ -310,7 +310,7 @@ __global__ void k_project_only(const float* __restrict__ verts, const CamParams*
   o[0] = p00 * cx_ + p02 * cz_; o[1] = p11 * cy_ + p12 * cz_; o[2] = p22 * cz_ + p23; o[3] = -cz_;
 }
 
-__global__ void __launch_bounds__(256) k_zero_multi(VhZeroSegs z) {
+__global__ void __launch_bounds__(256) k_zero_multi(VhZeroSegs z) { VH_PDL_SYNC();
   const int sgm = blockIdx.y;
   if (sgm >= z.n) return;
   const size_t n4 = z.bytes[sgm] >> 2;
@@ -329,17 +329,18 @@ void vh_zero_multi(vhap_ctx* c, const VhZeroSegs& z, cudaStream_t s) {
   for (int i = 0; i < z.n; ++i) mx = z.bytes[i] > mx ? z.bytes[i] : mx;
   int nb = (int)((mx / 16 + 255) / 256);
   nb = nb < 1 ? 1 : (nb > 148 * 4 ? 148 * 4 : nb);
-  LAUNCH(c, KID_MISC, s, k_zero_multi<<<dim3(nb, z.n), 256, 0, s>>>(z));
+  LAUNCH(c, KID_MISC, s, vh_launch(k_zero_multi, dim3(nb, z.n), 256, 0, s, z));
 }
 
 // per-step scratch of the backward pass + the loss accumulators, one launch
-static void zero_backward_scratch(vhap_ctx* c, int B, cudaStream_t s, bool with_acc = false) {
+static void zero_backward_scratch(vhap_ctx* c, int B, cudaStream_t s, bool with_acc = false, int ntiles = 0) {
   size_t V = c->V;
   VhZeroSegs z; z.n = 0;
   auto add = [&](void* p, size_t bytes) { z.p[z.n] = p; z.bytes[z.n] = bytes; ++z.n; };
   add(c->g_verts, B * V * 4 * sizeof(float)); add(c->g_clip, B * V * 4 * sizeof(float)); add(c->g_vnorm, B * V * 4 * sizeof(float));
   add(c->gA, (size_t)B * 60 * sizeof(float)); add(c->gpf, (size_t)B * 36 * sizeof(float)); add(c->gbetas, (size_t)B * c->K * sizeof(float));
-  if (with_acc) { add(c->acc, ACC_COUNT * sizeof(float)); add(c->maxslot, sizeof(unsigned long long)); add(c->pair_count, sizeof(int)); }   // (12 segments max)
+  if (with_acc) { add(c->acc, ACC_COUNT * sizeof(float)); add(c->maxslot, sizeof(unsigned long long)); add(c->pair_count, sizeof(int)); }
+  if (ntiles) { add(c->tile_count, sizeof(int) * ntiles); add(c->tile_cursor, sizeof(int) * ntiles); }      // the rasteriser's bins (12 segments max)
   vh_zero_multi(c, z, s);
 }
 
@@ -349,7 +350,7 @@ extern "C" int vhap_flame_forward(vhap_ctx* ctx, const vhap_params* p, const vha
   launch_cam_setup(ctx, p, fb, s);
   launch_flame_forward(ctx, p, fb, s);
   size_t n = (size_t)fb->B * ctx->V;
-  if (verts) LAUNCH(ctx, KID_MISC, s, k_copy_verts<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ctx->verts, verts, n));
+  if (verts) LAUNCH(ctx, KID_MISC, s, vh_launch(k_copy_verts, (unsigned)((n + 255) / 256), 256, 0, s, ctx->verts, verts, n));
   if (verts_cano) cudaMemcpyAsync(verts_cano, ctx->v_shaped, n * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s);
   if (lmks) launch_landmarks(ctx, fb, 0.f, 0, lmks, nullptr, 0, 0, fb->B, s);
   LAST();
@@ -362,7 +363,7 @@ extern "C" int vhap_flame_backward(vhap_ctx* ctx, const vhap_params* p, const vh
   if (check_batch(ctx, fb)) return -4;
   zero_backward_scratch(ctx, fb->B, s);
   size_t n = (size_t)fb->B * ctx->V;
-  if (g_verts) LAUNCH(ctx, KID_MISC, s, k_load_gverts<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(g_verts, ctx->g_verts, n));
+  if (g_verts) LAUNCH(ctx, KID_MISC, s, vh_launch(k_load_gverts, (unsigned)((n + 255) / 256), 256, 0, s, g_verts, ctx->g_verts, n));
   if (g_lmks) launch_landmarks(ctx, fb, 0.f, 0, nullptr, (float*)g_lmks, 0, 0, fb->B, s);
   launch_flame_backward(ctx, p, fb, g, 0, s);
   LAST();
@@ -374,7 +375,7 @@ extern "C" int vhap_project(vhap_ctx* ctx, const vhap_params* p, const vhap_fram
   if (check_batch(ctx, fb)) return -4;
   launch_cam_setup(ctx, p, fb, s);
   dim3 g((ctx->V + 127) / 128, fb->B);
-  LAUNCH(ctx, KID_MISC, s, k_project_only<<<g, 128, 0, s>>>(verts, ctx->cam, ctx->V, fb->H, fb->W, verts_clip));
+  LAUNCH(ctx, KID_MISC, s, vh_launch(k_project_only, g, 128, 0, s, verts, ctx->cam, ctx->V, fb->H, fb->W, verts_clip));
   LAST();
   return 0;
 }
@@ -405,7 +406,7 @@ extern "C" int vhap_tex_rebuild(vhap_ctx* ctx, const float* tex_extra, void* str
 }
 
 __global__ void k_assemble_losses(const float* __restrict__ acc, vhap_stage_cfg cfg, float max_hw, float* __restrict__ g_focal, int add_focal,
-                                  float* __restrict__ out, const float* __restrict__ tex_loss = nullptr) {
+                                  float* __restrict__ out, const float* __restrict__ tex_loss = nullptr) { VH_PDL_SYNC();
   if (threadIdx.x != 0) return;
   if (add_focal && g_focal) g_focal[0] += (acc[ACC_GFX] + acc[ACC_GFY]) * max_hw;       // fx = fy = focal * max(h,w) (tracker.py:153)
   if (!out) return;
@@ -426,10 +427,10 @@ extern "C" int vhap_energy_forward(vhap_ctx* ctx, const vhap_params* p, const vh
                                    void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (check_batch(ctx, fb)) return -4;
-  zero_backward_scratch(ctx, fb->B, s, true);
-  launch_cam_setup(ctx, p, fb, s);
-  launch_flame_forward(ctx, p, fb, s);
-  if (cfg->photometric && cfg->w_photo >= 0.f) {
+  const bool photo = cfg->photometric && cfg->w_photo >= 0.f;
+  zero_backward_scratch(ctx, fb->B, s, true, photo ? fb->B * ((fb->H + VH_TILE - 1) / VH_TILE) * ((fb->W + VH_TILE - 1) / VH_TILE) : 0);
+  launch_flame_forward(ctx, p, fb, s, true);            // (+ camera set-up)
+  if (photo) {
     // fork: vertex normals (needed only by the shading pass) run on aux stream 0 while the rasteriser runs on the main stream
     const bool vn_overlap = !ctx->no_overlap;
     if (vn_overlap) {
@@ -438,7 +439,7 @@ extern "C" int vhap_energy_forward(vhap_ctx* ctx, const vhap_params* p, const vh
       launch_vnormals(ctx, fb->geo ? fb->n_geo : fb->B, ctx->aux[0]);
       cudaEventRecord(ctx->ev[EV_VN_DONE], ctx->aux[0]);
     } else launch_vnormals(ctx, fb->geo ? fb->n_geo : fb->B, s);
-    launch_raster(ctx, ctx->clip, ctx->snap, fb->B, fb->H, fb->W, ctx->tri_id, 0, 0, s);
+    launch_raster(ctx, ctx->clip, ctx->snap, fb->B, fb->H, fb->W, ctx->tri_id, 0, 0, s, true);      // (bins cleared with the step's scratch above)
     if (vn_overlap) cudaStreamWaitEvent(s, ctx->ev[EV_VN_DONE], 0);
     PassArgs P;
     fill_render_args(ctx, P, fb, cfg, p->lights);
@@ -502,7 +503,7 @@ extern "C" int vhap_energy_backward(vhap_ctx* ctx, const vhap_params* p, const v
   if (regs_forked) cudaStreamWaitEvent(s, ctx->ev[EV_REGS_DONE], 0);        // join the side chain (landmarks, regularisers)
   if (!lights_joined) cudaStreamWaitEvent(s, ctx->ev[EV_LIGHTS_DONE], 0);   // ... and the light-gradient reduction
   float max_hw = (float)(fb->H > fb->W ? fb->H : fb->W);
-  LAUNCH(ctx, KID_ASSEMBLE, s, k_assemble_losses<<<1, 32, 0, s>>>(ctx->acc, *cfg, max_hw, gg->focal_length, opt_cam, losses_out, ctx->tex_loss));
+  LAUNCH(ctx, KID_ASSEMBLE, s, vh_launch(k_assemble_losses, 1, 32, 0, s, ctx->acc, *cfg, max_hw, gg->focal_length, opt_cam, losses_out, ctx->tex_loss));
   LAST();
   return 0;
 }
@@ -553,7 +554,7 @@ extern "C" int vhap_tex_reg_fold_adam(vhap_ctx* ctx, float* tex_extra, float* g_
   }
   if (losses_out) {
     // add the two texture terms to the loss vector produced by vhap_energy_backward
-    LAUNCH(ctx, KID_ASSEMBLE, (cudaStream_t)stream, k_assemble_losses<<<1, 32, 0, (cudaStream_t)stream>>>(ctx->acc, *cfg, 0.f, nullptr, 0, losses_out, ctx->tex_loss));
+    LAUNCH(ctx, KID_ASSEMBLE, (cudaStream_t)stream, vh_launch(k_assemble_losses, 1, 32, 0, (cudaStream_t)stream, ctx->acc, *cfg, 0.f, nullptr, 0, losses_out, ctx->tex_loss));
   }
   LAST();
   return 0;
@@ -710,7 +711,7 @@ extern "C" int vhap_tex_reg_loss(vhap_ctx* ctx, const float* tex_extra, const vh
 }
 // re-assemble the loss vector of the step that just ran (accumulators + the current texture-regulariser loss values)
 extern "C" int vhap_assemble_losses(vhap_ctx* ctx, const vhap_stage_cfg* cfg, float* losses_out, void* stream) {
-  LAUNCH(ctx, KID_ASSEMBLE, (cudaStream_t)stream, k_assemble_losses<<<1, 32, 0, (cudaStream_t)stream>>>(ctx->acc, *cfg, 0.f, nullptr, 0, losses_out, ctx->tex_loss));
+  LAUNCH(ctx, KID_ASSEMBLE, (cudaStream_t)stream, vh_launch(k_assemble_losses, 1, 32, 0, (cudaStream_t)stream, ctx->acc, *cfg, 0.f, nullptr, 0, losses_out, ctx->tex_loss));
   LAST();
   return 0;
 }
@@ -729,17 +730,17 @@ extern "C" int vhap_adam(vhap_ctx* ctx, float* param, const float* grad, float* 
 }
 
 // ---------------------------------------------------------------------------------------------- modular entry points
-__global__ void k_3to4(const float* __restrict__ a, float* __restrict__ b, size_t n, float w) {
+__global__ void k_3to4(const float* __restrict__ a, float* __restrict__ b, size_t n, float w) { VH_PDL_SYNC();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   b[i * 4] = a[i * 3]; b[i * 4 + 1] = a[i * 3 + 1]; b[i * 4 + 2] = a[i * 3 + 2]; b[i * 4 + 3] = w;
 }
-__global__ void k_4to3_add(const float* __restrict__ a, float* __restrict__ b, size_t n) {
+__global__ void k_4to3_add(const float* __restrict__ a, float* __restrict__ b, size_t n) { VH_PDL_SYNC();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   b[i * 3] += a[i * 4]; b[i * 3 + 1] += a[i * 4 + 1]; b[i * 3 + 2] += a[i * 4 + 2];
 }
-__global__ void k_4to3(const float* __restrict__ a, float* __restrict__ b, size_t n) {
+__global__ void k_4to3(const float* __restrict__ a, float* __restrict__ b, size_t n) { VH_PDL_SYNC();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   b[i * 3] = a[i * 4]; b[i * 3 + 1] = a[i * 4 + 1]; b[i * 3 + 2] = a[i * 4 + 2];
@@ -752,9 +753,9 @@ extern "C" int vhap_vertex_normals(vhap_ctx* ctx, const float* verts, int32_t B,
   vhap_frame_batch fb; memset(&fb, 0, sizeof(fb)); fb.B = B; fb.H = ctx->maxH; fb.W = ctx->maxW;
   if (check_batch(ctx, &fb)) return -4;
   size_t n = (size_t)B * ctx->V;
-  LAUNCH(ctx, KID_MISC, s, k_3to4<<<GRID1(n), 0, s>>>(verts, (float*)ctx->verts, n, 1.f));
+  LAUNCH(ctx, KID_MISC, s, vh_launch(k_3to4, GRID1(n), 0, s, verts, (float*)ctx->verts, n, 1.f));
   launch_vnormals(ctx, B, s);
-  LAUNCH(ctx, KID_MISC, s, k_4to3<<<GRID1(n), 0, s>>>((const float*)ctx->vnorm, vnorm, n));
+  LAUNCH(ctx, KID_MISC, s, vh_launch(k_4to3, GRID1(n), 0, s, (const float*)ctx->vnorm, vnorm, n));
   LAST();
   return 0;
 }
@@ -762,18 +763,18 @@ extern "C" int vhap_vertex_normals(vhap_ctx* ctx, const float* verts, int32_t B,
 extern "C" int vhap_vertex_normals_backward(vhap_ctx* ctx, const float* verts, const float* g_vnorm, int32_t B, float* g_verts, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   size_t n = (size_t)B * ctx->V;
-  LAUNCH(ctx, KID_MISC, s, k_3to4<<<GRID1(n), 0, s>>>(verts, (float*)ctx->verts, n, 1.f));
+  LAUNCH(ctx, KID_MISC, s, vh_launch(k_3to4, GRID1(n), 0, s, verts, (float*)ctx->verts, n, 1.f));
   launch_vnormals(ctx, B, s);
-  LAUNCH(ctx, KID_MISC, s, k_3to4<<<GRID1(n), 0, s>>>(g_vnorm, ctx->g_vnorm, n, 0.f));
+  LAUNCH(ctx, KID_MISC, s, vh_launch(k_3to4, GRID1(n), 0, s, g_vnorm, ctx->g_vnorm, n, 0.f));
   cudaMemsetAsync(ctx->g_verts, 0, n * 4 * sizeof(float), s);
   launch_vnormals_bwd(ctx, B, s);
-  LAUNCH(ctx, KID_MISC, s, k_4to3_add<<<GRID1(n), 0, s>>>(ctx->g_verts, g_verts, n));
+  LAUNCH(ctx, KID_MISC, s, vh_launch(k_4to3_add, GRID1(n), 0, s, ctx->g_verts, g_verts, n));
   LAST();
   return 0;
 }
 
 __global__ void k_project_bwd(const float* __restrict__ verts, const float* __restrict__ g_clip, const CamParams* __restrict__ cam, int V, int H, int W,
-                              float* __restrict__ g_verts, float* __restrict__ g_fxfy /* [2] accumulators */) {
+                              float* __restrict__ g_verts, float* __restrict__ g_fxfy /* [2] accumulators */) { VH_PDL_SYNC();
   int v = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
   if (v >= V) return;
   const float* p = verts + ((size_t)b * V + v) * 3;
@@ -797,10 +798,10 @@ extern "C" int vhap_project_backward(vhap_ctx* ctx, const vhap_params* p, const 
   launch_cam_setup(ctx, p, fb, s);
   cudaMemsetAsync(ctx->acc, 0, ACC_COUNT * sizeof(float), s);
   dim3 g((ctx->V + 127) / 128, fb->B);
-  LAUNCH(ctx, KID_MISC, s, k_project_bwd<<<g, 128, 0, s>>>(verts, g_clip, ctx->cam, ctx->V, fb->H, fb->W, g_verts, g_focal ? ctx->acc + ACC_GFX : nullptr));
+  LAUNCH(ctx, KID_MISC, s, vh_launch(k_project_bwd, g, 128, 0, s, verts, g_clip, ctx->cam, ctx->V, fb->H, fb->W, g_verts, g_focal ? ctx->acc + ACC_GFX : nullptr));
   if (g_focal) {
     vhap_stage_cfg dummy; memset(&dummy, 0, sizeof(dummy));
-    LAUNCH(ctx, KID_ASSEMBLE, s, k_assemble_losses<<<1, 32, 0, s>>>(ctx->acc, dummy, (float)(fb->H > fb->W ? fb->H : fb->W), g_focal, 1, nullptr));
+    LAUNCH(ctx, KID_ASSEMBLE, s, vh_launch(k_assemble_losses, 1, 32, 0, s, ctx->acc, dummy, (float)(fb->H > fb->W ? fb->H : fb->W), g_focal, 1, nullptr, nullptr));
   }
   LAST();
   return 0;
@@ -818,7 +819,7 @@ extern "C" int vhap_render_photometric(vhap_ctx* ctx, const vhap_params* p, cons
   cudaMemsetAsync(ctx->acc, 0, ACC_COUNT * sizeof(float), s);
   zero_backward_scratch(ctx, fb->B, s);
   cudaMemcpyAsync(ctx->clip, verts_clip, n * 4 * sizeof(float), cudaMemcpyDeviceToDevice, s);
-  LAUNCH(ctx, KID_MISC, s, k_3to4<<<GRID1(n), 0, s>>>(vnorm, (float*)ctx->vnorm, n, 0.f));
+  LAUNCH(ctx, KID_MISC, s, vh_launch(k_3to4, GRID1(n), 0, s, vnorm, (float*)ctx->vnorm, n, 0.f));
   launch_raster(ctx, ctx->clip, ctx->snap, fb->B, fb->H, fb->W, ctx->tri_id, 0, 1, s);
   PassArgs P;
   fill_render_args(ctx, P, fb, cfg, p->lights);
@@ -831,9 +832,9 @@ extern "C" int vhap_render_photometric(vhap_ctx* ctx, const vhap_params* p, cons
     P.g_tex = g_tex_pyramid;
     launch_render_backward(ctx, P, cfg, p->lights, g_lights, nullptr, s);
     if (g_clip) cudaMemcpyAsync(g_clip, ctx->g_clip, n * 4 * sizeof(float), cudaMemcpyDeviceToDevice, s);
-    if (g_vnorm) LAUNCH(ctx, KID_MISC, s, k_4to3<<<GRID1(n), 0, s>>>(ctx->g_vnorm, g_vnorm, n));
+    if (g_vnorm) LAUNCH(ctx, KID_MISC, s, vh_launch(k_4to3, GRID1(n), 0, s, ctx->g_vnorm, g_vnorm, n));
   }
-  LAUNCH(ctx, KID_ASSEMBLE, s, k_assemble_losses<<<1, 32, 0, s>>>(ctx->acc, *cfg, 0.f, nullptr, 0, losses_out, ctx->tex_loss));
+  LAUNCH(ctx, KID_ASSEMBLE, s, vh_launch(k_assemble_losses, 1, 32, 0, s, ctx->acc, *cfg, 0.f, nullptr, 0, losses_out, ctx->tex_loss));
   LAST();
   return 0;
 }
@@ -854,31 +855,31 @@ extern "C" int vhap_render_rgba_backward(vhap_ctx* ctx, const vhap_params* p, co
   if (g_lights) cudaMemsetAsync(g_lights, 0, 27 * sizeof(float), s);
   launch_render_backward(ctx, P, cfg, p->lights, g_lights, ctx->final_rgba, s);
   if (g_clip) cudaMemcpyAsync(g_clip, ctx->g_clip, n * 4 * sizeof(float), cudaMemcpyDeviceToDevice, s);
-  if (g_vnorm) k_4to3<<<GRID1(n), 0, s>>>(ctx->g_vnorm, g_vnorm, n);
+  if (g_vnorm) vh_launch(k_4to3, GRID1(n), 0, s, ctx->g_vnorm, g_vnorm, n);
   LAST();
   return 0;
 }
 
 // ---- device-resident step counters: make a whole optimisation step replayable as a CUDA graph (no host-varying kernel arguments)
-__global__ void k_step_set(int* d, int adam_step, int global_step) { d[0] = adam_step; d[1] = global_step; }
-__global__ void k_step_advance(int* d) { d[0] += 1; d[1] += 1; }
+__global__ void k_step_set(int* d, int adam_step, int global_step) { VH_PDL_SYNC(); d[0] = adam_step; d[1] = global_step; }
+__global__ void k_step_advance(int* d) { VH_PDL_SYNC(); d[0] += 1; d[1] += 1; }
 // on != 0: kernels read the Adam step ([0], 1-based) and the global RNG step ([1]) from device memory instead of their arguments
 extern "C" int vhap_step_counters(vhap_ctx* ctx, int32_t on, int32_t adam_step, int32_t global_step, void* stream) {
   ctx->use_dev_step = on;
-  LAUNCH(ctx, KID_MISC, (cudaStream_t)stream, k_step_set<<<1, 1, 0, (cudaStream_t)stream>>>(ctx->dev_step, adam_step, global_step));
+  LAUNCH(ctx, KID_MISC, (cudaStream_t)stream, vh_launch(k_step_set, 1, 1, 0, (cudaStream_t)stream, ctx->dev_step, adam_step, global_step));
   LAST();
   return 0;
 }
-__global__ void k_set_float(float* d, float v) { d[0] = v; }
+__global__ void k_set_float(float* d, float v) { VH_PDL_SYNC(); d[0] = v; }
 // learning-rate scale of the captured Adam kernels (torch's ExponentialLR between epochs, tracker.py:1407-1412): with device step
 // counters on, every Adam kernel multiplies its learning rate by this device scalar, so a captured step graph follows the schedule
 extern "C" int vhap_set_lr_scale(vhap_ctx* ctx, float scale, void* stream) {
-  LAUNCH(ctx, KID_MISC, (cudaStream_t)stream, k_set_float<<<1, 1, 0, (cudaStream_t)stream>>>(ctx->dev_lr_scale, scale));
+  LAUNCH(ctx, KID_MISC, (cudaStream_t)stream, vh_launch(k_set_float, 1, 1, 0, (cudaStream_t)stream, ctx->dev_lr_scale, scale));
   LAST();
   return 0;
 }
 extern "C" int vhap_step_advance(vhap_ctx* ctx, void* stream) {
-  LAUNCH(ctx, KID_MISC, (cudaStream_t)stream, k_step_advance<<<1, 1, 0, (cudaStream_t)stream>>>(ctx->dev_step));
+  LAUNCH(ctx, KID_MISC, (cudaStream_t)stream, vh_launch(k_step_advance, 1, 1, 0, (cudaStream_t)stream, ctx->dev_step));
   LAST();
   return 0;
 }

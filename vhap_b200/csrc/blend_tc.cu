@@ -76,7 +76,7 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 //   mode 1 (backward): atomicAdd(out[n * ldo + row], D)                (reduction split over blockIdx.y)
 __global__ void __launch_bounds__(128, 1) k_blend_tc(const float* __restrict__ A, int lda, int rows, const float* __restrict__ Bm, int ldb, int nb,
                                                      int nred, int red_per_cta, int mode, const float* __restrict__ add0,
-                                                     const float* __restrict__ add1, float* __restrict__ out, int ldo) {
+                                                     const float* __restrict__ add1, float* __restrict__ out, int ldo) { VH_PDL_SYNC();
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bar_free[TC_STAGES];     // stage may be overwritten (its MMAs completed)
   __shared__ uint64_t bar_done;                // accumulator complete
@@ -210,7 +210,7 @@ void launch_blend_tc_fwd(vhap_ctx* c, const float* offset, int B, cudaStream_t s
   for (int b0 = 0; b0 < B; b0 += TC_N) {
     int nb = B - b0 < TC_N ? B - b0 : TC_N;
     dim3 g((M + TC_ROWS - 1) / TC_ROWS, 1);
-    LAUNCH(c, KID_BLEND_FWD, s, k_blend_tc<<<g, 128, TC_SMEM_BYTES, s>>>(c->S_bwd, K, M, c->betas + (size_t)b0 * K, K, nb, K, K, 0, c->v_template, offset,
+    LAUNCH(c, KID_BLEND_FWD, s, vh_launch(k_blend_tc, g, 128, TC_SMEM_BYTES, s, c->S_bwd, K, M, c->betas + (size_t)b0 * K, K, nb, K, K, 0, c->v_template, offset,
                                                                          c->v_shaped + (size_t)b0 * M, M));
   }
 }
@@ -223,7 +223,7 @@ void launch_blend_tc_bwd(vhap_ctx* c, int B, cudaStream_t s) {
   for (int b0 = 0; b0 < B; b0 += TC_N) {
     int nb = B - b0 < TC_N ? B - b0 : TC_N;
     dim3 g((K + TC_ROWS - 1) / TC_ROWS, (M + red_per_cta - 1) / red_per_cta);
-    LAUNCH(c, KID_BLEND_BWD, s, k_blend_tc<<<g, 128, TC_SMEM_BYTES, s>>>(c->S_fwd_pad, Mp, K, c->g_vshaped + (size_t)b0 * Mp, Mp, nb, M, red_per_cta, 1, nullptr,
+    LAUNCH(c, KID_BLEND_BWD, s, vh_launch(k_blend_tc, g, 128, TC_SMEM_BYTES, s, c->S_fwd_pad, Mp, K, c->g_vshaped + (size_t)b0 * Mp, Mp, nb, M, red_per_cta, 1, nullptr,
                                                                          nullptr, c->gbetas + (size_t)b0 * K, K));
   }
 }

@@ -20,7 +20,7 @@
 // Reuse is safe: a rank overwrites its g_rm (next fold) only after it passed barrier B, i.e. after every peer finished reducing; a rank
 // writes into a peer's ex_rm (next broadcast) only after that peer passed barrier A again, i.e. after its rebuild of this step.
 #define DP_FLAG_OFF(which) ((size_t)2 * VH_DP_MAX * 8 + (size_t)(1 + (which)) * VH_DP_MAX)      // after the slab slots and the slab flags
-__global__ void k_dp_barrier(float* mine, float* const* peers, int rank, int world, int which, int* epoch, int* err) {
+__global__ void k_dp_barrier(float* mine, float* const* peers, int rank, int world, int which, int* epoch, int* err) { VH_PDL_SYNC();
   if (threadIdx.x != 0) return;
   const int e = epoch[which] + 1;
   epoch[which] = e;
@@ -43,7 +43,7 @@ __device__ __forceinline__ void mc_st(float* mc, float4 v) {
 }
 
 // g_band[i] = sum_r g_rm_r[band_off + i]   (float4 granularity)
-__global__ void __launch_bounds__(256) k_dp_reduce_band(const float* mc, float* const* peers, int world, size_t band_off4, size_t n4, float4* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_dp_reduce_band(const float* mc, float* const* peers, int world, size_t band_off4, size_t n4, float4* __restrict__ out) { VH_PDL_SYNC();
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (mc) {
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) k_dp_reduce_band(const float* mc, float* 
   }
 }
 // every rank's ex_rm[band_off + i] = ex_band[i]
-__global__ void __launch_bounds__(256) k_dp_bcast_band(float* mc, float* const* peers, int world, size_t band_off4, size_t n4, const float4* __restrict__ in) {
+__global__ void __launch_bounds__(256) k_dp_bcast_band(float* mc, float* const* peers, int world, size_t band_off4, size_t n4, const float4* __restrict__ in) { VH_PDL_SYNC();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     float4 v = in[i];
     if (mc) mc_st(mc + (band_off4 + i) * 4, v);
@@ -76,15 +76,15 @@ __global__ void __launch_bounds__(256) k_dp_bcast_band(float* mc, float* const* 
 }
 
 void launch_dp_barrier(vhap_ctx* c, int which, cudaStream_t s) {
-  LAUNCH(c, KID_MISC, s, k_dp_barrier<<<1, 32, 0, s>>>(c->dp_box, c->dp_peers_dev, c->dp_rank, c->dp_world, which, c->dp_epoch + 2, c->dp_err));
+  LAUNCH(c, KID_MISC, s, vh_launch(k_dp_barrier, 1, 32, 0, s, c->dp_box, c->dp_peers_dev, c->dp_rank, c->dp_world, which, c->dp_epoch + 2, c->dp_err));
 }
 void launch_dp_reduce_band(vhap_ctx* c, float* g_band, cudaStream_t s) {
   const size_t nb4 = (size_t)3 * c->T * c->T / c->dp_world / 4;
   const int grid = (int)((nb4 + 1023) / 1024 < 148 * 4 ? (nb4 + 1023) / 1024 : 148 * 4);
-  LAUNCH(c, KID_MISC, s, k_dp_reduce_band<<<grid, 256, 0, s>>>(c->dp_grm_mc, c->dp_grm_peers_dev, c->dp_world, nb4 * c->dp_rank, nb4, (float4*)g_band));
+  LAUNCH(c, KID_MISC, s, vh_launch(k_dp_reduce_band, grid, 256, 0, s, c->dp_grm_mc, c->dp_grm_peers_dev, c->dp_world, nb4 * c->dp_rank, nb4, (float4*)g_band));
 }
 void launch_dp_bcast_band(vhap_ctx* c, const float* ex_band, cudaStream_t s) {
   const size_t nb4 = (size_t)3 * c->T * c->T / c->dp_world / 4;
   const int grid = (int)((nb4 + 255) / 256 < 148 * 4 ? (nb4 + 255) / 256 : 148 * 4);
-  LAUNCH(c, KID_MISC, s, k_dp_bcast_band<<<grid, 256, 0, s>>>(c->dp_exrm_mc, c->dp_exrm_peers_dev, c->dp_world, nb4 * c->dp_rank, nb4, (const float4*)ex_band));
+  LAUNCH(c, KID_MISC, s, vh_launch(k_dp_bcast_band, grid, 256, 0, s, c->dp_exrm_mc, c->dp_exrm_peers_dev, c->dp_world, nb4 * c->dp_rank, nb4, (const float4*)ex_band));
 }

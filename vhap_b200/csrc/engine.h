@@ -1,5 +1,6 @@
 // Internal declarations shared by the translation units of libvhap_b200.so.
 #pragma once
+#include <stdlib.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -64,7 +65,7 @@ struct vhap_ctx {
   int *scan_aux, *scan_total;                     // [1024], [1]
   float* aa_code; int *pair_list, *pair_count;    // [2N], [2N], [1]
   f4* grgb;                                       // [N] d L / d rgb of the compacted foreground pixels
-  unsigned long long* scan_state;                 // [VH_SCAN_MAX_BLOCKS + 1] look-back words + ticket of the single-launch scan
+  unsigned long long* scan_state;                 // [VH_SCAN_MAX_BLOCKS + 2] look-back words + ticket + finished-block count of the single-launch scan (self-clearing)
   int* pool_tri;                                  // rasterised id per pool_list entry
   int* tex_l0_flag; int n_l0_regions;             // [regions] level-0 flags of the texel-gradient pyramid (texture.cu)
   const float* tex_apply_grad; int tex_gout_persistent;
@@ -118,6 +119,31 @@ static inline void vh_prof_end(vhap_ctx* c, int kid, cudaStream_t s) {
   VhProf* p = vh_prof(c);
   if (p->on && p->n[kid] < VH_PROF_SLOTS) { vh_prof_record(p, p->ev[kid][p->n[kid]][1], s); p->n[kid]++; }
 }
+// Programmatic dependent launch: every kernel of the engine is launched with the programmatic-stream-serialization attribute and starts
+// with VH_PDL_SYNC() -- "my dependents may be scheduled" followed by "wait until everything before me in the stream has completed and
+// is visible".  The step is a chain of ~40 short dependent kernels; the launch latency of kernel N+1 (2.7 us between graph nodes, r02
+// timeline) is paid while kernel N still runs, its CTAs sit resident at the wait.  Nothing is read or written before the wait, so the
+// semantics are those of plain stream order.  VHAP_B200_PDL=0 launches without the attribute (the wait is then a no-op).
+#if defined(__CUDA_ARCH__)
+#define VH_PDL_SYNC() do { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); asm volatile("griddepcontrol.wait;" ::: "memory"); } while (0)
+#else
+#define VH_PDL_SYNC() do { } while (0)
+#endif
+static inline int vh_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("VHAP_B200_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on;
+}
+template <typename... KArgs, typename... Args>
+static inline void vh_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = vh_pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<Args&&>(args)...);
+}
 #define LAUNCH(c, kid, s, ...) do { vh_prof_begin((c), (kid), (s)); __VA_ARGS__; vh_prof_end((c), (kid), (s)); } while (0)
 
 // kernel-based zero fill of up to 12 buffers in one launch (byte counts multiples of 4).  Unlike a memset node a kernel inherits the
@@ -128,7 +154,7 @@ static inline void vh_zero(vhap_ctx* c, void* p, size_t bytes, cudaStream_t s) {
 
 // flame.cu
 void launch_cam_setup(vhap_ctx* c, const vhap_params* p, const vhap_frame_batch* fb, cudaStream_t s);
-void launch_flame_forward(vhap_ctx* c, const vhap_params* p, const vhap_frame_batch* fb, cudaStream_t s);
+void launch_flame_forward(vhap_ctx* c, const vhap_params* p, const vhap_frame_batch* fb, cudaStream_t s, bool with_cam = false);   // with_cam: + camera set-up
 void launch_landmarks(vhap_ctx* c, const vhap_frame_batch* fb, float w_scale, int jawline_off, float* lmks_out, float* g_lmk_in,
                       int compute_loss, int opt_cam, int global_B, cudaStream_t s);
 void launch_flame_backward(vhap_ctx* c, const vhap_params* p, const vhap_frame_batch* fb, const vhap_grads* g, int opt_cam, cudaStream_t s);
@@ -140,9 +166,10 @@ void launch_regs(vhap_ctx* c, const vhap_params* p, const vhap_frame_batch* fb, 
 void launch_blend_tc_fwd(vhap_ctx* c, const float* offset, int B, cudaStream_t s);
 void launch_blend_tc_bwd(vhap_ctx* c, int B, cudaStream_t s);
 // raster.cu
-void launch_raster(vhap_ctx* c, const f4* clip, i4* snap, int B, int H, int W, int* tri_id, int cull_backface, int need_snap, cudaStream_t s);
+void launch_raster(vhap_ctx* c, const f4* clip, i4* snap, int B, int H, int W, int* tri_id, int cull_backface, int need_snap, cudaStream_t s,
+                   bool zeroed = false);      // zeroed: tile_count / tile_cursor already cleared by the caller (the step's clear kernel)
 void launch_rast_out(vhap_ctx* c, const f4* clip, int B, int H, int W, const int* tri_id, float* rast, float* rast_db, cudaStream_t s);
-void launch_scan(vhap_ctx* c, const int* in, int* out, int n, int* total, cudaStream_t s);
+void launch_scan(vhap_ctx* c, const int* in, int* out, int n, int* total, cudaStream_t s, int pad4 = 0);
 // render.cu
 void fill_render_args(vhap_ctx* c, PassArgs& P, const vhap_frame_batch* fb, const vhap_stage_cfg* cfg, const float* lights);
 void launch_render_forward(vhap_ctx* c, PassArgs& P, cudaStream_t s, bool zeroed = false);   // zeroed: maxslot / pair_count already cleared by the caller

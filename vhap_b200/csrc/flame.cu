@@ -28,19 +28,21 @@ __device__ float block_sum(float v, float* sh /*[33]*/) {
 }
 
 // ------------------------------------------------------------------------------------------------ camera
-__global__ void k_cam_setup(CamParams* cam, const float* RT, const float* K, const float* focal, int B, int H, int W) {
-  int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
+__device__ __forceinline__ CamParams cam_from(const float* RT, const float* K, const float* focal, int b, int H, int W) {
   CamParams c;
   if (RT) for (int i = 0; i < 12; ++i) c.RT[i] = RT[b * 12 + i];
   else { for (int i = 0; i < 12; ++i) c.RT[i] = 0.f; c.RT[0] = c.RT[5] = c.RT[10] = 1.f; c.RT[11] = -1.f; }   // tracker.py:1335-1337
   if (K) { c.fx = K[b * 4]; c.fy = K[b * 4 + 1]; c.cx = K[b * 4 + 2]; c.cy = K[b * 4 + 3]; }
   else { float f = focal[0] * (float)max(H, W); c.fx = f; c.fy = f; c.cx = 0.5f * W; c.cy = 0.5f * H; }       // tracker.py:141-157
-  cam[b] = c;
+  return c;
+}
+__global__ void k_cam_setup(CamParams* cam, const float* RT, const float* K, const float* focal, int B, int H, int W) { VH_PDL_SYNC();
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) cam[b] = cam_from(RT, K, focal, b, H, W);
 }
 
 void launch_cam_setup(vhap_ctx* c, const vhap_params* p, const vhap_frame_batch* fb, cudaStream_t s) {
-  LAUNCH(c, KID_CAM, s, k_cam_setup<<<(fb->B + 63) / 64, 64, 0, s>>>(c->cam, fb->RT, fb->K, p->focal_length, fb->B, fb->H, fb->W));
+  LAUNCH(c, KID_CAM, s, vh_launch(k_cam_setup, (fb->B + 63) / 64, 64, 0, s, c->cam, fb->RT, fb->K, p->focal_length, fb->B, fb->H, fb->W));
 }
 
 #define VH_NEAR 0.1f
@@ -60,7 +62,7 @@ __global__ void __launch_bounds__(256) k_pose_fwd(
     const float* __restrict__ shape, const float* __restrict__ expr, const float* __restrict__ rot, const float* __restrict__ neck,
     const float* __restrict__ jaw, const float* __restrict__ eyes, const float* __restrict__ offset, const int* __restrict__ ts,
     const float* __restrict__ JS, const float* __restrict__ Jt, const float* __restrict__ Jreg,
-    int V, int K, int n_shape, float* __restrict__ betas_out, PoseFwd* __restrict__ posebuf, float* __restrict__ poses) {
+    int V, int K, int n_shape, float* __restrict__ betas_out, PoseFwd* __restrict__ posebuf, float* __restrict__ poses) { VH_PDL_SYNC();
   __shared__ float sh[33];
   __shared__ float shJ[15];
   int b = blockIdx.x, t = ts[b], n_expr = K - n_shape;
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(256) k_pose_fwd(
 #define BLEND_KS 8
 template <int NB>
 __global__ void __launch_bounds__(128) k_blend_fwd(const float* __restrict__ S, const float* __restrict__ tmpl, const float* __restrict__ offset,
-                                                   const float* __restrict__ betas, int M, int K, int n_shape, int B, float* __restrict__ out) {
+                                                   const float* __restrict__ betas, int M, int K, int n_shape, int B, float* __restrict__ out) { VH_PDL_SYNC();
   extern __shared__ float shb[];      // [NB][K]
   int b0 = blockIdx.y * NB, nb = min(NB, B - b0);
   for (int i = threadIdx.x; i < nb * K; i += blockDim.x) shb[i] = betas[(size_t)b0 * K + i];
@@ -133,7 +135,7 @@ template <int NB>
 __global__ void __launch_bounds__(128) k_skin_fwd(const float* __restrict__ v_part, int KS, float* __restrict__ v_shaped, const float* __restrict__ posedirs, const float* __restrict__ lbs_w,
                                                   const PoseFwd* __restrict__ posebuf, const float* __restrict__ transl, const int* __restrict__ ts,
                                                   const CamParams* __restrict__ cam, int V, int B, int H, int W,
-                                                  float* __restrict__ v_posed, f4* __restrict__ verts, f4* __restrict__ clip, i4* __restrict__ snap, float* __restrict__ ndc) {
+                                                  float* __restrict__ v_posed, f4* __restrict__ verts, f4* __restrict__ clip, i4* __restrict__ snap, float* __restrict__ ndc) { VH_PDL_SYNC();
   __shared__ float shpf[NB][36];
   __shared__ float shA[NB][60];
   int b0 = blockIdx.y * NB, nb = min(NB, B - b0);
@@ -200,7 +202,7 @@ __global__ void __launch_bounds__(128) k_skin_fwd(const float* __restrict__ v_pa
 // view sharing: clip positions, raster snap and NDC of view b from the world vertices of its geometry geo[b] (the projection half of
 // k_skin_fwd, identical arithmetic)
 __global__ void __launch_bounds__(128) k_project_views(const f4* __restrict__ verts, const int* __restrict__ geo, const CamParams* __restrict__ cam, int V, int H, int W,
-                                                        f4* __restrict__ clip, i4* __restrict__ snap, float* __restrict__ ndc) {
+                                                        f4* __restrict__ clip, i4* __restrict__ snap, float* __restrict__ ndc) { VH_PDL_SYNC();
   int v = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
   if (v >= V) return;
   f4 vw = verts[(size_t)geo[b] * V + v];
@@ -226,7 +228,7 @@ __global__ void __launch_bounds__(128) k_project_views(const f4* __restrict__ ve
 }
 // adjoint: g_verts[geo[b]] += (d clip_b / d world)^T g_clip[b]; focal-length terms into acc (uncalibrated cameras)
 __global__ void __launch_bounds__(128) k_project_views_bwd(const f4* __restrict__ verts, const int* __restrict__ geo, const CamParams* __restrict__ cam, const float* __restrict__ g_clip,
-                                                            int V, int H, int W, int opt_cam, float* __restrict__ g_verts, float* __restrict__ acc) {
+                                                            int V, int H, int W, int opt_cam, float* __restrict__ g_verts, float* __restrict__ acc) { VH_PDL_SYNC();
   __shared__ float shr[33];
   int v = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
   float gfx = 0.f, gfy = 0.f;
@@ -258,13 +260,18 @@ __global__ void __launch_bounds__(128) k_project_views_bwd(const f4* __restrict_
 #define VH_SKIN_NB 2          // frames per CTA in the skinning kernel: 2 fills the machine at B=16 (8 left 82 CTAs for 148 SMs)
 #endif
 // blend-shape coefficients of the batch: beta[b] = [shape | expr[timestep[b]]]
+// (+ the camera set-up of the step as one extra block when cam != NULL: saves a launch at the head of the chain)
 __global__ void k_betas_gather(const float* __restrict__ shape, const float* __restrict__ expr, const int* __restrict__ ts, int K, int n_shape,
-                               float* __restrict__ betas) {
+                               float* __restrict__ betas, int n_geo, CamParams* cam, const float* RT, const float* Kc, const float* focal, int n_views, int H, int W) { VH_PDL_SYNC();
+  if ((int)blockIdx.x == n_geo) {
+    for (int b = threadIdx.x; b < n_views; b += blockDim.x) cam[b] = cam_from(RT, Kc, focal, b, H, W);
+    return;
+  }
   int b = blockIdx.x, t = ts[b], n_expr = K - n_shape;
   for (int k = threadIdx.x; k < K; k += blockDim.x) betas[(size_t)b * K + k] = k < n_shape ? shape[k] : expr[(size_t)t * n_expr + (k - n_shape)];
 }
 
-void launch_flame_forward(vhap_ctx* c, const vhap_params* p, const vhap_frame_batch* fb, cudaStream_t s) {
+void launch_flame_forward(vhap_ctx* c, const vhap_params* p, const vhap_frame_batch* fb, cudaStream_t s, bool with_cam) {
   // view sharing (fb->geo): FLAME runs once per distinct timestep (G geometries), the B views are only projected
   const bool shared = fb->geo != nullptr;
   const int nviews = fb->B;
@@ -274,9 +281,10 @@ void launch_flame_forward(vhap_ctx* c, const vhap_params* p, const vhap_frame_ba
   // on an aux stream beside the tensor-core contraction
   const bool fork = !c->no_overlap;
   cudaStream_t sp = fork ? c->aux[0] : s;
-  LAUNCH(c, KID_POSE_FWD, s, k_betas_gather<<<B, 128, 0, s>>>(p->shape, p->expr, ts, c->K, c->n_shape, c->betas));
+  LAUNCH(c, KID_POSE_FWD, s, vh_launch(k_betas_gather, B + (with_cam ? 1 : 0), 128, 0, s, p->shape, p->expr, ts, c->K, c->n_shape, c->betas, B, c->cam, fb->RT, fb->K, p->focal_length,
+                                       nviews, fb->H, fb->W));
   if (fork) { cudaEventRecord(c->ev[EV_POSE_FORK], s); cudaStreamWaitEvent(sp, c->ev[EV_POSE_FORK], 0); }
-  LAUNCH(c, KID_POSE_FWD, sp, k_pose_fwd<<<B, 256, 0, sp>>>(p->shape, p->expr, p->rotation, p->neck_pose, p->jaw_pose, p->eyes_pose, p->static_offset, ts,
+  LAUNCH(c, KID_POSE_FWD, sp, vh_launch(k_pose_fwd, B, 256, 0, sp, p->shape, p->expr, p->rotation, p->neck_pose, p->jaw_pose, p->eyes_pose, p->static_offset, ts,
                                c->JS, c->Jt, c->Jreg, V, c->K, c->n_shape, nullptr, c->posebuf, c->poses));
   if (fork) cudaEventRecord(c->ev[EV_POSE_DONE], sp);
   int ks = BLEND_KS;
@@ -286,16 +294,16 @@ void launch_flame_forward(vhap_ctx* c, const vhap_params* p, const vhap_frame_ba
     ks = 1; vpart = c->v_shaped;
   } else {
     dim3 g1((M + 127) / 128, (B + VH_MAXB_CHUNK - 1) / VH_MAXB_CHUNK, BLEND_KS);
-    LAUNCH(c, KID_BLEND_FWD, s, k_blend_fwd<VH_MAXB_CHUNK><<<g1, 128, VH_MAXB_CHUNK * c->K * sizeof(float), s>>>(c->S_fwd, c->v_template, p->static_offset, c->betas, M, c->K,
+    LAUNCH(c, KID_BLEND_FWD, s, vh_launch(k_blend_fwd<VH_MAXB_CHUNK>, g1, 128, VH_MAXB_CHUNK * c->K * sizeof(float), s, c->S_fwd, c->v_template, p->static_offset, c->betas, M, c->K,
                                                                                     c->n_shape, B, c->v_shaped_part));
   }
   if (fork) cudaStreamWaitEvent(s, c->ev[EV_POSE_DONE], 0);
   dim3 g2((V + 127) / 128, (B + VH_SKIN_NB - 1) / VH_SKIN_NB);
-  LAUNCH(c, KID_SKIN_FWD, s, k_skin_fwd<VH_SKIN_NB><<<g2, 128, 0, s>>>(vpart, ks, c->v_shaped, c->posedirs, c->lbs_w, c->posebuf, p->translation, ts, shared ? nullptr : c->cam, V, B, fb->H, fb->W,
+  LAUNCH(c, KID_SKIN_FWD, s, vh_launch(k_skin_fwd<VH_SKIN_NB>, g2, 128, 0, s, vpart, ks, c->v_shaped, c->posedirs, c->lbs_w, c->posebuf, p->translation, ts, shared ? nullptr : c->cam, V, B, fb->H, fb->W,
                                    c->v_posed, c->verts, c->clip, c->snap, c->ndc));
   if (shared) {
     dim3 g3((V + 127) / 128, nviews);
-    LAUNCH(c, KID_SKIN_FWD, s, k_project_views<<<g3, 128, 0, s>>>(c->verts, fb->geo, c->cam, V, fb->H, fb->W, c->clip, c->snap, c->ndc));
+    LAUNCH(c, KID_SKIN_FWD, s, vh_launch(k_project_views, g3, 128, 0, s, c->verts, fb->geo, c->cam, V, fb->H, fb->W, c->clip, c->snap, c->ndc));
   }
 }
 
@@ -306,7 +314,7 @@ __global__ void __launch_bounds__(96) k_landmarks(const f4* __restrict__ verts, 
                                                   const float* __restrict__ lmk_bary, const float* __restrict__ lmk2d, const CamParams* __restrict__ cam,
                                                   int V, int n_lmk, int H, int W, float w_scale, int jawline_off, int compute_loss, int opt_cam,
                                                   float* __restrict__ lmks_out, const float* __restrict__ g_lmk_in, float* __restrict__ g_verts,
-                                                  float* __restrict__ acc, const int* __restrict__ geo) {
+                                                  float* __restrict__ acc, const int* __restrict__ geo) { VH_PDL_SYNC();
   __shared__ float sh[33];
   int b = blockIdx.x, l = threadIdx.x;
   const int gb = geo ? geo[b] : b;               // geometry of this view
@@ -364,13 +372,13 @@ __global__ void __launch_bounds__(96) k_landmarks(const f4* __restrict__ verts, 
 void launch_landmarks(vhap_ctx* c, const vhap_frame_batch* fb, float w_scale, int jawline_off, float* lmks_out, float* g_lmk_in,
                       int compute_loss, int opt_cam, int global_B, cudaStream_t s) {
   (void)global_B;
-  LAUNCH(c, KID_LMK, s, k_landmarks<<<fb->B, 96, 0, s>>>(c->verts, c->faces, c->lmk_faces, c->lmk_bary, fb->lmk2d, c->cam, c->V, c->n_lmk, fb->H, fb->W, w_scale, jawline_off,
+  LAUNCH(c, KID_LMK, s, vh_launch(k_landmarks, fb->B, 96, 0, s, c->verts, c->faces, c->lmk_faces, c->lmk_bary, fb->lmk2d, c->cam, c->V, c->n_lmk, fb->H, fb->W, w_scale, jawline_off,
                                    compute_loss, opt_cam, lmks_out, g_lmk_in, c->g_verts, c->acc, fb->geo));
 }
 
 // ------------------------------------------------------------------------------------------------ vertex normals
 __global__ void __launch_bounds__(128) k_vnormals(const f4* __restrict__ verts, const i4* __restrict__ faces, const int* __restrict__ indptr,
-                                                  const int* __restrict__ vfaces, int V, f4* __restrict__ vnraw, f4* __restrict__ vnorm) {
+                                                  const int* __restrict__ vfaces, int V, f4* __restrict__ vnraw, f4* __restrict__ vnorm) { VH_PDL_SYNC();
   int v = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
   if (v >= V) return;
   const f4* vb = verts + (size_t)b * V;
@@ -390,11 +398,11 @@ __global__ void __launch_bounds__(128) k_vnormals(const f4* __restrict__ verts, 
 }
 void launch_vnormals(vhap_ctx* c, int B, cudaStream_t s) {
   dim3 g((c->V + 127) / 128, B);
-  LAUNCH(c, KID_VNORM, s, k_vnormals<<<g, 128, 0, s>>>(c->verts, c->faces, c->vf_indptr, c->vf_faces, c->V, c->vnraw, c->vnorm));
+  LAUNCH(c, KID_VNORM, s, vh_launch(k_vnormals, g, 128, 0, s, c->verts, c->faces, c->vf_indptr, c->vf_faces, c->V, c->vnraw, c->vnorm));
 }
 
 __global__ void __launch_bounds__(128) k_vnormals_bwd(const f4* __restrict__ verts, const i4* __restrict__ faces, const f4* __restrict__ vnraw,
-                                                      const float* __restrict__ g_vnorm, int V, int F, float* __restrict__ g_verts) {
+                                                      const float* __restrict__ g_vnorm, int V, int F, float* __restrict__ g_verts) { VH_PDL_SYNC();
   int fi = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
   if (fi >= F) return;
   i4 f = faces[fi];
@@ -422,7 +430,7 @@ __global__ void __launch_bounds__(128) k_vnormals_bwd(const f4* __restrict__ ver
 }
 void launch_vnormals_bwd(vhap_ctx* c, int B, cudaStream_t s) {
   dim3 g((c->F + 127) / 128, B);
-  LAUNCH(c, KID_VNORM_BWD, s, k_vnormals_bwd<<<g, 128, 0, s>>>(c->verts, c->faces, c->vnraw, c->g_vnorm, c->V, c->F, c->g_verts));
+  LAUNCH(c, KID_VNORM_BWD, s, vh_launch(k_vnormals_bwd, g, 128, 0, s, c->verts, c->faces, c->vnraw, c->g_vnorm, c->V, c->F, c->g_verts));
 }
 
 // ------------------------------------------------------------------------------------------------ skinning backward
@@ -432,7 +440,7 @@ __global__ void __launch_bounds__(128) k_skin_bwd(const float* __restrict__ v_po
                                                   const int* __restrict__ ts, const float* __restrict__ g_verts, const float* __restrict__ g_clip,
                                                   int V, int B, int H, int W, int opt_cam, int Mp,
                                                   float* __restrict__ g_vshaped, float* __restrict__ g_offset, float* __restrict__ g_transl,
-                                                  float* __restrict__ gA, float* __restrict__ gpf, float* __restrict__ acc) {
+                                                  float* __restrict__ gA, float* __restrict__ gpf, float* __restrict__ acc) { VH_PDL_SYNC();
   __shared__ float shA[NB][60];
   __shared__ float shr[33];
   __shared__ float red[60][128];
@@ -514,7 +522,7 @@ __global__ void __launch_bounds__(128) k_skin_bwd(const float* __restrict__ v_po
 __global__ void __launch_bounds__(128) k_pose_bwd(const float* __restrict__ poses, const PoseFwd* __restrict__ posebuf, const float* __restrict__ gA,
                                                   const float* __restrict__ gpf, const int* __restrict__ ts, const float* __restrict__ JS, int K,
                                                   float* g_rot, float* g_neck, float* g_jaw, float* g_eyes, float* __restrict__ gJ_out,
-                                                  float* __restrict__ gbetas) {
+                                                  float* __restrict__ gbetas) { VH_PDL_SYNC();
   __shared__ float shJ[15];
   int b = blockIdx.x;
   if (threadIdx.x == 0) {
@@ -540,7 +548,7 @@ __global__ void __launch_bounds__(128) k_pose_bwd(const float* __restrict__ pose
     }
 }
 
-__global__ void k_joff_bwd(const float* __restrict__ Jreg, const float* __restrict__ gJ, int V, int B, float* __restrict__ g_offset) {
+__global__ void k_joff_bwd(const float* __restrict__ Jreg, const float* __restrict__ gJ, int V, int B, float* __restrict__ g_offset) { VH_PDL_SYNC();
   int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= V) return;
   float s[3] = {0, 0, 0};
@@ -557,7 +565,7 @@ __global__ void k_joff_bwd(const float* __restrict__ Jreg, const float* __restri
 #define BB_ROWS 64
 template <int NB>
 __global__ void __launch_bounds__(512) k_blend_bwd(const float* __restrict__ S, const float* __restrict__ g_vshaped, int M, int Mp, int K, int B,
-                                                   float* __restrict__ gbetas) {
+                                                   float* __restrict__ gbetas) { VH_PDL_SYNC();
   __shared__ float sg[NB][BB_ROWS];
   int m0 = blockIdx.x * BB_ROWS, nm = min(BB_ROWS, M - m0);
   int b0 = blockIdx.y * NB, nb = min(NB, B - b0);
@@ -582,7 +590,7 @@ __global__ void __launch_bounds__(512) k_blend_bwd(const float* __restrict__ S, 
   for (int i = 0; i < NB; ++i) if (i < nb) atomicAdd(gbetas + (size_t)(b0 + i) * K + k, acc[i]);
 }
 
-__global__ void k_betas_scatter(const float* __restrict__ gbetas, const int* __restrict__ ts, int K, int n_shape, float* g_shape, float* g_expr) {
+__global__ void k_betas_scatter(const float* __restrict__ gbetas, const int* __restrict__ ts, int K, int n_shape, float* g_shape, float* g_expr) { VH_PDL_SYNC();
   int b = blockIdx.x, n_expr = K - n_shape;
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
     float g = gbetas[(size_t)b * K + k];
@@ -598,10 +606,10 @@ void launch_flame_backward(vhap_ctx* c, const vhap_params* p, const vhap_frame_b
   bool need_betas = g->shape || g->expr;
   if (shared) {                                   // projection adjoint of every view into its geometry's world-space gradient
     dim3 g0((V + 127) / 128, fb->B);
-    LAUNCH(c, KID_SKIN_BWD, s, k_project_views_bwd<<<g0, 128, 0, s>>>(c->verts, fb->geo, c->cam, c->g_clip, V, fb->H, fb->W, opt_cam, c->g_verts, c->acc));
+    LAUNCH(c, KID_SKIN_BWD, s, vh_launch(k_project_views_bwd, g0, 128, 0, s, c->verts, fb->geo, c->cam, c->g_clip, V, fb->H, fb->W, opt_cam, c->g_verts, c->acc));
   }
   dim3 g1((V + 127) / 128, (B + 1) / 2);
-  LAUNCH(c, KID_SKIN_BWD, s, k_skin_bwd<2><<<g1, 128, 0, s>>>(c->v_posed, c->verts, c->posedirs, c->lbs_w, c->posebuf, c->cam, ts, c->g_verts, shared ? nullptr : c->g_clip, V, B, fb->H, fb->W,
+  LAUNCH(c, KID_SKIN_BWD, s, vh_launch(k_skin_bwd<2>, g1, 128, 0, s, c->v_posed, c->verts, c->posedirs, c->lbs_w, c->posebuf, c->cam, ts, c->g_verts, shared ? nullptr : c->g_clip, V, B, fb->H, fb->W,
                                    shared ? 0 : opt_cam, c->Mpad, c->g_vshaped, g->static_offset, g->translation, c->gA, c->gpf, c->acc));
   // the blend-shape adjoint (tensor-core contraction of g_vshaped) only needs skin_bwd's output: it runs beside the serial
   // pose_bwd -> joff_bwd pair on the second high-priority stream; both add into gbetas atomically
@@ -612,16 +620,16 @@ void launch_flame_backward(vhap_ctx* c, const vhap_params* p, const vhap_frame_b
     if (c->use_tc_blend) launch_blend_tc_bwd(c, B, s2);
     else {
       dim3 g2((M + BB_ROWS - 1) / BB_ROWS, (B + VH_MAXB_CHUNK - 1) / VH_MAXB_CHUNK);
-      LAUNCH(c, KID_BLEND_BWD, s2, k_blend_bwd<VH_MAXB_CHUNK><<<g2, 512, 0, s2>>>(c->S_bwd, c->g_vshaped, M, c->Mpad, c->K, B, c->gbetas));
+      LAUNCH(c, KID_BLEND_BWD, s2, vh_launch(k_blend_bwd<VH_MAXB_CHUNK>, g2, 512, 0, s2, c->S_bwd, c->g_vshaped, M, c->Mpad, c->K, B, c->gbetas));
     }
     if (forked) cudaEventRecord(c->ev[EV_BLEND_DONE], s2);
   }
-  LAUNCH(c, KID_POSE_BWD, s, k_pose_bwd<<<B, 128, 0, s>>>(c->poses, c->posebuf, c->gA, c->gpf, ts, c->JS, c->K, g->rotation, g->neck_pose, g->jaw_pose, g->eyes_pose,
+  LAUNCH(c, KID_POSE_BWD, s, vh_launch(k_pose_bwd, B, 128, 0, s, c->poses, c->posebuf, c->gA, c->gpf, ts, c->JS, c->K, g->rotation, g->neck_pose, g->jaw_pose, g->eyes_pose,
                                c->gJ, need_betas ? c->gbetas : nullptr));
-  if (g->static_offset) LAUNCH(c, KID_JOFF_BWD, s, k_joff_bwd<<<(V + 127) / 128, 128, 0, s>>>(c->Jreg, c->gJ, V, B, g->static_offset));
+  if (g->static_offset) LAUNCH(c, KID_JOFF_BWD, s, vh_launch(k_joff_bwd, (V + 127) / 128, 128, 0, s, c->Jreg, c->gJ, V, B, g->static_offset));
   if (need_betas) {
     if (forked) cudaStreamWaitEvent(s, c->ev[EV_BLEND_DONE], 0);
-    LAUNCH(c, KID_BETAS_SCATTER, s, k_betas_scatter<<<B, 256, 0, s>>>(c->gbetas, ts, c->K, c->n_shape, g->shape, g->expr));
+    LAUNCH(c, KID_BETAS_SCATTER, s, vh_launch(k_betas_scatter, B, 256, 0, s, c->gbetas, ts, c->K, c->n_shape, g->shape, g->expr));
   }
   (void)p;
 }
@@ -672,7 +680,7 @@ __device__ void reg_joint_rot(const float* x, float* gx, const int* ts, int B, i
   }
 }
 
-__global__ void __launch_bounds__(1024) k_regs(RegArgs a) {
+__global__ void __launch_bounds__(1024) k_regs(RegArgs a) { VH_PDL_SYNC();
   __shared__ float sh[33];
   const vhap_stage_cfg& c = a.cfg;
   int B = a.B, GB = a.global_B;
@@ -821,5 +829,5 @@ void launch_regs(vhap_ctx* c, const vhap_params* p, const vhap_frame_batch* fb, 
   a.ts = fb->timesteps; a.B = fb->B; a.V = c->V; a.n_shape = c->n_shape; a.n_expr = c->n_expr; a.global_B = global_B;
   a.w_off = c->w_off; a.w_off_lap = c->w_off_lap; a.lap_indptr = c->lap_indptr; a.lap_idx = c->lap_idx; a.lap_val = c->lap_val; a.lap_y = c->lap_y;
   a.rigid_indptr = c->rigid_indptr; a.rigid_vids = c->rigid_vids; a.n_rigid = c->n_rigid; a.acc = c->acc;
-  LAUNCH(c, KID_REGS, s, k_regs<<<4 + (c->V + 1023) / 1024, 1024, 0, s>>>(a));
+  LAUNCH(c, KID_REGS, s, vh_launch(k_regs, 4 + (c->V + 1023) / 1024, 1024, 0, s, a));
 }

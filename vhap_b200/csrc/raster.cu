@@ -11,7 +11,7 @@
 #define SNAP_GUARD 131072.f
 #define FINE_CHUNK 128
 
-__global__ void k_snap(const f4* __restrict__ clip, i4* __restrict__ snap, float* __restrict__ ndc, int n, int H, int W) {
+__global__ void k_snap(const f4* __restrict__ clip, i4* __restrict__ snap, float* __restrict__ ndc, int n, int H, int W) { VH_PDL_SYNC();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   f4 cl = clip[i];
@@ -50,7 +50,7 @@ template <bool FILL>
 __global__ void __launch_bounds__(256) k_bin(const i4* __restrict__ snap, const i4* __restrict__ faces, int V, int F, int B, int H, int W,
                                              int tiles_x, int tiles_y, int cull_backface, int* __restrict__ tile_count,
                                              const int* __restrict__ tile_off, int* __restrict__ tile_cursor, int* __restrict__ tile_list,
-                                             int tile_cap, int* __restrict__ overflow) {
+                                             int tile_cap, int* __restrict__ overflow) { VH_PDL_SYNC();
   int t = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
   if (t >= F) return;
   i4 f = faces[t];
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) k_bin(const i4* __restrict__ snap, const 
 
 // exclusive scan of n ints in three small launches: 1024-thread blocks scan 4096 coalesced elements each and emit
 // their totals, one block scans the totals, the totals are added back (n up to 4 Mi elements)
-__global__ void __launch_bounds__(1024) k_scan_local(const int* __restrict__ in, int* __restrict__ out, int* __restrict__ aux, int n) {
+__global__ void __launch_bounds__(1024) k_scan_local(const int* __restrict__ in, int* __restrict__ out, int* __restrict__ aux, int n) { VH_PDL_SYNC();
   __shared__ int sh[1024];
   int i0 = (blockIdx.x * 1024 + threadIdx.x) * 4;
   int v[4], s = 0;
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(1024) k_scan_local(const int* __restrict__ in,
   for (int k = 0; k < 4; ++k) { if (i0 + k < n) out[i0 + k] = excl; excl += v[k]; }
   if (threadIdx.x == 1023) aux[blockIdx.x] = sh[1023];
 }
-__global__ void __launch_bounds__(1024) k_scan_aux(int* __restrict__ aux, int naux, int* __restrict__ total) {
+__global__ void __launch_bounds__(1024) k_scan_aux(int* __restrict__ aux, int naux, int* __restrict__ total) { VH_PDL_SYNC();
   __shared__ int sh[1024];
   int s = threadIdx.x < naux ? aux[threadIdx.x] : 0;
   sh[threadIdx.x] = s;
@@ -105,17 +105,20 @@ __global__ void __launch_bounds__(1024) k_scan_aux(int* __restrict__ aux, int na
   if (threadIdx.x < naux) aux[threadIdx.x] = sh[threadIdx.x] - s;
   if (threadIdx.x == 1023 && total) *total = sh[1023];
 }
-__global__ void __launch_bounds__(1024) k_scan_add(int* __restrict__ out, const int* __restrict__ aux, int n) {
+__global__ void __launch_bounds__(1024) k_scan_add(int* __restrict__ out, const int* __restrict__ aux, int n) { VH_PDL_SYNC();
   int i0 = (blockIdx.x * 1024 + threadIdx.x) * 4, a = aux[blockIdx.x];
 #pragma unroll
   for (int k = 0; k < 4; ++k) if (i0 + k < n) out[i0 + k] += a;
 }
 // Single-launch exclusive scan (decoupled look-back): blocks take a ticket (dynamic block id = forward progress), scan their
 // 4096 elements, publish (flag | aggregate) as ONE 64-bit word and the first warp looks back over the predecessors' words, 32 at
-// a time, until it meets an inclusive prefix.  state[0..nb) and the ticket (state[nb]) are zeroed by a memset node before.
+// a time, until it meets an inclusive prefix.  state[0..nb) (words), state[nb] (ticket) and state[nb + 1] (finished blocks) are zero on
+// entry and are cleared again by the block that finishes last, so consecutive scans need no clear launch.  pad4: the input is rounded
+// up to multiples of 4 on load (tile list starts are padded to 16 bytes for the TMA copies of the fine rasteriser).
 #define SCAN_FLAG_A 1ull
 #define SCAN_FLAG_P 2ull
-__global__ void __launch_bounds__(1024) k_scan_lb(const int* __restrict__ in, int* __restrict__ out, int n, unsigned long long* state, int nb, int* __restrict__ total) {
+__global__ void __launch_bounds__(1024) k_scan_lb(const int* __restrict__ in, int* __restrict__ out, int n, unsigned long long* state, int nb, int* __restrict__ total,
+                                                   int pad4) { VH_PDL_SYNC();
   __shared__ int sh[32];
   __shared__ int s_bid, s_prefix;
   if (threadIdx.x == 0) s_bid = (int)atomicAdd((unsigned*)(state + nb), 1u);
@@ -124,7 +127,7 @@ __global__ void __launch_bounds__(1024) k_scan_lb(const int* __restrict__ in, in
   int i0 = (bid * 1024 + threadIdx.x) * 4;
   int v[4], s = 0;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) { v[k] = (i0 + k < n) ? in[i0 + k] : 0; s += v[k]; }
+  for (int k = 0; k < 4; ++k) { v[k] = (i0 + k < n) ? in[i0 + k] : 0; if (pad4) v[k] = (v[k] + 3) & ~3; s += v[k]; }
   int incl = s;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
@@ -166,25 +169,30 @@ __global__ void __launch_bounds__(1024) k_scan_lb(const int* __restrict__ in, in
   int excl = s_prefix + incl - s;
 #pragma unroll
   for (int k = 0; k < 4; ++k) { if (i0 + k < n) out[i0 + k] = excl; excl += v[k]; }
-}
-
-void launch_scan(vhap_ctx* c, const int* in, int* out, int n, int* total, cudaStream_t s) {
-  int nb = (n + 4095) / 4096;
-  static const bool three_pass = getenv("VHAP_B200_SCAN3") != nullptr;       // previous three-launch scan, kept for A/B timing
-  if (three_pass || nb > VH_SCAN_MAX_BLOCKS) {
-    LAUNCH(c, KID_SCAN, s, k_scan_local<<<nb, 1024, 0, s>>>(in, out, c->scan_aux, n));
-    LAUNCH(c, KID_SCAN, s, k_scan_aux<<<1, 1024, 0, s>>>(c->scan_aux, nb, total));
-    LAUNCH(c, KID_SCAN, s, k_scan_add<<<nb, 1024, 0, s>>>(out, c->scan_aux, n));
-    return;
-  }
-  vh_zero(c, c->scan_state, (size_t)(nb + 1) * sizeof(unsigned long long), s);
-  LAUNCH(c, KID_SCAN, s, k_scan_lb<<<nb, 1024, 0, s>>>(in, out, n, c->scan_state, nb, total));
+  // self-reset: every block has finished its look-back when the last one arrives here
+  __shared__ int s_last;
+  if (threadIdx.x == 0) { __threadfence(); s_last = atomicAdd((unsigned*)(state + nb + 1), 1u) == (unsigned)(nb - 1); }
+  __syncthreads();
+  if (s_last) for (int j = threadIdx.x; j < nb + 2; j += 1024) state[j] = 0ull;
 }
 
 // tile list starts are padded to 4 ints (16 bytes) so that the fine rasteriser can stage them with TMA bulk copies
-__global__ void k_pad_counts(const int* __restrict__ cnt, int* __restrict__ padded, int n) {
+__global__ void k_pad_counts(const int* __restrict__ cnt, int* __restrict__ padded, int n) { VH_PDL_SYNC();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) padded[i] = (cnt[i] + 3) & ~3;
+}
+
+void launch_scan(vhap_ctx* c, const int* in, int* out, int n, int* total, cudaStream_t s, int pad4) {
+  int nb = (n + 4095) / 4096;
+  static const bool three_pass = getenv("VHAP_B200_SCAN3") != nullptr;       // previous three-launch scan, kept for A/B timing
+  if (three_pass || nb > VH_SCAN_MAX_BLOCKS) {
+    if (pad4) { LAUNCH(c, KID_SCAN, s, vh_launch(k_pad_counts, (n + 255) / 256, 256, 0, s, in, out, n)); in = out; }     // (in place: local scan reads before it writes)
+    LAUNCH(c, KID_SCAN, s, vh_launch(k_scan_local, nb, 1024, 0, s, in, out, c->scan_aux, n));
+    LAUNCH(c, KID_SCAN, s, vh_launch(k_scan_aux, 1, 1024, 0, s, c->scan_aux, nb, total));
+    LAUNCH(c, KID_SCAN, s, vh_launch(k_scan_add, nb, 1024, 0, s, out, c->scan_aux, n));
+    return;
+  }
+  LAUNCH(c, KID_SCAN, s, vh_launch(k_scan_lb, nb, 1024, 0, s, in, out, n, c->scan_state, nb, total, pad4));
 }
 
 struct FineTri {        // shared-memory record, struct of arrays
@@ -201,7 +209,7 @@ __device__ __forceinline__ int sat30(long long v) {
 
 __global__ void __launch_bounds__(128) k_fine(const i4* __restrict__ snap, const i4* __restrict__ faces, const int* __restrict__ tile_count,
                                               const int* __restrict__ tile_off, const int* __restrict__ tile_list, int tile_cap,
-                                              int V, int H, int W, int tiles_x, int tiles_y, int cull_backface, int* __restrict__ tri_id) {
+                                              int V, int H, int W, int tiles_x, int tiles_y, int cull_backface, int* __restrict__ tri_id) { VH_PDL_SYNC();
   __shared__ FineTri T;
   __shared__ __align__(16) int ids_s[2][FINE_CHUNK];     // triangle-id chunks staged by TMA (cp.async.bulk), double buffered
   __shared__ uint64_t bar[2];
@@ -315,23 +323,21 @@ __global__ void __launch_bounds__(128) k_fine(const i4* __restrict__ snap, const
   }
 }
 
-void launch_raster(vhap_ctx* c, const f4* clip, i4* snap, int B, int H, int W, int* tri_id, int cull_backface, int need_snap, cudaStream_t s) {
+void launch_raster(vhap_ctx* c, const f4* clip, i4* snap, int B, int H, int W, int* tri_id, int cull_backface, int need_snap, cudaStream_t s, bool zeroed) {
   int V = c->V, F = c->F;
-  if (need_snap) LAUNCH(c, KID_SNAP, s, k_snap<<<(B * V + 255) / 256, 256, 0, s>>>(clip, snap, c->ndc, B * V, H, W));
+  if (need_snap) LAUNCH(c, KID_SNAP, s, vh_launch(k_snap, (B * V + 255) / 256, 256, 0, s, clip, snap, c->ndc, B * V, H, W));
   int tiles_x = (W + VH_TILE - 1) / VH_TILE, tiles_y = (H + VH_TILE - 1) / VH_TILE, ntiles = B * tiles_x * tiles_y;
-  vh_zero(c, c->tile_count, sizeof(int) * ntiles, s);
+  if (!zeroed) { VhZeroSegs z; z.n = 2; z.p[0] = c->tile_count; z.p[1] = c->tile_cursor; z.bytes[0] = z.bytes[1] = sizeof(int) * ntiles; vh_zero_multi(c, z, s); }
   dim3 g((F + 255) / 256, B);
-  LAUNCH(c, KID_BIN, s, k_bin<false><<<g, 256, 0, s>>>(snap, c->faces, V, F, B, H, W, tiles_x, tiles_y, cull_backface, c->tile_count, nullptr, nullptr, nullptr, 0, c->overflow_flag));
-  LAUNCH(c, KID_SCAN, s, k_pad_counts<<<(ntiles + 255) / 256, 256, 0, s>>>(c->tile_count, c->tile_cursor, ntiles));   // cursor doubles as scratch
-  launch_scan(c, c->tile_cursor, c->tile_off, ntiles, nullptr, s);
-  vh_zero(c, c->tile_cursor, sizeof(int) * ntiles, s);
-  LAUNCH(c, KID_BIN, s, k_bin<true><<<g, 256, 0, s>>>(snap, c->faces, V, F, B, H, W, tiles_x, tiles_y, cull_backface, c->tile_count, c->tile_off, c->tile_cursor, c->tile_list,
+  LAUNCH(c, KID_BIN, s, vh_launch(k_bin<false>, g, 256, 0, s, snap, c->faces, V, F, B, H, W, tiles_x, tiles_y, cull_backface, c->tile_count, nullptr, nullptr, nullptr, 0, c->overflow_flag));
+  launch_scan(c, c->tile_count, c->tile_off, ntiles, nullptr, s, 1);          // starts of the tile lists, padded to 4 entries
+  LAUNCH(c, KID_BIN, s, vh_launch(k_bin<true>, g, 256, 0, s, snap, c->faces, V, F, B, H, W, tiles_x, tiles_y, cull_backface, c->tile_count, c->tile_off, c->tile_cursor, c->tile_list,
                                 c->tile_cap, c->overflow_flag));
-  LAUNCH(c, KID_FINE, s, k_fine<<<ntiles, 128, 0, s>>>(snap, c->faces, c->tile_count, c->tile_off, c->tile_list, c->tile_cap, V, H, W, tiles_x, tiles_y, cull_backface, tri_id));
+  LAUNCH(c, KID_FINE, s, vh_launch(k_fine, ntiles, 128, 0, s, snap, c->faces, c->tile_count, c->tile_off, c->tile_list, c->tile_cap, V, H, W, tiles_x, tiles_y, cull_backface, tri_id));
 }
 
 // dr.rasterize's float outputs for the modular API: rast = (u, v, z/w, id), rast_db = (du/dx, du/dy, dv/dx, dv/dy)
-__global__ void k_rast_out(RenderArgs A, float* __restrict__ rast, float* __restrict__ rast_db) {
+__global__ void k_rast_out(RenderArgs A, float* __restrict__ rast, float* __restrict__ rast_db) { VH_PDL_SYNC();
   size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t n = (size_t)A.B * A.H * A.W;
   if (pix >= n) return;
@@ -353,5 +359,5 @@ void launch_rast_out(vhap_ctx* c, const f4* clip, int B, int H, int W, const int
   memset(&A, 0, sizeof(A));
   A.B = B; A.H = H; A.W = W; A.V = c->V; A.F = c->F; A.faces = c->faces; A.clip = clip; A.tri_id = tri_id;
   size_t n = (size_t)B * H * W;
-  LAUNCH(c, KID_RAST_OUT, s, k_rast_out<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(A, rast, rast_db));
+  LAUNCH(c, KID_RAST_OUT, s, vh_launch(k_rast_out, (unsigned)((n + 255) / 256), 256, 0, s, A, rast, rast_db));
 }

@@ -45,19 +45,32 @@ __device__ __forceinline__ float unpack_max_val(unsigned long long p) {
 }
 
 // ---------------------------------------------------------------------------------------------- cluster pools
-__global__ void __launch_bounds__(PB) k_pool_count(const int* __restrict__ tri_id, const uint8_t* __restrict__ fid2cid, size_t n, int ncl, int* __restrict__ blk_count) {
+// Each CTA covers PB * POOL_PPT consecutive pixels; warp w owns the 32 * POOL_PPT pixels [w * 32 * POOL_PPT, ...) of that range as POOL_PPT
+// coalesced rows of 32, so list order = pixel order (the pools must be in torch's boolean-mask order: the reference draws a pool INDEX).
+// The POOL_PPT id loads of a thread are independent and issued together (one pixel per thread was latency-bound: 0.051 ms for 50 MB).
+#define POOL_PPT 4
+__global__ void __launch_bounds__(PB) k_pool_count(const int* __restrict__ tri_id, const uint8_t* __restrict__ fid2cid, size_t n, int ncl, int* __restrict__ blk_count) { VH_PDL_SYNC();
   __shared__ int cnt[16];
   if (threadIdx.x < 16) cnt[threadIdx.x] = 0;
   __syncthreads();
-  size_t pix = (size_t)blockIdx.x * PB + threadIdx.x;
-  int cid = pix < n ? fid2cid[tri_id[pix]] : -1;
-  unsigned any = __ballot_sync(0xffffffffu, cid > 0);
-  unsigned m0 = __ballot_sync(0xffffffffu, cid == 0);
-  if ((threadIdx.x & 31) == 0 && m0) atomicAdd(&cnt[0], __popc(m0));
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const size_t base = ((size_t)blockIdx.x * (PB / 32) + w) * (32 * POOL_PPT) + lane;
+  int id[POOL_PPT], cid[POOL_PPT];
+#pragma unroll
+  for (int j = 0; j < POOL_PPT; ++j) id[j] = base + 32 * j < n ? tri_id[base + 32 * j] : -1;
+#pragma unroll
+  for (int j = 0; j < POOL_PPT; ++j) cid[j] = id[j] >= 0 ? fid2cid[id[j]] : -1;
+  int c0 = 0;
+  unsigned any = 0;
+#pragma unroll
+  for (int j = 0; j < POOL_PPT; ++j) { c0 += __popc(__ballot_sync(0xffffffffu, cid[j] == 0)); any |= __ballot_sync(0xffffffffu, cid[j] > 0); }
+  if (lane == 0 && c0) atomicAdd(&cnt[0], c0);
   if (any)                                                       // warps that are all background skip the per-cluster ballots
     for (int c = 1; c < ncl; ++c) {
-      unsigned m = __ballot_sync(0xffffffffu, cid == c);
-      if ((threadIdx.x & 31) == 0 && m) atomicAdd(&cnt[c], __popc(m));
+      int k = 0;
+#pragma unroll
+      for (int j = 0; j < POOL_PPT; ++j) k += __popc(__ballot_sync(0xffffffffu, cid[j] == c));
+      if (lane == 0 && k) atomicAdd(&cnt[c], k);
     }
   __syncthreads();
   if (threadIdx.x < 16) blk_count[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = cnt[threadIdx.x];    // [16][nblk]
@@ -67,7 +80,7 @@ __global__ void __launch_bounds__(PB) k_pool_count(const int* __restrict__ tri_i
 __global__ void __launch_bounds__(PB) k_pool_scatter(const int* __restrict__ tri_id, const uint8_t* __restrict__ fid2cid, size_t n, int H, int W, int ncl,
                                                      const int* __restrict__ blk_off, int* __restrict__ pool_list, int* __restrict__ pool_tri,
                                                      int* __restrict__ pair_list, int* __restrict__ pair_count,
-                                                     const int* __restrict__ total, int* __restrict__ base, int* __restrict__ count) {
+                                                     const int* __restrict__ total, int* __restrict__ base, int* __restrict__ count) { VH_PDL_SYNC();
   __shared__ int wcnt[16][PB / 32];
   // base / count of every cluster from the scanned [16][nblk] offsets (lists laid out cluster after cluster): read by the passes that
   // follow this kernel, written here by the first CTA (was a launch of its own)
@@ -76,43 +89,73 @@ __global__ void __launch_bounds__(PB) k_pool_scatter(const int* __restrict__ tri
     const int b = blk_off[(size_t)c * nb], e = c < 15 ? blk_off[(size_t)(c + 1) * nb] : *total;
     base[c] = b; count[c] = e - b;
   }
-  size_t pix = (size_t)blockIdx.x * PB + threadIdx.x;
-  int id = pix < n ? tri_id[pix] : -1;
-  int cid = pix < n ? fid2cid[id] : -1;
-  {
-    int x = pix % W, y = (pix / W) % H;
-    bool h0 = pix < n && x + 1 < W && tri_id[pix + 1] != id;
-    bool h1 = pix < n && y + 1 < H && tri_id[pix + W] != id;
-    unsigned m0 = __ballot_sync(0xffffffffu, h0), m1 = __ballot_sync(0xffffffffu, h1);
-    int lane_ = threadIdx.x & 31, tot = __popc(m0) + __popc(m1), base = 0;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const unsigned below = (1u << lane) - 1;
+  const size_t pix0 = ((size_t)blockIdx.x * (PB / 32) + w) * (32 * POOL_PPT) + lane;
+  int id[POOL_PPT], cid[POOL_PPT], idr[POOL_PPT], idd[POOL_PPT];
+#pragma unroll
+  for (int j = 0; j < POOL_PPT; ++j) {
+    const size_t pix = pix0 + 32 * j;
+    id[j] = pix < n ? tri_id[pix] : -1;
+    const int x = pix % W, y = (pix / W) % H;
+    idr[j] = pix < n && x + 1 < W ? tri_id[pix + 1] : id[j];
+    idd[j] = pix < n && y + 1 < H ? tri_id[pix + W] : id[j];
+  }
+#pragma unroll
+  for (int j = 0; j < POOL_PPT; ++j) cid[j] = id[j] >= 0 ? fid2cid[id[j]] : -1;
+  {                                                            // antialias pairs: one counter reservation per warp
+    unsigned m0[POOL_PPT], m1[POOL_PPT];
+    int tot = 0;
+#pragma unroll
+    for (int j = 0; j < POOL_PPT; ++j) {
+      m0[j] = __ballot_sync(0xffffffffu, idr[j] != id[j]); m1[j] = __ballot_sync(0xffffffffu, idd[j] != id[j]);
+      tot += __popc(m0[j]) + __popc(m1[j]);
+    }
     if (tot) {
-      if (lane_ == 0) base = atomicAdd(pair_count, tot);
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (h0) pair_list[base + __popc(m0 & ((1u << lane_) - 1))] = (int)pix * 2;
-      if (h1) pair_list[base + __popc(m0) + __popc(m1 & ((1u << lane_) - 1))] = (int)pix * 2 + 1;
+      int at = 0;
+      if (lane == 0) at = atomicAdd(pair_count, tot);
+      at = __shfl_sync(0xffffffffu, at, 0);
+#pragma unroll
+      for (int j = 0; j < POOL_PPT; ++j) {
+        const int pix = (int)(pix0 + 32 * j);
+        if (idr[j] != id[j]) pair_list[at + __popc(m0[j] & below)] = pix * 2;
+        at += __popc(m0[j]);
+        if (idd[j] != id[j]) pair_list[at + __popc(m1[j] & below)] = pix * 2 + 1;
+        at += __popc(m1[j]);
+      }
     }
   }
-  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  int rank = 0;
-  unsigned any = __ballot_sync(0xffffffffu, cid > 0);
+  int rank[POOL_PPT];
+#pragma unroll
+  for (int j = 0; j < POOL_PPT; ++j) rank[j] = 0;
+  unsigned any = 0;
+#pragma unroll
+  for (int j = 0; j < POOL_PPT; ++j) any |= __ballot_sync(0xffffffffu, cid[j] > 0);
   for (int c = 0; c < 16; ++c) {
-    if (c >= ncl) { if (lane == 0) wcnt[c][w] = 0; continue; }
-    unsigned m = (c == 0 || any) ? __ballot_sync(0xffffffffu, cid == c) : 0u;
-    if (cid == c) rank = __popc(m & ((1u << lane) - 1));
-    if (lane == 0) wcnt[c][w] = __popc(m);
+    if (c >= ncl || (c > 0 && !any)) { if (lane == 0) wcnt[c][w] = 0; continue; }
+    int run = 0;                                               // members of cluster c in the rows before row j of this warp
+#pragma unroll
+    for (int j = 0; j < POOL_PPT; ++j) {
+      const unsigned m = __ballot_sync(0xffffffffu, cid[j] == c);
+      if (cid[j] == c) rank[j] = run + __popc(m & below);
+      run += __popc(m);
+    }
+    if (lane == 0) wcnt[c][w] = run;
   }
   __syncthreads();
-  if (cid >= 0) {
-    int before = 0;
-    for (int k = 0; k < w; ++k) before += wcnt[cid][k];
-    int pos = blk_off[(size_t)cid * gridDim.x + blockIdx.x] + before + rank;
-    pool_list[pos] = (int)pix;
-    pool_tri[pos] = id;
-  }
+#pragma unroll
+  for (int j = 0; j < POOL_PPT; ++j)
+    if (cid[j] >= 0) {
+      int before = 0;
+      for (int k = 0; k < w; ++k) before += wcnt[cid[j]][k];
+      const int pos = blk_off[(size_t)cid[j] * gridDim.x + blockIdx.x] + before + rank[j];
+      pool_list[pos] = (int)(pix0 + 32 * j);
+      pool_tri[pos] = id[j];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------- passes
-__global__ void __launch_bounds__(PB) k_aa_pairs(PassArgs P, const int* __restrict__ pair_list, const int* __restrict__ pair_count) {
+__global__ void __launch_bounds__(PB) k_aa_pairs(PassArgs P, const int* __restrict__ pair_list, const int* __restrict__ pair_count) { VH_PDL_SYNC();
   const RenderArgs& A = P.R;
   int n = *pair_count;
   for (int i = blockIdx.x * PB + threadIdx.x; i < n; i += gridDim.x * PB) {
@@ -136,7 +179,7 @@ __global__ void __launch_bounds__(PB, VH_A_MIN) k_passA(
 #else
 __global__ void __launch_bounds__(PB) k_passA(
 #endif
-    PassArgs P, float* __restrict__ partials, unsigned long long* __restrict__ maxslot) {
+    PassArgs P, float* __restrict__ partials, unsigned long long* __restrict__ maxslot) { VH_PDL_SYNC();
   __shared__ float sh[8 * 2];
   __shared__ unsigned long long shm[8];
   const RenderArgs& A = P.R;
@@ -160,7 +203,7 @@ __global__ void __launch_bounds__(PB) k_passA(
   }
 }
 
-__global__ void __launch_bounds__(PB, VH_B_MIN) k_passB(PassArgs P, float* __restrict__ partials) {
+__global__ void __launch_bounds__(PB, VH_B_MIN) k_passB(PassArgs P, float* __restrict__ partials) { VH_PDL_SYNC();
   __shared__ float sh[8 * 2];
   const RenderArgs& A = P.R;
   int n = A.B * A.H * A.W;
@@ -172,7 +215,7 @@ __global__ void __launch_bounds__(PB, VH_B_MIN) k_passB(PassArgs P, float* __res
   block_reduce_store<2>(acc, sh, partials + (size_t)blockIdx.x * VH_NPART + 2);
 }
 
-__global__ void __launch_bounds__(PB, VH_C1_MIN) k_passC1(PassArgs P, const float* __restrict__ ext_grad, f4* __restrict__ grgb) {
+__global__ void __launch_bounds__(PB, VH_C1_MIN) k_passC1(PassArgs P, const float* __restrict__ ext_grad, f4* __restrict__ grgb) { VH_PDL_SYNC();
   const RenderArgs& A = P.R;
   int n_fg = A.B * A.H * A.W - P.pool_count[0];
   const int* list = P.pool_list + P.pool_base[1];
@@ -199,7 +242,7 @@ __global__ void __launch_bounds__(PB, VH_C1_MIN) k_passC1(PassArgs P, const floa
 #define VH_C2_AGG 1            // warp-level reduction of the per-vertex gradients over the pixels of one triangle (0: one reduction per pixel)
 #endif
 // texel-gradient half of the shading adjoint (see shade_pixel_texgrad): a light kernel that only issues the 8 vector reductions per pixel
-__global__ void __launch_bounds__(PB, 4) k_passC2_tex(PassArgs P, const f4* __restrict__ grgb) {
+__global__ void __launch_bounds__(PB, 4) k_passC2_tex(PassArgs P, const f4* __restrict__ grgb) { VH_PDL_SYNC();
   const RenderArgs& A = P.R;
   int n_fg = A.B * A.H * A.W - P.pool_count[0];
   const int* list = P.pool_list + P.pool_base[1];
@@ -212,7 +255,7 @@ __global__ void __launch_bounds__(PB, 4) k_passC2_tex(PassArgs P, const f4* __re
   }
 }
 
-__global__ void __launch_bounds__(VH_C2_PB, VH_C2_MINBLOCKS) k_passC2(PassArgs P, const f4* __restrict__ grgb, float* __restrict__ partials) {
+__global__ void __launch_bounds__(VH_C2_PB, VH_C2_MINBLOCKS) k_passC2(PassArgs P, const f4* __restrict__ grgb, float* __restrict__ partials) { VH_PDL_SYNC();
   __shared__ float sh[(VH_C2_PB / 32) * 27];
   const RenderArgs& A = P.R;
   int n_fg = A.B * A.H * A.W - P.pool_count[0];
@@ -227,6 +270,7 @@ __global__ void __launch_bounds__(VH_C2_PB, VH_C2_MINBLOCKS) k_passC2(PassArgs P
   // and leave as ONE vector reduction per vertex per run instead of one per pixel (the L1 reduction path was 65 % busy, ncu r02 base).
   const int lane = threadIdx.x & 31;
   const int n_round = (n_fg + 31) & ~31;
+  // (a dynamic work queue -- warps drawing 32-entry chunks from a counter, grid = resident CTAs -- measured slower: 0.128 vs 0.118 ms, r13)
   for (int i = blockIdx.x * VH_C2_PB + threadIdx.x; i < n_round; i += gridDim.x * VH_C2_PB) {
     const bool on = i < n_fg;
     int id = 0, b = 0, key = -1 - lane;                 // inactive lanes: unique negative keys (runs of length 1, skipped)
@@ -284,7 +328,7 @@ __global__ void __launch_bounds__(VH_C2_PB, VH_C2_MINBLOCKS) k_passC2(PassArgs P
 
 // column sums of the [rows][VH_NPART] partial matrix: dst[slot ? slot[c] : c] += sum_r partials[r][col0 + c]
 __global__ void __launch_bounds__(256) k_reduce_cols(const float* __restrict__ partials, int rows, int col0, int ncol, float* __restrict__ dst,
-                                                     const int* __restrict__ slot) {
+                                                     const int* __restrict__ slot) { VH_PDL_SYNC();
   __shared__ float sh[8][32];
   int c = threadIdx.x & 31, g = threadIdx.x >> 5;
   float s = 0.f;
@@ -309,7 +353,7 @@ __global__ void __launch_bounds__(256) k_reduce_cols(const float* __restrict__ p
 struct DpBox { int rank, world; float* const* peers; int* epoch; int* err; float* mine; };
 __global__ void __launch_bounds__(256) k_forward_slab(const float* __restrict__ partials, int rows, float* __restrict__ acc,
                                const unsigned long long* __restrict__ maxslot, const float* __restrict__ lights, float n_pix_total, float* __restrict__ slab,
-                               DpBox dp) {
+                               DpBox dp) { VH_PDL_SYNC();
   __shared__ float shs[64][4];
   __shared__ float tot[4];
   {
@@ -356,7 +400,7 @@ __global__ void __launch_bounds__(256) k_forward_slab(const float* __restrict__ 
 
 // consumes the (possibly cross-rank reduced) slab: scal[] for pass C, loss values, background share of the light gradient
 __global__ void k_finalize(const float* __restrict__ slab, const float* __restrict__ local_slab, vhap_stage_cfg cfg, const float* __restrict__ lights,
-                           float n_pix_global, float* __restrict__ scal, float* __restrict__ acc, float* __restrict__ g_lights, DpBox dp) {
+                           float n_pix_global, float* __restrict__ scal, float* __restrict__ acc, float* __restrict__ g_lights, DpBox dp) { VH_PDL_SYNC();
   float abs_sum = slab[0], nfg = slab[1], varsum = slab[2], mx = slab[3];
   if (dp.world > 1) {                                        // gather the peers' slabs from this rank's mailbox (see k_forward_slab)
     const int e = *dp.epoch;
@@ -398,7 +442,7 @@ __global__ void k_finalize(const float* __restrict__ slab, const float* __restri
 }
 
 // flips a raster-orientation float4 plane into image orientation
-__global__ void k_flip_plane(const float4* __restrict__ in, float4* __restrict__ out, int B, int H, int W) {
+__global__ void k_flip_plane(const float4* __restrict__ in, float4* __restrict__ out, int B, int H, int W) { VH_PDL_SYNC();
   size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n = (size_t)B * H * W;
   if (pix >= n) return;
   int x = pix % W, y = (pix / W) % H, b = pix / ((size_t)W * H);
@@ -406,9 +450,9 @@ __global__ void k_flip_plane(const float4* __restrict__ in, float4* __restrict__
 }
 void launch_flip_plane(vhap_ctx* c, const float* in, float* out, int B, int H, int W, cudaStream_t s) {
   size_t n = (size_t)B * H * W;
-  LAUNCH(c, KID_MISC, s, k_flip_plane<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const float4*)in, (float4*)out, B, H, W));
+  LAUNCH(c, KID_MISC, s, vh_launch(k_flip_plane, (unsigned)((n + 255) / 256), 256, 0, s, (const float4*)in, (float4*)out, B, H, W));
 }
-__global__ void k_cid_plane(const int* __restrict__ tri_id, const uint8_t* __restrict__ fid2cid, float4* __restrict__ out, int B, int H, int W) {
+__global__ void k_cid_plane(const int* __restrict__ tri_id, const uint8_t* __restrict__ fid2cid, float4* __restrict__ out, int B, int H, int W) { VH_PDL_SYNC();
   size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n = (size_t)B * H * W;
   if (pix >= n) return;
   int x = pix % W, y = (pix / W) % H, b = pix / ((size_t)W * H);
@@ -417,7 +461,7 @@ __global__ void k_cid_plane(const int* __restrict__ tri_id, const uint8_t* __res
 }
 void launch_cid_plane(vhap_ctx* c, float* out, cudaStream_t s) {
   size_t n = (size_t)c->curB * c->curH * c->curW;
-  LAUNCH(c, KID_MISC, s, k_cid_plane<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(c->tri_id, c->fid2cid, (float4*)out, c->curB, c->curH, c->curW));
+  LAUNCH(c, KID_MISC, s, vh_launch(k_cid_plane, (unsigned)((n + 255) / 256), 256, 0, s, c->tri_id, c->fid2cid, (float4*)out, c->curB, c->curH, c->curW));
 }
 
 void fill_render_args(vhap_ctx* c, PassArgs& P, const vhap_frame_batch* fb, const vhap_stage_cfg* cfg, const float* lights) {
@@ -468,16 +512,17 @@ void launch_render_forward(vhap_ctx* c, PassArgs& P, cudaStream_t s, bool zeroed
   if (c->want_planes) {
     cudaMemsetAsync(c->plane_albedo, 0, n * 16, s); cudaMemsetAsync(c->plane_normal, 0, n * 16, s); cudaMemsetAsync(c->plane_diffuse, 0, n * 16, s);
   }
-  LAUNCH(c, KID_POOL_COUNT, s, k_pool_count<<<nblk, PB, 0, s>>>(A.tri_id, A.fid2cid, n, c->n_clusters, c->pool_blk_count));
-  launch_scan(c, c->pool_blk_count, c->pool_blk_off, 16 * nblk, c->scan_total, s);
-  LAUNCH(c, KID_POOL_SCATTER, s, k_pool_scatter<<<nblk, PB, 0, s>>>(A.tri_id, A.fid2cid, n, A.H, A.W, c->n_clusters, c->pool_blk_off, c->pool_list, c->pool_tri, c->pair_list, c->pair_count,
+  const int nblk_pool = (int)((n + (size_t)PB * POOL_PPT - 1) / ((size_t)PB * POOL_PPT));
+  LAUNCH(c, KID_POOL_COUNT, s, vh_launch(k_pool_count, nblk_pool, PB, 0, s, A.tri_id, A.fid2cid, n, c->n_clusters, c->pool_blk_count));
+  launch_scan(c, c->pool_blk_count, c->pool_blk_off, 16 * nblk_pool, c->scan_total, s);
+  LAUNCH(c, KID_POOL_SCATTER, s, vh_launch(k_pool_scatter, nblk_pool, PB, 0, s, A.tri_id, A.fid2cid, n, A.H, A.W, c->n_clusters, c->pool_blk_off, c->pool_list, c->pool_tri, c->pair_list, c->pair_count,
                                                                    c->scan_total, c->pool_base, c->pool_count));
   int grid = nblk < NPERSIST ? nblk : NPERSIST;
   // a deferred texture update (vhap_set_render_wait_event) is joined here: everything above is independent of the texture
   if (c->render_wait_ev) { cudaStreamWaitEvent(s, c->render_wait_ev, 0); c->render_wait_ev = nullptr; }
-  LAUNCH(c, KID_PASSA, s, k_passA<<<grid, PB, 0, s>>>(P, c->partials, c->maxslot));
-  LAUNCH(c, KID_AA_PAIRS, s, k_aa_pairs<<<grid, PB, 0, s>>>(P, c->pair_list, c->pair_count));
-  LAUNCH(c, KID_PASSB, s, k_passB<<<grid, PB, 0, s>>>(P, c->partials));
+  LAUNCH(c, KID_PASSA, s, vh_launch(k_passA, grid, PB, 0, s, P, c->partials, c->maxslot));
+  LAUNCH(c, KID_AA_PAIRS, s, vh_launch(k_aa_pairs, grid, PB, 0, s, P, c->pair_list, c->pair_count));
+  LAUNCH(c, KID_PASSB, s, vh_launch(k_passB, grid, PB, 0, s, P, c->partials));
   (void)slots;                              // the partial rows are summed by k_forward_slab (launch_forward_slab)
 }
 
@@ -489,13 +534,13 @@ void launch_forward_slab(vhap_ctx* c, const PassArgs& P, const float* lights, fl
   const RenderArgs& A = P.R;
   size_t n = (size_t)A.B * A.H * A.W;
   int nblk = (int)((n + PB - 1) / PB), rows = nblk < NPERSIST ? nblk : NPERSIST;          // grid of passes A / B (launch_render_forward)
-  LAUNCH(c, KID_SLAB, s, k_forward_slab<<<1, 256, 0, s>>>(c->partials, rows, c->acc, c->maxslot, lights, (float)n, slab, dp_box_of(c)));
+  LAUNCH(c, KID_SLAB, s, vh_launch(k_forward_slab, 1, 256, 0, s, c->partials, rows, c->acc, c->maxslot, lights, (float)n, slab, dp_box_of(c)));
 }
 
 void launch_finalize(vhap_ctx* c, const PassArgs& P, const vhap_stage_cfg* cfg, const float* slab_global, const float* slab_local, int global_B,
                      const float* lights, float* g_lights, cudaStream_t s) {
   const RenderArgs& A = P.R;
-  LAUNCH(c, KID_FINALIZE, s, k_finalize<<<1, 1, 0, s>>>(slab_global, slab_local, *cfg, lights, (float)((size_t)global_B * A.H * A.W), c->scal, c->acc, g_lights, dp_box_of(c)));
+  LAUNCH(c, KID_FINALIZE, s, vh_launch(k_finalize, 1, 1, 0, s, slab_global, slab_local, *cfg, lights, (float)((size_t)global_B * A.H * A.W), c->scal, c->acc, g_lights, dp_box_of(c)));
 }
 
 void launch_render_backward(vhap_ctx* c, PassArgs& P, const vhap_stage_cfg* cfg, const float* lights, float* g_lights, const float* ext_grad, cudaStream_t s,
@@ -505,7 +550,7 @@ void launch_render_backward(vhap_ctx* c, PassArgs& P, const vhap_stage_cfg* cfg,
   size_t n = (size_t)A.B * A.H * A.W;
   int nblk = (int)((n + PB - 1) / PB);
   int grid = nblk < NPERSIST ? nblk : NPERSIST;
-  LAUNCH(c, KID_PASSC1, s, k_passC1<<<grid, PB, 0, s>>>(P, ext_grad, c->grgb));
+  LAUNCH(c, KID_PASSC1, s, vh_launch(k_passC1, grid, PB, 0, s, P, ext_grad, c->grgb));
   int grid2 = grid * (PB / VH_C2_PB);
 #if VH_C2_SPLIT
   // the texel-gradient scatter (8 of the 10 vector reductions per pixel, no texel reads) runs as its own light kernel on a second
@@ -513,18 +558,18 @@ void launch_render_backward(vhap_ctx* c, PassArgs& P, const vhap_stage_cfg* cfg,
   if (side && P.g_tex) {
     cudaEventRecord(c->ev[EV_C1_DONE], s);
     cudaStreamWaitEvent(c->hp[1], c->ev[EV_C1_DONE], 0);
-    LAUNCH(c, KID_PASSC1, c->hp[1], k_passC2_tex<<<grid, PB, 0, c->hp[1]>>>(P, c->grgb));
+    LAUNCH(c, KID_PASSC1, c->hp[1], vh_launch(k_passC2_tex, grid, PB, 0, c->hp[1], P, c->grgb));
     cudaEventRecord(c->ev[EV_C2TEX_DONE], c->hp[1]);
     PassArgs Pg = P; Pg.g_tex = nullptr;
-    LAUNCH(c, KID_PASSC, s, k_passC2<<<grid2, VH_C2_PB, 0, s>>>(Pg, c->grgb, c->partials));
+    LAUNCH(c, KID_PASSC, s, vh_launch(k_passC2, grid2, VH_C2_PB, 0, s, Pg, c->grgb, c->partials));
     cudaStreamWaitEvent(s, c->ev[EV_C2TEX_DONE], 0);
   } else
 #endif
-  LAUNCH(c, KID_PASSC, s, k_passC2<<<grid2, VH_C2_PB, 0, s>>>(P, c->grgb, c->partials));
+  LAUNCH(c, KID_PASSC, s, vh_launch(k_passC2, grid2, VH_C2_PB, 0, s, P, c->grgb, c->partials));
   // side != NULL: the reduction of the light-gradient partials (only the Adam step needs it) leaves the step's critical chain; the caller
   // joins EV_LIGHTS_DONE.  EV_TEXGRAD_READY doubles as "pass C complete".
   cudaStream_t ls = s;
   if (side) { cudaEventRecord(c->ev[EV_TEXGRAD_READY], s); cudaStreamWaitEvent(side, c->ev[EV_TEXGRAD_READY], 0); ls = side; }
-  if (g_lights) LAUNCH(c, KID_LIGHTS_REDUCE, ls, k_reduce_cols<<<16, 256, 0, ls>>>(c->partials, grid2, 4, 27, g_lights, nullptr));
+  if (g_lights) LAUNCH(c, KID_LIGHTS_REDUCE, ls, vh_launch(k_reduce_cols, 16, 256, 0, ls, c->partials, grid2, 4, 27, g_lights, nullptr));
   if (side) cudaEventRecord(c->ev[EV_LIGHTS_DONE], side);
 }

@@ -7,7 +7,7 @@
 #include "engine.h"
 #include "accum.h"
 
-__global__ void k_tex_level0(const float* __restrict__ painted, const float* __restrict__ extra, int T, f4* __restrict__ out) {
+__global__ void k_tex_level0(const float* __restrict__ painted, const float* __restrict__ extra, int T, f4* __restrict__ out) { VH_PDL_SYNC();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n = (size_t)T * T;
   if (i >= n) return;
   f4 v;
@@ -25,7 +25,7 @@ __device__ __forceinline__ f4 avg4(const f4& a, const f4& b, const f4& c, const 
   return o;
 }
 __global__ void __launch_bounds__(256) k_mip_down(const f4* __restrict__ src, f4* __restrict__ pyr_base, int ssz, int nlev,
-                                                  int o1, int o2, int o3, int o4, int o5) {
+                                                  int o1, int o2, int o3, int o4, int o5) { VH_PDL_SYNC();
   __shared__ f4 A[32][33];
   __shared__ f4 Bf[16][17];
   int tile = ssz < 32 ? ssz : 32;                  // source tile edge handled by this CTA
@@ -60,7 +60,7 @@ static void build_mips(vhap_ctx* c, f4* pyr, cudaStream_t s, int from_level = 0)
     int tile = ssz < 32 ? ssz : 32, g = ssz / tile;
     int o[5] = {0, 0, 0, 0, 0};
     for (int k = 0; k < nlev; ++k) o[k] = c->mip_off[l + 1 + k];
-    LAUNCH(c, KID_MIP, s, k_mip_down<<<dim3(g, g), 256, 0, s>>>(pyr + c->mip_off[l], pyr, ssz, nlev, o[0], o[1], o[2], o[3], o[4]));
+    LAUNCH(c, KID_MIP, s, vh_launch(k_mip_down, dim3(g, g), 256, 0, s, pyr + c->mip_off[l], pyr, ssz, nlev, o[0], o[1], o[2], o[3], o[4]));
     l += nlev;
   }
 }
@@ -68,7 +68,7 @@ static void build_mips(vhap_ctx* c, f4* pyr, cudaStream_t s, int from_level = 0)
 void launch_tex_rebuild(vhap_ctx* c, const float* tex_extra, cudaStream_t s) {
   size_t n = (size_t)c->T * c->T;
   f4* pyr = c->mips[c->cur_mip];
-  LAUNCH(c, KID_TEX_L0, s, k_tex_level0<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(c->tex_painted, tex_extra, c->T, pyr));
+  LAUNCH(c, KID_TEX_L0, s, vh_launch(k_tex_level0, (unsigned)((n + 255) / 256), 256, 0, s, c->tex_painted, tex_extra, c->T, pyr));
   build_mips(c, pyr, s);
 }
 
@@ -131,7 +131,7 @@ __device__ __forceinline__ void row_load(const TexFoldArgs& a, int x, int y, boo
   r.msk = (a.w_res > 0.f && a.mask) ? a.mask[i] : 0;
 }
 
-__global__ void __launch_bounds__(256, TF_MINB) k_tex_fold2(TexFoldArgs a, float* __restrict__ partials, unsigned* __restrict__ counter, float* __restrict__ acc_out) {
+__global__ void __launch_bounds__(256, TF_MINB) k_tex_fold2(TexFoldArgs a, float* __restrict__ partials, unsigned* __restrict__ counter, float* __restrict__ acc_out) { VH_PDL_SYNC();
   __shared__ float sh[8 * 2];
   __shared__ float c1[(TF_ROWS / 2) * 128][3];        // folded gradient of levels >= 1 per level-1 texel of the band
   __shared__ float c2[((TF_ROWS + 3) / 4) * 64][3];
@@ -358,7 +358,7 @@ __device__ void tf3_issue(const TexFoldArgs& a, TF3Row* rows, uint64_t* bars, in
   if (want_mask) tf3_copy(r.msk, a.mask + i, 256u, bar);
 }
 
-__global__ void __launch_bounds__(256, 3) k_tex_fold3(TexFoldArgs a, float* __restrict__ partials, unsigned* __restrict__ counter, float* __restrict__ acc_out) {
+__global__ void __launch_bounds__(256, 3) k_tex_fold3(TexFoldArgs a, float* __restrict__ partials, unsigned* __restrict__ counter, float* __restrict__ acc_out) { VH_PDL_SYNC();
   extern __shared__ __align__(128) unsigned char tf3_smem[];
   TF3Row* rows = (TF3Row*)tf3_smem;
   __shared__ uint64_t bars[TF3_NS];
@@ -543,16 +543,16 @@ static void launch_fold_kernel(vhap_ctx* c, const TexFoldArgs& a, int rows, floa
     if (!attr_set) { const char* e = getenv("VHAP_B200_TEXFOLD_PAD_KB"); pad = e ? atoi(e) * 1024 : 0; }      // dev aid: fewer resident CTAs per SM
     const int smem = (int)(TF3_NS * sizeof(TF3Row)) + pad;
     if (!attr_set) { cudaFuncSetAttribute(k_tex_fold3, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
-    LAUNCH(c, KID_TEX_FOLD, s, k_tex_fold3<<<nblk, 256, smem, s>>>(a, c->tv_partials, c->tex_counter, acc_out));
+    LAUNCH(c, KID_TEX_FOLD, s, vh_launch(k_tex_fold3, nblk, 256, smem, s, a, c->tv_partials, c->tex_counter, acc_out));
   } else {
-    LAUNCH(c, KID_TEX_FOLD, s, k_tex_fold2<<<nblk, 256, 0, s>>>(a, c->tv_partials, c->tex_counter, acc_out));
+    LAUNCH(c, KID_TEX_FOLD, s, vh_launch(k_tex_fold2, nblk, 256, 0, s, a, c->tv_partials, c->tex_counter, acc_out));
   }
 }
 
 // TV + residual regulariser LOSS VALUES of the current texture (tracker.py:526-539), no gradient: used when the texture update is
 // deferred into the next step (the fold kernel then sees the texture one step late), so that a step's loss vector is complete.
 __global__ void __launch_bounds__(256) k_tex_reg_loss(const f4* __restrict__ tex, const float* __restrict__ extra, const uint8_t* __restrict__ mask, int T,
-                                                      float w_tv, float w_res, float* __restrict__ partials, unsigned* __restrict__ counter, float* __restrict__ out) {
+                                                      float w_tv, float w_res, float* __restrict__ partials, unsigned* __restrict__ counter, float* __restrict__ out) { VH_PDL_SYNC();
   __shared__ float sh[8 * 2];
   __shared__ bool is_last;
   const size_t n = (size_t)T * T;
@@ -599,7 +599,7 @@ void launch_tex_reg_loss(vhap_ctx* c, const float* tex_extra, const vhap_stage_c
   float w_tv = (cfg->training && cfg->opt_texture && cfg->w_reg_tex_tv >= 0.f) ? sh * cfg->w_reg_tex_tv / (3.f * (float)(T - 1) * (float)T) : 0.f;
   float w_res = (cfg->training && cfg->opt_texture && cfg->w_reg_tex_res >= 0.f) ? sh * cfg->w_reg_tex_res / (3.f * (float)T * (float)T) : 0.f;
   int nblk = c->tv_nblocks < 148 * 8 ? c->tv_nblocks : 148 * 8;
-  LAUNCH(c, KID_TEX_LOSS, s, k_tex_reg_loss<<<nblk, 256, 0, s>>>(c->mips[c->cur_mip], tex_extra, c->uvmask_res, T, w_tv, w_res, c->tv_partials, c->tex_counter, c->tex_loss));
+  LAUNCH(c, KID_TEX_LOSS, s, vh_launch(k_tex_reg_loss, nblk, 256, 0, s, c->mips[c->cur_mip], tex_extra, c->uvmask_res, T, w_tv, w_res, c->tv_partials, c->tex_counter, c->tex_loss));
 }
 
 void launch_tex_fold(vhap_ctx* c, float* tex_extra, float* g_out, float* m, float* v, float lr, int step, const vhap_stage_cfg* cfg,
@@ -672,7 +672,7 @@ int launch_tex_band_adam(vhap_ctx* c, float* tex_extra, const float* g_band, int
 
 // level 0 (painted + extra) and level 1 of the OTHER pyramid from the gathered row-major texture, planar tex_extra refreshed on the way
 __global__ void __launch_bounds__(256) k_tex_rebuild_rm(const float* __restrict__ ex_rm, const float* __restrict__ painted, int T, float* __restrict__ extra,
-                                                        f4* __restrict__ lvl0, f4* __restrict__ lvl1, int has_l1) {
+                                                        f4* __restrict__ lvl0, f4* __restrict__ lvl1, int has_l1) { VH_PDL_SYNC();
   const int tw = T < 256 ? T : 256, tpr = T / tw, tid = threadIdx.x;
   const int x = (blockIdx.x % tpr) * tw + tid, y = (blockIdx.x / tpr) * 2;
   const size_t n = (size_t)T * T;
@@ -698,13 +698,13 @@ void launch_tex_rebuild_rm(vhap_ctx* c, float* tex_extra, const float* ex_rm, cu
   int T = c->T, tw = T < 256 ? T : 256;
   f4* pyr = c->mips[c->cur_mip ^ 1];
   int has_l1 = c->max_level >= 1;
-  LAUNCH(c, KID_TEX_L0, s, k_tex_rebuild_rm<<<(T / tw) * (T / 2), 256, 0, s>>>(ex_rm, c->tex_painted, T, tex_extra, pyr, pyr + c->mip_off[has_l1 ? 1 : 0], has_l1));
+  LAUNCH(c, KID_TEX_L0, s, vh_launch(k_tex_rebuild_rm, (T / tw) * (T / 2), 256, 0, s, ex_rm, c->tex_painted, T, tex_extra, pyr, pyr + c->mip_off[has_l1 ? 1 : 0], has_l1));
   c->cur_mip ^= 1;
   build_mips(c, c->mips[c->cur_mip], s, has_l1);
 }
 
 __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
-                       float step_size, float bc2_sqrt) {
+                       float step_size, float bc2_sqrt) { VH_PDL_SYNC();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float gi = g[i];
@@ -715,7 +715,7 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
 
 struct AdamSegs { int n_seg; int off[24]; int len[24]; float lr[24]; };
 __global__ void k_adam_multi(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, AdamSegs sg, int total,
-                             float inv_bc1, float bc2_sqrt, const int* __restrict__ step_ptr, const float* __restrict__ lr_scale_ptr) {
+                             float inv_bc1, float bc2_sqrt, const int* __restrict__ step_ptr, const float* __restrict__ lr_scale_ptr) { VH_PDL_SYNC();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   if (step_ptr) { float st = (float)step_ptr[0]; inv_bc1 = lr_scale_ptr[0] / (1.f - powf(0.9f, st)); bc2_sqrt = sqrtf(1.f - powf(0.999f, st)); }
@@ -734,10 +734,10 @@ void launch_adam_multi(vhap_ctx* c, float* p, const float* g, float* m, float* v
   int total = 0;
   for (int k = 0; k < sg.n_seg; ++k) { sg.off[k] = (int)off[k]; sg.len[k] = (int)len[k]; sg.lr[k] = lr[k]; total += (int)len[k]; }
   float bc1 = 1.f - powf(0.9f, (float)step), bc2s = sqrtf(1.f - powf(0.999f, (float)step));
-  if (total > 0) LAUNCH(c, KID_ADAM, s, k_adam_multi<<<(total + 255) / 256, 256, 0, s>>>(p, g, m, v, sg, total, 1.f / bc1, bc2s, c->use_dev_step ? c->dev_step : nullptr, c->dev_lr_scale));
+  if (total > 0) LAUNCH(c, KID_ADAM, s, vh_launch(k_adam_multi, (total + 255) / 256, 256, 0, s, p, g, m, v, sg, total, 1.f / bc1, bc2s, c->use_dev_step ? c->dev_step : nullptr, c->dev_lr_scale));
 }
 
 void launch_adam(vhap_ctx* c, float* p, const float* g, float* m, float* v, int64_t n, float lr, int step, cudaStream_t s) {
   float bc1 = 1.f - powf(0.9f, (float)step), bc2s = sqrtf(1.f - powf(0.999f, (float)step));
-  LAUNCH(c, KID_ADAM, s, k_adam<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, g, m, v, n, lr / bc1, bc2s));
+  LAUNCH(c, KID_ADAM, s, vh_launch(k_adam, (unsigned)((n + 255) / 256), 256, 0, s, p, g, m, v, n, lr / bc1, bc2s));
 }
