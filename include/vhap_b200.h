@@ -212,6 +212,9 @@ int vhap_tex_apply_grad(vhap_ctx* ctx, float* tex_extra, const float* g_dense, f
 int vhap_dp_init(vhap_ctx* ctx, int32_t rank, int32_t world, unsigned char* handle_out_host /*64 bytes*/);
 int vhap_dp_connect(vhap_ctx* ctx, const unsigned char* handles_host /*[world][64]*/);
 int vhap_dp_status(vhap_ctx* ctx, int32_t* out_host);   /* 0 ok, 1 / 2 = a peer did not answer within ~4 s (slab / texture barrier; synchronises) */
+/* diagnostics: nanoseconds this rank waited for its peers since the last reset -- out[0] slab exchange, out[1] / out[2] texture barriers A / B,
+ * out[3] = number of slab exchanges (synchronises) */
+int vhap_dp_wait_stats(vhap_ctx* ctx, uint64_t* out_host /*[4]*/, int32_t reset);
 /* Peer-memory texture update: fold -> barrier -> in-switch reduction of this rank's row band (multimem.ld_reduce through the NVSwitch
  * multicast mapping; peer loads without one) -> regularisers + Adam on the band -> multicast store of the updated rows to every rank ->
  * barrier -> pyramid rebuild; no collective library.  g_rm / ex_rm ([T][3][T] floats) are SYMMETRIC buffers allocated by the caller on

@@ -16,6 +16,7 @@ ap.add_argument("--config", default="monocular")
 ap.add_argument("--dp-texture", default="auto")
 ap.add_argument("--dp-slab", default="peer")
 ap.add_argument("--json", default=None)
+ap.add_argument("--per-rank", default=None, help="prefix: every rank writes <prefix>.rank<r>.txt (rank 0 also prints)")
 a = ap.parse_args()
 world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -46,8 +47,14 @@ g0, g1 = [], []
 for k, v in per.items():
     h = len(v) // 2
     g0 += v[:h]; g1 += v[h:]
-if rank == 0:
-    print(f"# world {world}, texture mode {dp.texture_mode}, {a.config} {a.size} B={a.batch}")
+out = open(f"{a.per_rank}.rank{rank}.txt", "w") if a.per_rank else None
+if rank == 0 or out:
+    def print(*args, _p=print):            # noqa: A001  rank 0 -> stdout, every rank -> its file
+        if rank == 0:
+            _p(*args)
+        if out:
+            _p(*args, file=out)
+    print(f"# world {world}, rank {rank}, texture mode {dp.texture_mode}, {a.config} {a.size} B={a.batch}")
     for name, g in (("graph parity A", g0), ("graph parity B", g1)):
         g.sort()
         if not g:

@@ -105,6 +105,7 @@ def lib() -> C.CDLL:
         "vhap_dp_init": (i32, [vp, i32, i32, vp]),
         "vhap_dp_connect": (i32, [vp, vp]),
         "vhap_dp_status": (i32, [vp, P(i32)]),
+        "vhap_dp_wait_stats": (i32, [vp, P(C.c_uint64), i32]),
         "vhap_dp_tex_connect": (i32, [vp, vp, vp, vp, vp]),
         "vhap_dp_tex_update": (i32, [vp, vp, vp, vp, f32, i32, P(StageCfg), vp]),
         "vhap_dp_tex_part1": (i32, [vp, vp, vp]),
@@ -137,4 +138,4 @@ EXPORTED = ["vhap_abi_version", "vhap_last_error", "vhap_ctx_create", "vhap_ctx_
             "vhap_energy_forward", "vhap_energy_backward", "vhap_get_plane", "vhap_get_geometry", "vhap_profile_enable", "vhap_profile_kernel_count", "vhap_profile_kernel_name",
             "vhap_profile_read", "vhap_profile_timeline", "vhap_set_overlap", "vhap_set_want_planes", "vhap_overflow_flag",
             "vhap_set_injected_random", "vhap_set_loss_mask", "vhap_set_lr_scale", "vhap_project_backward", "vhap_vertex_normals",
-            "vhap_vertex_normals_backward", "vhap_render_photometric", "vhap_render_rgba_backward", "vhap_tex_grad_ptr", "vhap_set_tex_painted", "vhap_tex_rebuild", "vhap_tex_reg_fold_adam", "vhap_tex_apply_grad", "vhap_set_tex_grad_persistent", "vhap_dp_init", "vhap_dp_connect", "vhap_dp_status", "vhap_dp_tex_connect", "vhap_dp_tex_update", "vhap_dp_tex_part1", "vhap_dp_tex_join", "vhap_dp_tex_part2", "vhap_tex_fold_grad_rm", "vhap_tex_band_adam", "vhap_tex_rebuild_rm", "vhap_tex_defer", "vhap_tex_reg_loss", "vhap_set_render_wait_event", "vhap_assemble_losses", "vhap_adam", "vhap_adam_multi", "vhap_step_counters", "vhap_step_advance", "vhap_get_cur_mip", "vhap_set_cur_mip"]
+            "vhap_vertex_normals_backward", "vhap_render_photometric", "vhap_render_rgba_backward", "vhap_tex_grad_ptr", "vhap_set_tex_painted", "vhap_tex_rebuild", "vhap_tex_reg_fold_adam", "vhap_tex_apply_grad", "vhap_set_tex_grad_persistent", "vhap_dp_init", "vhap_dp_connect", "vhap_dp_status", "vhap_dp_wait_stats", "vhap_dp_tex_connect", "vhap_dp_tex_update", "vhap_dp_tex_part1", "vhap_dp_tex_join", "vhap_dp_tex_part2", "vhap_tex_fold_grad_rm", "vhap_tex_band_adam", "vhap_tex_rebuild_rm", "vhap_tex_defer", "vhap_tex_reg_loss", "vhap_set_render_wait_event", "vhap_assemble_losses", "vhap_adam", "vhap_adam_multi", "vhap_step_counters", "vhap_step_advance", "vhap_get_cur_mip", "vhap_set_cur_mip"]

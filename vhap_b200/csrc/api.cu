@@ -242,7 +242,7 @@ extern "C" void vhap_ctx_destroy(vhap_ctx* c) {
   FREE(c->face_flags); FREE(c->vert_flags); FREE(c->w_off); FREE(c->w_off_lap); FREE(c->rigid_indptr); FREE(c->rigid_vids); FREE(c->uvmask_res);
   FREE(c->mips[0]); FREE(c->mips[1]); FREE(c->tex_painted); FREE(c->g_tex); FREE(c->tv_partials); FREE(c->tex_counter); FREE(c->tex_loss); FREE(c->scan_state); FREE(c->scal); FREE(c->acc); FREE(c->maxslot);
   for (int r = 0; r < VH_DP_MAX; ++r) if (c->dp_peers_host[r]) cudaIpcCloseMemHandle(c->dp_peers_host[r]);
-  FREE(c->dp_box); FREE(c->dp_epoch); FREE(c->dp_peers_dev); FREE(c->dp_grm_peers_dev); FREE(c->dp_exrm_peers_dev); FREE(c->dp_gband); FREE(c->dp_exband); FREE(c->dp_counter);
+  FREE(c->dp_box); FREE(c->dp_epoch); FREE(c->dp_wait); FREE(c->dp_peers_dev); FREE(c->dp_grm_peers_dev); FREE(c->dp_exrm_peers_dev); FREE(c->dp_gband); FREE(c->dp_exband); FREE(c->dp_counter);
   FREE(c->overflow_flag); FREE(c->pool_base); FREE(c->pool_count); FREE(c->dev_lr_scale); FREE(c->dev_step);
   free(c);
 }
@@ -580,6 +580,7 @@ extern "C" int vhap_dp_init(vhap_ctx* ctx, int32_t rank, int32_t world, unsigned
   if (!ctx->dp_box) {
     CK(cudaMalloc((void**)&ctx->dp_box, VH_DP_BOX_FLOATS * sizeof(float)));
     CK(cudaMalloc((void**)&ctx->dp_epoch, 4 * sizeof(int)));       // [0] slab epoch, [1] error flag, [2] [3] epochs of the texture barriers A / B
+    CK(cudaMalloc((void**)&ctx->dp_wait, 4 * sizeof(unsigned long long))); CK(cudaMemset(ctx->dp_wait, 0, 4 * sizeof(unsigned long long)));
     ctx->dp_err = ctx->dp_epoch + 1;
   }
   CK(cudaMemset(ctx->dp_box, 0, VH_DP_BOX_FLOATS * sizeof(float)));
@@ -675,6 +676,16 @@ extern "C" int vhap_dp_tex_update(vhap_ctx* ctx, float* tex_extra, float* adam_m
 extern "C" int vhap_dp_status(vhap_ctx* ctx, int32_t* out_host) {
   *out_host = 0;
   if (ctx->dp_err) CK(cudaMemcpy(out_host, ctx->dp_err, sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// time this rank spent waiting for its peers since the last reset: out[0] ns in the mid-step slab exchange (k_finalize), out[1] / out[2] ns
+// in the texture barriers A / B, out[3] number of slab exchanges.  Synchronises the device.
+extern "C" int vhap_dp_wait_stats(vhap_ctx* ctx, uint64_t* out_host, int32_t reset) {
+  for (int i = 0; i < 4; ++i) out_host[i] = 0;
+  if (!ctx->dp_wait) return 0;
+  CK(cudaMemcpy(out_host, ctx->dp_wait, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (reset) CK(cudaMemset(ctx->dp_wait, 0, 4 * sizeof(unsigned long long)));
   return 0;
 }
 

@@ -20,7 +20,7 @@
 // Reuse is safe: a rank overwrites its g_rm (next fold) only after it passed barrier B, i.e. after every peer finished reducing; a rank
 // writes into a peer's ex_rm (next broadcast) only after that peer passed barrier A again, i.e. after its rebuild of this step.
 #define DP_FLAG_OFF(which) ((size_t)2 * VH_DP_MAX * 8 + (size_t)(1 + (which)) * VH_DP_MAX)      // after the slab slots and the slab flags
-__global__ void k_dp_barrier(float* mine, float* const* peers, int rank, int world, int which, int* epoch, int* err) { VH_PDL_SYNC();
+__global__ void k_dp_barrier(float* mine, float* const* peers, int rank, int world, int which, int* epoch, int* err, unsigned long long* wait) { VH_PDL_SYNC();
   if (threadIdx.x != 0) return;
   const int e = epoch[which] + 1;
   epoch[which] = e;
@@ -28,9 +28,11 @@ __global__ void k_dp_barrier(float* mine, float* const* peers, int rank, int wor
   for (int p = 0; p < world; ++p) ((volatile int*)(peers[p] + DP_FLAG_OFF(which)))[rank] = e;
   volatile const int* flags = (volatile const int*)(mine + DP_FLAG_OFF(which));
   const long long t0 = clock64();
+  unsigned long long w0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(w0));
   for (int j = 0; j < world; ++j)
     while (flags[j] - e < 0) { if (clock64() - t0 > (1ll << 33)) { *err = 2; break; } }      // ~4 s: a dead peer must not hang the GPU
   __threadfence_system();
+  if (wait) { unsigned long long w1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(w1)); wait[1 + which] += w1 - w0; }
 }
 
 __device__ __forceinline__ float4 mc_ld_reduce(const float* mc) {
@@ -76,7 +78,7 @@ __global__ void __launch_bounds__(256) k_dp_bcast_band(float* mc, float* const* 
 }
 
 void launch_dp_barrier(vhap_ctx* c, int which, cudaStream_t s) {
-  LAUNCH(c, KID_MISC, s, vh_launch(k_dp_barrier, 1, 32, 0, s, c->dp_box, c->dp_peers_dev, c->dp_rank, c->dp_world, which, c->dp_epoch + 2, c->dp_err));
+  LAUNCH(c, KID_MISC, s, vh_launch(k_dp_barrier, 1, 32, 0, s, c->dp_box, c->dp_peers_dev, c->dp_rank, c->dp_world, which, c->dp_epoch + 2, c->dp_err, c->dp_wait));
 }
 void launch_dp_reduce_band(vhap_ctx* c, float* g_band, cudaStream_t s) {
   const size_t nb4 = (size_t)3 * c->T * c->T / c->dp_world / 4;

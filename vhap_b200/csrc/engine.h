@@ -78,7 +78,7 @@ struct vhap_ctx {
   int* dev_step; int use_dev_step;                // device counters [0] Adam step (1-based), [1] global step; used when use_dev_step
   // data-parallel peer exchange of the forward slab over NVLink (CUDA IPC mailboxes, render.cu k_forward_slab / k_finalize): replaces the
   // mid-step NCCL all-gather + its host-side glue kernels on the step's critical chain
-  int dp_rank, dp_world; float* dp_box; float** dp_peers_dev; void* dp_peers_host[VH_DP_MAX]; int* dp_epoch; int* dp_err;
+  int dp_rank, dp_world; float* dp_box; float** dp_peers_dev; void* dp_peers_host[VH_DP_MAX]; int* dp_epoch; int* dp_err; unsigned long long* dp_wait;   // dp_wait[4]: ns spent waiting for peers (slab, barrier A, barrier B), exchanges
   // peer-memory texture update (dp_tex.cu): caller-allocated symmetric buffers g_rm / ex_rm [T][3][T], their NVSwitch multicast mappings (or NULL)
   unsigned* dp_counter; int dp_tex_forked;
   float *dp_grm, *dp_grm_mc, **dp_grm_peers_dev, *dp_exrm, *dp_exrm_mc, **dp_exrm_peers_dev, *dp_gband, *dp_exband;
@@ -119,11 +119,13 @@ static inline void vh_prof_end(vhap_ctx* c, int kid, cudaStream_t s) {
   VhProf* p = vh_prof(c);
   if (p->on && p->n[kid] < VH_PROF_SLOTS) { vh_prof_record(p, p->ev[kid][p->n[kid]][1], s); p->n[kid]++; }
 }
-// Programmatic dependent launch: every kernel of the engine is launched with the programmatic-stream-serialization attribute and starts
-// with VH_PDL_SYNC() -- "my dependents may be scheduled" followed by "wait until everything before me in the stream has completed and
-// is visible".  The step is a chain of ~40 short dependent kernels; the launch latency of kernel N+1 (2.7 us between graph nodes, r02
-// timeline) is paid while kernel N still runs, its CTAs sit resident at the wait.  Nothing is read or written before the wait, so the
-// semantics are those of plain stream order.  VHAP_B200_PDL=0 launches without the attribute (the wait is then a no-op).
+// Programmatic dependent launch (opt-in, VHAP_B200_PDL=1): every kernel of the engine starts with VH_PDL_SYNC() -- "my dependents may be
+// scheduled" followed by "wait until everything before me in the stream has completed and is visible" -- and can be launched with the
+// programmatic-stream-serialization attribute, so that the launch latency of kernel N+1 is paid while kernel N still runs (its CTAs sit
+// resident at the wait).  Nothing is read or written before the wait: the semantics are those of plain stream order, and without the
+// attribute the two instructions are no-ops.  MEASURED (tools/micro/graph_gap.cu, profiles/r02_graph_gap.txt): a graph node costs 1.0-2.7 us
+// plain and 0.8-1.9 us with PDL edges; on the step that is 0.7305 vs 0.7318 ms at one GPU (noise) but 0.9035 vs 0.8621 ms at two GPUs --
+// the early-resident CTAs of the chain keep the collective kernels of the side streams off the SMs.  Hence OFF by default.
 #if defined(__CUDA_ARCH__)
 #define VH_PDL_SYNC() do { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); asm volatile("griddepcontrol.wait;" ::: "memory"); } while (0)
 #else
@@ -131,7 +133,7 @@ static inline void vh_prof_end(vhap_ctx* c, int kid, cudaStream_t s) {
 #endif
 static inline int vh_pdl_enabled() {
   static int on = -1;
-  if (on < 0) { const char* e = getenv("VHAP_B200_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
+  if (on < 0) { const char* e = getenv("VHAP_B200_PDL"); on = (e && e[0] == '1') ? 1 : 0; }
   return on;
 }
 template <typename... KArgs, typename... Args>

@@ -60,18 +60,11 @@ __global__ void __launch_bounds__(PB) k_pool_count(const int* __restrict__ tri_i
   for (int j = 0; j < POOL_PPT; ++j) id[j] = base + 32 * j < n ? tri_id[base + 32 * j] : -1;
 #pragma unroll
   for (int j = 0; j < POOL_PPT; ++j) cid[j] = id[j] >= 0 ? fid2cid[id[j]] : -1;
-  int c0 = 0;
-  unsigned any = 0;
 #pragma unroll
-  for (int j = 0; j < POOL_PPT; ++j) { c0 += __popc(__ballot_sync(0xffffffffu, cid[j] == 0)); any |= __ballot_sync(0xffffffffu, cid[j] > 0); }
-  if (lane == 0 && c0) atomicAdd(&cnt[0], c0);
-  if (any)                                                       // warps that are all background skip the per-cluster ballots
-    for (int c = 1; c < ncl; ++c) {
-      int k = 0;
-#pragma unroll
-      for (int j = 0; j < POOL_PPT; ++j) k += __popc(__ballot_sync(0xffffffffu, cid[j] == c));
-      if (lane == 0 && k) atomicAdd(&cnt[c], k);
-    }
+  for (int j = 0; j < POOL_PPT; ++j) {                           // one shared-memory add per (row, cluster present in the row)
+    const unsigned grp = __match_any_sync(0xffffffffu, cid[j]);
+    if (lane == __ffs(grp) - 1 && cid[j] >= 0) atomicAdd(&cnt[cid[j]], __popc(grp));
+  }
   __syncthreads();
   if (threadIdx.x < 16) blk_count[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = cnt[threadIdx.x];    // [16][nblk]
 }
@@ -103,46 +96,51 @@ __global__ void __launch_bounds__(PB) k_pool_scatter(const int* __restrict__ tri
   }
 #pragma unroll
   for (int j = 0; j < POOL_PPT; ++j) cid[j] = id[j] >= 0 ? fid2cid[id[j]] : -1;
-  {                                                            // antialias pairs: one counter reservation per warp
-    unsigned m0[POOL_PPT], m1[POOL_PPT];
-    int tot = 0;
+  // antialias pairs: ONE reservation on the global counter per CTA (per-warp reservations were thousands of same-address atomics)
+  __shared__ int wpair[PB / 32];
+  __shared__ int s_pair_base;
+  unsigned m0[POOL_PPT], m1[POOL_PPT];
+  int tot = 0;
 #pragma unroll
-    for (int j = 0; j < POOL_PPT; ++j) {
-      m0[j] = __ballot_sync(0xffffffffu, idr[j] != id[j]); m1[j] = __ballot_sync(0xffffffffu, idd[j] != id[j]);
-      tot += __popc(m0[j]) + __popc(m1[j]);
-    }
-    if (tot) {
-      int at = 0;
-      if (lane == 0) at = atomicAdd(pair_count, tot);
-      at = __shfl_sync(0xffffffffu, at, 0);
-#pragma unroll
-      for (int j = 0; j < POOL_PPT; ++j) {
-        const int pix = (int)(pix0 + 32 * j);
-        if (idr[j] != id[j]) pair_list[at + __popc(m0[j] & below)] = pix * 2;
-        at += __popc(m0[j]);
-        if (idd[j] != id[j]) pair_list[at + __popc(m1[j] & below)] = pix * 2 + 1;
-        at += __popc(m1[j]);
-      }
-    }
+  for (int j = 0; j < POOL_PPT; ++j) {
+    m0[j] = __ballot_sync(0xffffffffu, idr[j] != id[j]); m1[j] = __ballot_sync(0xffffffffu, idd[j] != id[j]);
+    tot += __popc(m0[j]) + __popc(m1[j]);
   }
+  if (lane == 0) wpair[w] = tot;
+  // cluster ranks: lanes of one cluster find each other with match.any; the running per-warp count of a cluster lives in shared memory
+  // (rows are processed in order, the group's lowest lane updates it), so rank = members in earlier rows + members in lower lanes
+  for (int c = lane; c < 16; c += 32) wcnt[c][w] = 0;
+  __syncwarp();
   int rank[POOL_PPT];
 #pragma unroll
-  for (int j = 0; j < POOL_PPT; ++j) rank[j] = 0;
-  unsigned any = 0;
-#pragma unroll
-  for (int j = 0; j < POOL_PPT; ++j) any |= __ballot_sync(0xffffffffu, cid[j] > 0);
-  for (int c = 0; c < 16; ++c) {
-    if (c >= ncl || (c > 0 && !any)) { if (lane == 0) wcnt[c][w] = 0; continue; }
-    int run = 0;                                               // members of cluster c in the rows before row j of this warp
-#pragma unroll
-    for (int j = 0; j < POOL_PPT; ++j) {
-      const unsigned m = __ballot_sync(0xffffffffu, cid[j] == c);
-      if (cid[j] == c) rank[j] = run + __popc(m & below);
-      run += __popc(m);
-    }
-    if (lane == 0) wcnt[c][w] = run;
+  for (int j = 0; j < POOL_PPT; ++j) {
+    const unsigned grp = __match_any_sync(0xffffffffu, cid[j]);
+    const int leader = __ffs(grp) - 1;
+    int prev = 0;
+    if (lane == leader && cid[j] >= 0) { prev = wcnt[cid[j]][w]; wcnt[cid[j]][w] = prev + __popc(grp); }
+    prev = __shfl_sync(0xffffffffu, prev, leader);
+    rank[j] = prev + __popc(grp & below);
+    __syncwarp();
   }
   __syncthreads();
+  if (threadIdx.x == 0) {
+    int sum = 0;
+    for (int k = 0; k < PB / 32; ++k) sum += wpair[k];
+    s_pair_base = sum ? atomicAdd(pair_count, sum) : 0;
+  }
+  __syncthreads();
+  if (tot) {
+    int at = s_pair_base;
+    for (int k = 0; k < w; ++k) at += wpair[k];
+#pragma unroll
+    for (int j = 0; j < POOL_PPT; ++j) {
+      const int pix = (int)(pix0 + 32 * j);
+      if (idr[j] != id[j]) pair_list[at + __popc(m0[j] & below)] = pix * 2;
+      at += __popc(m0[j]);
+      if (idd[j] != id[j]) pair_list[at + __popc(m1[j] & below)] = pix * 2 + 1;
+      at += __popc(m1[j]);
+    }
+  }
 #pragma unroll
   for (int j = 0; j < POOL_PPT; ++j)
     if (cid[j] >= 0) {
@@ -230,10 +228,10 @@ __global__ void __launch_bounds__(PB, VH_C1_MIN) k_passC1(PassArgs P, const floa
 }
 
 #ifndef VH_C2_MINBLOCKS
-#define VH_C2_MINBLOCKS 2
+#define VH_C2_MINBLOCKS 4      // x 128 threads = 128 registers per thread; 3 x 256 (85 registers, spills) measured 0.156 vs 0.117 ms (r14)
 #endif
 #ifndef VH_C2_PB
-#define VH_C2_PB 256
+#define VH_C2_PB 128           // 128-thread CTAs: 0.115 vs 0.117 ms with 256 (r14), finer tail
 #endif
 #ifndef VH_C2_SPLIT
 #define VH_C2_SPLIT 0          // 1: texel-gradient half of pass C2 as a concurrent kernel on a second stream -- measured SLOWER (0.757 vs 0.735 ms/step, r6)
@@ -350,7 +348,8 @@ __global__ void __launch_bounds__(256) k_reduce_cols(const float* __restrict__ p
 // there; k_finalize spins on its own mailbox's flags and reduces the slots in rank order (identical result on every rank).  Two slot
 // parities make the reuse safe: a rank can only write epoch e + 2 after it passed k_finalize(e + 1), which needed every peer's flag e + 1,
 // raised after that peer's k_finalize(e) had finished reading the slots of epoch e.
-struct DpBox { int rank, world; float* const* peers; int* epoch; int* err; float* mine; };
+struct DpBox { int rank, world; float* const* peers; int* epoch; int* err; float* mine; unsigned long long* wait; };
+__device__ __forceinline__ unsigned long long vh_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __global__ void __launch_bounds__(256) k_forward_slab(const float* __restrict__ partials, int rows, float* __restrict__ acc,
                                const unsigned long long* __restrict__ maxslot, const float* __restrict__ lights, float n_pix_total, float* __restrict__ slab,
                                DpBox dp) { VH_PDL_SYNC();
@@ -406,6 +405,7 @@ __global__ void k_finalize(const float* __restrict__ slab, const float* __restri
     const int e = *dp.epoch;
     volatile int* flags = (volatile int*)(dp.mine + 2 * VH_DP_MAX * 8);
     const long long t0 = clock64();
+    const unsigned long long w0 = vh_globaltimer();
     abs_sum = 0.f; nfg = 0.f; varsum = 0.f; mx = -INFINITY;
     for (int j = 0; j < dp.world; ++j) {
       while (flags[j] - e < 0) { if (clock64() - t0 > (1ll << 33)) { *dp.err = 1; break; } }      // ~4 s: a dead peer must not hang the GPU
@@ -414,6 +414,7 @@ __global__ void k_finalize(const float* __restrict__ slab, const float* __restri
       abs_sum += sl[0]; nfg += sl[1]; varsum += sl[2]; mx = fmaxf(mx, sl[3]);
     }
     *dp.epoch = e + 1;
+    if (dp.wait) { dp.wait[0] += vh_globaltimer() - w0; dp.wait[3] += 1; }
   }
   float photo_scale = (cfg.w_photo >= 0.f && nfg > 0.f) ? cfg.w_photo / (3.f * nfg) : 0.f;
   scal[0] = photo_scale;
@@ -527,7 +528,7 @@ void launch_render_forward(vhap_ctx* c, PassArgs& P, cudaStream_t s, bool zeroed
 }
 
 static DpBox dp_box_of(vhap_ctx* c) {
-  DpBox d; d.rank = c->dp_rank; d.world = c->dp_peers_dev ? c->dp_world : 1; d.peers = c->dp_peers_dev; d.epoch = c->dp_epoch; d.err = c->dp_err; d.mine = c->dp_box;
+  DpBox d; d.rank = c->dp_rank; d.world = c->dp_peers_dev ? c->dp_world : 1; d.peers = c->dp_peers_dev; d.epoch = c->dp_epoch; d.err = c->dp_err; d.mine = c->dp_box; d.wait = c->dp_wait;
   return d;
 }
 void launch_forward_slab(vhap_ctx* c, const PassArgs& P, const float* lights, float* slab, cudaStream_t s) {
