@@ -129,8 +129,8 @@ class DataParallelStep:
         """texture: "peer" (fold -> in-switch band reduction over NVSwitch multicast -> Adam on 1/world of the rows -> multicast store ->
         rebuild, all in the engine's own kernels over symmetric memory), "shard" (the same dataflow with NCCL reduce-scatter / all-gather,
         TexShardComm on its own communicator), "allreduce" (round-1 baseline: dense all-reduce of the regularised gradient, full-texture Adam
-        on every rank) or "auto" (default: "allreduce" at 2 ranks, "peer" from 3 ranks on -- falling back to "shard" when symmetric memory
-        cannot be set up; the choice is in .texture_mode).
+        on every rank) or "auto" (default: "peer", falling back to "shard" when symmetric memory cannot be set up; the choice is in
+        .texture_mode).
         slab: "peer" (default: the mid-step batch-global scalars travel through CUDA-IPC mailboxes written / read by the engine's own
         kernels over NVLink, Engine.dp_connect) or "nccl" (round-1 baseline: an all-gather + host-side reduction between the halves)"""
         self.e, self.group = engine, group
@@ -146,10 +146,8 @@ class DataParallelStep:
             engine.dp_connect(dist.get_rank(group), self.world, gather)
             self.peer_slab = True
         self.texture_mode = "single" if self.world == 1 else texture
-        if texture == "auto" and self.world == 2:
-            # measured (profiles/r02_scale.md): at 2 ranks the dense all-reduce + full-texture Adam wins (0.873 vs 0.926 ms/step: one exchange
-            # instead of two barriers, and only half of the Adam traffic to save); from 4 ranks on the peer-memory path is flat in N and ahead
-            texture = self.texture_mode = "allreduce"
+        # "auto" = the peer-memory path at every world size: measured (profiles/r02_scale.md, final state) 0.856 vs 0.861 ms/step at 2 ranks
+        # (dense all-reduce + full-texture Adam), 0.850 vs 0.989 at 8
         if self.world > 1 and texture in ("peer", "auto"):
             # peer-memory update (NVLS when the fabric has multicast): needs the barrier mailboxes of the peer slab exchange
             try:
