@@ -1,6 +1,6 @@
 #!/bin/bash
 # dev aid: A/B the experiment variants built into vhap_b200/variants/ (build_ext.py with VH_SO_OUT / VH_EXTRA_FLAGS) on the GPU box
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 run() { timeout 200 python bench.py --steps 40 --warmup 5 --no-cpu 2>&1 | tail -1 | python -c "
 import sys,json
 d=json.loads(sys.stdin.read()); k=d['kernels']

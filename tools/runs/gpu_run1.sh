@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 GPU call 1: all GPU tests (incl. the new bench-configuration parity tests), baseline bench, ncu captures of the hot kernels
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 rm -f gpurun_out/parity_r02.jsonl
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/r1_smi.txt 2>&1

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 GPU call 10a (2 GPUs): DP parity with the split peer chain + N=2 bench (peer, allreduce) + timeline
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_shard.py -q -p no:cacheprovider -s > gpurun_out/r10_pytest_shard.log 2>&1
 bn() { timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $1 --master-addr 127.0.0.1 --master-port 29655 bench.py --gpus $1 --steps 40 --warmup 5 --no-extra --dp-texture $2 \

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 GPU call 10b (1 GPU): full GPU suite, smoke, bench (+ A/B: no-pipeline, 4-row TMA ring), ncu launch list, timeline
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 rm -f gpurun_out/parity_r02.jsonl
 timeout 1800 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/r10_pytest_all.log 2>&1

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 GPU call 11 (1 GPU): programmatic dependent launch on / off
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q -x -p no:cacheprovider > gpurun_out/r11_pytest_all.log 2>&1
 timeout 300 python bench.py --steps 40 --warmup 5 --no-extra --no-cpu > gpurun_out/r11_bench_n1_pdl.json 2> gpurun_out/r11_bench_n1_pdl.err

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 GPU call 12 (1 GPU): graph node latency micro-benchmark, pass C2 software prefetch variant
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 120 tools/micro/graph_gap > gpurun_out/r12_graph_gap.txt 2>&1
 VHAP_B200_SO=$PWD/vhap_b200/variants/c2pf.so timeout 300 python bench.py --steps 40 --warmup 5 --no-extra --no-cpu > gpurun_out/r12_bench_n1_c2pf.json 2> gpurun_out/r12_bench_n1_c2pf.err

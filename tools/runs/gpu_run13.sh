@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 GPU call 13 (1 GPU): pools with 4 pixels per thread, dynamic work queue in the backward passes
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q -x -p no:cacheprovider > gpurun_out/r13_pytest_all.log 2>&1
 timeout 300 python bench.py --steps 40 --warmup 5 --no-extra --no-cpu > gpurun_out/r13_bench_n1.json 2> gpurun_out/r13_bench_n1.err

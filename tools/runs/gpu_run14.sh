@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 GPU call 14 (1 GPU): fewer launches (self-clearing scan, merged clears, camera set-up folded), pass C2 block-shape variants
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q -x -p no:cacheprovider > gpurun_out/r14_pytest_all.log 2>&1
 timeout 300 python bench.py --steps 40 --warmup 5 --no-extra --no-cpu > gpurun_out/r14_bench_n1.json 2> gpurun_out/r14_bench_n1.err

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 GPU call 16 (2 GPUs): full GPU suite (pool kernels changed), N=2 bench variants with per-rank peer-wait diagnostics
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q -x -p no:cacheprovider > gpurun_out/r16_pytest_all.log 2>&1
 bn() { tag=$1; shift; timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29655 bench.py --gpus 2 --steps 40 --warmup 5 --no-extra "$@" \

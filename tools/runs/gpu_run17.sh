@@ -1,7 +1,7 @@
 #!/bin/bash
 # round-2 GPU call 17 (1 GPU): validation of the final state -- full GPU suite, smoke, default bench line, ncu launch list + full capture
 # of the kernels changed since the last capture, graph timeline
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 rm -f gpurun_out/parity_r02.jsonl
 timeout 1800 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/r17_pytest_all.log 2>&1

@@ -1,7 +1,7 @@
 #!/bin/bash
 # round-2 GPU call 18 (8 GPUs): scaling points of the final state -- N = 8 (auto = peer+nvls, with the extra configurations), N = 8 allreduce,
 # N = 4 and N = 2 (auto), N = 2 peer
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 bn() { n=$1; tag=$2; shift; shift; timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29655 bench.py --gpus $n --steps 40 --warmup 5 "$@" \
      > gpurun_out/r18_bench_n${n}_$tag.json 2> gpurun_out/r18_bench_n${n}_$tag.err; }

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 GPU call 19 (1 GPU): occupancy variants of passes A / C1
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 for v in base c1m3 c1m5 c1m6 am3 am6; do
   if [ $v = base ]; then unset VHAP_B200_SO; else export VHAP_B200_SO=$PWD/vhap_b200/variants/$v.so; fi

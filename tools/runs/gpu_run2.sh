@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 GPU call 2: GPU tests (full log), new bench incl. extra_configs, A/B of the texture fold (v1/v2) and the C2 vertex aggregation
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 rm -f gpurun_out/parity_r02.jsonl
 timeout 1500 python -m pytest tests -m gpu -q -p no:cacheprovider -x --deselect tests/test_gpu_bench_configs.py --deselect tests/test_gpu_dropin_tracker.py > gpurun_out/r2_pytest_old.log 2>&1

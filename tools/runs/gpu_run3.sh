@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 GPU call 3 (2 GPUs): data-parallel parity on real NCCL + scaling at N=2 for both texture-update variants
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 nvidia-smi -L > gpurun_out/r3_smi.txt 2>&1
 timeout 900 python -m pytest tests/test_gpu_shard.py -q -p no:cacheprovider -s > gpurun_out/r3_pytest_shard.log 2>&1

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 GPU call 4 (2 GPUs): DP parity (default peer+shard and the NCCL baseline), N=2 bench for the variants, single-GPU tests + bench + ncu of the TMA fold
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 rm -f gpurun_out/parity_r02.jsonl
 timeout 900 python -m pytest tests/test_gpu_shard.py -q -p no:cacheprovider -s > gpurun_out/r4_pytest_shard.log 2>&1

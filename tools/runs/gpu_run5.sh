@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 GPU call 5 (2 GPUs): peer-memory / NVLS texture update parity + N=2 bench variants; view-sharing + bench-config tests; N=1 bench with extras
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 rm -f gpurun_out/parity_r02.jsonl
 timeout 900 python -m pytest tests/test_gpu_shard.py -q -p no:cacheprovider -s > gpurun_out/r5_pytest_shard.log 2>&1

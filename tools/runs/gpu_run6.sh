@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 GPU call 6 (2 GPUs): DP parity after the barrier merge / lean gradient fold, N=2 variants, N=1 A/B of the C2 split
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_shard.py tests/test_gpu_modular.py tests/test_gpu_parity.py -q -p no:cacheprovider -s > gpurun_out/r6_pytest.log 2>&1
 b2() { timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29633 bench.py --gpus 2 --steps 40 --warmup 5 --no-extra $2 \

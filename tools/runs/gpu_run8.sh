@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 GPU call 8 (8 GPUs): scaling at N=8 for the three data-parallel texture-update variants (+ the extra configs once)
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 nvidia-smi -L | wc -l > gpurun_out/r8_ngpu.txt
 b8() { timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29655 bench.py --gpus 8 --steps 40 --warmup 5 $2 \
