@@ -465,7 +465,7 @@ def cpu_baseline(H, W, sample_frames=4, steps=3, warmup=1):
     d1 = time.perf_counter() - t1
     return {"value": round(B * steps / dtm, 4), "unit": UNIT, "cores": ncores, "kind": "port",
             "sample": f"{B} frames per step x {steps} timed iterations after {warmup} warm-up at {H}x{W}, 2048^2 texture, full energy+backward+Adam (oracle/, torch CPU "
-                      f"fp32, {ncores} of {os.cpu_count()} host threads; per-triangle numpy rasteriser); {dtm:.1f} s; NOTE the bench batch is 16 frames per step: "
+                      f"fp32, {ncores} of {os.cpu_count()} host threads; batched numpy rasteriser); {dtm:.1f} s; NOTE the bench batch is 16 frames per step: "
                       f"the per-step 2048^2 texture cost (TV, mip pyramid, Adam) is amortised over {B} frames here instead of 16",
             "landmark_stage_iters_per_s": round(n1 / d1, 2),
             "landmark_stage_sample": f"configs[0]: 1 frame 256x256 lmk_init_all, {n1} iterations, {ncores} threads"}

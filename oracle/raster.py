@@ -48,9 +48,11 @@ def _floordiv(a, b):
     return a // b
 
 
-def rasterize_ids(clip, tri, H, W, cull_backface=False):
-    """clip [B,V,4] float32 numpy, tri [F,3] int -> ids [B,H,W] int32 (triangle index + 1, 0 = empty;
-    row 0 = bottom) and the winning depth [B,H,W] float32 (inf where empty)."""
+def rasterize_ids_loop(clip, tri, H, W, cull_backface=False):
+    """The specification written as one numpy block per triangle (slow: a Python loop over the triangles).  `rasterize_ids` evaluates the same
+    arithmetic batched over the triangles; tests/test_oracle_raster_fast.py holds the two to bit-identical ids AND depths.
+    clip [B,V,4] float32 numpy, tri [F,3] int -> ids [B,H,W] int32 (triangle index + 1, 0 = empty; row 0 = bottom) and the winning
+    depth [B,H,W] float32 (inf where empty)."""
     clip = np.asarray(clip, dtype=F32)
     tri = np.asarray(tri, dtype=np.int64)
     B = clip.shape[0]
@@ -106,6 +108,112 @@ def rasterize_ids(clip, tri, H, W, cull_backface=False):
             win = ok & ((zp < zs) | ((zp == zs) & (t + 1 < isub)))
             zs[win] = zp[win]
             isub[win] = t + 1
+    return ids, zbuf
+
+
+
+_BOXES = (4, 8, 16, 32)     # triangles are evaluated batched on the smallest K x K pixel grid their bounding box fits; larger ones go through the per-triangle block
+
+
+def _order_key(z):
+    """fp32 depth -> uint32 whose unsigned order is the float order (z in [-1, 1], finite)"""
+    u = z.view(np.uint32)
+    return np.where(u & np.uint32(0x80000000), ~u, u | np.uint32(0x80000000))
+
+
+def rasterize_ids(clip, tri, H, W, cull_backface=False):
+    """clip [B,V,4] float32 numpy, tri [F,3] int -> ids [B,H,W] int32 (triangle index + 1, 0 = empty;
+    row 0 = bottom) and the winning depth [B,H,W] float32 (inf where empty).
+
+    Same arithmetic as `rasterize_ids_loop` (the specification above), batched: all triangles with a pixel bounding box of at most
+    K x K (K in _BOXES) are tested on a [n, K, K] grid at once (int64 edge functions, individually rounded fp32 depth plane), the
+    candidates are resolved per pixel by the minimum of the packed key (order-preserving depth bits << 32 | triangle id) = nearest
+    depth, ties to the lower triangle index; the few larger triangles are merged with the per-triangle block afterwards."""
+    clip = np.asarray(clip, dtype=F32)
+    tri = np.asarray(tri, dtype=np.int64)
+    B = clip.shape[0]
+    ids = np.zeros((B, H, W), np.int32)
+    zbuf = np.full((B, H, W), np.inf, F32)
+    for b in range(B):
+        X, Y, zw, valid = snap_vertices(clip[b], H, W)
+        tv = valid[tri].all(1)
+        X3, Y3, Z3 = X[tri], Y[tri], zw[tri]
+        d1x, d1y = X3[:, 1] - X3[:, 0], Y3[:, 1] - Y3[:, 0]
+        d2x, d2y = X3[:, 2] - X3[:, 0], Y3[:, 2] - Y3[:, 0]
+        area2 = d1x * d2y - d2x * d1y
+        keep = tv & (area2 != 0)
+        if cull_backface:
+            keep &= area2 > 0
+        mnx, mxx = X3.min(1), X3.max(1)
+        mny, mxy = Y3.min(1), Y3.max(1)
+        px0 = np.maximum(-_floordiv(-(mnx + W * 8 - 8), 16), 0)
+        px1 = np.minimum(_floordiv(mxx + W * 8 - 8, 16), W - 1)
+        py0 = np.maximum(-_floordiv(-(mny + H * 8 - 8), 16), 0)
+        py1 = np.minimum(_floordiv(mxy + H * 8 - 8, 16), H - 1)
+        keep &= (px0 <= px1) & (py0 <= py1)
+        ext = np.maximum(px1 - px0, py1 - py0)                          # bounding-box extent - 1
+        small = keep & (ext < _BOXES[-1])
+        key = np.full(H * W, np.uint64(0xFFFFFFFFFFFFFFFF), np.uint64)
+        zflat = np.full(H * W, np.inf, F32)
+        work = []
+        lo = -1
+        for K in _BOXES:
+            ts = np.nonzero(keep & (ext > lo) & (ext < K))[0]
+            lo = K - 1
+            CH = max(64, (1 << 18) // (K * K))
+            work += [(K, ts[c0:c0 + CH]) for c0 in range(0, len(ts), CH)]
+        for K, t in work:
+            oy, ox = np.meshgrid(np.arange(K, dtype=np.int64), np.arange(K, dtype=np.int64), indexing="ij")
+            gx = px0[t][:, None, None] + ox[None]                     # [n,K,K] pixel coordinates
+            gy = py0[t][:, None, None] + oy[None]
+            inb = (gx <= px1[t][:, None, None]) & (gy <= py1[t][:, None, None])
+            Cx = (2 * gx + 1 - W) * 8
+            Cy = (2 * gy + 1 - H) * 8
+            sgn = np.where(area2[t] > 0, 1, -1).astype(np.int64)[:, None, None]
+            inside = inb
+            for a, c in ((1, 2), (2, 0), (0, 1)):
+                ax, ay = X3[t, a][:, None, None], Y3[t, a][:, None, None]
+                dx = sgn * (X3[t, c][:, None, None] - ax)
+                dy = sgn * (Y3[t, c][:, None, None] - ay)
+                E = dx * (Cy - ay) - dy * (Cx - ax)
+                tl = (dy < 0) | ((dy == 0) & (dx < 0))
+                inside = inside & np.where(tl, E >= 0, E > 0)
+            if not inside.any():
+                continue
+            z0, z1, z2 = Z3[t, 0], Z3[t, 1], Z3[t, 2]
+            f1x, f1y, f2x, f2y = d1x[t].astype(F32), d1y[t].astype(F32), d2x[t].astype(F32), d2y[t].astype(F32)
+            dz1, dz2 = (z1 - z0).astype(F32), (z2 - z0).astype(F32)
+            af = area2[t].astype(F32)
+            with np.errstate(all="ignore"):
+                zx = ((dz1 * f2y).astype(F32) - (dz2 * f1y).astype(F32)).astype(F32) / af
+                zy = ((dz2 * f1x).astype(F32) - (dz1 * f2x).astype(F32)).astype(F32) / af
+                zc = ((z0 - (zx * X3[t, 0].astype(F32)).astype(F32)).astype(F32) - (zy * Y3[t, 0].astype(F32)).astype(F32)).astype(F32)
+                zp = ((zx[:, None, None] * Cx.astype(F32)) + (zy[:, None, None] * Cy.astype(F32))) + zc[:, None, None]
+            assert zp.dtype == F32 and zx.dtype == F32 and zc.dtype == F32
+            ok = inside & (zp >= F32(-1)) & (zp <= F32(1))
+            n_i, y_i, x_i = np.nonzero(ok)
+            if len(n_i) == 0:
+                continue
+            zz = zp[n_i, y_i, x_i]
+            pix = gy[n_i, y_i, x_i] * W + gx[n_i, y_i, x_i]
+            k = (_order_key(np.where(zz == 0, F32(0), zz)).astype(np.uint64) << np.uint64(32)) | (t[n_i] + 1).astype(np.uint64)
+            np.minimum.at(key, pix, k)
+        hit = key != np.uint64(0xFFFFFFFFFFFFFFFF)
+        idb = (key & np.uint64(0xFFFFFFFF)).astype(np.int64)
+        ub = (key >> np.uint64(32)).astype(np.uint32)
+        zb_bits = np.where(ub & np.uint32(0x80000000), ub & np.uint32(0x7FFFFFFF), ~ub)
+        zflat[hit] = zb_bits.view(F32)[hit]
+        ids[b] = np.where(hit, idb, 0).astype(np.int32).reshape(H, W)
+        zbuf[b] = zflat.reshape(H, W)
+        big = keep & ~small
+        if big.any():                                                  # merged in ascending index order with the same comparison
+            sub = np.nonzero(big)[0]
+            ids_l, z_l = rasterize_ids_loop(clip[b:b + 1], tri[sub], H, W, cull_backface)
+            idl = np.where(ids_l[0] > 0, sub[np.maximum(ids_l[0] - 1, 0)] + 1, 0).astype(np.int32)
+            zl = z_l[0]
+            win = (idl > 0) & ((zl < zbuf[b]) | ((zl == zbuf[b]) & ((ids[b] == 0) | (idl < ids[b]))))
+            ids[b][win] = idl[win]
+            zbuf[b][win] = zl[win]
     return ids, zbuf
 
 
